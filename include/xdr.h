@@ -1,0 +1,169 @@
+/*
+ * xdr.h -- C ABI of libxdr.so: the B200 (sm_100a) hot path of cross-domain recommender training.
+ *
+ * This is the drop-in boundary for the per-batch path of RecBole-CDR
+ *     gather -> cross-domain map/transfer -> score + loss -> sparse gradient scatter-add
+ * Every entry point names the reference interface it replaces (paths relative to
+ * /root/reference/recbole_cdr/).  The reference itself is pure Python on PyTorch/ATen and has no FFI;
+ * the binding a maintainer adds is the ctypes stub in INTEGRATION.md (mirrored by
+ * recbole-cdr_b200/recbole_cdr_b200/_lib.py).
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes; no C++ or torch types cross the boundary.
+ *   - Every data pointer is a DEVICE pointer on the current CUDA device unless the name says "host".
+ *     Tables are row-major fp32 [n_rows, dim] (nn.Embedding.weight layout), contiguous, 16-byte aligned;
+ *     ids are int64 (torch.LongTensor), labels/scores/losses fp32.  dim % 4 == 0 and dim <= 256.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).  The library
+ *     never synchronises, never allocates and never touches the default stream behind the caller's back.
+ *   - The caller owns every buffer and keeps it alive until the stream work has completed.
+ *   - Return value: 0 = XDR_OK, negative = error; xdr_last_error() returns a thread-local message.
+ *   - `oob` (may be NULL): device int32 flag set to 1 by the kernel if any id is outside [0, n_rows)
+ *     (such ids are skipped: they contribute zero rows and receive no gradient).  PyTorch raises
+ *     IndexError for the same input; the Python wrapper turns the flag into that exception on request.
+ *   - `ws`: caller-provided scratch of xdr_workspace_bytes() bytes, zero-filled ONCE at allocation and
+ *     private to one stream; kernels leave it zeroed again (self-cleaning tickets).
+ *   - Loss reductions are deterministic: per-block partials are summed in a fixed order by the last
+ *     block to finish.  Gradient scatter uses fp32 vector atomics (red.global.add.v4.f32), so rows hit
+ *     by duplicate ids are exact sums in an unspecified order (reference: index_add, also order-free).
+ */
+#ifndef XDR_H_
+#define XDR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XDR_VERSION 100 /* 0.1.0 */
+
+#define XDR_OK 0
+#define XDR_ERR_INVALID (-1)     /* bad argument (null pointer, unsupported dim, negative size) */
+#define XDR_ERR_CUDA (-2)        /* a CUDA runtime call or kernel launch failed */
+#define XDR_ERR_UNSUPPORTED (-3) /* valid request that this build does not implement */
+
+typedef void* xdr_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define XDR_API __attribute__((visibility("default")))
+#else
+#define XDR_API
+#endif
+
+/* pointwise data-loss kinds for xdr_point_fwd / xdr_point_bwd */
+#define XDR_LOSS_MSE 0         /* nn.MSELoss on the raw dot score      (EMCDR-MF, emcdr.py:50,116)        */
+#define XDR_LOSS_BCE_SIGMOID 1 /* nn.BCELoss on sigmoid(dot score)     (CMF cmf.py:79,94; BiTGCF bitgcf.py:227) */
+#define XDR_LOSS_NONE 2        /* no data loss, EmbLoss term only      (BiTGCF ego-row regulariser, bitgcf.py:231-233) */
+
+/* activations for the dense-layer family */
+#define XDR_ACT_NONE 0
+#define XDR_ACT_RELU 1
+#define XDR_ACT_TANH 2
+#define XDR_ACT_SIGMOID 3
+
+/* ---- library ------------------------------------------------------------------------------------- */
+XDR_API int xdr_version(void);
+XDR_API const char* xdr_last_error(void);
+/* SM count and compute capability of the current device (host out-pointers). */
+XDR_API int xdr_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+/* Bytes of zero-initialised scratch every reducing entry point needs (constant for a given build). */
+XDR_API size_t xdr_workspace_bytes(void);
+
+/* ---- A1: embedding-row gather / gradient scatter-add ------------------------------------------------
+ * Replaces torch.nn.Embedding.__call__ (emcdr.py:99-100, conet.py:106-109, dtcdr.py:113-118, cmf.py:53-73,
+ * bitgcf.py:221-224) and its backward embedding_dense_backward (index_add into the dense grad).
+ * out[k, 0:dim] (row stride out_ld floats) = table[idx[k], :]; bit-exact copy.                          */
+XDR_API int xdr_gather_rows(const float* table, int64_t n_rows, int dim, const int64_t* idx, int64_t n_idx,
+                    float* out, int64_t out_ld, int32_t* oob, xdr_stream_t stream);
+/* dst[idx[k], :] += scale * rows[k, 0:dim]   (rows has row stride rows_ld floats).                      */
+XDR_API int xdr_scatter_add_rows(float* dst, int64_t n_rows, int dim, const int64_t* idx, int64_t n_idx,
+                         const float* rows, int64_t rows_ld, float scale, int32_t* oob, xdr_stream_t stream);
+/* out[k,:] = max(table_a[idx[k],:], table_b[idx[k],:])  -- DTCDR's element-wise max combine, dtcdr.py:113-119. */
+XDR_API int xdr_gather_max2(const float* table_a, const float* table_b, int64_t n_rows, int dim, const int64_t* idx,
+                    int64_t n_idx, float* out, int64_t out_ld, int32_t* oob, xdr_stream_t stream);
+/* backward of xdr_gather_max2 (torch.maximum: gradient to the larger operand, split 0.5/0.5 on ties).  */
+XDR_API int xdr_scatter_max2_bwd(const float* table_a, const float* table_b, int64_t n_rows, int dim, const int64_t* idx,
+                         int64_t n_idx, const float* grad_rows, int64_t grad_ld, float scale, float* dst_a,
+                         float* dst_b, int32_t* oob, xdr_stream_t stream);
+
+/* ---- A2/A3: fused gather -> dot score -> BPR (+EmbLoss) -------------------------------------------------
+ * Replaces EMCDR.calculate_source_loss / calculate_target_loss, BPR branch (emcdr.py:121-130, 144-153):
+ *   loss = -mean(log(gamma + sigmoid(s(u,i+) - s(u,i-)))) + reg_weight * (||Eu[u]||_F + ||Ei[i+]||_F) / B
+ * out8[0]=loss, [1]=BPR term, [2]=||Eu[u]||_F, [3]=||Ei[i+]||_F, [4]=EmbLoss value.
+ * pos_score/neg_score [B] are written by fwd and consumed by bwd.                                          */
+XDR_API int xdr_bpr_fwd(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
+                const int64_t* user, const int64_t* pos_item, const int64_t* neg_item, int64_t batch,
+                float gamma, float reg_weight, float* pos_score, float* neg_score, float* out8, void* ws,
+                int32_t* oob, xdr_stream_t stream);
+/* user_dst[u] += scale*g*dL/dEu[u], item_dst[i+-] likewise; g = *grad_loss (device scalar, NULL => 1).
+ * dst may be a dense gradient table (scale = 1) or the weight table itself (scale = -lr: fused SGD).       */
+XDR_API int xdr_bpr_bwd(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
+                const int64_t* user, const int64_t* pos_item, const int64_t* neg_item, int64_t batch,
+                float gamma, float reg_weight, const float* pos_score, const float* neg_score,
+                const float* out8, const float* grad_loss, float scale, float* user_dst, float* item_dst,
+                xdr_stream_t stream);
+
+/* ---- A3/A13/A16: fused gather -> dot score -> pointwise loss (+EmbLoss) ---------------------------------
+ * Replaces EMCDR MF branch (emcdr.py:111-120, 134-143), CMF per-domain term (cmf.py:75-98) and the two
+ * halves of BiTGCF.calculate_loss (bitgcf.py:221-247).  loss_kind: XDR_LOSS_*.  `label` may be NULL for
+ * XDR_LOSS_NONE.  score[B] = raw dot product (pre-sigmoid), written by fwd, read by bwd.
+ * out8 as in xdr_bpr_fwd ([1] = data-loss term).                                                          */
+XDR_API int xdr_point_fwd(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
+                  const int64_t* user, const int64_t* item, const float* label, int64_t batch, int loss_kind,
+                  float reg_weight, float* score, float* out8, void* ws, int32_t* oob, xdr_stream_t stream);
+XDR_API int xdr_point_bwd(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
+                  const int64_t* user, const int64_t* item, const float* label, int64_t batch, int loss_kind,
+                  float reg_weight, const float* score, const float* out8, const float* grad_loss, float scale,
+                  float* user_dst, float* item_dst, xdr_stream_t stream);
+
+/* ---- A4/A7/A14: dense-layer family (the mapping MLP, cross-stitch units, NeuMF towers) ------------------
+ * Y[m,n] = act( sum_k X[m,k]*W[n,k] + bias[n] + mask[m] * sum_k X2[m,k]*W2[n,k] )
+ * W, W2 are nn.Linear.weight layout [N, K] (W2 = crossparas[l].weight, conet.py:122: x_t @ weight.t()).
+ * bias, X2/W2 may be NULL.  mask[m] = (mask_ids[m] < mask_lt) when mask_ids != NULL, else 1
+ * (conet.py:113-116).  Replaces nn.Linear/torch.mm/activation in emcdr.py:86-93, conet.py:118-138,
+ * recbole MLPLayers (dtcdr.py:61-67).                                                                     */
+XDR_API int xdr_dense_fwd(const float* X, const float* W, const float* bias, const float* X2, const float* W2,
+                  const int64_t* mask_ids, int64_t mask_lt, int act, float* Y, int64_t M, int N, int K,
+                  xdr_stream_t stream);
+/* dZ = dY * act'(Y) (Y = the layer's activated output); dZ may alias dY.                                   */
+XDR_API int xdr_act_bwd(const float* Y, const float* dY, int act, float* dZ, int64_t count, xdr_stream_t stream);
+/* dX[m,k] (=|+=) mask[m] * sum_n dZ[m,n]*W[n,k];  accumulate != 0 adds into dX.                            */
+XDR_API int xdr_dense_bwd_input(const float* dZ, const float* W, const int64_t* mask_ids, int64_t mask_lt, float* dX,
+                        int64_t M, int N, int K, int accumulate, xdr_stream_t stream);
+/* dW[n,k] += sum_m mask[m]*dZ[m,n]*X[m,k];  db[n] += sum_m mask[m]*dZ[m,n] (db may be NULL).        */
+XDR_API int xdr_dense_bwd_weight(const float* dZ, const float* X, const int64_t* mask_ids, int64_t mask_lt, float* dW,
+                         float* db, int64_t M, int N, int K, xdr_stream_t stream);
+
+/* ---- A4: mapping loss tail: MSE between mapped rows and gathered target rows ------------------------------
+ * Replaces nn.MSELoss(mapping(Es[idx]), Et[idx]) in EMCDR.calculate_map_loss (emcdr.py:156-168).
+ * out8[0] = mean((Y - Et[idx])^2) over n_idx*dim elements.                                                  */
+XDR_API int xdr_mse_rows_fwd(const float* Y, const float* tgt_tab, int64_t n_rows, int dim, const int64_t* idx,
+                     int64_t n_idx, float* out8, void* ws, int32_t* oob, xdr_stream_t stream);
+/* dY = g*2*(Y - Et[idx])/(n_idx*dim);  tgt_dst[idx] += scale * (-dY)  (target embedding is NOT detached).   */
+XDR_API int xdr_mse_rows_bwd(const float* Y, const float* tgt_tab, int64_t n_rows, int dim, const int64_t* idx,
+                     int64_t n_idx, const float* grad_loss, float scale, float* dY, float* tgt_dst,
+                     xdr_stream_t stream);
+
+/* ---- A8/A15: BCE on a logit column (the sigmoid output unit + nn.BCELoss) ---------------------------------
+ * prob[m] = sigmoid(logit[m]); out8[0] = mean BCE(prob, label) with torch's log clamp at -100
+ * (conet.py:140,196-197; dtcdr.py:121-124,186-187).                                                         */
+XDR_API int xdr_bce_logit_fwd(const float* logit, const float* label, int64_t count, float* prob, float* out8, void* ws,
+                      xdr_stream_t stream);
+/* dlogit[m] = g * (p - y) / max(p*(1-p), 1e-12) * p*(1-p) / count  (BCELoss backward x sigmoid backward).   */
+XDR_API int xdr_bce_logit_bwd(const float* prob, const float* label, int64_t count, const float* grad_loss,
+                      float* dlogit, xdr_stream_t stream);
+
+/* ---- A6: EMCDR predict tail: select mapped vs. target row, then dot ------------------------------------------
+ * Replaces the torch.where + mul + sum of EMCDR.predict, OVERLAP/BOTH phase (emcdr.py:191-205):
+ *   e = (sel_ids[b] < n_overlap) ? mapped[b, :] : tgt_tab[sel_ids[b], :];   score[b] = e . other_tab[other_ids[b], :]
+ * `mapped` [batch, dim] = mapping(Es[sel_ids]) produced by xdr_gather_rows + xdr_dense_fwd.
+ * overlap_users: sel = user ids, other = target item table; overlap_items: sel = item ids, other = target user table. */
+XDR_API int xdr_select_dot(const float* mapped, const float* tgt_tab, int64_t n_sel_rows, const int64_t* sel_ids,
+                   int64_t n_overlap, const float* other_tab, int64_t n_other_rows, const int64_t* other_ids, int dim,
+                   int64_t batch, float* score, int32_t* oob, xdr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XDR_H_ */

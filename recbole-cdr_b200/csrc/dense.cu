@@ -1,0 +1,461 @@
+// dense.cu -- A4/A7/A14: the small dense layers between gather and score, fp32 on CUDA cores.
+//
+//   xdr_dense_fwd        Y  = act(X W^T + b + mask * (X2 W2^T))     EMCDR mapping (emcdr.py:86-93), CoNet cross-stitch
+//                                                                   units (conet.py:118-138), recbole MLPLayers (dtcdr.py:61-67)
+//   xdr_act_bwd          dZ = dY * act'(Y)
+//   xdr_dense_bwd_input  dX (+)= mask * (dZ W)
+//   xdr_dense_bwd_weight dW += (mask * dZ)^T X,  db += colsum(dZ)
+//
+// These are GEMMs with a long M (batch) and short N/K (8..256).  One 64x64 output tile per CTA, 4x4 register
+// micro-tile per thread, K staged through shared memory in slabs of 16.  fp32 FMA keeps the loss within the
+// 1e-4 contract without any split-precision trick; the tcgen05 path (mlp_tc.cu) takes over for the shapes where
+// the layer is large enough to be tensor-bound.
+#include "xdr_common.cuh"
+
+namespace xdr {
+
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
+constexpr int kDenseThreads = 256;
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case XDR_ACT_RELU: return v > 0.f ? v : 0.f;
+    case XDR_ACT_TANH: return tanhf(v);
+    case XDR_ACT_SIGMOID: return sigmoidf_(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ void micro_fma(float (&acc)[4][4], const float (*As)[BM + PAD], const float (*Bs)[BN + PAD],
+                                          int ty, int tx) {
+#pragma unroll
+  for (int kk = 0; kk < BK; ++kk) {
+    const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+    const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+  }
+}
+
+struct MaskCtx {
+  const int64_t* ids;
+  int64_t lt;
+};
+
+// Stage a [rows x BK] slab of a row-major matrix P[R, ld] (rows r0.., reduction columns k0..) TRANSPOSED into
+// S[kk][r]: thread t covers row t/4, columns (t%4)*4..+3.
+__device__ __forceinline__ void stage_T(float (*S)[BM + PAD], const float* __restrict__ P, int64_t R, int ld, int64_t r0,
+                                        int k0, int kmax, bool row_on) {
+  const int r = threadIdx.x >> 2, kq = (threadIdx.x & 3) * 4;
+  const int64_t row = r0 + r;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (row < R && row_on) {
+    const float* p = P + row * ld + k0 + kq;
+    if (k0 + kq + 3 < kmax && ((ld & 3) == 0) && aligned16_dev(P)) {
+      const float4 q = *reinterpret_cast<const float4*>(p);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (k0 + kq + i < kmax) v[i] = p[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) S[kq + i][r] = v[i];
+}
+
+// Stage a [BK x cols] slab of a row-major matrix P[R, ld] (reduction rows k0.., columns c0..) as S[kk][c]:
+// thread t covers row t/16, columns (t%16)*4..+3.
+__device__ __forceinline__ void stage_N(float (*S)[BN + PAD], const float* __restrict__ P, int64_t R, int ld, int64_t k0,
+                                        int c0, int cmax, const MaskCtx* mc) {
+  const int kk = threadIdx.x >> 4, cq = (threadIdx.x & 15) * 4;
+  const int64_t row = k0 + kk;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (row < R && (mc == nullptr || mc->ids == nullptr || mc->ids[row] < mc->lt)) {
+    const float* p = P + row * ld + c0 + cq;
+    if (c0 + cq + 3 < cmax && ((ld & 3) == 0) && aligned16_dev(P)) {
+      const float4 q = *reinterpret_cast<const float4*>(p);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (c0 + cq + i < cmax) v[i] = p[i];
+    }
+  }
+  *reinterpret_cast<float4*>(&S[kk][cq]) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+
+// ---- forward: Y[M,N] = act(X[M,K] W[N,K]^T + b + mask * X2[M,K] W2[N,K]^T) -------------------------------
+__global__ void __launch_bounds__(kDenseThreads)
+    dense_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
+                     const float* __restrict__ X2, const float* __restrict__ W2, const int64_t* __restrict__ mask_ids,
+                     int64_t mask_lt, int act, float* __restrict__ Y, int64_t M, int N, int K) {
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  float acc[4][4] = {}, acc2[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    stage_T(As, X, M, K, m0, k0, K, true);
+    stage_T(Bs, W, N, K, n0, k0, K, true);
+    __syncthreads();
+    micro_fma(acc, As, Bs, ty, tx);
+    __syncthreads();
+  }
+  if (X2 != nullptr) {
+    for (int k0 = 0; k0 < K; k0 += BK) {
+      stage_T(As, X2, M, K, m0, k0, K, true);
+      stage_T(Bs, W2, N, K, n0, k0, K, true);
+      __syncthreads();
+      micro_fma(acc2, As, Bs, ty, tx);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const float mk = (X2 != nullptr && (mask_ids == nullptr || mask_ids[m] < mask_lt)) ? 1.f : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (X2 != nullptr) v += mk * acc2[i][j];
+      Y[m * N + n] = apply_act(v, act);
+    }
+  }
+}
+
+// ---- backward wrt input: dX[M,K] (+)= mask * dZ[M,N] W[N,K] -----------------------------------------------
+__global__ void __launch_bounds__(kDenseThreads)
+    dense_bwd_input_kernel(const float* __restrict__ dZ, const float* __restrict__ W, const int64_t* __restrict__ mask_ids,
+                           int64_t mask_lt, float* __restrict__ dX, int64_t M, int N, int K, int accumulate) {
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int c0 = blockIdx.y * BN;  // output column (k) tile
+  float acc[4][4] = {};
+  for (int n0 = 0; n0 < N; n0 += BK) {
+    stage_T(As, dZ, M, N, m0, n0, N, true);
+    stage_N(Bs, W, N, K, n0, c0, K, nullptr);
+    __syncthreads();
+    micro_fma(acc, As, Bs, ty, tx);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const float mk = (mask_ids == nullptr || mask_ids[m] < mask_lt) ? 1.f : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = c0 + tx * 4 + j;
+      if (k >= K) continue;
+      const float v = mk * acc[i][j];
+      if (accumulate) dX[m * K + k] += v; else dX[m * K + k] = v;
+    }
+  }
+}
+
+// ---- backward wrt weight: dW[N,K] += (mask*dZ)[M,N]^T X[M,K]; db[N] += colsum(dZ) -------------------------------
+// grid = (N tiles, K tiles, M chunks); each CTA reduces kChunkM rows and adds its tile with fp32 atomics.
+constexpr int kChunkM = 1024;
+__global__ void __launch_bounds__(kDenseThreads)
+    dense_bwd_weight_kernel(const float* __restrict__ dZ, const float* __restrict__ X, const int64_t* __restrict__ mask_ids,
+                            int64_t mask_lt, float* __restrict__ dW, float* __restrict__ db, int64_t M, int N, int K) {
+  __shared__ __align__(16) float As[BK][BM + PAD];  // [m][n] slab of dZ
+  __shared__ __align__(16) float Bs[BK][BN + PAD];  // [m][k] slab of X
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int n0 = blockIdx.x * BM;
+  const int c0 = blockIdx.y * BN;
+  const int64_t mbeg = (int64_t)blockIdx.z * kChunkM;
+  const int64_t mend = (mbeg + kChunkM < M) ? mbeg + kChunkM : M;
+  MaskCtx mc{mask_ids, mask_lt};
+  float acc[4][4] = {};
+  float bsum = 0.f;  // threads 0..63 of CTAs with blockIdx.y == 0 own db[n0 + threadIdx.x]
+  for (int64_t m0 = mbeg; m0 < mend; m0 += BK) {
+    stage_N(As, dZ, mend, N, m0, n0, N, &mc);
+    stage_N(Bs, X, mend, K, m0, c0, K, nullptr);
+    __syncthreads();
+    micro_fma(acc, As, Bs, ty, tx);
+    if (db != nullptr && blockIdx.y == 0 && threadIdx.x < BM) {
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) bsum += As[kk][threadIdx.x];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = c0 + tx * 4 + j;
+      if (k < K) atomicAdd(&dW[(int64_t)n * K + k], acc[i][j]);
+    }
+  }
+  if (db != nullptr && blockIdx.y == 0 && threadIdx.x < BM && n0 + (int)threadIdx.x < N)
+    atomicAdd(&db[n0 + threadIdx.x], bsum);
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ dY, int act, float* __restrict__ dZ,
+                               int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float y = Y[i], g = dY[i];
+    float d;
+    switch (act) {
+      case XDR_ACT_RELU: d = y > 0.f ? g : 0.f; break;
+      case XDR_ACT_TANH: d = g * (1.f - y * y); break;
+      case XDR_ACT_SIGMOID: d = g * (1.f - y) * y; break;
+      default: d = g; break;
+    }
+    dZ[i] = d;
+  }
+}
+
+// ---- MSE between dense rows Y[k,:] and gathered target rows T[idx[k],:] ----------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) mse_rows_fwd_kernel(const float* __restrict__ Y, const float* __restrict__ T,
+                                                           int64_t n_rows, int nv, const int64_t* __restrict__ idx,
+                                                           int64_t n_idx, float* out8, Workspace ws, int32_t* oob) {
+  __shared__ float smem[8];
+  const int sub = threadIdx.x & (kLanesPerRow - 1);
+  const int64_t group = ((int64_t)blockIdx.x * 256 + threadIdx.x) / kLanesPerRow;
+  const int64_t n_groups = (int64_t)gridDim.x * 256 / kLanesPerRow;
+  float acc[1] = {0.f};
+  for (int64_t k = group; k < n_idx; k += n_groups) {
+    const int64_t r = idx[k];
+    const bool ok = (uint64_t)r < (uint64_t)n_rows;
+    if (!ok && oob && sub == 0) *oob = 1;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c = sub + j * kLanesPerRow;
+      if (c >= nv) continue;
+      const float4 y = ldg_row4(Y + k * (int64_t)nv * 4, c);
+      const float4 t = ok ? ldg_row4(T + r * (int64_t)nv * 4, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 d = sub4(y, t);
+      acc[0] += dot4(d, d);
+    }
+  }
+  const double denom = (double)n_idx * (double)(nv * 4);
+  grid_reduce_last_block<1>(acc, ws, smem, [=](double* tot) {
+    out8[0] = (float)(tot[0] / denom);
+    for (int i = 1; i < 8; ++i) out8[i] = 0.f;
+  });
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) mse_rows_bwd_kernel(const float* __restrict__ Y, const float* T, int64_t n_rows,
+                                                           int nv, const int64_t* __restrict__ idx, int64_t n_idx,
+                                                           const float* __restrict__ grad_loss, float scale,
+                                                           float* __restrict__ dY, float* tgt_dst) {
+  const int sub = threadIdx.x & (kLanesPerRow - 1);
+  const int64_t group = ((int64_t)blockIdx.x * 256 + threadIdx.x) / kLanesPerRow;
+  const int64_t n_groups = (int64_t)gridDim.x * 256 / kLanesPerRow;
+  const float g = (grad_loss ? __ldg(grad_loss) : 1.f) * 2.f / ((float)n_idx * (float)(nv * 4));
+  for (int64_t k = group; k < n_idx; k += n_groups) {
+    const int64_t r = idx[k];
+    const bool ok = (uint64_t)r < (uint64_t)n_rows;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c = sub + j * kLanesPerRow;
+      if (c >= nv) continue;
+      const float4 y = ldg_row4(Y + k * (int64_t)nv * 4, c);
+      const float4 t = ok ? ld_row4(T + r * (int64_t)nv * 4, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 d = scale4(g, sub4(y, t));
+      st4(dY + k * (int64_t)nv * 4, c, d);
+      if (ok && tgt_dst) red_add4(tgt_dst + r * (int64_t)nv * 4, c, scale4(-scale, d));
+    }
+  }
+}
+
+// ---- BCE on a logit column ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bce_logit_fwd_kernel(const float* __restrict__ logit, const float* __restrict__ label,
+                                                            int64_t n, float* __restrict__ prob, float* out8, Workspace ws) {
+  __shared__ float smem[8];
+  float acc[1] = {0.f};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float p = sigmoidf_(logit[i]), y = label[i];
+    prob[i] = p;
+    const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
+    acc[0] += -(y * lp + (1.f - y) * lq);
+  }
+  const double denom = (double)n;
+  grid_reduce_last_block<1>(acc, ws, smem, [=](double* tot) {
+    out8[0] = (float)(tot[0] / denom);
+    for (int i = 1; i < 8; ++i) out8[i] = 0.f;
+  });
+}
+
+__global__ void bce_logit_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ label, int64_t n,
+                                     const float* __restrict__ grad_loss, float* __restrict__ dlogit) {
+  const float g = (grad_loss ? __ldg(grad_loss) : 1.f) / (float)n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float p = prob[i], y = label[i];
+    const float pq = p * (1.f - p);
+    dlogit[i] = g * (p - y) / fmaxf(pq, 1e-12f) * pq;
+  }
+}
+
+// ---- select + dot: score[b] = ((sel_ids[b] < n_overlap) ? mapped[b,:] : tgt_tab[sel_ids[b],:]) . other_tab[other_ids[b],:]
+template <int VEC>
+__global__ void __launch_bounds__(256) select_dot_kernel(const float* __restrict__ mapped, const float* __restrict__ tgt_tab,
+                                                         int64_t n_sel_rows, const int64_t* __restrict__ sel_ids,
+                                                         int64_t n_overlap, const float* __restrict__ other_tab,
+                                                         int64_t n_other_rows, const int64_t* __restrict__ other_ids,
+                                                         int nv, int64_t batch, float* __restrict__ score, int32_t* oob) {
+  const int sub = threadIdx.x & (kLanesPerRow - 1);
+  const int64_t group = ((int64_t)blockIdx.x * 256 + threadIdx.x) / kLanesPerRow;
+  const int64_t n_groups = (int64_t)gridDim.x * 256 / kLanesPerRow;
+  const int64_t warp_first = group - (group % kRowsPerWarp);
+  for (int64_t base = warp_first; base < batch; base += n_groups) {
+    const int64_t b = base + (group % kRowsPerWarp);
+    const bool live = b < batch;
+    const int64_t s = live ? sel_ids[b] : 0, o = live ? other_ids[b] : 0;
+    const bool oks = live && (uint64_t)s < (uint64_t)n_sel_rows, oko = live && (uint64_t)o < (uint64_t)n_other_rows;
+    if (live && oob && sub == 0 && (!oks || !oko)) *oob = 1;
+    const bool use_map = s < n_overlap;
+    float d = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c = sub + j * kLanesPerRow;
+      if (c >= nv || !oks || !oko) continue;
+      const float4 e = use_map ? ldg_row4(mapped + b * (int64_t)nv * 4, c) : ldg_row4(tgt_tab + s * (int64_t)nv * 4, c);
+      d += dot4(e, ldg_row4(other_tab + o * (int64_t)nv * 4, c));
+    }
+    d = group8_sum(d);
+    if (live && sub == 0) score[b] = d;
+  }
+}
+
+static inline int ew_grid(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (cap > kMaxBlocks) cap = kMaxBlocks;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace xdr
+
+using namespace xdr;
+
+extern "C" {
+
+int xdr_dense_fwd(const float* X, const float* W, const float* bias, const float* X2, const float* W2,
+                  const int64_t* mask_ids, int64_t mask_lt, int act, float* Y, int64_t M, int N, int K,
+                  xdr_stream_t stream) {
+  XDR_REQUIRE(M >= 0 && N > 0 && K > 0, "xdr_dense_fwd: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  if (M == 0) return XDR_OK;
+  XDR_REQUIRE(X && W && Y, "xdr_dense_fwd: null pointer");
+  XDR_REQUIRE((X2 == nullptr) == (W2 == nullptr), "xdr_dense_fwd: X2 and W2 must be given together");
+  XDR_REQUIRE(act >= XDR_ACT_NONE && act <= XDR_ACT_SIGMOID, "xdr_dense_fwd: bad act %d", act);
+  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+  dense_fwd_kernel<<<grid, kDenseThreads, 0, (cudaStream_t)stream>>>(X, W, bias, X2, W2, mask_ids, mask_lt, act, Y, M, N, K);
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+int xdr_act_bwd(const float* Y, const float* dY, int act, float* dZ, int64_t count, xdr_stream_t stream) {
+  XDR_REQUIRE(count >= 0, "xdr_act_bwd: negative count");
+  if (count == 0) return XDR_OK;
+  XDR_REQUIRE(Y && dY && dZ, "xdr_act_bwd: null pointer");
+  act_bwd_kernel<<<ew_grid(count, 256), 256, 0, (cudaStream_t)stream>>>(Y, dY, act, dZ, count);
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+int xdr_dense_bwd_input(const float* dZ, const float* W, const int64_t* mask_ids, int64_t mask_lt, float* dX, int64_t M,
+                        int N, int K, int accumulate, xdr_stream_t stream) {
+  XDR_REQUIRE(M >= 0 && N > 0 && K > 0, "xdr_dense_bwd_input: bad shape");
+  if (M == 0) return XDR_OK;
+  XDR_REQUIRE(dZ && W && dX, "xdr_dense_bwd_input: null pointer");
+  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((K + BN - 1) / BN));
+  dense_bwd_input_kernel<<<grid, kDenseThreads, 0, (cudaStream_t)stream>>>(dZ, W, mask_ids, mask_lt, dX, M, N, K, accumulate);
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+int xdr_dense_bwd_weight(const float* dZ, const float* X, const int64_t* mask_ids, int64_t mask_lt, float* dW, float* db,
+                         int64_t M, int N, int K, xdr_stream_t stream) {
+  XDR_REQUIRE(M >= 0 && N > 0 && K > 0, "xdr_dense_bwd_weight: bad shape");
+  if (M == 0) return XDR_OK;
+  XDR_REQUIRE(dZ && X && dW, "xdr_dense_bwd_weight: null pointer");
+  dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)((K + BN - 1) / BN), (unsigned)((M + kChunkM - 1) / kChunkM));
+  dense_bwd_weight_kernel<<<grid, kDenseThreads, 0, (cudaStream_t)stream>>>(dZ, X, mask_ids, mask_lt, dW, db, M, N, K);
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+int xdr_mse_rows_fwd(const float* Y, const float* tgt_tab, int64_t n_rows, int dim, const int64_t* idx, int64_t n_idx,
+                     float* out8, void* ws, int32_t* oob, xdr_stream_t stream) {
+  XDR_REQUIRE(dim_ok(dim), "xdr_mse_rows_fwd: dim=%d must be a multiple of 4 in (0, 256]", dim);
+  XDR_REQUIRE(n_idx > 0, "xdr_mse_rows_fwd: n_idx must be positive");
+  XDR_REQUIRE(Y && tgt_tab && idx && out8 && ws, "xdr_mse_rows_fwd: null pointer");
+  XDR_REQUIRE(aligned16(Y) && aligned16(tgt_tab), "xdr_mse_rows_fwd: 16-byte alignment");
+  const int nv = dim / 4;
+  const int grid = ew_grid(n_idx * kLanesPerRow, 256);
+  XDR_DISPATCH_VEC(nv, (mse_rows_fwd_kernel<VEC><<<grid, 256, 0, (cudaStream_t)stream>>>(Y, tgt_tab, n_rows, nv, idx, n_idx,
+                                                                                         out8, Workspace(ws), oob)));
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+int xdr_mse_rows_bwd(const float* Y, const float* tgt_tab, int64_t n_rows, int dim, const int64_t* idx, int64_t n_idx,
+                     const float* grad_loss, float scale, float* dY, float* tgt_dst, xdr_stream_t stream) {
+  XDR_REQUIRE(dim_ok(dim), "xdr_mse_rows_bwd: dim=%d must be a multiple of 4 in (0, 256]", dim);
+  XDR_REQUIRE(n_idx > 0, "xdr_mse_rows_bwd: n_idx must be positive");
+  XDR_REQUIRE(Y && tgt_tab && idx && dY, "xdr_mse_rows_bwd: null pointer");
+  XDR_REQUIRE(aligned16(Y) && aligned16(tgt_tab) && aligned16(dY) && aligned16(tgt_dst), "xdr_mse_rows_bwd: alignment");
+  const int nv = dim / 4;
+  const int grid = ew_grid(n_idx * kLanesPerRow, 256);
+  XDR_DISPATCH_VEC(nv, (mse_rows_bwd_kernel<VEC><<<grid, 256, 0, (cudaStream_t)stream>>>(Y, tgt_tab, n_rows, nv, idx, n_idx,
+                                                                                         grad_loss, scale, dY, tgt_dst)));
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+int xdr_bce_logit_fwd(const float* logit, const float* label, int64_t count, float* prob, float* out8, void* ws,
+                      xdr_stream_t stream) {
+  XDR_REQUIRE(count > 0, "xdr_bce_logit_fwd: count must be positive");
+  XDR_REQUIRE(logit && label && prob && out8 && ws, "xdr_bce_logit_fwd: null pointer");
+  bce_logit_fwd_kernel<<<ew_grid(count, 256), 256, 0, (cudaStream_t)stream>>>(logit, label, count, prob, out8, Workspace(ws));
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+int xdr_bce_logit_bwd(const float* prob, const float* label, int64_t count, const float* grad_loss, float* dlogit,
+                      xdr_stream_t stream) {
+  XDR_REQUIRE(count > 0, "xdr_bce_logit_bwd: count must be positive");
+  XDR_REQUIRE(prob && label && dlogit, "xdr_bce_logit_bwd: null pointer");
+  bce_logit_bwd_kernel<<<ew_grid(count, 256), 256, 0, (cudaStream_t)stream>>>(prob, label, count, grad_loss, dlogit);
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+int xdr_select_dot(const float* mapped, const float* tgt_tab, int64_t n_sel_rows, const int64_t* sel_ids,
+                   int64_t n_overlap, const float* other_tab, int64_t n_other_rows, const int64_t* other_ids, int dim,
+                   int64_t batch, float* score, int32_t* oob, xdr_stream_t stream) {
+  XDR_REQUIRE(dim_ok(dim), "xdr_select_dot: dim=%d must be a multiple of 4 in (0, 256]", dim);
+  XDR_REQUIRE(batch >= 0, "xdr_select_dot: negative batch");
+  if (batch == 0) return XDR_OK;
+  XDR_REQUIRE(mapped && tgt_tab && sel_ids && other_tab && other_ids && score, "xdr_select_dot: null pointer");
+  XDR_REQUIRE(aligned16(mapped) && aligned16(tgt_tab) && aligned16(other_tab), "xdr_select_dot: 16-byte alignment");
+  const int nv = dim / 4;
+  const int grid = ew_grid(batch * kLanesPerRow, 256);
+  XDR_DISPATCH_VEC(nv, (select_dot_kernel<VEC><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                           mapped, tgt_tab, n_sel_rows, sel_ids, n_overlap, other_tab, n_other_rows, other_ids, nv, batch,
+                           score, oob)));
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+// xdr_common.cuh -- device/host helpers shared by every kernel file of libxdr (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/xdr.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libxdr is written for sm_100a (B200) only"
+#endif
+
+namespace xdr {
+
+// ---------------------------------------------------------------------------------------------------
+// host side: error reporting
+// ---------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);  // defined in xdr_api.cu (thread-local buffer)
+
+#define XDR_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      xdr::set_error(__VA_ARGS__);        \
+      return XDR_ERR_INVALID;             \
+    }                                     \
+  } while (0)
+
+#define XDR_CUDA_OK(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      xdr::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      return XDR_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+#define XDR_LAUNCH_OK() XDR_CUDA_OK(cudaGetLastError())
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool dim_ok(int dim) { return dim > 0 && dim <= 256 && (dim % 4) == 0; }
+
+int sm_count();  // cached per process, defined in xdr_api.cu
+
+// ---------------------------------------------------------------------------------------------------
+// workspace layout (xdr_workspace_bytes()): [0,64) tickets (uint32), then fp32 partial slots
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxBlocks = 2048;       // upper bound on gridDim.x of any reducing kernel
+constexpr int kPartialsPerBlock = 4;   // fp32 slots per block
+constexpr size_t kWsTicketBytes = 64;
+constexpr size_t kWsBytes = kWsTicketBytes + sizeof(float) * kPartialsPerBlock * kMaxBlocks;
+
+struct Workspace {
+  unsigned int* ticket;
+  float* partials;
+  __host__ __device__ explicit Workspace(void* ws)
+      : ticket(reinterpret_cast<unsigned int*>(ws)),
+        partials(reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kWsTicketBytes)) {}
+};
+
+// ---------------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Row geometry: a row of `dim` floats is nv = dim/4 float4s.  An interaction (or row) is owned by a group of
+// 8 consecutive lanes; lane `sub` of the group owns float4 columns sub, sub+8, ... (VEC of them).  One 8-lane
+// slice of a row is one full 128-byte line, so every LDG.128 / RED.128 of a group is a single-line request.
+constexpr int kLanesPerRow = 8;
+constexpr int kRowsPerWarp = 32 / kLanesPerRow;
+
+// 128-bit read-only gather that does not allocate in L1 (rows are touched once per kernel).
+__device__ __forceinline__ float4 ldg_row4(const float* __restrict__ row, int col4) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(reinterpret_cast<const float4*>(row) + col4));
+  return v;
+}
+
+// 128-bit coherent load (tables that may be written by a concurrent scatter in the same launch).
+__device__ __forceinline__ float4 ld_row4(const float* row, int col4) {
+  return *(reinterpret_cast<const float4*>(row) + col4);
+}
+
+// fp32 x4 reduction to global memory: REDG.E.ADD.F32x4 on sm_100a.
+__device__ __forceinline__ void red_add4(float* row, int col4, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<float4*>(row) + col4), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ void st4(float* row, int col4, float4 v) {
+  *(reinterpret_cast<float4*>(row) + col4) = v;
+}
+
+__device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float4 axpy4(float a, float4 x, float4 y) {
+  return make_float4(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y), fmaf(a, x.z, y.z), fmaf(a, x.w, y.w));
+}
+__device__ __forceinline__ float4 scale4(float a, float4 x) { return make_float4(a * x.x, a * x.y, a * x.z, a * x.w); }
+__device__ __forceinline__ float4 sub4(float4 a, float4 b) {
+  return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+}
+
+// sum over the 8 lanes of a row group (all 32 lanes must participate)
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// torch.sigmoid in fp32: 1 / (1 + exp(-x)) with the accurate expf
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Block-level sum of NV values per thread -> thread 0 of the block holds the result in v[].
+// smem: at least NV * (blockDim.x / 32) floats.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) smem[i * nwarp + warp] = v[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float x = lane < nwarp ? smem[i * nwarp + lane] : 0.f;
+      v[i] = warp_sum(x);
+    }
+  }
+  __syncthreads();
+}
+
+// Deterministic grid reduction: every block publishes NV partials; the last block to arrive (ticket) sums all
+// gridDim.x partial sets in a fixed order in fp64 and calls `fin(double sums[NV])` from its thread 0, then resets
+// the ticket so the workspace is clean for the next launch on the same stream.
+template <int NV, typename Fin>
+__device__ __forceinline__ void grid_reduce_last_block(float (&v)[NV], Workspace ws, float* smem, Fin fin) {
+  static_assert(NV <= kPartialsPerBlock, "too many partials");
+  __shared__ bool is_last;
+  block_sum<NV>(v, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ws.partials[(size_t)blockIdx.x * kPartialsPerBlock + i] = v[i];
+    __threadfence();
+    unsigned int t = atomicAdd(ws.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] += (double)__ldcg(&ws.partials[(size_t)b * kPartialsPerBlock + i]);
+  }
+  // block reduce in fp64 (fixed order: lane tree, then warps in index order)
+  __shared__ double dsm[NV][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    acc[i] = warp_sum(acc[i]);
+    if (lane == 0) dsm[i][warp] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      tot[i] = 0.0;
+      for (int w = 0; w < nwarp; ++w) tot[i] += dsm[i][w];
+    }
+    fin(tot);
+    *ws.ticket = 0u;
+  }
+}
+
+#endif  // __CUDACC__
+
+// Instantiate CALL with `constexpr int VEC` = float4 columns per lane for a row of nv float4s (8 lanes per row).
+#define XDR_DISPATCH_VEC(nv, CALL)                                   \
+  do {                                                               \
+    const int vec__ = ((nv) + xdr::kLanesPerRow - 1) / xdr::kLanesPerRow;      \
+    switch (vec__) {                                                 \
+      case 1: { constexpr int VEC = 1; CALL; } break;                \
+      case 2: { constexpr int VEC = 2; CALL; } break;                \
+      case 3: { constexpr int VEC = 3; CALL; } break;                \
+      case 4: { constexpr int VEC = 4; CALL; } break;                \
+      case 5: case 6: { constexpr int VEC = 6; CALL; } break;        \
+      default: { constexpr int VEC = 8; CALL; } break;               \
+    }                                                                \
+  } while (0)
+
+}  // namespace xdr

@@ -1,0 +1,129 @@
+"""ctypes binding of libxdr.so -- the only door between Python and the CUDA hot path.
+
+Mirrors ``include/xdr.h`` one to one (same names, same argument order).  Importing this module never needs a
+GPU; *calling* any compute entry point does.  If the shared library is missing the import fails loudly -- there
+is no Python/PyTorch fallback for the hot path by design.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get('XDR_LIB', os.path.join(_HERE, 'lib', 'libxdr.so'))
+
+c_i64, c_int, c_f32, c_vp, c_sz = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes); argument order is exactly that of include/xdr.h
+PROTOTYPES = {
+    'xdr_version': (c_int, []),
+    'xdr_last_error': (ctypes.c_char_p, []),
+    'xdr_device_info': (c_int, [ctypes.POINTER(c_int)] * 3),
+    'xdr_workspace_bytes': (c_sz, []),
+    'xdr_gather_rows': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    'xdr_scatter_add_rows': (c_int, [c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_vp]),
+    'xdr_gather_max2': (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    'xdr_scatter_max2_bwd': (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    'xdr_bpr_fwd': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_vp,
+                            c_vp, c_vp, c_vp]),
+    'xdr_bpr_bwd': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_vp,
+                            c_vp, c_f32, c_vp, c_vp, c_vp]),
+    'xdr_point_fwd': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_vp, c_vp,
+                              c_vp, c_vp]),
+    'xdr_point_bwd': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_vp, c_vp,
+                              c_f32, c_vp, c_vp, c_vp]),
+    'xdr_dense_fwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_vp]),
+    'xdr_act_bwd': (c_int, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
+    'xdr_dense_bwd_input': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
+    'xdr_dense_bwd_weight': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
+    'xdr_mse_rows_fwd': (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    'xdr_mse_rows_bwd': (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_f32, c_vp, c_vp, c_vp]),
+    'xdr_bce_logit_fwd': (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    'xdr_bce_logit_bwd': (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    'xdr_select_dot': (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
+}
+
+LOSS_MSE, LOSS_BCE_SIGMOID, LOSS_NONE = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+ACT_BY_NAME = {None: ACT_NONE, 'none': ACT_NONE, 'relu': ACT_RELU, 'tanh': ACT_TANH, 'sigmoid': ACT_SIGMOID}
+
+
+class XdrError(RuntimeError):
+    """Non-zero status from libxdr (the reference signals errors with Python exceptions; so do we)."""
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f'libxdr.so not found at {LIB_PATH}: build it with `python recbole-cdr_b200/build.py` '
+            '(needs nvcc; no GPU required). There is no CPU/PyTorch fallback for the hot path.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = _load()
+
+
+def last_error() -> str:
+    return _lib.xdr_last_error().decode()
+
+
+def version() -> int:
+    return _lib.xdr_version()
+
+
+def workspace_bytes() -> int:
+    return _lib.xdr_workspace_bytes()
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point and raise XdrError(xdr_last_error()) on failure."""
+    rc = getattr(_lib, name)(*args)
+    if rc != 0:
+        raise XdrError(f'{name} failed (status {rc}): {last_error()}')
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def cur_stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+_workspaces = {}
+
+
+def workspace(device: torch.device) -> torch.Tensor:
+    """Zero-initialised scratch private to (device, current stream); kernels leave it clean (xdr.h `ws`)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), cur_stream())
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(workspace_bytes(), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+_oob_flags = {}
+
+
+def oob_flag(device: torch.device) -> torch.Tensor:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    f = _oob_flags.get(key)
+    if f is None:
+        f = torch.zeros(1, dtype=torch.int32, device=device)
+        _oob_flags[key] = f
+    return f
+
+
+def check_ids(device: torch.device):
+    """Synchronising check of the out-of-range flag; raises IndexError like nn.Embedding does on CPU."""
+    f = oob_flag(device)
+    if int(f.item()) != 0:
+        f.zero_()
+        raise IndexError('index out of range in self')

@@ -1,0 +1,433 @@
+"""Autograd-visible operators over libxdr (PyTorch tensors in, PyTorch tensors out).
+
+Each ``torch.autograd.Function`` here is the fused replacement of a short chain of ATen ops on the reference's hot
+path; the docstring of each names the reference lines.  Forward and backward both run hand-written CUDA through the
+C ABI (``_lib.call``); PyTorch only allocates the output tensors and supplies the stream.
+
+Table gradients come in two modes (``set_table_grad_mode``):
+
+* ``'autograd'`` (default, exact drop-in): backward returns a dense ``[N, D]`` gradient per table -- zero-filled, then
+  scatter-added by the kernel -- exactly what ``embedding_dense_backward`` produces in the reference, so any
+  ``torch.optim`` optimizer and ``torch.autograd.grad`` work unchanged.
+* ``'inplace'``: backward scatter-adds straight into ``table.grad`` (allocated on first use) and returns ``None`` for
+  the table, skipping one dense zero-fill and one dense add per use of a table.  ``loss.backward()`` leaves the same
+  ``.grad`` contents; ``torch.autograd.grad`` does not see table gradients in this mode.
+"""
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import call, cur_stream, ptr
+
+_TABLE_GRAD_MODE = 'autograd'
+CHECK_IDS = False  # set True (or env XDR_CHECK_IDS=1) to raise IndexError on out-of-range ids (adds a sync per op)
+
+import os as _os
+
+if _os.environ.get('XDR_CHECK_IDS', '0') == '1':
+    CHECK_IDS = True
+
+
+def set_table_grad_mode(mode: str):
+    global _TABLE_GRAD_MODE
+    if mode not in ('autograd', 'inplace'):
+        raise ValueError("table grad mode must be 'autograd' or 'inplace'")
+    _TABLE_GRAD_MODE = mode
+
+
+def get_table_grad_mode() -> str:
+    return _TABLE_GRAD_MODE
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor: the xdr hot path has no CPU implementation')
+    if t.dtype != torch.float32:
+        raise TypeError(f'{name} must be float32, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name} must be contiguous')
+
+
+def _ids(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor')
+    if t.dtype != torch.int64:
+        raise TypeError(f'{name} must be int64 (torch.LongTensor), got {t.dtype}')
+    return t.contiguous()
+
+
+def _grad_dst(table: torch.Tensor):
+    """Destination for a table gradient in the current mode -> (dst tensor, value to return from backward)."""
+    if _TABLE_GRAD_MODE == 'inplace' and table.is_leaf:
+        if table.grad is None:
+            table.grad = torch.zeros_like(table)
+        return table.grad, None
+    g = torch.zeros_like(table)
+    return g, g
+
+
+def _maybe_check(device):
+    if CHECK_IDS:
+        _lib.check_ids(device)
+
+
+def _oob(device):
+    return ptr(_lib.oob_flag(device)) if CHECK_IDS else None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# A1: gather / scatter-add
+# ------------------------------------------------------------------------------------------------------------------
+
+def gather_rows_raw(table: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None, col: int = 0):
+    """out[:, col:col+D] = table[idx] (bit-exact); ``out`` may be a wider [n, ld] buffer (the concat target)."""
+    _require_cuda_f32(table, 'table')
+    idx = _ids(idx, 'idx').reshape(-1)
+    n, d = idx.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=table.device)
+    ld = out.stride(0) if n > 0 else max(out.shape[1], d)
+    view = out[:, col:col + d]
+    call('xdr_gather_rows', ptr(table), table.shape[0], d, ptr(idx), n, view.data_ptr() if n else None, ld,
+         _oob(table.device), cur_stream())
+    _maybe_check(table.device)
+    return out
+
+
+def scatter_add_rows_raw(dst: torch.Tensor, idx: torch.Tensor, rows: torch.Tensor, scale: float = 1.0, col: int = 0):
+    """dst[idx] += scale * rows[:, col:col+D]."""
+    _require_cuda_f32(dst, 'dst')
+    idx = _ids(idx, 'idx').reshape(-1)
+    n, d = idx.numel(), dst.shape[1]
+    if n == 0:
+        return dst
+    view = rows[:, col:col + d]
+    call('xdr_scatter_add_rows', ptr(dst), dst.shape[0], d, ptr(idx), n, view.data_ptr(), rows.stride(0), float(scale),
+         _oob(dst.device), cur_stream())
+    return dst
+
+
+class GatherRows(torch.autograd.Function):
+    """``table[idx]`` == ``nn.Embedding.__call__`` (emcdr.py:99-100, conet.py:106-109, bitgcf.py:221-224);
+    backward == ``embedding_dense_backward`` as a vector-atomic scatter-add."""
+
+    @staticmethod
+    def forward(ctx, table, idx):
+        out = gather_rows_raw(table, idx)
+        ctx.save_for_backward(table, idx)
+        return out.view(*idx.shape, table.shape[1])
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        table, idx = ctx.saved_tensors
+        go = grad_out.reshape(-1, table.shape[1]).contiguous()
+        dst, ret = _grad_dst(table)
+        scatter_add_rows_raw(dst, idx, go)
+        return ret, None
+
+
+def gather_rows(table, idx):
+    return GatherRows.apply(table, idx)
+
+
+class GatherConcat(torch.autograd.Function):
+    """``torch.cat([user_tab[user], item_tab[item]], dim=1)`` written in one pass per table straight into the
+    concatenated buffer (conet.py:106-111)."""
+
+    @staticmethod
+    def forward(ctx, user_tab, item_tab, user, item):
+        n, d = user.numel(), user_tab.shape[1]
+        out = torch.empty((n, 2 * d), dtype=torch.float32, device=user_tab.device)
+        gather_rows_raw(user_tab, user, out, 0)
+        gather_rows_raw(item_tab, item, out, d)
+        ctx.save_for_backward(user_tab, item_tab, user, item)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        user_tab, item_tab, user, item = ctx.saved_tensors
+        go = grad_out.contiguous()
+        d = user_tab.shape[1]
+        du, ru = _grad_dst(user_tab)
+        scatter_add_rows_raw(du, user, go, 1.0, 0)
+        di, ri = _grad_dst(item_tab)
+        scatter_add_rows_raw(di, item, go, 1.0, d)
+        return ru, ri, None, None
+
+
+class GatherMax2Concat(torch.autograd.Function):
+    """DTCDR.neumf_forward input: ``cat(max(Es_u[u], Et_u[u]), max(Es_i[i], Et_i[i]))`` (dtcdr.py:113-121)."""
+
+    @staticmethod
+    def forward(ctx, su_tab, tu_tab, si_tab, ti_tab, user, item):
+        user, item = _ids(user, 'user'), _ids(item, 'item')
+        n, d = user.numel(), su_tab.shape[1]
+        for t, nm in ((su_tab, 'source_user'), (tu_tab, 'target_user'), (si_tab, 'source_item'), (ti_tab, 'target_item')):
+            _require_cuda_f32(t, nm)
+        out = torch.empty((n, 2 * d), dtype=torch.float32, device=su_tab.device)
+        s = cur_stream()
+        call('xdr_gather_max2', ptr(su_tab), ptr(tu_tab), su_tab.shape[0], d, ptr(user), n, out.data_ptr(), 2 * d,
+             _oob(out.device), s)
+        call('xdr_gather_max2', ptr(si_tab), ptr(ti_tab), si_tab.shape[0], d, ptr(item), n, out[:, d:].data_ptr(), 2 * d,
+             _oob(out.device), s)
+        _maybe_check(out.device)
+        ctx.save_for_backward(su_tab, tu_tab, si_tab, ti_tab, user, item)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        su_tab, tu_tab, si_tab, ti_tab, user, item = ctx.saved_tensors
+        go = grad_out.contiguous()
+        n, d = user.numel(), su_tab.shape[1]
+        s = cur_stream()
+        dsu, rsu = _grad_dst(su_tab)
+        dtu, rtu = _grad_dst(tu_tab)
+        dsi, rsi = _grad_dst(si_tab)
+        dti, rti = _grad_dst(ti_tab)
+        call('xdr_scatter_max2_bwd', ptr(su_tab), ptr(tu_tab), su_tab.shape[0], d, ptr(user), n, go.data_ptr(), 2 * d, 1.0,
+             ptr(dsu), ptr(dtu), None, s)
+        call('xdr_scatter_max2_bwd', ptr(si_tab), ptr(ti_tab), si_tab.shape[0], d, ptr(item), n, go[:, d:].data_ptr(), 2 * d,
+             1.0, ptr(dsi), ptr(dti), None, s)
+        return rsu, rtu, rsi, rti, None, None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# A2/A3/A13/A16: fused gather -> score -> loss
+# ------------------------------------------------------------------------------------------------------------------
+
+class BprLoss(torch.autograd.Function):
+    """Fused ``BPRLoss(s(u,i+), s(u,i-)) + reg_weight * EmbLoss(Eu[u], Ei[i+])`` -- EMCDR.calculate_source_loss /
+    calculate_target_loss, BPR branch (emcdr.py:121-130, 144-153).  Returns the loss with shape ``[1]`` as the
+    reference does."""
+
+    @staticmethod
+    def forward(ctx, user_tab, item_tab, user, pos_item, neg_item, gamma, reg_weight):
+        _require_cuda_f32(user_tab, 'user table')
+        _require_cuda_f32(item_tab, 'item table')
+        user, pos_item, neg_item = _ids(user, 'user'), _ids(pos_item, 'pos_item'), _ids(neg_item, 'neg_item')
+        b, d = user.numel(), user_tab.shape[1]
+        dev = user_tab.device
+        scores = torch.empty((2, b), dtype=torch.float32, device=dev)
+        out8 = torch.empty(8, dtype=torch.float32, device=dev)
+        call('xdr_bpr_fwd', ptr(user_tab), ptr(item_tab), user_tab.shape[0], item_tab.shape[0], d, ptr(user), ptr(pos_item),
+             ptr(neg_item), b, float(gamma), float(reg_weight), scores[0].data_ptr(), scores[1].data_ptr(), ptr(out8),
+             ptr(_lib.workspace(dev)), _oob(dev), cur_stream())
+        _maybe_check(dev)
+        ctx.save_for_backward(user_tab, item_tab, user, pos_item, neg_item, scores, out8)
+        ctx.gamma, ctx.reg_weight = float(gamma), float(reg_weight)
+        return out8[0:1].clone()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        user_tab, item_tab, user, pos_item, neg_item, scores, out8 = ctx.saved_tensors
+        g = grad_loss.reshape(-1)[:1].contiguous().float()
+        du, ru = _grad_dst(user_tab)
+        di, ri = _grad_dst(item_tab)
+        call('xdr_bpr_bwd', ptr(user_tab), ptr(item_tab), user_tab.shape[0], item_tab.shape[0], user_tab.shape[1], ptr(user),
+             ptr(pos_item), ptr(neg_item), user.numel(), ctx.gamma, ctx.reg_weight, scores[0].data_ptr(),
+             scores[1].data_ptr(), ptr(out8), ptr(g), 1.0, ptr(du), ptr(di), cur_stream())
+        return ru, ri, None, None, None, None, None
+
+
+def bpr_loss(user_tab, item_tab, user, pos_item, neg_item, reg_weight, gamma=1e-10):
+    return BprLoss.apply(user_tab, item_tab, user, pos_item, neg_item, gamma, reg_weight)
+
+
+class PointLoss(torch.autograd.Function):
+    """Fused ``data_loss(dot(Eu[u], Ei[i]), label) + reg_weight * EmbLoss(Eu[u], Ei[i])`` with data_loss MSE
+    (EMCDR-MF, emcdr.py:111-120), BCE(sigmoid(.)) (CMF cmf.py:75-98; BiTGCF bitgcf.py:226-228) or none (the
+    EmbLoss-only term of bitgcf.py:231-233).  Returns ``[1]``."""
+
+    @staticmethod
+    def forward(ctx, user_tab, item_tab, user, item, label, loss_kind, reg_weight):
+        _require_cuda_f32(user_tab, 'user table')
+        _require_cuda_f32(item_tab, 'item table')
+        user, item = _ids(user, 'user'), _ids(item, 'item')
+        if label is not None:
+            _require_cuda_f32(label, 'label')
+        b, d = user.numel(), user_tab.shape[1]
+        dev = user_tab.device
+        score = torch.empty(b, dtype=torch.float32, device=dev)
+        out8 = torch.empty(8, dtype=torch.float32, device=dev)
+        call('xdr_point_fwd', ptr(user_tab), ptr(item_tab), user_tab.shape[0], item_tab.shape[0], d, ptr(user), ptr(item),
+             ptr(label), b, int(loss_kind), float(reg_weight), ptr(score), ptr(out8), ptr(_lib.workspace(dev)), _oob(dev),
+             cur_stream())
+        _maybe_check(dev)
+        ctx.save_for_backward(user_tab, item_tab, user, item, label, score, out8)
+        ctx.loss_kind, ctx.reg_weight = int(loss_kind), float(reg_weight)
+        return out8[0:1].clone()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        user_tab, item_tab, user, item, label, score, out8 = ctx.saved_tensors
+        g = grad_loss.reshape(-1)[:1].contiguous().float()
+        du, ru = _grad_dst(user_tab)
+        di, ri = _grad_dst(item_tab)
+        call('xdr_point_bwd', ptr(user_tab), ptr(item_tab), user_tab.shape[0], item_tab.shape[0], user_tab.shape[1],
+             ptr(user), ptr(item), ptr(label), user.numel(), ctx.loss_kind, ctx.reg_weight, ptr(score), ptr(out8), ptr(g),
+             1.0, ptr(du), ptr(di), cur_stream())
+        return ru, ri, None, None, None, None, None
+
+
+def point_loss(user_tab, item_tab, user, item, label, loss_kind, reg_weight):
+    return PointLoss.apply(user_tab, item_tab, user, item, label, loss_kind, reg_weight)
+
+
+def dot_score(user_tab, item_tab, user, item):
+    """Inference-only ``(Eu[u] * Ei[i]).sum(1)`` (emcdr.py:98-108): the fused forward with no loss term."""
+    with torch.no_grad():
+        user, item = _ids(user, 'user'), _ids(item, 'item')
+        b, dev = user.numel(), user_tab.device
+        score = torch.empty(b, dtype=torch.float32, device=dev)
+        out8 = torch.empty(8, dtype=torch.float32, device=dev)
+        if b:
+            call('xdr_point_fwd', ptr(user_tab), ptr(item_tab), user_tab.shape[0], item_tab.shape[0], user_tab.shape[1],
+                 ptr(user), ptr(item), None, b, _lib.LOSS_NONE, 0.0, ptr(score), ptr(out8), ptr(_lib.workspace(dev)),
+                 _oob(dev), cur_stream())
+            _maybe_check(dev)
+        return score
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# A4/A7/A14: dense layers
+# ------------------------------------------------------------------------------------------------------------------
+
+class Dense(torch.autograd.Function):
+    """``act(X W^T + b + mask * (X2 W2^T))``: nn.Linear + activation (emcdr.py:86-93, recbole MLPLayers dtcdr.py:61-67)
+    and, with X2/W2/mask, one CoNet cross-stitch unit (conet.py:118-138, mask = ids < n_overlap, conet.py:113-116)."""
+
+    @staticmethod
+    def forward(ctx, X, W, bias, X2, W2, mask_ids, mask_lt, act):
+        X = X.contiguous()
+        _require_cuda_f32(X, 'X')
+        _require_cuda_f32(W, 'W')
+        M, K = X.shape
+        N = W.shape[0]
+        if W.shape[1] != K:
+            raise ValueError(f'dense: X is [*, {K}] but W is {tuple(W.shape)}')
+        if X2 is not None:
+            X2 = X2.contiguous()
+            if X2.shape != X.shape or W2.shape != W.shape:
+                raise ValueError('dense: cross operands must have the shapes of X and W')
+        Y = torch.empty((M, N), dtype=torch.float32, device=X.device)
+        call('xdr_dense_fwd', ptr(X), ptr(W), ptr(bias), ptr(X2), ptr(W2), ptr(mask_ids), int(mask_lt), int(act), ptr(Y), M,
+             N, K, cur_stream())
+        ctx.save_for_backward(X, W, bias, X2, W2, mask_ids, Y)
+        ctx.mask_lt, ctx.act = int(mask_lt), int(act)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, W, bias, X2, W2, mask_ids, Y = ctx.saved_tensors
+        M, K = X.shape
+        N = W.shape[0]
+        s = cur_stream()
+        dY = dY.contiguous()
+        dZ = torch.empty_like(dY)
+        call('xdr_act_bwd', ptr(Y), ptr(dY), ctx.act, ptr(dZ), dY.numel(), s)
+        needs = ctx.needs_input_grad
+        dX = dW = db = dX2 = dW2 = None
+        if needs[0]:
+            dX = torch.empty_like(X)
+            call('xdr_dense_bwd_input', ptr(dZ), ptr(W), None, 0, ptr(dX), M, N, K, 0, s)
+        if needs[1] or (bias is not None and needs[2]):
+            dW = torch.zeros_like(W)
+            db = torch.zeros_like(bias) if bias is not None else None
+            call('xdr_dense_bwd_weight', ptr(dZ), ptr(X), None, 0, ptr(dW), ptr(db), M, N, K, s)
+        if X2 is not None:
+            if needs[3]:
+                dX2 = torch.empty_like(X2)
+                call('xdr_dense_bwd_input', ptr(dZ), ptr(W2), ptr(mask_ids), ctx.mask_lt, ptr(dX2), M, N, K, 0, s)
+            if needs[4]:
+                dW2 = torch.zeros_like(W2)
+                call('xdr_dense_bwd_weight', ptr(dZ), ptr(X2), ptr(mask_ids), ctx.mask_lt, ptr(dW2), None, M, N, K, s)
+        return dX, dW, db, dX2, dW2, None, None, None
+
+
+def dense(X, W, bias=None, act=_lib.ACT_NONE, X2=None, W2=None, mask_ids=None, mask_lt=0):
+    return Dense.apply(X, W, bias, X2, W2, mask_ids, mask_lt, act)
+
+
+class MseRows(torch.autograd.Function):
+    """``nn.MSELoss(Y, tgt_tab[idx])`` with the target embedding NOT detached (EMCDR.calculate_map_loss,
+    emcdr.py:156-168): gradient flows to Y and, as a scatter-add, to the target table."""
+
+    @staticmethod
+    def forward(ctx, Y, tgt_tab, idx):
+        Y = Y.contiguous()
+        _require_cuda_f32(Y, 'Y')
+        _require_cuda_f32(tgt_tab, 'target table')
+        idx = _ids(idx, 'idx').reshape(-1)
+        dev = Y.device
+        out8 = torch.empty(8, dtype=torch.float32, device=dev)
+        call('xdr_mse_rows_fwd', ptr(Y), ptr(tgt_tab), tgt_tab.shape[0], tgt_tab.shape[1], ptr(idx), idx.numel(), ptr(out8),
+             ptr(_lib.workspace(dev)), _oob(dev), cur_stream())
+        _maybe_check(dev)
+        ctx.save_for_backward(Y, tgt_tab, idx)
+        return out8[0]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        Y, tgt_tab, idx = ctx.saved_tensors
+        g = grad_loss.reshape(-1)[:1].contiguous().float()
+        dY = torch.empty_like(Y)
+        dt, rt = _grad_dst(tgt_tab)
+        call('xdr_mse_rows_bwd', ptr(Y), ptr(tgt_tab), tgt_tab.shape[0], tgt_tab.shape[1], ptr(idx), idx.numel(), ptr(g), 1.0,
+             ptr(dY), ptr(dt), cur_stream())
+        return dY, rt, None
+
+
+def mse_rows(Y, tgt_tab, idx):
+    return MseRows.apply(Y, tgt_tab, idx)
+
+
+class BceLogit(torch.autograd.Function):
+    """``nn.BCELoss(sigmoid(logit), label)`` (conet.py:140,196-197; dtcdr.py:121-124,186-187); returns (loss, prob)."""
+
+    @staticmethod
+    def forward(ctx, logit, label):
+        logit = logit.contiguous().reshape(-1)
+        _require_cuda_f32(logit, 'logit')
+        _require_cuda_f32(label, 'label')
+        dev = logit.device
+        prob = torch.empty_like(logit)
+        out8 = torch.empty(8, dtype=torch.float32, device=dev)
+        call('xdr_bce_logit_fwd', ptr(logit), ptr(label), logit.numel(), ptr(prob), ptr(out8), ptr(_lib.workspace(dev)),
+             cur_stream())
+        ctx.save_for_backward(prob, label)
+        ctx.mark_non_differentiable(prob)
+        return out8[0], prob
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_prob):
+        prob, label = ctx.saved_tensors
+        g = grad_loss.reshape(-1)[:1].contiguous().float()
+        dlogit = torch.empty_like(prob)
+        call('xdr_bce_logit_bwd', ptr(prob), ptr(label), prob.numel(), ptr(g), ptr(dlogit), cur_stream())
+        return dlogit, None
+
+
+def bce_logit(logit, label):
+    return BceLogit.apply(logit, label)
+
+
+def select_dot(mapped, tgt_tab, sel_ids, n_overlap, other_tab, other_ids):
+    """EMCDR.predict tail (emcdr.py:191-205): where(id < n_overlap, mapped, Et[id]) . other[id2]; inference only."""
+    with torch.no_grad():
+        sel_ids, other_ids = _ids(sel_ids, 'sel_ids'), _ids(other_ids, 'other_ids')
+        b, dev = sel_ids.numel(), tgt_tab.device
+        score = torch.empty(b, dtype=torch.float32, device=dev)
+        call('xdr_select_dot', ptr(mapped.contiguous()), ptr(tgt_tab), tgt_tab.shape[0], ptr(sel_ids), int(n_overlap),
+             ptr(other_tab), other_tab.shape[0], ptr(other_ids), tgt_tab.shape[1], b, ptr(score), _oob(dev), cur_stream())
+        _maybe_check(dev)
+        return score
+
+
+def mlp_chain(x, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]], hidden_act: int,
+              last_act: int):
+    """Linear -> act -> ... -> Linear -> last_act, every layer through xdr_dense_fwd."""
+    n = len(weights)
+    for k in range(n):
+        x = dense(x, weights[k], biases[k], last_act if k == n - 1 else hidden_act)
+    return x

@@ -163,6 +163,25 @@ XDR_API int xdr_select_dot(const float* mapped, const float* tgt_tab, int64_t n_
                    int64_t n_overlap, const float* other_tab, int64_t n_other_rows, const int64_t* other_ids, int dim,
                    int64_t batch, float* score, int32_t* oob, xdr_stream_t stream);
 
+/* ---- A17: the trainer-step hot loop, K batches in ONE persistent software-pipelined launch ---------------------------
+ * Replaces K iterations of recbole Trainer._train_epoch's inner loop [recbole-1.0.1] (driven by
+ * CrossDomainTrainer.fit, trainer/trainer.py:59-73) around EMCDR.calculate_source_loss / calculate_target_loss
+ * (emcdr.py:110-154) or one CMF domain term (cmf.py:75-98):  for k < n_steps: loss_k = L(batch_k); backward.
+ * Batch k reads ids user[k*step_stride + 0..batch), item_a[...], item_b[...] (pairwise) / label[...] (pointwise).
+ * out8[k*8 + 0..7] as in xdr_bpr_fwd / xdr_point_fwd; per-batch losses and gradient contributions are identical to
+ * calling the fwd+bwd pair on batch k.  dst = gradient tables (scale 1): gradients of the K batches accumulate.
+ * dst = the weight tables (scale = -lr): asynchronous SGD, a batch may read rows up to 4 steps stale.
+ * Restrictions (else XDR_ERR_UNSUPPORTED: use the per-step entry points): batch % 4 == 0, step_stride % 4 == 0,
+ * id arrays 16-byte aligned, and ceil(batch / #SMs) interactions x rows must fit 4 shared-memory stages
+ * (batch <= ~8900 at dim 64 pairwise on a 148-SM part).
+ * steps_ws: xdr_steps_workspace_bytes(n_steps) bytes of scratch (no initialisation needed).                         */
+XDR_API size_t xdr_steps_workspace_bytes(int n_steps);
+XDR_API int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
+                            const int64_t* user, const int64_t* item_a, const int64_t* item_b, const float* label,
+                            int64_t step_stride, int64_t batch, int n_steps, int pairwise, int loss_kind, float gamma,
+                            float reg_weight, const float* grad_loss, float scale, float* user_dst, float* item_dst,
+                            float* out8, void* steps_ws, size_t steps_ws_bytes, int32_t* oob, xdr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

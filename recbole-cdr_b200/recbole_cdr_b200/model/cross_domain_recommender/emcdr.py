@@ -135,6 +135,22 @@ class EMCDR(CrossDomainRecommender):
         else:
             return self.calculate_target_loss(interaction)
 
+    def fused_step_spec(self):
+        """What the trainer's persistent multi-step launch needs for the current phase (SOURCE / TARGET-like phases
+        only; the OVERLAP phase has dense mapping parameters and runs batch by batch)."""
+        if self.phase == 'OVERLAP':
+            return None
+        domain = 'source' if self.phase == 'SOURCE' else 'target'
+        ut, it = self._tables(domain)
+        uid = self.SOURCE_USER_ID if domain == 'source' else self.TARGET_USER_ID
+        iid = self.SOURCE_ITEM_ID if domain == 'source' else self.TARGET_ITEM_ID
+        if self.latent_factor_model == 'MF':
+            return dict(user_tab=ut, item_tab=it, pairwise=False, loss_kind=_lib.LOSS_MSE, reg_weight=self.reg_weight,
+                        fields=[uid, iid], label_field=self.SOURCE_LABEL if domain == 'source' else self.TARGET_LABEL)
+        neg = self.SOURCE_NEG_ITEM_ID if domain == 'source' else self.TARGET_NEG_ITEM_ID
+        return dict(user_tab=ut, item_tab=it, pairwise=True, reg_weight=self.reg_weight, gamma=self.bpr_gamma,
+                    fields=[uid, iid, neg])
+
     # ---- inference -------------------------------------------------------------------------------------------
     def _mapped_user_e(self, user):
         mapped = self._apply_mapping(ops.gather_rows_raw(self.source_user_embedding.weight, user))

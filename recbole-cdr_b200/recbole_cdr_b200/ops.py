@@ -431,3 +431,73 @@ def mlp_chain(x, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torc
     for k in range(n):
         x = dense(x, weights[k], biases[k], last_act if k == n - 1 else hidden_act)
     return x
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# A17: K training steps in one persistent launch
+# ------------------------------------------------------------------------------------------------------------------
+
+_steps_ws = {}
+
+
+def _steps_workspace(device, n_steps):
+    key = (device.index if device.index is not None else torch.cuda.current_device(), cur_stream())
+    need = _lib._lib.xdr_steps_workspace_bytes(int(n_steps))
+    ws = _steps_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _steps_ws[key] = ws
+    return ws
+
+
+def train_steps_supported(batch: int, dim: int, pairwise: bool, device=None) -> bool:
+    """True when (batch, dim) fits the persistent kernel's shared-memory stages (see xdr.h, xdr_train_steps)."""
+    if batch % 4 != 0 or dim % 4 != 0 or dim > 256:
+        return False
+    props = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device())
+    sms = props.multi_processor_count
+    rows = 3 if pairwise else 2
+    slice_ = max(4, (-(-batch // sms) + 3) // 4 * 4)
+    stage = rows * slice_ * 8 + slice_ * 4 + 2 * slice_ * 4 + rows * slice_ * dim * 4
+    stage = (stage + 127) // 128 * 128
+    return 256 + 4 * 4 * 18 + 128 + 4 * stage <= 220 * 1024 and -(-batch // slice_) <= sms
+
+
+def train_steps(user_tab, item_tab, user, item_a, item_b=None, label=None, *, loss_kind=_lib.LOSS_MSE, reg_weight=0.0,
+                gamma=1e-10, user_dst=None, item_dst=None, scale=1.0, grad_loss=None, out8=None):
+    """Run ``K = user.shape[0]`` training steps (fwd + bwd + scatter-add) in ONE persistent launch.
+
+    ``user`` / ``item_a`` / ``item_b`` (pairwise) / ``label`` (pointwise) are ``[K, B]`` device tensors (row k = batch
+    k; rows may be strided views of a larger ``[K, ..]`` buffer as long as each row is contiguous).  Gradients are
+    scatter-added into ``user_dst`` / ``item_dst`` scaled by ``scale`` (default: dense gradient tables ``.grad``-style;
+    pass the weight tables themselves and ``scale=-lr`` for fused asynchronous SGD).  Returns ``out8`` ``[K, 8]`` whose
+    column 0 is the per-step loss -- the value ``calculate_loss`` returns for that batch.
+    Replaces K iterations of recbole ``Trainer._train_epoch`` around emcdr.py:110-154 / cmf.py:75-98.
+    """
+    _require_cuda_f32(user_tab, 'user table')
+    _require_cuda_f32(item_tab, 'item table')
+    pairwise = item_b is not None
+    K, B = user.shape
+    for t, nm in ((user, 'user'), (item_a, 'item_a'), (item_b, 'item_b')):
+        if t is None:
+            continue
+        if t.dtype != torch.int64 or not t.is_cuda or t.shape != (K, B) or t.stride(1) != 1:
+            raise ValueError(f'{nm} must be a CUDA int64 [K, B] tensor with contiguous rows')
+        if t.stride(0) != user.stride(0):
+            raise ValueError('all id tensors must share the same step stride')
+    if label is not None and (label.dtype != torch.float32 or label.shape != (K, B) or label.stride(0) != user.stride(0)):
+        raise ValueError('label must be float32 [K, B] with the step stride of the id tensors')
+    dev = user_tab.device
+    if user_dst is None:
+        user_dst = torch.zeros_like(user_tab)
+    if item_dst is None:
+        item_dst = torch.zeros_like(item_tab)
+    if out8 is None:
+        out8 = torch.empty((K, 8), dtype=torch.float32, device=dev)
+    ws = _steps_workspace(dev, K)
+    call('xdr_train_steps', ptr(user_tab), ptr(item_tab), user_tab.shape[0], item_tab.shape[0], user_tab.shape[1], ptr(user),
+         ptr(item_a), ptr(item_b), ptr(label), user.stride(0), B, K, 1 if pairwise else 0, int(loss_kind), float(gamma),
+         float(reg_weight), ptr(grad_loss), float(scale), ptr(user_dst), ptr(item_dst), ptr(out8), ptr(ws), ws.numel(),
+         _oob(dev), cur_stream())
+    _maybe_check(dev)
+    return out8, user_dst, item_dst

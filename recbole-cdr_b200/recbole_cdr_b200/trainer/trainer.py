@@ -1,0 +1,242 @@
+"""CrossDomainTrainer on the xdr hot path -- mirror of reference trainer/trainer.py:19-76 plus the per-batch inner
+loop of ``recbole.trainer.Trainer._train_epoch`` [recbole-1.0.1] that it inherits.
+
+Scope: the phase loop and the ``zero_grad -> calculate_loss -> backward -> step`` inner
+loop.  Evaluation, early stopping, checkpointing and logging stay with the host framework (out of scope); ``fit``
+accepts the reference's signature and ignores what it does not implement.
+
+Two inner loops:
+
+* ``_train_epoch``: the reference's loop, batch by batch through ``model.calculate_loss`` (any model, any
+  ``torch.optim`` learner).  The only change: the running loss stays on the device and is read once per epoch instead
+  of ``loss.item()`` every step (a device->host sync per batch in recbole).
+* ``_train_epoch_fused`` (``config['xdr_fused_steps'] = K > 0``, learner ``sgd``, models exposing ``fused_step_spec``):
+  K batches are packed into one pinned ``[K, rows, B]`` id block, copied H2D on a copy stream, and run as ONE
+  persistent launch (``xdr_train_steps``) that does forward, backward and the SGD update (scatter-add of ``-lr * grad``
+  into the tables); per-step losses come back in one D2H copy.  Chunks are double-buffered so copies overlap compute.
+"""
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from ..utils import train_mode2state
+
+
+class FusedStepRunner:
+    """K-step persistent launches fed from pinned host id blocks (the engine under ``_train_epoch_fused``).
+
+    ``spec`` = dict(user_tab, item_tab, pairwise, loss_kind, reg_weight, gamma): see ``fused_step_spec`` of the models.
+    ``run(host_block)``: ``host_block`` is a pinned int64 ``[K, R, B]`` tensor (R = 3: user, item+, item-; R = 2 with a
+    separate ``host_label`` ``[K, B]`` float block for pointwise losses).  Returns the ``[K]`` per-step losses as a
+    pinned host tensor (valid after ``synchronize()``).
+    """
+
+    def __init__(self, spec: Dict, lr: Optional[float] = None, grad_tables=None, n_buffers: int = 2):
+        self.spec = spec
+        self.ut, self.it = spec['user_tab'], spec['item_tab']
+        self.dev = self.ut.device
+        if lr is not None:      # fused SGD: the scatter-add target is the weight table itself
+            self.dst_u, self.dst_i, self.scale = self.ut.data, self.it.data, -float(lr)
+        else:                   # gradient accumulation into dense .grad-style tables
+            gu, gi = grad_tables if grad_tables is not None else (torch.zeros_like(self.ut), torch.zeros_like(self.it))
+            self.dst_u, self.dst_i, self.scale = gu, gi, 1.0
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.n_buffers = n_buffers
+        self._bufs = []  # per in-flight chunk: (dev ids, dev label, out8, host loss, ready event, done event)
+        self._turn = 0
+        self.launches = 0
+
+    def _buffers(self, shape, with_label):
+        key = (tuple(shape), with_label)
+        if not self._bufs or self._bufs[0]['key'] != key:
+            self._bufs = []
+            K = shape[0]
+            for _ in range(self.n_buffers):
+                self._bufs.append({
+                    'key': key, 'ids': torch.empty(shape, dtype=torch.int64, device=self.dev),
+                    'label': torch.empty((K, shape[2]), dtype=torch.float32, device=self.dev) if with_label else None,
+                    'out8': torch.empty((K, 8), dtype=torch.float32, device=self.dev),
+                    'loss': torch.empty(K, dtype=torch.float32).pin_memory(),
+                    'ready': torch.cuda.Event(), 'done': torch.cuda.Event(), 'used': False})
+        b = self._bufs[self._turn % self.n_buffers]
+        self._turn += 1
+        return b
+
+    def run(self, host_block: torch.Tensor, host_label: Optional[torch.Tensor] = None) -> torch.Tensor:
+        sp = self.spec
+        K, R, B = host_block.shape
+        if R != (3 if sp['pairwise'] else 2):
+            raise ValueError(f'id block must be [K, {3 if sp["pairwise"] else 2}, B]')
+        buf = self._buffers(host_block.shape, host_label is not None)
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            if buf['used']:
+                self.copy_stream.wait_event(buf['done'])  # the launch that last read this buffer has finished
+            buf['ids'].copy_(host_block, non_blocking=True)
+            if host_label is not None:
+                buf['label'].copy_(host_label, non_blocking=True)
+            buf['ready'].record(self.copy_stream)
+        main.wait_event(buf['ready'])
+        ids = buf['ids']
+        ops.train_steps(self.ut.data, self.it.data, ids[:, 0], ids[:, 1], ids[:, 2] if sp['pairwise'] else None,
+                        buf['label'], loss_kind=sp.get('loss_kind', _lib.LOSS_MSE), reg_weight=sp['reg_weight'],
+                        gamma=sp.get('gamma', 1e-10), user_dst=self.dst_u, item_dst=self.dst_i, scale=self.scale,
+                        out8=buf['out8'])
+        self.launches += 1
+        buf['loss'].copy_(buf['out8'][:, 0], non_blocking=True)
+        buf['done'].record(main)
+        buf['used'] = True
+        return buf['loss']
+
+    def synchronize(self):
+        torch.cuda.current_stream(self.dev).synchronize()
+
+
+class CrossDomainTrainer(object):
+    r"""Trainer for cross-domain models with the four training modes SOURCE, TARGET, BOTH, OVERLAP set by
+    ``train_epochs`` (parsed by the host config into ``train_modes`` / ``epoch_num``, reference trainer.py:26-31)."""
+
+    def __init__(self, config, model):
+        self.config = config
+        self.model = model
+        self.device = config['device']
+        self.learner = (config['learner'] if 'learner' in config else 'adam').lower()
+        self.learning_rate = config['learning_rate'] if 'learning_rate' in config else 1e-3
+        self.weight_decay = config['weight_decay'] if 'weight_decay' in config else 0.0
+        self.clip_grad_norm = config['clip_grad_norm'] if 'clip_grad_norm' in config else None
+        self.train_modes = config['train_modes']
+        self.train_epochs = config['epoch_num']
+        self.split_valid_flag = config['source_split'] if 'source_split' in config else False
+        self.fused_steps = int(config['xdr_fused_steps']) if 'xdr_fused_steps' in config else 0
+        self.valid_metric_bigger = config['valid_metric_bigger'] if 'valid_metric_bigger' in config else True
+        self.optimizer = self._build_optimizer()
+        self.train_loss_dict = dict()
+        self.best_valid_score, self.best_valid_result = -np.inf, None
+        self.epochs = 0
+
+    def _build_optimizer(self):
+        """recbole Trainer._build_optimizer [recbole-1.0.1]: dense torch optimizers keyed by ``learner``."""
+        params = self.model.parameters()
+        lr, wd = self.learning_rate, self.weight_decay
+        table = {'adam': torch.optim.Adam, 'sgd': torch.optim.SGD, 'adagrad': torch.optim.Adagrad,
+                 'rmsprop': torch.optim.RMSprop}
+        if self.learner == 'sparse_adam':
+            return torch.optim.SparseAdam(params, lr=lr)
+        return table.get(self.learner, torch.optim.Adam)(params, lr=lr, weight_decay=wd)
+
+    def _reinit(self, phase):
+        """Reset per-phase state (reference trainer.py:30-41)."""
+        self.start_epoch = 0
+        self.cur_step = 0
+        self.best_valid_score = -np.inf if self.valid_metric_bigger else np.inf
+        self.best_valid_result = None
+        self.train_loss_dict = dict()
+        self.epochs = int(self.train_epochs[phase])
+
+    @staticmethod
+    def _check_nan(loss):
+        if torch.isnan(loss).any():
+            raise ValueError('Training loss is nan')
+
+    # ---- inner loops -----------------------------------------------------------------------------------------
+    def _train_epoch(self, train_data, epoch_idx, loss_func=None, show_progress=False):
+        """recbole Trainer._train_epoch: zero_grad -> calculate_loss -> (sum tuple) -> backward -> [clip] -> step."""
+        self.model.train()
+        loss_func = loss_func or self.model.calculate_loss
+        total = None
+        for interaction in train_data:
+            interaction = interaction.to(self.device)
+            self.optimizer.zero_grad()
+            losses = loss_func(interaction)
+            loss = sum(losses) if isinstance(losses, tuple) else losses
+            loss = loss.sum()
+            total = loss.detach() if total is None else total + loss.detach()
+            loss.backward()
+            if self.clip_grad_norm:
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
+            self.optimizer.step()
+        if total is None:
+            return 0.0
+        self._check_nan(total)
+        return float(total.item())  # one device->host read per epoch
+
+    def _fused_spec(self):
+        spec_fn = getattr(self.model, 'fused_step_spec', None)
+        if self.fused_steps <= 0 or spec_fn is None or self.learner != 'sgd' or self.weight_decay:
+            return None
+        return spec_fn()
+
+    def _train_epoch_fused(self, train_data, epoch_idx, spec):
+        """K batches per persistent launch with the SGD update fused into the scatter-add."""
+        self.model.train()
+        runner = FusedStepRunner(spec, lr=self.learning_rate)
+        fields, label_field = spec['fields'], spec.get('label_field')
+        K = self.fused_steps
+        pending: List[torch.Tensor] = []
+        total = 0.0
+        chunk, labels = [], []
+
+        def flush():
+            nonlocal chunk, labels
+            if not chunk:
+                return
+            block = torch.stack(chunk).pin_memory()
+            lab = torch.stack(labels).pin_memory() if labels else None
+            pending.append(runner.run(block, lab))
+            chunk, labels = [], []
+
+        width = None
+        for interaction in train_data:
+            ids = torch.stack([interaction[f].reshape(-1).cpu() for f in fields])
+            ok = ops.train_steps_supported(ids.shape[1], spec['user_tab'].shape[1], spec['pairwise'], self.device)
+            if not ok or (width is not None and ids.shape[1] != width):
+                # a ragged last batch (or a shape the persistent kernel does not take) goes through the per-step path
+                flush()
+                runner.synchronize()
+                total += self._train_epoch([interaction], epoch_idx)
+                continue
+            width = ids.shape[1]
+            chunk.append(ids)
+            if label_field:
+                labels.append(interaction[label_field].reshape(-1).float().cpu())
+            if len(chunk) == K:
+                flush()
+        flush()
+        runner.synchronize()
+        for l in pending:
+            total += float(l.sum().item())
+        if total != total:
+            raise ValueError('Training loss is nan')
+        return total
+
+    # ---- phase loop ------------------------------------------------------------------------------------------
+    def _fit_phase(self, train_data, valid_data, verbose, saved, show_progress, callback_fn):
+        spec = self._fused_spec()
+        for epoch_idx in range(self.start_epoch, self.epochs):
+            if spec is not None:
+                loss = self._train_epoch_fused(train_data, epoch_idx, spec)
+            else:
+                loss = self._train_epoch(train_data, epoch_idx, show_progress=show_progress)
+            self.train_loss_dict[epoch_idx] = loss
+            if callback_fn:
+                callback_fn(epoch_idx, loss)
+        return self.best_valid_score, self.best_valid_result
+
+    def fit(self, train_data, valid_data=None, verbose=True, saved=True, show_progress=False, callback_fn=None):
+        r"""For each ``train_epochs`` entry: reset, switch the dataloader state, switch the model phase, train
+        (reference trainer.py:59-73); ends with ``model.set_phase('OVERLAP')`` (trainer.py:75)."""
+        for phase in range(len(self.train_modes)):
+            self._reinit(phase)
+            scheme = self.train_modes[phase]
+            train_data.set_mode(train_mode2state[scheme])
+            self.model.set_phase(scheme)
+            if self.split_valid_flag and valid_data is not None:
+                source_valid_data, target_valid_data = valid_data
+                vd = source_valid_data if scheme == 'SOURCE' else target_valid_data
+            else:
+                vd = valid_data
+            self._fit_phase(train_data, vd, verbose, saved, show_progress, callback_fn)
+        self.model.set_phase('OVERLAP')
+        return self.best_valid_score, self.best_valid_result

@@ -41,7 +41,10 @@ def rand_ids(n, hi, seed, zipf=None):
 
 
 def assert_grad_close(got, ref, what):
-    torch.testing.assert_close(got.cpu(), ref, rtol=GRAD_RTOL, atol=GRAD_ATOL, msg=lambda m: f'{what}: {m}')
+    # rows hit by thousands of duplicate ids are sums in a different order than index_add: allow 1e-4 of the
+    # gradient's scale on top of the element-wise relative bound
+    atol = max(GRAD_ATOL, 1e-4 * ref.abs().max().item())
+    torch.testing.assert_close(got.cpu(), ref, rtol=GRAD_RTOL, atol=atol, msg=lambda m: f'{what}: {m}')
 
 
 # ---------------------------------------------------------------------------------------------------- A1
@@ -74,7 +77,11 @@ def test_scatter_add_matches_index_add(dim, zipf):
     ref = torch.zeros(n, dim).index_add_(0, idx, rows * 0.5)
     dst = torch.zeros(n, dim, device=dev())
     ops().scatter_add_rows_raw(dst, idx.to(dev()), rows.to(dev()), 0.5)
-    torch.testing.assert_close(dst.cpu(), ref, rtol=1e-5, atol=1e-5)
+    ref64 = torch.zeros(n, dim, dtype=torch.float64).index_add_(0, idx, rows.double() * 0.5)
+    # fp32 sums of up to thousands of duplicates in atomic order vs index_add order: compare both to the fp64 sum
+    tol = 1e-6 * torch.zeros(n, dim, dtype=torch.float64).index_add_(0, idx, rows.double().abs() * 0.5) + 1e-6
+    assert ((dst.cpu().double() - ref64).abs() <= 8 * tol).all()
+    assert ((ref.double() - ref64).abs() <= 8 * tol).all()
 
 
 def test_scatter_add_all_duplicates():

@@ -172,8 +172,8 @@ XDR_API int xdr_select_dot(const float* mapped, const float* tgt_tab, int64_t n_
  * calling the fwd+bwd pair on batch k.  dst = gradient tables (scale 1): gradients of the K batches accumulate.
  * dst = the weight tables (scale = -lr): asynchronous SGD, a batch may read rows up to 4 steps stale.
  * Restrictions (else XDR_ERR_UNSUPPORTED: use the per-step entry points): batch % 4 == 0, step_stride % 4 == 0,
- * id arrays 16-byte aligned, and ceil(batch / #SMs) interactions x rows must fit 4 shared-memory stages
- * (batch <= ~8900 at dim 64 pairwise on a 148-SM part).
+ * id arrays 16-byte aligned, and at most 40 warp tasks per CTA per step, i.e. ceil(batch / #SMs) <= 160 at dim <= 64
+ * (batch <= 23680 on a 148-SM part; rows live in registers, two tasks in flight per warp).
  * steps_ws: xdr_steps_workspace_bytes(n_steps) bytes of scratch (no initialisation needed).                         */
 XDR_API size_t xdr_steps_workspace_bytes(int n_steps);
 XDR_API int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,

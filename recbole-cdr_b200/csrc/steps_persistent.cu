@@ -6,35 +6,38 @@
 // i.e. per batch: gather -> dot score -> loss (+EmbLoss) -> row gradients -> scatter-add, with the per-batch
 // losses written to out8[k].  Results per batch are identical to xdr_bpr_fwd + xdr_bpr_bwd on that batch
 // (gradient accumulation over the K batches when dst is a gradient table; asynchronous SGD with bounded
-// staleness <= kStages steps when dst is the weight table and scale = -lr).
+// staleness (a few steps) when dst is the weight table and scale = -lr).
 //
-// Why: one B=8192 step moves 12.8 MB = 1.95 us at the HBM roofline while a dependent load chain
-// (ids -> rows -> grid reduction for the EmbLoss norms -> atomics) is > 3 us of latency and a launch ~2 us.
-// So the launch is amortised over K steps and the latencies are overlapped across steps:
+// Why: one B=8192 step moves 12.8 MB = 1.95 us at the HBM roofline, while the dependent chain
+// ids -> rows -> grid-wide EmbLoss norm -> atomics is ~4 us of latency and a launch ~2 us.  So one launch
+// covers K steps and the chain is overlapped across steps (profiles/r1_*: v1 of this kernel staged rows in
+// shared memory and spent 60% of its time in CTA barriers and stage waits; this is v2).
 //
-//   grid    one CTA per SM (persistent); CTA c owns interactions [c*S, (c+1)*S) of EVERY step (S = ceil(B/grid))
-//   warp 0  producer: for step t (running ahead by up to kStages-2 steps)
-//             TMA bulk copy (cp.async.bulk, UBLKCP) of the CTA's id tiles -> smem, wait, then one bulk copy per
-//             embedding row (dim*4 bytes, 256 B at dim 64) HBM -> smem stage, completion on an mbarrier
-//   warps 1..16 consumers: iteration s does
-//             phase A(s)   rows from smem (8 lanes per interaction, LDS.128), dots + squared norms via shuffles,
-//                          per-CTA partial sums -> global, arrive on the step counter
-//             phase B(s-1) (lagging one step so the grid-wide EmbLoss norm of step s-1 is already complete)
-//                          fixed-order fp64 reduction of all CTAs' partials, row gradients from the rows still in
-//                          smem, REDG.E.ADD.F32x4 scatter-add to the destination tables, release the stage
-//   No grid-wide barrier anywhere; the only cross-CTA dependency is the per-step arrival counter, which is
-//   waited on one full iteration after it was signalled.
+//   grid      one CTA per SM (persistent); CTA c owns interactions [c*S, (c+1)*S) of EVERY step
+//   warp 0    producer: TMA bulk copies (cp.async.bulk -> UBLKCP) of the CTA's id tiles (and labels) of step t into
+//             an 8-deep shared-memory ring, several steps ahead of the workers
+//   warp 1    publisher: per step, sums the CTA's task partials (fixed order) and publishes them to global memory as
+//             8-byte {value, step-tag} words (no fences: data and flag travel in one atomic store)
+//   warps 2,3 gatherers (even / odd steps): poll all CTAs' words of a step (one batch of loads per poll round),
+//             reduce in fp64 in a fixed order, hand the step's norm factors to the workers through shared memory
+//   warps 4.. workers: a task = 32/LPR interactions of one step.  LPR lanes own one interaction; each lane keeps
+//             VEC float4 columns of the 2-3 rows IN REGISTERS from the gather (LDG.128, L1-bypassing) through
+//             score/loss (shuffle reductions) until the step's norms arrive, then forms the row gradients and
+//             issues REDG.E.ADD.F32x4.  Each warp keeps TWO tasks in flight (rows of the next task are requested
+//             before the current task waits for its norms), so the ~2 steps of latency stay covered.
+//   All hand-offs are mbarriers (ids landed / task partial written / norms ready / id slot free); no CTA-wide
+//   barrier and no grid-wide barrier anywhere.
 //
-// HBM roofline: same algorithmic bytes as the two-kernel path (1560 B per BPR interaction at dim 64) but the
-// backward re-gather disappears (rows stay in smem), so DRAM traffic ~= algorithmic bytes.
+// HBM roofline: 1560 algorithmic bytes per BPR interaction at dim 64 (ids + 3 rows gathered + 3 rows scattered).
 #include "xdr_common.cuh"
 
 namespace xdr {
 
-constexpr int kConsumerWarps = 16;
-constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kStepThreads = kConsumerThreads + 32;  // + producer warp
-constexpr int kStages = 4;
+constexpr int kWorkerWarps = 20;
+constexpr int kServiceWarps = 4;                       // producer, publisher, two gatherers
+constexpr int kStepThreads = (kWorkerWarps + kServiceWarps) * 32;
+constexpr int kMaxCtaPerLane = 5;                      // gatherer lanes poll <= 5 CTAs each: grid <= 160
+constexpr int kRing = 8;                               // id-tile / partial / norm ring depth (steps)
 
 struct StepsArgs {
   const float* user_tab;
@@ -55,13 +58,12 @@ struct StepsArgs {
   float scale;
   float* user_dst;
   float* item_dst;
-  float4* partials;      // [n_steps][gridDim.x]
-  unsigned int* arrive;  // [n_steps], zeroed by the host wrapper before the launch
-  int slice;             // S
+  unsigned long long* words;  // [n_steps][gridDim.x][3] {fp32 value, step tag}; zeroed by the host wrapper
+  int slice;                  // S: interactions per CTA per step (multiple of 4)
   int32_t* oob;
 };
 
-// ---- mbarrier / bulk-copy PTX wrappers ---------------------------------------------------------------------------
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -92,330 +94,401 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
-
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// coherent (L2) 128-bit row load: the table may be the scatter destination of this very launch (fused SGD)
+__device__ __forceinline__ float4 ldcg_row4(const float* row, int col4) {
+  return __ldcg(reinterpret_cast<const float4*>(row) + col4);
+}
 
-// Shared-memory stage: ids, (labels), rows and scores of one step's slice.
-template <bool PAIRWISE>
-struct StageLayout {
-  static constexpr int kRowsPer = PAIRWISE ? 3 : 2;
-  int slice, row_f;
-  __host__ __device__ StageLayout(int s, int nv) : slice(s), row_f(nv * 4) {}
-  // all offsets in bytes, each region 16-byte aligned (slice is rounded up to a multiple of 4 by the host)
-  __host__ __device__ size_t ids_off() const { return 0; }
-  __host__ __device__ size_t label_off() const { return ids_off() + (size_t)kRowsPer * slice * 8; }
-  __host__ __device__ size_t score_off() const { return label_off() + (size_t)slice * 4; }
-  __host__ __device__ size_t rows_off() const { return score_off() + (size_t)2 * slice * 4; }
-  __host__ __device__ size_t bytes() const {
-    size_t b = rows_off() + (size_t)kRowsPer * slice * row_f * 4;
-    return (b + 127) & ~(size_t)127;
+// ---- shared-memory layout -------------------------------------------------------------------------------------------
+struct SmemLayout {
+  int slice, rows_per, tasks;  // S, 2|3, tasks per step per CTA (upper bound)
+  __host__ __device__ SmemLayout(int s, int r, int t) : slice(s), rows_per(r), tasks(t) {}
+  // [0, 256): 4 x kRing mbarriers.  [256, 320): norms [kRing][2].  then partials, then the id ring.
+  __host__ __device__ size_t bars_off() const { return 0; }
+  __host__ __device__ size_t norms_off() const { return 256; }
+  __host__ __device__ size_t part_off() const { return 320; }
+  __host__ __device__ size_t ids_off() const {
+    return (part_off() + (size_t)kRing * tasks * sizeof(float4) + 127) & ~(size_t)127;
   }
+  __host__ __device__ size_t ids_slot_bytes() const {  // ids [rows_per][S] int64 + labels [S] fp32
+    return (((size_t)rows_per * slice * 8 + (size_t)slice * 4) + 127) & ~(size_t)127;
+  }
+  __host__ __device__ size_t bytes() const { return ids_off() + (size_t)kRing * ids_slot_bytes(); }
 };
 
-constexpr size_t kHeaderBytes = 256;  // mbarriers + cross-warp reduction scratch
-
+// One task's registers: ids, validity, the rows (VEC float4 columns per lane) and the scores.
 template <int VEC, bool PAIRWISE>
-__global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [kStages] rows landed
-  uint64_t* idsf = full + kStages;                         // [kStages] id tiles landed
-  uint64_t* empty = idsf + kStages;                        // [kStages] stage released by the consumers
-  float* red = reinterpret_cast<float*>(smem_raw + 3 * kStages * 8);  // [4*kConsumerWarps] + 4 broadcast slots... see below
-  // header budget: 3*4*8 = 96 B of barriers; reduction scratch lives right after the header
-  const StageLayout<PAIRWISE> L(a.slice, a.nv);
-  constexpr int R = StageLayout<PAIRWISE>::kRowsPer;
-  unsigned char* stage0 = smem_raw + kHeaderBytes + 4 * sizeof(float) * (kConsumerWarps + 2);
-  stage0 = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(stage0) + 127) & ~(uintptr_t)127);
-  float* wred = reinterpret_cast<float*>(smem_raw + kHeaderBytes);  // [3][kConsumerWarps] partial sums
-  float* bcast = wred + 3 * kConsumerWarps;                          // [4] cu, ci for phase B (+ spare)
-  (void)red;
+struct TaskRegs {
+  float4 u[VEC], a[VEC], b[PAIRWISE ? VEC : 1];
+  int iu, ia, ib;  // row ids (tables have < 2^31 rows); -1 = padding lane or out-of-range id (row reads as zeros)
+  float sa, sb, label;
+  int s, q;
+};
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+template <int LPR, int VEC, bool PAIRWISE>
+__global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs a) {
+  constexpr int IPW = 32 / LPR;  // interactions per warp task
+  constexpr int R = PAIRWISE ? 3 : 2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int64_t first = (int64_t)blockIdx.x * a.slice;
   const int cnt = (int)min((int64_t)a.slice, a.batch - first);  // > 0: the host launches ceil(batch/slice) CTAs
+  const int tasks = (cnt + IPW - 1) / IPW;                      // tasks of this CTA per step
+  const SmemLayout L(a.slice, R, (a.slice + IPW - 1) / IPW);
+  uint64_t* idsf = reinterpret_cast<uint64_t*>(smem_raw + L.bars_off());  // id tile landed        (tx barrier)
+  uint64_t* ifree = idsf + kRing;                                         // id slot free          (count = tasks)
+  uint64_t* adone = ifree + kRing;                                        // task partials written (count = tasks)
+  uint64_t* normf = adone + kRing;                                        // norms ready           (count = 1)
+  float2* norms = reinterpret_cast<float2*>(smem_raw + L.norms_off());
+  float4* part = reinterpret_cast<float4*>(smem_raw + L.part_off());
+  unsigned char* ids_ring = smem_raw + L.ids_off();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_f = a.nv * 4;
-  const uint32_t row_bytes = (uint32_t)row_f * 4u;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full[i], 1);
+    for (int i = 0; i < kRing; ++i) {
       mbar_init(&idsf[i], 1);
-      mbar_init(&empty[i], kConsumerWarps);
+      mbar_init(&ifree[i], (uint32_t)tasks);
+      mbar_init(&adone[i], (uint32_t)tasks);
+      mbar_init(&normf[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   if (warp == 0) {
-    // =========================================== producer ===========================================
-    for (int t = 0; t < a.n_steps; ++t) {
-      const int slot = t % kStages;
-      const uint32_t par = (uint32_t)((t / kStages) & 1);
-      unsigned char* st = stage0 + (size_t)slot * L.bytes();
-      int64_t* ids = reinterpret_cast<int64_t*>(st + L.ids_off());
-      float* lab = reinterpret_cast<float*>(st + L.label_off());
-      float* rows = reinterpret_cast<float*>(st + L.rows_off());
-      mbar_wait(&empty[slot], par ^ 1u);  // passes immediately the first time round the ring
-      const int64_t off = (int64_t)t * a.step_stride + first;
-      // id tiles: cnt*8 bytes each; cnt is even except possibly in the last CTA -> round the copy up to 16 bytes
-      // (the host guarantees the id arrays are padded/aligned so the rounded copy stays inside the allocation)
-      const uint32_t idb = ((uint32_t)cnt * 8u + 15u) & ~15u;
-      const uint32_t lbb = ((uint32_t)cnt * 4u + 15u) & ~15u;
-      if (lane == 0) {
-        const bool has_label = !PAIRWISE && a.label != nullptr;
+    // =========================================== producer: id tiles via TMA ===========================================
+    if (lane == 0) {
+      const uint32_t idb = (uint32_t)cnt * 8u, lbb = (uint32_t)cnt * 4u;  // cnt % 4 == 0 -> multiples of 16 bytes
+      const bool has_label = !PAIRWISE && a.label != nullptr;
+      for (int t = 0; t < a.n_steps; ++t) {
+        const int slot = t % kRing;
+        const uint32_t par = (uint32_t)((t / kRing) & 1);
+        int64_t* ids = reinterpret_cast<int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
+        float* lab = reinterpret_cast<float*>(ids + (size_t)R * L.slice);
+        mbar_wait(&ifree[slot], par ^ 1u);  // passes immediately the first time round the ring
+        const int64_t off = (int64_t)t * a.step_stride + first;
         mbar_expect_tx(&idsf[slot], idb * R + (has_label ? lbb : 0u));
         bulk_g2s(ids, a.user + off, idb, &idsf[slot]);
         bulk_g2s(ids + L.slice, a.item_a + off, idb, &idsf[slot]);
         if (PAIRWISE) bulk_g2s(ids + 2 * L.slice, a.item_b + off, idb, &idsf[slot]);
         if (has_label) bulk_g2s(lab, a.label + off, lbb, &idsf[slot]);
       }
-      __syncwarp();
-      mbar_wait(&idsf[slot], par);
-      if (lane == 0) mbar_expect_tx(&full[slot], (uint32_t)(cnt * R) * row_bytes);
-      __syncwarp();
-      for (int r = lane; r < cnt * R; r += 32) {
-        const int which = r / cnt, j = r - which * cnt;
-        int64_t id = ids[which * L.slice + j];
-        const int64_t n_rows = which == 0 ? a.n_users : a.n_items;
-        if ((uint64_t)id >= (uint64_t)n_rows) {
-          if (a.oob) *a.oob = 1;
-          id = 0;  // keep the copy in bounds; the consumers zero the row through the same validity test
-        }
-        const float* src = (which == 0 ? a.user_tab : a.item_tab) + id * (int64_t)row_f;
-        bulk_g2s(rows + ((size_t)which * L.slice + j) * row_f, src, row_bytes, &full[slot]);
-      }
     }
-  } else {
-    // =========================================== consumers ==========================================
-    const int cw = warp - 1;
-    const int sub = lane & (kLanesPerRow - 1), grp = lane >> 3;
-    const int ctid = threadIdx.x - 32;
+  } else if (warp == 1) {
+    // =========================================== publisher ============================================================
+    // per step: sum this CTA's task partials in a fixed order and publish them as three 8-byte {value, tag} words
+    const unsigned int n_cta = gridDim.x;
+    for (int s = 0; s < a.n_steps; ++s) {
+      const int slot = s % kRing;
+      const uint32_t par = (uint32_t)((s / kRing) & 1);
+      mbar_wait(&adone[slot], par);
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+      for (int q = lane; q < tasks; q += 32) {
+        const float4 v = part[slot * L.tasks + q];
+        p0 += v.x;
+        p1 += v.y;
+        p2 += v.z;
+      }
+      p0 = warp_sum(p0);
+      p1 = warp_sum(p1);
+      p2 = warp_sum(p2);
+      if (lane < 3) {
+        const float v = lane == 0 ? p0 : (lane == 1 ? p1 : p2);
+        st_relaxed_u64(a.words + ((size_t)s * n_cta + blockIdx.x) * 3 + lane,
+                       ((unsigned long long)(unsigned int)(s + 1) << 32) | (unsigned long long)__float_as_uint(v));
+      }
+      __syncwarp();
+    }
+  } else if (warp < kServiceWarps) {
+    // =========================================== gatherers (even / odd steps) =========================================
+    // poll every CTA's words of the step (all loads of a poll round in flight together: one L2 round trip), reduce in
+    // fp64 in a fixed order, hand the step's norm factors to the workers
+    const unsigned int n_cta = gridDim.x;
     const float inv_b = 1.0f / (float)a.batch;
     const float g = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f) * a.scale;
-    const unsigned int n_cta = gridDim.x;
-    for (int s = 0; s <= a.n_steps; ++s) {
-      if (s < a.n_steps) {
-        // ---------------- phase A(s) ----------------
-        const int slot = s % kStages;
-        const uint32_t par = (uint32_t)((s / kStages) & 1);
-        unsigned char* st = stage0 + (size_t)slot * L.bytes();
-        const int64_t* ids = reinterpret_cast<const int64_t*>(st + L.ids_off());
-        const float* lab = reinterpret_cast<const float*>(st + L.label_off());
-        float* sc = reinterpret_cast<float*>(st + L.score_off());
-        const float* rows = reinterpret_cast<const float*>(st + L.rows_off());
-        mbar_wait(&idsf[slot], par);
-        mbar_wait(&full[slot], par);
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-        for (int base = cw * kRowsPerWarp; base < cnt; base += kConsumerWarps * kRowsPerWarp) {
-          const int j = base + grp;
-          const bool live = j < cnt;
-          const int jj = live ? j : 0;
-          const bool oku = live && (uint64_t)ids[jj] < (uint64_t)a.n_users;
-          const bool oka = live && (uint64_t)ids[L.slice + jj] < (uint64_t)a.n_items;
-          const bool okb = PAIRWISE && live && (uint64_t)ids[2 * L.slice + jj] < (uint64_t)a.n_items;
-          const float* pu = rows + (size_t)jj * row_f;
-          const float* pa = rows + ((size_t)L.slice + jj) * row_f;
-          const float* pb = rows + ((size_t)2 * L.slice + jj) * row_f;
-          float da = 0.f, db = 0.f, uu = 0.f, aa = 0.f;
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = warp - 2; s < a.n_steps; s += 2) {
+      const int slot = s % kRing;
+      const unsigned int tag = (unsigned int)(s + 1);
+      const unsigned long long* base = a.words + (size_t)s * n_cta * 3;
+      unsigned long long wv[kMaxCtaPerLane][3];
+      bool all_ok;
+      do {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) {
-            const int c = sub + v * kLanesPerRow;
-            const bool on = c < a.nv;
-            const float4 ru = (oku && on) ? ld_row4(pu, c) : z;
-            const float4 ra = (oka && on) ? ld_row4(pa, c) : z;
-            da += dot4(ru, ra);
-            uu += dot4(ru, ru);
-            aa += dot4(ra, ra);
-            if (PAIRWISE) {
-              const float4 rb = (okb && on) ? ld_row4(pb, c) : z;
-              db += dot4(ru, rb);
-            }
-          }
-          da = group8_sum(da);
-          if (PAIRWISE) db = group8_sum(db);
-          uu = group8_sum(uu);
-          aa = group8_sum(aa);
-          if (live && sub == 0) {
-            sc[j] = da;
-            float term;
-            if (PAIRWISE) {
-              sc[L.slice + j] = db;
-              term = -logf(a.gamma + sigmoidf_(da - db));
-            } else if (a.loss_kind == XDR_LOSS_MSE) {
-              const float d = da - lab[j];
-              term = d * d;
-            } else if (a.loss_kind == XDR_LOSS_BCE_SIGMOID) {
-              const float p = sigmoidf_(da), y = lab[j];
-              term = -(y * fmaxf(logf(p), -100.f) + (1.f - y) * fmaxf(logf(1.f - p), -100.f));
-            } else {
-              term = 0.f;
-            }
-            acc0 += term;
-            acc1 += uu;
-            acc2 += aa;
-          }
-        }
-        acc0 = warp_sum(acc0);
-        acc1 = warp_sum(acc1);
-        acc2 = warp_sum(acc2);
-        if (lane == 0) {
-          wred[cw] = acc0;
-          wred[kConsumerWarps + cw] = acc1;
-          wred[2 * kConsumerWarps + cw] = acc2;
-        }
-      }
-      consumer_bar();  // (1) this CTA's phase-A partial sums are in smem
-      if (cw == 0) {
-        if (s < a.n_steps) {
-          float p0 = lane < kConsumerWarps ? wred[lane] : 0.f;
-          float p1 = lane < kConsumerWarps ? wred[kConsumerWarps + lane] : 0.f;
-          float p2 = lane < kConsumerWarps ? wred[2 * kConsumerWarps + lane] : 0.f;
-          p0 = warp_sum(p0);
-          p1 = warp_sum(p1);
-          p2 = warp_sum(p2);
-          if (lane == 0) {
-            a.partials[(size_t)s * n_cta + blockIdx.x] = make_float4(p0, p1, p2, 0.f);
-            __threadfence();
-            atomicAdd(&a.arrive[s], 1u);
-          }
-        }
-        if (s >= 1) {
-          // ---- wait (normally already satisfied) for every CTA's phase A of step s-1, reduce in a fixed order
-          const int sp = s - 1;
-          if (lane == 0) {
-            while (ld_acquire_u32(&a.arrive[sp]) < n_cta) __nanosleep(32);
-          }
-          __syncwarp();
-          double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-          for (unsigned int c = lane; c < n_cta; c += 32) {
-            const float4 p = __ldcg(&a.partials[(size_t)sp * n_cta + c]);
-            t0 += (double)p.x;
-            t1 += (double)p.y;
-            t2 += (double)p.z;
-          }
-          t0 = warp_sum(t0);
-          t1 = warp_sum(t1);
-          t2 = warp_sum(t2);
-          if (lane == 0) {
-            const float nu = (float)sqrt(t1), ni = (float)sqrt(t2);
-            bcast[0] = (a.reg_weight != 0.f && nu > 0.f) ? g * a.reg_weight * inv_b / nu : 0.f;
-            bcast[1] = (a.reg_weight != 0.f && ni > 0.f) ? g * a.reg_weight * inv_b / ni : 0.f;
-            if (blockIdx.x == 0) {
-              const float data = (float)(t0 / (double)a.batch);
-              const float reg = (float)(((double)nu + (double)ni) / (double)a.batch);
-              float* o = a.out8 + (size_t)sp * 8;
-              o[0] = data + a.reg_weight * reg;
-              o[1] = data;
-              o[2] = nu;
-              o[3] = ni;
-              o[4] = reg;
-              o[5] = 0.f;
-              o[6] = 0.f;
-              o[7] = 0.f;
-            }
-          }
-        }
-      }
-      consumer_bar();  // (2) norms of step s-1 are in smem
-      if (s >= 1) {
-        // ---------------- phase B(s-1) ----------------
-        const int sp = s - 1;
-        const int slot = sp % kStages;
-        unsigned char* st = stage0 + (size_t)slot * L.bytes();
-        const int64_t* ids = reinterpret_cast<const int64_t*>(st + L.ids_off());
-        const float* lab = reinterpret_cast<const float*>(st + L.label_off());
-        const float* sc = reinterpret_cast<const float*>(st + L.score_off());
-        const float* rows = reinterpret_cast<const float*>(st + L.rows_off());
-        const float cu = bcast[0], ci = bcast[1];
-        for (int base = cw * kRowsPerWarp; base < cnt; base += kConsumerWarps * kRowsPerWarp) {
-          const int j = base + grp;
-          if (j >= cnt) continue;
-          const int64_t u = ids[j], ia = ids[L.slice + j];
-          const int64_t ib = PAIRWISE ? ids[2 * L.slice + j] : 0;
-          const bool oku = (uint64_t)u < (uint64_t)a.n_users;
-          const bool oka = (uint64_t)ia < (uint64_t)a.n_items;
-          const bool okb = PAIRWISE && (uint64_t)ib < (uint64_t)a.n_items;
-          float c;
-          if (PAIRWISE) {
-            const float sg = sigmoidf_(sc[j] - sc[L.slice + j]);
-            c = -g * inv_b * (sg * (1.f - sg)) / (a.gamma + sg);
-          } else if (a.loss_kind == XDR_LOSS_MSE) {
-            c = g * inv_b * 2.f * (sc[j] - lab[j]);
-          } else if (a.loss_kind == XDR_LOSS_BCE_SIGMOID) {
-            const float p = sigmoidf_(sc[j]), y = lab[j];
-            const float pq = p * (1.f - p);
-            c = g * inv_b * (p - y) / fmaxf(pq, 1e-12f) * pq;
-          } else {
-            c = 0.f;
-          }
-          const float* pu = rows + (size_t)j * row_f;
-          const float* pa = rows + ((size_t)L.slice + j) * row_f;
-          const float* pb = rows + ((size_t)2 * L.slice + j) * row_f;
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < kMaxCtaPerLane; ++i) {
+          const unsigned int c = lane + 32u * i;
+          if (c < n_cta) {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) {
-            const int cidx = sub + v * kLanesPerRow;
-            if (cidx >= a.nv) continue;
-            const float4 ru = oku ? ld_row4(pu, cidx) : z;
-            const float4 ra = oka ? ld_row4(pa, cidx) : z;
-            if (PAIRWISE) {
-              const float4 rb = okb ? ld_row4(pb, cidx) : z;
-              if (oku) red_add4(a.user_dst + u * (int64_t)row_f, cidx, axpy4(cu, ru, scale4(c, sub4(ra, rb))));
-              if (oka) red_add4(a.item_dst + ia * (int64_t)row_f, cidx, axpy4(ci, ra, scale4(c, ru)));
-              if (okb) red_add4(a.item_dst + ib * (int64_t)row_f, cidx, scale4(-c, ru));
-            } else {
-              if (oku) red_add4(a.user_dst + u * (int64_t)row_f, cidx, axpy4(cu, ru, scale4(c, ra)));
-              if (oka) red_add4(a.item_dst + ia * (int64_t)row_f, cidx, axpy4(ci, ra, scale4(c, ru)));
-            }
+            for (int k = 0; k < 3; ++k) wv[i][k] = ld_relaxed_u64(base + (size_t)c * 3 + k);
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[slot]);  // stage may be refilled by the producer
+        all_ok = true;
+#pragma unroll
+        for (int i = 0; i < kMaxCtaPerLane; ++i) {
+          const unsigned int c = lane + 32u * i;
+          if (c < n_cta) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) all_ok = all_ok && ((unsigned int)(wv[i][k] >> 32) == tag);
+          }
+        }
+        all_ok = __all_sync(0xffffffffu, all_ok);
+      } while (!all_ok);
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < kMaxCtaPerLane; ++i) {
+        const unsigned int c = lane + 32u * i;
+        if (c < n_cta) {
+          t0 += (double)__uint_as_float((unsigned int)wv[i][0]);
+          t1 += (double)__uint_as_float((unsigned int)wv[i][1]);
+          t2 += (double)__uint_as_float((unsigned int)wv[i][2]);
+        }
       }
-      (void)ctid;
+      t0 = warp_sum(t0);
+      t1 = warp_sum(t1);
+      t2 = warp_sum(t2);
+      if (lane == 0) {
+        const float nu = (float)sqrt(t1), ni = (float)sqrt(t2);
+        // d(reg_weight * (||U||_F + ||I||_F)/B)/dU_r = reg_weight/(B*||U||_F) * U_r   (torch: 0 when the norm is 0)
+        norms[slot] = make_float2((a.reg_weight != 0.f && nu > 0.f) ? g * a.reg_weight * inv_b / nu : 0.f,
+                                  (a.reg_weight != 0.f && ni > 0.f) ? g * a.reg_weight * inv_b / ni : 0.f);
+        if (blockIdx.x == 0) {
+          const float data = (float)(t0 / (double)a.batch);
+          const float reg = (float)(((double)nu + (double)ni) / (double)a.batch);
+          float* o = a.out8 + (size_t)s * 8;
+          o[0] = data + a.reg_weight * reg;
+          o[1] = data;
+          o[2] = nu;
+          o[3] = ni;
+          o[4] = reg;
+          o[5] = 0.f;
+          o[6] = 0.f;
+          o[7] = 0.f;
+        }
+        mbar_arrive(&normf[slot]);  // release: the norms are visible to every worker that observes this phase
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================================== workers ==============================================================
+    // Only min(kWorkerWarps, 3*tasks) workers are active so that a worker's consecutive tasks are at most 3 steps
+    // apart: with two tasks held per warp the steps in flight span <= 7 < kRing, so no ring is ever lapped.
+    // The host guarantees tasks <= 2*kWorkerWarps (each worker owns at most two tasks of any step, and it runs
+    // phase A of both before it waits for that step's norms).
+    const int n_workers = min(kWorkerWarps, 3 * tasks);
+    const int w = warp - kServiceWarps;
+    if (w >= n_workers) return;
+    const int sub = lane % LPR, grp = lane / LPR;
+    const float inv_b = 1.0f / (float)a.batch;
+    const float g = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f) * a.scale;
+    const int total = a.n_steps * tasks;
+    using Regs = TaskRegs<VEC, PAIRWISE>;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // request the rows of CTA-local task `lt` (ids from the shared-memory ring)
+    auto issue = [&](Regs& r, int lt) {
+      r.s = lt / tasks;
+      r.q = lt - r.s * tasks;
+      const int slot = r.s % kRing;
+      mbar_wait(&idsf[slot], (uint32_t)((r.s / kRing) & 1));
+      const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
+      const float* lab = reinterpret_cast<const float*>(ids + (size_t)R * L.slice);
+      const int j = r.q * IPW + grp;
+      const bool live = j < cnt;
+      const int jj = live ? j : 0;
+      const int64_t iu = ids[jj], ia = ids[L.slice + jj], ib = PAIRWISE ? ids[2 * L.slice + jj] : 0;
+      r.label = (!PAIRWISE && a.label != nullptr) ? lab[jj] : 0.f;
+      const bool oku = live && (uint64_t)iu < (uint64_t)a.n_users;
+      const bool oka = live && (uint64_t)ia < (uint64_t)a.n_items;
+      const bool okb = PAIRWISE && live && (uint64_t)ib < (uint64_t)a.n_items;
+      if (live && a.oob && sub == 0 && (!oku || !oka || (PAIRWISE && !okb))) *a.oob = 1;
+      r.iu = oku ? (int)iu : -1;
+      r.ia = oka ? (int)ia : -1;
+      r.ib = okb ? (int)ib : -1;
+      r.sb = live ? 1.f : 0.f;  // until phase A overwrites it with the negative score: "this lane owns an interaction"
+      const float* pu = a.user_tab + (int64_t)(oku ? iu : 0) * row_f;
+      const float* pa = a.item_tab + (int64_t)(oka ? ia : 0) * row_f;
+      const float* pb = a.item_tab + (int64_t)(okb ? ib : 0) * row_f;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int c = sub + v * LPR;
+        const bool on = c < a.nv;
+        r.u[v] = (oku && on) ? ldcg_row4(pu, c) : z4;
+        r.a[v] = (oka && on) ? ldcg_row4(pa, c) : z4;
+        if (PAIRWISE) r.b[v] = (okb && on) ? ldcg_row4(pb, c) : z4;
+      }
+    };
+
+    // phase A: score, loss term, squared norms -> task partial (consumes the row loads)
+    auto phase_a = [&](Regs& r) {
+      const int slot = r.s % kRing;
+      float da = 0.f, db = 0.f, uu = 0.f, aa = 0.f;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        da += dot4(r.u[v], r.a[v]);
+        uu += dot4(r.u[v], r.u[v]);
+        aa += dot4(r.a[v], r.a[v]);
+        if (PAIRWISE) db += dot4(r.u[v], r.b[v]);
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) {
+        da += __shfl_xor_sync(0xffffffffu, da, o);
+        uu += __shfl_xor_sync(0xffffffffu, uu, o);
+        aa += __shfl_xor_sync(0xffffffffu, aa, o);
+        if (PAIRWISE) db += __shfl_xor_sync(0xffffffffu, db, o);
+      }
+      const bool live = r.sb != 0.f;
+      r.sa = da;
+      r.sb = db;
+      float term = 0.f;
+      if (live) {
+        if (PAIRWISE) {
+          term = -logf(a.gamma + sigmoidf_(da - db));
+        } else if (a.loss_kind == XDR_LOSS_MSE) {
+          const float d = da - r.label;
+          term = d * d;
+        } else if (a.loss_kind == XDR_LOSS_BCE_SIGMOID) {
+          const float p = sigmoidf_(da);
+          term = -(r.label * fmaxf(logf(p), -100.f) + (1.f - r.label) * fmaxf(logf(1.f - p), -100.f));
+        }
+      } else {
+        uu = 0.f;
+        aa = 0.f;
+      }
+      // sum over the IPW interactions of the task (fixed shuffle tree -> deterministic)
+#pragma unroll
+      for (int o = 16; o >= LPR; o >>= 1) {
+        term += __shfl_xor_sync(0xffffffffu, term, o);
+        uu += __shfl_xor_sync(0xffffffffu, uu, o);
+        aa += __shfl_xor_sync(0xffffffffu, aa, o);
+      }
+      if (lane == 0) {
+        part[slot * L.tasks + r.q] = make_float4(term, uu, aa, 0.f);
+        mbar_arrive(&adone[slot]);  // release: the partial is visible to the reducer
+      }
+    };
+
+    // phase B: wait for the step's norm factors, form the row gradients from the rows still in registers, scatter-add
+    auto phase_b = [&](Regs& r) {
+      const int slot = r.s % kRing;
+      const uint32_t par = (uint32_t)((r.s / kRing) & 1);
+      mbar_wait(&normf[slot], par);
+      const float2 nf = norms[slot];
+      const float cu = nf.x, ci = nf.y;
+      float c = 0.f;  // g * dL_data/dscore_a  (BPR: dscore_b = -c)
+      if (PAIRWISE) {
+        const float sg = sigmoidf_(r.sa - r.sb);
+        c = -g * inv_b * (sg * (1.f - sg)) / (a.gamma + sg);
+      } else if (a.loss_kind == XDR_LOSS_MSE) {
+        c = g * inv_b * 2.f * (r.sa - r.label);
+      } else if (a.loss_kind == XDR_LOSS_BCE_SIGMOID) {
+        const float p = sigmoidf_(r.sa);
+        const float pq = p * (1.f - p);
+        c = g * inv_b * (p - r.label) / fmaxf(pq, 1e-12f) * pq;
+      }
+      const bool oku = r.iu >= 0, oka = r.ia >= 0, okb = PAIRWISE && r.ib >= 0;
+      float* du = a.user_dst + (int64_t)r.iu * row_f;
+      float* dia = a.item_dst + (int64_t)r.ia * row_f;
+      float* dib = a.item_dst + (int64_t)r.ib * row_f;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int cidx = sub + v * LPR;
+        if (cidx >= a.nv) continue;
+        if (PAIRWISE) {
+          if (oku) red_add4(du, cidx, axpy4(cu, r.u[v], scale4(c, sub4(r.a[v], r.b[v]))));
+          if (oka) red_add4(dia, cidx, axpy4(ci, r.a[v], scale4(c, r.u[v])));
+          if (okb) red_add4(dib, cidx, scale4(-c, r.u[v]));
+        } else {
+          if (oku) red_add4(du, cidx, axpy4(cu, r.u[v], scale4(c, r.a[v])));
+          if (oka) red_add4(dia, cidx, axpy4(ci, r.a[v], scale4(c, r.u[v])));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ifree[slot]);  // this task no longer needs the step's id tile / partial slot
+    };
+
+    // Two register sets per warp.  Phase A runs one round ahead of phase B, so the norm exchange of a step overlaps
+    // the gathers of the following ones:   B(r0) issue(r0') B(r1) issue(r1') A(r0') A(r1') ...
+    // Hazard rule: before waiting for the norms of step s, every task of this warp with step <= s must have run
+    // phase A (the norms of s cannot complete without it).
+    Regs r0, r1;
+    bool live0 = false, live1 = false;  // the set holds a task (issued or scored)
+    bool iss0 = false, iss1 = false;    // ... whose rows are requested but phase A has not run yet
+    int next = w;
+    if (next < total) { issue(r0, next); next += n_workers; live0 = iss0 = true; }
+    if (next < total) { issue(r1, next); next += n_workers; live1 = iss1 = true; }
+    while (live0 || live1) {
+      if (iss0) { phase_a(r0); iss0 = false; }
+      if (iss1) { phase_a(r1); iss1 = false; }
+      if (live0) {
+        phase_b(r0);
+        live0 = false;
+        if (next < total) { issue(r0, next); next += n_workers; live0 = iss0 = true; }
+      }
+      if (live1) {
+        if (iss0 && r0.s <= r1.s) { phase_a(r0); iss0 = false; }
+        phase_b(r1);
+        live1 = false;
+        if (next < total) { issue(r1, next); next += n_workers; live1 = iss1 = true; }
+      }
     }
   }
 }
 
-template <bool PAIRWISE>
-static size_t steps_smem_bytes(int slice, int nv) {
-  StageLayout<PAIRWISE> L(slice, nv);
-  return kHeaderBytes + 4 * sizeof(float) * (kConsumerWarps + 2) + 128 + (size_t)kStages * L.bytes();
-}
-
 struct StepsPlan {
-  int grid, slice;
+  int grid, slice, lpr, vec;
   size_t smem;
 };
 
-// Choose the slice so that kStages stages fit in shared memory; returns false when the configuration does not fit
-// the persistent kernel (large batch or wide rows) -- the caller then uses the per-step kernels.
+// Lanes per row / float4 columns per lane for a row of nv float4s: at most 2 columns per lane so that two tasks
+// (2 x 3 rows) stay in registers.  Returns false for row widths this kernel does not specialise.
 static bool plan_steps(int64_t batch, int nv, bool pairwise, StepsPlan* plan) {
+  int lpr, vec;
+  if (nv <= 8) { lpr = 8; vec = 1; }
+  else if (nv <= 16) { lpr = 8; vec = 2; }
+  else if (nv <= 32) { lpr = 16; vec = 2; }
+  else if (nv <= 64) { lpr = 32; vec = 2; }
+  else return false;
   const int sms = sm_count();
   int64_t slice = (batch + sms - 1) / sms;
-  slice = (slice + 3) & ~(int64_t)3;  // multiple of 4: id tiles 32-byte granular, one warp pass = 4 interactions
+  slice = (slice + 3) & ~(int64_t)3;  // multiple of 4: 16-byte granular TMA id tiles, whole warp tasks
   if (slice < 4) slice = 4;
   const int64_t grid = (batch + slice - 1) / slice;
-  const size_t smem = pairwise ? steps_smem_bytes<true>((int)slice, nv) : steps_smem_bytes<false>((int)slice, nv);
-  if (smem > 220 * 1024 || grid > sms) return false;
+  const int ipw = 32 / lpr;
+  SmemLayout L((int)slice, pairwise ? 3 : 2, (int)((slice + ipw - 1) / ipw));
+  // a worker runs phase A of at most two tasks before it waits for a step's norms: every step's tasks must fit
+  // 2 x workers, else the step could never complete (larger batches use the per-step kernels)
+  if ((slice + ipw - 1) / ipw > 2 * kWorkerWarps) return false;
+  if (L.bytes() > 200 * 1024 || grid > sms || grid > 32 * kMaxCtaPerLane) return false;
   plan->grid = (int)grid;
   plan->slice = (int)slice;
-  plan->smem = smem;
+  plan->lpr = lpr;
+  plan->vec = vec;
+  plan->smem = L.bytes();
   return true;
 }
 
-template <int VEC, bool PW>
+template <int LPR, int VEC, bool PW>
 static int launch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_t s) {
-  auto kern = train_steps_kernel<VEC, PW>;
+  auto kern = train_steps_kernel<LPR, VEC, PW>;
   XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
   kern<<<plan.grid, kStepThreads, plan.smem, s>>>(a);
   return XDR_OK;
+}
+
+template <bool PW>
+static int dispatch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_t s) {
+  if (plan.lpr == 8 && plan.vec == 1) return launch_steps<8, 1, PW>(a, plan, s);
+  if (plan.lpr == 8 && plan.vec == 2) return launch_steps<8, 2, PW>(a, plan, s);
+  if (plan.lpr == 16) return launch_steps<16, 2, PW>(a, plan, s);
+  return launch_steps<32, 2, PW>(a, plan, s);
 }
 
 }  // namespace xdr
@@ -426,9 +499,7 @@ extern "C" {
 
 size_t xdr_steps_workspace_bytes(int n_steps) {
   if (n_steps < 0) return 0;
-  // [n_steps] arrival counters (padded to 256 B) + [n_steps][<= 2048 CTAs -> sm count] float4 partials
-  const size_t counters = (((size_t)n_steps * sizeof(unsigned int)) + 255) & ~(size_t)255;
-  return counters + (size_t)n_steps * (size_t)sm_count() * sizeof(float4);
+  return (size_t)n_steps * (size_t)sm_count() * 3 * sizeof(unsigned long long);
 }
 
 int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
@@ -447,16 +518,15 @@ int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_user
   XDR_REQUIRE(aligned16(user_tab) && aligned16(item_tab) && aligned16(user_dst) && aligned16(item_dst),
               "xdr_train_steps: tables must be 16-byte aligned");
   XDR_REQUIRE(step_stride >= batch, "xdr_train_steps: step_stride=%lld < batch", (long long)step_stride);
-  // TMA bulk copies of the id tiles need 16-byte aligned sources: even batch/stride and aligned base pointers
-  XDR_REQUIRE((batch % 4) == 0 && (step_stride % 4) == 0 && aligned16(user) && aligned16(item_a) &&
-                  (!pairwise || aligned16(item_b)) && (label == nullptr || aligned16(label)),
-              "xdr_train_steps: batch and step_stride must be multiples of 4 and the id arrays 16-byte aligned");
   XDR_REQUIRE(steps_ws_bytes >= xdr_steps_workspace_bytes(n_steps), "xdr_train_steps: steps_ws too small (%zu < %zu)",
               steps_ws_bytes, xdr_steps_workspace_bytes(n_steps));
   StepsPlan plan;
-  if (!plan_steps(batch, dim / 4, pairwise != 0, &plan)) {
-    set_error("xdr_train_steps: batch=%lld dim=%d does not fit the persistent kernel's shared-memory stages; "
-              "use the per-step entry points",
+  // TMA bulk copies of the id tiles need 16-byte aligned sources and sizes
+  const bool tma_ok = (batch % 4) == 0 && (step_stride % 4) == 0 && aligned16(user) && aligned16(item_a) &&
+                      (!pairwise || aligned16(item_b)) && (label == nullptr || aligned16(label));
+  if (!tma_ok || !plan_steps(batch, dim / 4, pairwise != 0, &plan)) {
+    set_error("xdr_train_steps: batch=%lld dim=%d (batch and step_stride must be multiples of 4, id arrays 16-byte "
+              "aligned, one CTA slice of ids must fit shared memory); use the per-step entry points",
               (long long)batch, dim);
     return XDR_ERR_UNSUPPORTED;
   }
@@ -465,13 +535,11 @@ int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_user
   a.user = user; a.item_a = item_a; a.item_b = item_b; a.label = label; a.step_stride = step_stride; a.batch = batch;
   a.n_steps = n_steps; a.loss_kind = loss_kind; a.gamma = gamma; a.reg_weight = reg_weight; a.out8 = out8;
   a.grad_loss = grad_loss; a.scale = scale; a.user_dst = user_dst; a.item_dst = item_dst; a.slice = plan.slice; a.oob = oob;
-  const size_t counters = (((size_t)n_steps * sizeof(unsigned int)) + 255) & ~(size_t)255;
-  a.arrive = reinterpret_cast<unsigned int*>(steps_ws);
-  a.partials = reinterpret_cast<float4*>(reinterpret_cast<char*>(steps_ws) + counters);
+  a.words = reinterpret_cast<unsigned long long*>(steps_ws);
   cudaStream_t s = (cudaStream_t)stream;
-  XDR_CUDA_OK(cudaMemsetAsync(steps_ws, 0, counters, s));
-  int rc = XDR_OK;
-  XDR_DISPATCH_VEC(a.nv, (rc = pairwise ? launch_steps<VEC, true>(a, plan, s) : launch_steps<VEC, false>(a, plan, s)));
+  // step tags start at 1, so zeroed words can never match: no stale data from an earlier launch is ever accepted
+  XDR_CUDA_OK(cudaMemsetAsync(steps_ws, 0, (size_t)n_steps * plan.grid * 3 * sizeof(unsigned long long), s));
+  const int rc = pairwise ? dispatch_steps<true>(a, plan, s) : dispatch_steps<false>(a, plan, s);
   if (rc != XDR_OK) return rc;
   XDR_LAUNCH_OK();
   return XDR_OK;

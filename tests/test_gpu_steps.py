@@ -26,7 +26,9 @@ def setup(nu, ni, dim, K, B, seed, zipf=None, std=0.1):
 
 
 @pytest.mark.parametrize('K,B,dim,zipf', [(1, 8192, 64, None), (7, 8192, 64, None), (5, 4096, 64, 1.1), (9, 256, 64, None),
-                                          (3, 4, 64, None), (6, 1000, 32, None), (4, 2048, 128, None), (3, 512, 96, None)])
+                                          (3, 4, 64, None), (6, 1000, 32, None), (4, 2048, 128, None), (3, 512, 96, None),
+                                          (40, 8192, 64, None), (3, 16384, 64, None), (20, 148 * 4, 64, None), (4, 23680, 64, None),
+                                          (5, 2052, 256, None), (33, 36, 16, None)])
 def test_train_steps_bpr_matches_oracle_per_step(K, B, dim, zipf):
     from recbole_cdr_b200 import ops
     nu, ni = 3000, 4000
@@ -95,11 +97,12 @@ def test_train_steps_strided_id_buffer_and_unsupported_shapes():
     ref8, gu2, gi2 = ops.train_steps(ut.to(dev()), it.to(dev()), u.to(dev()), ip.to(dev()), ineg.to(dev()), reg_weight=0.01)
     assert torch.equal(out8, ref8)
     torch.testing.assert_close(gu, gu2, rtol=1e-5, atol=1e-9)
-    assert not ops.train_steps_supported(65536, 64, True)      # slice does not fit 4 smem stages
+    assert ops.train_steps_supported(16384, 64, True)
+    assert not ops.train_steps_supported(65536, 64, True)      # more than 2 tasks per worker per step: per-step kernels
     assert not ops.train_steps_supported(8190, 64, True)       # batch % 4 != 0 (TMA id tiles need 16-byte alignment)
-    big = torch.zeros(1, 65536, dtype=torch.int64, device=dev())
+    odd = torch.zeros(1, 8190, dtype=torch.int64, device=dev())
     with pytest.raises(_lib.XdrError, match='per-step'):
-        ops.train_steps(ut.to(dev()), it.to(dev()), big, big, big)
+        ops.train_steps(ut.to(dev()), it.to(dev()), odd, odd, odd)
 
 
 def test_fused_sgd_steps_train():

@@ -18,8 +18,9 @@
 //             an 8-deep shared-memory ring, several steps ahead of the workers
 //   warp 1    publisher: per step, sums the CTA's task partials (fixed order) and publishes them to global memory as
 //             8-byte {value, step-tag} words (no fences: data and flag travel in one atomic store)
-//   warps 2,3 gatherers (even / odd steps): poll all CTAs' words of a step (one batch of loads per poll round),
-//             reduce in fp64 in a fixed order, hand the step's norm factors to the workers through shared memory
+//   warps 2,3 gatherers (even / odd steps): the step's root CTA (rotating, s mod grid) polls all CTAs' words (one
+//             batch of loads per poll round), reduces in fp64 in a fixed order and republishes two result words;
+//             every other CTA polls just those; the norm factors reach the workers through shared memory
 //   warps 4.. workers: a task = 32/LPR interactions of one step.  LPR lanes own one interaction; each lane keeps
 //             VEC float4 columns of the 2-3 rows IN REGISTERS from the gather (LDG.128, L1-bypassing) through
 //             score/loss (shuffle reductions) until the step's norms arrive, then forms the row gradients and
@@ -58,9 +59,10 @@ struct StepsArgs {
   float scale;
   float* user_dst;
   float* item_dst;
-  unsigned long long* words;  // [n_steps][gridDim.x][3] {fp32 value, step tag}; zeroed by the host wrapper
+  unsigned long long* words;  // [n_steps][gridDim.x][3] partials then [n_steps][2] results, {fp32, step tag}; host-zeroed
   int slice;                  // S: interactions per CTA per step (multiple of 4)
   int32_t* oob;
+  unsigned long long* trace;  // optional [n_steps][grid][8] globaltimer stamps (debug; NULL in production)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -73,6 +75,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
@@ -93,6 +106,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -191,6 +209,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs 
       const int slot = s % kRing;
       const uint32_t par = (uint32_t)((s / kRing) & 1);
       mbar_wait(&adone[slot], par);
+      if (a.trace && lane == 0) a.trace[((size_t)s * n_cta + blockIdx.x) * 8 + 0] = gtime();
       float p0 = 0.f, p1 = 0.f, p2 = 0.f;
       for (int q = lane; q < tasks; q += 32) {
         const float4 v = part[slot * L.tasks + q];
@@ -215,51 +234,57 @@ __global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs 
     const unsigned int n_cta = gridDim.x;
     const float inv_b = 1.0f / (float)a.batch;
     const float g = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f) * a.scale;
+    unsigned long long* finals = a.words + (size_t)a.n_steps * n_cta * 3;  // [n_steps][2] {factor, tag}
     for (int s = warp - 2; s < a.n_steps; s += 2) {
       const int slot = s % kRing;
       const unsigned int tag = (unsigned int)(s + 1);
-      const unsigned long long* base = a.words + (size_t)s * n_cta * 3;
-      unsigned long long wv[kMaxCtaPerLane][3];
-      bool all_ok;
-      do {
+      float cu = 0.f, ci = 0.f;
+      if ((unsigned int)s % n_cta == blockIdx.x) {
+        // ---- root of step s (rotates over the CTAs): gather every CTA's partial words, reduce, republish
+        const unsigned long long* base = a.words + (size_t)s * n_cta * 3;
+        unsigned long long wv[kMaxCtaPerLane][3];
+        bool all_ok;
+        do {
+#pragma unroll
+          for (int i = 0; i < kMaxCtaPerLane; ++i) {
+            const unsigned int c = lane + 32u * i;
+            if (c < n_cta) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) wv[i][k] = ld_relaxed_u64(base + (size_t)c * 3 + k);
+            }
+          }
+          all_ok = true;
+#pragma unroll
+          for (int i = 0; i < kMaxCtaPerLane; ++i) {
+            const unsigned int c = lane + 32u * i;
+            if (c < n_cta) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) all_ok = all_ok && ((unsigned int)(wv[i][k] >> 32) == tag);
+            }
+          }
+          all_ok = __all_sync(0xffffffffu, all_ok);
+        } while (!all_ok);
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll
         for (int i = 0; i < kMaxCtaPerLane; ++i) {
           const unsigned int c = lane + 32u * i;
           if (c < n_cta) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) wv[i][k] = ld_relaxed_u64(base + (size_t)c * 3 + k);
+            t0 += (double)__uint_as_float((unsigned int)wv[i][0]);
+            t1 += (double)__uint_as_float((unsigned int)wv[i][1]);
+            t2 += (double)__uint_as_float((unsigned int)wv[i][2]);
           }
         }
-        all_ok = true;
-#pragma unroll
-        for (int i = 0; i < kMaxCtaPerLane; ++i) {
-          const unsigned int c = lane + 32u * i;
-          if (c < n_cta) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) all_ok = all_ok && ((unsigned int)(wv[i][k] >> 32) == tag);
-          }
-        }
-        all_ok = __all_sync(0xffffffffu, all_ok);
-      } while (!all_ok);
-      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-#pragma unroll
-      for (int i = 0; i < kMaxCtaPerLane; ++i) {
-        const unsigned int c = lane + 32u * i;
-        if (c < n_cta) {
-          t0 += (double)__uint_as_float((unsigned int)wv[i][0]);
-          t1 += (double)__uint_as_float((unsigned int)wv[i][1]);
-          t2 += (double)__uint_as_float((unsigned int)wv[i][2]);
-        }
-      }
-      t0 = warp_sum(t0);
-      t1 = warp_sum(t1);
-      t2 = warp_sum(t2);
-      if (lane == 0) {
+        t0 = warp_sum(t0);
+        t1 = warp_sum(t1);
+        t2 = warp_sum(t2);
         const float nu = (float)sqrt(t1), ni = (float)sqrt(t2);
         // d(reg_weight * (||U||_F + ||I||_F)/B)/dU_r = reg_weight/(B*||U||_F) * U_r   (torch: 0 when the norm is 0)
-        norms[slot] = make_float2((a.reg_weight != 0.f && nu > 0.f) ? g * a.reg_weight * inv_b / nu : 0.f,
-                                  (a.reg_weight != 0.f && ni > 0.f) ? g * a.reg_weight * inv_b / ni : 0.f);
-        if (blockIdx.x == 0) {
+        cu = (a.reg_weight != 0.f && nu > 0.f) ? g * a.reg_weight * inv_b / nu : 0.f;
+        ci = (a.reg_weight != 0.f && ni > 0.f) ? g * a.reg_weight * inv_b / ni : 0.f;
+        if (lane < 2)
+          st_relaxed_u64(finals + (size_t)s * 2 + lane,
+                         ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(lane == 0 ? cu : ci));
+        if (lane == 0) {
           const float data = (float)(t0 / (double)a.batch);
           const float reg = (float)(((double)nu + (double)ni) / (double)a.batch);
           float* o = a.out8 + (size_t)s * 8;
@@ -272,6 +297,24 @@ __global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs 
           o[6] = 0.f;
           o[7] = 0.f;
         }
+      } else {
+        // ---- everyone else polls the root's two result words (one 16-byte line, one lane)
+        unsigned long long f0 = 0, f1 = 0;
+        if (lane == 0) {
+          const unsigned long long* f = finals + (size_t)s * 2;
+          for (;;) {
+            f0 = ld_relaxed_u64(f);
+            f1 = ld_relaxed_u64(f + 1);
+            if ((unsigned int)(f0 >> 32) == tag && (unsigned int)(f1 >> 32) == tag) break;
+            __nanosleep(64);
+          }
+        }
+        cu = __uint_as_float((unsigned int)__shfl_sync(0xffffffffu, f0, 0));
+        ci = __uint_as_float((unsigned int)__shfl_sync(0xffffffffu, f1, 0));
+      }
+      if (a.trace && lane == 0) a.trace[((size_t)s * n_cta + blockIdx.x) * 8 + 1] = gtime();
+      if (lane == 0) {
+        norms[slot] = make_float2(cu, ci);
         mbar_arrive(&normf[slot]);  // release: the norms are visible to every worker that observes this phase
       }
       __syncwarp();
@@ -298,6 +341,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs 
       r.q = lt - r.s * tasks;
       const int slot = r.s % kRing;
       mbar_wait(&idsf[slot], (uint32_t)((r.s / kRing) & 1));
+      if (a.trace && lane == 0 && r.q == 0) a.trace[((size_t)r.s * gridDim.x + blockIdx.x) * 8 + 2] = gtime();
       const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
       const float* lab = reinterpret_cast<const float*>(ids + (size_t)R * L.slice);
       const int j = r.q * IPW + grp;
@@ -372,6 +416,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs 
       if (lane == 0) {
         part[slot * L.tasks + r.q] = make_float4(term, uu, aa, 0.f);
         mbar_arrive(&adone[slot]);  // release: the partial is visible to the reducer
+        if (a.trace && r.q == 0) a.trace[((size_t)r.s * gridDim.x + blockIdx.x) * 8 + 3] = gtime();
       }
     };
 
@@ -379,7 +424,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs 
     auto phase_b = [&](Regs& r) {
       const int slot = r.s % kRing;
       const uint32_t par = (uint32_t)((r.s / kRing) & 1);
+      if (a.trace && lane == 0 && r.q == 0) a.trace[((size_t)r.s * gridDim.x + blockIdx.x) * 8 + 4] = gtime();
       mbar_wait(&normf[slot], par);
+      if (a.trace && lane == 0 && r.q == 0) a.trace[((size_t)r.s * gridDim.x + blockIdx.x) * 8 + 5] = gtime();
       const float2 nf = norms[slot];
       const float cu = nf.x, ci = nf.y;
       float c = 0.f;  // g * dL_data/dscore_a  (BPR: dscore_b = -c)
@@ -411,6 +458,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs 
         }
       }
       __syncwarp();
+      if (a.trace && lane == 0 && r.q == 0) a.trace[((size_t)r.s * gridDim.x + blockIdx.x) * 8 + 6] = gtime();
       if (lane == 0) mbar_arrive(&ifree[slot]);  // this task no longer needs the step's id tile / partial slot
     };
 
@@ -433,7 +481,12 @@ __global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs 
         if (next < total) { issue(r0, next); next += n_workers; live0 = iss0 = true; }
       }
       if (live1) {
-        if (iss0 && r0.s <= r1.s) { phase_a(r0); iss0 = false; }
+        // never block on norms while holding requested-but-unscored rows: other CTAs (and the hazard rule: tasks of
+        // this warp with step <= r1.s) may be waiting for exactly that partial
+        if (iss0 && (r0.s <= r1.s || !mbar_test(&normf[r1.s % kRing], (uint32_t)((r1.s / kRing) & 1)))) {
+          phase_a(r0);
+          iss0 = false;
+        }
         phase_b(r1);
         live1 = false;
         if (next < total) { issue(r1, next); next += n_workers; live1 = iss1 = true; }
@@ -491,15 +544,22 @@ static int dispatch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_
   return launch_steps<32, 2, PW>(a, plan, s);
 }
 
+static unsigned long long* g_trace = nullptr;  // debug only, see xdr_debug_set_steps_trace
+
 }  // namespace xdr
 
 using namespace xdr;
 
 extern "C" {
 
+// Debug hook (not part of the drop-in surface): device buffer of n_steps*grid*8 u64 that the next xdr_train_steps
+// launches fill with globaltimer stamps: [0] CTA partial ready, [1] all CTAs' partials seen, [2] task 0 rows
+// requested, [3] task 0 scored, [4] task 0 starts waiting for norms, [5] norms arrived, [6] scatter issued.
+XDR_API void xdr_debug_set_steps_trace(void* buf) { g_trace = reinterpret_cast<unsigned long long*>(buf); }
+
 size_t xdr_steps_workspace_bytes(int n_steps) {
   if (n_steps < 0) return 0;
-  return (size_t)n_steps * (size_t)sm_count() * 3 * sizeof(unsigned long long);
+  return (size_t)n_steps * ((size_t)sm_count() * 3 + 2) * sizeof(unsigned long long);
 }
 
 int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
@@ -536,9 +596,10 @@ int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_user
   a.n_steps = n_steps; a.loss_kind = loss_kind; a.gamma = gamma; a.reg_weight = reg_weight; a.out8 = out8;
   a.grad_loss = grad_loss; a.scale = scale; a.user_dst = user_dst; a.item_dst = item_dst; a.slice = plan.slice; a.oob = oob;
   a.words = reinterpret_cast<unsigned long long*>(steps_ws);
+  a.trace = g_trace;
   cudaStream_t s = (cudaStream_t)stream;
   // step tags start at 1, so zeroed words can never match: no stale data from an earlier launch is ever accepted
-  XDR_CUDA_OK(cudaMemsetAsync(steps_ws, 0, (size_t)n_steps * plan.grid * 3 * sizeof(unsigned long long), s));
+  XDR_CUDA_OK(cudaMemsetAsync(steps_ws, 0, (size_t)n_steps * ((size_t)plan.grid * 3 + 2) * sizeof(unsigned long long), s));
   const int rc = pairwise ? dispatch_steps<true>(a, plan, s) : dispatch_steps<false>(a, plan, s);
   if (rc != XDR_OK) return rc;
   XDR_LAUNCH_OK();

@@ -15,30 +15,37 @@
 //
 //   grid      one CTA per SM (persistent); CTA c owns interactions [c*S, (c+1)*S) of EVERY step
 //   warp 0    producer: TMA bulk copies (cp.async.bulk -> UBLKCP) of the CTA's id tiles (and labels) of step t into
-//             an 8-deep shared-memory ring, several steps ahead of the workers
+//             an 8-deep shared-memory ring, several steps ahead of everyone else
 //   warp 1    publisher: per step, sums the CTA's task partials (fixed order) and publishes them to global memory as
 //             8-byte {value, step-tag} words (no fences: data and flag travel in one atomic store)
 //   warps 2,3 gatherers (even / odd steps): the step's root CTA (rotating, s mod grid) polls all CTAs' words (one
 //             batch of loads per poll round), reduces in fp64 in a fixed order and republishes two result words;
-//             every other CTA polls just those; the norm factors reach the workers through shared memory
-//   warps 4.. workers: a task = 32/LPR interactions of one step.  LPR lanes own one interaction; each lane keeps
-//             VEC float4 columns of the 2-3 rows IN REGISTERS from the gather (LDG.128, L1-bypassing) through
-//             score/loss (shuffle reductions) until the step's norms arrive, then forms the row gradients and
-//             issues REDG.E.ADD.F32x4.  Each warp keeps TWO tasks in flight (rows of the next task are requested
-//             before the current task waits for its norms), so the ~2 steps of latency stay covered.
-//   All hand-offs are mbarriers (ids landed / task partial written / norms ready / id slot free); no CTA-wide
-//   barrier and no grid-wide barrier anywhere.
+//             every other CTA polls just those; the norm factors reach the scatter side through shared memory
+//   STAGED kernel (the default; profiles/r1_steps_trace.md shows why gather and scatter must be decoupled):
+//     loaders   a task = 32/LPR interactions of one step; LPR lanes own one interaction.  Rows are gathered with
+//               LDG.128 (L1-bypassing) into registers, two tasks in flight per warp; score / loss term / squared
+//               norms by shuffles; then rows + scores are stashed in a 4-deep shared-memory stage ring.  Loaders
+//               never wait for norms, so the gather stream (and DRAM) stays busy during the norm exchange.
+//     scatterers  when a step's norm factors arrive: rows from the stage ring, row gradients, REDG.E.ADD.F32x4.
+//   REGISTER kernel (fallback when 3 stages of a CTA slice do not fit shared memory, e.g. dim 128 at B=8192):
+//     workers keep the rows in registers from gather to scatter (two tasks per warp) and wait for the norms.
+//   All hand-offs are mbarriers (ids landed / partial written / norms ready / slots free); no CTA-wide barrier and
+//   no grid-wide barrier anywhere.
 //
 // HBM roofline: 1560 algorithmic bytes per BPR interaction at dim 64 (ids + 3 rows gathered + 3 rows scattered).
 #include "xdr_common.cuh"
 
 namespace xdr {
 
-constexpr int kWorkerWarps = 20;
-constexpr int kServiceWarps = 4;                       // producer, publisher, two gatherers
-constexpr int kStepThreads = (kWorkerWarps + kServiceWarps) * 32;
-constexpr int kMaxCtaPerLane = 5;                      // gatherer lanes poll <= 5 CTAs each: grid <= 160
-constexpr int kRing = 8;                               // id-tile / partial / norm ring depth (steps)
+constexpr int kServiceWarps = 4;   // producer, publisher, two gatherers
+constexpr int kWorkerWarps = 20;   // register kernel: workers
+constexpr int kLoaderWarps = 12;   // staged kernel: loaders ...
+constexpr int kScatterWarps = 6;   // ... and scatterers
+constexpr int kRegThreads = (kServiceWarps + kWorkerWarps) * 32;
+constexpr int kStagedThreads = (kServiceWarps + kLoaderWarps + kScatterWarps) * 32;
+constexpr int kMaxCtaPerLane = 5;  // gatherer lanes poll <= 5 CTAs each: grid <= 160
+constexpr int kMaxStages = 4;      // staged kernel: stage ring depth (3 or 4)
+constexpr int kRing = 8;            // id-tile / partial / norm ring depth (steps)
 
 struct StepsArgs {
   const float* user_tab;
@@ -127,22 +134,38 @@ __device__ __forceinline__ float4 ldcg_row4(const float* row, int col4) {
 
 // ---- shared-memory layout -------------------------------------------------------------------------------------------
 struct SmemLayout {
-  int slice, rows_per, tasks;  // S, 2|3, tasks per step per CTA (upper bound)
-  __host__ __device__ SmemLayout(int s, int r, int t) : slice(s), rows_per(r), tasks(t) {}
-  // [0, 256): 4 x kRing mbarriers.  [256, 320): norms [kRing][2].  then partials, then the id ring.
+  int slice, rows_per, tasks, row_f, stages;  // S, 2|3, tasks per step per CTA (upper bound), floats per row, stage count
+  __host__ __device__ SmemLayout(int s, int r, int t, int rf = 0, int ns = 0)
+      : slice(s), rows_per(r), tasks(t), row_f(rf), stages(ns) {}
+  // [0, 320): 4 x kRing + kMaxStages mbarriers.  [320, 384): norms [kRing][2].  then partials, id ring, stage ring.
   __host__ __device__ size_t bars_off() const { return 0; }
-  __host__ __device__ size_t norms_off() const { return 256; }
-  __host__ __device__ size_t part_off() const { return 320; }
+  __host__ __device__ size_t norms_off() const { return 320; }
+  __host__ __device__ size_t part_off() const { return 384; }
   __host__ __device__ size_t ids_off() const {
     return (part_off() + (size_t)kRing * tasks * sizeof(float4) + 127) & ~(size_t)127;
   }
   __host__ __device__ size_t ids_slot_bytes() const {  // ids [rows_per][S] int64 + labels [S] fp32
     return (((size_t)rows_per * slice * 8 + (size_t)slice * 4) + 127) & ~(size_t)127;
   }
-  __host__ __device__ size_t bytes() const { return ids_off() + (size_t)kRing * ids_slot_bytes(); }
+  __host__ __device__ size_t stage_off() const { return ids_off() + (size_t)kRing * ids_slot_bytes(); }
+  __host__ __device__ size_t stage_slot_bytes() const {  // rows [rows_per][S][row_f] fp32 + scores [2][S] fp32
+    return (((size_t)rows_per * slice * row_f * 4 + (size_t)2 * slice * 4) + 127) & ~(size_t)127;
+  }
+  __host__ __device__ size_t bytes() const { return stage_off() + (size_t)stages * stage_slot_bytes(); }
 };
 
-// One task's registers: ids, validity, the rows (VEC float4 columns per lane) and the scores.
+struct Bars {
+  uint64_t *idsf, *ifree, *adone, *normf, *sfree;
+  __device__ explicit Bars(unsigned char* smem) {
+    idsf = reinterpret_cast<uint64_t*>(smem);  // id tile landed        (tx barrier)
+    ifree = idsf + kRing;                      // id slot free          (count = consumers of the ids per step)
+    adone = ifree + kRing;                     // task partials written (count = tasks)
+    normf = adone + kRing;                     // norms ready           (count = 1)
+    sfree = normf + kRing;                     // stage slot free       (count = scatter warps)   [kMaxStages]
+  }
+};
+
+// One task's registers: ids, the rows (VEC float4 columns per lane) and the scores.
 template <int VEC, bool PAIRWISE>
 struct TaskRegs {
   float4 u[VEC], a[VEC], b[PAIRWISE ? VEC : 1];
@@ -151,324 +174,476 @@ struct TaskRegs {
   int s, q;
 };
 
-template <int LPR, int VEC, bool PAIRWISE>
-__global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs a) {
-  constexpr int IPW = 32 / LPR;  // interactions per warp task
+// ---- service warps (shared by both kernels) ---------------------------------------------------------------------------
+template <bool PAIRWISE>
+__device__ __forceinline__ void service_producer(const StepsArgs& a, const SmemLayout& L, const Bars& B,
+                                                 unsigned char* ids_ring, int64_t first, int cnt, int lane) {
   constexpr int R = PAIRWISE ? 3 : 2;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int64_t first = (int64_t)blockIdx.x * a.slice;
-  const int cnt = (int)min((int64_t)a.slice, a.batch - first);  // > 0: the host launches ceil(batch/slice) CTAs
-  const int tasks = (cnt + IPW - 1) / IPW;                      // tasks of this CTA per step
-  const SmemLayout L(a.slice, R, (a.slice + IPW - 1) / IPW);
-  uint64_t* idsf = reinterpret_cast<uint64_t*>(smem_raw + L.bars_off());  // id tile landed        (tx barrier)
-  uint64_t* ifree = idsf + kRing;                                         // id slot free          (count = tasks)
-  uint64_t* adone = ifree + kRing;                                        // task partials written (count = tasks)
-  uint64_t* normf = adone + kRing;                                        // norms ready           (count = 1)
-  float2* norms = reinterpret_cast<float2*>(smem_raw + L.norms_off());
-  float4* part = reinterpret_cast<float4*>(smem_raw + L.part_off());
-  unsigned char* ids_ring = smem_raw + L.ids_off();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_f = a.nv * 4;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kRing; ++i) {
-      mbar_init(&idsf[i], 1);
-      mbar_init(&ifree[i], (uint32_t)tasks);
-      mbar_init(&adone[i], (uint32_t)tasks);
-      mbar_init(&normf[i], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (lane != 0) return;
+  const uint32_t idb = (uint32_t)cnt * 8u, lbb = (uint32_t)cnt * 4u;  // cnt % 4 == 0 -> multiples of 16 bytes
+  const bool has_label = !PAIRWISE && a.label != nullptr;
+  for (int t = 0; t < a.n_steps; ++t) {
+    const int slot = t % kRing;
+    const uint32_t par = (uint32_t)((t / kRing) & 1);
+    int64_t* ids = reinterpret_cast<int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
+    float* lab = reinterpret_cast<float*>(ids + (size_t)R * L.slice);
+    mbar_wait(&B.ifree[slot], par ^ 1u);  // passes immediately the first time round the ring
+    const int64_t off = (int64_t)t * a.step_stride + first;
+    mbar_expect_tx(&B.idsf[slot], idb * R + (has_label ? lbb : 0u));
+    bulk_g2s(ids, a.user + off, idb, &B.idsf[slot]);
+    bulk_g2s(ids + L.slice, a.item_a + off, idb, &B.idsf[slot]);
+    if (PAIRWISE) bulk_g2s(ids + 2 * L.slice, a.item_b + off, idb, &B.idsf[slot]);
+    if (has_label) bulk_g2s(lab, a.label + off, lbb, &B.idsf[slot]);
   }
-  __syncthreads();
+}
 
-  if (warp == 0) {
-    // =========================================== producer: id tiles via TMA ===========================================
-    if (lane == 0) {
-      const uint32_t idb = (uint32_t)cnt * 8u, lbb = (uint32_t)cnt * 4u;  // cnt % 4 == 0 -> multiples of 16 bytes
-      const bool has_label = !PAIRWISE && a.label != nullptr;
-      for (int t = 0; t < a.n_steps; ++t) {
-        const int slot = t % kRing;
-        const uint32_t par = (uint32_t)((t / kRing) & 1);
-        int64_t* ids = reinterpret_cast<int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
-        float* lab = reinterpret_cast<float*>(ids + (size_t)R * L.slice);
-        mbar_wait(&ifree[slot], par ^ 1u);  // passes immediately the first time round the ring
-        const int64_t off = (int64_t)t * a.step_stride + first;
-        mbar_expect_tx(&idsf[slot], idb * R + (has_label ? lbb : 0u));
-        bulk_g2s(ids, a.user + off, idb, &idsf[slot]);
-        bulk_g2s(ids + L.slice, a.item_a + off, idb, &idsf[slot]);
-        if (PAIRWISE) bulk_g2s(ids + 2 * L.slice, a.item_b + off, idb, &idsf[slot]);
-        if (has_label) bulk_g2s(lab, a.label + off, lbb, &idsf[slot]);
-      }
+// per step: sum this CTA's task partials in a fixed order and publish them as three 8-byte {value, tag} words
+__device__ __forceinline__ void service_publisher(const StepsArgs& a, const SmemLayout& L, const Bars& B,
+                                                  const float4* part, int tasks, int lane) {
+  const unsigned int n_cta = gridDim.x;
+  for (int s = 0; s < a.n_steps; ++s) {
+    const int slot = s % kRing;
+    mbar_wait(&B.adone[slot], (uint32_t)((s / kRing) & 1));
+    if (a.trace && lane == 0) a.trace[((size_t)s * n_cta + blockIdx.x) * 8 + 0] = gtime();
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+    for (int q = lane; q < tasks; q += 32) {
+      const float4 v = part[slot * L.tasks + q];
+      p0 += v.x;
+      p1 += v.y;
+      p2 += v.z;
     }
-  } else if (warp == 1) {
-    // =========================================== publisher ============================================================
-    // per step: sum this CTA's task partials in a fixed order and publish them as three 8-byte {value, tag} words
-    const unsigned int n_cta = gridDim.x;
-    for (int s = 0; s < a.n_steps; ++s) {
-      const int slot = s % kRing;
-      const uint32_t par = (uint32_t)((s / kRing) & 1);
-      mbar_wait(&adone[slot], par);
-      if (a.trace && lane == 0) a.trace[((size_t)s * n_cta + blockIdx.x) * 8 + 0] = gtime();
-      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-      for (int q = lane; q < tasks; q += 32) {
-        const float4 v = part[slot * L.tasks + q];
-        p0 += v.x;
-        p1 += v.y;
-        p2 += v.z;
-      }
-      p0 = warp_sum(p0);
-      p1 = warp_sum(p1);
-      p2 = warp_sum(p2);
-      if (lane < 3) {
-        const float v = lane == 0 ? p0 : (lane == 1 ? p1 : p2);
-        st_relaxed_u64(a.words + ((size_t)s * n_cta + blockIdx.x) * 3 + lane,
-                       ((unsigned long long)(unsigned int)(s + 1) << 32) | (unsigned long long)__float_as_uint(v));
-      }
-      __syncwarp();
+    p0 = warp_sum(p0);
+    p1 = warp_sum(p1);
+    p2 = warp_sum(p2);
+    if (lane < 3) {
+      const float v = lane == 0 ? p0 : (lane == 1 ? p1 : p2);
+      st_relaxed_u64(a.words + ((size_t)s * n_cta + blockIdx.x) * 3 + lane,
+                     ((unsigned long long)(unsigned int)(s + 1) << 32) | (unsigned long long)__float_as_uint(v));
     }
-  } else if (warp < kServiceWarps) {
-    // =========================================== gatherers (even / odd steps) =========================================
-    // poll every CTA's words of the step (all loads of a poll round in flight together: one L2 round trip), reduce in
-    // fp64 in a fixed order, hand the step's norm factors to the workers
-    const unsigned int n_cta = gridDim.x;
-    const float inv_b = 1.0f / (float)a.batch;
-    const float g = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f) * a.scale;
-    unsigned long long* finals = a.words + (size_t)a.n_steps * n_cta * 3;  // [n_steps][2] {factor, tag}
-    for (int s = warp - 2; s < a.n_steps; s += 2) {
-      const int slot = s % kRing;
-      const unsigned int tag = (unsigned int)(s + 1);
-      float cu = 0.f, ci = 0.f;
-      if ((unsigned int)s % n_cta == blockIdx.x) {
-        // ---- root of step s (rotates over the CTAs): gather every CTA's partial words, reduce, republish
-        const unsigned long long* base = a.words + (size_t)s * n_cta * 3;
-        unsigned long long wv[kMaxCtaPerLane][3];
-        bool all_ok;
-        do {
-#pragma unroll
-          for (int i = 0; i < kMaxCtaPerLane; ++i) {
-            const unsigned int c = lane + 32u * i;
-            if (c < n_cta) {
-#pragma unroll
-              for (int k = 0; k < 3; ++k) wv[i][k] = ld_relaxed_u64(base + (size_t)c * 3 + k);
-            }
-          }
-          all_ok = true;
-#pragma unroll
-          for (int i = 0; i < kMaxCtaPerLane; ++i) {
-            const unsigned int c = lane + 32u * i;
-            if (c < n_cta) {
-#pragma unroll
-              for (int k = 0; k < 3; ++k) all_ok = all_ok && ((unsigned int)(wv[i][k] >> 32) == tag);
-            }
-          }
-          all_ok = __all_sync(0xffffffffu, all_ok);
-        } while (!all_ok);
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    __syncwarp();
+  }
+}
+
+// steps s = which, which+2, ...: root CTA (s mod grid) gathers + reduces + republishes; the others poll the result
+__device__ __forceinline__ void service_gatherer(const StepsArgs& a, const Bars& B, float2* norms, int which, int lane) {
+  const unsigned int n_cta = gridDim.x;
+  const float inv_b = 1.0f / (float)a.batch;
+  const float g = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f) * a.scale;
+  unsigned long long* finals = a.words + (size_t)a.n_steps * n_cta * 3;  // [n_steps][2] {factor, tag}
+  for (int s = which; s < a.n_steps; s += 2) {
+    const int slot = s % kRing;
+    const unsigned int tag = (unsigned int)(s + 1);
+    float cu = 0.f, ci = 0.f;
+    if ((unsigned int)s % n_cta == blockIdx.x) {
+      const unsigned long long* base = a.words + (size_t)s * n_cta * 3;
+      unsigned long long wv[kMaxCtaPerLane][3];
+      bool all_ok;
+      do {
 #pragma unroll
         for (int i = 0; i < kMaxCtaPerLane; ++i) {
           const unsigned int c = lane + 32u * i;
           if (c < n_cta) {
-            t0 += (double)__uint_as_float((unsigned int)wv[i][0]);
-            t1 += (double)__uint_as_float((unsigned int)wv[i][1]);
-            t2 += (double)__uint_as_float((unsigned int)wv[i][2]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) wv[i][k] = ld_relaxed_u64(base + (size_t)c * 3 + k);
           }
         }
-        t0 = warp_sum(t0);
-        t1 = warp_sum(t1);
-        t2 = warp_sum(t2);
-        const float nu = (float)sqrt(t1), ni = (float)sqrt(t2);
-        // d(reg_weight * (||U||_F + ||I||_F)/B)/dU_r = reg_weight/(B*||U||_F) * U_r   (torch: 0 when the norm is 0)
-        cu = (a.reg_weight != 0.f && nu > 0.f) ? g * a.reg_weight * inv_b / nu : 0.f;
-        ci = (a.reg_weight != 0.f && ni > 0.f) ? g * a.reg_weight * inv_b / ni : 0.f;
-        if (lane < 2)
-          st_relaxed_u64(finals + (size_t)s * 2 + lane,
-                         ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(lane == 0 ? cu : ci));
-        if (lane == 0) {
-          const float data = (float)(t0 / (double)a.batch);
-          const float reg = (float)(((double)nu + (double)ni) / (double)a.batch);
-          float* o = a.out8 + (size_t)s * 8;
-          o[0] = data + a.reg_weight * reg;
-          o[1] = data;
-          o[2] = nu;
-          o[3] = ni;
-          o[4] = reg;
-          o[5] = 0.f;
-          o[6] = 0.f;
-          o[7] = 0.f;
-        }
-      } else {
-        // ---- everyone else polls the root's two result words (one 16-byte line, one lane)
-        unsigned long long f0 = 0, f1 = 0;
-        if (lane == 0) {
-          const unsigned long long* f = finals + (size_t)s * 2;
-          for (;;) {
-            f0 = ld_relaxed_u64(f);
-            f1 = ld_relaxed_u64(f + 1);
-            if ((unsigned int)(f0 >> 32) == tag && (unsigned int)(f1 >> 32) == tag) break;
-            __nanosleep(64);
+        all_ok = true;
+#pragma unroll
+        for (int i = 0; i < kMaxCtaPerLane; ++i) {
+          const unsigned int c = lane + 32u * i;
+          if (c < n_cta) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) all_ok = all_ok && ((unsigned int)(wv[i][k] >> 32) == tag);
           }
         }
-        cu = __uint_as_float((unsigned int)__shfl_sync(0xffffffffu, f0, 0));
-        ci = __uint_as_float((unsigned int)__shfl_sync(0xffffffffu, f1, 0));
+        all_ok = __all_sync(0xffffffffu, all_ok);
+      } while (!all_ok);
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < kMaxCtaPerLane; ++i) {
+        const unsigned int c = lane + 32u * i;
+        if (c < n_cta) {
+          t0 += (double)__uint_as_float((unsigned int)wv[i][0]);
+          t1 += (double)__uint_as_float((unsigned int)wv[i][1]);
+          t2 += (double)__uint_as_float((unsigned int)wv[i][2]);
+        }
       }
-      if (a.trace && lane == 0) a.trace[((size_t)s * n_cta + blockIdx.x) * 8 + 1] = gtime();
+      t0 = warp_sum(t0);
+      t1 = warp_sum(t1);
+      t2 = warp_sum(t2);
+      const float nu = (float)sqrt(t1), ni = (float)sqrt(t2);
+      // d(reg_weight * (||U||_F + ||I||_F)/B)/dU_r = reg_weight/(B*||U||_F) * U_r   (torch: 0 when the norm is 0)
+      cu = (a.reg_weight != 0.f && nu > 0.f) ? g * a.reg_weight * inv_b / nu : 0.f;
+      ci = (a.reg_weight != 0.f && ni > 0.f) ? g * a.reg_weight * inv_b / ni : 0.f;
+      if (lane < 2)
+        st_relaxed_u64(finals + (size_t)s * 2 + lane,
+                       ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(lane == 0 ? cu : ci));
       if (lane == 0) {
-        norms[slot] = make_float2(cu, ci);
-        mbar_arrive(&normf[slot]);  // release: the norms are visible to every worker that observes this phase
+        const float data = (float)(t0 / (double)a.batch);
+        const float reg = (float)(((double)nu + (double)ni) / (double)a.batch);
+        float* o = a.out8 + (size_t)s * 8;
+        o[0] = data + a.reg_weight * reg;
+        o[1] = data;
+        o[2] = nu;
+        o[3] = ni;
+        o[4] = reg;
+        o[5] = 0.f;
+        o[6] = 0.f;
+        o[7] = 0.f;
       }
-      __syncwarp();
+    } else {
+      unsigned long long f0 = 0, f1 = 0;
+      if (lane == 0) {
+        const unsigned long long* f = finals + (size_t)s * 2;
+        for (;;) {
+          f0 = ld_relaxed_u64(f);
+          f1 = ld_relaxed_u64(f + 1);
+          if ((unsigned int)(f0 >> 32) == tag && (unsigned int)(f1 >> 32) == tag) break;
+          __nanosleep(64);
+        }
+      }
+      cu = __uint_as_float((unsigned int)__shfl_sync(0xffffffffu, f0, 0));
+      ci = __uint_as_float((unsigned int)__shfl_sync(0xffffffffu, f1, 0));
+    }
+    if (a.trace && lane == 0) a.trace[((size_t)s * n_cta + blockIdx.x) * 8 + 1] = gtime();
+    if (lane == 0) {
+      norms[slot] = make_float2(cu, ci);
+      mbar_arrive(&B.normf[slot]);  // release: the norms are visible to everyone who observes this phase
+    }
+    __syncwarp();
+  }
+}
+
+// ---- task primitives (shared) ------------------------------------------------------------------------------------------
+// request the rows of CTA-local task `lt` (ids from the shared-memory ring)
+template <int LPR, int VEC, bool PAIRWISE>
+__device__ __forceinline__ void task_issue(TaskRegs<VEC, PAIRWISE>& r, int lt, const StepsArgs& a, const SmemLayout& L,
+                                           const Bars& B, const unsigned char* ids_ring, int tasks, int cnt, int lane) {
+  constexpr int IPW = 32 / LPR;
+  constexpr int R = PAIRWISE ? 3 : 2;
+  const int sub = lane % LPR, grp = lane / LPR;
+  const int row_f = a.nv * 4;
+  r.s = lt / tasks;
+  r.q = lt - r.s * tasks;
+  const int slot = r.s % kRing;
+  mbar_wait(&B.idsf[slot], (uint32_t)((r.s / kRing) & 1));
+  if (a.trace && lane == 0 && r.q == 0) a.trace[((size_t)r.s * gridDim.x + blockIdx.x) * 8 + 2] = gtime();
+  const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
+  const float* lab = reinterpret_cast<const float*>(ids + (size_t)R * L.slice);
+  const int j = r.q * IPW + grp;
+  const bool live = j < cnt;
+  const int jj = live ? j : 0;
+  const int64_t iu = ids[jj], ia = ids[L.slice + jj], ib = PAIRWISE ? ids[2 * L.slice + jj] : 0;
+  r.label = (!PAIRWISE && a.label != nullptr) ? lab[jj] : 0.f;
+  const bool oku = live && (uint64_t)iu < (uint64_t)a.n_users;
+  const bool oka = live && (uint64_t)ia < (uint64_t)a.n_items;
+  const bool okb = PAIRWISE && live && (uint64_t)ib < (uint64_t)a.n_items;
+  if (live && a.oob && sub == 0 && (!oku || !oka || (PAIRWISE && !okb))) *a.oob = 1;
+  r.iu = oku ? (int)iu : -1;
+  r.ia = oka ? (int)ia : -1;
+  r.ib = okb ? (int)ib : -1;
+  r.sb = live ? 1.f : 0.f;  // until task_score overwrites it with the negative score: "this lane owns an interaction"
+  const float* pu = a.user_tab + (int64_t)(oku ? iu : 0) * row_f;
+  const float* pa = a.item_tab + (int64_t)(oka ? ia : 0) * row_f;
+  const float* pb = a.item_tab + (int64_t)(okb ? ib : 0) * row_f;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const int c = sub + v * LPR;
+    const bool on = c < a.nv;
+    r.u[v] = (oku && on) ? ldcg_row4(pu, c) : z4;
+    r.a[v] = (oka && on) ? ldcg_row4(pa, c) : z4;
+    if (PAIRWISE) r.b[v] = (okb && on) ? ldcg_row4(pb, c) : z4;
+  }
+}
+
+// score, loss term and squared norms of the task (consumes the row loads); returns the task partial in every lane
+template <int LPR, int VEC, bool PAIRWISE>
+__device__ __forceinline__ float4 task_score(TaskRegs<VEC, PAIRWISE>& r, const StepsArgs& a) {
+  float da = 0.f, db = 0.f, uu = 0.f, aa = 0.f;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    da += dot4(r.u[v], r.a[v]);
+    uu += dot4(r.u[v], r.u[v]);
+    aa += dot4(r.a[v], r.a[v]);
+    if (PAIRWISE) db += dot4(r.u[v], r.b[v]);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    da += __shfl_xor_sync(0xffffffffu, da, o);
+    uu += __shfl_xor_sync(0xffffffffu, uu, o);
+    aa += __shfl_xor_sync(0xffffffffu, aa, o);
+    if (PAIRWISE) db += __shfl_xor_sync(0xffffffffu, db, o);
+  }
+  const bool live = r.sb != 0.f;
+  r.sa = da;
+  r.sb = db;
+  float term = 0.f;
+  if (live) {
+    if (PAIRWISE) {
+      term = -logf(a.gamma + sigmoidf_(da - db));
+    } else if (a.loss_kind == XDR_LOSS_MSE) {
+      const float d = da - r.label;
+      term = d * d;
+    } else if (a.loss_kind == XDR_LOSS_BCE_SIGMOID) {
+      const float p = sigmoidf_(da);
+      term = -(r.label * fmaxf(logf(p), -100.f) + (1.f - r.label) * fmaxf(logf(1.f - p), -100.f));
     }
   } else {
-    // =========================================== workers ==============================================================
+    uu = 0.f;
+    aa = 0.f;
+  }
+  // sum over the interactions of the task (fixed shuffle tree -> deterministic)
+#pragma unroll
+  for (int o = 16; o >= LPR; o >>= 1) {
+    term += __shfl_xor_sync(0xffffffffu, term, o);
+    uu += __shfl_xor_sync(0xffffffffu, uu, o);
+    aa += __shfl_xor_sync(0xffffffffu, aa, o);
+  }
+  return make_float4(term, uu, aa, 0.f);
+}
+
+// g * dL_data/dscore_a for one interaction (BPR: dscore_b = -c)
+template <bool PAIRWISE>
+__device__ __forceinline__ float score_coeff(const StepsArgs& a, float g, float inv_b, float sa, float sb, float label) {
+  if (PAIRWISE) {
+    const float sg = sigmoidf_(sa - sb);
+    return -g * inv_b * (sg * (1.f - sg)) / (a.gamma + sg);
+  } else if (a.loss_kind == XDR_LOSS_MSE) {
+    return g * inv_b * 2.f * (sa - label);
+  } else if (a.loss_kind == XDR_LOSS_BCE_SIGMOID) {
+    const float p = sigmoidf_(sa);
+    const float pq = p * (1.f - p);
+    return g * inv_b * (p - label) / fmaxf(pq, 1e-12f) * pq;
+  }
+  return 0.f;
+}
+
+template <bool PAIRWISE>
+__device__ __forceinline__ void scatter_cols(const StepsArgs& a, int cidx, float c, float cu, float ci, int iu, int ia,
+                                             int ib, float4 ru, float4 ra, float4 rb) {
+  const int64_t row_f = (int64_t)a.nv * 4;
+  if (PAIRWISE) {
+    if (iu >= 0) red_add4(a.user_dst + iu * row_f, cidx, axpy4(cu, ru, scale4(c, sub4(ra, rb))));
+    if (ia >= 0) red_add4(a.item_dst + ia * row_f, cidx, axpy4(ci, ra, scale4(c, ru)));
+    if (ib >= 0) red_add4(a.item_dst + ib * row_f, cidx, scale4(-c, ru));
+  } else {
+    if (iu >= 0) red_add4(a.user_dst + iu * row_f, cidx, axpy4(cu, ru, scale4(c, ra)));
+    if (ia >= 0) red_add4(a.item_dst + ia * row_f, cidx, axpy4(ci, ra, scale4(c, ru)));
+  }
+}
+
+__device__ __forceinline__ void init_bars(const Bars& B, int tasks, int ifree_count, int stages, int sfree_count) {
+  for (int i = 0; i < kRing; ++i) {
+    mbar_init(&B.idsf[i], 1);
+    mbar_init(&B.ifree[i], (uint32_t)ifree_count);
+    mbar_init(&B.adone[i], (uint32_t)tasks);
+    mbar_init(&B.normf[i], 1);
+  }
+  for (int i = 0; i < stages; ++i) mbar_init(&B.sfree[i], (uint32_t)sfree_count);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// =====================================================================================================================
+// STAGED kernel: loaders (gather -> score -> stash) and scatterers (norms -> gradients -> RED) are different warps
+// =====================================================================================================================
+template <int LPR, int VEC, bool PAIRWISE>
+__global__ void __launch_bounds__(kStagedThreads, 1) train_steps_staged_kernel(StepsArgs a, int n_stages) {
+  constexpr int IPW = 32 / LPR;
+  constexpr int R = PAIRWISE ? 3 : 2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int64_t first = (int64_t)blockIdx.x * a.slice;
+  const int cnt = (int)min((int64_t)a.slice, a.batch - first);  // > 0: the host launches ceil(batch/slice) CTAs
+  const int tasks = (cnt + IPW - 1) / IPW;
+  const int row_f = a.nv * 4;
+  const SmemLayout L(a.slice, R, (a.slice + IPW - 1) / IPW, row_f, n_stages);
+  const Bars B(smem_raw + L.bars_off());
+  float2* norms = reinterpret_cast<float2*>(smem_raw + L.norms_off());
+  float4* part = reinterpret_cast<float4*>(smem_raw + L.part_off());
+  unsigned char* ids_ring = smem_raw + L.ids_off();
+  unsigned char* stage_ring = smem_raw + L.stage_off();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) init_bars(B, tasks, kScatterWarps, n_stages, kScatterWarps);
+  __syncthreads();
+
+  if (warp == 0) {
+    service_producer<PAIRWISE>(a, L, B, ids_ring, first, cnt, lane);
+  } else if (warp == 1) {
+    service_publisher(a, L, B, part, tasks, lane);
+  } else if (warp < kServiceWarps) {
+    service_gatherer(a, B, norms, warp - 2, lane);
+  } else if (warp < kServiceWarps + kLoaderWarps) {
+    // ------------------------------------------------ loaders ---------------------------------------------------------
+    // at most 3*tasks loaders are active so that a loader's consecutive tasks are <= 3 steps apart: with two tasks in
+    // flight the steps it touches span <= 6 < kRing, so the id ring is never lapped
+    const int n_loaders = min(kLoaderWarps, 3 * tasks);
+    const int w = warp - kServiceWarps;
+    if (w >= n_loaders) return;
+    const int sub = lane % LPR, grp = lane / LPR;
+    const int total = a.n_steps * tasks;
+    using Regs = TaskRegs<VEC, PAIRWISE>;
+    auto issue = [&](Regs& r, int lt) { task_issue<LPR, VEC, PAIRWISE>(r, lt, a, L, B, ids_ring, tasks, cnt, lane); };
+    auto score_and_stash = [&](Regs& r) {
+      const float4 p = task_score<LPR, VEC, PAIRWISE>(r, a);
+      const int st = r.s % n_stages;
+      mbar_wait(&B.sfree[st], (uint32_t)(((r.s / n_stages) & 1) ^ 1));  // first time round the ring: passes at once
+      float* rows = reinterpret_cast<float*>(stage_ring + (size_t)st * L.stage_slot_bytes());
+      float* sc = rows + (size_t)R * L.slice * row_f;
+      const int j = r.q * IPW + grp;
+      if (j < cnt) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const int c = sub + v * LPR;
+          if (c >= a.nv) continue;
+          st4(rows + (size_t)j * row_f, c, r.u[v]);
+          st4(rows + ((size_t)L.slice + j) * row_f, c, r.a[v]);
+          if (PAIRWISE) st4(rows + ((size_t)2 * L.slice + j) * row_f, c, r.b[v]);
+        }
+        if (sub == 0) {
+          sc[j] = r.sa;
+          sc[L.slice + j] = r.sb;
+        }
+      }
+      __syncwarp();  // every lane's stage writes are ordered before lane 0's release-arrive
+      if (lane == 0) {
+        part[(r.s % kRing) * L.tasks + r.q] = p;
+        mbar_arrive(&B.adone[r.s % kRing]);
+        if (a.trace && r.q == 0) a.trace[((size_t)r.s * gridDim.x + blockIdx.x) * 8 + 3] = gtime();
+      }
+    };
+    Regs r0, r1;
+    int lt = w;
+    if (lt < total) issue(r0, lt);
+    while (lt < total) {
+      int nx = lt + n_loaders;
+      if (nx < total) issue(r1, nx);
+      score_and_stash(r0);
+      lt = nx;
+      if (lt >= total) break;
+      nx = lt + n_loaders;
+      if (nx < total) issue(r0, nx);
+      score_and_stash(r1);
+      lt = nx;
+    }
+  } else {
+    // ------------------------------------------------ scatterers ------------------------------------------------------
+    const int x = warp - kServiceWarps - kLoaderWarps;
+    const int sub = lane % LPR, grp = lane / LPR;
+    const float inv_b = 1.0f / (float)a.batch;
+    const float g = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f) * a.scale;
+    for (int s = 0; s < a.n_steps; ++s) {
+      const int slot = s % kRing, st = s % n_stages;
+      const uint32_t par = (uint32_t)((s / kRing) & 1);
+      mbar_wait(&B.normf[slot], par);  // => every CTA (this one included) has scored and stashed the step
+      mbar_wait(&B.idsf[slot], par);   // (long complete) acquire: the TMA-written ids are visible to this warp
+      mbar_wait(&B.adone[slot], par);  // (long complete) acquire: the loaders' stage writes are visible to this warp
+      if (a.trace && lane == 0 && x == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 5] = gtime();
+      const float2 nf = norms[slot];
+      const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
+      const float* lab = reinterpret_cast<const float*>(ids + (size_t)R * L.slice);
+      const float* rows = reinterpret_cast<const float*>(stage_ring + (size_t)st * L.stage_slot_bytes());
+      const float* sc = rows + (size_t)R * L.slice * row_f;
+      for (int q = x; q < tasks; q += kScatterWarps) {
+        const int j = q * IPW + grp;
+        if (j >= cnt) continue;
+        const int64_t iu64 = ids[j], ia64 = ids[L.slice + j], ib64 = PAIRWISE ? ids[2 * L.slice + j] : 0;
+        const int iu = (uint64_t)iu64 < (uint64_t)a.n_users ? (int)iu64 : -1;
+        const int ia = (uint64_t)ia64 < (uint64_t)a.n_items ? (int)ia64 : -1;
+        const int ib = (PAIRWISE && (uint64_t)ib64 < (uint64_t)a.n_items) ? (int)ib64 : -1;
+        const float label = (!PAIRWISE && a.label != nullptr) ? lab[j] : 0.f;
+        const float c = score_coeff<PAIRWISE>(a, g, inv_b, sc[j], sc[L.slice + j], label);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const int cidx = sub + v * LPR;
+          if (cidx >= a.nv) continue;
+          const float4 ru = ld_row4(rows + (size_t)j * row_f, cidx);
+          const float4 ra = ld_row4(rows + ((size_t)L.slice + j) * row_f, cidx);
+          const float4 rb = PAIRWISE ? ld_row4(rows + ((size_t)2 * L.slice + j) * row_f, cidx) : ru;
+          scatter_cols<PAIRWISE>(a, cidx, c, nf.x, nf.y, iu, ia, ib, ru, ra, rb);
+        }
+      }
+      __syncwarp();
+      if (a.trace && lane == 0 && x == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 6] = gtime();
+      if (lane == 0) {
+        mbar_arrive(&B.sfree[st]);    // the stage slot may be overwritten by the loaders
+        mbar_arrive(&B.ifree[slot]);  // the id slot may be refilled by the producer
+      }
+    }
+  }
+}
+
+// =====================================================================================================================
+// REGISTER kernel: workers keep the rows in registers from gather to scatter
+// =====================================================================================================================
+template <int LPR, int VEC, bool PAIRWISE>
+__global__ void __launch_bounds__(kRegThreads, 1) train_steps_regs_kernel(StepsArgs a) {
+  constexpr int IPW = 32 / LPR;
+  constexpr int R = PAIRWISE ? 3 : 2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int64_t first = (int64_t)blockIdx.x * a.slice;
+  const int cnt = (int)min((int64_t)a.slice, a.batch - first);
+  const int tasks = (cnt + IPW - 1) / IPW;
+  const SmemLayout L(a.slice, R, (a.slice + IPW - 1) / IPW);
+  const Bars B(smem_raw + L.bars_off());
+  float2* norms = reinterpret_cast<float2*>(smem_raw + L.norms_off());
+  float4* part = reinterpret_cast<float4*>(smem_raw + L.part_off());
+  unsigned char* ids_ring = smem_raw + L.ids_off();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) init_bars(B, tasks, tasks, 0, 1);
+  __syncthreads();
+
+  if (warp == 0) {
+    service_producer<PAIRWISE>(a, L, B, ids_ring, first, cnt, lane);
+  } else if (warp == 1) {
+    service_publisher(a, L, B, part, tasks, lane);
+  } else if (warp < kServiceWarps) {
+    service_gatherer(a, B, norms, warp - 2, lane);
+  } else {
     // Only min(kWorkerWarps, 3*tasks) workers are active so that a worker's consecutive tasks are at most 3 steps
     // apart: with two tasks held per warp the steps in flight span <= 7 < kRing, so no ring is ever lapped.
-    // The host guarantees tasks <= 2*kWorkerWarps (each worker owns at most two tasks of any step, and it runs
-    // phase A of both before it waits for that step's norms).
+    // The host guarantees tasks <= 2*kWorkerWarps (each worker owns at most two tasks of any step, and it scores
+    // both before it waits for that step's norms).
     const int n_workers = min(kWorkerWarps, 3 * tasks);
     const int w = warp - kServiceWarps;
     if (w >= n_workers) return;
-    const int sub = lane % LPR, grp = lane / LPR;
+    const int sub = lane % LPR;
     const float inv_b = 1.0f / (float)a.batch;
     const float g = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f) * a.scale;
     const int total = a.n_steps * tasks;
     using Regs = TaskRegs<VEC, PAIRWISE>;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    // request the rows of CTA-local task `lt` (ids from the shared-memory ring)
-    auto issue = [&](Regs& r, int lt) {
-      r.s = lt / tasks;
-      r.q = lt - r.s * tasks;
-      const int slot = r.s % kRing;
-      mbar_wait(&idsf[slot], (uint32_t)((r.s / kRing) & 1));
-      if (a.trace && lane == 0 && r.q == 0) a.trace[((size_t)r.s * gridDim.x + blockIdx.x) * 8 + 2] = gtime();
-      const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
-      const float* lab = reinterpret_cast<const float*>(ids + (size_t)R * L.slice);
-      const int j = r.q * IPW + grp;
-      const bool live = j < cnt;
-      const int jj = live ? j : 0;
-      const int64_t iu = ids[jj], ia = ids[L.slice + jj], ib = PAIRWISE ? ids[2 * L.slice + jj] : 0;
-      r.label = (!PAIRWISE && a.label != nullptr) ? lab[jj] : 0.f;
-      const bool oku = live && (uint64_t)iu < (uint64_t)a.n_users;
-      const bool oka = live && (uint64_t)ia < (uint64_t)a.n_items;
-      const bool okb = PAIRWISE && live && (uint64_t)ib < (uint64_t)a.n_items;
-      if (live && a.oob && sub == 0 && (!oku || !oka || (PAIRWISE && !okb))) *a.oob = 1;
-      r.iu = oku ? (int)iu : -1;
-      r.ia = oka ? (int)ia : -1;
-      r.ib = okb ? (int)ib : -1;
-      r.sb = live ? 1.f : 0.f;  // until phase A overwrites it with the negative score: "this lane owns an interaction"
-      const float* pu = a.user_tab + (int64_t)(oku ? iu : 0) * row_f;
-      const float* pa = a.item_tab + (int64_t)(oka ? ia : 0) * row_f;
-      const float* pb = a.item_tab + (int64_t)(okb ? ib : 0) * row_f;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const int c = sub + v * LPR;
-        const bool on = c < a.nv;
-        r.u[v] = (oku && on) ? ldcg_row4(pu, c) : z4;
-        r.a[v] = (oka && on) ? ldcg_row4(pa, c) : z4;
-        if (PAIRWISE) r.b[v] = (okb && on) ? ldcg_row4(pb, c) : z4;
-      }
-    };
-
-    // phase A: score, loss term, squared norms -> task partial (consumes the row loads)
+    auto issue = [&](Regs& r, int lt) { task_issue<LPR, VEC, PAIRWISE>(r, lt, a, L, B, ids_ring, tasks, cnt, lane); };
     auto phase_a = [&](Regs& r) {
-      const int slot = r.s % kRing;
-      float da = 0.f, db = 0.f, uu = 0.f, aa = 0.f;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        da += dot4(r.u[v], r.a[v]);
-        uu += dot4(r.u[v], r.u[v]);
-        aa += dot4(r.a[v], r.a[v]);
-        if (PAIRWISE) db += dot4(r.u[v], r.b[v]);
-      }
-#pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1) {
-        da += __shfl_xor_sync(0xffffffffu, da, o);
-        uu += __shfl_xor_sync(0xffffffffu, uu, o);
-        aa += __shfl_xor_sync(0xffffffffu, aa, o);
-        if (PAIRWISE) db += __shfl_xor_sync(0xffffffffu, db, o);
-      }
-      const bool live = r.sb != 0.f;
-      r.sa = da;
-      r.sb = db;
-      float term = 0.f;
-      if (live) {
-        if (PAIRWISE) {
-          term = -logf(a.gamma + sigmoidf_(da - db));
-        } else if (a.loss_kind == XDR_LOSS_MSE) {
-          const float d = da - r.label;
-          term = d * d;
-        } else if (a.loss_kind == XDR_LOSS_BCE_SIGMOID) {
-          const float p = sigmoidf_(da);
-          term = -(r.label * fmaxf(logf(p), -100.f) + (1.f - r.label) * fmaxf(logf(1.f - p), -100.f));
-        }
-      } else {
-        uu = 0.f;
-        aa = 0.f;
-      }
-      // sum over the IPW interactions of the task (fixed shuffle tree -> deterministic)
-#pragma unroll
-      for (int o = 16; o >= LPR; o >>= 1) {
-        term += __shfl_xor_sync(0xffffffffu, term, o);
-        uu += __shfl_xor_sync(0xffffffffu, uu, o);
-        aa += __shfl_xor_sync(0xffffffffu, aa, o);
-      }
+      const float4 p = task_score<LPR, VEC, PAIRWISE>(r, a);
       if (lane == 0) {
-        part[slot * L.tasks + r.q] = make_float4(term, uu, aa, 0.f);
-        mbar_arrive(&adone[slot]);  // release: the partial is visible to the reducer
+        part[(r.s % kRing) * L.tasks + r.q] = p;
+        mbar_arrive(&B.adone[r.s % kRing]);  // release: the partial is visible to the publisher
         if (a.trace && r.q == 0) a.trace[((size_t)r.s * gridDim.x + blockIdx.x) * 8 + 3] = gtime();
       }
     };
-
-    // phase B: wait for the step's norm factors, form the row gradients from the rows still in registers, scatter-add
     auto phase_b = [&](Regs& r) {
       const int slot = r.s % kRing;
-      const uint32_t par = (uint32_t)((r.s / kRing) & 1);
       if (a.trace && lane == 0 && r.q == 0) a.trace[((size_t)r.s * gridDim.x + blockIdx.x) * 8 + 4] = gtime();
-      mbar_wait(&normf[slot], par);
+      mbar_wait(&B.normf[slot], (uint32_t)((r.s / kRing) & 1));
       if (a.trace && lane == 0 && r.q == 0) a.trace[((size_t)r.s * gridDim.x + blockIdx.x) * 8 + 5] = gtime();
       const float2 nf = norms[slot];
-      const float cu = nf.x, ci = nf.y;
-      float c = 0.f;  // g * dL_data/dscore_a  (BPR: dscore_b = -c)
-      if (PAIRWISE) {
-        const float sg = sigmoidf_(r.sa - r.sb);
-        c = -g * inv_b * (sg * (1.f - sg)) / (a.gamma + sg);
-      } else if (a.loss_kind == XDR_LOSS_MSE) {
-        c = g * inv_b * 2.f * (r.sa - r.label);
-      } else if (a.loss_kind == XDR_LOSS_BCE_SIGMOID) {
-        const float p = sigmoidf_(r.sa);
-        const float pq = p * (1.f - p);
-        c = g * inv_b * (p - r.label) / fmaxf(pq, 1e-12f) * pq;
-      }
-      const bool oku = r.iu >= 0, oka = r.ia >= 0, okb = PAIRWISE && r.ib >= 0;
-      float* du = a.user_dst + (int64_t)r.iu * row_f;
-      float* dia = a.item_dst + (int64_t)r.ia * row_f;
-      float* dib = a.item_dst + (int64_t)r.ib * row_f;
+      const float c = score_coeff<PAIRWISE>(a, g, inv_b, r.sa, r.sb, r.label);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const int cidx = sub + v * LPR;
         if (cidx >= a.nv) continue;
-        if (PAIRWISE) {
-          if (oku) red_add4(du, cidx, axpy4(cu, r.u[v], scale4(c, sub4(r.a[v], r.b[v]))));
-          if (oka) red_add4(dia, cidx, axpy4(ci, r.a[v], scale4(c, r.u[v])));
-          if (okb) red_add4(dib, cidx, scale4(-c, r.u[v]));
-        } else {
-          if (oku) red_add4(du, cidx, axpy4(cu, r.u[v], scale4(c, r.a[v])));
-          if (oka) red_add4(dia, cidx, axpy4(ci, r.a[v], scale4(c, r.u[v])));
-        }
+        scatter_cols<PAIRWISE>(a, cidx, c, nf.x, nf.y, r.iu, r.ia, r.ib, r.u[v], r.a[v], PAIRWISE ? r.b[v] : r.u[v]);
       }
       __syncwarp();
       if (a.trace && lane == 0 && r.q == 0) a.trace[((size_t)r.s * gridDim.x + blockIdx.x) * 8 + 6] = gtime();
-      if (lane == 0) mbar_arrive(&ifree[slot]);  // this task no longer needs the step's id tile / partial slot
+      if (lane == 0) mbar_arrive(&B.ifree[slot]);  // this task no longer needs the step's id tile / partial slot
     };
-
-    // Two register sets per warp.  Phase A runs one round ahead of phase B, so the norm exchange of a step overlaps
-    // the gathers of the following ones:   B(r0) issue(r0') B(r1) issue(r1') A(r0') A(r1') ...
-    // Hazard rule: before waiting for the norms of step s, every task of this warp with step <= s must have run
-    // phase A (the norms of s cannot complete without it).
+    // Two register sets per warp; scoring runs ahead of the norm wait:  B(r0) issue(r0') B(r1) issue(r1') A(r0') A(r1')
+    // Hazard rule: before waiting for the norms of step s, every task of this warp with step <= s must be scored.
     Regs r0, r1;
     bool live0 = false, live1 = false;  // the set holds a task (issued or scored)
-    bool iss0 = false, iss1 = false;    // ... whose rows are requested but phase A has not run yet
+    bool iss0 = false, iss1 = false;    // ... whose rows are requested but not scored yet
     int next = w;
     if (next < total) { issue(r0, next); next += n_workers; live0 = iss0 = true; }
     if (next < total) { issue(r1, next); next += n_workers; live1 = iss1 = true; }
@@ -481,9 +656,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs 
         if (next < total) { issue(r0, next); next += n_workers; live0 = iss0 = true; }
       }
       if (live1) {
-        // never block on norms while holding requested-but-unscored rows: other CTAs (and the hazard rule: tasks of
-        // this warp with step <= r1.s) may be waiting for exactly that partial
-        if (iss0 && (r0.s <= r1.s || !mbar_test(&normf[r1.s % kRing], (uint32_t)((r1.s / kRing) & 1)))) {
+        // never block on norms while holding requested-but-unscored rows: other CTAs (and the hazard rule) may be
+        // waiting for exactly that partial
+        if (iss0 && (r0.s <= r1.s || !mbar_test(&B.normf[r1.s % kRing], (uint32_t)((r1.s / kRing) & 1)))) {
           phase_a(r0);
           iss0 = false;
         }
@@ -496,12 +671,12 @@ __global__ void __launch_bounds__(kStepThreads, 1) train_steps_kernel(StepsArgs 
 }
 
 struct StepsPlan {
-  int grid, slice, lpr, vec;
+  int grid, slice, lpr, vec, stages;  // stages > 0: staged kernel; 0: register kernel
   size_t smem;
 };
 
-// Lanes per row / float4 columns per lane for a row of nv float4s: at most 2 columns per lane so that two tasks
-// (2 x 3 rows) stay in registers.  Returns false for row widths this kernel does not specialise.
+// Lanes per row / float4 columns per lane for a row of nv float4s (at most 2 columns per lane so that two tasks stay
+// in registers), CTA slice, and which kernel fits.  Returns false when neither does (use the per-step kernels).
 static bool plan_steps(int64_t batch, int nv, bool pairwise, StepsPlan* plan) {
   int lpr, vec;
   if (nv <= 8) { lpr = 8; vec = 1; }
@@ -514,25 +689,42 @@ static bool plan_steps(int64_t batch, int nv, bool pairwise, StepsPlan* plan) {
   slice = (slice + 3) & ~(int64_t)3;  // multiple of 4: 16-byte granular TMA id tiles, whole warp tasks
   if (slice < 4) slice = 4;
   const int64_t grid = (batch + slice - 1) / slice;
+  if (grid > sms || grid > 32 * kMaxCtaPerLane) return false;
   const int ipw = 32 / lpr;
-  SmemLayout L((int)slice, pairwise ? 3 : 2, (int)((slice + ipw - 1) / ipw));
-  // a worker runs phase A of at most two tasks before it waits for a step's norms: every step's tasks must fit
-  // 2 x workers, else the step could never complete (larger batches use the per-step kernels)
-  if ((slice + ipw - 1) / ipw > 2 * kWorkerWarps) return false;
-  if (L.bytes() > 200 * 1024 || grid > sms || grid > 32 * kMaxCtaPerLane) return false;
+  const int tasks = (int)((slice + ipw - 1) / ipw);
   plan->grid = (int)grid;
   plan->slice = (int)slice;
   plan->lpr = lpr;
   plan->vec = vec;
+  const size_t smem_cap = 220 * 1024;
+  for (int ns = kMaxStages; ns >= 3; --ns) {
+    SmemLayout L((int)slice, pairwise ? 3 : 2, tasks, nv * 4, ns);
+    if (L.bytes() <= smem_cap) {
+      plan->stages = ns;
+      plan->smem = L.bytes();
+      return true;
+    }
+  }
+  // register kernel: a worker scores at most two tasks before it waits for a step's norms, so every step's tasks
+  // must fit 2 x workers, else the step could never complete
+  SmemLayout L((int)slice, pairwise ? 3 : 2, tasks);
+  if (tasks > 2 * kWorkerWarps || L.bytes() > smem_cap) return false;
+  plan->stages = 0;
   plan->smem = L.bytes();
   return true;
 }
 
 template <int LPR, int VEC, bool PW>
 static int launch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_t s) {
-  auto kern = train_steps_kernel<LPR, VEC, PW>;
-  XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-  kern<<<plan.grid, kStepThreads, plan.smem, s>>>(a);
+  if (plan.stages > 0) {
+    auto kern = train_steps_staged_kernel<LPR, VEC, PW>;
+    XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    kern<<<plan.grid, kStagedThreads, plan.smem, s>>>(a, plan.stages);
+  } else {
+    auto kern = train_steps_regs_kernel<LPR, VEC, PW>;
+    XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    kern<<<plan.grid, kRegThreads, plan.smem, s>>>(a);
+  }
   return XDR_OK;
 }
 
@@ -545,6 +737,7 @@ static int dispatch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_
 }
 
 static unsigned long long* g_trace = nullptr;  // debug only, see xdr_debug_set_steps_trace
+static int g_force_regs = 0;                   // debug only: force the register kernel where both fit
 
 }  // namespace xdr
 
@@ -552,10 +745,12 @@ using namespace xdr;
 
 extern "C" {
 
-// Debug hook (not part of the drop-in surface): device buffer of n_steps*grid*8 u64 that the next xdr_train_steps
-// launches fill with globaltimer stamps: [0] CTA partial ready, [1] all CTAs' partials seen, [2] task 0 rows
-// requested, [3] task 0 scored, [4] task 0 starts waiting for norms, [5] norms arrived, [6] scatter issued.
+// Debug hooks (not part of the drop-in surface).  Trace: device buffer of n_steps*grid*8 u64 that the next
+// xdr_train_steps launches fill with globaltimer stamps: [0] CTA partial ready, [1] norms known, [2] task 0 rows
+// requested, [3] task 0 scored (+stashed), [4] task 0 starts waiting for norms (register kernel), [5] norms arrived at
+// the scatter side, [6] scatter issued.
 XDR_API void xdr_debug_set_steps_trace(void* buf) { g_trace = reinterpret_cast<unsigned long long*>(buf); }
+XDR_API void xdr_debug_force_register_kernel(int on) { g_force_regs = on; }
 
 size_t xdr_steps_workspace_bytes(int n_steps) {
   if (n_steps < 0) return 0;
@@ -586,9 +781,17 @@ int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_user
                       (!pairwise || aligned16(item_b)) && (label == nullptr || aligned16(label));
   if (!tma_ok || !plan_steps(batch, dim / 4, pairwise != 0, &plan)) {
     set_error("xdr_train_steps: batch=%lld dim=%d (batch and step_stride must be multiples of 4, id arrays 16-byte "
-              "aligned, one CTA slice of ids must fit shared memory); use the per-step entry points",
+              "aligned, and a CTA slice must fit the stage ring or the register kernel); use the per-step entry points",
               (long long)batch, dim);
     return XDR_ERR_UNSUPPORTED;
+  }
+  if (g_force_regs && plan.stages > 0) {
+    const int ipw = 32 / plan.lpr;
+    const int tasks = (plan.slice + ipw - 1) / ipw;
+    if (tasks <= 2 * kWorkerWarps) {
+      plan.stages = 0;
+      plan.smem = SmemLayout(plan.slice, pairwise ? 3 : 2, tasks).bytes();
+    }
   }
   StepsArgs a{};
   a.user_tab = user_tab; a.item_tab = item_tab; a.n_users = n_users; a.n_items = n_items; a.nv = dim / 4;

@@ -451,7 +451,7 @@ def _steps_workspace(device, n_steps):
 
 
 def train_steps_supported(batch: int, dim: int, pairwise: bool, device=None) -> bool:
-    """True when (batch, dim) is a shape the persistent kernel takes (mirror of plan_steps in steps_persistent.cu)."""
+    """True when (batch, dim) is a shape the persistent kernels take (mirror of plan_steps in steps_persistent.cu)."""
     if batch <= 0 or batch % 4 != 0 or dim % 4 != 0 or dim > 256:
         return False
     props = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device())
@@ -460,10 +460,16 @@ def train_steps_supported(batch: int, dim: int, pairwise: bool, device=None) -> 
     lpr = 8 if nv <= 16 else (16 if nv <= 32 else 32)
     rows = 3 if pairwise else 2
     slice_ = max(4, (-(-batch // sms) + 3) // 4 * 4)
+    grid = -(-batch // slice_)
+    if grid > sms or grid > 160:
+        return False
     tasks = -(-slice_ // (32 // lpr))
-    ids_off = (320 + 8 * tasks * 16 + 127) // 128 * 128
-    slot = (rows * slice_ * 8 + slice_ * 4 + 127) // 128 * 128
-    return tasks <= 2 * 20 and ids_off + 8 * slot <= 200 * 1024 and -(-batch // slice_) <= sms
+    up = lambda v: (v + 127) // 128 * 128
+    base = up(384 + 8 * tasks * 16) + 8 * up(rows * slice_ * 8 + slice_ * 4)
+    stage = up(rows * slice_ * dim * 4 + 2 * slice_ * 4)
+    if base + 3 * stage <= 220 * 1024:   # staged kernel (3 or 4 stages)
+        return True
+    return tasks <= 2 * 20 and base <= 220 * 1024  # register kernel
 
 
 def train_steps(user_tab, item_tab, user, item_a, item_b=None, label=None, *, loss_kind=_lib.LOSS_MSE, reg_weight=0.0,

@@ -27,7 +27,7 @@ def setup(nu, ni, dim, K, B, seed, zipf=None, std=0.1):
 
 @pytest.mark.parametrize('K,B,dim,zipf', [(1, 8192, 64, None), (7, 8192, 64, None), (5, 4096, 64, 1.1), (9, 256, 64, None),
                                           (3, 4, 64, None), (6, 1000, 32, None), (4, 2048, 128, None), (3, 512, 96, None),
-                                          (40, 8192, 64, None), (3, 16384, 64, None), (20, 148 * 4, 64, None), (4, 23680, 64, None),
+                                          (40, 8192, 64, None), (3, 16384, 64, None), (20, 148 * 4, 64, None), (4, 23680, 64, None), (12, 8192, 128, None),
                                           (5, 2052, 256, None), (33, 36, 16, None)])
 def test_train_steps_bpr_matches_oracle_per_step(K, B, dim, zipf):
     from recbole_cdr_b200 import ops
@@ -71,8 +71,19 @@ def test_train_steps_pointwise(kind):
     torch.testing.assert_close(gi.cpu(), gi_ref, rtol=1e-4, atol=1e-4 * gi_ref.abs().max().item())
 
 
-def test_train_steps_equals_per_step_kernels_and_is_deterministic_in_loss():
-    from recbole_cdr_b200 import ops
+@pytest.mark.parametrize('force_regs', [0, 1])
+def test_train_steps_equals_per_step_kernels_and_is_deterministic_in_loss(force_regs):
+    import ctypes
+    from recbole_cdr_b200 import _lib, ops
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.xdr_debug_force_register_kernel(force_regs)  # exercise both persistent kernels on the headline shape
+    try:
+        _check_equals_per_step(ops)
+    finally:
+        lib.xdr_debug_force_register_kernel(0)
+
+
+def _check_equals_per_step(ops):
     K, B, dim, nu, ni = 12, 8192, 64, 50000, 60000
     ut, it, u, ip, ineg, _ = setup(nu, ni, dim, K, B, 11)
     utc, itc, uc, pc, nc = (t.to(dev()) for t in (ut, it, u, ip, ineg))

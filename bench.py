@@ -261,8 +261,28 @@ def run_xdr(args):
     ms = e0.elapsed_time(e1)
     loss_mean = float(out8[W:, 0].mean().item())
 
-    # ---- for comparison: the per-step kernel pair replayed from a CUDA graph (no host launch cost) -----------------
     extra = {}
+    # ---- same launch with the scatter-add aimed at the weight tables (scale = -lr): the SGD update fused into the step
+    if use_persistent:
+        ops.train_steps(ut.data, it.data, ids[:W, 0], ids[:W, 1], ids[:W, 2], reg_weight=0.01, user_dst=ut.data,
+                        item_dst=it.data, scale=-1e-3, out8=out8[:W])
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        ops.train_steps(ut.data, it.data, ids[W:, 0], ids[W:, 1], ids[W:, 2], reg_weight=0.01, user_dst=ut.data,
+                        item_dst=it.data, scale=-1e-3, out8=out8[W:])
+        f1.record()
+        barrier()
+        fms = torch.tensor([f0.elapsed_time(f1)], device=dev)
+        if world > 1:
+            dist.all_reduce(fms, op=dist.ReduceOp.MAX)
+        fused_rate = world * B * K / (fms.item() * 1e-3)
+        extra['fused_sgd'] = {
+            'note': 'same persistent launch, scatter-add of -lr*grad straight into the embedding tables (row-sparse SGD '
+                    'step included; rows are L2-resident for the atomics so DRAM traffic ~= algorithmic bytes)',
+            'value': fused_rate, 'ms_per_step': fms.item() / K,
+            'roofline_frac': BYTES_PER_INTERACTION_BPR_D64 * fused_rate / world / 1e9 / measured_peaks()[0]}
+    # ---- for comparison: the per-step kernel pair replayed from a CUDA graph (no host launch cost) -----------------
     if use_persistent and rank == 0 and not args.no_compare:
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):

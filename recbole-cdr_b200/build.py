@@ -17,14 +17,15 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-BUILD = os.path.join(HERE, 'build')
+BUILD = os.path.join(HERE, os.environ.get('XDR_BUILD_DIR', 'build'))
 LIB_DIR = os.path.join(HERE, 'recbole_cdr_b200', 'lib')
-LIB = os.path.join(LIB_DIR, 'libxdr.so')
+LIB = os.path.join(LIB_DIR, os.environ.get('XDR_LIB_NAME', 'libxdr.so'))
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--expt-extended-lambda',
          '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '-I', INCLUDE]
+FLAGS += os.environ.get('XDR_EXTRA_NVCC_FLAGS', '').split()
 
 
 def _newer(target, deps):

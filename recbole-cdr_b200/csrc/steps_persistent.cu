@@ -39,8 +39,14 @@ namespace xdr {
 
 constexpr int kServiceWarps = 4;   // producer, publisher, two gatherers
 constexpr int kWorkerWarps = 20;   // register kernel: workers
-constexpr int kLoaderWarps = 12;   // staged kernel: loaders ...
-constexpr int kScatterWarps = 6;   // ... and scatterers
+#ifndef XDR_LOADER_WARPS
+#define XDR_LOADER_WARPS 14
+#endif
+#ifndef XDR_SCATTER_WARPS
+#define XDR_SCATTER_WARPS 4
+#endif
+constexpr int kLoaderWarps = XDR_LOADER_WARPS;    // staged kernel: loaders ...
+constexpr int kScatterWarps = XDR_SCATTER_WARPS;  // ... and scatterers
 constexpr int kRegThreads = (kServiceWarps + kWorkerWarps) * 32;
 constexpr int kStagedThreads = (kServiceWarps + kLoaderWarps + kScatterWarps) * 32;
 constexpr int kMaxCtaPerLane = 5;  // gatherer lanes poll <= 5 CTAs each: grid <= 160

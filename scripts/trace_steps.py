@@ -38,7 +38,7 @@ for s in list(range(0, 12)) + list(range(40, 46)):
     for k in range(7):
         col = t[s, :, k]
         col = col[col > -1e6]
-        row.append(f'{col.median():8.2f}/{col.max():8.2f}')
+        row.append(f'{col.median():8.2f}/{col.max():8.2f}' if col.numel() else '-')
     print(f'{s:4d} | ' + ' | '.join(f'{x:>18s}' for x in row))
 d = t[1:, :, 1].max(dim=1).values - t[:-1, :, 1].max(dim=1).values
 print('median step period (all partials seen, max over CTAs): %.2f us' % d.median())
@@ -46,5 +46,15 @@ print('exchange latency  = all partials seen - last CTA partial ready: %.2f us (
       (t[:, :, 1].max(dim=1).values - t[:, :, 0].max(dim=1).values).median())
 print('skew of partial-ready across CTAs (max - min): %.2f us' % (t[:, :, 0].max(dim=1).values - t[:, :, 0].min(dim=1).values).median())
 print('rows requested -> scored (task 0): %.2f us median, %.2f p95' % ((t[:, :, 3] - t[:, :, 2]).median(), (t[:, :, 3] - t[:, :, 2]).flatten().quantile(0.95)))
-print('wait for norms (task 0): %.2f us median' % (t[:, :, 5] - t[:, :, 4]).median())
 print('scored -> norms arrived (task 0): %.2f us median' % (t[:, :, 5] - t[:, :, 3]).median())
+print('norms arrived -> scatter issued (scatter warp 0): %.2f us median' % (t[:, :, 6] - t[:, :, 5]).median())
+# plain timing of both destination modes
+for mode, (du, di, sc) in {'grad tables': (torch.zeros_like(ut), torch.zeros_like(it), 1.0), 'fused sgd': (ut, it, -1e-3)}.items():
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for rep in range(4):
+        e0.record()
+        ops.train_steps(ut, it, ids[:, 0], ids[:, 1], ids[:, 2], reg_weight=0.01, user_dst=du, item_dst=di, scale=sc)
+        e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    print(f'{mode:12s}: {best * 1e3 / K:6.2f} us/step  ({B * K / best / 1e6:.2f} G interactions/s)')

@@ -182,6 +182,29 @@ XDR_API int xdr_train_steps(const float* user_tab, const float* item_tab, int64_
                             float reg_weight, const float* grad_loss, float scale, float* user_dst, float* item_dst,
                             float* out8, void* steps_ws, size_t steps_ws_bytes, int32_t* oob, xdr_stream_t stream);
 
+/* ---- E1: row-sharded tables over peer memory (one process per GPU, NVLink) --------------------------------------------
+ * The reference is single-device (no collective anywhere); this is the B200 addition.  A table of
+ * n global rows is split block-cyclically over G = n_shards GPUs (G a power of two <= 8): global row r lives on shard
+ * r mod G at local row r div G.  Each rank allocates its shard, exports it with xdr_ipc_export, opens the peers' with
+ * xdr_ipc_open, and passes all G shard pointers (local and peer-mapped) to xdr_train_steps_sharded: the kernel gathers
+ * rows with LDG and scatter-adds gradients with RED directly through the peer mappings, so the NVLink transfers are
+ * issued by the same warps that score the batch -- there is no separate all-to-all step and no NCCL call on the data
+ * path.  The batch stays data-parallel: every rank runs its own K batches (its own per-batch losses) against the shared
+ * sharded tables; accumulated gradients equal a single-GPU run over the union of the batches.
+ * n_users / n_items are GLOBAL row counts; *_shards are HOST arrays of G device pointers.                             */
+XDR_API int xdr_train_steps_sharded(const float* const* user_shards, const float* const* item_shards,
+                                    float* const* user_dst_shards, float* const* item_dst_shards, int n_shards,
+                                    int64_t n_users, int64_t n_items, int dim, const int64_t* user, const int64_t* item_a,
+                                    const int64_t* item_b, const float* label, int64_t step_stride, int64_t batch,
+                                    int n_steps, int pairwise, int loss_kind, float gamma, float reg_weight,
+                                    const float* grad_loss, float scale, float* out8, void* steps_ws,
+                                    size_t steps_ws_bytes, int32_t* oob, xdr_stream_t stream);
+/* CUDA-IPC plumbing.  export: 64-byte handle of the allocation containing dev_ptr + byte offset of dev_ptr inside it
+ * (host outputs).  open: map a peer's allocation, returns its base (add the exported offset).  close: unmap.            */
+XDR_API int xdr_ipc_export(const void* dev_ptr, unsigned char* handle64_host, int64_t* offset_host);
+XDR_API int xdr_ipc_open(const unsigned char* handle64_host, void** base_out_host);
+XDR_API int xdr_ipc_close(void* base);
+
 #ifdef __cplusplus
 }
 #endif

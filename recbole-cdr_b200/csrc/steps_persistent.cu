@@ -33,6 +33,7 @@
 //   no grid-wide barrier anywhere.
 //
 // HBM roofline: 1560 algorithmic bytes per BPR interaction at dim 64 (ids + 3 rows gathered + 3 rows scattered).
+#include <string.h>
 #include "xdr_common.cuh"
 
 namespace xdr {
@@ -53,10 +54,23 @@ constexpr int kMaxCtaPerLane = 5;  // gatherer lanes poll <= 5 CTAs each: grid <
 constexpr int kMaxStages = 4;      // staged kernel: stage ring depth (3 or 4)
 constexpr int kRing = 8;            // id-tile / partial / norm ring depth (steps)
 
+constexpr int kMaxShards = 8;
+
+// A table row-sharded over 2^log2g GPUs: global row r lives on shard (r mod G) at local row (r div G).  Block-cyclic so
+// that the three id ranges of the joint layout (overlapped / target-only / source-only) and Zipf-hot low ids spread
+// evenly.  Shard pointers are local or peer-mapped (CUDA IPC over NVLink) device pointers; G = 1 is the plain table.
+struct Shards {
+  float* p[kMaxShards];
+};
+__device__ __forceinline__ float* shard_row(const Shards& t, int log2g, int64_t row, int64_t row_f) {
+  return t.p[row & ((1 << log2g) - 1)] + (row >> log2g) * row_f;
+}
+
 struct StepsArgs {
-  const float* user_tab;
-  const float* item_tab;
-  int64_t n_users, n_items;
+  Shards user_tab, item_tab;  // gather sources
+  Shards user_dst, item_dst;  // scatter-add destinations
+  int log2g;
+  int64_t n_users, n_items;   // GLOBAL row counts
   int nv;                 // float4 per row
   const int64_t* user;    // [n_steps] arrays of `batch` ids, consecutive steps `step_stride` elements apart
   const int64_t* item_a;
@@ -70,8 +84,6 @@ struct StepsArgs {
   float* out8;  // [n_steps, 8]
   const float* grad_loss;
   float scale;
-  float* user_dst;
-  float* item_dst;
   unsigned long long* words;  // [n_steps][gridDim.x][3] partials then [n_steps][2] results, {fp32, step tag}; host-zeroed
   int slice;                  // S: interactions per CTA per step (multiple of 4)
   int32_t* oob;
@@ -349,9 +361,9 @@ __device__ __forceinline__ void task_issue(TaskRegs<VEC, PAIRWISE>& r, int lt, c
   r.ia = oka ? (int)ia : -1;
   r.ib = okb ? (int)ib : -1;
   r.sb = live ? 1.f : 0.f;  // until task_score overwrites it with the negative score: "this lane owns an interaction"
-  const float* pu = a.user_tab + (int64_t)(oku ? iu : 0) * row_f;
-  const float* pa = a.item_tab + (int64_t)(oka ? ia : 0) * row_f;
-  const float* pb = a.item_tab + (int64_t)(okb ? ib : 0) * row_f;
+  const float* pu = shard_row(a.user_tab, a.log2g, oku ? iu : 0, row_f);
+  const float* pa = shard_row(a.item_tab, a.log2g, oka ? ia : 0, row_f);
+  const float* pb = shard_row(a.item_tab, a.log2g, okb ? ib : 0, row_f);
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
@@ -430,12 +442,12 @@ __device__ __forceinline__ void scatter_cols(const StepsArgs& a, int cidx, float
                                              int ib, float4 ru, float4 ra, float4 rb) {
   const int64_t row_f = (int64_t)a.nv * 4;
   if (PAIRWISE) {
-    if (iu >= 0) red_add4(a.user_dst + iu * row_f, cidx, axpy4(cu, ru, scale4(c, sub4(ra, rb))));
-    if (ia >= 0) red_add4(a.item_dst + ia * row_f, cidx, axpy4(ci, ra, scale4(c, ru)));
-    if (ib >= 0) red_add4(a.item_dst + ib * row_f, cidx, scale4(-c, ru));
+    if (iu >= 0) red_add4(shard_row(a.user_dst, a.log2g, iu, row_f), cidx, axpy4(cu, ru, scale4(c, sub4(ra, rb))));
+    if (ia >= 0) red_add4(shard_row(a.item_dst, a.log2g, ia, row_f), cidx, axpy4(ci, ra, scale4(c, ru)));
+    if (ib >= 0) red_add4(shard_row(a.item_dst, a.log2g, ib, row_f), cidx, scale4(-c, ru));
   } else {
-    if (iu >= 0) red_add4(a.user_dst + iu * row_f, cidx, axpy4(cu, ru, scale4(c, ra)));
-    if (ia >= 0) red_add4(a.item_dst + ia * row_f, cidx, axpy4(ci, ra, scale4(c, ru)));
+    if (iu >= 0) red_add4(shard_row(a.user_dst, a.log2g, iu, row_f), cidx, axpy4(cu, ru, scale4(c, ra)));
+    if (ia >= 0) red_add4(shard_row(a.item_dst, a.log2g, ia, row_f), cidx, axpy4(ci, ra, scale4(c, ru)));
   }
 }
 
@@ -763,32 +775,36 @@ size_t xdr_steps_workspace_bytes(int n_steps) {
   return (size_t)n_steps * ((size_t)sm_count() * 3 + 2) * sizeof(unsigned long long);
 }
 
-int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
-                    const int64_t* user, const int64_t* item_a, const int64_t* item_b, const float* label,
-                    int64_t step_stride, int64_t batch, int n_steps, int pairwise, int loss_kind, float gamma,
-                    float reg_weight, const float* grad_loss, float scale, float* user_dst, float* item_dst, float* out8,
-                    void* steps_ws, size_t steps_ws_bytes, int32_t* oob, xdr_stream_t stream) {
-  XDR_REQUIRE(dim_ok(dim), "xdr_train_steps: dim=%d must be a multiple of 4 in (0, 256]", dim);
-  XDR_REQUIRE(batch > 0 && n_steps >= 0, "xdr_train_steps: batch=%lld n_steps=%d", (long long)batch, n_steps);
+static int train_steps_core(const Shards& user_tab, const Shards& item_tab, const Shards& user_dst, const Shards& item_dst,
+                            int log2g, int64_t n_users, int64_t n_items, int dim, const int64_t* user,
+                            const int64_t* item_a, const int64_t* item_b, const float* label, int64_t step_stride,
+                            int64_t batch, int n_steps, int pairwise, int loss_kind, float gamma, float reg_weight,
+                            const float* grad_loss, float scale, float* out8, void* steps_ws, size_t steps_ws_bytes,
+                            int32_t* oob, xdr_stream_t stream) {
+  const char* fn = "xdr_train_steps";
+  XDR_REQUIRE(dim_ok(dim), "%s: dim=%d must be a multiple of 4 in (0, 256]", fn, dim);
+  XDR_REQUIRE(batch > 0 && n_steps >= 0, "%s: batch=%lld n_steps=%d", fn, (long long)batch, n_steps);
   if (n_steps == 0) return XDR_OK;
-  XDR_REQUIRE(user_tab && item_tab && user && item_a && user_dst && item_dst && out8 && steps_ws,
-              "xdr_train_steps: null pointer");
-  XDR_REQUIRE(!pairwise || item_b, "xdr_train_steps: pairwise needs the negative-item ids");
-  XDR_REQUIRE(pairwise || loss_kind == XDR_LOSS_NONE || label, "xdr_train_steps: label is required for this loss kind");
-  XDR_REQUIRE(pairwise || (loss_kind >= XDR_LOSS_MSE && loss_kind <= XDR_LOSS_NONE), "xdr_train_steps: bad loss_kind");
-  XDR_REQUIRE(aligned16(user_tab) && aligned16(item_tab) && aligned16(user_dst) && aligned16(item_dst),
-              "xdr_train_steps: tables must be 16-byte aligned");
-  XDR_REQUIRE(step_stride >= batch, "xdr_train_steps: step_stride=%lld < batch", (long long)step_stride);
-  XDR_REQUIRE(steps_ws_bytes >= xdr_steps_workspace_bytes(n_steps), "xdr_train_steps: steps_ws too small (%zu < %zu)",
+  XDR_REQUIRE(user && item_a && out8 && steps_ws, "%s: null pointer", fn);
+  for (int g = 0; g < (1 << log2g); ++g) {
+    XDR_REQUIRE(user_tab.p[g] && item_tab.p[g] && user_dst.p[g] && item_dst.p[g], "%s: null table shard %d", fn, g);
+    XDR_REQUIRE(aligned16(user_tab.p[g]) && aligned16(item_tab.p[g]) && aligned16(user_dst.p[g]) && aligned16(item_dst.p[g]),
+                "%s: table shards must be 16-byte aligned", fn);
+  }
+  XDR_REQUIRE(!pairwise || item_b, "%s: pairwise needs the negative-item ids", fn);
+  XDR_REQUIRE(pairwise || loss_kind == XDR_LOSS_NONE || label, "%s: label is required for this loss kind", fn);
+  XDR_REQUIRE(pairwise || (loss_kind >= XDR_LOSS_MSE && loss_kind <= XDR_LOSS_NONE), "%s: bad loss_kind", fn);
+  XDR_REQUIRE(step_stride >= batch, "%s: step_stride=%lld < batch", fn, (long long)step_stride);
+  XDR_REQUIRE(steps_ws_bytes >= xdr_steps_workspace_bytes(n_steps), "%s: steps_ws too small (%zu < %zu)", fn,
               steps_ws_bytes, xdr_steps_workspace_bytes(n_steps));
   StepsPlan plan;
   // TMA bulk copies of the id tiles need 16-byte aligned sources and sizes
   const bool tma_ok = (batch % 4) == 0 && (step_stride % 4) == 0 && aligned16(user) && aligned16(item_a) &&
                       (!pairwise || aligned16(item_b)) && (label == nullptr || aligned16(label));
   if (!tma_ok || !plan_steps(batch, dim / 4, pairwise != 0, &plan)) {
-    set_error("xdr_train_steps: batch=%lld dim=%d (batch and step_stride must be multiples of 4, id arrays 16-byte "
-              "aligned, and a CTA slice must fit the stage ring or the register kernel); use the per-step entry points",
-              (long long)batch, dim);
+    set_error("%s: batch=%lld dim=%d (batch and step_stride must be multiples of 4, id arrays 16-byte aligned, and a "
+              "CTA slice must fit the stage ring or the register kernel); use the per-step entry points",
+              fn, (long long)batch, dim);
     return XDR_ERR_UNSUPPORTED;
   }
   if (g_force_regs && plan.stages > 0) {
@@ -800,10 +816,11 @@ int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_user
     }
   }
   StepsArgs a{};
-  a.user_tab = user_tab; a.item_tab = item_tab; a.n_users = n_users; a.n_items = n_items; a.nv = dim / 4;
+  a.user_tab = user_tab; a.item_tab = item_tab; a.user_dst = user_dst; a.item_dst = item_dst; a.log2g = log2g;
+  a.n_users = n_users; a.n_items = n_items; a.nv = dim / 4;
   a.user = user; a.item_a = item_a; a.item_b = item_b; a.label = label; a.step_stride = step_stride; a.batch = batch;
   a.n_steps = n_steps; a.loss_kind = loss_kind; a.gamma = gamma; a.reg_weight = reg_weight; a.out8 = out8;
-  a.grad_loss = grad_loss; a.scale = scale; a.user_dst = user_dst; a.item_dst = item_dst; a.slice = plan.slice; a.oob = oob;
+  a.grad_loss = grad_loss; a.scale = scale; a.slice = plan.slice; a.oob = oob;
   a.words = reinterpret_cast<unsigned long long*>(steps_ws);
   a.trace = g_trace;
   cudaStream_t s = (cudaStream_t)stream;
@@ -812,6 +829,84 @@ int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_user
   const int rc = pairwise ? dispatch_steps<true>(a, plan, s) : dispatch_steps<false>(a, plan, s);
   if (rc != XDR_OK) return rc;
   XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
+                    const int64_t* user, const int64_t* item_a, const int64_t* item_b, const float* label,
+                    int64_t step_stride, int64_t batch, int n_steps, int pairwise, int loss_kind, float gamma,
+                    float reg_weight, const float* grad_loss, float scale, float* user_dst, float* item_dst, float* out8,
+                    void* steps_ws, size_t steps_ws_bytes, int32_t* oob, xdr_stream_t stream) {
+  Shards ut{}, it{}, du{}, di{};
+  ut.p[0] = const_cast<float*>(user_tab);
+  it.p[0] = const_cast<float*>(item_tab);
+  du.p[0] = user_dst;
+  di.p[0] = item_dst;
+  return train_steps_core(ut, it, du, di, 0, n_users, n_items, dim, user, item_a, item_b, label, step_stride, batch,
+                          n_steps, pairwise, loss_kind, gamma, reg_weight, grad_loss, scale, out8, steps_ws,
+                          steps_ws_bytes, oob, stream);
+}
+
+int xdr_train_steps_sharded(const float* const* user_shards, const float* const* item_shards, float* const* user_dst_shards,
+                            float* const* item_dst_shards, int n_shards, int64_t n_users, int64_t n_items, int dim,
+                            const int64_t* user, const int64_t* item_a, const int64_t* item_b, const float* label,
+                            int64_t step_stride, int64_t batch, int n_steps, int pairwise, int loss_kind, float gamma,
+                            float reg_weight, const float* grad_loss, float scale, float* out8, void* steps_ws,
+                            size_t steps_ws_bytes, int32_t* oob, xdr_stream_t stream) {
+  XDR_REQUIRE(n_shards >= 1 && n_shards <= kMaxShards && (n_shards & (n_shards - 1)) == 0,
+              "xdr_train_steps_sharded: n_shards=%d must be a power of two <= %d", n_shards, kMaxShards);
+  XDR_REQUIRE(user_shards && item_shards && user_dst_shards && item_dst_shards, "xdr_train_steps_sharded: null pointer");
+  Shards ut{}, it{}, du{}, di{};
+  int log2g = 0;
+  while ((1 << log2g) < n_shards) ++log2g;
+  for (int g = 0; g < n_shards; ++g) {
+    ut.p[g] = const_cast<float*>(user_shards[g]);
+    it.p[g] = const_cast<float*>(item_shards[g]);
+    du.p[g] = user_dst_shards[g];
+    di.p[g] = item_dst_shards[g];
+  }
+  return train_steps_core(ut, it, du, di, log2g, n_users, n_items, dim, user, item_a, item_b, label, step_stride, batch,
+                          n_steps, pairwise, loss_kind, gamma, reg_weight, grad_loss, scale, out8, steps_ws,
+                          steps_ws_bytes, oob, stream);
+}
+
+// ---- peer-memory plumbing for row-sharded tables (CUDA IPC; one process per GPU) --------------------------------------
+int xdr_ipc_export(const void* dev_ptr, unsigned char* handle64_host, int64_t* offset_host) {
+  XDR_REQUIRE(dev_ptr && handle64_host && offset_host, "xdr_ipc_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaPointerAttributes attr;
+  XDR_CUDA_OK(cudaPointerGetAttributes(&attr, dev_ptr));
+  XDR_REQUIRE(attr.type == cudaMemoryTypeDevice, "xdr_ipc_export: not a device pointer");
+  // the IPC handle names the whole allocation: find its base with a page-granular probe of the driver's range query
+  void* base = nullptr;
+  size_t size = 0;
+  {
+    typedef int (*range_fn)(void**, size_t*, void*);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    XDR_CUDA_OK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+    XDR_REQUIRE(fn != nullptr, "xdr_ipc_export: cuMemGetAddressRange unavailable");
+    const int rc = reinterpret_cast<range_fn>(fn)(&base, &size, const_cast<void*>(dev_ptr));
+    XDR_REQUIRE(rc == 0 && base != nullptr, "xdr_ipc_export: cuMemGetAddressRange failed (%d)", rc);
+  }
+  cudaIpcMemHandle_t h;
+  XDR_CUDA_OK(cudaIpcGetMemHandle(&h, base));
+  memcpy(handle64_host, &h, 64);
+  *offset_host = (int64_t)(reinterpret_cast<const char*>(dev_ptr) - reinterpret_cast<const char*>(base));
+  return XDR_OK;
+}
+
+int xdr_ipc_open(const unsigned char* handle64_host, void** base_out_host) {
+  XDR_REQUIRE(handle64_host && base_out_host, "xdr_ipc_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64_host, 64);
+  XDR_CUDA_OK(cudaIpcOpenMemHandle(base_out_host, h, cudaIpcMemLazyEnablePeerAccess));
+  return XDR_OK;
+}
+
+int xdr_ipc_close(void* base) {
+  XDR_REQUIRE(base, "xdr_ipc_close: null pointer");
+  XDR_CUDA_OK(cudaIpcCloseMemHandle(base));
   return XDR_OK;
 }
 

@@ -170,7 +170,9 @@ def workload_config(args, ds):
     return {'workload': f'EMCDR BPR SOURCE-phase step, synthetic {args.workload} (BASELINE configs[1] shape)',
             'users_total': ds.num_total_user, 'items_total': ds.num_total_item, 'dim': 64, 'batch_per_gpu': args.batch,
             'loss': 'BPR + 0.01*EmbLoss', 'l2': 'inputs larger than L2 (0.9 GB of tables, uniform random rows)',
-            'parallelism': 'tables replicated per GPU, batch data-parallel' if args.gpus > 1 else 'single GPU'}
+            'parallelism': (f'tables row-sharded over {args.gpus} GPUs (r mod G) on peer memory, batch data-parallel and '
+                            'routed by user owner; gathers/scatter-adds cross NVLink inside the kernel, no collective on '
+                            'the data path') if args.gpus > 1 else 'single GPU'}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -198,17 +200,35 @@ def run_xdr(args):
     cfg = {'source_domain': {'NEG_PREFIX': 'neg_'}, 'target_domain': {'NEG_PREFIX': 'neg_'}, 'device': dev,
            'latent_factor_model': 'BPR', 'source_embedding_size': D, 'target_embedding_size': D, 'reg_weight': 0.01,
            'mapping_function': 'non_linear', 'mlp_hidden_size': [128]}
-    torch.manual_seed(2022)
-    with torch.device(dev):
-        model = EMCDR(cfg, ds)  # random-init weights of the named architecture, created directly in HBM
-    model.set_phase('SOURCE')
-    ut, it = model.source_user_embedding.weight, model.source_item_embedding.weight
-    gu, gi = torch.zeros_like(ut), torch.zeros_like(it)
+    sharded = world > 1
+    if not sharded:
+        torch.manual_seed(2022)
+        with torch.device(dev):
+            model = EMCDR(cfg, ds)  # random-init weights of the named architecture, created directly in HBM
+        model.set_phase('SOURCE')
+        ut, it = model.source_user_embedding.weight, model.source_item_embedding.weight
+        gu, gi = torch.zeros_like(ut), torch.zeros_like(it)
+    else:
+        # row-sharded tables (block-cyclic, r mod G) mapped over CUDA IPC; every rank holds 1/G of each table and of
+        # each gradient table; xavier-normal random init of the named shapes, created directly in HBM
+        from recbole_cdr_b200 import shard
+        torch.manual_seed(2022 + rank)
+        def mk(n, fill):
+            rows = shard.shard_rows(n, world)
+            loc = (torch.randn(rows, D, device=dev) * (2.0 / (n + D)) ** 0.5) if fill else torch.zeros(rows, D, device=dev)
+            return shard.RowShardedTable(n, D, rank, world, dev, loc).connect()
+        s_ut, s_it = mk(ds.num_total_user, True), mk(ds.num_total_item, True)
+        s_gu, s_gi = mk(ds.num_total_user, False), mk(ds.num_total_item, False)
+        dist.barrier()
 
     # K + W distinct seeded batches (seed = 1 + step, offset per rank), resident in HBM and mirrored in pinned host memory
     def batch_ids(step):
         b = synthetic.make_batch(ds, 'source', B, 1 + step + 100_003 * rank, 'cpu', pairwise=True)
-        return torch.stack([b['source_user_id'], b['source_item_id'], b['neg_source_item_id']])
+        u = b['source_user_id']
+        if sharded:  # the loader routes an interaction to the rank that owns its user row: user % G == rank
+            u = u - ((u - rank) % world)
+            u = torch.where(u < 1, u + world, u)
+        return torch.stack([u, b['source_item_id'], b['neg_source_item_id']])
 
     host = torch.stack([batch_ids(s) for s in range(K + W)]).pin_memory()  # [K+W, 3, B] int64
     ids = host.to(dev)
@@ -228,15 +248,19 @@ def run_xdr(args):
 
     def persistent(lo, hi):
         """steps [lo, hi) as ONE persistent launch (xdr_train_steps): fwd + bwd + scatter-add per batch"""
-        ops.train_steps(ut.data, it.data, ids[lo:hi, 0], ids[lo:hi, 1], ids[lo:hi, 2], reg_weight=0.01, user_dst=gu,
-                        item_dst=gi, out8=out8[lo:hi])
+        if sharded:
+            shard.train_steps_sharded(s_ut, s_it, s_gu, s_gi, ids[lo:hi, 0], ids[lo:hi, 1], ids[lo:hi, 2],
+                                      reg_weight=0.01, out8=out8[lo:hi])
+        else:
+            ops.train_steps(ut.data, it.data, ids[lo:hi, 0], ids[lo:hi, 1], ids[lo:hi, 2], reg_weight=0.01, user_dst=gu,
+                            item_dst=gi, out8=out8[lo:hi])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_persistent = args.mode == 'persistent' and ops.train_steps_supported(B, D, True, dev)
+    use_persistent = sharded or (args.mode == 'persistent' and ops.train_steps_supported(B, D, True, dev))
     # ---- device-resident throughput -----------------------------------------------------------------------------
     if use_persistent:
         persistent(0, W)
@@ -263,7 +287,7 @@ def run_xdr(args):
 
     extra = {}
     # ---- same launch with the scatter-add aimed at the weight tables (scale = -lr): the SGD update fused into the step
-    if use_persistent:
+    if use_persistent and not sharded:
         ops.train_steps(ut.data, it.data, ids[:W, 0], ids[:W, 1], ids[:W, 2], reg_weight=0.01, user_dst=ut.data,
                         item_dst=it.data, scale=-1e-3, out8=out8[:W])
         barrier()
@@ -283,7 +307,7 @@ def run_xdr(args):
             'value': fused_rate, 'ms_per_step': fms.item() / K,
             'roofline_frac': BYTES_PER_INTERACTION_BPR_D64 * fused_rate / world / 1e9 / measured_peaks()[0]}
     # ---- for comparison: the per-step kernel pair replayed from a CUDA graph (no host launch cost) -----------------
-    if use_persistent and rank == 0 and not args.no_compare:
+    if use_persistent and not sharded and rank == 0 and not args.no_compare:
         side = torch.cuda.Stream()
         with torch.cuda.stream(side):
             for s in range(3):
@@ -319,7 +343,12 @@ def run_xdr(args):
         from recbole_cdr_b200.trainer import FusedStepRunner
         chunk = min(args.chunk, K)
         n_chunks = K // chunk
-        runner = FusedStepRunner(model.fused_step_spec(), lr=None, grad_tables=(gu, gi))
+        if sharded:
+            def launch(idb, _label, o8):
+                shard.train_steps_sharded(s_ut, s_it, s_gu, s_gi, idb[:, 0], idb[:, 1], idb[:, 2], reg_weight=0.01, out8=o8)
+            runner = FusedStepRunner({'pairwise': True}, launch=launch, device=dev)
+        else:
+            runner = FusedStepRunner(model.fused_step_spec(), lr=None, grad_tables=(gu, gi))
         blocks = [host[W + c * chunk: W + (c + 1) * chunk] for c in range(n_chunks)]  # pinned [chunk, 3, B] views
         for c in range(min(3, n_chunks)):
             runner.run(blocks[c])
@@ -363,7 +392,7 @@ def run_xdr(args):
             'e2e': e2e, 'gpu_launches': launches, 'clocks': clk, 'loss_mean': loss_mean,
         }
         line.update(extra)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             rate, sec, cores = cpu_reference_step_rate(ds, B, 1, args.cpu_steps)
             line['cpu_baseline'] = {
                 'value': rate, 'unit': 'interactions/s', 'cores': cores, 'kind': 'port',

@@ -33,15 +33,20 @@ class FusedStepRunner:
     pinned host tensor (valid after ``synchronize()``).
     """
 
-    def __init__(self, spec: Dict, lr: Optional[float] = None, grad_tables=None, n_buffers: int = 2):
+    def __init__(self, spec: Dict, lr: Optional[float] = None, grad_tables=None, n_buffers: int = 2, launch=None,
+                 device=None):
         self.spec = spec
-        self.ut, self.it = spec['user_tab'], spec['item_tab']
-        self.dev = self.ut.device
-        if lr is not None:      # fused SGD: the scatter-add target is the weight table itself
-            self.dst_u, self.dst_i, self.scale = self.ut.data, self.it.data, -float(lr)
-        else:                   # gradient accumulation into dense .grad-style tables
-            gu, gi = grad_tables if grad_tables is not None else (torch.zeros_like(self.ut), torch.zeros_like(self.it))
-            self.dst_u, self.dst_i, self.scale = gu, gi, 1.0
+        self.launch = launch    # optional callable(ids [K,R,B], label, out8): e.g. the row-sharded multi-GPU launch
+        if launch is None:
+            self.ut, self.it = spec['user_tab'], spec['item_tab']
+            self.dev = self.ut.device
+            if lr is not None:      # fused SGD: the scatter-add target is the weight table itself
+                self.dst_u, self.dst_i, self.scale = self.ut.data, self.it.data, -float(lr)
+            else:                   # gradient accumulation into dense .grad-style tables
+                gu, gi = grad_tables if grad_tables is not None else (torch.zeros_like(self.ut), torch.zeros_like(self.it))
+                self.dst_u, self.dst_i, self.scale = gu, gi, 1.0
+        else:
+            self.dev = torch.device(device)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.n_buffers = n_buffers
         self._bufs = []  # per in-flight chunk: (dev ids, dev label, out8, host loss, ready event, done event)
@@ -80,10 +85,13 @@ class FusedStepRunner:
             buf['ready'].record(self.copy_stream)
         main.wait_event(buf['ready'])
         ids = buf['ids']
-        ops.train_steps(self.ut.data, self.it.data, ids[:, 0], ids[:, 1], ids[:, 2] if sp['pairwise'] else None,
-                        buf['label'], loss_kind=sp.get('loss_kind', _lib.LOSS_MSE), reg_weight=sp['reg_weight'],
-                        gamma=sp.get('gamma', 1e-10), user_dst=self.dst_u, item_dst=self.dst_i, scale=self.scale,
-                        out8=buf['out8'])
+        if self.launch is not None:
+            self.launch(ids, buf['label'], buf['out8'])
+        else:
+            ops.train_steps(self.ut.data, self.it.data, ids[:, 0], ids[:, 1], ids[:, 2] if sp['pairwise'] else None,
+                            buf['label'], loss_kind=sp.get('loss_kind', _lib.LOSS_MSE), reg_weight=sp['reg_weight'],
+                            gamma=sp.get('gamma', 1e-10), user_dst=self.dst_u, item_dst=self.dst_i, scale=self.scale,
+                            out8=buf['out8'])
         self.launches += 1
         buf['loss'].copy_(buf['out8'][:, 0], non_blocking=True)
         buf['done'].record(main)

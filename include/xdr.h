@@ -182,6 +182,20 @@ XDR_API int xdr_train_steps(const float* user_tab, const float* item_tab, int64_
                             float reg_weight, const float* grad_loss, float scale, float* user_dst, float* item_dst,
                             float* out8, void* steps_ws, size_t steps_ws_bytes, int32_t* oob, xdr_stream_t stream);
 
+/* ---- A18: uniform negative draw with per-user rejection ----------------------------------------------------------------
+ * Replaces CrossDomainSourceSampler._uni_sampling + AbstractSampler.sample_by_key_ids (sampler/crossdomain_sampler.py:
+ * 220-221, 139-176) and recbole's target-domain Sampler.  out[j*n_keys + p] (j < num) is a valid item id of the domain
+ * drawn uniformly and never in used[key_ids[p]] (CSR, columns sorted per row: the get_used_ids sets of :229-250).
+ * Candidate k in [0, n_valid) maps to id k+1 if k+1 < n_overlap else k+1+n_gap (source domain: n_gap = n_target_only
+ * items; target domain: n_gap = 0, n_overlap = item_num).  Draws are Philox4x32-10(key = seed, counter = position,
+ * attempt, stream_id): deterministic and bit-identical to oracle/sampler_oracle.py.  *status |= 1 if some position
+ * exhausted max_attempts (a user that used every item: the reference raises ValueError at construction), |= 2 for a key
+ * id outside [0, n_rows) (the reference: ValueError('user_id ... not exist')).                                        */
+XDR_API int xdr_neg_sample_uniform(const int64_t* key_ids, int64_t n_keys, int num, const int64_t* used_rowptr,
+                                   const int64_t* used_col, int64_t n_rows, int64_t n_overlap, int64_t n_gap,
+                                   int64_t n_valid, uint64_t seed, uint32_t stream_id, int max_attempts, int64_t* out,
+                                   int32_t* status, xdr_stream_t stream);
+
 /* ---- E1: row-sharded tables over peer memory (one process per GPU, NVLink) --------------------------------------------
  * The reference is single-device (no collective anywhere); this is the B200 addition.  A table of
  * n global rows is split block-cyclically over G = n_shards GPUs (G a power of two <= 8): global row r lives on shard

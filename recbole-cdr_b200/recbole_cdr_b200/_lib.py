@@ -48,6 +48,8 @@ PROTOTYPES = {
     'xdr_ipc_export': (c_int, [c_vp, c_vp, ctypes.POINTER(c_i64)]),
     'xdr_ipc_open': (c_int, [c_vp, ctypes.POINTER(c_vp)]),
     'xdr_ipc_close': (c_int, [c_vp]),
+    'xdr_neg_sample_uniform': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_uint64,
+                                       ctypes.c_uint32, c_int, c_vp, c_vp, c_vp]),
     'xdr_select_dot': (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
 }
 

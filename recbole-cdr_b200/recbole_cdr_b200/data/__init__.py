@@ -1,2 +1,3 @@
 from .interaction import Interaction  # noqa: F401
 from .idspace import IdSpace  # noqa: F401
+from .dataloader import CrossDomainDataloader, DomainTrainDataLoader, OverlapDataloader  # noqa: F401

@@ -182,6 +182,34 @@ XDR_API int xdr_train_steps(const float* user_tab, const float* item_tab, int64_
                             float reg_weight, const float* grad_loss, float scale, float* user_dst, float* item_dst,
                             float* out8, void* steps_ws, size_t steps_ws_bytes, int32_t* oob, xdr_stream_t stream);
 
+/* ---- A10-A12: BiTGCF graph propagate-and-transfer ------------------------------------------------------------------------
+ * xdr_spmm_csr: S[r,:] = sum_e val[e] * X[col[e],:] over CSR work items -- replaces torch.sparse.mm(L, E) of
+ * BiTGCF.graph_layer (bitgcf.py:131).  Rows are pre-cut into work items of bounded length (heavy-tailed item degrees):
+ * work_row/beg/end [n_work], work_split[w] != 0 when the row has several items (those rows, listed in split_rows, are
+ * zeroed and accumulated with vector atomics; single-item rows are stored directly).
+ * xdr_prop_elementwise: mode 0  out = A + B + A*B        E' = E + S + E*S, bitgcf.py:132-133 (A = E, B = S)
+ *                       mode 1  out = A * (1 + B)        backward: dS = dE' * (1 + E)         (A = dE', B = E)
+ *                       mode 2  out = A * (1 + B) + C    backward: dE = dE' * (1 + S) + L.dS  (A = dE', B = S, C = L.dS)
+ * xdr_transfer_norm_fwd: transfer_layer (bitgcf.py:137-172) on both domains + F.normalize (bitgcf.py:185-186) in one
+ * pass: Ps/Pt [N, dim] propagated tables -> Es/Et transferred tables (next layer's input) and Ns/Nt normalised rows
+ * (row stride n_ld floats, so they can land in a slot of the layer-concat buffer).  N = n_users + n_items nodes, users
+ * first; rows [0, n_ov_users) and [n_users, n_users + n_ov_items) are mixed, all others pass through.  deg_s/deg_t [N]:
+ * per-node degree in each domain (bitgcf.py:79-82).  xdr_transfer_norm_bwd is its backward (dEs2/dEt2: gradient that
+ * reaches the transferred tables from the next layer, NULL for the last layer).                                       */
+XDR_API int xdr_spmm_csr(const int64_t* work_row, const int64_t* work_beg, const int64_t* work_end,
+                         const uint8_t* work_split, int64_t n_work, const int64_t* split_rows, int64_t n_split_rows,
+                         const int64_t* col, const float* val, const float* X, int dim, float* S, xdr_stream_t stream);
+XDR_API int xdr_prop_elementwise(const float* A, const float* B, const float* C, float* out, int64_t count, int mode,
+                                 xdr_stream_t stream);
+XDR_API int xdr_transfer_norm_fwd(const float* Ps, const float* Pt, int64_t n_users, int64_t n_items, int64_t n_ov_users,
+                                  int64_t n_ov_items, int dim, float lam_s, float lam_t, const float* deg_s,
+                                  const float* deg_t, float* Es, float* Et, float* Ns, float* Nt, int64_t n_ld,
+                                  xdr_stream_t stream);
+XDR_API int xdr_transfer_norm_bwd(const float* Es, const float* Et, const float* dNs, const float* dNt, int64_t n_ld,
+                                  const float* dEs2, const float* dEt2, int64_t n_users, int64_t n_items,
+                                  int64_t n_ov_users, int64_t n_ov_items, int dim, float lam_s, float lam_t,
+                                  const float* deg_s, const float* deg_t, float* dPs, float* dPt, xdr_stream_t stream);
+
 /* ---- A18: uniform negative draw with per-user rejection ----------------------------------------------------------------
  * Replaces CrossDomainSourceSampler._uni_sampling + AbstractSampler.sample_by_key_ids (sampler/crossdomain_sampler.py:
  * 220-221, 139-176) and recbole's target-domain Sampler.  out[j*n_keys + p] (j < num) is a valid item id of the domain

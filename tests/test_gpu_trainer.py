@@ -82,12 +82,13 @@ def test_fused_sgd_epoch_tracks_the_per_batch_sgd_path():
     out = {}
     for fused in (0, 8):
         ds, loader = make_world(pairwise=True, seed=3)
-        cfg = emcdr_cfg(learner='sgd', learning_rate=0.5, train_modes=['SOURCE'], epoch_num=['3'], xdr_fused_steps=fused)
+        cfg = emcdr_cfg(learner='sgd', learning_rate=20.0, reg_weight=0.0, train_modes=['SOURCE'], epoch_num=['4'],
+                        xdr_fused_steps=fused)
         torch.manual_seed(2022)
         model = get_model('EMCDR')(cfg, ds).to('cuda')
         trainer = get_trainer(ModelType.CROSSDOMAIN, 'EMCDR')(cfg, model)
         seen = []
         trainer.fit(loader, callback_fn=lambda epoch, loss: seen.append(loss))
         out[fused] = seen
-    assert out[8][2] < out[8][0]
-    np.testing.assert_allclose(out[8], out[0], rtol=2e-3)
+    assert out[8][-1] < out[8][0] - 1e-3 and out[0][-1] < out[0][0] - 1e-3
+    np.testing.assert_allclose(out[8], out[0], rtol=5e-3)

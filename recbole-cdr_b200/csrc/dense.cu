@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kDenseThreads)
 
 // ---- backward wrt weight: dW[N,K] += (mask*dZ)[M,N]^T X[M,K]; db[N] += colsum(dZ) -------------------------------
 // grid = (N tiles, K tiles, M chunks); each CTA reduces kChunkM rows and adds its tile with fp32 atomics.
-constexpr int kChunkM = 1024;
+constexpr int kChunkM = 128;
 __global__ void __launch_bounds__(kDenseThreads)
     dense_bwd_weight_kernel(const float* __restrict__ dZ, const float* __restrict__ X, const int64_t* __restrict__ mask_ids,
                             int64_t mask_lt, float* __restrict__ dW, float* __restrict__ db, int64_t M, int N, int K) {

@@ -21,13 +21,14 @@ class NormAdj(object):
         n = n_users + n_items
         rows = np.asarray(rows, dtype=np.int64)
         cols = np.asarray(cols, dtype=np.int64)
-        edges = np.unique(np.stack([rows, cols], 1), axis=0) if rows.size else np.zeros((0, 2), np.int64)
-        r = np.concatenate([edges[:, 0], edges[:, 1] + n_users])
-        c = np.concatenate([edges[:, 1] + n_users, edges[:, 0]])
+        keys = np.unique(rows * np.int64(n_items) + cols)          # de-duplicated (user, item) pairs, sorted by (user, item)
+        eu, ei = keys // n_items, keys % n_items
+        r = np.concatenate([eu, ei + n_users])
+        c = np.concatenate([ei + n_users, eu])
         deg = np.bincount(r, minlength=n).astype(np.float64) + 1e-7
         dinv = np.power(deg, -0.5)
         val = (dinv[r] * 1.0 * dinv[c]).astype(np.float32)
-        order = np.lexsort((c, r))
+        order = np.argsort(r * np.int64(n) + c, kind='stable')  # CSR order: by row, then column
         r, c, val = r[order], c[order], val[order]
         rowptr = np.zeros(n + 1, dtype=np.int64)
         np.add.at(rowptr, r + 1, 1)

@@ -1,0 +1,82 @@
+"""CUDA-graph capture of one whole training step (forward + backward [+ optimizer]) of a drop-in model.
+
+The composed models (EMCDR map phase, CoNet, DTCDR, BiTGCF) are chains of 20-60 small libxdr kernels per step; launched
+one by one from Python the step is pure host overhead (measured: DTCDR 1.24 ms/step eager for ~0.15 ms of GPU work).
+Static batch shapes make the chain capturable: ids/labels live in static device buffers, the captured graph is replayed
+per batch with no Python between kernels.  This is the "CUDA streams and graphs instead of a tracing compiler" path: the
+kernels are the same hand-written ones, only the launch mechanism changes.
+
+Embedding-table gradients follow ``ops`` table-grad mode ``'inplace'`` during capture: ``loss.backward()`` scatter-adds
+into the persistent ``weight.grad`` of every table (allocated once, before capture), so no dense ``[N, D]`` tensor is
+created or zero-filled inside the graph.  Small dense parameters get fresh ``.grad`` tensors from the graph's pool.
+"""
+from typing import Callable, Optional
+
+import torch
+
+from .. import ops
+from ..data.interaction import Interaction
+
+_TABLE_NUMEL = 1 << 18  # parameters at least this large are treated as embedding tables (persistent .grad)
+
+
+class GraphedTrainStep(object):
+    def __init__(self, model, example: Interaction, optimizer: Optional[torch.optim.Optimizer] = None,
+                 loss_fn: Optional[Callable] = None, warmup: int = 3):
+        self.model, self.optimizer = model, optimizer
+        self.loss_fn = loss_fn or model.calculate_loss
+        self.static = Interaction({k: example[k].clone() for k in example.columns})
+        self._prev_mode = ops.get_table_grad_mode()
+        ops.set_table_grad_mode('inplace')
+        self._table_grads = {}
+        for p in model.parameters():
+            if p.numel() >= _TABLE_NUMEL:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                self._table_grads[p] = p.grad   # the captured kernels scatter-add into exactly this memory
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._zero_small()
+                self._step()
+            torch.cuda.synchronize()
+            self._zero_small()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.loss = self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        ops.set_table_grad_mode(self._prev_mode)
+
+    def zero_table_grads(self):
+        for gbuf in self._table_grads.values():
+            gbuf.zero_()
+
+    def _zero_small(self):
+        for p in self.model.parameters():
+            if p.numel() < _TABLE_NUMEL:
+                p.grad = None
+
+    def _step(self):
+        losses = self.loss_fn(self.static)
+        loss = sum(losses) if isinstance(losses, tuple) else losses
+        loss = loss.sum()
+        loss.backward()
+        if self.optimizer is not None:
+            self.optimizer.step()
+        return loss.detach()
+
+    def __call__(self, interaction: Interaction) -> torch.Tensor:
+        """Copy the batch into the static buffers (shapes must match the example) and replay the captured step.
+        Table gradients ACCUMULATE in the persistent ``weight.grad`` buffers across calls (``zero_table_grads()`` clears
+        them); if the caller dropped or replaced ``weight.grad`` it is re-attached here."""
+        for p, gbuf in self._table_grads.items():
+            if p.grad is not gbuf:
+                p.grad = gbuf
+        for k in self.static.columns:
+            src = interaction[k]
+            if src.shape != self.static[k].shape:
+                raise ValueError(f'field {k}: shape {tuple(src.shape)} differs from the captured {tuple(self.static[k].shape)}')
+            self.static[k].copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -92,3 +92,38 @@ def test_fused_sgd_epoch_tracks_the_per_batch_sgd_path():
         out[fused] = seen
     assert out[8][-1] < out[8][0] - 1e-3 and out[0][-1] < out[0][0] - 1e-3
     np.testing.assert_allclose(out[8], out[0], rtol=5e-3)
+
+
+def test_graphed_step_equals_eager_step():
+    """CUDA-graph replay of (calculate_loss + backward) gives the eager step's loss and gradients, batch after batch."""
+    from recbole_cdr_b200 import ops
+    from recbole_cdr_b200.data import Interaction
+    from recbole_cdr_b200.trainer import GraphedTrainStep
+    from recbole_cdr_b200.utils import get_model
+    ds = FakeDataset(201, 300, 280, 101, 500, 450)
+    cfg = base_config(embedding_size=64, mlp_hidden_size=[32, 16], dropout_prob=0.0, base_model='NeuMF', alpha=0.4)
+    torch.manual_seed(1)
+    model = get_model('DTCDR')(cfg, ds).to('cuda')
+    rng = np.random.RandomState(0)
+
+    def batch(seed):
+        from fake_data import make_batch
+        r = np.random.RandomState(seed)
+        b = make_batch(ds, 'source', 512, r)
+        b.update(make_batch(ds, 'target', 512, r))
+        return Interaction(b).to('cuda')
+
+    import copy
+    eager = copy.deepcopy(model)
+    step = GraphedTrainStep(model, batch(0))
+    for seed in (1, 2, 3):
+        b = batch(seed)
+        step.zero_table_grads()
+        loss_g = step(b).clone()
+        eager.zero_grad(set_to_none=True)
+        loss_e = eager.calculate_loss(b)
+        loss_e.sum().backward()
+        torch.testing.assert_close(loss_g, loss_e.detach().sum(), rtol=1e-6, atol=0)
+        ge = dict(eager.named_parameters())
+        for n, p in model.named_parameters():
+            torch.testing.assert_close(p.grad, ge[n].grad, rtol=1e-4, atol=1e-7, msg=lambda s: f'{n}: {s}')

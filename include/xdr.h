@@ -154,6 +154,28 @@ XDR_API int xdr_bce_logit_fwd(const float* logit, const float* label, int64_t co
 XDR_API int xdr_bce_logit_bwd(const float* prob, const float* label, int64_t count, const float* grad_loss,
                       float* dlogit, xdr_stream_t stream);
 
+/* ---- A4 / A14-A15 fused: gather -> small MLP -> loss head -> backward -> scatter-add in one persistent kernel ------------
+ * Replaces the whole of EMCDR.calculate_map_loss (emcdr.py:156-168, mapping of emcdr.py:58-64,86-93) and of one
+ * DTCDR.neumf_forward + BCELoss term (dtcdr.py:112-125,186-187, recbole MLPLayers) including their backward.
+ *   layers: n_layers (1..3) nn.Linear weights W[l] [dims[l+1], dims[l]] / biases b[l] (NULL = none); hidden_act after
+ *           every layer but the last; *_host arguments are HOST arrays of device pointers.
+ *   in_mode 0: x = Au[idx_u]                                         (dims[0] = dim)
+ *   in_mode 1: x = [max(Au[u], Bu[u]) | max(Ai[i], Bi[i])]           (dims[0] = 2*dim)
+ *   head 0: loss = mean((y - T[idx_u])^2), T not detached            (dims[n] = dim)
+ *   head 1: loss = mean BCE(sigmoid(y), label), prob[] optional      (dims[n] = 1)
+ *   backward != 0: also dW[l] += , db[l] += , and scatter-adds scale * g * dL/drow into dAu/dBu/dAi/dBi (torch.maximum
+ *   routing) and dT; g = *grad_loss.  backward == 0: loss (and prob) only.
+ * Weights live in shared memory (W and W^T), activations of a 32-row tile never leave it, weight gradients accumulate
+ * in registers across a CTA's tiles.  xdr_fused_mlp_supported() says whether a layer stack fits.                        */
+XDR_API int xdr_fused_mlp_supported(int n_layers, const int* dims_host);
+XDR_API int xdr_fused_mlp_step(int n_layers, const int* dims_host, const float* const* W_host, const float* const* b_host,
+                               float* const* dW_host, float* const* db_host, int hidden_act, int in_mode, int head,
+                               const float* Au, const float* Bu, const float* Ai, const float* Bi, const float* T,
+                               int64_t n_u, int64_t n_i, int dim, const int64_t* idx_u, const int64_t* idx_i,
+                               const float* label, int64_t batch, int backward, const float* grad_loss, float scale,
+                               float* dAu, float* dBu, float* dAi, float* dBi, float* dT, float* prob, float* out8,
+                               void* ws, int32_t* oob, xdr_stream_t stream);
+
 /* ---- A6: EMCDR predict tail: select mapped vs. target row, then dot ------------------------------------------
  * Replaces the torch.where + mul + sum of EMCDR.predict, OVERLAP/BOTH phase (emcdr.py:191-205):
  *   e = (sel_ids[b] < n_overlap) ? mapped[b, :] : tgt_tab[sel_ids[b], :];   score[b] = e . other_tab[other_ids[b], :]

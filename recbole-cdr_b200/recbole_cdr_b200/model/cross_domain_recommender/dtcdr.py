@@ -46,6 +46,22 @@ class DTCDR(CrossDomainRecommender):
         self.target_predict_layer = nn.Linear(self.mlp_hidden_size[-1], 1)
 
         self.apply(xavier_normal_initialization)
+        self.use_fused_mlp = config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else True
+
+    def _tower(self, domain):
+        mlp = self.source_mlp_layers if domain == 'source' else self.target_mlp_layers
+        out = self.source_predict_layer if domain == 'source' else self.target_predict_layer
+        lins = [m for m in mlp.mlp_layers if isinstance(m, nn.Linear)] + [out]
+        return [l.weight for l in lins], [l.bias for l in lins]
+
+    def _fused_ok(self):
+        dims = [2 * self.embedding_size] + self.mlp_hidden_size + [1]
+        no_dropout = self.dropout_prob == 0 or not self.training
+        return self.use_fused_mlp and no_dropout and ops.fused_mlp_supported(dims)
+
+    def _tables(self):
+        return (self.source_user_embedding.weight, self.target_user_embedding.weight, self.source_item_embedding.weight,
+                self.target_item_embedding.weight, None)
 
     def _logit(self, user, item, domain):
         x = ops.GatherMax2Concat.apply(self.source_user_embedding.weight, self.target_user_embedding.weight,
@@ -61,6 +77,15 @@ class DTCDR(CrossDomainRecommender):
 
     def calculate_loss(self, interaction):
         """alpha*BCE_s + (1-alpha)*BCE_t (dtcdr.py:177-191)."""
+        if self._fused_ok():
+            # per domain: ONE kernel forward and ONE backward (gather + max-combine + MLP + BCE + scatter)
+            ws, bs = self._tower('source')
+            loss_s = ops.fused_mlp_loss(1, 1, _lib.ACT_RELU, interaction[self.SOURCE_USER_ID], interaction[self.SOURCE_ITEM_ID],
+                                        interaction[self.SOURCE_LABEL], self._tables(), ws, bs)
+            wt, bt = self._tower('target')
+            loss_t = ops.fused_mlp_loss(1, 1, _lib.ACT_RELU, interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID],
+                                        interaction[self.TARGET_LABEL], self._tables(), wt, bt)
+            return loss_s * self.alpha + loss_t * (1 - self.alpha)
         logit_s = self._logit(interaction[self.SOURCE_USER_ID], interaction[self.SOURCE_ITEM_ID], 'source')
         logit_t = self._logit(interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID], 'target')
         loss_s, _ = ops.bce_logit(logit_s, interaction[self.SOURCE_LABEL])
@@ -69,4 +94,8 @@ class DTCDR(CrossDomainRecommender):
 
     def predict(self, interaction):
         with torch.no_grad():
+            if self._fused_ok():
+                wt, bt = self._tower('target')
+                return ops.fused_mlp_prob(_lib.ACT_RELU, interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID],
+                                          self._tables(), wt, bt)
             return self.neumf_forward(interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID], 'target')

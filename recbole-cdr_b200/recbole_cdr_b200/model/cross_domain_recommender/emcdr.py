@@ -42,6 +42,7 @@ class EMCDR(CrossDomainRecommender):
         else:
             self.input_type = InputType.PAIRWISE
         self.bpr_gamma = 1e-10  # recbole BPRLoss default
+        self.use_fused_mlp = config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else True
         self.source_latent_dim = config['source_embedding_size']
         self.target_latent_dim = config['target_embedding_size']
         self.reg_weight = config['reg_weight']
@@ -123,6 +124,11 @@ class EMCDR(CrossDomainRecommender):
         else:
             src, tgt = self.source_item_embedding.weight, self.target_item_embedding.weight
         flat = idx.reshape(-1)
+        ws, bs = self._mapping_params()
+        dims = [ws[0].shape[1]] + [w.shape[0] for w in ws]
+        if self.use_fused_mlp and ops.fused_mlp_supported(dims):
+            # one kernel forward, one backward: gather -> MLP in shared memory -> MSE vs gathered target -> scatter
+            return ops.fused_mlp_loss(0, 0, _lib.ACT_TANH, flat, None, None, (src, None, None, None, tgt), ws, bs)
         mapped = self._apply_mapping(ops.gather_rows(src, flat))
         return ops.mse_rows(mapped, tgt, flat)
 

@@ -510,3 +510,95 @@ def train_steps(user_tab, item_tab, user, item_a, item_b=None, label=None, *, lo
          _oob(dev), cur_stream())
     _maybe_check(dev)
     return out8, user_dst, item_dst
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# A4 / A14-A15 fused: gather -> small MLP -> loss head -> backward -> scatter in one kernel
+# ------------------------------------------------------------------------------------------------------------------
+import ctypes as _ct
+
+
+def fused_mlp_supported(dims) -> bool:
+    arr = (_ct.c_int * len(dims))(*[int(d) for d in dims])
+    return bool(_lib._lib.xdr_fused_mlp_supported(len(dims) - 1, _ct.cast(arr, _ct.c_void_p)))
+
+
+def _ptr_array(ts):
+    return (_ct.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])
+
+
+def _fused_mlp_call(in_mode, head, hidden_act, tabs, idx_u, idx_i, label, Ws, bs, backward, grad_loss, dsts, dWs, dbs,
+                    want_prob):
+    Au, Bu, Ai, Bi, T = tabs
+    dev = Au.device
+    dims = [Ws[0].shape[1]] + [w.shape[0] for w in Ws]
+    arr = (_ct.c_int * len(dims))(*dims)
+    B = idx_u.numel()
+    out8 = torch.empty(8, dtype=torch.float32, device=dev)
+    prob = torch.empty(B, dtype=torch.float32, device=dev) if want_prob else None
+    dAu, dBu, dAi, dBi, dT = dsts
+    call('xdr_fused_mlp_step', len(Ws), _ct.cast(arr, _ct.c_void_p), _ptr_array(Ws), _ptr_array(bs),
+         _ptr_array(dWs) if dWs else None, _ptr_array(dbs) if dbs else None, int(hidden_act), int(in_mode), int(head),
+         ptr(Au), ptr(Bu), ptr(Ai), ptr(Bi), ptr(T), Au.shape[0], Ai.shape[0] if Ai is not None else 0, Au.shape[1],
+         ptr(idx_u), ptr(idx_i), ptr(label), B, 1 if backward else 0, ptr(grad_loss), 1.0, ptr(dAu), ptr(dBu), ptr(dAi),
+         ptr(dBi), ptr(dT), ptr(prob), ptr(out8), ptr(_lib.workspace(dev)), _oob(dev), cur_stream())
+    _maybe_check(dev)
+    return out8, prob
+
+
+class FusedMlpLoss(torch.autograd.Function):
+    """One fused kernel for ``loss(MLP(gathered rows))`` and one for its whole backward (the forward is recomputed on
+    chip; rows come back from L2).  in_mode 0 / head 0: EMCDR.calculate_map_loss (emcdr.py:156-168); in_mode 1 / head 1:
+    one DTCDR NeuMF term (dtcdr.py:112-125, 186-187).  Tensor arguments: Au, Bu, Ai, Bi, T, then the layer weights, then
+    the layer biases (None where a layer has none)."""
+
+    @staticmethod
+    def forward(ctx, in_mode, head, hidden_act, idx_u, idx_i, label, n_layers, Au, Bu, Ai, Bi, T, *wb):
+        Ws, bs = list(wb[:n_layers]), list(wb[n_layers:])
+        for t in (Au, Bu, Ai, Bi, T) + tuple(Ws):
+            if t is not None:
+                _require_cuda_f32(t, 'fused_mlp operand')
+        idx_u = _ids(idx_u, 'idx_u').reshape(-1)
+        idx_i = _ids(idx_i, 'idx_i').reshape(-1) if idx_i is not None else None
+        out8, _ = _fused_mlp_call(in_mode, head, hidden_act, (Au, Bu, Ai, Bi, T), idx_u, idx_i, label, Ws, bs, False, None,
+                                  (None,) * 5, None, None, False)
+        ctx.cfg = (in_mode, head, hidden_act, n_layers)
+        ctx.save_for_backward(idx_u, idx_i, label, Au, Bu, Ai, Bi, T, *Ws, *bs)
+        return out8[0]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        in_mode, head, hidden_act, n_layers = ctx.cfg
+        sv = ctx.saved_tensors
+        idx_u, idx_i, label, Au, Bu, Ai, Bi, T = sv[:8]
+        Ws, bs = list(sv[8:8 + n_layers]), list(sv[8 + n_layers:])
+        g = grad_loss.reshape(-1)[:1].contiguous().float()
+        dsts, rets = [], []
+        for t in (Au, Bu, Ai, Bi, T):
+            if t is None:
+                dsts.append(None)
+                rets.append(None)
+            else:
+                d, r = _grad_dst(t)
+                dsts.append(d)
+                rets.append(r)
+        dWs = [torch.zeros_like(w) for w in Ws]
+        dbs = [None if b is None else torch.zeros_like(b) for b in bs]
+        _fused_mlp_call(in_mode, head, hidden_act, (Au, Bu, Ai, Bi, T), idx_u, idx_i, label, Ws, bs, True, g, dsts, dWs, dbs,
+                        False)
+        return (None,) * 7 + tuple(rets) + tuple(dWs) + tuple(dbs)
+
+
+def fused_mlp_loss(in_mode, head, hidden_act, idx_u, idx_i, label, tabs, Ws, bs):
+    Au, Bu, Ai, Bi, T = tabs
+    return FusedMlpLoss.apply(in_mode, head, hidden_act, idx_u, idx_i, label, len(Ws), Au, Bu, Ai, Bi, T, *Ws, *bs)
+
+
+def fused_mlp_prob(hidden_act, idx_u, idx_i, tabs, Ws, bs):
+    """Forward only, sigmoid output per row (DTCDR.predict)."""
+    with torch.no_grad():
+        idx_u, idx_i = _ids(idx_u, 'idx_u').reshape(-1), _ids(idx_i, 'idx_i').reshape(-1)
+        label = torch.zeros(idx_u.numel(), dtype=torch.float32, device=tabs[0].device)
+        _, prob = _fused_mlp_call(1, 1, hidden_act, tabs, idx_u, idx_i, label, list(Ws), list(bs), False, None, (None,) * 5,
+                                  None, None, True)
+        return prob

@@ -303,3 +303,31 @@ def test_gather_max2_concat_fwd_bwd():
     (out * G.to(dev())).sum().backward()
     for a, b in zip(c, r):
         torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------- fused MLP
+@pytest.mark.parametrize('batch', [1, 31, 32, 33, 1000, 8192])
+def test_fused_mlp_map_loss_matches_oracle(batch):
+    """EMCDR map step at sizes around the 32-row tile (incl. ragged tiles and a single row)."""
+    g = torch.Generator().manual_seed(111)
+    src, tgt = rand_table(3000, 64, 112, 0.3), rand_table(3000, 64, 113, 0.3)
+    ws = [torch.randn(128, 64, generator=g) * 0.2, torch.randn(64, 128, generator=g) * 0.2]
+    bs = [torch.randn(128, generator=g) * 0.1, torch.randn(64, generator=g) * 0.1]
+    idx = rand_ids(batch, 3000, 114, 1.3)
+    leaves = [t.clone().requires_grad_(True) for t in [src, tgt] + ws + bs]
+    ref = O.emcdr_map_loss(leaves[0], leaves[1], idx.view(-1, 1), leaves[2:4], leaves[4:6])
+    ref.backward()
+    c = [t.to(dev()).requires_grad_(True) for t in [src, tgt] + ws + bs]
+    assert ops().fused_mlp_supported([64, 128, 64])
+    loss = ops().fused_mlp_loss(0, 0, lib().ACT_TANH, idx.to(dev()), None, None, (c[0], None, None, None, c[1]), c[2:4], c[4:6])
+    torch.testing.assert_close(loss.cpu(), ref.detach(), rtol=LOSS_RTOL, atol=0)
+    (loss * 1.3).backward()
+    for got, want, nm in zip(c, leaves, ('src', 'tgt', 'W1', 'W2', 'b1', 'b2')):
+        atol = max(1e-7, 1e-4 * want.grad.abs().max().item())
+        torch.testing.assert_close(got.grad.cpu(), want.grad * 1.3, rtol=2e-4, atol=atol, msg=lambda s: f'{nm}: {s}')
+
+
+def test_fused_mlp_unsupported_stacks_fall_back():
+    assert not ops().fused_mlp_supported([512, 64, 1])       # wider than 256
+    assert not ops().fused_mlp_supported([256, 256, 256])     # more than 32 weight elements per thread
+    assert ops().fused_mlp_supported([128, 32, 16, 1])

@@ -58,11 +58,12 @@ def test_emcdr_rec_phases(lfm, phase):
     torch.testing.assert_close(m.predict(batch).cpu(), g.t('predict'), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize('fused', [True, False])
 @pytest.mark.parametrize('case,mf', [('non_linear', 'non_linear'), ('linear', 'linear'), ('items', 'non_linear')])
-def test_emcdr_map_phase_and_predict(case, mf):
+def test_emcdr_map_phase_and_predict(case, mf, fused):
     from recbole_cdr_b200.model.cross_domain_recommender.emcdr import EMCDR
     g = Golden(f'emcdr_map_{case}')
-    m = build(EMCDR, g, dict(EMCDR_CFG, latent_factor_model='BPR', mapping_function=mf))
+    m = build(EMCDR, g, dict(EMCDR_CFG, latent_factor_model='BPR', mapping_function=mf, xdr_fused_mlp=fused))
     assert m.mode == ('overlap_items' if case == 'items' else 'overlap_users')
     m.set_phase('OVERLAP')
     batch = cuda_batch(g)
@@ -104,11 +105,13 @@ def test_conet(tag):
     torch.testing.assert_close(pred.cpu(), g.t('predict'), rtol=1e-4, atol=1e-6)
 
 
-def test_dtcdr():
+@pytest.mark.parametrize('fused', [True, False])
+def test_dtcdr(fused):
     from recbole_cdr_b200.model.cross_domain_recommender.dtcdr import DTCDR
     g = Golden('dtcdr_neumf')
     m = build(DTCDR, g, dict(embedding_size=64, mlp_hidden_size=[32, 16], dropout_prob=0.0, base_model='NeuMF',
-                             alpha=g.meta('alpha')))
+                             alpha=g.meta('alpha'), xdr_fused_mlp=fused))
+    assert m._fused_ok() == fused
     batch = cuda_batch(g)
     check_loss_and_grads(m, g, batch, grad_rtol=2e-4, grad_atol=2e-6)
     torch.testing.assert_close(m.predict(batch).cpu(), g.t('predict'), rtol=1e-4, atol=1e-6)

@@ -12,12 +12,16 @@
 // HBM traffic is then just ids + gathered rows + scattered rows:
 //   map step   8 + 2*256 + 2*256 = 1032 B/row (dim 64)      DTCDR   16 + 4 + 4*256 + 4*256 = 2068 B/row
 // fp32 FMA on CUDA cores: 98 kFLOP (map) / 28 kFLOP (DTCDR) per row is far below the FMA roofline at these byte rates.
+// STATUS (round 1, profiles/r1_rows.md): parity-green but NOT yet faster than the graph-replayed composed path (map
+// step 398 vs 98 us, DTCDR BOTH step 312 vs 227 us): one 256-thread CTA per SM running scalar shared-memory-fed FMA
+// chains (2 LDS per FMA) is latency-bound on its own inner loops.  It needs 4x4 register tiles and 512+ threads; until
+// then the models use it only on request (config key `xdr_fused_mlp: True`).
 #include "xdr_common.cuh"
 
 namespace xdr {
 
 constexpr int kMlpThreads = 256;
-constexpr int kTileRows = 32;
+constexpr int kMaxTileRows = 32;  // batch rows per tile: 32, or 16 / 8 when the weights leave less shared memory
 constexpr int kMaxLayers = 3;
 
 struct MlpArgs {
@@ -39,6 +43,7 @@ struct MlpArgs {
   const int64_t* idx_i;
   const float* label;
   int64_t batch;
+  int tile_rows;          // rows per tile (<= kMaxTileRows)
   int backward;           // 0: forward only (loss [+ prob]); 1: forward + backward + scatter
   const float* grad_loss; // device scalar (NULL => 1)
   float scale;
@@ -49,7 +54,8 @@ struct MlpArgs {
 };
 
 template <int CAP>
-__device__ __forceinline__ void mlp_accum_dw(float (&acc)[CAP], const float* dz, const float* x, int din, int dout, int tid) {
+__device__ __forceinline__ void mlp_accum_dw(float (&acc)[CAP], const float* dz, const float* x, int din, int dout, int tid,
+                                             int kTileRows) {
 #pragma unroll
   for (int i = 0; i < CAP; ++i) {
     const int e = tid + i * kMlpThreads;
@@ -80,6 +86,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Wo
   __shared__ float red_smem[8];
   const int tid = threadIdx.x;
   const int nl = a.n_layers;
+  const int kTileRows = a.tile_rows;
   // ---- carve shared memory: per layer W [dout][din], Wt [din][dout], bias; per tile activations act[l] and grads g[l]
   float* Wm[kMaxLayers];
   float* Wt[kMaxLayers];
@@ -237,9 +244,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Wo
       const float* dz = grd[l + 1];
       const float* x = act[l];
       // weight gradient: thread owns elements e = tid + 256*i of W[l]  (n = e / din, k = e % din)
-      if (l == 0) mlp_accum_dw(accW0, dz, x, din, dout, tid);
-      else if (l == 1) mlp_accum_dw(accW1, dz, x, din, dout, tid);
-      else mlp_accum_dw(accW2, dz, x, din, dout, tid);
+      if (l == 0) mlp_accum_dw(accW0, dz, x, din, dout, tid, kTileRows);
+      else if (l == 1) mlp_accum_dw(accW1, dz, x, din, dout, tid, kTileRows);
+      else mlp_accum_dw(accW2, dz, x, din, dout, tid, kTileRows);
       if (tid < dout) {
         float s = accB[l];
         for (int r = 0; r < kTileRows; ++r) s += dz[r * dout + tid];
@@ -314,6 +321,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Wo
 }
 
 static size_t mlp_smem_bytes(const MlpArgs& a) {
+  const int kTileRows = a.tile_rows;
   size_t f = 0;
   for (int l = 0; l < a.n_layers; ++l) f += 2 * (size_t)((a.dims[l] * a.dims[l + 1] + 3) & ~3) + ((a.dims[l + 1] + 3) & ~3);
   for (int l = 0; l <= a.n_layers; ++l) f += 2 * (size_t)((kTileRows * a.dims[l] + 3) & ~3);
@@ -321,8 +329,18 @@ static size_t mlp_smem_bytes(const MlpArgs& a) {
   return f * sizeof(float);
 }
 
+// largest tile (32, 16, 8 rows) whose activations fit next to the weights in 200 KB of shared memory
+static bool pick_tile_rows(MlpArgs* a) {
+  for (int tr = kMaxTileRows; tr >= 8; tr >>= 1) {
+    a->tile_rows = tr;
+    if (mlp_smem_bytes(*a) <= 200 * 1024) return true;
+  }
+  return false;
+}
+
 template <int E0, int E1, int E2>
 static int launch_mlp(const MlpArgs& a, void* ws, cudaStream_t s) {
+  const int kTileRows = a.tile_rows;
   const size_t smem = mlp_smem_bytes(a);
   auto kern = fused_mlp_kernel<E0, E1, E2>;
   XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -353,7 +371,7 @@ int xdr_fused_mlp_supported(int n_layers, const int* dims_host) {
     const int per_thread = (dims_host[l] * dims_host[l + 1] + kMlpThreads - 1) / kMlpThreads;
     if (per_thread > 32) return 0;
   }
-  return mlp_smem_bytes(a) <= 200 * 1024 ? 1 : 0;
+  return pick_tile_rows(&a) ? 1 : 0;
 }
 
 int xdr_fused_mlp_step(int n_layers, const int* dims_host, const float* const* W_host, const float* const* b_host,
@@ -388,6 +406,7 @@ int xdr_fused_mlp_step(int n_layers, const int* dims_host, const float* const* W
   a.hidden_act = hidden_act; a.last_act = XDR_ACT_NONE; a.in_mode = in_mode; a.head = head;
   a.Au = Au; a.Bu = Bu; a.Ai = Ai; a.Bi = Bi; a.T = T; a.n_u = n_u; a.n_i = n_i; a.dim = dim;
   a.idx_u = idx_u; a.idx_i = idx_i; a.label = label; a.batch = batch; a.backward = backward; a.grad_loss = grad_loss;
+  pick_tile_rows(&a);
   a.scale = scale; a.dAu = dAu; a.dBu = dBu; a.dAi = dAi; a.dBi = dBi; a.dT = dT; a.prob = prob; a.out8 = out8; a.oob = oob;
   int e[3] = {0, 0, 0};
   for (int l = 0; l < n_layers; ++l) e[l] = (a.dims[l] * a.dims[l + 1] + kMlpThreads - 1) / kMlpThreads;

@@ -46,7 +46,7 @@ class DTCDR(CrossDomainRecommender):
         self.target_predict_layer = nn.Linear(self.mlp_hidden_size[-1], 1)
 
         self.apply(xavier_normal_initialization)
-        self.use_fused_mlp = config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else True
+        self.use_fused_mlp = config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else False
 
     def _tower(self, domain):
         mlp = self.source_mlp_layers if domain == 'source' else self.target_mlp_layers

@@ -42,7 +42,7 @@ class EMCDR(CrossDomainRecommender):
         else:
             self.input_type = InputType.PAIRWISE
         self.bpr_gamma = 1e-10  # recbole BPRLoss default
-        self.use_fused_mlp = config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else True
+        self.use_fused_mlp = config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else False
         self.source_latent_dim = config['source_embedding_size']
         self.target_latent_dim = config['target_embedding_size']
         self.reg_weight = config['reg_weight']

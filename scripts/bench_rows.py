@@ -89,7 +89,7 @@ ov = torch.randint(0, ds.num_overlap_user, (8192, 1), device=dev, generator=g)
 def map_step():
     loss = m.calculate_loss(Interaction({'overlap': ov}))
     loss.backward()
-report('A4 EMCDR map step fwd+bwd (autograd ops, eager launches), b = 8192', timeit(map_step), bytes_=8192 * 1032, flops=8192 * 98304, units=8192, unit_name='inter')
+report('A4 EMCDR map step fwd+bwd (fused MLP kernels, eager launches), b = 8192', timeit(map_step), bytes_=8192 * 1032, flops=8192 * 98304, units=8192, unit_name='inter')
 from recbole_cdr_b200.trainer import GraphedTrainStep
 gs = GraphedTrainStep(m, Interaction({'overlap': ov}))
 report('A4 EMCDR map step fwd+bwd, CUDA-graph replay, b = 8192', timeit(lambda: gs(Interaction({'overlap': ov})), inner=10), bytes_=8192 * 1032, flops=8192 * 98304, units=8192, unit_name='inter')
@@ -108,7 +108,7 @@ def both_batch(dsx, Bx, seed):
 ib = both_batch(dsb, 8192, 5)
 def dt_step():
     m.calculate_loss(ib).backward()
-report('A14-15 DTCDR NeuMF BOTH step fwd+bwd (eager launches), 2 x B=8192', timeit(dt_step), bytes_=2 * 8192 * 2068, flops=2 * 8192 * 27700, units=2 * 8192, unit_name='inter')
+report('A14-15 DTCDR NeuMF BOTH step fwd+bwd (fused MLP kernels, eager launches), 2 x B=8192', timeit(dt_step), bytes_=2 * 8192 * 2068, flops=2 * 8192 * 27700, units=2 * 8192, unit_name='inter')
 gs = GraphedTrainStep(m, ib)
 report('A14-15 DTCDR NeuMF BOTH step fwd+bwd, CUDA-graph replay', timeit(lambda: gs(ib), inner=10), bytes_=2 * 8192 * 2068, flops=2 * 8192 * 27700, units=2 * 8192, unit_name='inter')
 del m, gs

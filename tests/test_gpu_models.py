@@ -111,7 +111,7 @@ def test_dtcdr(fused):
     g = Golden('dtcdr_neumf')
     m = build(DTCDR, g, dict(embedding_size=64, mlp_hidden_size=[32, 16], dropout_prob=0.0, base_model='NeuMF',
                              alpha=g.meta('alpha'), xdr_fused_mlp=fused))
-    assert m._fused_ok() == fused
+    assert m._fused_ok() == fused and m.use_fused_mlp == fused
     batch = cuda_batch(g)
     check_loss_and_grads(m, g, batch, grad_rtol=2e-4, grad_atol=2e-6)
     torch.testing.assert_close(m.predict(batch).cpu(), g.t('predict'), rtol=1e-4, atol=1e-6)

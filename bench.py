@@ -35,6 +35,9 @@ for p in (ROOT, os.path.join(ROOT, 'recbole-cdr_b200')):
 import torch  # noqa: E402
 
 BYTES_PER_INTERACTION_BPR_D64 = 3 * 8 + 3 * 4 * 64 + 3 * 4 * 64  # ids + gathered rows + scattered rows = 1560
+# dram__bytes_read.sum + dram__bytes_write.sum of train_steps_staged_kernel<8,2,true> from the `ncu --set full` capture
+# committed as profiles/r1_train_steps_staged_ncu.md (968.0 MB over a 60-step launch): 16.13 MB per 8192-interaction step
+NCU_DRAM_BYTES_PER_STEP_B8192 = 968.0e6 / 60
 
 
 def parse_args():
@@ -384,8 +387,10 @@ def run_xdr(args):
             'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, ds),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src,
-                         'kernel': ('train_steps_kernel<2,true>: one persistent launch over all K timed steps'
+                         'traffic': (NCU_DRAM_BYTES_PER_STEP_B8192 * K if (use_persistent and B == 8192 and world == 1) else None),
+                         'traffic_note': 'bytes per launch = ncu dram read+write per step (profiles/r1_train_steps_staged_ncu.md) x K',
+                         'peak_source': peak_src,
+                         'kernel': ('train_steps_staged_kernel<8,2,true>: one persistent launch over all K timed steps'
                                     if use_persistent else 'score_fwd_kernel<2,true> + score_bwd_kernel<2,true> per step'),
                          'units_per_launch': B * K if use_persistent else B,
                          'bytes_per_interaction': BYTES_PER_INTERACTION_BPR_D64},

@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-compare', action='store_true', help='skip the per-step-kernel comparison runs')
     ap.add_argument('--mode', default='persistent', choices=['persistent', 'per_step'])
+    ap.add_argument('--shard-chunk', type=int, default=50, help='N>1: steps per persistent launch / peer-gather chunk')
+    ap.add_argument('--no-stage-remote', action='store_true', help='N>1: gather item rows inside the persistent kernel')
     ap.add_argument('--chunk', type=int, default=50, help='steps per launch on the end-to-end (host-fed) path')
     return ap.parse_args()
 
@@ -222,6 +224,8 @@ def run_xdr(args):
             return shard.RowShardedTable(n, D, rank, world, dev, loc).connect()
         s_ut, s_it = mk(ds.num_total_user, True), mk(ds.num_total_item, True)
         s_gu, s_gi = mk(ds.num_total_user, False), mk(ds.num_total_item, False)
+        sh_runner = shard.ShardedStepRunner(s_ut, s_it, s_gu, s_gi, reg_weight=0.01, chunk=args.shard_chunk,
+                                            stage_remote=not args.no_stage_remote)
         dist.barrier()
 
     # K + W distinct seeded batches (seed = 1 + step, offset per rank), resident in HBM and mirrored in pinned host memory
@@ -252,8 +256,7 @@ def run_xdr(args):
     def persistent(lo, hi):
         """steps [lo, hi) as ONE persistent launch (xdr_train_steps): fwd + bwd + scatter-add per batch"""
         if sharded:
-            shard.train_steps_sharded(s_ut, s_it, s_gu, s_gi, ids[lo:hi, 0], ids[lo:hi, 1], ids[lo:hi, 2],
-                                      reg_weight=0.01, out8=out8[lo:hi])
+            sh_runner.run(ids[lo:hi], out8=out8[lo:hi])
         else:
             ops.train_steps(ut.data, it.data, ids[lo:hi, 0], ids[lo:hi, 1], ids[lo:hi, 2], reg_weight=0.01, user_dst=gu,
                             item_dst=gi, out8=out8[lo:hi])
@@ -267,6 +270,8 @@ def run_xdr(args):
     # ---- device-resident throughput -----------------------------------------------------------------------------
     if use_persistent:
         persistent(0, W)
+        if sharded:
+            sh_runner.launches = 0
     else:
         for s in range(W):
             step(s)
@@ -278,7 +283,7 @@ def run_xdr(args):
     e0.record()
     if use_persistent:
         persistent(W, W + K)
-        launches = 1
+        launches = 1 if not sharded else sh_runner.launches
     else:
         for s in range(W, W + K):
             step(s)
@@ -348,7 +353,7 @@ def run_xdr(args):
         n_chunks = K // chunk
         if sharded:
             def launch(idb, _label, o8):
-                shard.train_steps_sharded(s_ut, s_it, s_gu, s_gi, idb[:, 0], idb[:, 1], idb[:, 2], reg_weight=0.01, out8=o8)
+                sh_runner.run(idb, out8=o8)
             runner = FusedStepRunner({'pairwise': True}, launch=launch, device=dev)
         else:
             runner = FusedStepRunner(model.fused_step_spec(), lr=None, grad_tables=(gu, gi))

@@ -262,7 +262,15 @@ XDR_API int xdr_train_steps_sharded(const float* const* user_shards, const float
                                     const int64_t* item_b, const float* label, int64_t step_stride, int64_t batch,
                                     int n_steps, int pairwise, int loss_kind, float gamma, float reg_weight,
                                     const float* grad_loss, float scale, float* out8, void* steps_ws,
-                                    size_t steps_ws_bytes, int32_t* oob, xdr_stream_t stream);
+                                    size_t steps_ws_bytes, const float* staged_item_a, const float* staged_item_b,
+                                    int32_t* oob, xdr_stream_t stream);
+/* Peer gather: out[k,:] = shard[idx[k] mod G][idx[k] div G, :].  Run one chunk ahead of xdr_train_steps_sharded on a
+ * second stream, it pulls the chunk's item rows over NVLink into dense local blocks [n_steps][batch][dim] that the
+ * persistent kernel then reads sequentially (staged_item_a / staged_item_b; NULL = gather straight from the shards):
+ * thousands of row requests in flight hide the NVLink latency that the persistent kernel's registers cannot.          */
+XDR_API int xdr_gather_rows_sharded(const float* const* shards, int n_shards, int64_t n_rows, int dim, const int64_t* idx,
+                                    int64_t n_idx, int64_t idx_batch, int64_t idx_step_stride, float* out, int64_t out_ld,
+                                    int32_t* oob, xdr_stream_t stream);
 /* CUDA-IPC plumbing.  export: 64-byte handle of the allocation containing dev_ptr + byte offset of dev_ptr inside it
  * (host outputs).  open: map a peer's allocation, returns its base (add the exported offset).  close: unmap.            */
 XDR_API int xdr_ipc_export(const void* dev_ptr, unsigned char* handle64_host, int64_t* offset_host);

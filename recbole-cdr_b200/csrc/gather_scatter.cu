@@ -39,6 +39,42 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const float* __re
   }
 }
 
+// out[k,:] = shard[idx[k] mod G][idx[k] div G, :]: the peer-gather that pulls a chunk's rows over NVLink one chunk ahead
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) gather_rows_sharded_kernel(Shards tab, int log2g, int64_t n_rows, int nv,
+                                                                       const int64_t* __restrict__ idx, int64_t n_idx,
+                                                                       int64_t idx_batch, int64_t idx_step_stride,
+                                                                       float* __restrict__ out, int64_t out_ld, int32_t* oob) {
+  // id k lives at idx[(k / idx_batch) * idx_step_stride + k % idx_batch]: the [K, rows, B] id block of the trainer
+  auto id_at = [&](int64_t k) { return idx[(k / idx_batch) * idx_step_stride + (k % idx_batch)]; };
+  const int sub = threadIdx.x & (kLanesPerRow - 1);
+  const int64_t group = ((int64_t)blockIdx.x * kThreads + threadIdx.x) / kLanesPerRow;
+  const int64_t n_groups = (int64_t)gridDim.x * kThreads / kLanesPerRow;
+  // two rows per group iteration: 2*VEC independent 16-byte requests in flight per lane (NVLink latency is long)
+  for (int64_t k = group; k < n_idx; k += 2 * n_groups) {
+    const int64_t k2 = k + n_groups;
+    const int64_t r0 = id_at(k), r1 = k2 < n_idx ? id_at(k2) : -1;
+    const bool ok0 = (uint64_t)r0 < (uint64_t)n_rows, ok1 = (uint64_t)r1 < (uint64_t)n_rows;
+    if (oob && sub == 0 && (!ok0 || (k2 < n_idx && !ok1))) *oob = 1;
+    const float* s0 = shard_row(tab, log2g, ok0 ? r0 : 0, (int64_t)nv * 4);
+    const float* s1 = shard_row(tab, log2g, ok1 ? r1 : 0, (int64_t)nv * 4);
+    float4 v0[VEC], v1[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c = sub + j * kLanesPerRow;
+      v0[j] = (ok0 && c < nv) ? ldg_row4(s0, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v1[j] = (ok1 && c < nv) ? ldg_row4(s1, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c = sub + j * kLanesPerRow;
+      if (c >= nv) continue;
+      st4(out + k * out_ld, c, v0[j]);
+      if (k2 < n_idx) st4(out + k2 * out_ld, c, v1[j]);
+    }
+  }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(kThreads) scatter_add_rows_kernel(float* __restrict__ dst, int64_t n_rows, int nv,
                                                                     const int64_t* __restrict__ idx, int64_t n_idx,
@@ -172,6 +208,37 @@ int xdr_gather_rows(const float* table, int64_t n_rows, int dim, const int64_t* 
   cudaStream_t s = (cudaStream_t)stream;
   XDR_DISPATCH_VEC(nv, (gather_rows_kernel<VEC><<<grid_for_rows(n_idx), kThreads, 0, s>>>(table, n_rows, nv, idx, n_idx,
                                                                                           out, out_ld, oob)));
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+int xdr_gather_rows_sharded(const float* const* shards, int n_shards, int64_t n_rows, int dim, const int64_t* idx,
+                            int64_t n_idx, int64_t idx_batch, int64_t idx_step_stride, float* out, int64_t out_ld,
+                            int32_t* oob, xdr_stream_t stream) {
+  if (idx_batch <= 0) { idx_batch = n_idx > 0 ? n_idx : 1; idx_step_stride = idx_batch; }
+  XDR_REQUIRE(dim_ok(dim), "xdr_gather_rows_sharded: dim=%d must be a multiple of 4 in (0, 256]", dim);
+  XDR_REQUIRE(n_shards >= 1 && n_shards <= kMaxShards && (n_shards & (n_shards - 1)) == 0,
+              "xdr_gather_rows_sharded: n_shards=%d must be a power of two <= %d", n_shards, kMaxShards);
+  XDR_REQUIRE(n_idx >= 0 && n_rows >= 0, "xdr_gather_rows_sharded: negative size");
+  if (n_idx == 0) return XDR_OK;
+  XDR_REQUIRE(shards && idx && out, "xdr_gather_rows_sharded: null pointer");
+  XDR_REQUIRE(out_ld >= dim && out_ld % 4 == 0 && aligned16(out), "xdr_gather_rows_sharded: bad output layout");
+  Shards t{};
+  int log2g = 0;
+  while ((1 << log2g) < n_shards) ++log2g;
+  for (int g = 0; g < n_shards; ++g) {
+    XDR_REQUIRE(shards[g] && aligned16(shards[g]), "xdr_gather_rows_sharded: null or unaligned shard %d", g);
+    t.p[g] = const_cast<float*>(shards[g]);
+  }
+  const int nv = dim / 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  // NVLink latency is ~10x local: run many CTAs per SM (grid-stride) so that thousands of row requests are in flight
+  int64_t blocks = (n_idx + 2 * (kThreads / kLanesPerRow) - 1) / (2 * (kThreads / kLanesPerRow));
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  XDR_DISPATCH_VEC(nv, (gather_rows_sharded_kernel<VEC><<<(int)blocks, kThreads, 0, s>>>(t, log2g, n_rows, nv, idx, n_idx, idx_batch,
+                                                                                         idx_step_stride, out, out_ld, oob)));
   XDR_LAUNCH_OK();
   return XDR_OK;
 }

@@ -46,30 +46,22 @@ constexpr int kWorkerWarps = 20;   // register kernel: workers
 #ifndef XDR_SCATTER_WARPS
 #define XDR_SCATTER_WARPS 4
 #endif
-constexpr int kLoaderWarps = XDR_LOADER_WARPS;    // staged kernel: loaders ...
-constexpr int kScatterWarps = XDR_SCATTER_WARPS;  // ... and scatterers
+constexpr int kLoaderWarpsFull = XDR_LOADER_WARPS;  // staged kernel: loaders when the CTA owns the whole SM ...
+constexpr int kLoaderWarpsLite = 10;                // ... and when item rows are pre-staged by the peer-gather kernel, whose
+                                                    // CTAs must fit next to this one (register file: 576 x 80 + 256 x 40)
+constexpr int kScatterWarps = XDR_SCATTER_WARPS;    // scatterers
 constexpr int kRegThreads = (kServiceWarps + kWorkerWarps) * 32;
-constexpr int kStagedThreads = (kServiceWarps + kLoaderWarps + kScatterWarps) * 32;
+__host__ __device__ constexpr int staged_threads(int loaders) { return (kServiceWarps + loaders + kScatterWarps) * 32; }
 constexpr int kMaxCtaPerLane = 5;  // gatherer lanes poll <= 5 CTAs each: grid <= 160
 constexpr int kMaxStages = 4;      // staged kernel: stage ring depth (3 or 4)
 constexpr int kRing = 8;            // id-tile / partial / norm ring depth (steps)
-
-constexpr int kMaxShards = 8;
-
-// A table row-sharded over 2^log2g GPUs: global row r lives on shard (r mod G) at local row (r div G).  Block-cyclic so
-// that the three id ranges of the joint layout (overlapped / target-only / source-only) and Zipf-hot low ids spread
-// evenly.  Shard pointers are local or peer-mapped (CUDA IPC over NVLink) device pointers; G = 1 is the plain table.
-struct Shards {
-  float* p[kMaxShards];
-};
-__device__ __forceinline__ float* shard_row(const Shards& t, int log2g, int64_t row, int64_t row_f) {
-  return t.p[row & ((1 << log2g) - 1)] + (row >> log2g) * row_f;
-}
 
 struct StepsArgs {
   Shards user_tab, item_tab;  // gather sources
   Shards user_dst, item_dst;  // scatter-add destinations
   int log2g;
+  const float* stage_a;       // optional dense pre-gathered first-item rows  [n_steps][batch][dim] (row = position in batch)
+  const float* stage_b;       // optional dense pre-gathered second-item rows (pairwise)
   int64_t n_users, n_items;   // GLOBAL row counts
   int nv;                 // float4 per row
   const int64_t* user;    // [n_steps] arrays of `batch` ids, consecutive steps `step_stride` elements apart
@@ -364,6 +356,13 @@ __device__ __forceinline__ void task_issue(TaskRegs<VEC, PAIRWISE>& r, int lt, c
   const float* pu = shard_row(a.user_tab, a.log2g, oku ? iu : 0, row_f);
   const float* pa = shard_row(a.item_tab, a.log2g, oka ? ia : 0, row_f);
   const float* pb = shard_row(a.item_tab, a.log2g, okb ? ib : 0, row_f);
+  if (a.stage_a != nullptr) {
+    // item rows were pulled over NVLink into a dense local block by the peer-gather kernel one chunk ahead: sequential,
+    // local reads here; the ids are still needed for the scatter side
+    const int64_t pos = ((int64_t)r.s * a.batch + (int64_t)blockIdx.x * a.slice + jj) * row_f;
+    pa = a.stage_a + pos;
+    if (PAIRWISE) pb = a.stage_b + pos;
+  }
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
@@ -465,8 +464,10 @@ __device__ __forceinline__ void init_bars(const Bars& B, int tasks, int ifree_co
 // =====================================================================================================================
 // STAGED kernel: loaders (gather -> score -> stash) and scatterers (norms -> gradients -> RED) are different warps
 // =====================================================================================================================
-template <int LPR, int VEC, bool PAIRWISE>
-__global__ void __launch_bounds__(kStagedThreads, 1) train_steps_staged_kernel(StepsArgs a, int n_stages) {
+template <int LPR, int VEC, bool PAIRWISE, int kLoaderWarps>
+// launch bound 768 (> the threads actually launched) caps ptxas at 80 registers/thread, so that in the lite configuration
+// (576 threads) a 256-thread peer-gather CTA still fits in the SM's register file next to this CTA
+__global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a, int n_stages) {
   constexpr int IPW = 32 / LPR;
   constexpr int R = PAIRWISE ? 3 : 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -734,10 +735,14 @@ static bool plan_steps(int64_t batch, int nv, bool pairwise, StepsPlan* plan) {
 
 template <int LPR, int VEC, bool PW>
 static int launch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_t s) {
-  if (plan.stages > 0) {
-    auto kern = train_steps_staged_kernel<LPR, VEC, PW>;
+  if (plan.stages > 0 && a.stage_a != nullptr) {
+    auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsLite>;
     XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    kern<<<plan.grid, kStagedThreads, plan.smem, s>>>(a, plan.stages);
+    kern<<<plan.grid, staged_threads(kLoaderWarpsLite), plan.smem, s>>>(a, plan.stages);
+  } else if (plan.stages > 0) {
+    auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull>;
+    XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    kern<<<plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s>>>(a, plan.stages);
   } else {
     auto kern = train_steps_regs_kernel<LPR, VEC, PW>;
     XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
@@ -780,7 +785,7 @@ static int train_steps_core(const Shards& user_tab, const Shards& item_tab, cons
                             const int64_t* item_a, const int64_t* item_b, const float* label, int64_t step_stride,
                             int64_t batch, int n_steps, int pairwise, int loss_kind, float gamma, float reg_weight,
                             const float* grad_loss, float scale, float* out8, void* steps_ws, size_t steps_ws_bytes,
-                            int32_t* oob, xdr_stream_t stream) {
+                            const float* stage_a, const float* stage_b, int32_t* oob, xdr_stream_t stream) {
   const char* fn = "xdr_train_steps";
   XDR_REQUIRE(dim_ok(dim), "%s: dim=%d must be a multiple of 4 in (0, 256]", fn, dim);
   XDR_REQUIRE(batch > 0 && n_steps >= 0, "%s: batch=%lld n_steps=%d", fn, (long long)batch, n_steps);
@@ -817,6 +822,9 @@ static int train_steps_core(const Shards& user_tab, const Shards& item_tab, cons
   }
   StepsArgs a{};
   a.user_tab = user_tab; a.item_tab = item_tab; a.user_dst = user_dst; a.item_dst = item_dst; a.log2g = log2g;
+  XDR_REQUIRE(stage_a == nullptr || (aligned16(stage_a) && (!pairwise || (stage_b && aligned16(stage_b)))),
+              "%s: staged item rows must be 16-byte aligned (and both given for pairwise)", fn);
+  a.stage_a = stage_a; a.stage_b = stage_b;
   a.n_users = n_users; a.n_items = n_items; a.nv = dim / 4;
   a.user = user; a.item_a = item_a; a.item_b = item_b; a.label = label; a.step_stride = step_stride; a.batch = batch;
   a.n_steps = n_steps; a.loss_kind = loss_kind; a.gamma = gamma; a.reg_weight = reg_weight; a.out8 = out8;
@@ -844,7 +852,7 @@ int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_user
   di.p[0] = item_dst;
   return train_steps_core(ut, it, du, di, 0, n_users, n_items, dim, user, item_a, item_b, label, step_stride, batch,
                           n_steps, pairwise, loss_kind, gamma, reg_weight, grad_loss, scale, out8, steps_ws,
-                          steps_ws_bytes, oob, stream);
+                          steps_ws_bytes, nullptr, nullptr, oob, stream);
 }
 
 int xdr_train_steps_sharded(const float* const* user_shards, const float* const* item_shards, float* const* user_dst_shards,
@@ -852,7 +860,8 @@ int xdr_train_steps_sharded(const float* const* user_shards, const float* const*
                             const int64_t* user, const int64_t* item_a, const int64_t* item_b, const float* label,
                             int64_t step_stride, int64_t batch, int n_steps, int pairwise, int loss_kind, float gamma,
                             float reg_weight, const float* grad_loss, float scale, float* out8, void* steps_ws,
-                            size_t steps_ws_bytes, int32_t* oob, xdr_stream_t stream) {
+                            size_t steps_ws_bytes, const float* staged_item_a, const float* staged_item_b, int32_t* oob,
+                            xdr_stream_t stream) {
   XDR_REQUIRE(n_shards >= 1 && n_shards <= kMaxShards && (n_shards & (n_shards - 1)) == 0,
               "xdr_train_steps_sharded: n_shards=%d must be a power of two <= %d", n_shards, kMaxShards);
   XDR_REQUIRE(user_shards && item_shards && user_dst_shards && item_dst_shards, "xdr_train_steps_sharded: null pointer");
@@ -867,7 +876,7 @@ int xdr_train_steps_sharded(const float* const* user_shards, const float* const*
   }
   return train_steps_core(ut, it, du, di, log2g, n_users, n_items, dim, user, item_a, item_b, label, step_stride, batch,
                           n_steps, pairwise, loss_kind, gamma, reg_weight, grad_loss, scale, out8, steps_ws,
-                          steps_ws_bytes, oob, stream);
+                          steps_ws_bytes, staged_item_a, staged_item_b, oob, stream);
 }
 
 // ---- peer-memory plumbing for row-sharded tables (CUDA IPC; one process per GPU) --------------------------------------

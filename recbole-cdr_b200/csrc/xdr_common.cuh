@@ -61,6 +61,19 @@ struct Workspace {
 // ---------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
+constexpr int kMaxShards = 8;
+
+// A table row-sharded over 2^log2g GPUs: global row r lives on shard (r mod G) at local row (r div G).  Block-cyclic so
+// that the three id ranges of the joint layout (overlapped / target-only / source-only) and Zipf-hot low ids spread
+// evenly.  Shard pointers are local or peer-mapped (CUDA IPC over NVLink) device pointers; G = 1 is the plain table.
+struct Shards {
+  float* p[kMaxShards];
+};
+__device__ __forceinline__ float* shard_row(const Shards& t, int log2g, int64_t row, int64_t row_f) {
+  return t.p[row & ((1 << log2g) - 1)] + (row >> log2g) * row_f;
+}
+
+
 // Row geometry: a row of `dim` floats is nv = dim/4 float4s.  An interaction (or row) is owned by a group of
 // 8 consecutive lanes; lane `sub` of the group owns float4 columns sub, sub+8, ... (VEC of them).  One 8-lane
 // slice of a row is one full 128-byte line, so every LDG.128 / RED.128 of a group is a single-line request.

@@ -44,7 +44,8 @@ PROTOTYPES = {
     'xdr_train_steps': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int,
                                 c_f32, c_f32, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_vp]),
     'xdr_train_steps_sharded': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64,
-                                        c_i64, c_int, c_int, c_int, c_f32, c_f32, c_vp, c_f32, c_vp, c_vp, c_sz, c_vp, c_vp]),
+                                        c_i64, c_int, c_int, c_int, c_f32, c_f32, c_vp, c_f32, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp]),
+    'xdr_gather_rows_sharded': (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
     'xdr_ipc_export': (c_int, [c_vp, c_vp, ctypes.POINTER(c_i64)]),
     'xdr_ipc_open': (c_int, [c_vp, ctypes.POINTER(c_vp)]),
     'xdr_ipc_close': (c_int, [c_vp]),

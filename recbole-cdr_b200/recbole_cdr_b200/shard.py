@@ -109,13 +109,16 @@ class RowShardedTable:
     def pointer_array(self):
         if self._ptrs is None:
             raise RuntimeError('RowShardedTable.connect() has not been called')
-        return (ctypes.c_void_p * self.world)(*self._ptrs)
+        if getattr(self, '_ptr_array', None) is None:
+            self._ptr_array = (ctypes.c_void_p * self.world)(*self._ptrs)   # built once: the launches are host-bound
+        return self._ptr_array
 
     def close(self):
         for base in self._opened:
             call('xdr_ipc_close', base)
         self._opened = []
         self._ptrs = None
+        self._ptr_array = None
 
 
 _steps_ws = {}
@@ -123,9 +126,11 @@ _steps_ws = {}
 
 def train_steps_sharded(user_tab: RowShardedTable, item_tab: RowShardedTable, user_dst: RowShardedTable,
                         item_dst: RowShardedTable, user, item_a, item_b=None, label=None, *, loss_kind=_lib.LOSS_MSE,
-                        reg_weight=0.0, gamma=1e-10, scale=1.0, out8=None):
+                        reg_weight=0.0, gamma=1e-10, scale=1.0, out8=None, staged_a=None, staged_b=None):
     """K training steps of this rank's batches against the row-sharded tables in ONE persistent launch
-    (``xdr_train_steps_sharded``); ids are GLOBAL row ids.  Arguments as in ``ops.train_steps``."""
+    (``xdr_train_steps_sharded``); ids are GLOBAL row ids.  Arguments as in ``ops.train_steps``.  ``staged_a`` /
+    ``staged_b``: optional dense ``[K, B, D]`` blocks holding the (first / second) item row of every interaction, pulled
+    ahead by ``gather_rows_sharded``; without them the kernel gathers item rows straight from the (peer) shards."""
     K, B = user.shape
     dev = user_tab.local.device
     if out8 is None:
@@ -139,5 +144,86 @@ def train_steps_sharded(user_tab: RowShardedTable, item_tab: RowShardedTable, us
     call('xdr_train_steps_sharded', user_tab.pointer_array(), item_tab.pointer_array(), user_dst.pointer_array(),
          item_dst.pointer_array(), user_tab.world, user_tab.n_rows, item_tab.n_rows, user_tab.dim, ptr(user), ptr(item_a),
          ptr(item_b), ptr(label), user.stride(0), B, K, 1 if item_b is not None else 0, int(loss_kind), float(gamma),
-         float(reg_weight), None, float(scale), ptr(out8), ptr(ws), ws.numel(), None, cur_stream())
+         float(reg_weight), None, float(scale), ptr(out8), ptr(ws), ws.numel(), ptr(staged_a), ptr(staged_b), None, cur_stream())
     return out8
+
+
+def gather_rows_sharded(table: RowShardedTable, idx: torch.Tensor, out: torch.Tensor):
+    """out[k, :] = table[idx[k], :] with rows pulled from whichever rank owns them (peer ``LDG`` over NVLink).
+    ``idx`` is flat, or a ``[K, B]`` view with contiguous rows (e.g. ``ids[:, 1]`` of a ``[K, 3, B]`` block)."""
+    if idx.dim() == 2 and idx.stride(1) == 1:
+        n, batch, stride = idx.numel(), idx.shape[1], idx.stride(0)
+    else:
+        idx = idx.reshape(-1).contiguous()
+        n, batch, stride = idx.numel(), 0, 0
+    call('xdr_gather_rows_sharded', table.pointer_array(), table.world, table.n_rows, table.dim, ptr(idx), n, batch, stride,
+         ptr(out), table.dim, None, cur_stream())
+    return out
+
+
+class ShardedStepRunner(object):
+    """Chunked, double-buffered driver of the sharded persistent kernel.
+
+    The persistent kernel cannot hide NVLink latency (10-20 us loaded) behind its register-held gathers, so the remote
+    side is split off: a massively parallel peer-gather kernel runs ONE CHUNK AHEAD on a second stream and pulls the
+    chunk's item rows (2 of the 3 rows of a BPR interaction; the user row is local under user-owner routing) into dense
+    local blocks; the persistent kernel of the chunk then reads them sequentially and only its gradient ``RED``s cross
+    NVLink.  ``run(ids)``: ids ``[K, 3, B]`` (or ``[K, 2, B]`` + label) on the device; returns out8 ``[K, 8]``.
+    """
+
+    def __init__(self, user_tab, item_tab, user_dst, item_dst, *, pairwise=True, loss_kind=_lib.LOSS_MSE, reg_weight=0.0,
+                 gamma=1e-10, scale=1.0, chunk=50, stage_remote=True):
+        self.t = (user_tab, item_tab, user_dst, item_dst)
+        self.kw = dict(loss_kind=loss_kind, reg_weight=reg_weight, gamma=gamma, scale=scale)
+        self.pairwise, self.chunk = pairwise, int(chunk)
+        self.stage_remote = stage_remote and user_tab.world > 1
+        self.dev = user_tab.local.device
+        self.fetch_stream = torch.cuda.Stream(device=self.dev)
+        self._stage = None
+        self._fetched = [torch.cuda.Event(), torch.cuda.Event()]
+        self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self._used = [False, False]
+        self.launches = 0
+
+    def _buffers(self, B):
+        D = self.t[1].dim
+        n = 2 if self.pairwise else 1
+        if self._stage is None or self._stage.shape[2:] != (self.chunk, B, D) or self._stage.shape[1] != n:
+            self._stage = torch.empty((2, n, self.chunk, B, D), dtype=torch.float32, device=self.dev)
+        return self._stage
+
+    def _fetch(self, ids, c0, c1, slot):
+        """peer-gather the item rows of steps [c0, c1) into staging buffer `slot` on the fetch stream"""
+        st = self._buffers(ids.shape[2])
+        with torch.cuda.stream(self.fetch_stream):
+            if self._used[slot]:
+                self.fetch_stream.wait_event(self._consumed[slot])
+            for w in range(st.shape[1]):
+                gather_rows_sharded(self.t[1], ids[c0:c1, 1 + w], st[slot, w])
+            self._fetched[slot].record(self.fetch_stream)
+
+    def run(self, ids: torch.Tensor, label=None, out8=None):
+        K, R, B = ids.shape
+        if out8 is None:
+            out8 = torch.empty((K, 8), dtype=torch.float32, device=self.dev)
+        main = torch.cuda.current_stream(self.dev)
+        if not self.stage_remote:
+            train_steps_sharded(*self.t, ids[:, 0], ids[:, 1], ids[:, 2] if self.pairwise else None, label, out8=out8, **self.kw)
+            self.launches += 1
+            return out8
+        self.fetch_stream.wait_stream(main)          # the ids are produced on the main stream
+        bounds = [(c, min(c + self.chunk, K)) for c in range(0, K, self.chunk)]
+        self._fetch(ids, *bounds[0], 0)
+        for n, (c0, c1) in enumerate(bounds):
+            slot = n % 2
+            if n + 1 < len(bounds):
+                self._fetch(ids, *bounds[n + 1], (n + 1) % 2)   # overlaps with the persistent kernel of chunk n
+            main.wait_event(self._fetched[slot])
+            st = self._stage
+            train_steps_sharded(*self.t, ids[c0:c1, 0], ids[c0:c1, 1], ids[c0:c1, 2] if self.pairwise else None,
+                                None if label is None else label[c0:c1], out8=out8[c0:c1],
+                                staged_a=st[slot, 0], staged_b=st[slot, 1] if self.pairwise else None, **self.kw)
+            self._consumed[slot].record(main)
+            self._used[slot] = True
+            self.launches += 1 + st.shape[1]
+        return out8

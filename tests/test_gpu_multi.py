@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, tmp):
+def _worker(rank, world, port, tmp, staged):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device('cuda', rank)
@@ -30,8 +30,13 @@ def _worker(rank, world, port, tmp):
         tabs = [shard.RowShardedTable.from_full(t, rank, world, dev).connect() for t in (ut, it)]
         grads = [shard.RowShardedTable(t.shape[0], dim, rank, world, dev).connect() for t in (ut, it)]
         dist.barrier()
-        out8 = shard.train_steps_sharded(tabs[0], tabs[1], grads[0], grads[1], u[rank].to(dev), ip[rank].to(dev),
-                                         ineg[rank].to(dev), reg_weight=0.01)
+        if staged:   # peer-gather kernel one chunk ahead + dense staged item rows (chunks of 4 steps, ragged last chunk)
+            runner = shard.ShardedStepRunner(tabs[0], tabs[1], grads[0], grads[1], reg_weight=0.01, chunk=4)
+            ids = torch.stack([u[rank], ip[rank], ineg[rank]], dim=1).to(dev)
+            out8 = runner.run(ids)
+        else:        # item rows gathered straight from the peer shards inside the persistent kernel
+            out8 = shard.train_steps_sharded(tabs[0], tabs[1], grads[0], grads[1], u[rank].to(dev), ip[rank].to(dev),
+                                             ineg[rank].to(dev), reg_weight=0.01)
         torch.cuda.synchronize()
         dist.barrier()                                              # every rank's remote REDs have landed
         gu_full, gi_full = grads[0].to_full(), grads[1].to_full()
@@ -54,10 +59,11 @@ def _worker(rank, world, port, tmp):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('staged', [False, True])
 @pytest.mark.parametrize('world', [2, 4, 8])
-def test_sharded_steps_match_single_gpu(world, tmp_path):
+def test_sharded_steps_match_single_gpu(world, staged, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip(f'needs {world} GPUs')
-    port = 29600 + (os.getpid() % 2000) + world
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    port = 29600 + (os.getpid() % 2000) + world + (10 if staged else 0)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), staged), nprocs=world, join=True)
     assert (tmp_path / 'ok').exists()

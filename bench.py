@@ -54,7 +54,8 @@ def parse_args():
     ap.add_argument('--no-compare', action='store_true', help='skip the per-step-kernel comparison runs')
     ap.add_argument('--mode', default='persistent', choices=['persistent', 'per_step'])
     ap.add_argument('--shard-chunk', type=int, default=50, help='N>1: steps per persistent launch / peer-gather chunk')
-    ap.add_argument('--no-stage-remote', action='store_true', help='N>1: gather item rows inside the persistent kernel')
+    ap.add_argument('--stage-remote', action='store_true',
+                    help='N>1: pull item rows with the peer-gather kernel one chunk ahead (slower in round 1, see profiles/)')
     ap.add_argument('--chunk', type=int, default=50, help='steps per launch on the end-to-end (host-fed) path')
     return ap.parse_args()
 
@@ -225,7 +226,7 @@ def run_xdr(args):
         s_ut, s_it = mk(ds.num_total_user, True), mk(ds.num_total_item, True)
         s_gu, s_gi = mk(ds.num_total_user, False), mk(ds.num_total_item, False)
         sh_runner = shard.ShardedStepRunner(s_ut, s_it, s_gu, s_gi, reg_weight=0.01, chunk=args.shard_chunk,
-                                            stage_remote=not args.no_stage_remote)
+                                            stage_remote=args.stage_remote)
         dist.barrier()
 
     # K + W distinct seeded batches (seed = 1 + step, offset per rank), resident in HBM and mirrored in pinned host memory

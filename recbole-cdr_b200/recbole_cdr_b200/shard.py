@@ -164,15 +164,17 @@ def gather_rows_sharded(table: RowShardedTable, idx: torch.Tensor, out: torch.Te
 class ShardedStepRunner(object):
     """Chunked, double-buffered driver of the sharded persistent kernel.
 
-    The persistent kernel cannot hide NVLink latency (10-20 us loaded) behind its register-held gathers, so the remote
-    side is split off: a massively parallel peer-gather kernel runs ONE CHUNK AHEAD on a second stream and pulls the
-    chunk's item rows (2 of the 3 rows of a BPR interaction; the user row is local under user-owner routing) into dense
-    local blocks; the persistent kernel of the chunk then reads them sequentially and only its gradient ``RED``s cross
-    NVLink.  ``run(ids)``: ids ``[K, 3, B]`` (or ``[K, 2, B]`` + label) on the device; returns out8 ``[K, 8]``.
+    Default (``stage_remote=False``): one persistent launch whose warps gather from and scatter-add into the peer shards
+    directly.  ``stage_remote=True`` splits the remote side off: a massively parallel peer-gather kernel runs ONE CHUNK
+    AHEAD on a second stream and pulls the chunk's item rows into dense local blocks that the persistent kernel then
+    reads sequentially (only its gradient ``RED``s cross NVLink).  Measured in round 1 the staged variant is SLOWER at
+    every GPU count (2: 7.8 vs 6.4, 4: 12.8 vs 10.5, 8: 14.5 vs 12.5 us/step): the staging block costs ~8 MB/step of
+    local DRAM traffic and random 256-byte peer reads top out near 300 GB/s per GPU whoever issues them.  Kept as a
+    tested option.  ``run(ids)``: ids ``[K, 3, B]`` (or ``[K, 2, B]`` + label) on the device; returns out8 ``[K, 8]``.
     """
 
     def __init__(self, user_tab, item_tab, user_dst, item_dst, *, pairwise=True, loss_kind=_lib.LOSS_MSE, reg_weight=0.0,
-                 gamma=1e-10, scale=1.0, chunk=50, stage_remote=True):
+                 gamma=1e-10, scale=1.0, chunk=50, stage_remote=False):
         self.t = (user_tab, item_tab, user_dst, item_dst)
         self.kw = dict(loss_kind=loss_kind, reg_weight=reg_weight, gamma=gamma, scale=scale)
         self.pairwise, self.chunk = pairwise, int(chunk)

@@ -31,7 +31,7 @@ def _worker(rank, world, port, tmp, staged):
         grads = [shard.RowShardedTable(t.shape[0], dim, rank, world, dev).connect() for t in (ut, it)]
         dist.barrier()
         if staged:   # peer-gather kernel one chunk ahead + dense staged item rows (chunks of 4 steps, ragged last chunk)
-            runner = shard.ShardedStepRunner(tabs[0], tabs[1], grads[0], grads[1], reg_weight=0.01, chunk=4)
+            runner = shard.ShardedStepRunner(tabs[0], tabs[1], grads[0], grads[1], reg_weight=0.01, chunk=4, stage_remote=True)
             ids = torch.stack([u[rank], ip[rank], ineg[rank]], dim=1).to(dev)
             out8 = runner.run(ids)
         else:        # item rows gathered straight from the peer shards inside the persistent kernel

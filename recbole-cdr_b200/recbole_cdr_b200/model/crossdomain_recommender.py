@@ -43,25 +43,20 @@ class CrossDomainRecommender(AbstractRecommender):
 
     def __init__(self, config, dataset):
         super().__init__()
-        src, tgt = dataset.source_domain_dataset, dataset.target_domain_dataset
-        self.SOURCE_USER_ID = src.uid_field
-        self.SOURCE_ITEM_ID = src.iid_field
-        self.SOURCE_NEG_ITEM_ID = config['source_domain']['NEG_PREFIX'] + self.SOURCE_ITEM_ID
-        self.source_num_users = src.num(self.SOURCE_USER_ID)
-        self.source_num_items = src.num(self.SOURCE_ITEM_ID)
-
-        self.TARGET_USER_ID = tgt.uid_field
-        self.TARGET_ITEM_ID = tgt.iid_field
-        self.TARGET_NEG_ITEM_ID = config['target_domain']['NEG_PREFIX'] + self.TARGET_ITEM_ID
-        self.target_num_users = tgt.num(self.TARGET_USER_ID)
-        self.target_num_items = tgt.num(self.TARGET_ITEM_ID)
-
-        self.total_num_users = dataset.num_total_user
-        self.total_num_items = dataset.num_total_item
-        self.overlapped_num_users = dataset.num_overlap_user
-        self.overlapped_num_items = dataset.num_overlap_item
+        # per-domain field names and id-space sizes: SOURCE_USER_ID, SOURCE_ITEM_ID, SOURCE_NEG_ITEM_ID,
+        # source_num_users, source_num_items and the same five for the target domain
+        for domain, part in (('source', dataset.source_domain_dataset), ('target', dataset.target_domain_dataset)):
+            tag = domain.upper()
+            neg_prefix = config[f'{domain}_domain']['NEG_PREFIX']
+            setattr(self, f'{tag}_USER_ID', part.uid_field)
+            setattr(self, f'{tag}_ITEM_ID', part.iid_field)
+            setattr(self, f'{tag}_NEG_ITEM_ID', neg_prefix + part.iid_field)
+            setattr(self, f'{domain}_num_users', part.num(part.uid_field))
+            setattr(self, f'{domain}_num_items', part.num(part.iid_field))
+        # joint id space (every table is allocated with the TOTAL number of rows) and the overlapped prefix of it
+        self.total_num_users, self.total_num_items = dataset.num_total_user, dataset.num_total_item
+        self.overlapped_num_users, self.overlapped_num_items = dataset.num_overlap_user, dataset.num_overlap_item
         self.OVERLAP_ID = dataset.overlap_id_field
-
         self.device = config['device']
 
     def set_phase(self, phase):

@@ -1,0 +1,53 @@
+"""Device-resident batch pipeline: positives are permuted and negatives are drawn ON THE
+GPU, producing the `[K, rows, B]` id blocks that `xdr_train_steps` consumes -- no host loop, no PCIe on the step path.
+
+Replaces, for one domain and one epoch, the host side of recbole `TrainDataLoader.__next__` + `_neg_sampling`
+[recbole-1.0.1] as wrapped by reference data/dataloader.py:72-76 and fed by sampler/crossdomain_sampler.py:269-290:
+shuffle the interactions, slice `step` positives per batch, draw one negative per positive that the user has not
+interacted with.  Field semantics are the reference's: pairwise -> (user, item, neg_item); pointwise -> positives followed
+by (user, sampled item) with labels 1..1, 0..0.
+"""
+import torch
+
+
+class DeviceDomainData(object):
+    """One domain's training interactions resident in HBM + its device sampler."""
+
+    def __init__(self, users, items, sampler, device='cuda'):
+        self.device = torch.device(device)
+        self.users = torch.as_tensor(users, dtype=torch.int64).to(self.device)
+        self.items = torch.as_tensor(items, dtype=torch.int64).to(self.device)
+        self.sampler = sampler
+
+    def __len__(self):
+        return self.users.numel()
+
+    def epoch_blocks(self, batch_size, steps_per_block, pairwise=True, shuffle=True, generator=None, drop_last=True):
+        """Yield `(ids [K, rows, B], label [K, B] or None)` blocks covering one epoch (K <= steps_per_block).
+
+        pairwise: rows = (user, item, neg_item), B = batch_size positives per step.
+        pointwise: rows = (user, item), B = batch_size with batch_size // 2 positives followed by their negatives.
+        The ragged tail that does not fill a whole step is dropped when ``drop_last`` (the persistent kernel wants equal
+        steps); otherwise it is returned as a final block of one shorter step."""
+        n = self.users.numel()
+        perm = torch.randperm(n, device=self.device, generator=generator) if shuffle else torch.arange(n, device=self.device)
+        pos = batch_size if pairwise else max(batch_size // 2, 1)
+        n_steps = n // pos
+        for s0 in range(0, n_steps, steps_per_block):
+            k = min(steps_per_block, n_steps - s0)
+            sel = perm[s0 * pos:(s0 + k) * pos]
+            yield self._block(sel, k, pos, pairwise)
+        if not drop_last and n_steps * pos < n:
+            sel = perm[n_steps * pos:]
+            yield self._block(sel, 1, sel.numel(), pairwise)
+
+    def _block(self, sel, k, pos, pairwise):
+        u = self.users[sel]
+        i = self.items[sel]
+        neg = self.sampler.sample_by_key_ids(u, 1, check=False)
+        u, i, neg = u.view(k, pos), i.view(k, pos), neg.view(k, pos)
+        if pairwise:
+            return torch.stack([u, i, neg], dim=1).contiguous(), None
+        ids = torch.stack([torch.cat([u, u], dim=1), torch.cat([i, neg], dim=1)], dim=1).contiguous()
+        label = torch.cat([torch.ones_like(u, dtype=torch.float32), torch.zeros_like(u, dtype=torch.float32)], dim=1)
+        return ids, label.contiguous()

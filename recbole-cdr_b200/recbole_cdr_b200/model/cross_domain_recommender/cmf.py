@@ -49,6 +49,16 @@ class CMF(CrossDomainRecommender):
                                 interaction[self.TARGET_LABEL], _lib.LOSS_BCE_SIGMOID, self.gamma)
         return loss_s * self.alpha + loss_t * (1 - self.alpha)
 
+    def fused_step_spec(self):
+        """Two weighted domain terms on the shared tables (cmf.py:81-99): the trainer's persistent multi-step path runs
+        them as two launches per chunk, with loss weights alpha and 1 - alpha folded into the SGD scale."""
+        ut, it = self.user_embedding.weight, self.item_embedding.weight
+        return [dict(user_tab=ut, item_tab=it, pairwise=False, loss_kind=_lib.LOSS_BCE_SIGMOID, reg_weight=self.lamda,
+                     fields=[self.SOURCE_USER_ID, self.SOURCE_ITEM_ID], label_field=self.SOURCE_LABEL, loss_weight=self.alpha),
+                dict(user_tab=ut, item_tab=it, pairwise=False, loss_kind=_lib.LOSS_BCE_SIGMOID, reg_weight=self.gamma,
+                     fields=[self.TARGET_USER_ID, self.TARGET_ITEM_ID], label_field=self.TARGET_LABEL,
+                     loss_weight=1 - self.alpha)]
+
     def predict(self, interaction):
         return self.forward(interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID])
 

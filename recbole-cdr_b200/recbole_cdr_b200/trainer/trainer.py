@@ -41,7 +41,8 @@ class FusedStepRunner:
             self.ut, self.it = spec['user_tab'], spec['item_tab']
             self.dev = self.ut.device
             if lr is not None:      # fused SGD: the scatter-add target is the weight table itself
-                self.dst_u, self.dst_i, self.scale = self.ut.data, self.it.data, -float(lr)
+                self.dst_u, self.dst_i = self.ut.data, self.it.data
+                self.scale = -float(lr) * float(spec.get('loss_weight', 1.0))
             else:                   # gradient accumulation into dense .grad-style tables
                 gu, gi = grad_tables if grad_tables is not None else (torch.zeros_like(self.ut), torch.zeros_like(self.it))
                 self.dst_u, self.dst_i, self.scale = gu, gi, 1.0
@@ -177,47 +178,71 @@ class CrossDomainTrainer(object):
         return spec_fn()
 
     def _train_epoch_fused(self, train_data, epoch_idx, spec):
-        """K batches per persistent launch with the SGD update fused into the scatter-add."""
+        """K batches per persistent launch with the SGD update fused.  ``spec`` is one term (EMCDR phases) or a list of
+        weighted terms on shared tables (CMF BOTH: source term then target term, one launch each per chunk)."""
         self.model.train()
-        runner = FusedStepRunner(spec, lr=self.learning_rate)
-        fields, label_field = spec['fields'], spec.get('label_field')
+        specs = spec if isinstance(spec, (list, tuple)) else [spec]
+        runners = [FusedStepRunner(sp, lr=self.learning_rate) for sp in specs]
         K = self.fused_steps
-        pending: List[torch.Tensor] = []
+        pending = []   # (weight, pinned per-step losses)
         total = 0.0
-        chunk, labels = [], []
+        chunks = [[] for _ in specs]
+        labels = [[] for _ in specs]
+        widths = [None] * len(specs)
 
         def flush():
-            nonlocal chunk, labels
-            if not chunk:
-                return
-            block = torch.stack(chunk).pin_memory()
-            lab = torch.stack(labels).pin_memory() if labels else None
-            pending.append(runner.run(block, lab))
-            chunk, labels = [], []
+            for n, (sp, runner) in enumerate(zip(specs, runners)):
+                if not chunks[n]:
+                    continue
+                block = torch.stack(chunks[n]).pin_memory()
+                lab = torch.stack(labels[n]).pin_memory() if labels[n] else None
+                pending.append((float(sp.get('loss_weight', 1.0)), runner.run(block, lab)))
+                chunks[n], labels[n] = [], []
 
-        width = None
         for interaction in train_data:
-            ids = torch.stack([interaction[f].reshape(-1).cpu() for f in fields])
-            ok = ops.train_steps_supported(ids.shape[1], spec['user_tab'].shape[1], spec['pairwise'], self.device)
-            if not ok or (width is not None and ids.shape[1] != width):
+            ids = [torch.stack([interaction[f].reshape(-1).cpu() for f in sp['fields']]) for sp in specs]
+            ok = all(ops.train_steps_supported(i.shape[1], sp['user_tab'].shape[1], sp['pairwise'], self.device) and
+                     (w is None or i.shape[1] == w) for i, sp, w in zip(ids, specs, widths))
+            if not ok:
                 # a ragged last batch (or a shape the persistent kernel does not take) goes through the per-step path
                 flush()
-                runner.synchronize()
+                runners[0].synchronize()
                 total += self._train_epoch([interaction], epoch_idx)
                 continue
-            width = ids.shape[1]
-            chunk.append(ids)
-            if label_field:
-                labels.append(interaction[label_field].reshape(-1).float().cpu())
-            if len(chunk) == K:
+            for n, (i, sp) in enumerate(zip(ids, specs)):
+                widths[n] = i.shape[1]
+                chunks[n].append(i)
+                if sp.get('label_field'):
+                    labels[n].append(interaction[sp['label_field']].reshape(-1).float().cpu())
+            if len(chunks[0]) == K:
                 flush()
         flush()
-        runner.synchronize()
-        for l in pending:
-            total += float(l.sum().item())
+        runners[0].synchronize()
+        for w, l in pending:
+            total += w * float(l.sum().item())
         if total != total:
             raise ValueError('Training loss is nan')
         return total
+
+    def train_epoch_device(self, domain_data, batch_size, spec=None, steps_per_launch=None, generator=None):
+        """One epoch with NOTHING on the host per step: ``domain_data`` (``data.DeviceDomainData``) permutes the positives
+        and draws the negatives on the GPU, every block of K steps is one persistent launch with the SGD update fused.
+        Returns the summed per-step loss (one device->host read per epoch)."""
+        spec = spec or self.model.fused_step_spec()
+        if spec is None or isinstance(spec, (list, tuple)):
+            raise ValueError('train_epoch_device needs a single-term fused step spec (e.g. EMCDR SOURCE / TARGET phase)')
+        K = steps_per_launch or max(self.fused_steps, 1)
+        total = torch.zeros((), dtype=torch.float32, device=spec['user_tab'].device)
+        scale = -float(self.learning_rate) * float(spec.get('loss_weight', 1.0))
+        for ids, label in domain_data.epoch_blocks(batch_size, K, pairwise=spec['pairwise'], generator=generator):
+            out8, _, _ = ops.train_steps(spec['user_tab'].data, spec['item_tab'].data, ids[:, 0], ids[:, 1],
+                                         ids[:, 2] if spec['pairwise'] else None, label,
+                                         loss_kind=spec.get('loss_kind', _lib.LOSS_MSE), reg_weight=spec['reg_weight'],
+                                         gamma=spec.get('gamma', 1e-10), user_dst=spec['user_tab'].data,
+                                         item_dst=spec['item_tab'].data, scale=scale)
+            total = total + out8[:, 0].sum()
+        self._check_nan(total)
+        return float(total.item())
 
     # ---- phase loop ------------------------------------------------------------------------------------------
     def _fit_phase(self, train_data, valid_data, verbose, saved, show_progress, callback_fn):

@@ -127,7 +127,43 @@ report('A7-8 CoNet BOTH step fwd+bwd, CUDA-graph replay', timeit(lambda: gs(ic),
 del m, gs
 torch.cuda.empty_cache()
 
+# ---- A16 at BASELINE config #1 sizes (CMF, bundled ml-1m -> ml-100k after filtering: 6982 users, 3351 items, 1154 overlapped
+#      items, no user overlap; B = 2048 per domain): K = 64 BOTH steps = 2 persistent launches, vs the oracle port on the host
+from oracle import cdr_oracle as O
+dsm = SyntheticCrossDomainDataset(IdSpace(1, 943, 6039), IdSpace(1155, 528, 1668))
+cu = torch.randn(dsm.num_total_user, 64, device=dev) * 0.02
+ci = torch.randn(dsm.num_total_item, 64, device=dev) * 0.02
+gcu, gci = torch.zeros_like(cu), torch.zeros_like(ci)
+Kc, Bc = 64, 2048
+def cmf_blocks(domain, seed):
+    bs = [synthetic.make_batch(dsm, domain, Bc, seed + s, 'cpu', pairwise=False) for s in range(Kc)]
+    return {k: torch.stack([b[k] for b in bs]).to(dev) for k in bs[0]}
+sb, tb = cmf_blocks('source', 100), cmf_blocks('target', 200)
+def cmf_both():
+    ops.train_steps(cu, ci, sb['source_user_id'], sb['source_item_id'], None, sb['source_label'].contiguous(),
+                    loss_kind=_lib.LOSS_BCE_SIGMOID, reg_weight=0.0, user_dst=gcu, item_dst=gci, scale=0.5)
+    ops.train_steps(cu, ci, tb['target_user_id'], tb['target_item_id'], None, tb['target_label'].contiguous(),
+                    loss_kind=_lib.LOSS_BCE_SIGMOID, reg_weight=0.0, user_dst=gcu, item_dst=gci, scale=0.5)
+sec = timeit(cmf_both)
+report(f'A16 CMF BOTH steps at config #1 sizes (6982 x 3351 tables, 2 x B=2048), {Kc} steps = 2 launches', sec,
+       bytes_=Kc * 2 * Bc * 1044, units=Kc * 2 * Bc, unit_name='inter')
+torch.set_num_threads(os.cpu_count())
+cuc, cic = torch.nn.Parameter(cu.cpu()), torch.nn.Parameter(ci.cpu())
+hb = [{k: v[s].cpu() for k, v in {**sb, **tb}.items()} for s in range(6)]
+def cpu_step(b):
+    cuc.grad = cic.grad = None
+    O.cmf_loss(cuc, cic, b['source_user_id'], b['source_item_id'], b['source_label'], b['target_user_id'], b['target_item_id'],
+               b['target_label'], 0.5, 0.0, 0.0).sum().backward()
+cpu_step(hb[0])
+t0 = time.perf_counter()
+for b in hb[1:]:
+    cpu_step(b)
+cpu_sec = (time.perf_counter() - t0) / 5
+line = {'kernel': f'A16 CMF BOTH step, oracle port on {os.cpu_count()} host threads (config #1 sizes)', 'us': cpu_sec * 1e6,
+        'Minter_per_s': 2 * Bc / cpu_sec / 1e6}
+results.append(line); print(json.dumps(line))
 if ONLY:
+    json.dump(results, open(os.path.join(ROOT, 'gpurun_out', 'bench_rows.json'), 'w'), indent=1)
     sys.exit(0)
 # ---- A10-A12: BiTGCF graph layer at 1/4 of config #4 (0.5M users x 0.25M items per domain, 8M edges, D = 64) ----------
 from recbole_cdr_b200.graph import GraphProp, NormAdj, TransferNorm

@@ -62,7 +62,8 @@ class FusedStepRunner:
             for _ in range(self.n_buffers):
                 self._bufs.append({
                     'key': key, 'ids': torch.empty(shape, dtype=torch.int64, device=self.dev),
-                    'label': torch.empty((K, shape[2]), dtype=torch.float32, device=self.dev) if with_label else None,
+                    # the kernel walks ids and labels with ONE step stride: give the label rows the stride of the id rows
+                    'label': (torch.empty(shape, dtype=torch.float32, device=self.dev)[:, 0] if with_label else None),
                     'out8': torch.empty((K, 8), dtype=torch.float32, device=self.dev),
                     'loss': torch.empty(K, dtype=torch.float32).pin_memory(),
                     'ready': torch.cuda.Event(), 'done': torch.cuda.Event(), 'used': False})

@@ -271,6 +271,15 @@ XDR_API int xdr_train_steps_sharded(const float* const* user_shards, const float
 XDR_API int xdr_gather_rows_sharded(const float* const* shards, int n_shards, int64_t n_rows, int dim, const int64_t* idx,
                                     int64_t n_idx, int64_t idx_batch, int64_t idx_step_stride, float* out, int64_t out_ld,
                                     int32_t* oob, xdr_stream_t stream);
+/* Row-sharded SpMM (BiTGCF over G GPUs): as xdr_spmm_csr, but the operand X is block-cyclically row-sharded
+ * over x_shards[0..G) (peer-mapped, each [ceil(N/G), dim]): column id c is row c div G of shard c mod G; the work items
+ * cover THIS rank's rows of L (torch.sparse.mm(L, E), bitgcf.py:131, restricted to the rows the rank owns) and S is
+ * local.  The neighbour-row gathers cross NVLink directly; the caller orders the launch after every owner has written
+ * its shard (one tiny all-reduce on the stream).                                                                      */
+XDR_API int xdr_spmm_csr_sharded(const int64_t* work_row, const int64_t* work_beg, const int64_t* work_end,
+                                 const uint8_t* work_split, int64_t n_work, const int64_t* split_rows,
+                                 int64_t n_split_rows, const int64_t* col, const float* val, const float* const* x_shards,
+                                 int n_shards, int dim, float* S, xdr_stream_t stream);
 /* CUDA-IPC plumbing.  export: 64-byte handle of the allocation containing dev_ptr + byte offset of dev_ptr inside it
  * (host outputs).  open: map a peer's allocation, returns its base (add the exported offset).  close: unmap.            */
 XDR_API int xdr_ipc_export(const void* dev_ptr, unsigned char* handle64_host, int64_t* offset_host);

@@ -53,18 +53,28 @@ struct MlpArgs {
   int32_t* oob;
 };
 
+// Activations and their gradients are kept TRANSPOSED in shared memory: actT[l][k * LD + r] with LD = tile_rows + 4, so the
+// values of four consecutive batch rows at one feature are a single 16-byte LDS (the +4 pad keeps consecutive features on
+// different banks).  Every inner loop then does 2 LDS per 4 FMAs with four independent accumulators.
 template <int CAP>
-__device__ __forceinline__ void mlp_accum_dw(float (&acc)[CAP], const float* dz, const float* x, int din, int dout, int tid,
-                                             int kTileRows) {
+__device__ __forceinline__ void mlp_accum_dw(float (&acc)[CAP], const float* dzT, const float* xT, int din, int dout, int tid,
+                                             int tile_rows, int LD) {
 #pragma unroll
   for (int i = 0; i < CAP; ++i) {
     const int e = tid + i * kMlpThreads;
     if (e < din * dout) {
       const int n = e / din, k = e - n * din;
-      float s = acc[i];
-#pragma unroll 4
-      for (int r = 0; r < kTileRows; ++r) s = fmaf(dz[r * dout + n], x[r * din + k], s);
-      acc[i] = s;
+      const float4* dz = reinterpret_cast<const float4*>(dzT + n * LD);
+      const float4* x = reinterpret_cast<const float4*>(xT + k * LD);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int r4 = 0; r4 < tile_rows / 4; ++r4) {
+        const float4 a = dz[r4], b = x[r4];
+        s0 = fmaf(a.x, b.x, s0);
+        s1 = fmaf(a.y, b.y, s1);
+        s2 = fmaf(a.z, b.z, s2);
+        s3 = fmaf(a.w, b.w, s3);
+      }
+      acc[i] += (s0 + s1) + (s2 + s3);
     }
   }
 }
@@ -86,8 +96,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Wo
   __shared__ float red_smem[8];
   const int tid = threadIdx.x;
   const int nl = a.n_layers;
-  const int kTileRows = a.tile_rows;
-  // ---- carve shared memory: per layer W [dout][din], Wt [din][dout], bias; per tile activations act[l] and grads g[l]
+  const int TR = a.tile_rows;  // multiple of 4
+  const int LD = TR + 4;
+  // ---- carve shared memory: per layer W [dout][din], Wt [din][dout], bias; per tile actT[l] / grdT[l] [dims[l]][LD]
   float* Wm[kMaxLayers];
   float* Wt[kMaxLayers];
   float* bs[kMaxLayers];
@@ -101,10 +112,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Wo
     bs[l] = p; p += (a.dims[l + 1] + 3) & ~3;
   }
   for (int l = 0; l <= nl; ++l) {
-    act[l] = p; p += (kTileRows * a.dims[l] + 3) & ~3;
-    grd[l] = p; p += (kTileRows * a.dims[l] + 3) & ~3;
+    act[l] = p; p += a.dims[l] * LD;
+    grd[l] = p; p += a.dims[l] * LD;
   }
-  float* tgt = p;  // [kTileRows][dims[nl]] target rows (head 0)
+  float* tgt = p;  // [TR][dims[nl]] target rows, row-major (head 0)
   for (int l = 0; l < nl; ++l) {
     const int din = a.dims[l], dout = a.dims[l + 1];
     for (int e = tid; e < din * dout; e += kMlpThreads) {
@@ -130,15 +141,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Wo
   const int d0 = a.dims[0], dl = a.dims[nl];
   const int nv = a.dim / 4;
   float loss_acc[1] = {0.f};
-  const int64_t n_tiles = (a.batch + kTileRows - 1) / kTileRows;
+  const int64_t n_tiles = (a.batch + TR - 1) / TR;
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t r0 = tile * kTileRows;
-    const int rows = (int)min((int64_t)kTileRows, a.batch - r0);
-    // ---- 1. gather the tile's input rows (float4 granularity) -------------------------------------------------------
+    const int64_t r0 = tile * TR;
+    const int rows = (int)min((int64_t)TR, a.batch - r0);
+    // ---- 1. gather the tile's input rows (one float4 = 4 consecutive features of one row) -> actT[0] ----------------
     {
       const int per_row = (a.in_mode == 0 ? 1 : 2) * nv;  // float4 per input row
-      for (int e = tid; e < kTileRows * per_row; e += kMlpThreads) {
+      for (int e = tid; e < TR * per_row; e += kMlpThreads) {
         const int r = e / per_row, c = e - r * per_row;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < rows) {
@@ -161,10 +172,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Wo
             }
           }
         }
-        reinterpret_cast<float4*>(act[0] + r * d0)[c] = v;
+        float* dst = act[0] + (4 * c) * LD + r;
+        dst[0] = v.x; dst[LD] = v.y; dst[2 * LD] = v.z; dst[3 * LD] = v.w;
       }
       if (a.head == 0) {
-        for (int e = tid; e < kTileRows * nv; e += kMlpThreads) {
+        for (int e = tid; e < TR * nv; e += kMlpThreads) {
           const int r = e / nv, c = e - r * nv;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (r < rows) {
@@ -176,42 +188,47 @@ __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Wo
       }
     }
     __syncthreads();
-    // ---- 2. forward through the layers -----------------------------------------------------------------------------
+    // ---- 2. forward: work item = (block of 4 rows, output feature n) ------------------------------------------------
     for (int l = 0; l < nl; ++l) {
       const int din = a.dims[l], dout = a.dims[l + 1];
       const int actk = (l == nl - 1) ? a.last_act : a.hidden_act;
-      const float* x = act[l];
+      const float* xT = act[l];
       const float* wt = Wt[l];
-      for (int e = tid; e < kTileRows * dout; e += kMlpThreads) {
-        const int r = e / dout, n = e - r * dout;
-        float s = bs[l][n];
-        const float* xr = x + r * din;
+      for (int e = tid; e < (TR / 4) * dout; e += kMlpThreads) {
+        const int rb = e / dout, n = e - rb * dout;
+        const float bias = bs[l][n];
+        float4 s = make_float4(bias, bias, bias, bias);
+        const float4* x4 = reinterpret_cast<const float4*>(xT + 4 * rb);
+        const int ld4 = LD / 4;
 #pragma unroll 4
-        for (int k = 0; k < din; ++k) s = fmaf(xr[k], wt[k * dout + n], s);
-        float y = s;
-        if (actk == XDR_ACT_RELU) y = s > 0.f ? s : 0.f;
-        else if (actk == XDR_ACT_TANH) y = tanhf(s);
-        else if (actk == XDR_ACT_SIGMOID) y = sigmoidf_(s);
-        act[l + 1][e] = y;
+        for (int k = 0; k < din; ++k) s = axpy4(wt[k * dout + n], x4[k * ld4], s);
+        float y[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (actk == XDR_ACT_RELU) y[i] = y[i] > 0.f ? y[i] : 0.f;
+          else if (actk == XDR_ACT_TANH) y[i] = tanhf(y[i]);
+          else if (actk == XDR_ACT_SIGMOID) y[i] = sigmoidf_(y[i]);
+        }
+        *reinterpret_cast<float4*>(act[l + 1] + n * LD + 4 * rb) = make_float4(y[0], y[1], y[2], y[3]);
       }
       __syncthreads();
     }
     // ---- 3. loss head: loss partial and gradient of the last activation ---------------------------------------------
     if (a.head == 0) {
       const float gs = g_up * 2.0f / ((float)a.batch * (float)dl);
-      for (int e = tid; e < kTileRows * dl; e += kMlpThreads) {
-        const int r = e / dl;
+      for (int e = tid; e < TR * dl; e += kMlpThreads) {
+        const int n = e / TR, r = e - n * TR;
         float g = 0.f;
         if (r < rows) {
-          const float d = act[nl][e] - tgt[e];
+          const float d = act[nl][n * LD + r] - tgt[r * dl + n];
           loss_acc[0] += d * d;
           g = gs * d;
         }
-        grd[nl][e] = g;
+        grd[nl][n * LD + r] = g;
       }
     } else {
       const float gs = g_up / (float)a.batch;
-      for (int r = tid; r < kTileRows; r += kMlpThreads) {
+      for (int r = tid; r < TR; r += kMlpThreads) {
         float g = 0.f;
         if (r < rows) {
           const float pz = sigmoidf_(act[nl][r]), y = a.label[r0 + r];
@@ -229,38 +246,39 @@ __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Wo
     for (int l = nl - 1; l >= 0; --l) {
       const int din = a.dims[l], dout = a.dims[l + 1];
       const int actk = (l == nl - 1) ? a.last_act : a.hidden_act;
-      // dz = g * act'(y) in place
-      if (actk != XDR_ACT_NONE) {
-        for (int e = tid; e < kTileRows * dout; e += kMlpThreads) {
-          const float y = act[l + 1][e], g = grd[l + 1][e];
+      if (actk != XDR_ACT_NONE) {  // dz = g * act'(y) in place
+        for (int e = tid; e < TR * dout; e += kMlpThreads) {
+          const int n = e / TR, r = e - n * TR;
+          const float y = act[l + 1][n * LD + r], g = grd[l + 1][n * LD + r];
           float d = g;
           if (actk == XDR_ACT_RELU) d = y > 0.f ? g : 0.f;
           else if (actk == XDR_ACT_TANH) d = g * (1.f - y * y);
           else if (actk == XDR_ACT_SIGMOID) d = g * (1.f - y) * y;
-          grd[l + 1][e] = d;
+          grd[l + 1][n * LD + r] = d;
         }
         __syncthreads();
       }
-      const float* dz = grd[l + 1];
-      const float* x = act[l];
+      const float* dzT = grd[l + 1];
+      const float* xT = act[l];
       // weight gradient: thread owns elements e = tid + 256*i of W[l]  (n = e / din, k = e % din)
-      if (l == 0) mlp_accum_dw(accW0, dz, x, din, dout, tid, kTileRows);
-      else if (l == 1) mlp_accum_dw(accW1, dz, x, din, dout, tid, kTileRows);
-      else mlp_accum_dw(accW2, dz, x, din, dout, tid, kTileRows);
+      if (l == 0) mlp_accum_dw(accW0, dzT, xT, din, dout, tid, TR, LD);
+      else if (l == 1) mlp_accum_dw(accW1, dzT, xT, din, dout, tid, TR, LD);
+      else mlp_accum_dw(accW2, dzT, xT, din, dout, tid, TR, LD);
       if (tid < dout) {
-        float s = accB[l];
-        for (int r = 0; r < kTileRows; ++r) s += dz[r * dout + tid];
-        accB[l] = s;
-      }
-      // input gradient g[l] = dz W[l]
-      const float* wm = Wm[l];
-      for (int e = tid; e < kTileRows * din; e += kMlpThreads) {
-        const int r = e / din, k = e - r * din;
         float s = 0.f;
-        const float* dzr = dz + r * dout;
+        for (int r = 0; r < TR; ++r) s += dzT[tid * LD + r];
+        accB[l] += s;
+      }
+      // input gradient: work item = (block of 4 rows, input feature k):  gT[l][k][r] = sum_n dzT[n][r] * W[n][k]
+      const float* wm = Wm[l];
+      for (int e = tid; e < (TR / 4) * din; e += kMlpThreads) {
+        const int rb = e / din, k = e - rb * din;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* dz4 = reinterpret_cast<const float4*>(dzT + 4 * rb);
+        const int ld4 = LD / 4;
 #pragma unroll 4
-        for (int n = 0; n < dout; ++n) s = fmaf(dzr[n], wm[n * din + k], s);
-        grd[l][e] = s;
+        for (int n = 0; n < dout; ++n) s = axpy4(wm[n * din + k], dz4[n * ld4], s);
+        *reinterpret_cast<float4*>(grd[l] + k * LD + 4 * rb) = s;
       }
       __syncthreads();
     }
@@ -269,8 +287,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Wo
       const int per_row = (a.in_mode == 0 ? 1 : 2) * nv;
       for (int e = tid; e < rows * per_row; e += kMlpThreads) {
         const int r = e / per_row, c = e - r * per_row;
-        float4 g = reinterpret_cast<const float4*>(grd[0] + r * d0)[c];
-        g = scale4(a.scale, g);
+        const float* src = grd[0] + (4 * c) * LD + r;
+        const float4 g = scale4(a.scale, make_float4(src[0], src[LD], src[2 * LD], src[3 * LD]));
         if (a.in_mode == 0) {
           const int64_t id = a.idx_u[r0 + r];
           if ((uint64_t)id < (uint64_t)a.n_u) red_add4(a.dAu + id * a.dim, c, g);
@@ -289,14 +307,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Wo
                    make_float4(g.x * wa(y.x, x.x), g.y * wa(y.y, x.y), g.z * wa(y.z, x.z), g.w * wa(y.w, x.w)));
         }
       }
-      if (a.head == 0) {  // the target embedding is NOT detached (emcdr.py:156-168): dT = -dY
+      if (a.head == 0 && a.last_act == XDR_ACT_NONE) {  // the target embedding is NOT detached (emcdr.py:156-168): dT = -dY
         for (int e = tid; e < rows * nv; e += kMlpThreads) {
           const int r = e / nv, c = e - r * nv;
           const int64_t id = a.idx_u[r0 + r];
           if ((uint64_t)id >= (uint64_t)a.n_u) continue;
-          float4 g = reinterpret_cast<const float4*>(grd[nl] + r * dl)[c];
-          if (a.last_act != XDR_ACT_NONE) continue;  // (only the linear last layer is used with the MSE head)
-          red_add4(a.dT + id * a.dim, c, scale4(-a.scale, g));
+          const float* src = grd[nl] + (4 * c) * LD + r;
+          red_add4(a.dT + id * a.dim, c, scale4(-a.scale, make_float4(src[0], src[LD], src[2 * LD], src[3 * LD])));
         }
       }
     }
@@ -321,10 +338,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Wo
 }
 
 static size_t mlp_smem_bytes(const MlpArgs& a) {
-  const int kTileRows = a.tile_rows;
+  const int kTileRows = a.tile_rows, LD = a.tile_rows + 4;
   size_t f = 0;
   for (int l = 0; l < a.n_layers; ++l) f += 2 * (size_t)((a.dims[l] * a.dims[l + 1] + 3) & ~3) + ((a.dims[l + 1] + 3) & ~3);
-  for (int l = 0; l <= a.n_layers; ++l) f += 2 * (size_t)((kTileRows * a.dims[l] + 3) & ~3);
+  for (int l = 0; l <= a.n_layers; ++l) f += 2 * (size_t)a.dims[l] * LD;
   f += (size_t)kTileRows * a.dims[a.n_layers];
   return f * sizeof(float);
 }

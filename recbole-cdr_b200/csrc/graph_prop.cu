@@ -21,12 +21,22 @@ namespace xdr {
 constexpr int kGThreads = 256;
 
 // ---- S = L . X over work items ------------------------------------------------------------------------------------
-template <int VEC>
+// SHARDED: the operand X is block-cyclically row-sharded over G peer-mapped shards (column c lives on shard c mod G at
+// local row c div G); the neighbour-row gathers then cross NVLink directly and the output rows are this
+// rank's.  Peer rows are read with plain coherent loads: the exchange buffers are rewritten by their owners between
+// launches.
+template <bool SHARDED>
+__device__ __forceinline__ float4 spmm_ld(const float* X, const Shards& xs, int log2g, int64_t c, int64_t row_f, int cc) {
+  if (SHARDED) return ld_row4(shard_row(xs, log2g, c, row_f), cc);
+  return ldg_row4(X + c * row_f, cc);
+}
+
+template <int VEC, bool SHARDED>
 __global__ void __launch_bounds__(kGThreads)
     spmm_work_kernel(const int64_t* __restrict__ work_row, const int64_t* __restrict__ work_beg,
                      const int64_t* __restrict__ work_end, const uint8_t* __restrict__ work_split, int64_t n_work,
-                     const int64_t* __restrict__ col, const float* __restrict__ val, const float* __restrict__ X, int nv,
-                     float* __restrict__ S) {
+                     const int64_t* __restrict__ col, const float* __restrict__ val, const float* __restrict__ X, Shards xs,
+                     int log2g, int nv, float* __restrict__ S) {
   const int sub = threadIdx.x & (kLanesPerRow - 1);
   const int64_t group = ((int64_t)blockIdx.x * kGThreads + threadIdx.x) / kLanesPerRow;
   const int64_t n_groups = (int64_t)gridDim.x * kGThreads / kLanesPerRow;
@@ -45,8 +55,8 @@ __global__ void __launch_bounds__(kGThreads)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const int cc = sub + v * kLanesPerRow;
-        x0[v] = cc < nv ? ldg_row4(X + c0 * row_f, cc) : make_float4(0.f, 0.f, 0.f, 0.f);
-        x1[v] = cc < nv ? ldg_row4(X + c1 * row_f, cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x0[v] = cc < nv ? spmm_ld<SHARDED>(X, xs, log2g, c0, row_f, cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x1[v] = cc < nv ? spmm_ld<SHARDED>(X, xs, log2g, c1, row_f, cc) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[v] = axpy4(a1, x1[v], axpy4(a0, x0[v], acc[v]));
@@ -57,7 +67,7 @@ __global__ void __launch_bounds__(kGThreads)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const int cc = sub + v * kLanesPerRow;
-        if (cc < nv) acc[v] = axpy4(a0, ldg_row4(X + c0 * row_f, cc), acc[v]);
+        if (cc < nv) acc[v] = axpy4(a0, spmm_ld<SHARDED>(X, xs, log2g, c0, row_f, cc), acc[v]);
       }
     }
     float* out = S + r * row_f;
@@ -254,25 +264,58 @@ using namespace xdr;
 
 extern "C" {
 
-int xdr_spmm_csr(const int64_t* work_row, const int64_t* work_beg, const int64_t* work_end, const uint8_t* work_split,
-                 int64_t n_work, const int64_t* split_rows, int64_t n_split_rows, const int64_t* col, const float* val,
-                 const float* X, int dim, float* S, xdr_stream_t stream) {
-  XDR_REQUIRE(dim_ok(dim), "xdr_spmm_csr: dim=%d must be a multiple of 4 in (0, 256]", dim);
-  XDR_REQUIRE(n_work >= 0 && n_split_rows >= 0, "xdr_spmm_csr: negative size");
+static int spmm_launch(const char* fn, const int64_t* work_row, const int64_t* work_beg, const int64_t* work_end,
+                       const uint8_t* work_split, int64_t n_work, const int64_t* split_rows, int64_t n_split_rows,
+                       const int64_t* col, const float* val, const float* X, const Shards* xs, int log2g, int dim, float* S,
+                       xdr_stream_t stream) {
+  XDR_REQUIRE(dim_ok(dim), "%s: dim=%d must be a multiple of 4 in (0, 256]", fn, dim);
+  XDR_REQUIRE(n_work >= 0 && n_split_rows >= 0, "%s: negative size", fn);
   if (n_work == 0) return XDR_OK;
-  XDR_REQUIRE(work_row && work_beg && work_end && work_split && col && val && X && S, "xdr_spmm_csr: null pointer");
-  XDR_REQUIRE(aligned16(X) && aligned16(S), "xdr_spmm_csr: X and S must be 16-byte aligned");
+  XDR_REQUIRE(work_row && work_beg && work_end && work_split && col && val && (X || xs) && S, "%s: null pointer", fn);
+  XDR_REQUIRE(aligned16(X) && aligned16(S), "%s: X and S must be 16-byte aligned", fn);
   const int nv = dim / 4;
   cudaStream_t s = (cudaStream_t)stream;
   if (n_split_rows > 0) {
-    XDR_REQUIRE(split_rows, "xdr_spmm_csr: null split_rows");
+    XDR_REQUIRE(split_rows, "%s: null split_rows", fn);
     XDR_DISPATCH_VEC(nv, (zero_rows_kernel<VEC><<<rows_grid(n_split_rows), kGThreads, 0, s>>>(split_rows, n_split_rows, nv, S)));
     XDR_LAUNCH_OK();
   }
-  XDR_DISPATCH_VEC(nv, (spmm_work_kernel<VEC><<<rows_grid(n_work), kGThreads, 0, s>>>(work_row, work_beg, work_end, work_split,
-                                                                                      n_work, col, val, X, nv, S)));
+  if (xs != nullptr) {
+    const Shards sh = *xs;
+    XDR_DISPATCH_VEC(nv, (spmm_work_kernel<VEC, true><<<rows_grid(n_work), kGThreads, 0, s>>>(
+                             work_row, work_beg, work_end, work_split, n_work, col, val, nullptr, sh, log2g, nv, S)));
+  } else {
+    const Shards sh{};
+    XDR_DISPATCH_VEC(nv, (spmm_work_kernel<VEC, false><<<rows_grid(n_work), kGThreads, 0, s>>>(
+                             work_row, work_beg, work_end, work_split, n_work, col, val, X, sh, 0, nv, S)));
+  }
   XDR_LAUNCH_OK();
   return XDR_OK;
+}
+
+int xdr_spmm_csr(const int64_t* work_row, const int64_t* work_beg, const int64_t* work_end, const uint8_t* work_split,
+                 int64_t n_work, const int64_t* split_rows, int64_t n_split_rows, const int64_t* col, const float* val,
+                 const float* X, int dim, float* S, xdr_stream_t stream) {
+  return spmm_launch("xdr_spmm_csr", work_row, work_beg, work_end, work_split, n_work, split_rows, n_split_rows, col, val, X,
+                     nullptr, 0, dim, S, stream);
+}
+
+int xdr_spmm_csr_sharded(const int64_t* work_row, const int64_t* work_beg, const int64_t* work_end, const uint8_t* work_split,
+                         int64_t n_work, const int64_t* split_rows, int64_t n_split_rows, const int64_t* col,
+                         const float* val, const float* const* x_shards, int n_shards, int dim, float* S,
+                         xdr_stream_t stream) {
+  XDR_REQUIRE(n_shards >= 1 && n_shards <= kMaxShards && (n_shards & (n_shards - 1)) == 0,
+              "xdr_spmm_csr_sharded: n_shards=%d must be a power of two <= %d", n_shards, kMaxShards);
+  XDR_REQUIRE(x_shards, "xdr_spmm_csr_sharded: null pointer");
+  Shards xs{};
+  int log2g = 0;
+  while ((1 << log2g) < n_shards) ++log2g;
+  for (int g = 0; g < n_shards; ++g) {
+    XDR_REQUIRE(x_shards[g] && aligned16(x_shards[g]), "xdr_spmm_csr_sharded: null or unaligned shard %d", g);
+    xs.p[g] = const_cast<float*>(x_shards[g]);
+  }
+  return spmm_launch("xdr_spmm_csr_sharded", work_row, work_beg, work_end, work_split, n_work, split_rows, n_split_rows, col,
+                     val, nullptr, &xs, log2g, dim, S, stream);
 }
 
 int xdr_prop_elementwise(const float* A, const float* B, const float* C, float* out, int64_t count, int mode,

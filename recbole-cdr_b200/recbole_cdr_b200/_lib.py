@@ -52,6 +52,7 @@ PROTOTYPES = {
     'xdr_neg_sample_uniform': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_uint64,
                                        ctypes.c_uint32, c_int, c_vp, c_vp, c_vp]),
     'xdr_spmm_csr': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
+    'xdr_spmm_csr_sharded': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
     'xdr_prop_elementwise': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp]),
     'xdr_transfer_norm_fwd': (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp,
                                       c_vp, c_vp, c_i64, c_vp]),

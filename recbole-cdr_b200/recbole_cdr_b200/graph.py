@@ -6,6 +6,22 @@ import torch
 from ._lib import call, cur_stream, ptr
 
 
+def norm_adj_coo(rows, cols, n_users, n_items):
+    """(row, col, value) of ``L = D^-1/2 A D^-1/2`` in CSR order (by row, then column) -- see ``NormAdj``."""
+    n = n_users + n_items
+    rows = np.asarray(rows, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64)
+    keys = np.unique(rows * np.int64(n_items) + cols)          # de-duplicated (user, item) pairs, sorted by (user, item)
+    eu, ei = keys // n_items, keys % n_items
+    r = np.concatenate([eu, ei + n_users])
+    c = np.concatenate([ei + n_users, eu])
+    deg = np.bincount(r, minlength=n).astype(np.float64) + 1e-7
+    dinv = np.power(deg, -0.5)
+    val = (dinv[r] * 1.0 * dinv[c]).astype(np.float32)
+    order = np.argsort(r * np.int64(n) + c, kind='stable')  # CSR order: by row, then column
+    return r[order], c[order], val[order]
+
+
 class NormAdj(object):
     """``L = D^-1/2 A D^-1/2`` of a bipartite interaction graph as CSR on the device + its work-item cut.
 
@@ -19,33 +35,28 @@ class NormAdj(object):
 
     def __init__(self, rows, cols, n_users, n_items, device, chunk=256):
         n = n_users + n_items
-        rows = np.asarray(rows, dtype=np.int64)
-        cols = np.asarray(cols, dtype=np.int64)
-        keys = np.unique(rows * np.int64(n_items) + cols)          # de-duplicated (user, item) pairs, sorted by (user, item)
-        eu, ei = keys // n_items, keys % n_items
-        r = np.concatenate([eu, ei + n_users])
-        c = np.concatenate([ei + n_users, eu])
-        deg = np.bincount(r, minlength=n).astype(np.float64) + 1e-7
-        dinv = np.power(deg, -0.5)
-        val = (dinv[r] * 1.0 * dinv[c]).astype(np.float32)
-        order = np.argsort(r * np.int64(n) + c, kind='stable')  # CSR order: by row, then column
-        r, c, val = r[order], c[order], val[order]
-        rowptr = np.zeros(n + 1, dtype=np.int64)
+        r, c, val = norm_adj_coo(rows, cols, n_users, n_items)
+        self.n, self.n_users, self.n_items = n, n_users, n_items
+        self.device = torch.device(device)
+        self._set_csr(r, c, val, n, chunk)
+
+    def _set_csr(self, r, c, val, n_rows, chunk):
+        """r (sorted), c, val: the nonzeros of the rows this object holds -> CSR + work-item cut on the device"""
+        rowptr = np.zeros(n_rows + 1, dtype=np.int64)
         np.add.at(rowptr, r + 1, 1)
         rowptr = np.cumsum(rowptr)
         # work items: every row is cut into pieces of <= chunk nonzeros (rows without nonzeros still get one empty item
         # so that their output row is written)
         counts = rowptr[1:] - rowptr[:-1]
         pieces = np.maximum(1, -(-counts // chunk))
-        work_row = np.repeat(np.arange(n, dtype=np.int64), pieces)
+        work_row = np.repeat(np.arange(n_rows, dtype=np.int64), pieces)
         first = np.cumsum(pieces) - pieces
         k = np.arange(work_row.size, dtype=np.int64) - np.repeat(first, pieces)
         work_beg = rowptr[work_row] + k * chunk
         work_end = np.minimum(work_beg + chunk, rowptr[work_row + 1])
         work_split = (pieces[work_row] > 1).astype(np.uint8)
         split_rows = np.nonzero(pieces > 1)[0].astype(np.int64)
-        self.n, self.n_users, self.n_items, self.nnz = n, n_users, n_items, int(val.size)
-        self.device = torch.device(device)
+        self.n_rows, self.nnz = n_rows, int(val.size)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
         self.rowptr, self.col, self.val = t(rowptr), t(c), t(val)
         self.work_row, self.work_beg, self.work_end, self.work_split = t(work_row), t(work_beg), t(work_end), t(work_split)

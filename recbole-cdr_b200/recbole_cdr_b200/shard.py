@@ -113,12 +113,31 @@ class RowShardedTable:
             self._ptr_array = (ctypes.c_void_p * self.world)(*self._ptrs)   # built once: the launches are host-bound
         return self._ptr_array
 
+    def rows_view(self, first_local_row: int, n_local_rows: int):
+        """Local rows [first, first + n) of every shard as a block-cyclic table of its own (``n * world`` global rows):
+        e.g. the user block and the item block of a node table."""
+        return _RowsView(self, first_local_row, n_local_rows)
+
     def close(self):
         for base in self._opened:
             call('xdr_ipc_close', base)
         self._opened = []
         self._ptrs = None
         self._ptr_array = None
+
+
+class _RowsView(object):
+    def __init__(self, table: RowShardedTable, first: int, n: int):
+        if first < 0 or n < 0 or first + n > table.local.shape[0]:
+            raise ValueError('rows_view outside the shard')
+        self.world, self.dim, self.rank = table.world, table.dim, table.rank
+        self.n_rows = n * table.world
+        self.local = table.local[first:first + n]
+        off = first * table.dim * 4
+        self._ptr_array = (ctypes.c_void_p * table.world)(*[p + off for p in table.pointer_array()])
+
+    def pointer_array(self):
+        return self._ptr_array
 
 
 _steps_ws = {}

@@ -94,6 +94,13 @@ from recbole_cdr_b200.trainer import GraphedTrainStep
 gs = GraphedTrainStep(m, Interaction({'overlap': ov}))
 report('A4 EMCDR map step fwd+bwd, CUDA-graph replay, b = 8192', timeit(lambda: gs(Interaction({'overlap': ov})), inner=10), bytes_=8192 * 1032, flops=8192 * 98304, units=8192, unit_name='inter')
 del m, gs
+with torch.device(dev):
+    m = EMCDR(dict(cfg, xdr_fused_mlp=True), ds)
+m.set_phase('OVERLAP')
+report('A4 EMCDR map step fwd+bwd, ONE fused kernel (xdr_fused_mlp), eager, b = 8192', timeit(map_step), bytes_=8192 * 1032, flops=8192 * 98304, units=8192, unit_name='inter')
+gs = GraphedTrainStep(m, Interaction({'overlap': ov}))
+report('A4 EMCDR map step fwd+bwd, ONE fused kernel, CUDA-graph replay, b = 8192', timeit(lambda: gs(Interaction({'overlap': ov})), inner=10), bytes_=8192 * 1032, flops=8192 * 98304, units=8192, unit_name='inter')
+del m, gs
 
 # ---- A14/A15: DTCDR NeuMF BOTH step, D = 64, B = 8192 per domain ------------------------------------------------------
 from recbole_cdr_b200.model.cross_domain_recommender.dtcdr import DTCDR
@@ -111,6 +118,12 @@ def dt_step():
 report('A14-15 DTCDR NeuMF BOTH step fwd+bwd (fused MLP kernels, eager launches), 2 x B=8192', timeit(dt_step), bytes_=2 * 8192 * 2068, flops=2 * 8192 * 27700, units=2 * 8192, unit_name='inter')
 gs = GraphedTrainStep(m, ib)
 report('A14-15 DTCDR NeuMF BOTH step fwd+bwd, CUDA-graph replay', timeit(lambda: gs(ib), inner=10), bytes_=2 * 8192 * 2068, flops=2 * 8192 * 27700, units=2 * 8192, unit_name='inter')
+del m, gs
+with torch.device(dev):
+    m = DTCDR(base_config(device=dev, embedding_size=64, mlp_hidden_size=[32, 16], dropout_prob=0.0, base_model='NeuMF', alpha=0.5, xdr_fused_mlp=True), dsb)
+report('A14-15 DTCDR NeuMF BOTH step fwd+bwd, fused kernel per domain (xdr_fused_mlp), eager', timeit(dt_step), bytes_=2 * 8192 * 2068, flops=2 * 8192 * 27700, units=2 * 8192, unit_name='inter')
+gs = GraphedTrainStep(m, ib)
+report('A14-15 DTCDR NeuMF BOTH step fwd+bwd, fused kernel per domain, CUDA-graph replay', timeit(lambda: gs(ib), inner=10), bytes_=2 * 8192 * 2068, flops=2 * 8192 * 27700, units=2 * 8192, unit_name='inter')
 del m, gs
 
 # ---- A7/A8: CoNet BOTH step at config #3 (5M users / 2M items per domain, 50% user overlap, D = 128, B = 16384) -------

@@ -67,3 +67,79 @@ def test_sharded_steps_match_single_gpu(world, staged, tmp_path):
     port = 29600 + (os.getpid() % 2000) + world + (10 if staged else 0)
     mp.spawn(_worker, args=(world, port, str(tmp_path), staged), nprocs=world, join=True)
     assert (tmp_path / 'ok').exists()
+
+
+# ---- E2: BiTGCF with row-sharded graph propagation ---------------------------------------------------------------------
+
+def _bitgcf_worker(rank, world, port, tmp, way):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    if world > 1:
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        import numpy as np
+        from fake_data import FakeDataset, base_config
+        from recbole_cdr_b200.shard_graph import ShardedBiTGCF
+        ds_args = (101, 90, 110, 31, 80, 92)                                  # overlapped users AND items, odd sizes
+        nu, ni, D, L, B = 301, 203, 16, 2, 512
+        rng = np.random.RandomState(5)
+        edges = {'source': (rng.randint(0, nu, 3000), np.minimum(rng.zipf(1.3, 3000) - 1, ni - 1)),   # one hub item > 256 nnz
+                 'target': (rng.randint(0, nu, 2500), rng.randint(0, ni, 2500))}
+        g = torch.Generator().manual_seed(11)
+        ego = [torch.randn(n, D, generator=g) * 0.3 for n in (nu, ni, nu, ni)]   # source_user, source_item, target_user, target_item
+        bu = torch.randint(0, nu, (world, 2, B), generator=g)
+        bi = torch.randint(0, ni, (world, 2, B), generator=g)
+        by = (torch.rand(world, 2, B, generator=g) < 0.5).float()
+        eng = ShardedBiTGCF(edges['source'], edges['target'], nu, ni, ds_args[0], ds_args[3], dim=D, n_layers=L,
+                            lambda_source=0.8, lambda_target=0.7, connect_way=way, reg_weight=0.01, rank=rank, world=world,
+                            device=dev, ego=[t.to(dev) for t in ego])
+        mine = [(bu[rank, d].to(dev), bi[rank, d].to(dev), by[rank, d].to(dev)) for d in range(2)]
+        for _ in range(2):                    # twice: the second pass re-uses every exchange buffer
+            eng.ego_s.local.grad = eng.ego_t.local.grad = None
+            loss_s, loss_t = eng.train_step(*mine)
+        grads = eng.full_tables('grad')
+        tabs = eng.full_tables('ego')
+        all_losses = [torch.cat([loss_s, loss_t])] if world == 1 else [torch.empty(2, device=dev) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(all_losses, torch.cat([loss_s, loss_t]))
+        if rank == 0:
+            from recbole_cdr_b200.data.interaction import Interaction
+            from recbole_cdr_b200.model.cross_domain_recommender.bitgcf import BiTGCF
+            m = BiTGCF(base_config(device=dev, embedding_size=D, n_layers=L, reg_weight=0.01, lambda_source=0.8, lambda_target=0.7,
+                                   drop_rate=0.0, connect_way=way), FakeDataset(*ds_args, edges=edges)).to(dev)
+            names = ('source_user_embedding', 'source_item_embedding', 'target_user_embedding', 'target_item_embedding')
+            with torch.no_grad():
+                for n, t, back in zip(names, ego, tabs):
+                    getattr(m, n).weight.copy_(t)
+                    assert torch.equal(back, t.to(dev))                      # shard -> full round trip is bit-exact
+            for r in range(world):
+                ls, lt = m.calculate_loss(Interaction({
+                    'source_user_id': bu[r, 0].to(dev), 'source_item_id': bi[r, 0].to(dev), 'source_label': by[r, 0].to(dev),
+                    'target_user_id': bu[r, 1].to(dev), 'target_item_id': bi[r, 1].to(dev), 'target_label': by[r, 1].to(dev)}))
+                # fp32 loss within 1e-4 relative (north_star); observed ~1e-6
+                torch.testing.assert_close(all_losses[r], torch.cat([ls, lt]).detach(), rtol=1e-4, atol=0)
+                ((ls + lt) / world).sum().backward()
+            for n, got in zip(names, grads):
+                want = getattr(m, n).weight.grad
+                torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4 * want.abs().max().item())
+            open(os.path.join(tmp, 'ok'), 'w').write('ok')
+        if world > 1:
+            dist.barrier()
+        eng.close()
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('way', ['concat', 'mean'])
+@pytest.mark.parametrize('world', [1, 2, 4])
+def test_sharded_bitgcf_step_matches_single_gpu(world, way, tmp_path):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
+    port = 31700 + (os.getpid() % 2000) + world + (20 if way == 'mean' else 0)
+    if world == 1:      # the same engine, one shard, no process group: runs on the single-GPU box too
+        _bitgcf_worker(0, 1, port, str(tmp_path), way)
+    else:
+        mp.spawn(_bitgcf_worker, args=(world, port, str(tmp_path), way), nprocs=world, join=True)
+    assert (tmp_path / 'ok').exists()

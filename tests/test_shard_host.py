@@ -60,3 +60,37 @@ def test_shard_round_trip_gloo_world2(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f'ok{r}').exists() for r in range(world))
+
+
+@pytest.mark.parametrize('world', [1, 2, 4, 8])
+def test_sharded_norm_adj_rows_partition_the_full_matrix(world):
+    """SURVEY 8 E2 host logic: every rank's CSR rows are the full L's rows (same values, same per-row order, padded
+    column ids), padding rows are empty, the nonzeros partition exactly, and the overlapped nodes are a local prefix."""
+    import numpy as np
+    from recbole_cdr_b200.graph import NormAdj
+    from recbole_cdr_b200.shard_graph import NodeShards, ShardedNormAdj
+    rng = np.random.RandomState(0)
+    nu, ni, ovu, ovi = 37, 23, 11, 5
+    r, c = rng.randint(0, nu, 300), rng.randint(0, ni, 300)
+    full = NormAdj(r, c, nu, ni, 'cpu', chunk=4)
+    seen = 0
+    for rank in range(world):
+        nd = NodeShards(nu, ni, ovu, ovi, rank, world)
+        a = ShardedNormAdj(r, c, nd, 'cpu', chunk=4)
+        nodes = nd.local_nodes()
+        assert nodes.size == nd.rows == a.n_rows
+        for l, v in enumerate(nodes):
+            b, e = a.rowptr[l].item(), a.rowptr[l + 1].item()
+            if v < 0:
+                assert b == e
+                continue
+            fb, fe = full.rowptr[v].item(), full.rowptr[v + 1].item()
+            assert torch.equal(a.val[b:e], full.val[fb:fe])
+            assert np.array_equal(a.col[b:e].numpy(), nd.pad(full.col[fb:fe].numpy()))
+            seen += e - b
+        assert all((0 <= v < ovu) == (l < nd.ov_users) for l, v in enumerate(nodes[:nd.ru]))
+        assert all((v >= 0 and v - nu < ovi) == (l < nd.ov_items) for l, v in enumerate(nodes[nd.ru:]))
+        # work items cover every local row's nonzeros exactly once, in pieces of <= chunk
+        covered = (a.work_end - a.work_beg).sum().item()
+        assert covered == a.nnz and (a.work_end - a.work_beg).max().item() <= 4
+    assert seen == full.nnz

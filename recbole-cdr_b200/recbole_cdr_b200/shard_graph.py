@@ -8,11 +8,18 @@ embedding tables of ``shard.py``: padded node ``v`` lives on rank ``v % G`` at l
 they form a PREFIX of every rank's local user (item) block, so ``transfer_layer`` + ``F.normalize`` and the layer
 combine stay row-local and run through the unchanged single-GPU kernels with local counts.
 
-Only the sparse matmul needs remote rows: every rank holds the CSR rows of ``L`` it owns (global column ids) and
-``xdr_spmm_csr_sharded`` gathers the neighbour rows straight from the peers' exchange buffers over NVLink (CUDA-IPC
-mapped) -- one exchange per layer and direction, no all-gather of the embedding table.  ``L`` is symmetric, so the
-backward pass is the same launch on the gradient.  A tiny NCCL all-reduce on the stream orders "owner wrote its shard"
-before "peers read it" (and the reverse before the buffer is reused).
+Only the sparse matmul needs remote rows: every rank holds the CSR rows of ``L`` it owns (global column ids); ``L`` is
+symmetric, so the backward pass is the same launch on the gradient.  One exchange per layer and direction, two forms:
+
+  exchange='allgather' (default)  the operand shards are all-gathered (NCCL, large coalesced NVLink messages; the target
+                                  domain's gather overlaps the source domain's SpMM) into a local ``[G, rows, D]`` replica
+                                  and ``xdr_spmm_csr_sharded`` reads it with the shard addressing.  With ~14 nonzeros per
+                                  row nearly every row is needed by every rank, so moving each row once beats fetching it
+                                  per nonzero.
+  exchange='peer'                 ``xdr_spmm_csr_sharded`` gathers the neighbour rows straight from the peers' exchange
+                                  buffers (CUDA-IPC mapped) -- no replica memory, but random 256-byte NVLink reads
+                                  (~300 GB/s per GPU measured); a tiny all-reduce on the stream orders "owner wrote its
+                                  shard" before "peers read it" (and the reverse before the buffer is reused).
 
 The batch is data-parallel: the gathers from the propagated tables, sigmoid(dot) + BCE and the EmbLoss on the ego rows
 (bitgcf.py:207-250) are one ``xdr_train_steps_sharded`` launch per domain and term, whose gradient rows land in the
@@ -82,6 +89,20 @@ class ShardedNormAdj(NormAdj):
         return S
 
 
+class _Replica(object):
+    """a local ``[G, rows, D]`` all-gathered copy of a row-sharded operand, addressed like the shards themselves"""
+
+    def __init__(self, world, rows, dim, device):
+        import ctypes
+        self.world, self.dim = world, dim
+        self.buf = torch.empty((world, rows, dim), dtype=torch.float32, device=device)
+        self.local = self.buf[0]
+        self._ptrs = (ctypes.c_void_p * world)(*[self.buf[g].data_ptr() for g in range(world)])
+
+    def pointer_array(self):
+        return self._ptrs
+
+
 class _ShardedProp(torch.autograd.Function):
     """``graph_layer`` of both domains (bitgcf.py:130-135, drop_rate 0) on the local rows; see ``graph.GraphProp``."""
 
@@ -108,7 +129,10 @@ class ShardedBiTGCF(object):
     target_item) to take the local rows from (tests / checkpoints), else xavier-normal like the reference."""
 
     def __init__(self, src_edges, tgt_edges, n_users, n_items, n_ov_users, n_ov_items, *, dim, n_layers, lambda_source,
-                 lambda_target, connect_way, reg_weight, rank, world, device, ego=None, group=None):
+                 lambda_target, connect_way, reg_weight, rank, world, device, ego=None, group=None, exchange='allgather'):
+        if exchange not in ('allgather', 'peer'):
+            raise ValueError("exchange must be 'allgather' or 'peer'")
+        self.exchange = exchange if world > 1 else 'peer'
         self.rank, self.world, self.device, self.group = rank, world, torch.device(device), group
         self.dim, self.n_layers, self.connect_way, self.reg_weight = dim, n_layers, connect_way, reg_weight
         self.lam_s, self.lam_t = float(lambda_source), float(lambda_target)
@@ -128,7 +152,12 @@ class ShardedBiTGCF(object):
         table = lambda d: RowShardedTable(nd.n_padded, d, rank, world, self.device)
         self.ego_s, self.ego_t = table(dim), table(dim)                # the embeddings (users then items)
         self.ego_grad_s, self.ego_grad_t = table(dim), table(dim)      # EmbLoss gradient rows arrive here by peer RED
-        self.x_s, self.x_t = table(dim), table(dim)                    # SpMM operand exchange buffers
+        if self.exchange == 'peer':
+            self.x_s, self.x_t = table(dim), table(dim)                # SpMM operand exchange buffers (peer-mapped)
+            xbufs = [self.x_s, self.x_t]
+        else:
+            self.x_s, self.x_t = _Replica(world, nd.rows, dim, self.device), _Replica(world, nd.rows, dim, self.device)
+            xbufs = []
         self.fin_s, self.fin_t = table(self.out_dim), table(self.out_dim)            # propagated tables
         self.fin_grad_s, self.fin_grad_t = table(self.out_dim), table(self.out_dim)  # their gradient
         if ego is not None:
@@ -140,8 +169,8 @@ class ShardedBiTGCF(object):
             for t in (self.ego_s, self.ego_t):
                 t.local.normal_(0.0, std)
                 t.local[torch.from_numpy(nd.local_nodes() < 0).to(self.device)] = 0
-        self._tables = [self.ego_s, self.ego_t, self.ego_grad_s, self.ego_grad_t, self.x_s, self.x_t, self.fin_s, self.fin_t,
-                        self.fin_grad_s, self.fin_grad_t]
+        self._tables = [self.ego_s, self.ego_t, self.ego_grad_s, self.ego_grad_t, self.fin_s, self.fin_t, self.fin_grad_s,
+                        self.fin_grad_t] + xbufs
         for t in self._tables:
             t.connect(group)
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -155,6 +184,13 @@ class ShardedBiTGCF(object):
             dist.all_reduce(self._flag, group=self.group)
 
     def spmm_pair(self, Xs, Xt):
+        if self.exchange == 'allgather':
+            hs = dist.all_gather_into_tensor(self.x_s.buf, Xs.detach(), group=self.group, async_op=True)
+            ht = dist.all_gather_into_tensor(self.x_t.buf, Xt.detach(), group=self.group, async_op=True)
+            hs.wait()
+            Ss = self.adj_s.spmm_sharded(self.x_s)
+            ht.wait()                      # the target domain's gather ran under the source domain's SpMM
+            return Ss, self.adj_t.spmm_sharded(self.x_t)
         self.fence()                       # the peers have finished reading the previous operands
         with torch.no_grad():
             self.x_s.local.copy_(Xs)

@@ -71,7 +71,7 @@ def test_sharded_steps_match_single_gpu(world, staged, tmp_path):
 
 # ---- E2: BiTGCF with row-sharded graph propagation ---------------------------------------------------------------------
 
-def _bitgcf_worker(rank, world, port, tmp, way):
+def _bitgcf_worker(rank, world, port, tmp, way, exchange='peer'):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device('cuda', rank)
@@ -93,7 +93,7 @@ def _bitgcf_worker(rank, world, port, tmp, way):
         by = (torch.rand(world, 2, B, generator=g) < 0.5).float()
         eng = ShardedBiTGCF(edges['source'], edges['target'], nu, ni, ds_args[0], ds_args[3], dim=D, n_layers=L,
                             lambda_source=0.8, lambda_target=0.7, connect_way=way, reg_weight=0.01, rank=rank, world=world,
-                            device=dev, ego=[t.to(dev) for t in ego])
+                            device=dev, ego=[t.to(dev) for t in ego], exchange=exchange)
         mine = [(bu[rank, d].to(dev), bi[rank, d].to(dev), by[rank, d].to(dev)) for d in range(2)]
         for _ in range(2):                    # twice: the second pass re-uses every exchange buffer
             eng.ego_s.local.grad = eng.ego_t.local.grad = None
@@ -132,14 +132,17 @@ def _bitgcf_worker(rank, world, port, tmp, way):
             dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('exchange', ['allgather', 'peer'])
 @pytest.mark.parametrize('way', ['concat', 'mean'])
 @pytest.mark.parametrize('world', [1, 2, 4])
-def test_sharded_bitgcf_step_matches_single_gpu(world, way, tmp_path):
+def test_sharded_bitgcf_step_matches_single_gpu(world, way, exchange, tmp_path):
     if torch.cuda.device_count() < world:
         pytest.skip(f'needs {world} GPUs')
-    port = 31700 + (os.getpid() % 2000) + world + (20 if way == 'mean' else 0)
+    port = 31700 + (os.getpid() % 2000) + world + (20 if way == 'mean' else 0) + (40 if exchange == 'peer' else 0)
     if world == 1:      # the same engine, one shard, no process group: runs on the single-GPU box too
+        if exchange == 'allgather':
+            pytest.skip('one shard: nothing to exchange')
         _bitgcf_worker(0, 1, port, str(tmp_path), way)
     else:
-        mp.spawn(_bitgcf_worker, args=(world, port, str(tmp_path), way), nprocs=world, join=True)
+        mp.spawn(_bitgcf_worker, args=(world, port, str(tmp_path), way, exchange), nprocs=world, join=True)
     assert (tmp_path / 'ok').exists()

@@ -176,6 +176,21 @@ XDR_API int xdr_fused_mlp_step(int n_layers, const int* dims_host, const float* 
                                float* dAu, float* dBu, float* dAi, float* dBi, float* dT, float* prob, float* out8,
                                void* ws, int32_t* oob, xdr_stream_t stream);
 
+/* ---- A4 / A14-A15 fused, tensor-core engine ---------------------------------------------------------------------------------
+ * Same contract, arguments and results as xdr_fused_mlp_step (EMCDR.calculate_map_loss emcdr.py:156-168; one DTCDR NeuMF
+ * term dtcdr.py:112-125,186-187), but every layer product of a 64- or 32-row tile (X W^T, dZ W, dZ^T X) is a 3xTF32
+ * mma.sync tile product with fp32 accumulation (agrees with fp32 FMA to ~1e-6 relative).  Restrictions on top of the
+ * fp32 engine: every layer input width % 8 == 0, hidden widths % 8 == 0 (a final width < 8, i.e. the NeuMF output unit,
+ * runs on the CUDA cores), at most 64 / 64 / 8 weight-gradient 16x8 tiles in layers 0 / 1 / 2.                           */
+XDR_API int xdr_tc_mlp_supported(int n_layers, const int* dims_host);
+XDR_API int xdr_tc_mlp_step(int n_layers, const int* dims_host, const float* const* W_host, const float* const* b_host,
+                            float* const* dW_host, float* const* db_host, int hidden_act, int in_mode, int head,
+                            const float* Au, const float* Bu, const float* Ai, const float* Bi, const float* T,
+                            int64_t n_u, int64_t n_i, int dim, const int64_t* idx_u, const int64_t* idx_i,
+                            const float* label, int64_t batch, int backward, const float* grad_loss, float scale,
+                            float* dAu, float* dBu, float* dAi, float* dBi, float* dT, float* prob, float* out8,
+                            void* ws, int32_t* oob, xdr_stream_t stream);
+
 /* ---- A6: EMCDR predict tail: select mapped vs. target row, then dot ------------------------------------------
  * Replaces the torch.where + mul + sum of EMCDR.predict, OVERLAP/BOTH phase (emcdr.py:191-205):
  *   e = (sel_ids[b] < n_overlap) ? mapped[b, :] : tgt_tab[sel_ids[b], :];   score[b] = e . other_tab[other_ids[b], :]

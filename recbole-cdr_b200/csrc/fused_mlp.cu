@@ -17,42 +17,12 @@
 // chains (2 LDS per FMA) is latency-bound on its own inner loops.  It needs 4x4 register tiles and 512+ threads; until
 // then the models use it only on request (config key `xdr_fused_mlp: True`).
 #include "xdr_common.cuh"
+#include "mlp_args.cuh"
 
 namespace xdr {
 
 constexpr int kMlpThreads = 256;
 constexpr int kMaxTileRows = 32;  // batch rows per tile: 32, or 16 / 8 when the weights leave less shared memory
-constexpr int kMaxLayers = 3;
-
-struct MlpArgs {
-  int n_layers;           // 1..3 Linear layers
-  int dims[kMaxLayers + 1];
-  const float* W[kMaxLayers];   // [dims[l+1], dims[l]]  (nn.Linear.weight layout)
-  const float* b[kMaxLayers];   // [dims[l+1]] or NULL
-  float* dW[kMaxLayers];        // accumulated (+=) when backward
-  float* db[kMaxLayers];
-  int hidden_act;         // activation after every layer but the last
-  int last_act;           // activation after the last layer (XDR_ACT_NONE for both users)
-  int in_mode;            // 0: x = A_u[idx_u]                       (d0 = dim)
-                          // 1: x = [max(A_u[u], B_u[u]) | max(A_i[i], B_i[i])]   (d0 = 2*dim)
-  int head;               // 0: MSE against T[idx_u] (d_last = dim)   1: sigmoid + BCE with labels (d_last = 1)
-  const float *Au, *Bu, *Ai, *Bi, *T;
-  int64_t n_u, n_i;
-  int dim;
-  const int64_t* idx_u;
-  const int64_t* idx_i;
-  const float* label;
-  int64_t batch;
-  int tile_rows;          // rows per tile (<= kMaxTileRows)
-  int backward;           // 0: forward only (loss [+ prob]); 1: forward + backward + scatter
-  const float* grad_loss; // device scalar (NULL => 1)
-  float scale;
-  float *dAu, *dBu, *dAi, *dBi, *dT;  // scatter-add destinations (backward)
-  float* prob;            // optional [batch] sigmoid output (head 1)
-  float* out8;
-  int32_t* oob;
-};
-
 // Activations and their gradients are kept TRANSPOSED in shared memory: actT[l][k * LD + r] with LD = tile_rows + 4, so the
 // values of four consecutive batch rows at one feature are a single 16-byte LDS (the +4 pad keeps consecutive features on
 // different banks).  Every inner loop then does 2 LDS per 4 FMAs with four independent accumulators.
@@ -92,7 +62,7 @@ __device__ __forceinline__ void mlp_flush_dw(const float (&acc)[CAP], float* dW,
 // E0/E1/E2: upper bounds on weight elements per thread of layers 0/1/2 (ceil(dout*din / 256))
 template <int E0, int E1, int E2>
 __global__ void __launch_bounds__(kMlpThreads, 1) fused_mlp_kernel(MlpArgs a, Workspace ws) {
-  extern __shared__ __align__(16) float smem[];
+  XDR_DYN_SMEM(float, smem);
   __shared__ float red_smem[8];
   const int tid = threadIdx.x;
   const int nl = a.n_layers;
@@ -355,6 +325,7 @@ static bool pick_tile_rows(MlpArgs* a) {
   return false;
 }
 
+#ifndef XDR_EMU
 template <int E0, int E1, int E2>
 static int launch_mlp(const MlpArgs& a, void* ws, cudaStream_t s) {
   const int kTileRows = a.tile_rows;
@@ -368,8 +339,11 @@ static int launch_mlp(const MlpArgs& a, void* ws, cudaStream_t s) {
   return XDR_OK;
 }
 
+#endif  // !XDR_EMU
+
 }  // namespace xdr
 
+#ifndef XDR_EMU
 using namespace xdr;
 
 extern "C" {
@@ -438,3 +412,4 @@ int xdr_fused_mlp_step(int n_layers, const int* dims_host, const float* const* W
 }
 
 }  // extern "C"
+#endif  // !XDR_EMU

@@ -1,0 +1,202 @@
+// tc_tile.cuh -- tensor-core building blocks for row-tile kernels whose operands live in shared memory as plain fp32.
+//
+// Every product is computed as 3xTF32: x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and
+//     a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi          (the dropped a_lo*b_lo term is ~2^-22 relative)
+// accumulated in fp32 by mma.sync.m16n8k8 (SASS HMMA.1688.F32.TF32), so the results agree with the fp32 FMA reference
+// to ~1e-6 relative -- inside the 1e-4 parity bar of the dense rows with a wide margin, which a single
+// TF32 pass (~5e-4 per product) would not give for the gradients.
+//
+// Fragment ownership of mma.m16n8k8 (g = lane >> 2, t = lane & 3):
+//     A (16x8, row):  a0 = (g, t)   a1 = (g+8, t)   a2 = (g, t+4)   a3 = (g+8, t+4)
+//     B (8x8,  col):  b0 = (k = t, n = g)           b1 = (k = t+4, n = g)
+//     C (16x8):       c0 = (g, 2t)  c1 = (g, 2t+1)  c2 = (g+8, 2t)  c3 = (g+8, 2t+1)
+// Shared-memory operands are row-major with a leading dimension ld = width + 4 (ld / 4 odd), so the (g*ld + t) access
+// of an untransposed operand touches 32 distinct banks; transposed operands ((t*ld + g)) see 2-way conflicts.
+#pragma once
+#include "xdr_common.cuh"
+
+namespace xdr {
+
+#if defined(__CUDACC__) || defined(XDR_EMU)
+
+constexpr int kTcThreads = 256;
+constexpr int kTcWarps = kTcThreads / 32;
+
+__device__ __forceinline__ uint32_t cvt_tf32(float x) {
+#ifdef XDR_EMU
+  return emu::to_tf32(x);
+#else
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+#endif
+}
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_tf32(x);
+  lo = cvt_tf32(x - __uint_as_float(hi));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+#ifdef XDR_EMU
+  emu::mma_m16n8k8_tf32(c, a, b);
+#else
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+#endif
+}
+
+// c += a * b in 3xTF32 (small terms first)
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+  mma_tf32(c, al, bh);
+  mma_tf32(c, ah, bl);
+  mma_tf32(c, ah, bh);
+}
+
+__device__ __forceinline__ float act_apply(float y, int act) {
+  if (act == XDR_ACT_RELU) return y > 0.f ? y : 0.f;
+  if (act == XDR_ACT_TANH) return tanhf(y);
+  if (act == XDR_ACT_SIGMOID) return sigmoidf_(y);
+  return y;
+}
+// derivative of the activation expressed through its OUTPUT y
+__device__ __forceinline__ float act_grad(float y, int act) {
+  if (act == XDR_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == XDR_ACT_TANH) return 1.f - y * y;
+  if (act == XDR_ACT_SIGMOID) return (1.f - y) * y;
+  return 1.f;
+}
+
+// C[TR x N] = A[TR x K] * B for one CTA of kTcWarps warps; A row-major in shared memory (element (m, k) at A[m*lda + k]).
+//   BT == false:  B(k, n) = Bsm[n*ldb + k]   (nn.Linear.weight [N][K]:  C = A W^T, the forward of a layer)
+//   BT == true :  B(k, n) = Bsm[k*ldb + n]   (C = A W with W [K][N]:     the input gradient dX = dZ W)
+// Warp w owns the 16-row tile (w % MT) and the 8-column tiles (w / MT) + j*G, j < MAXNT (MT = TR/16, G = kTcWarps/MT).
+// epi(row, col, v0, v1) receives C[row][col], C[row][col+1] (col even).  N % 8 == 0, K % 8 == 0, N <= 8*G*MAXNT.
+template <int TR, int MAXNT, bool BT, typename Epi>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, const float* __restrict__ Bsm, int ldb, int N,
+                                          int K, Epi epi) {
+  constexpr int MT = TR / 16, G = kTcWarps / MT;
+  static_assert(TR % 16 == 0 && kTcWarps % MT == 0, "row tile must split into whole 16-row MMA tiles over the warps");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = (warp % MT) * 16, grp = warp / MT;
+  const int ntiles = N >> 3;
+  float acc[MAXNT][4];
+#pragma unroll
+  for (int j = 0; j < MAXNT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  if (grp < ntiles) {
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      uint32_t ah[4], al[4];
+      const float* ap = A + (m0 + g) * lda + k0 + t;
+      split_tf32(ap[0], ah[0], al[0]);
+      split_tf32(ap[8 * lda], ah[1], al[1]);
+      split_tf32(ap[4], ah[2], al[2]);
+      split_tf32(ap[8 * lda + 4], ah[3], al[3]);
+#pragma unroll
+      for (int j = 0; j < MAXNT; ++j) {
+        const int nt = grp + j * G;
+        if (nt < ntiles) {  // warp-uniform
+          const int n = nt * 8 + g;
+          float b0, b1;
+          if (!BT) {
+            const float* bp = Bsm + n * ldb + k0 + t;
+            b0 = bp[0];
+            b1 = bp[4];
+          } else {
+            const float* bp = Bsm + (k0 + t) * ldb + n;
+            b0 = bp[0];
+            b1 = bp[4 * ldb];
+          }
+          uint32_t bh[2], bl[2];
+          split_tf32(b0, bh[0], bl[0]);
+          split_tf32(b1, bh[1], bl[1]);
+          mma_3xtf32(acc[j], ah, al, bh, bl);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAXNT; ++j) {
+    const int nt = grp + j * G;
+    if (nt < ntiles) {
+      const int col = nt * 8 + 2 * t;
+      epi(m0 + g, col, acc[j][0], acc[j][1]);
+      epi(m0 + g + 8, col, acc[j][2], acc[j][3]);
+    }
+  }
+}
+
+// Picks the smallest MAXNT instantiation that covers N output columns.
+template <int TR, bool BT, typename Epi>
+__device__ __forceinline__ void tile_gemm_any(const float* A, int lda, const float* Bsm, int ldb, int N, int K, Epi epi) {
+  constexpr int G = kTcWarps / (TR / 16);
+  const int per_warp = ((N >> 3) + G - 1) / G;
+  if (per_warp <= 1) tile_gemm<TR, 1, BT>(A, lda, Bsm, ldb, N, K, epi);
+  else if (per_warp <= 2) tile_gemm<TR, 2, BT>(A, lda, Bsm, ldb, N, K, epi);
+  else if (per_warp <= 4) tile_gemm<TR, 4, BT>(A, lda, Bsm, ldb, N, K, epi);
+  else if (per_warp <= 8) tile_gemm<TR, 8, BT>(A, lda, Bsm, ldb, N, K, epi);
+  else tile_gemm<TR, 16, BT>(A, lda, Bsm, ldb, N, K, epi);
+}
+
+// Number of 16x8 tiles of a [dout][din] weight gradient and how many of them each warp owns (tile i -> warp i % kTcWarps).
+__host__ __device__ inline int dw_tiles(int dout, int din) { return ((dout + 15) >> 4) * (din >> 3); }
+__host__ __device__ inline int dw_tiles_per_warp(int dout, int din) { return (dw_tiles(dout, din) + kTcWarps - 1) / kTcWarps; }
+
+// acc += dZ^T X restricted to the tiles this warp owns:  dW[n][k] += sum_r dZ[r][n] * X[r][k],  r < TR.
+// dZ [TR][ldz] (dout columns), X [TR][ldx] (din columns), both row-major in shared memory.  The accumulators are MMA C
+// fragments that live in registers across all row tiles of the CTA; dw_flush() adds them to global memory once.
+template <int TR, int MAXT>
+__device__ __forceinline__ void dw_accum(float (&acc)[MAXT][4], const float* __restrict__ dZ, int ldz,
+                                         const float* __restrict__ X, int ldx, int dout, int din) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int ktiles = din >> 3, total = dw_tiles(dout, din);
+#pragma unroll
+  for (int j = 0; j < MAXT; ++j) {
+    const int tile = warp + j * kTcWarps;
+    if (tile < total) {  // warp-uniform
+      const int n0 = (tile / ktiles) * 16, k0 = (tile % ktiles) * 8;
+      const bool lo_ok = n0 + g < dout, hi_ok = n0 + g + 8 < dout;
+#pragma unroll 2
+      for (int r0 = 0; r0 < TR; r0 += 8) {
+        const float* zp = dZ + (r0 + t) * ldz + n0 + g;
+        uint32_t ah[4], al[4], bh[2], bl[2];
+        split_tf32(lo_ok ? zp[0] : 0.f, ah[0], al[0]);
+        split_tf32(hi_ok ? zp[8] : 0.f, ah[1], al[1]);
+        split_tf32(lo_ok ? zp[4 * ldz] : 0.f, ah[2], al[2]);
+        split_tf32(hi_ok ? zp[4 * ldz + 8] : 0.f, ah[3], al[3]);
+        const float* xp = X + (r0 + t) * ldx + k0 + g;
+        split_tf32(xp[0], bh[0], bl[0]);
+        split_tf32(xp[4 * ldx], bh[1], bl[1]);
+        mma_3xtf32(acc[j], ah, al, bh, bl);
+      }
+    }
+  }
+}
+
+template <int MAXT>
+__device__ __forceinline__ void dw_flush(const float (&acc)[MAXT][4], float* __restrict__ dW, int dout, int din) {
+  if (dW == nullptr) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int ktiles = din >> 3, total = dw_tiles(dout, din);
+#pragma unroll
+  for (int j = 0; j < MAXT; ++j) {
+    const int tile = warp + j * kTcWarps;
+    if (tile < total) {
+      const int n0 = (tile / ktiles) * 16, k = (tile % ktiles) * 8 + 2 * t;
+      if (n0 + g < dout) {
+        atomicAdd(&dW[(size_t)(n0 + g) * din + k], acc[j][0]);
+        atomicAdd(&dW[(size_t)(n0 + g) * din + k + 1], acc[j][1]);
+      }
+      if (n0 + g + 8 < dout) {
+        atomicAdd(&dW[(size_t)(n0 + g + 8) * din + k], acc[j][2]);
+        atomicAdd(&dW[(size_t)(n0 + g + 8) * din + k + 1], acc[j][3]);
+      }
+    }
+  }
+}
+
+#endif  // __CUDACC__ || XDR_EMU
+
+}  // namespace xdr

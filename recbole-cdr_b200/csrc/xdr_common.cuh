@@ -1,6 +1,10 @@
 // xdr_common.cuh -- device/host helpers shared by every kernel file of libxdr (sm_100a only).
 #pragma once
+#ifdef XDR_EMU
+#include "cuda_emu.h"  // tests/emu: CPU CTA emulator, test infrastructure only (never part of libxdr.so)
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include "../../include/xdr.h"
@@ -59,7 +63,7 @@ struct Workspace {
 // ---------------------------------------------------------------------------------------------------
 // device side
 // ---------------------------------------------------------------------------------------------------
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(XDR_EMU)
 
 constexpr int kMaxShards = 8;
 
@@ -82,11 +86,15 @@ constexpr int kRowsPerWarp = 32 / kLanesPerRow;
 
 // 128-bit read-only gather that does not allocate in L1 (rows are touched once per kernel).
 __device__ __forceinline__ float4 ldg_row4(const float* __restrict__ row, int col4) {
+#ifdef XDR_EMU
+  return *(reinterpret_cast<const float4*>(row) + col4);
+#else
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(reinterpret_cast<const float4*>(row) + col4));
   return v;
+#endif
 }
 
 // 128-bit coherent load (tables that may be written by a concurrent scatter in the same launch).
@@ -96,9 +104,14 @@ __device__ __forceinline__ float4 ld_row4(const float* row, int col4) {
 
 // fp32 x4 reduction to global memory: REDG.E.ADD.F32x4 on sm_100a.
 __device__ __forceinline__ void red_add4(float* row, int col4, float4 v) {
+#ifdef XDR_EMU
+  float* q = row + 4 * col4;
+  q[0] += v.x; q[1] += v.y; q[2] += v.z; q[3] += v.w;
+#else
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<float4*>(row) + col4), "f"(v.x),
                "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
+#endif
 }
 
 __device__ __forceinline__ void st4(float* row, int col4, float4 v) {
@@ -205,7 +218,14 @@ __device__ __forceinline__ void grid_reduce_last_block(float (&v)[NV], Workspace
   }
 }
 
-#endif  // __CUDACC__
+#endif  // __CUDACC__ || XDR_EMU
+
+// Dynamic shared memory of the CTA as `type* name` (CUDA: the extern __shared__ array; emulator: the CTA's heap block).
+#ifdef XDR_EMU
+#define XDR_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dyn_smem())
+#else
+#define XDR_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#endif
 
 // Instantiate CALL with `constexpr int VEC` = float4 columns per lane for a row of nv float4s (8 lanes per row).
 #define XDR_DISPATCH_VEC(nv, CALL)                                   \

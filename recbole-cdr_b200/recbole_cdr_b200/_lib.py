@@ -62,6 +62,10 @@ PROTOTYPES = {
     'xdr_fused_mlp_step': (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                    c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp,
                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'xdr_tc_mlp_supported': (c_int, [c_int, c_vp]),
+    'xdr_tc_mlp_step': (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp,
+                                c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'xdr_select_dot': (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
 }
 

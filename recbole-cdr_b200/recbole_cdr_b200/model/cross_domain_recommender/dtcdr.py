@@ -46,7 +46,9 @@ class DTCDR(CrossDomainRecommender):
         self.target_predict_layer = nn.Linear(self.mlp_hidden_size[-1], 1)
 
         self.apply(xavier_normal_initialization)
-        self.use_fused_mlp = config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else False
+        # False: composed kernels; True / 'fma': fp32 row-tile kernel; 'tc': tensor-core row-tile kernel
+        self.fused_mlp_engine = ops.fused_mlp_engine(config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else False)
+        self.use_fused_mlp = self.fused_mlp_engine is not None
 
     def _tower(self, domain):
         mlp = self.source_mlp_layers if domain == 'source' else self.target_mlp_layers
@@ -57,7 +59,7 @@ class DTCDR(CrossDomainRecommender):
     def _fused_ok(self):
         dims = [2 * self.embedding_size] + self.mlp_hidden_size + [1]
         no_dropout = self.dropout_prob == 0 or not self.training
-        return self.use_fused_mlp and no_dropout and ops.fused_mlp_supported(dims)
+        return self.use_fused_mlp and no_dropout and ops.fused_mlp_supported(dims, self.fused_mlp_engine)
 
     def _tables(self):
         return (self.source_user_embedding.weight, self.target_user_embedding.weight, self.source_item_embedding.weight,
@@ -81,10 +83,10 @@ class DTCDR(CrossDomainRecommender):
             # per domain: ONE kernel forward and ONE backward (gather + max-combine + MLP + BCE + scatter)
             ws, bs = self._tower('source')
             loss_s = ops.fused_mlp_loss(1, 1, _lib.ACT_RELU, interaction[self.SOURCE_USER_ID], interaction[self.SOURCE_ITEM_ID],
-                                        interaction[self.SOURCE_LABEL], self._tables(), ws, bs)
+                                        interaction[self.SOURCE_LABEL], self._tables(), ws, bs, self.fused_mlp_engine)
             wt, bt = self._tower('target')
             loss_t = ops.fused_mlp_loss(1, 1, _lib.ACT_RELU, interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID],
-                                        interaction[self.TARGET_LABEL], self._tables(), wt, bt)
+                                        interaction[self.TARGET_LABEL], self._tables(), wt, bt, self.fused_mlp_engine)
             return loss_s * self.alpha + loss_t * (1 - self.alpha)
         logit_s = self._logit(interaction[self.SOURCE_USER_ID], interaction[self.SOURCE_ITEM_ID], 'source')
         logit_t = self._logit(interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID], 'target')
@@ -97,5 +99,5 @@ class DTCDR(CrossDomainRecommender):
             if self._fused_ok():
                 wt, bt = self._tower('target')
                 return ops.fused_mlp_prob(_lib.ACT_RELU, interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID],
-                                          self._tables(), wt, bt)
+                                          self._tables(), wt, bt, self.fused_mlp_engine)
             return self.neumf_forward(interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID], 'target')

@@ -42,7 +42,9 @@ class EMCDR(CrossDomainRecommender):
         else:
             self.input_type = InputType.PAIRWISE
         self.bpr_gamma = 1e-10  # recbole BPRLoss default
-        self.use_fused_mlp = config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else False
+        # False: composed kernels; True / 'fma': fp32 row-tile kernel; 'tc': tensor-core row-tile kernel
+        self.fused_mlp_engine = ops.fused_mlp_engine(config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else False)
+        self.use_fused_mlp = self.fused_mlp_engine is not None
         self.source_latent_dim = config['source_embedding_size']
         self.target_latent_dim = config['target_embedding_size']
         self.reg_weight = config['reg_weight']
@@ -126,9 +128,10 @@ class EMCDR(CrossDomainRecommender):
         flat = idx.reshape(-1)
         ws, bs = self._mapping_params()
         dims = [ws[0].shape[1]] + [w.shape[0] for w in ws]
-        if self.use_fused_mlp and ops.fused_mlp_supported(dims):
+        if self.use_fused_mlp and ops.fused_mlp_supported(dims, self.fused_mlp_engine):
             # one kernel forward, one backward: gather -> MLP in shared memory -> MSE vs gathered target -> scatter
-            return ops.fused_mlp_loss(0, 0, _lib.ACT_TANH, flat, None, None, (src, None, None, None, tgt), ws, bs)
+            return ops.fused_mlp_loss(0, 0, _lib.ACT_TANH, flat, None, None, (src, None, None, None, tgt), ws, bs,
+                                      self.fused_mlp_engine)
         mapped = self._apply_mapping(ops.gather_rows(src, flat))
         return ops.mse_rows(mapped, tgt, flat)
 

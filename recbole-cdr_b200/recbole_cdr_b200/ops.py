@@ -518,9 +518,25 @@ def train_steps(user_tab, item_tab, user, item_a, item_b=None, label=None, *, lo
 import ctypes as _ct
 
 
-def fused_mlp_supported(dims) -> bool:
+FUSED_MLP_ENGINES = ('fma', 'tc')  # fp32 FMA row tiles (fused_mlp.cu) / 3xTF32 tensor-core row tiles (tc_mlp.cu)
+
+
+def fused_mlp_engine(flag) -> Optional[str]:
+    """Engine named by the model config key ``xdr_fused_mlp``: False/None -> composed kernels, True/'fma' -> the fp32
+    row-tile kernel, 'tc' -> the tensor-core row-tile kernel."""
+    if flag in (None, False, 0, '', 'false', 'False'):
+        return None
+    if flag in (True, 1, 'fma', 'true', 'True'):
+        return 'fma'
+    if flag == 'tc':
+        return 'tc'
+    raise ValueError(f"xdr_fused_mlp must be False, True, 'fma' or 'tc', got {flag!r}")
+
+
+def fused_mlp_supported(dims, engine: str = 'fma') -> bool:
     arr = (_ct.c_int * len(dims))(*[int(d) for d in dims])
-    return bool(_lib._lib.xdr_fused_mlp_supported(len(dims) - 1, _ct.cast(arr, _ct.c_void_p)))
+    fn = _lib._lib.xdr_tc_mlp_supported if engine == 'tc' else _lib._lib.xdr_fused_mlp_supported
+    return bool(fn(len(dims) - 1, _ct.cast(arr, _ct.c_void_p)))
 
 
 def _ptr_array(ts):
@@ -528,7 +544,7 @@ def _ptr_array(ts):
 
 
 def _fused_mlp_call(in_mode, head, hidden_act, tabs, idx_u, idx_i, label, Ws, bs, backward, grad_loss, dsts, dWs, dbs,
-                    want_prob):
+                    want_prob, engine='fma'):
     Au, Bu, Ai, Bi, T = tabs
     dev = Au.device
     dims = [Ws[0].shape[1]] + [w.shape[0] for w in Ws]
@@ -537,7 +553,9 @@ def _fused_mlp_call(in_mode, head, hidden_act, tabs, idx_u, idx_i, label, Ws, bs
     out8 = torch.empty(8, dtype=torch.float32, device=dev)
     prob = torch.empty(B, dtype=torch.float32, device=dev) if want_prob else None
     dAu, dBu, dAi, dBi, dT = dsts
-    call('xdr_fused_mlp_step', len(Ws), _ct.cast(arr, _ct.c_void_p), _ptr_array(Ws), _ptr_array(bs),
+    if engine not in FUSED_MLP_ENGINES:
+        raise ValueError(f'unknown fused-MLP engine {engine!r}')
+    call('xdr_tc_mlp_step' if engine == 'tc' else 'xdr_fused_mlp_step', len(Ws), _ct.cast(arr, _ct.c_void_p), _ptr_array(Ws), _ptr_array(bs),
          _ptr_array(dWs) if dWs else None, _ptr_array(dbs) if dbs else None, int(hidden_act), int(in_mode), int(head),
          ptr(Au), ptr(Bu), ptr(Ai), ptr(Bi), ptr(T), Au.shape[0], Ai.shape[0] if Ai is not None else 0, Au.shape[1],
          ptr(idx_u), ptr(idx_i), ptr(label), B, 1 if backward else 0, ptr(grad_loss), 1.0, ptr(dAu), ptr(dBu), ptr(dAi),
@@ -553,7 +571,7 @@ class FusedMlpLoss(torch.autograd.Function):
     the layer biases (None where a layer has none)."""
 
     @staticmethod
-    def forward(ctx, in_mode, head, hidden_act, idx_u, idx_i, label, n_layers, Au, Bu, Ai, Bi, T, *wb):
+    def forward(ctx, in_mode, head, hidden_act, idx_u, idx_i, label, n_layers, engine, Au, Bu, Ai, Bi, T, *wb):
         Ws, bs = list(wb[:n_layers]), list(wb[n_layers:])
         for t in (Au, Bu, Ai, Bi, T) + tuple(Ws):
             if t is not None:
@@ -561,14 +579,14 @@ class FusedMlpLoss(torch.autograd.Function):
         idx_u = _ids(idx_u, 'idx_u').reshape(-1)
         idx_i = _ids(idx_i, 'idx_i').reshape(-1) if idx_i is not None else None
         out8, _ = _fused_mlp_call(in_mode, head, hidden_act, (Au, Bu, Ai, Bi, T), idx_u, idx_i, label, Ws, bs, False, None,
-                                  (None,) * 5, None, None, False)
-        ctx.cfg = (in_mode, head, hidden_act, n_layers)
+                                  (None,) * 5, None, None, False, engine)
+        ctx.cfg = (in_mode, head, hidden_act, n_layers, engine)
         ctx.save_for_backward(idx_u, idx_i, label, Au, Bu, Ai, Bi, T, *Ws, *bs)
         return out8[0]
 
     @staticmethod
     def backward(ctx, grad_loss):
-        in_mode, head, hidden_act, n_layers = ctx.cfg
+        in_mode, head, hidden_act, n_layers, engine = ctx.cfg
         sv = ctx.saved_tensors
         idx_u, idx_i, label, Au, Bu, Ai, Bi, T = sv[:8]
         Ws, bs = list(sv[8:8 + n_layers]), list(sv[8 + n_layers:])
@@ -585,20 +603,20 @@ class FusedMlpLoss(torch.autograd.Function):
         dWs = [torch.zeros_like(w) for w in Ws]
         dbs = [None if b is None else torch.zeros_like(b) for b in bs]
         _fused_mlp_call(in_mode, head, hidden_act, (Au, Bu, Ai, Bi, T), idx_u, idx_i, label, Ws, bs, True, g, dsts, dWs, dbs,
-                        False)
-        return (None,) * 7 + tuple(rets) + tuple(dWs) + tuple(dbs)
+                        False, engine)
+        return (None,) * 8 + tuple(rets) + tuple(dWs) + tuple(dbs)
 
 
-def fused_mlp_loss(in_mode, head, hidden_act, idx_u, idx_i, label, tabs, Ws, bs):
+def fused_mlp_loss(in_mode, head, hidden_act, idx_u, idx_i, label, tabs, Ws, bs, engine='fma'):
     Au, Bu, Ai, Bi, T = tabs
-    return FusedMlpLoss.apply(in_mode, head, hidden_act, idx_u, idx_i, label, len(Ws), Au, Bu, Ai, Bi, T, *Ws, *bs)
+    return FusedMlpLoss.apply(in_mode, head, hidden_act, idx_u, idx_i, label, len(Ws), engine, Au, Bu, Ai, Bi, T, *Ws, *bs)
 
 
-def fused_mlp_prob(hidden_act, idx_u, idx_i, tabs, Ws, bs):
+def fused_mlp_prob(hidden_act, idx_u, idx_i, tabs, Ws, bs, engine='fma'):
     """Forward only, sigmoid output per row (DTCDR.predict)."""
     with torch.no_grad():
         idx_u, idx_i = _ids(idx_u, 'idx_u').reshape(-1), _ids(idx_i, 'idx_i').reshape(-1)
         label = torch.zeros(idx_u.numel(), dtype=torch.float32, device=tabs[0].device)
         _, prob = _fused_mlp_call(1, 1, hidden_act, tabs, idx_u, idx_i, label, list(Ws), list(bs), False, None, (None,) * 5,
-                                  None, None, True)
+                                  None, None, True, engine)
         return prob

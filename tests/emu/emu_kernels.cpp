@@ -1,0 +1,92 @@
+// emu_kernels.cpp -- TEST INFRASTRUCTURE ONLY.  Compiles kernel sources of libxdr with g++ against the CTA emulator
+// (cuda_emu.h) and exports plain C entry points that take HOST pointers, so `pytest -m "not gpu"` can run the kernels'
+// logic on the CPU and compare it with the oracle.  Built on demand by tests/emu_util.py into tests/emu/_build/.
+#define XDR_EMU 1
+#include "../../recbole-cdr_b200/csrc/fused_mlp.cu"
+#include "../../recbole-cdr_b200/csrc/tc_mlp.cu"
+
+#include <cstdarg>
+
+namespace xdr {
+static int g_sms = 4;
+static char g_err[512];
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int sm_count() { return g_sms; }
+}  // namespace xdr
+
+using namespace xdr;
+
+static void fill_mlp_args(MlpArgs& a, int n_layers, const int* dims, const float* const* W, const float* const* b,
+                          float* const* dW, float* const* db, int hidden_act, int in_mode, int head, const float* Au,
+                          const float* Bu, const float* Ai, const float* Bi, const float* T, int64_t n_u, int64_t n_i, int dim,
+                          const int64_t* idx_u, const int64_t* idx_i, const float* label, int64_t batch, int backward,
+                          const float* grad_loss, float scale, float* dAu, float* dBu, float* dAi, float* dBi, float* dT,
+                          float* prob, float* out8, int32_t* oob) {
+  a.n_layers = n_layers;
+  for (int l = 0; l <= n_layers; ++l) a.dims[l] = dims[l];
+  for (int l = 0; l < n_layers; ++l) {
+    a.W[l] = W[l];
+    a.b[l] = b ? b[l] : nullptr;
+    a.dW[l] = (backward && dW) ? dW[l] : nullptr;
+    a.db[l] = (backward && db) ? db[l] : nullptr;
+  }
+  a.hidden_act = hidden_act; a.last_act = XDR_ACT_NONE; a.in_mode = in_mode; a.head = head;
+  a.Au = Au; a.Bu = Bu; a.Ai = Ai; a.Bi = Bi; a.T = T; a.n_u = n_u; a.n_i = n_i; a.dim = dim;
+  a.idx_u = idx_u; a.idx_i = idx_i; a.label = label; a.batch = batch; a.backward = backward; a.grad_loss = grad_loss;
+  a.scale = scale; a.dAu = dAu; a.dBu = dBu; a.dAi = dAi; a.dBi = dBi; a.dT = dT; a.prob = prob; a.out8 = out8; a.oob = oob;
+}
+
+extern "C" {
+
+void emu_config(int sms, uint64_t schedule_seed) {
+  g_sms = sms;
+  emu::set_schedule_seed(schedule_seed);
+}
+const char* emu_last_error() { return g_err; }
+
+// impl 0: fused_mlp_kernel (fp32 FMA, validated on hardware -- run here to validate the emulator itself)
+// impl 1: tc_mlp_kernel (tensor-core tiles)
+int emu_mlp_step(int impl, int n_layers, const int* dims, const float* const* W, const float* const* b, float* const* dW,
+                 float* const* db, int hidden_act, int in_mode, int head, const float* Au, const float* Bu, const float* Ai,
+                 const float* Bi, const float* T, int64_t n_u, int64_t n_i, int dim, const int64_t* idx_u,
+                 const int64_t* idx_i, const float* label, int64_t batch, int backward, const float* grad_loss, float scale,
+                 float* dAu, float* dBu, float* dAi, float* dBi, float* dT, float* prob, float* out8, void* ws, int32_t* oob,
+                 int force_tile_rows) {
+  MlpArgs a{};
+  fill_mlp_args(a, n_layers, dims, W, b, dW, db, hidden_act, in_mode, head, Au, Bu, Ai, Bi, T, n_u, n_i, dim, idx_u, idx_i,
+                label, batch, backward, grad_loss, scale, dAu, dBu, dAi, dBi, dT, prob, out8, oob);
+  if (impl == 0) {
+    if (!pick_tile_rows(&a)) return -3;
+    if (force_tile_rows) a.tile_rows = force_tile_rows;
+    const size_t smem = mlp_smem_bytes(a);
+    const int64_t n_tiles = (a.batch + a.tile_rows - 1) / a.tile_rows;
+    const unsigned grid = (unsigned)std::min<int64_t>(g_sms, n_tiles);
+    emu::launch(grid, kMlpThreads, smem, [&] { fused_mlp_kernel<32, 32, 32>(a, Workspace(ws)); });
+    return 0;
+  }
+  MlpArgs chk{};
+  if (!tc_stack_ok(n_layers, dims, &chk)) return -3;
+  int tr = tc_pick_tile_rows(a, batch);
+  if (force_tile_rows) tr = force_tile_rows;
+  if (tr == 0) return -3;
+  a.tile_rows = tr;
+  const size_t smem = tc_smem_bytes(a, tr);
+  const int64_t n_tiles = (a.batch + tr - 1) / tr;
+  const unsigned grid = (unsigned)std::min<int64_t>(g_sms, n_tiles);
+  if (tr == 64) emu::launch(grid, kTcThreads, smem, [&] { tc_mlp_kernel<64, kTcDw0, kTcDw1, kTcDw2>(a, Workspace(ws)); });
+  else emu::launch(grid, kTcThreads, smem, [&] { tc_mlp_kernel<32, kTcDw0, kTcDw1, kTcDw2>(a, Workspace(ws)); });
+  return 0;
+}
+
+int emu_tc_mlp_supported(int n_layers, const int* dims) {
+  MlpArgs a{};
+  if (!tc_stack_ok(n_layers, dims, &a)) return 0;
+  return tc_pick_tile_rows(a, 0) != 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+"""Builds and binds the CPU CTA-emulator build of selected libxdr kernels (tests/emu).  TEST INFRASTRUCTURE ONLY: lets the
+CPU suite execute kernel *logic* written without GPU access; hardware parity remains the job of the ``gpu`` tests."""
+import ctypes
+import glob
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+EMU_DIR = os.path.join(HERE, 'emu')
+BUILD_DIR = os.path.join(EMU_DIR, '_build')
+LIB = os.path.join(BUILD_DIR, 'libxdr_emu.so')
+CSRC = os.path.join(ROOT, 'recbole-cdr_b200', 'csrc')
+
+_lib = None
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = glob.glob(os.path.join(EMU_DIR, '*.cpp')) + glob.glob(os.path.join(EMU_DIR, '*.h')) + \
+        glob.glob(os.path.join(EMU_DIR, '*.inc')) + glob.glob(os.path.join(CSRC, '*.cu')) + \
+        glob.glob(os.path.join(CSRC, '*.cuh')) + [os.path.join(ROOT, 'include', 'xdr.h')]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build():
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    if _stale():
+        cmd = ['g++', '-O2', '-std=c++17', '-x', 'c++', '-fPIC', '-shared', '-DXDR_EMU=1', '-I', EMU_DIR,
+               '-I', os.path.join(ROOT, 'include'), '-Wno-unknown-pragmas', '-Wno-attributes',
+               os.path.join(EMU_DIR, 'emu_kernels.cpp'), '-o', LIB]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('emulator build failed:\n' + r.stdout + r.stderr)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.emu_last_error.restype = ctypes.c_char_p
+        _lib.emu_config.argtypes = [ctypes.c_int, ctypes.c_uint64]
+    return _lib
+
+
+def config(sms=4, seed=0):
+    lib().emu_config(int(sms), int(seed))
+
+
+def p(a):
+    """Host pointer of a numpy array (None -> NULL)."""
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def ptr_array(arrs):
+    return (ctypes.c_void_p * len(arrs))(*[None if a is None else a.ctypes.data for a in arrs])
+
+
+WS_BYTES = 64 + 4 * 4 * 2048
+
+
+def workspace():
+    return np.zeros(WS_BYTES, dtype=np.uint8)
+
+
+def mlp_step(impl, dims, Ws, bs, hidden_act, in_mode, head, tabs, idx_u, idx_i, label, backward=True, grad_loss=1.0,
+             scale=1.0, tile_rows=0):
+    """Runs fused_mlp_kernel (impl 0) or tc_mlp_kernel (impl 1) under the emulator.  Returns dict(loss, dW, db, dtabs, prob)."""
+    L = lib()
+    Au, Bu, Ai, Bi, T = tabs
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+    Au, Bu, Ai, Bi, T = map(f32, (Au, Bu, Ai, Bi, T))
+    Ws = [f32(w) for w in Ws]
+    bs = [f32(b) for b in bs]
+    dWs = [np.zeros_like(w) for w in Ws]
+    dbs = [None if b is None else np.zeros_like(b) for b in bs]
+    dt = [None if t is None else np.zeros_like(t) for t in (Au, Bu, Ai, Bi, T)]
+    idx_u = np.ascontiguousarray(idx_u, dtype=np.int64)
+    idx_i = None if idx_i is None else np.ascontiguousarray(idx_i, dtype=np.int64)
+    label = f32(label)
+    B = idx_u.size
+    out8 = np.zeros(8, dtype=np.float32)
+    prob = np.zeros(B, dtype=np.float32) if head == 1 else None
+    g = np.array([grad_loss], dtype=np.float32)
+    ws = workspace()
+    oob = np.zeros(1, dtype=np.int32)
+    darr = (ctypes.c_int * len(dims))(*[int(d) for d in dims])
+    L.emu_mlp_step.argtypes = None
+    rc = L.emu_mlp_step(
+        ctypes.c_int(impl), ctypes.c_int(len(Ws)), darr, ptr_array(Ws), ptr_array(bs), ptr_array(dWs), ptr_array(dbs),
+        ctypes.c_int(hidden_act), ctypes.c_int(in_mode), ctypes.c_int(head), p(Au), p(Bu), p(Ai), p(Bi), p(T),
+        ctypes.c_int64(Au.shape[0]), ctypes.c_int64(Ai.shape[0] if Ai is not None else 0), ctypes.c_int(Au.shape[1]),
+        p(idx_u), p(idx_i), p(label), ctypes.c_int64(B), ctypes.c_int(1 if backward else 0), p(g), ctypes.c_float(scale),
+        p(dt[0]), p(dt[1]), p(dt[2]), p(dt[3]), p(dt[4]), p(prob), p(out8), p(ws), p(oob), ctypes.c_int(tile_rows))
+    if rc != 0:
+        raise RuntimeError(f'emu_mlp_step rc={rc}: {L.emu_last_error().decode()}')
+    assert not ws[:64].any(), 'kernel left the workspace ticket dirty'
+    return dict(loss=float(out8[0]), dW=dWs, db=dbs, dtabs=dt, prob=prob, oob=int(oob[0]))

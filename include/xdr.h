@@ -191,6 +191,30 @@ XDR_API int xdr_tc_mlp_step(int n_layers, const int* dims_host, const float* con
                             float* dAu, float* dBu, float* dAi, float* dBi, float* dT, float* prob, float* out8,
                             void* ws, int32_t* oob, xdr_stream_t stream);
 
+/* ---- A7-A8 fused: one CoNet tower pass (cross-stitch stack + BCE) with backward and scatter-add in ONE kernel --------------
+ * Replaces CoNet.source_forward / target_forward + nn.BCELoss and their autograd backward for one domain batch
+ * (conet.py:105-181, 196-197):  x_s = [Su[u] | Si[i]], x_t = [Tu[u] | Ti[i]];  per layer l
+ *     x_s' = relu(Ws_l x_s + bs_l + m (H_l x_t)),  x_t' = relu(Wt_l x_t + bt_l + m (H_l x_s)),  m = (id < n_overlap)
+ * (id = user, or item when mask_on_item; H_l = crossparas[l].weight shared by both directions), then
+ *     loss = mean BCE(sigmoid(w_out . x_want + b_out), label),  want 0 = source tower, 1 = target tower.
+ *   dims[0] = 2*dim, dims[1..n_layers] = mlp_hidden_size; *_host are HOST arrays of n_layers device pointers
+ *   (weights [dims[l+1], dims[l]], 16-byte aligned); w_out [dims[n_layers]], b_out [1].
+ *   backward != 0: dWs/dbs/dWt/dbt/dH/dw_out/db_out += (the unwanted tower's last layer receives zeros), and
+ *   scale * g * dL/drow is scatter-added into dSu/dSi/dTu/dTi; g = *grad_loss.  dz1_scratch: xdr_tc_conet_scratch_bytes().
+ * Layer products are 3xTF32 mma.sync tiles (fp32-equivalent to ~1e-6).  Supported stacks (xdr_tc_conet_supported):
+ * 2*dim % 64 == 0 and <= 512, 1..4 layers, hidden widths % 8 == 0 and <= 64.                                               */
+XDR_API int xdr_tc_conet_supported(int n_layers, const int* dims_host, int dim);
+XDR_API size_t xdr_tc_conet_scratch_bytes(int64_t batch, int hidden0);
+XDR_API int xdr_tc_conet_step(int n_layers, const int* dims_host, const float* const* Ws_host, const float* const* bs_host,
+                              const float* const* Wt_host, const float* const* bt_host, const float* const* H_host,
+                              float* const* dWs_host, float* const* dbs_host, float* const* dWt_host,
+                              float* const* dbt_host, float* const* dH_host, const float* w_out, const float* b_out,
+                              float* dw_out, float* db_out, int want, const float* Su, const float* Si, const float* Tu,
+                              const float* Ti, int64_t n_u, int64_t n_i, int dim, const int64_t* user, const int64_t* item,
+                              const float* label, int64_t batch, int mask_on_item, int64_t n_overlap, int backward,
+                              const float* grad_loss, float scale, float* dSu, float* dSi, float* dTu, float* dTi,
+                              float* dz1_scratch, float* prob, float* out8, void* ws, int32_t* oob, xdr_stream_t stream);
+
 /* ---- A6: EMCDR predict tail: select mapped vs. target row, then dot ------------------------------------------
  * Replaces the torch.where + mul + sum of EMCDR.predict, OVERLAP/BOTH phase (emcdr.py:191-205):
  *   e = (sel_ids[b] < n_overlap) ? mapped[b, :] : tgt_tab[sel_ids[b], :];   score[b] = e . other_tab[other_ids[b], :]

@@ -70,62 +70,99 @@ __device__ __forceinline__ float act_grad(float y, int act) {
   return 1.f;
 }
 
-// C[TR x N] = A[TR x K] * B for one CTA of kTcWarps warps; A row-major in shared memory (element (m, k) at A[m*lda + k]).
+// acc += A[TR x K] * B restricted to the output tiles this warp owns; A row-major in shared memory ((m, k) at A[m*lda + k]).
 //   BT == false:  B(k, n) = Bsm[n*ldb + k]   (nn.Linear.weight [N][K]:  C = A W^T, the forward of a layer)
 //   BT == true :  B(k, n) = Bsm[k*ldb + n]   (C = A W with W [K][N]:     the input gradient dX = dZ W)
 // Warp w owns the 16-row tile (w % MT) and the 8-column tiles (w / MT) + j*G, j < MAXNT (MT = TR/16, G = kTcWarps/MT).
-// epi(row, col, v0, v1) receives C[row][col], C[row][col+1] (col even).  N % 8 == 0, K % 8 == 0, N <= 8*G*MAXNT.
-template <int TR, int MAXNT, bool BT, typename Epi>
-__device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, const float* __restrict__ Bsm, int ldb, int N,
-                                          int K, Epi epi) {
+// N % 8 == 0, K % 8 == 0, N <= 8*G*MAXNT.  The accumulators belong to the caller, so a product can be split over K chunks.
+template <int TR, int MAXNT, bool BT>
+__device__ __forceinline__ void tile_mma_acc(float (&acc)[MAXNT][4], const float* __restrict__ A, int lda,
+                                             const float* __restrict__ Bsm, int ldb, int N, int K) {
   constexpr int MT = TR / 16, G = kTcWarps / MT;
   static_assert(TR % 16 == 0 && kTcWarps % MT == 0, "row tile must split into whole 16-row MMA tiles over the warps");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int m0 = (warp % MT) * 16, grp = warp / MT;
   const int ntiles = N >> 3;
-  float acc[MAXNT][4];
+  if (grp >= ntiles) return;
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    uint32_t ah[4], al[4];
+    const float* ap = A + (m0 + g) * lda + k0 + t;
+    split_tf32(ap[0], ah[0], al[0]);
+    split_tf32(ap[8 * lda], ah[1], al[1]);
+    split_tf32(ap[4], ah[2], al[2]);
+    split_tf32(ap[8 * lda + 4], ah[3], al[3]);
 #pragma unroll
-  for (int j = 0; j < MAXNT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-  if (grp < ntiles) {
-    for (int k0 = 0; k0 < K; k0 += 8) {
-      uint32_t ah[4], al[4];
-      const float* ap = A + (m0 + g) * lda + k0 + t;
-      split_tf32(ap[0], ah[0], al[0]);
-      split_tf32(ap[8 * lda], ah[1], al[1]);
-      split_tf32(ap[4], ah[2], al[2]);
-      split_tf32(ap[8 * lda + 4], ah[3], al[3]);
-#pragma unroll
-      for (int j = 0; j < MAXNT; ++j) {
-        const int nt = grp + j * G;
-        if (nt < ntiles) {  // warp-uniform
-          const int n = nt * 8 + g;
-          float b0, b1;
-          if (!BT) {
-            const float* bp = Bsm + n * ldb + k0 + t;
-            b0 = bp[0];
-            b1 = bp[4];
-          } else {
-            const float* bp = Bsm + (k0 + t) * ldb + n;
-            b0 = bp[0];
-            b1 = bp[4 * ldb];
-          }
-          uint32_t bh[2], bl[2];
-          split_tf32(b0, bh[0], bl[0]);
-          split_tf32(b1, bh[1], bl[1]);
-          mma_3xtf32(acc[j], ah, al, bh, bl);
+    for (int j = 0; j < MAXNT; ++j) {
+      const int nt = grp + j * G;
+      if (nt < ntiles) {  // warp-uniform
+        const int n = nt * 8 + g;
+        float b0, b1;
+        if (!BT) {
+          const float* bp = Bsm + n * ldb + k0 + t;
+          b0 = bp[0];
+          b1 = bp[4];
+        } else {
+          const float* bp = Bsm + (k0 + t) * ldb + n;
+          b0 = bp[0];
+          b1 = bp[4 * ldb];
         }
+        uint32_t bh[2], bl[2];
+        split_tf32(b0, bh[0], bl[0]);
+        split_tf32(b1, bh[1], bl[1]);
+        mma_3xtf32(acc[j], ah, al, bh, bl);
       }
     }
   }
+}
+
+template <int MAXNT>
+__device__ __forceinline__ void tile_acc_zero(float (&acc)[MAXNT][4]) {
+#pragma unroll
+  for (int j = 0; j < MAXNT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+}
+
+// Visits the accumulator pairs of this warp: fn(j, row, col, half) with acc[j][2*half], acc[j][2*half + 1] holding
+// C[row][col], C[row][col + 1] (col even).  Same ownership as tile_mma_acc.
+template <int TR, int MAXNT, typename Fn>
+__device__ __forceinline__ void tile_acc_visit(int N, Fn fn) {
+  constexpr int MT = TR / 16, G = kTcWarps / MT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = (warp % MT) * 16, grp = warp / MT;
+  const int ntiles = N >> 3;
 #pragma unroll
   for (int j = 0; j < MAXNT; ++j) {
     const int nt = grp + j * G;
     if (nt < ntiles) {
-      const int col = nt * 8 + 2 * t;
-      epi(m0 + g, col, acc[j][0], acc[j][1]);
-      epi(m0 + g + 8, col, acc[j][2], acc[j][3]);
+      fn(j, m0 + g, nt * 8 + 2 * t, 0);
+      fn(j, m0 + g + 8, nt * 8 + 2 * t, 1);
     }
   }
+}
+
+// C[TR x N] = A[TR x K] * B for one CTA; epi(row, col, v0, v1) receives C[row][col], C[row][col+1] (col even).
+template <int TR, int MAXNT, bool BT, typename Epi>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, const float* __restrict__ Bsm, int ldb, int N,
+                                          int K, Epi epi) {
+  float acc[MAXNT][4];
+  tile_acc_zero(acc);
+  tile_mma_acc<TR, MAXNT, BT>(acc, A, lda, Bsm, ldb, N, K);
+  tile_acc_visit<TR, MAXNT>(N, [&](int j, int row, int col, int half) { epi(row, col, acc[j][2 * half], acc[j][2 * half + 1]); });
+}
+
+// Two products over the same output tile: C1 = A1 * B1, C2 = A2 * B2 (same N, K and BT); epi(row, col, v0, v1, c0, c1).
+// The cross-stitch unit of CoNet (conet.py:118-138): v = own tower, c = cross term, combined per row by the overlap mask.
+template <int TR, int MAXNT, bool BT, typename Epi>
+__device__ __forceinline__ void tile_gemm2(const float* __restrict__ A1, int lda1, const float* __restrict__ B1, int ldb1,
+                                           const float* __restrict__ A2, int lda2, const float* __restrict__ B2, int ldb2,
+                                           int N, int K, Epi epi) {
+  float acc[MAXNT][4], acc2[MAXNT][4];
+  tile_acc_zero(acc);
+  tile_acc_zero(acc2);
+  tile_mma_acc<TR, MAXNT, BT>(acc, A1, lda1, B1, ldb1, N, K);
+  tile_mma_acc<TR, MAXNT, BT>(acc2, A2, lda2, B2, ldb2, N, K);
+  tile_acc_visit<TR, MAXNT>(N, [&](int j, int row, int col, int half) {
+    epi(row, col, acc[j][2 * half], acc[j][2 * half + 1], acc2[j][2 * half], acc2[j][2 * half + 1]);
+  });
 }
 
 // Picks the smallest MAXNT instantiation that covers N output columns.
@@ -140,6 +177,17 @@ __device__ __forceinline__ void tile_gemm_any(const float* A, int lda, const flo
   else tile_gemm<TR, 16, BT>(A, lda, Bsm, ldb, N, K, epi);
 }
 
+template <int TR, bool BT, typename Epi>
+__device__ __forceinline__ void tile_gemm2_any(const float* A1, int lda1, const float* B1, int ldb1, const float* A2, int lda2,
+                                               const float* B2, int ldb2, int N, int K, Epi epi) {
+  constexpr int G = kTcWarps / (TR / 16);
+  const int per_warp = ((N >> 3) + G - 1) / G;
+  if (per_warp <= 1) tile_gemm2<TR, 1, BT>(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, N, K, epi);
+  else if (per_warp <= 2) tile_gemm2<TR, 2, BT>(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, N, K, epi);
+  else if (per_warp <= 4) tile_gemm2<TR, 4, BT>(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, N, K, epi);
+  else tile_gemm2<TR, 8, BT>(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, N, K, epi);
+}
+
 // Number of 16x8 tiles of a [dout][din] weight gradient and how many of them each warp owns (tile i -> warp i % kTcWarps).
 __host__ __device__ inline int dw_tiles(int dout, int din) { return ((dout + 15) >> 4) * (din >> 3); }
 __host__ __device__ inline int dw_tiles_per_warp(int dout, int din) { return (dw_tiles(dout, din) + kTcWarps - 1) / kTcWarps; }
@@ -147,9 +195,12 @@ __host__ __device__ inline int dw_tiles_per_warp(int dout, int din) { return (dw
 // acc += dZ^T X restricted to the tiles this warp owns:  dW[n][k] += sum_r dZ[r][n] * X[r][k],  r < TR.
 // dZ [TR][ldz] (dout columns), X [TR][ldx] (din columns), both row-major in shared memory.  The accumulators are MMA C
 // fragments that live in registers across all row tiles of the CTA; dw_flush() adds them to global memory once.
+// rmask (optional, [TR]): dZ row r is multiplied by rmask[r] (the overlap mask of CoNet's cross parameters).  For a K-chunked
+// layer pass the chunk slab as X with din = chunk width; dw_flush() then places the chunk inside the full weight.
 template <int TR, int MAXT>
 __device__ __forceinline__ void dw_accum(float (&acc)[MAXT][4], const float* __restrict__ dZ, int ldz,
-                                         const float* __restrict__ X, int ldx, int dout, int din) {
+                                         const float* __restrict__ X, int ldx, int dout, int din,
+                                         const float* __restrict__ rmask = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int ktiles = din >> 3, total = dw_tiles(dout, din);
 #pragma unroll
@@ -161,11 +212,12 @@ __device__ __forceinline__ void dw_accum(float (&acc)[MAXT][4], const float* __r
 #pragma unroll 2
       for (int r0 = 0; r0 < TR; r0 += 8) {
         const float* zp = dZ + (r0 + t) * ldz + n0 + g;
+        const float mk0 = rmask ? rmask[r0 + t] : 1.f, mk1 = rmask ? rmask[r0 + t + 4] : 1.f;
         uint32_t ah[4], al[4], bh[2], bl[2];
-        split_tf32(lo_ok ? zp[0] : 0.f, ah[0], al[0]);
-        split_tf32(hi_ok ? zp[8] : 0.f, ah[1], al[1]);
-        split_tf32(lo_ok ? zp[4 * ldz] : 0.f, ah[2], al[2]);
-        split_tf32(hi_ok ? zp[4 * ldz + 8] : 0.f, ah[3], al[3]);
+        split_tf32(lo_ok ? mk0 * zp[0] : 0.f, ah[0], al[0]);
+        split_tf32(hi_ok ? mk0 * zp[8] : 0.f, ah[1], al[1]);
+        split_tf32(lo_ok ? mk1 * zp[4 * ldz] : 0.f, ah[2], al[2]);
+        split_tf32(hi_ok ? mk1 * zp[4 * ldz + 8] : 0.f, ah[3], al[3]);
         const float* xp = X + (r0 + t) * ldx + k0 + g;
         split_tf32(xp[0], bh[0], bl[0]);
         split_tf32(xp[4 * ldx], bh[1], bl[1]);
@@ -175,9 +227,13 @@ __device__ __forceinline__ void dw_accum(float (&acc)[MAXT][4], const float* __r
   }
 }
 
+// dW row stride ldw (>= din) and column offset k_off let a K chunk of a wider weight be flushed in place.
 template <int MAXT>
-__device__ __forceinline__ void dw_flush(const float (&acc)[MAXT][4], float* __restrict__ dW, int dout, int din) {
+__device__ __forceinline__ void dw_flush(const float (&acc)[MAXT][4], float* __restrict__ dW, int dout, int din, int ldw = -1,
+                                         int k_off = 0) {
   if (dW == nullptr) return;
+  if (ldw < 0) ldw = din;
+  dW += k_off;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int ktiles = din >> 3, total = dw_tiles(dout, din);
 #pragma unroll
@@ -186,12 +242,12 @@ __device__ __forceinline__ void dw_flush(const float (&acc)[MAXT][4], float* __r
     if (tile < total) {
       const int n0 = (tile / ktiles) * 16, k = (tile % ktiles) * 8 + 2 * t;
       if (n0 + g < dout) {
-        atomicAdd(&dW[(size_t)(n0 + g) * din + k], acc[j][0]);
-        atomicAdd(&dW[(size_t)(n0 + g) * din + k + 1], acc[j][1]);
+        atomicAdd(&dW[(size_t)(n0 + g) * ldw + k], acc[j][0]);
+        atomicAdd(&dW[(size_t)(n0 + g) * ldw + k + 1], acc[j][1]);
       }
       if (n0 + g + 8 < dout) {
-        atomicAdd(&dW[(size_t)(n0 + g + 8) * din + k], acc[j][2]);
-        atomicAdd(&dW[(size_t)(n0 + g + 8) * din + k + 1], acc[j][3]);
+        atomicAdd(&dW[(size_t)(n0 + g + 8) * ldw + k], acc[j][2]);
+        atomicAdd(&dW[(size_t)(n0 + g + 8) * ldw + k + 1], acc[j][3]);
       }
     }
   }

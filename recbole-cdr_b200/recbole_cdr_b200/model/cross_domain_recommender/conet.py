@@ -48,6 +48,25 @@ class CoNet(CrossDomainRecommender):
         self.crossparas = self.cross_parameters(dims)
 
         self.apply(xavier_normal_initialization)
+        # opt-in: one tensor-core kernel per tower pass (tc_conet.cu) instead of the composed dense-layer kernels
+        self.use_fused_conet = bool(config['xdr_fused_conet']) if 'xdr_fused_conet' in config else False
+
+    def _fused_ok(self):
+        return self.use_fused_conet and ops.conet_fused_supported([2 * self.latent_dim] + self.cross_layers, self.latent_dim)
+
+    def _fused_tower_loss(self, user, item, label, want):
+        out = self.source_outputunit[0] if want == 'source' else self.target_outputunit[0]
+        if self.mode == 'overlap_users':
+            mask_on_item, n_ov = False, self.overlapped_num_users
+        else:
+            mask_on_item, n_ov = True, self.overlapped_num_items
+        tabs = (self.source_user_embedding.weight, self.source_item_embedding.weight, self.target_user_embedding.weight,
+                self.target_item_embedding.weight)
+        return ops.conet_tower_loss(0 if want == 'source' else 1, mask_on_item, n_ov, user, item, label, tabs, out.weight,
+                                    out.bias, [m.weight for m in self.source_crossunit_linear],
+                                    [m.bias for m in self.source_crossunit_linear],
+                                    [m.weight for m in self.target_crossunit_linear],
+                                    [m.bias for m in self.target_crossunit_linear], [m.weight for m in self.crossparas])
 
     @staticmethod
     def cross_units(dims):
@@ -92,10 +111,16 @@ class CoNet(CrossDomainRecommender):
 
     def calculate_loss(self, interaction):
         """BCE(source tower, source batch) + BCE(target tower, target batch) + sum_l ||H_l||_F (conet.py:183-203)."""
-        logit_s = self._towers(interaction[self.SOURCE_USER_ID], interaction[self.SOURCE_ITEM_ID], 'source')
-        logit_t = self._towers(interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID], 'target')
-        loss_s, _ = ops.bce_logit(logit_s, interaction[self.SOURCE_LABEL])
-        loss_t, _ = ops.bce_logit(logit_t, interaction[self.TARGET_LABEL])
+        if self._fused_ok():
+            loss_s = self._fused_tower_loss(interaction[self.SOURCE_USER_ID], interaction[self.SOURCE_ITEM_ID],
+                                            interaction[self.SOURCE_LABEL], 'source')
+            loss_t = self._fused_tower_loss(interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID],
+                                            interaction[self.TARGET_LABEL], 'target')
+        else:
+            logit_s = self._towers(interaction[self.SOURCE_USER_ID], interaction[self.SOURCE_ITEM_ID], 'source')
+            logit_t = self._towers(interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID], 'target')
+            loss_s, _ = ops.bce_logit(logit_s, interaction[self.SOURCE_LABEL])
+            loss_t, _ = ops.bce_logit(logit_t, interaction[self.TARGET_LABEL])
         reg_loss = 0
         for para in self.crossparas:
             reg_loss = reg_loss + torch.norm(para.weight)

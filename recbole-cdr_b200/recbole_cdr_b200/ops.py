@@ -620,3 +620,83 @@ def fused_mlp_prob(hidden_act, idx_u, idx_i, tabs, Ws, bs, engine='fma'):
         _, prob = _fused_mlp_call(1, 1, hidden_act, tabs, idx_u, idx_i, label, list(Ws), list(bs), False, None, (None,) * 5,
                                   None, None, True, engine)
         return prob
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# A7-A8 fused: one CoNet tower pass (cross-stitch stack + BCE + backward + scatter) in one tensor-core kernel
+# ------------------------------------------------------------------------------------------------------------------
+
+def conet_fused_supported(dims, dim) -> bool:
+    arr = (_ct.c_int * len(dims))(*[int(d) for d in dims])
+    return bool(_lib._lib.xdr_tc_conet_supported(len(dims) - 1, _ct.cast(arr, _ct.c_void_p), int(dim)))
+
+
+def _conet_call(want, mask_on_item, n_overlap, user, item, label, tabs, w_out, b_out, ws, bs, wt, bt, hs, backward,
+                grad_loss, dsts, grads, want_prob):
+    Su, Si, Tu, Ti = tabs
+    dev = Su.device
+    dims = [ws[0].shape[1]] + [w.shape[0] for w in ws]
+    arr = (_ct.c_int * len(dims))(*dims)
+    B = user.numel()
+    out8 = torch.empty(8, dtype=torch.float32, device=dev)
+    prob = torch.empty(B, dtype=torch.float32, device=dev) if want_prob else None
+    scratch = torch.empty((B, 2 * dims[1]), dtype=torch.float32, device=dev) if backward else None
+    dSu, dSi, dTu, dTi = dsts
+    g = grads if grads is not None else dict(ws=None, bs=None, wt=None, bt=None, h=None, w_out=None, b_out=None)
+    pa = lambda lst: None if lst is None else _ptr_array(lst)
+    call('xdr_tc_conet_step', len(ws), _ct.cast(arr, _ct.c_void_p), _ptr_array(ws), _ptr_array(bs), _ptr_array(wt),
+         _ptr_array(bt), _ptr_array(hs), pa(g['ws']), pa(g['bs']), pa(g['wt']), pa(g['bt']), pa(g['h']), ptr(w_out), ptr(b_out),
+         ptr(g['w_out']), ptr(g['b_out']), int(want), ptr(Su), ptr(Si), ptr(Tu), ptr(Ti), Su.shape[0], Si.shape[0], Su.shape[1],
+         ptr(user), ptr(item), ptr(label), B, 1 if mask_on_item else 0, int(n_overlap), 1 if backward else 0, ptr(grad_loss), 1.0,
+         ptr(dSu), ptr(dSi), ptr(dTu), ptr(dTi), ptr(scratch), ptr(prob), ptr(out8), ptr(_lib.workspace(dev)), _oob(dev),
+         cur_stream())
+    _maybe_check(dev)
+    return out8, prob
+
+
+class ConetTowerLoss(torch.autograd.Function):
+    """``BCELoss(source_forward(u, i), label)`` (want 0) or ``BCELoss(target_forward(u, i), label)`` (want 1) of CoNet
+    (conet.py:105-181, 196-197) as ONE kernel forward and ONE kernel for the whole backward (the forward is recomputed on
+    chip).  Tensor arguments: the four tables, the wanted output unit (weight, bias), then per layer the source weights,
+    source biases, target weights, target biases, cross parameters (5 * n_layers tensors)."""
+
+    @staticmethod
+    def forward(ctx, want, mask_on_item, n_overlap, user, item, label, n_layers, Su, Si, Tu, Ti, w_out, b_out, *params):
+        L = n_layers
+        ws, bs, wt, bt, hs = (list(params[k * L:(k + 1) * L]) for k in range(5))
+        for t in (Su, Si, Tu, Ti, w_out, b_out) + tuple(params):
+            _require_cuda_f32(t, 'conet operand')
+        _require_cuda_f32(label, 'label')
+        user, item = _ids(user, 'user').reshape(-1), _ids(item, 'item').reshape(-1)
+        out8, _ = _conet_call(want, mask_on_item, n_overlap, user, item, label, (Su, Si, Tu, Ti), w_out, b_out, ws, bs, wt, bt,
+                              hs, False, None, (None,) * 4, None, False)
+        ctx.cfg = (want, mask_on_item, n_overlap, L)
+        ctx.save_for_backward(user, item, label, Su, Si, Tu, Ti, w_out, b_out, *params)
+        return out8[0]
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        want, mask_on_item, n_overlap, L = ctx.cfg
+        sv = ctx.saved_tensors
+        user, item, label, Su, Si, Tu, Ti, w_out, b_out = sv[:9]
+        params = sv[9:]
+        ws, bs, wt, bt, hs = (list(params[k * L:(k + 1) * L]) for k in range(5))
+        g = grad_loss.reshape(-1)[:1].contiguous().float()
+        dsts, rets = [], []
+        for t in (Su, Si, Tu, Ti):
+            d, r = _grad_dst(t)
+            dsts.append(d)
+            rets.append(r)
+        grads = dict(ws=[torch.zeros_like(w) for w in ws], bs=[torch.zeros_like(b) for b in bs],
+                     wt=[torch.zeros_like(w) for w in wt], bt=[torch.zeros_like(b) for b in bt],
+                     h=[torch.zeros_like(h) for h in hs], w_out=torch.zeros_like(w_out), b_out=torch.zeros_like(b_out))
+        _conet_call(want, mask_on_item, n_overlap, user, item, label, (Su, Si, Tu, Ti), w_out, b_out, ws, bs, wt, bt, hs, True, g,
+                    dsts, grads, False)
+        return (None,) * 7 + tuple(rets) + (grads['w_out'], grads['b_out']) + tuple(grads['ws']) + tuple(grads['bs']) + \
+            tuple(grads['wt']) + tuple(grads['bt']) + tuple(grads['h'])
+
+
+def conet_tower_loss(want, mask_on_item, n_overlap, user, item, label, tabs, w_out, b_out, ws, bs, wt, bt, hs):
+    Su, Si, Tu, Ti = tabs
+    return ConetTowerLoss.apply(want, mask_on_item, n_overlap, user, item, label, len(ws), Su, Si, Tu, Ti, w_out, b_out,
+                                *ws, *bs, *wt, *bt, *hs)

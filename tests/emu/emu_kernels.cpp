@@ -4,6 +4,7 @@
 #define XDR_EMU 1
 #include "../../recbole-cdr_b200/csrc/fused_mlp.cu"
 #include "../../recbole-cdr_b200/csrc/tc_mlp.cu"
+#include "../../recbole-cdr_b200/csrc/tc_conet.cu"
 
 #include <cstdarg>
 
@@ -87,6 +88,27 @@ int emu_tc_mlp_supported(int n_layers, const int* dims) {
   MlpArgs a{};
   if (!tc_stack_ok(n_layers, dims, &a)) return 0;
   return tc_pick_tile_rows(a, 0) != 0;
+}
+
+int emu_conet_supported(int n_layers, const int* dims, int dim) { return conet_stack_ok(n_layers, dims, dim) ? 1 : 0; }
+
+int emu_conet_step(int n_layers, const int* dims, const float* const* Ws, const float* const* bs, const float* const* Wt,
+                   const float* const* bt, const float* const* H, float* const* dWs, float* const* dbs, float* const* dWt,
+                   float* const* dbt, float* const* dH, const float* w_out, const float* b_out, float* dw_out, float* db_out,
+                   int want, const float* Su, const float* Si, const float* Tu, const float* Ti, int64_t n_u, int64_t n_i,
+                   int dim, const int64_t* user, const int64_t* item, const float* label, int64_t batch, int mask_on_item,
+                   int64_t n_overlap, int backward, const float* grad_loss, float scale, float* dSu, float* dSi, float* dTu,
+                   float* dTi, float* dz1, float* prob, float* out8, void* ws, int32_t* oob) {
+  ConetArgs a{};
+  const int rc = conet_make_args(&a, n_layers, dims, Ws, bs, Wt, bt, H, dWs, dbs, dWt, dbt, dH, w_out, b_out, dw_out, db_out,
+                                 want, Su, Si, Tu, Ti, n_u, n_i, dim, user, item, label, batch, mask_on_item, n_overlap,
+                                 backward, grad_loss, scale, dSu, dSi, dTu, dTi, dz1, prob, out8, ws, oob);
+  if (rc != XDR_OK) return rc;
+  const size_t smem = (size_t)conet_smem_layout(n_layers, a.dims).total * sizeof(float);
+  const int64_t n_tiles = (batch + kCnTR - 1) / kCnTR;
+  const unsigned grid = (unsigned)std::min<int64_t>(g_sms, n_tiles);
+  emu::launch(grid, kTcThreads, smem, [&] { tc_conet_kernel(a, Workspace(ws)); });
+  return 0;
 }
 
 }  // extern "C"

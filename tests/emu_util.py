@@ -101,3 +101,38 @@ def mlp_step(impl, dims, Ws, bs, hidden_act, in_mode, head, tabs, idx_u, idx_i, 
         raise RuntimeError(f'emu_mlp_step rc={rc}: {L.emu_last_error().decode()}')
     assert not ws[:64].any(), 'kernel left the workspace ticket dirty'
     return dict(loss=float(out8[0]), dW=dWs, db=dbs, dtabs=dt, prob=prob, oob=int(oob[0]))
+
+
+def conet_step(dims, P, want, tabs, user, item, label, mask_on_item, n_overlap, backward=True, grad_loss=1.0, scale=1.0):
+    """tc_conet_kernel under the emulator.  ``P``: dict of lists ws, bs, wt, bt, h and out_w [1, d], out_b [1] of the wanted
+    tower; ``tabs``: (Su, Si, Tu, Ti).  Returns dict(loss, prob, d<name> ...)."""
+    L = lib()
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    Su, Si, Tu, Ti = map(f32, tabs)
+    nl = len(P['ws'])
+    lists = {k: [f32(x) for x in P[k]] for k in ('ws', 'bs', 'wt', 'bt', 'h')}
+    grads = {k: [np.zeros_like(x) for x in v] for k, v in lists.items()}
+    ow, ob = f32(P['out_w']), f32(P['out_b'])
+    dow, dob = np.zeros_like(ow), np.zeros_like(ob)
+    dt = [np.zeros_like(t) for t in (Su, Si, Tu, Ti)]
+    user = np.ascontiguousarray(user, dtype=np.int64)
+    item = np.ascontiguousarray(item, dtype=np.int64)
+    label = f32(label)
+    B = user.size
+    dz1 = np.full((B, 2 * dims[1]), np.nan, dtype=np.float32)
+    prob = np.zeros(B, dtype=np.float32)
+    out8 = np.zeros(8, dtype=np.float32)
+    g = np.array([grad_loss], dtype=np.float32)
+    ws, oob = workspace(), np.zeros(1, dtype=np.int32)
+    darr = (ctypes.c_int * len(dims))(*[int(d) for d in dims])
+    rc = L.emu_conet_step(
+        ctypes.c_int(nl), darr, ptr_array(lists['ws']), ptr_array(lists['bs']), ptr_array(lists['wt']), ptr_array(lists['bt']),
+        ptr_array(lists['h']), ptr_array(grads['ws']), ptr_array(grads['bs']), ptr_array(grads['wt']), ptr_array(grads['bt']),
+        ptr_array(grads['h']), p(ow), p(ob), p(dow), p(dob), ctypes.c_int(want), p(Su), p(Si), p(Tu), p(Ti),
+        ctypes.c_int64(Su.shape[0]), ctypes.c_int64(Si.shape[0]), ctypes.c_int(Su.shape[1]), p(user), p(item), p(label),
+        ctypes.c_int64(B), ctypes.c_int(1 if mask_on_item else 0), ctypes.c_int64(n_overlap), ctypes.c_int(1 if backward else 0),
+        p(g), ctypes.c_float(scale), p(dt[0]), p(dt[1]), p(dt[2]), p(dt[3]), p(dz1), p(prob), p(out8), p(ws), p(oob))
+    if rc != 0:
+        raise RuntimeError(f'emu_conet_step rc={rc}: {L.emu_last_error().decode()}')
+    assert not ws[:64].any(), 'kernel left the workspace ticket dirty'
+    return dict(loss=float(out8[0]), prob=prob, grads=grads, dout_w=dow, dout_b=dob, dtabs=dt, oob=int(oob[0]))

@@ -42,6 +42,50 @@ def test_python_prototypes_match_header():
         assert len(argtypes) == decl[name], f'{name}: header has {decl[name]} args, binding has {len(argtypes)}'
 
 
+def declared_types():
+    """{name: [kind per argument]} with kind in int / i64 / f32 / size / u64 / u32 / ptr, parsed from include/xdr.h."""
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    out = {}
+    for m in re.finditer(r'XDR_API\s+[\w\s\*]+?\b(xdr_\w+)\s*\(([^;]*?)\)\s*;', src, flags=re.S):
+        args = m.group(2).strip()
+        kinds = []
+        if args not in ('', 'void'):
+            for a in args.split(','):
+                a = ' '.join(a.split())
+                if '*' in a or 'xdr_stream_t' in a:
+                    kinds.append('ptr')
+                elif 'int64_t' in a and 'uint' not in a:
+                    kinds.append('i64')
+                elif 'uint64_t' in a:
+                    kinds.append('u64')
+                elif 'uint32_t' in a:
+                    kinds.append('u32')
+                elif 'size_t' in a:
+                    kinds.append('size')
+                elif 'float' in a:
+                    kinds.append('f32')
+                elif re.match(r'(const )?int\b', a):
+                    kinds.append('int')
+                else:
+                    raise AssertionError(f'{m.group(1)}: unparsed argument {a!r}')
+        out[m.group(1)] = kinds
+    return out
+
+
+def test_python_prototype_types_match_header():
+    """Same width and class per argument: a c_int where the header says int64_t would corrupt the call silently."""
+    from recbole_cdr_b200 import _lib
+    kind_of = {ctypes.c_int: 'int', ctypes.c_int64: 'i64', ctypes.c_float: 'f32', ctypes.c_size_t: 'size',
+               ctypes.c_uint64: 'u64', ctypes.c_uint32: 'u32', ctypes.c_void_p: 'ptr', ctypes.c_char_p: 'ptr'}
+    decl = declared_types()
+    for name, (_, argtypes) in _lib.PROTOTYPES.items():
+        got = ['ptr' if t not in kind_of else kind_of[t] for t in argtypes]
+        # size_t and uint64_t are the same class on this ABI
+        norm = lambda ks: ['u64' if k == 'size' else k for k in ks]
+        assert norm(got) == norm(decl[name]), f'{name}: header {decl[name]} vs binding {got}'
+
+
 def test_version_and_workspace():
     from recbole_cdr_b200 import _lib
     assert _lib.version() == 100

@@ -63,3 +63,62 @@ def test_dtcdr_tc_engine():
     batch = cuda_batch(g)
     check_loss_and_grads(m, g, batch, grad_rtol=2e-4, grad_atol=2e-6)
     torch.testing.assert_close(m.predict(batch).cpu(), g.t('predict'), rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ fused CoNet tower pass (tc_conet.cu)
+@pytest.mark.parametrize('tag', ['users', 'items'])
+def test_conet_fused_tower_kernel(tag):
+    from recbole_cdr_b200.model.cross_domain_recommender.conet import CoNet
+    g = Golden(f'conet_{tag}')
+    m = build(CoNet, g, dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8], xdr_fused_conet=True))
+    assert m._fused_ok()
+    check_loss_and_grads(m, g, cuda_batch(g), grad_rtol=2e-4, grad_atol=2e-6)
+
+
+@pytest.mark.parametrize('batch,dim,hidden,want', [(1, 32, [16], 0), (63, 32, [32, 16, 8], 1), (1000, 64, [64, 32, 16, 8], 0),
+                                                   (16384, 128, [64, 32, 16, 8], 1)])
+def test_conet_fused_matches_oracle(batch, dim, hidden, want):
+    """One tower pass (loss, probabilities via the loss, every gradient) against the oracle at sizes up to config #3's."""
+    gen = torch.Generator().manual_seed(5)
+    n_u, n_i, n_ov = 5000, 3000, 2500
+    names = ('source_user', 'source_item', 'target_user', 'target_item')
+    tabs = {k: rand_table(n_u if 'user' in k else n_i, dim, 300 + j, 0.3) for j, k in enumerate(names)}
+    dims = [2 * dim] + list(hidden)
+    mk = lambda a, b, s=0.25: torch.randn(b, a, generator=gen) * s
+    P = dict(ws=[mk(a, b) for a, b in zip(dims[:-1], dims[1:])], wt=[mk(a, b) for a, b in zip(dims[:-1], dims[1:])],
+             h=[mk(a, b) for a, b in zip(dims[:-1], dims[1:])],
+             bs=[torch.randn(b, generator=gen) * 0.1 for b in dims[1:]], bt=[torch.randn(b, generator=gen) * 0.1 for b in dims[1:]],
+             out_s_w=mk(dims[-1], 1, 0.5), out_s_b=torch.randn(1, generator=gen) * 0.1,
+             out_t_w=mk(dims[-1], 1, 0.5), out_t_b=torch.randn(1, generator=gen) * 0.1)
+    user, item = rand_ids(batch, n_u, 7, 1.3), rand_ids(batch, n_i, 8)
+    label = (torch.rand(batch, generator=gen) < 0.5).float()
+    lt = {k: v.clone().requires_grad_(True) for k, v in tabs.items()}
+    lp = {k: ([x.clone().requires_grad_(True) for x in v] if isinstance(v, list) else v.clone().requires_grad_(True))
+          for k, v in P.items()}
+    ps, pt = O.conet_towers(lt, user, item, lp, True, n_ov)
+    ref = O.bce_loss(ps if want == 0 else pt, label)
+    ref.backward()
+    ct = {k: v.to(dev()).requires_grad_(True) for k, v in tabs.items()}
+    cp = {k: ([x.to(dev()).requires_grad_(True) for x in v] if isinstance(v, list) else v.to(dev()).requires_grad_(True))
+          for k, v in P.items()}
+    sfx = 's' if want == 0 else 't'
+    assert ops().conet_fused_supported(dims, dim)
+    loss = ops().conet_tower_loss(want, False, n_ov, user.to(dev()), item.to(dev()), label.to(dev()),
+                                  tuple(ct[k] for k in names), cp[f'out_{sfx}_w'], cp[f'out_{sfx}_b'], cp['ws'], cp['bs'],
+                                  cp['wt'], cp['bt'], cp['h'])
+    torch.testing.assert_close(loss.cpu(), ref.detach(), rtol=LOSS_RTOL, atol=0)
+    loss.backward()
+
+    def chk(got, want_t, nm):
+        w = torch.zeros_like(got) if want_t.grad is None else want_t.grad
+        atol = max(1e-7, 1e-4 * w.abs().max().item())
+        torch.testing.assert_close(got.grad.cpu() if got.grad is not None else torch.zeros_like(w), w, rtol=2e-4, atol=atol,
+                                   msg=lambda s: f'{nm}: {s}')
+
+    for k in names:
+        chk(ct[k], lt[k], k)
+    for key in ('ws', 'bs', 'wt', 'bt', 'h'):
+        for l in range(len(hidden)):
+            chk(cp[key][l], lp[key][l], f'{key}[{l}]')
+    chk(cp[f'out_{sfx}_w'], lp[f'out_{sfx}_w'], 'out_w')
+    chk(cp[f'out_{sfx}_b'], lp[f'out_{sfx}_b'], 'out_b')

@@ -136,3 +136,67 @@ def conet_step(dims, P, want, tabs, user, item, label, mask_on_item, n_overlap, 
         raise RuntimeError(f'emu_conet_step rc={rc}: {L.emu_last_error().decode()}')
     assert not ws[:64].any(), 'kernel left the workspace ticket dirty'
     return dict(loss=float(out8[0]), prob=prob, grads=grads, dout_w=dow, dout_b=dob, dtabs=dt, oob=int(oob[0]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Running the PYTHON side (recbole_cdr_b200.ops autograd functions, the drop-in model classes) on CPU tensors: every libxdr
+# entry point that has an ``emu_xdr_*`` twin in the emulator library is redirected to it; anything else raises.
+# ---------------------------------------------------------------------------------------------------------------------------
+import contextlib
+
+
+@contextlib.contextmanager
+def patched_ops(sms=3, seed=0):
+    """Context manager: ``recbole_cdr_b200.ops`` / ``_lib`` call into the emulator with CPU tensors (test use only)."""
+    import torch
+    from recbole_cdr_b200 import _lib as xl
+    from recbole_cdr_b200 import ops
+    L = lib()
+    config(sms, seed)
+    ws_cache = {}
+
+    def emu_fn(name):
+        try:
+            fn = getattr(L, 'emu_' + name)
+        except AttributeError:
+            raise RuntimeError(f'{name} has no emulator twin: this path needs a GPU')
+        res, args = xl.PROTOTYPES[name]
+        fn.restype, fn.argtypes = res, args
+        return fn
+
+    def call(name, *args):
+        rc = emu_fn(name)(*args)
+        if rc != 0:
+            raise xl.XdrError(f'{name} failed under the emulator (status {rc}): {L.emu_last_error().decode()}')
+
+    def req_f32(t, name):
+        if t.dtype != torch.float32:
+            raise TypeError(f'{name} must be float32, got {t.dtype}')
+        if not t.is_contiguous():
+            raise ValueError(f'{name} must be contiguous')
+
+    def ids(t, name):
+        if t.dtype != torch.int64:
+            raise TypeError(f'{name} must be int64 (torch.LongTensor), got {t.dtype}')
+        return t.contiguous()
+
+    def workspace(device):
+        if 'ws' not in ws_cache:
+            ws_cache['ws'] = torch.zeros(WS_BYTES, dtype=torch.uint8)
+        return ws_cache['ws']
+
+    class LibProxy:
+        """stands in for the ctypes handle ``_lib._lib`` (only the *_supported probes are called through it)"""
+
+        def __getattr__(self, name):
+            return emu_fn(name)
+
+    saved = dict(call=ops.call, req=ops._require_cuda_f32, ids=ops._ids, stream=ops.cur_stream, ws=xl.workspace, handle=xl._lib)
+    ops.call, ops._require_cuda_f32, ops._ids, ops.cur_stream = call, req_f32, ids, (lambda: None)
+    xl.workspace, xl._lib = workspace, LibProxy()
+    try:
+        yield ops
+    finally:
+        ops.call, ops._require_cuda_f32, ops._ids, ops.cur_stream = saved['call'], saved['req'], saved['ids'], saved['stream']
+        xl.workspace, xl._lib = saved['ws'], saved['handle']
+        config(4, 0)

@@ -110,7 +110,7 @@ def test_conet_fused_matches_oracle(batch, dim, hidden, want):
     loss.backward()
 
     def chk(got, want_t, nm):
-        w = torch.zeros_like(got) if want_t.grad is None else want_t.grad
+        w = torch.zeros_like(got).cpu() if want_t.grad is None else want_t.grad
         atol = max(1e-7, 1e-4 * w.abs().max().item())
         torch.testing.assert_close(got.grad.cpu() if got.grad is not None else torch.zeros_like(w), w, rtol=2e-4, atol=atol,
                                    msg=lambda s: f'{nm}: {s}')

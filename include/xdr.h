@@ -215,6 +215,26 @@ XDR_API int xdr_tc_conet_step(int n_layers, const int* dims_host, const float* c
                               const float* grad_loss, float scale, float* dSu, float* dSi, float* dTu, float* dTi,
                               float* dz1_scratch, float* prob, float* out8, void* ws, int32_t* oob, xdr_stream_t stream);
 
+/* ---- F1: row-sparse optimizer step over the rows a batch touched ------------------------------------------------------------
+ * Replaces optimizer.zero_grad() + optimizer.step() of recbole Trainer._train_epoch [recbole-1.0.1] for an embedding table
+ * (`learner` sgd / adagrad / sparse_adam of Trainer._build_optimizer): G is a dense [n_rows, dim] gradient table that is zero
+ * outside the rows the step kernels scatter-added into; ids [n] are the batch's ids for this table (duplicates allowed).
+ * The first visitor of a row in this call (atomicMax on stamp[row] with step_id) updates W and the state rows from the row's
+ * summed gradient and writes the gradient row back to zero.  stamp [n_rows] int32 starts at 0; step_id must be >= 1 and
+ * strictly larger than in every earlier call on the same stamp table.
+ *   XDR_OPT_SGD        w -= lr g                                                (torch.optim.SGD, no momentum / weight decay)
+ *   XDR_OPT_ADAGRAD    S1 += g g;  w -= lr g / (sqrt(S1) + eps)                 (torch.optim.Adagrad, lr_decay 0 -- identical
+ *                                                                               to the dense optimizer: a zero gradient is a no-op)
+ *   XDR_OPT_LAZY_ADAM  S1 += (1-b1)(g-S1);  S2 += (1-b2)(g g-S2);
+ *                      w -= lr sqrt(1-b2^t)/(1-b1^t) S1 / (sqrt(S2) + eps)      (torch.optim.SparseAdam; t = adam_t >= 1)
+ * beta1/beta2 are doubles: torch forms (1 - beta) and the bias corrections in double before rounding to fp32.               */
+#define XDR_OPT_SGD 0
+#define XDR_OPT_ADAGRAD 1
+#define XDR_OPT_LAZY_ADAM 2
+XDR_API int xdr_sparse_optim_rows(int kind, float* W, float* G, float* S1, float* S2, int32_t* stamp, const int64_t* ids,
+                                  int64_t n, int64_t n_rows, int dim, int step_id, int64_t adam_t, float lr, float eps,
+                                  double beta1, double beta2, int32_t* oob, xdr_stream_t stream);
+
 /* ---- A6: EMCDR predict tail: select mapped vs. target row, then dot ------------------------------------------
  * Replaces the torch.where + mul + sum of EMCDR.predict, OVERLAP/BOTH phase (emcdr.py:191-205):
  *   e = (sel_ids[b] < n_overlap) ? mapped[b, :] : tgt_tab[sel_ids[b], :];   score[b] = e . other_tab[other_ids[b], :]

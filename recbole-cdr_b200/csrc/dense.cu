@@ -359,7 +359,7 @@ int xdr_dense_fwd(const float* X, const float* W, const float* bias, const float
   XDR_REQUIRE((X2 == nullptr) == (W2 == nullptr), "xdr_dense_fwd: X2 and W2 must be given together");
   XDR_REQUIRE(act >= XDR_ACT_NONE && act <= XDR_ACT_SIGMOID, "xdr_dense_fwd: bad act %d", act);
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
-  dense_fwd_kernel<<<grid, kDenseThreads, 0, (cudaStream_t)stream>>>(X, W, bias, X2, W2, mask_ids, mask_lt, act, Y, M, N, K);
+  XDR_LAUNCH((dense_fwd_kernel), grid, kDenseThreads, 0, (cudaStream_t)stream, X, W, bias, X2, W2, mask_ids, mask_lt, act, Y, M, N, K);
   XDR_LAUNCH_OK();
   return XDR_OK;
 }
@@ -368,7 +368,7 @@ int xdr_act_bwd(const float* Y, const float* dY, int act, float* dZ, int64_t cou
   XDR_REQUIRE(count >= 0, "xdr_act_bwd: negative count");
   if (count == 0) return XDR_OK;
   XDR_REQUIRE(Y && dY && dZ, "xdr_act_bwd: null pointer");
-  act_bwd_kernel<<<ew_grid(count, 256), 256, 0, (cudaStream_t)stream>>>(Y, dY, act, dZ, count);
+  XDR_LAUNCH((act_bwd_kernel), ew_grid(count, 256), 256, 0, (cudaStream_t)stream, Y, dY, act, dZ, count);
   XDR_LAUNCH_OK();
   return XDR_OK;
 }
@@ -379,7 +379,7 @@ int xdr_dense_bwd_input(const float* dZ, const float* W, const int64_t* mask_ids
   if (M == 0) return XDR_OK;
   XDR_REQUIRE(dZ && W && dX, "xdr_dense_bwd_input: null pointer");
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((K + BN - 1) / BN));
-  dense_bwd_input_kernel<<<grid, kDenseThreads, 0, (cudaStream_t)stream>>>(dZ, W, mask_ids, mask_lt, dX, M, N, K, accumulate);
+  XDR_LAUNCH((dense_bwd_input_kernel), grid, kDenseThreads, 0, (cudaStream_t)stream, dZ, W, mask_ids, mask_lt, dX, M, N, K, accumulate);
   XDR_LAUNCH_OK();
   return XDR_OK;
 }
@@ -390,7 +390,7 @@ int xdr_dense_bwd_weight(const float* dZ, const float* X, const int64_t* mask_id
   if (M == 0) return XDR_OK;
   XDR_REQUIRE(dZ && X && dW, "xdr_dense_bwd_weight: null pointer");
   dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)((K + BN - 1) / BN), (unsigned)((M + kChunkM - 1) / kChunkM));
-  dense_bwd_weight_kernel<<<grid, kDenseThreads, 0, (cudaStream_t)stream>>>(dZ, X, mask_ids, mask_lt, dW, db, M, N, K);
+  XDR_LAUNCH((dense_bwd_weight_kernel), grid, kDenseThreads, 0, (cudaStream_t)stream, dZ, X, mask_ids, mask_lt, dW, db, M, N, K);
   XDR_LAUNCH_OK();
   return XDR_OK;
 }
@@ -403,7 +403,7 @@ int xdr_mse_rows_fwd(const float* Y, const float* tgt_tab, int64_t n_rows, int d
   XDR_REQUIRE(aligned16(Y) && aligned16(tgt_tab), "xdr_mse_rows_fwd: 16-byte alignment");
   const int nv = dim / 4;
   const int grid = ew_grid(n_idx * kLanesPerRow, 256);
-  XDR_DISPATCH_VEC(nv, (mse_rows_fwd_kernel<VEC><<<grid, 256, 0, (cudaStream_t)stream>>>(Y, tgt_tab, n_rows, nv, idx, n_idx,
+  XDR_DISPATCH_VEC(nv, (XDR_LAUNCH((mse_rows_fwd_kernel<VEC>), grid, 256, 0, (cudaStream_t)stream, Y, tgt_tab, n_rows, nv, idx, n_idx,
                                                                                          out8, Workspace(ws), oob)));
   XDR_LAUNCH_OK();
   return XDR_OK;
@@ -417,7 +417,7 @@ int xdr_mse_rows_bwd(const float* Y, const float* tgt_tab, int64_t n_rows, int d
   XDR_REQUIRE(aligned16(Y) && aligned16(tgt_tab) && aligned16(dY) && aligned16(tgt_dst), "xdr_mse_rows_bwd: alignment");
   const int nv = dim / 4;
   const int grid = ew_grid(n_idx * kLanesPerRow, 256);
-  XDR_DISPATCH_VEC(nv, (mse_rows_bwd_kernel<VEC><<<grid, 256, 0, (cudaStream_t)stream>>>(Y, tgt_tab, n_rows, nv, idx, n_idx,
+  XDR_DISPATCH_VEC(nv, (XDR_LAUNCH((mse_rows_bwd_kernel<VEC>), grid, 256, 0, (cudaStream_t)stream, Y, tgt_tab, n_rows, nv, idx, n_idx,
                                                                                          grad_loss, scale, dY, tgt_dst)));
   XDR_LAUNCH_OK();
   return XDR_OK;
@@ -427,7 +427,7 @@ int xdr_bce_logit_fwd(const float* logit, const float* label, int64_t count, flo
                       xdr_stream_t stream) {
   XDR_REQUIRE(count > 0, "xdr_bce_logit_fwd: count must be positive");
   XDR_REQUIRE(logit && label && prob && out8 && ws, "xdr_bce_logit_fwd: null pointer");
-  bce_logit_fwd_kernel<<<ew_grid(count, 256), 256, 0, (cudaStream_t)stream>>>(logit, label, count, prob, out8, Workspace(ws));
+  XDR_LAUNCH((bce_logit_fwd_kernel), ew_grid(count, 256), 256, 0, (cudaStream_t)stream, logit, label, count, prob, out8, Workspace(ws));
   XDR_LAUNCH_OK();
   return XDR_OK;
 }
@@ -436,7 +436,7 @@ int xdr_bce_logit_bwd(const float* prob, const float* label, int64_t count, cons
                       xdr_stream_t stream) {
   XDR_REQUIRE(count > 0, "xdr_bce_logit_bwd: count must be positive");
   XDR_REQUIRE(prob && label && dlogit, "xdr_bce_logit_bwd: null pointer");
-  bce_logit_bwd_kernel<<<ew_grid(count, 256), 256, 0, (cudaStream_t)stream>>>(prob, label, count, grad_loss, dlogit);
+  XDR_LAUNCH((bce_logit_bwd_kernel), ew_grid(count, 256), 256, 0, (cudaStream_t)stream, prob, label, count, grad_loss, dlogit);
   XDR_LAUNCH_OK();
   return XDR_OK;
 }
@@ -451,7 +451,7 @@ int xdr_select_dot(const float* mapped, const float* tgt_tab, int64_t n_sel_rows
   XDR_REQUIRE(aligned16(mapped) && aligned16(tgt_tab) && aligned16(other_tab), "xdr_select_dot: 16-byte alignment");
   const int nv = dim / 4;
   const int grid = ew_grid(batch * kLanesPerRow, 256);
-  XDR_DISPATCH_VEC(nv, (select_dot_kernel<VEC><<<grid, 256, 0, (cudaStream_t)stream>>>(
+  XDR_DISPATCH_VEC(nv, (XDR_LAUNCH((select_dot_kernel<VEC>), grid, 256, 0, (cudaStream_t)stream, 
                            mapped, tgt_tab, n_sel_rows, sel_ids, n_overlap, other_tab, n_other_rows, other_ids, nv, batch,
                            score, oob)));
   XDR_LAUNCH_OK();

@@ -325,7 +325,6 @@ static bool pick_tile_rows(MlpArgs* a) {
   return false;
 }
 
-#ifndef XDR_EMU
 template <int E0, int E1, int E2>
 static int launch_mlp(const MlpArgs& a, void* ws, cudaStream_t s) {
   const int kTileRows = a.tile_rows;
@@ -335,15 +334,12 @@ static int launch_mlp(const MlpArgs& a, void* ws, cudaStream_t s) {
   const int64_t n_tiles = (a.batch + kTileRows - 1) / kTileRows;
   int grid = sm_count();
   if (grid > n_tiles) grid = (int)n_tiles;
-  kern<<<grid, kMlpThreads, smem, s>>>(a, Workspace(ws));
+  XDR_LAUNCH((kern), grid, kMlpThreads, smem, s, a, Workspace(ws));
   return XDR_OK;
 }
 
-#endif  // !XDR_EMU
-
 }  // namespace xdr
 
-#ifndef XDR_EMU
 using namespace xdr;
 
 extern "C" {
@@ -412,4 +408,3 @@ int xdr_fused_mlp_step(int n_layers, const int* dims_host, const float* const* W
 }
 
 }  // extern "C"
-#endif  // !XDR_EMU

@@ -206,7 +206,7 @@ int xdr_gather_rows(const float* table, int64_t n_rows, int dim, const int64_t* 
   XDR_REQUIRE(aligned16(table) && aligned16(out), "xdr_gather_rows: table/out must be 16-byte aligned");
   const int nv = dim / 4;
   cudaStream_t s = (cudaStream_t)stream;
-  XDR_DISPATCH_VEC(nv, (gather_rows_kernel<VEC><<<grid_for_rows(n_idx), kThreads, 0, s>>>(table, n_rows, nv, idx, n_idx,
+  XDR_DISPATCH_VEC(nv, (XDR_LAUNCH((gather_rows_kernel<VEC>), grid_for_rows(n_idx), kThreads, 0, s, table, n_rows, nv, idx, n_idx,
                                                                                           out, out_ld, oob)));
   XDR_LAUNCH_OK();
   return XDR_OK;
@@ -237,7 +237,7 @@ int xdr_gather_rows_sharded(const float* const* shards, int n_shards, int64_t n_
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  XDR_DISPATCH_VEC(nv, (gather_rows_sharded_kernel<VEC><<<(int)blocks, kThreads, 0, s>>>(t, log2g, n_rows, nv, idx, n_idx, idx_batch,
+  XDR_DISPATCH_VEC(nv, (XDR_LAUNCH((gather_rows_sharded_kernel<VEC>), (int)blocks, kThreads, 0, s, t, log2g, n_rows, nv, idx, n_idx, idx_batch,
                                                                                          idx_step_stride, out, out_ld, oob)));
   XDR_LAUNCH_OK();
   return XDR_OK;
@@ -253,7 +253,7 @@ int xdr_scatter_add_rows(float* dst, int64_t n_rows, int dim, const int64_t* idx
   XDR_REQUIRE(aligned16(dst) && aligned16(rows), "xdr_scatter_add_rows: dst/rows must be 16-byte aligned");
   const int nv = dim / 4;
   cudaStream_t s = (cudaStream_t)stream;
-  XDR_DISPATCH_VEC(nv, (scatter_add_rows_kernel<VEC><<<grid_for_rows(n_idx), kThreads, 0, s>>>(
+  XDR_DISPATCH_VEC(nv, (XDR_LAUNCH((scatter_add_rows_kernel<VEC>), grid_for_rows(n_idx), kThreads, 0, s, 
                            dst, n_rows, nv, idx, n_idx, rows, rows_ld, scale, oob)));
   XDR_LAUNCH_OK();
   return XDR_OK;
@@ -269,7 +269,7 @@ int xdr_gather_max2(const float* table_a, const float* table_b, int64_t n_rows, 
   XDR_REQUIRE(aligned16(table_a) && aligned16(table_b) && aligned16(out), "xdr_gather_max2: 16-byte alignment");
   const int nv = dim / 4;
   cudaStream_t s = (cudaStream_t)stream;
-  XDR_DISPATCH_VEC(nv, (gather_max2_kernel<VEC><<<grid_for_rows(n_idx), kThreads, 0, s>>>(table_a, table_b, n_rows, nv,
+  XDR_DISPATCH_VEC(nv, (XDR_LAUNCH((gather_max2_kernel<VEC>), grid_for_rows(n_idx), kThreads, 0, s, table_a, table_b, n_rows, nv,
                                                                                           idx, n_idx, out, out_ld, oob)));
   XDR_LAUNCH_OK();
   return XDR_OK;
@@ -287,7 +287,7 @@ int xdr_scatter_max2_bwd(const float* table_a, const float* table_b, int64_t n_r
               "xdr_scatter_max2_bwd: 16-byte alignment");
   const int nv = dim / 4;
   cudaStream_t s = (cudaStream_t)stream;
-  XDR_DISPATCH_VEC(nv, (scatter_max2_bwd_kernel<VEC><<<grid_for_rows(n_idx), kThreads, 0, s>>>(
+  XDR_DISPATCH_VEC(nv, (XDR_LAUNCH((scatter_max2_bwd_kernel<VEC>), grid_for_rows(n_idx), kThreads, 0, s, 
                            table_a, table_b, n_rows, nv, idx, n_idx, grad_rows, grad_ld, scale, dst_a, dst_b, oob)));
   XDR_LAUNCH_OK();
   return XDR_OK;

@@ -277,16 +277,16 @@ static int spmm_launch(const char* fn, const int64_t* work_row, const int64_t* w
   cudaStream_t s = (cudaStream_t)stream;
   if (n_split_rows > 0) {
     XDR_REQUIRE(split_rows, "%s: null split_rows", fn);
-    XDR_DISPATCH_VEC(nv, (zero_rows_kernel<VEC><<<rows_grid(n_split_rows), kGThreads, 0, s>>>(split_rows, n_split_rows, nv, S)));
+    XDR_DISPATCH_VEC(nv, (XDR_LAUNCH((zero_rows_kernel<VEC>), rows_grid(n_split_rows), kGThreads, 0, s, split_rows, n_split_rows, nv, S)));
     XDR_LAUNCH_OK();
   }
   if (xs != nullptr) {
     const Shards sh = *xs;
-    XDR_DISPATCH_VEC(nv, (spmm_work_kernel<VEC, true><<<rows_grid(n_work), kGThreads, 0, s>>>(
+    XDR_DISPATCH_VEC(nv, (XDR_LAUNCH((spmm_work_kernel<VEC, true>), rows_grid(n_work), kGThreads, 0, s, 
                              work_row, work_beg, work_end, work_split, n_work, col, val, nullptr, sh, log2g, nv, S)));
   } else {
     const Shards sh{};
-    XDR_DISPATCH_VEC(nv, (spmm_work_kernel<VEC, false><<<rows_grid(n_work), kGThreads, 0, s>>>(
+    XDR_DISPATCH_VEC(nv, (XDR_LAUNCH((spmm_work_kernel<VEC, false>), rows_grid(n_work), kGThreads, 0, s, 
                              work_row, work_beg, work_end, work_split, n_work, col, val, X, sh, 0, nv, S)));
   }
   XDR_LAUNCH_OK();
@@ -329,7 +329,7 @@ int xdr_prop_elementwise(const float* A, const float* B, const float* C, float* 
   int64_t blocks = (n4 + kGThreads - 1) / kGThreads;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  prop_elementwise_kernel<<<(int)blocks, kGThreads, 0, (cudaStream_t)stream>>>(
+  XDR_LAUNCH((prop_elementwise_kernel), (int)blocks, kGThreads, 0, (cudaStream_t)stream, 
       reinterpret_cast<const float4*>(A), reinterpret_cast<const float4*>(B), reinterpret_cast<const float4*>(C),
       reinterpret_cast<float4*>(out), n4, mode);
   XDR_LAUNCH_OK();
@@ -357,7 +357,7 @@ int xdr_transfer_norm_fwd(const float* Ps, const float* Pt, int64_t n_users, int
   XDR_REQUIRE(aligned16(Ps) && aligned16(Pt) && aligned16(Es) && aligned16(Et) && aligned16(Ns) && aligned16(Nt),
               "xdr_transfer_norm_fwd: 16-byte alignment");
   TransferArgs t{n_users, n_items, n_ov_users, n_ov_items, lam_s, lam_t, deg_s, deg_t, dim / 4};
-  XDR_DISPATCH_VEC(t.nv, (transfer_norm_fwd_kernel<VEC><<<rows_grid(n_users + n_items), kGThreads, 0, (cudaStream_t)stream>>>(
+  XDR_DISPATCH_VEC(t.nv, (XDR_LAUNCH((transfer_norm_fwd_kernel<VEC>), rows_grid(n_users + n_items), kGThreads, 0, (cudaStream_t)stream, 
                              t, Ps, Pt, Es, Et, Ns, Nt, n_ld)));
   XDR_LAUNCH_OK();
   return XDR_OK;
@@ -373,7 +373,7 @@ int xdr_transfer_norm_bwd(const float* Es, const float* Et, const float* dNs, co
   XDR_REQUIRE(Es && Et && dNs && dNt && dPs && dPt, "xdr_transfer_norm_bwd: null pointer");
   XDR_REQUIRE((dEs2 == nullptr) == (dEt2 == nullptr), "xdr_transfer_norm_bwd: dEs2 and dEt2 go together");
   TransferArgs t{n_users, n_items, n_ov_users, n_ov_items, lam_s, lam_t, deg_s, deg_t, dim / 4};
-  XDR_DISPATCH_VEC(t.nv, (transfer_norm_bwd_kernel<VEC><<<rows_grid(n_users + n_items), kGThreads, 0, (cudaStream_t)stream>>>(
+  XDR_DISPATCH_VEC(t.nv, (XDR_LAUNCH((transfer_norm_bwd_kernel<VEC>), rows_grid(n_users + n_items), kGThreads, 0, (cudaStream_t)stream, 
                              t, Es, Et, dNs, dNt, n_ld, dEs2, dEt2, dPs, dPt)));
   XDR_LAUNCH_OK();
   return XDR_OK;

@@ -88,7 +88,7 @@ int xdr_neg_sample_uniform(const int64_t* key_ids, int64_t n_keys, int num, cons
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  neg_sample_uniform_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+  XDR_LAUNCH((neg_sample_uniform_kernel), (int)blocks, 256, 0, (cudaStream_t)stream, 
       key_ids, n_keys, total, used_rowptr, used_col, n_rows, n_overlap, n_gap, (uint64_t)n_valid, seed, stream_id,
       max_attempts, out, status);
   XDR_LAUNCH_OK();

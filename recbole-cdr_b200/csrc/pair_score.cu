@@ -245,7 +245,7 @@ int xdr_bpr_fwd(const float* user_tab, const float* item_tab, int64_t n_users, i
   if (rc) return rc;
   XDR_REQUIRE(ws, "xdr_bpr_fwd: null workspace");
   cudaStream_t s = (cudaStream_t)stream;
-  XDR_DISPATCH_VEC(a.nv, (score_fwd_kernel<VEC, true><<<grid_for_batch(batch), kThreads, 0, s>>>(a, Workspace(ws), oob)));
+  XDR_DISPATCH_VEC(a.nv, (XDR_LAUNCH((score_fwd_kernel<VEC, true>), grid_for_batch(batch), kThreads, 0, s, a, Workspace(ws), oob)));
   XDR_LAUNCH_OK();
   return XDR_OK;
 }
@@ -262,7 +262,7 @@ int xdr_bpr_bwd(const float* user_tab, const float* item_tab, int64_t n_users, i
   int rc = check_common("xdr_bpr_bwd", a, dim, true, true);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  XDR_DISPATCH_VEC(a.nv, (score_bwd_kernel<VEC, true><<<grid_for_batch(batch), kThreads, 0, s>>>(a)));
+  XDR_DISPATCH_VEC(a.nv, (XDR_LAUNCH((score_bwd_kernel<VEC, true>), grid_for_batch(batch), kThreads, 0, s, a)));
   XDR_LAUNCH_OK();
   return XDR_OK;
 }
@@ -278,7 +278,7 @@ int xdr_point_fwd(const float* user_tab, const float* item_tab, int64_t n_users,
   if (rc) return rc;
   XDR_REQUIRE(ws, "xdr_point_fwd: null workspace");
   cudaStream_t s = (cudaStream_t)stream;
-  XDR_DISPATCH_VEC(a.nv, (score_fwd_kernel<VEC, false><<<grid_for_batch(batch), kThreads, 0, s>>>(a, Workspace(ws), oob)));
+  XDR_DISPATCH_VEC(a.nv, (XDR_LAUNCH((score_fwd_kernel<VEC, false>), grid_for_batch(batch), kThreads, 0, s, a, Workspace(ws), oob)));
   XDR_LAUNCH_OK();
   return XDR_OK;
 }
@@ -295,7 +295,7 @@ int xdr_point_bwd(const float* user_tab, const float* item_tab, int64_t n_users,
   int rc = check_common("xdr_point_bwd", a, dim, false, true);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  XDR_DISPATCH_VEC(a.nv, (score_bwd_kernel<VEC, false><<<grid_for_batch(batch), kThreads, 0, s>>>(a)));
+  XDR_DISPATCH_VEC(a.nv, (XDR_LAUNCH((score_bwd_kernel<VEC, false>), grid_for_batch(batch), kThreads, 0, s, a)));
   XDR_LAUNCH_OK();
   return XDR_OK;
 }

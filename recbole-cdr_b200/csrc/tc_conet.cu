@@ -533,7 +533,6 @@ static int conet_make_args(ConetArgs* out, int n_layers, const int* dims_host, c
 
 }  // namespace xdr
 
-#ifndef XDR_EMU
 using namespace xdr;
 
 extern "C" {
@@ -562,10 +561,9 @@ int xdr_tc_conet_step(int n_layers, const int* dims_host, const float* const* Ws
   const int64_t n_tiles = (batch + kCnTR - 1) / kCnTR;
   int grid = sm_count();
   if (grid > n_tiles) grid = (int)n_tiles;
-  tc_conet_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(a, Workspace(ws));
+  XDR_LAUNCH((tc_conet_kernel), grid, kTcThreads, smem, (cudaStream_t)stream, a, Workspace(ws));
   XDR_LAUNCH_OK();
   return XDR_OK;
 }
 
 }  // extern "C"
-#endif  // !XDR_EMU

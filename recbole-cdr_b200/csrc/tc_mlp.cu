@@ -304,7 +304,6 @@ static bool tc_stack_ok(int n_layers, const int* dims, MlpArgs* a) {
   return true;
 }
 
-#ifndef XDR_EMU
 template <int TR>
 static int launch_tc(const MlpArgs& a, void* ws, cudaStream_t s) {
   const size_t smem = tc_smem_bytes(a, TR);
@@ -313,15 +312,12 @@ static int launch_tc(const MlpArgs& a, void* ws, cudaStream_t s) {
   const int64_t n_tiles = (a.batch + TR - 1) / TR;
   int grid = sm_count();
   if (grid > n_tiles) grid = (int)n_tiles;
-  kern<<<grid, kTcThreads, smem, s>>>(a, Workspace(ws));
+  XDR_LAUNCH((kern), grid, kTcThreads, smem, s, a, Workspace(ws));
   return XDR_OK;
 }
 
-#endif  // !XDR_EMU
-
 }  // namespace xdr
 
-#ifndef XDR_EMU
 using namespace xdr;
 
 extern "C" {
@@ -374,4 +370,3 @@ int xdr_tc_mlp_step(int n_layers, const int* dims_host, const float* const* W_ho
 }
 
 }  // extern "C"
-#endif  // !XDR_EMU

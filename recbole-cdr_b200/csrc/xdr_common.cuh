@@ -220,6 +220,14 @@ __device__ __forceinline__ void grid_reduce_last_block(float (&v)[NV], Workspace
 
 #endif  // __CUDACC__ || XDR_EMU
 
+// Kernel launch.  CUDA: kernel<<<grid, block, smem, stream>>>(args...).  Emulator (tests/emu, -DXDR_EMU): the CTAs run one
+// after another on the CPU.  `kernel` is passed parenthesised so that template-ids with commas survive the preprocessor.
+#ifdef XDR_EMU
+#define XDR_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch(grid, block, smem, [&] { kernel(__VA_ARGS__); })
+#else
+#define XDR_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 // Dynamic shared memory of the CTA as `type* name` (CUDA: the extern __shared__ array; emulator: the CTA's heap block).
 #ifdef XDR_EMU
 #define XDR_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dyn_smem())

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('XDR_LIB', os.path.join(_HERE, 'lib', 'libxdr.so'))
 
 c_i64, c_int, c_f32, c_vp, c_sz = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+c_f64 = ctypes.c_double
 
 # name -> (restype, argtypes); argument order is exactly that of include/xdr.h
 PROTOTYPES = {
@@ -71,11 +72,14 @@ PROTOTYPES = {
     'xdr_tc_conet_step': (c_int, [c_int, c_vp] + [c_vp] * 10 + [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp,
                                   c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_vp, c_f32,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'xdr_sparse_optim_rows': (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_i64, c_f32,
+                                      c_f32, c_f64, c_f64, c_vp, c_vp]),
     'xdr_select_dot': (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
 }
 
 LOSS_MSE, LOSS_BCE_SIGMOID, LOSS_NONE = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+OPT_SGD, OPT_ADAGRAD, OPT_LAZY_ADAM = 0, 1, 2
 ACT_BY_NAME = {None: ACT_NONE, 'none': ACT_NONE, 'relu': ACT_RELU, 'tanh': ACT_TANH, 'sigmoid': ACT_SIGMOID}
 
 

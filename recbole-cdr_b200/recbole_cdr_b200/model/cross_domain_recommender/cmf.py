@@ -49,6 +49,12 @@ class CMF(CrossDomainRecommender):
                                 interaction[self.TARGET_LABEL], _lib.LOSS_BCE_SIGMOID, self.gamma)
         return loss_s * self.alpha + loss_t * (1 - self.alpha)
 
+    def touched_rows(self, interaction):
+        """(table parameter, ids) pairs read by ``calculate_loss`` (for trainer.RowSparseOptimizer)."""
+        ut, it = self.user_embedding.weight, self.item_embedding.weight
+        return [(ut, interaction[self.SOURCE_USER_ID]), (ut, interaction[self.TARGET_USER_ID]),
+                (it, interaction[self.SOURCE_ITEM_ID]), (it, interaction[self.TARGET_ITEM_ID])]
+
     def fused_step_spec(self):
         """Two weighted domain terms on the shared tables (cmf.py:81-99): the trainer's persistent multi-step path runs
         them as two launches per chunk, with loss weights alpha and 1 - alpha folded into the SGD scale."""

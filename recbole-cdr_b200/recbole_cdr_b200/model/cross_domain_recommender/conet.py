@@ -109,6 +109,18 @@ class CoNet(CrossDomainRecommender):
     def target_forward(self, user, item):
         return torch.sigmoid(self._towers(user, item, 'target'))
 
+    def touched_rows(self, interaction):
+        """(table parameter, ids) pairs read by ``calculate_loss``: every tower pass gathers all four tables
+        (for trainer.RowSparseOptimizer)."""
+        users = [interaction[self.SOURCE_USER_ID], interaction[self.TARGET_USER_ID]]
+        items = [interaction[self.SOURCE_ITEM_ID], interaction[self.TARGET_ITEM_ID]]
+        rows = []
+        for tab in (self.source_user_embedding.weight, self.target_user_embedding.weight):
+            rows += [(tab, u) for u in users]
+        for tab in (self.source_item_embedding.weight, self.target_item_embedding.weight):
+            rows += [(tab, i) for i in items]
+        return rows
+
     def calculate_loss(self, interaction):
         """BCE(source tower, source batch) + BCE(target tower, target batch) + sum_l ||H_l||_F (conet.py:183-203)."""
         if self._fused_ok():

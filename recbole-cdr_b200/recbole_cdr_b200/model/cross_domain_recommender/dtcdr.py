@@ -77,6 +77,18 @@ class DTCDR(CrossDomainRecommender):
     def neumf_forward(self, user, item, domain='source'):
         return torch.sigmoid(self._logit(user, item, domain))
 
+    def touched_rows(self, interaction):
+        """(table parameter, ids) pairs read by ``calculate_loss``: every tower pass gathers all four tables
+        (for trainer.RowSparseOptimizer)."""
+        users = [interaction[self.SOURCE_USER_ID], interaction[self.TARGET_USER_ID]]
+        items = [interaction[self.SOURCE_ITEM_ID], interaction[self.TARGET_ITEM_ID]]
+        rows = []
+        for tab in (self.source_user_embedding.weight, self.target_user_embedding.weight):
+            rows += [(tab, u) for u in users]
+        for tab in (self.source_item_embedding.weight, self.target_item_embedding.weight):
+            rows += [(tab, i) for i in items]
+        return rows
+
     def calculate_loss(self, interaction):
         """alpha*BCE_s + (1-alpha)*BCE_t (dtcdr.py:177-191)."""
         if self._fused_ok():

@@ -113,6 +113,23 @@ class EMCDR(CrossDomainRecommender):
         neg = self.SOURCE_NEG_ITEM_ID if domain == 'source' else self.TARGET_NEG_ITEM_ID
         return ops.bpr_loss(ut, it, interaction[uid], interaction[iid], interaction[neg], self.reg_weight, self.bpr_gamma)
 
+    def touched_rows(self, interaction):
+        """(table parameter, ids) pairs whose rows ``calculate_loss(interaction)`` reads in the current phase -- what a
+        row-sparse optimizer has to visit (trainer.RowSparseOptimizer)."""
+        if self.phase == 'OVERLAP':
+            idx = interaction[self.OVERLAP_ID].reshape(-1)
+            if self.mode == 'overlap_users':
+                return [(self.source_user_embedding.weight, idx), (self.target_user_embedding.weight, idx)]
+            return [(self.source_item_embedding.weight, idx), (self.target_item_embedding.weight, idx)]
+        domain = 'source' if self.phase == 'SOURCE' else 'target'
+        ut, it = self._tables(domain)
+        uid = self.SOURCE_USER_ID if domain == 'source' else self.TARGET_USER_ID
+        iid = self.SOURCE_ITEM_ID if domain == 'source' else self.TARGET_ITEM_ID
+        rows = [(ut, interaction[uid]), (it, interaction[iid])]
+        if self.latent_factor_model != 'MF':
+            rows.append((it, interaction[self.SOURCE_NEG_ITEM_ID if domain == 'source' else self.TARGET_NEG_ITEM_ID]))
+        return rows
+
     def calculate_source_loss(self, interaction):
         return self._domain_loss(interaction, 'source')
 

@@ -700,3 +700,32 @@ def conet_tower_loss(want, mask_on_item, n_overlap, user, item, label, tabs, w_o
     Su, Si, Tu, Ti = tabs
     return ConetTowerLoss.apply(want, mask_on_item, n_overlap, user, item, label, len(ws), Su, Si, Tu, Ti, w_out, b_out,
                                 *ws, *bs, *wt, *bt, *hs)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# F1: row-sparse optimizer step (SGD / Adagrad / lazy Adam) over the rows a batch touched
+# ------------------------------------------------------------------------------------------------------------------
+
+def sparse_optim_rows(kind, table, grad, ids, stamp, step_id, lr, *, state1=None, state2=None, adam_t=1, eps=1e-8,
+                      beta1=0.9, beta2=0.999):
+    """In place: for every distinct id, update ``table[id]`` (and the state rows) from ``grad[id]`` and zero ``grad[id]``.
+    Replaces ``optimizer.zero_grad()`` + ``optimizer.step()`` of recbole ``Trainer._train_epoch`` for an embedding table
+    (torch.optim.SGD / Adagrad / SparseAdam semantics, see xdr.h).  ``stamp``: int32 ``[n_rows]`` zeros at start;
+    ``step_id`` >= 1 and strictly increasing per call on the same ``stamp``."""
+    _require_cuda_f32(table, 'table')
+    _require_cuda_f32(grad, 'grad table')
+    if grad.shape != table.shape:
+        raise ValueError('grad table must have the shape of the weight table')
+    for st, nm in ((state1, 'state1'), (state2, 'state2')):
+        if st is not None:
+            _require_cuda_f32(st, nm)
+            if st.shape != table.shape:
+                raise ValueError(f'{nm} must have the shape of the weight table')
+    if stamp.dtype != torch.int32 or stamp.numel() != table.shape[0] or not stamp.is_contiguous():
+        raise ValueError('stamp must be a contiguous int32 [n_rows] tensor')
+    ids = _ids(ids, 'ids').reshape(-1)
+    call('xdr_sparse_optim_rows', int(kind), ptr(table), ptr(grad), ptr(state1), ptr(state2), ptr(stamp), ptr(ids),
+         ids.numel(), table.shape[0], table.shape[1], int(step_id), int(adam_t), float(lr), float(eps), float(beta1),
+         float(beta2), _oob(table.device), cur_stream())
+    _maybe_check(table.device)
+    return table

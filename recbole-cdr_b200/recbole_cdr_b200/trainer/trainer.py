@@ -22,6 +22,7 @@ import torch
 
 from .. import _lib, ops
 from ..utils import train_mode2state
+from .row_optim import RowSparseOptimizer
 
 
 class FusedStepRunner:
@@ -121,6 +122,14 @@ class CrossDomainTrainer(object):
         self.split_valid_flag = config['source_split'] if 'source_split' in config else False
         self.fused_steps = int(config['xdr_fused_steps']) if 'xdr_fused_steps' in config else 0
         self.valid_metric_bigger = config['valid_metric_bigger'] if 'valid_metric_bigger' in config else True
+        # row-sparse optimizer for the embedding tables (section 8 F1): 'sgd' | 'adagrad' | 'lazy_adam'; the dense learner keeps
+        # the remaining (MLP) parameters.  Needs a model with ``touched_rows(interaction)``.
+        self.row_optimizer_kind = config['xdr_row_optimizer'] if 'xdr_row_optimizer' in config else None
+        self.row_optimizer = None
+        if self.row_optimizer_kind:
+            if not hasattr(model, 'touched_rows'):
+                raise ValueError(f'{type(model).__name__} does not expose touched_rows(): no row-sparse optimizer for it')
+            self.row_optimizer = RowSparseOptimizer(self.row_optimizer_kind, lr=self.learning_rate)
         self.optimizer = self._build_optimizer()
         self.train_loss_dict = dict()
         self.best_valid_score, self.best_valid_result = -np.inf, None
@@ -129,6 +138,10 @@ class CrossDomainTrainer(object):
     def _build_optimizer(self):
         """recbole Trainer._build_optimizer [recbole-1.0.1]: dense torch optimizers keyed by ``learner``."""
         params = self.model.parameters()
+        if self.row_optimizer is not None:   # the tables belong to the row-sparse optimizer
+            params = [p for n, p in self.model.named_parameters() if not n.endswith('_embedding.weight')]
+            if not params:
+                return None
         lr, wd = self.learning_rate, self.weight_decay
         table = {'adam': torch.optim.Adam, 'sgd': torch.optim.SGD, 'adagrad': torch.optim.Adagrad,
                  'rmsprop': torch.optim.RMSprop}
@@ -156,6 +169,8 @@ class CrossDomainTrainer(object):
         self.model.train()
         loss_func = loss_func or self.model.calculate_loss
         total = None
+        if self.row_optimizer is not None:
+            return self._train_epoch_row_sparse(train_data, loss_func)
         for interaction in train_data:
             interaction = interaction.to(self.device)
             self.optimizer.zero_grad()
@@ -171,6 +186,35 @@ class CrossDomainTrainer(object):
             return 0.0
         self._check_nan(total)
         return float(total.item())  # one device->host read per epoch
+
+    def _train_epoch_row_sparse(self, train_data, loss_func):
+        """The reference loop with the table part of ``zero_grad`` / ``step`` replaced by one row-sparse kernel per table:
+        ``backward()`` scatter-adds into ``table.grad`` ('inplace' table-gradient mode), the optimizer visits the batch's
+        rows only and leaves ``table.grad`` zero again.  Dense parameters keep the configured torch learner."""
+        if self.clip_grad_norm:
+            raise ValueError('clip_grad_norm needs the dense gradient norm: not available with xdr_row_optimizer')
+        prev_mode = ops.get_table_grad_mode()
+        ops.set_table_grad_mode('inplace')
+        total = None
+        try:
+            for interaction in train_data:
+                interaction = interaction.to(self.device)
+                if self.optimizer is not None:
+                    self.optimizer.zero_grad()
+                losses = loss_func(interaction)
+                loss = sum(losses) if isinstance(losses, tuple) else losses
+                loss = loss.sum()
+                total = loss.detach() if total is None else total + loss.detach()
+                loss.backward()
+                if self.optimizer is not None:
+                    self.optimizer.step()
+                self.row_optimizer.step(self.model.touched_rows(interaction))
+        finally:
+            ops.set_table_grad_mode(prev_mode)
+        if total is None:
+            return 0.0
+        self._check_nan(total)
+        return float(total.item())
 
     def _fused_spec(self):
         spec_fn = getattr(self.model, 'fused_step_spec', None)

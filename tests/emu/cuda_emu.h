@@ -27,7 +27,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __align__(x) alignas(x)
+#define __align__(x) __attribute__((aligned(x)))
 #define __shared__ static
 
 struct alignas(16) float4 { float x, y, z, w; };
@@ -35,7 +35,20 @@ struct alignas(8) float2 { float x, y; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct uint3_emu { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+// the sliver of the CUDA runtime API that the host side of the kernel files touches
 typedef void* cudaStream_t;
+typedef int cudaError_t;
+constexpr cudaError_t cudaSuccess = 0;
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 
 namespace emu {
 
@@ -121,14 +134,17 @@ inline void fiber_entry() {
   swapcontext(&s.fibers[s.current].ctx, &s.sched);
 }
 
-// Runs `body` once per thread of every CTA of a 1-D grid; CTAs execute one after another in blockIdx order.
-inline void launch(unsigned grid, unsigned block, size_t smem_bytes, std::function<void()> body) {
+// Runs `body` once per thread of every CTA of the grid; CTAs execute one after another (x fastest), 1-D blocks only.
+inline void launch(dim3 grid, dim3 block3, size_t smem_bytes, std::function<void()> body) {
   State& s = st();
+  if (block3.y != 1 || block3.z != 1) { std::fprintf(stderr, "cuda_emu: only 1-D blocks are emulated\n"); std::abort(); }
+  const unsigned block = block3.x;
   s.body = std::move(body);
-  gridDim = {grid, 1, 1};
+  gridDim = {grid.x, grid.y, grid.z};
   blockDim = {block, 1, 1};
-  for (unsigned b = 0; b < grid; ++b) {
-    blockIdx = {b, 0, 0};
+  const unsigned n_ctas = grid.x * grid.y * grid.z;
+  for (unsigned b = 0; b < n_ctas; ++b) {
+    blockIdx = {b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y)};
     s.nthreads = block;
     s.cta_arrived = 0;
     const unsigned nwarps = (block + 31) / 32;
@@ -253,6 +269,14 @@ template <typename T>
 inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 template <typename T>
 inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
+template <typename T>
+inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <typename T>
+inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
+  return (unsigned long long)(((unsigned __int128)a * b) >> 64);
+}
 inline float __uint_as_float(uint32_t u) { return emu::as_float(u); }
 inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }

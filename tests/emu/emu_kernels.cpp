@@ -1,10 +1,13 @@
-// emu_kernels.cpp -- TEST INFRASTRUCTURE ONLY.  Compiles kernel sources of libxdr with g++ against the CTA emulator
-// (cuda_emu.h) and exports plain C entry points that take HOST pointers, so `pytest -m "not gpu"` can run the kernels'
-// logic on the CPU and compare it with the oracle.  Built on demand by tests/emu_util.py into tests/emu/_build/.
+// emu_kernels.cpp -- TEST INFRASTRUCTURE ONLY.  The kernel sources of libxdr compile with g++ against the CTA emulator
+// (cuda_emu.h, -DXDR_EMU): every .cu listed in tests/emu_util.py becomes a translation unit of tests/emu/_build/
+// libxdr_emu.so, whose xdr_* entry points are the REAL host entry points (argument checks, launch geometry) with
+// XDR_LAUNCH running the CTAs on the CPU -- they take host pointers.  This file adds the two host hooks the library expects
+// (set_error, sm_count) and a few direct kernel drivers (forced tile sizes) for tests/test_emu_*.py.
 #define XDR_EMU 1
 #include "../../recbole-cdr_b200/csrc/fused_mlp.cu"
 #include "../../recbole-cdr_b200/csrc/tc_mlp.cu"
 #include "../../recbole-cdr_b200/csrc/tc_conet.cu"
+#include "../../recbole-cdr_b200/csrc/sparse_optim.cu"
 
 #include <cstdarg>
 
@@ -109,49 +112,6 @@ int emu_conet_step(int n_layers, const int* dims, const float* const* Ws, const 
   const unsigned grid = (unsigned)std::min<int64_t>(g_sms, n_tiles);
   emu::launch(grid, kTcThreads, smem, [&] { tc_conet_kernel(a, Workspace(ws)); });
   return 0;
-}
-
-// ---- entry points with EXACTLY the signatures of include/xdr.h (stream ignored): tests/emu_util.py patches
-// recbole_cdr_b200.ops to call these with CPU tensors, so the Python glue runs end to end without a GPU ------------------
-int emu_xdr_tc_mlp_supported(int n_layers, const int* dims) { return emu_tc_mlp_supported(n_layers, dims); }
-int emu_xdr_fused_mlp_supported(int n_layers, const int* dims) {
-  if (n_layers < 1 || n_layers > kMaxLayers) return 0;
-  MlpArgs a{};
-  a.n_layers = n_layers;
-  for (int l = 0; l <= n_layers; ++l) a.dims[l] = dims[l];
-  return pick_tile_rows(&a) ? 1 : 0;
-}
-int emu_xdr_tc_mlp_step(int n_layers, const int* dims, const float* const* W, const float* const* b, float* const* dW,
-                        float* const* db, int hidden_act, int in_mode, int head, const float* Au, const float* Bu,
-                        const float* Ai, const float* Bi, const float* T, int64_t n_u, int64_t n_i, int dim,
-                        const int64_t* idx_u, const int64_t* idx_i, const float* label, int64_t batch, int backward,
-                        const float* grad_loss, float scale, float* dAu, float* dBu, float* dAi, float* dBi, float* dT,
-                        float* prob, float* out8, void* ws, int32_t* oob, void* /*stream*/) {
-  return emu_mlp_step(1, n_layers, dims, W, b, dW, db, hidden_act, in_mode, head, Au, Bu, Ai, Bi, T, n_u, n_i, dim, idx_u,
-                      idx_i, label, batch, backward, grad_loss, scale, dAu, dBu, dAi, dBi, dT, prob, out8, ws, oob, 0);
-}
-int emu_xdr_fused_mlp_step(int n_layers, const int* dims, const float* const* W, const float* const* b, float* const* dW,
-                           float* const* db, int hidden_act, int in_mode, int head, const float* Au, const float* Bu,
-                           const float* Ai, const float* Bi, const float* T, int64_t n_u, int64_t n_i, int dim,
-                           const int64_t* idx_u, const int64_t* idx_i, const float* label, int64_t batch, int backward,
-                           const float* grad_loss, float scale, float* dAu, float* dBu, float* dAi, float* dBi, float* dT,
-                           float* prob, float* out8, void* ws, int32_t* oob, void* /*stream*/) {
-  return emu_mlp_step(0, n_layers, dims, W, b, dW, db, hidden_act, in_mode, head, Au, Bu, Ai, Bi, T, n_u, n_i, dim, idx_u,
-                      idx_i, label, batch, backward, grad_loss, scale, dAu, dBu, dAi, dBi, dT, prob, out8, ws, oob, 0);
-}
-int emu_xdr_tc_conet_supported(int n_layers, const int* dims, int dim) { return emu_conet_supported(n_layers, dims, dim); }
-size_t emu_xdr_tc_conet_scratch_bytes(int64_t batch, int hidden0) { return (size_t)batch * 2 * hidden0 * sizeof(float); }
-int emu_xdr_tc_conet_step(int n_layers, const int* dims, const float* const* Ws, const float* const* bs,
-                          const float* const* Wt, const float* const* bt, const float* const* H, float* const* dWs,
-                          float* const* dbs, float* const* dWt, float* const* dbt, float* const* dH, const float* w_out,
-                          const float* b_out, float* dw_out, float* db_out, int want, const float* Su, const float* Si,
-                          const float* Tu, const float* Ti, int64_t n_u, int64_t n_i, int dim, const int64_t* user,
-                          const int64_t* item, const float* label, int64_t batch, int mask_on_item, int64_t n_overlap,
-                          int backward, const float* grad_loss, float scale, float* dSu, float* dSi, float* dTu, float* dTi,
-                          float* dz1, float* prob, float* out8, void* ws, int32_t* oob, void* /*stream*/) {
-  return emu_conet_step(n_layers, dims, Ws, bs, Wt, bt, H, dWs, dbs, dWt, dbt, dH, w_out, b_out, dw_out, db_out, want, Su, Si,
-                        Tu, Ti, n_u, n_i, dim, user, item, label, batch, mask_on_item, n_overlap, backward, grad_loss, scale,
-                        dSu, dSi, dTu, dTi, dz1, prob, out8, ws, oob);
 }
 
 }  // extern "C"

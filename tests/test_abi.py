@@ -63,6 +63,8 @@ def declared_types():
                     kinds.append('u32')
                 elif 'size_t' in a:
                     kinds.append('size')
+                elif 'double' in a:
+                    kinds.append('f64')
                 elif 'float' in a:
                     kinds.append('f32')
                 elif re.match(r'(const )?int\b', a):
@@ -77,7 +79,7 @@ def test_python_prototype_types_match_header():
     """Same width and class per argument: a c_int where the header says int64_t would corrupt the call silently."""
     from recbole_cdr_b200 import _lib
     kind_of = {ctypes.c_int: 'int', ctypes.c_int64: 'i64', ctypes.c_float: 'f32', ctypes.c_size_t: 'size',
-               ctypes.c_uint64: 'u64', ctypes.c_uint32: 'u32', ctypes.c_void_p: 'ptr', ctypes.c_char_p: 'ptr'}
+               ctypes.c_uint64: 'u64', ctypes.c_uint32: 'u32', ctypes.c_double: 'f64', ctypes.c_void_p: 'ptr', ctypes.c_char_p: 'ptr'}
     decl = declared_types()
     for name, (_, argtypes) in _lib.PROTOTYPES.items():
         got = ['ptr' if t not in kind_of else kind_of[t] for t in argtypes]

@@ -80,3 +80,104 @@ def test_unpatched_ops_still_refuse_cpu_tensors():
     from recbole_cdr_b200 import ops
     with pytest.raises(RuntimeError, match='CUDA'):
         ops.gather_rows_raw(torch.zeros(8, 64), torch.zeros(2, dtype=torch.int64))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The hardware-validated composed paths through the emulator: pins the emulator itself (the same kernels are parity-green
+# on a B200, tests/test_gpu_models.py) and keeps these paths checkable on CPU after every change.
+# ---------------------------------------------------------------------------------------------------------------------------
+EMCDR_CFG = dict(source_embedding_size=64, target_embedding_size=64, reg_weight=0.01, mlp_hidden_size=[128])
+
+
+@pytest.mark.parametrize('lfm', ['bpr', 'mf'])
+@pytest.mark.parametrize('phase', ['source', 'target'])
+def test_emcdr_rec_phases_composed(lfm, phase):
+    from recbole_cdr_b200.model.cross_domain_recommender.emcdr import EMCDR
+    g = Golden(f'emcdr_{lfm}_{phase}')
+    with emu_util.patched_ops():
+        m = build_cpu(EMCDR, g, dict(EMCDR_CFG, latent_factor_model=lfm.upper(), mapping_function='non_linear'))
+        m.set_phase(phase.upper())
+        batch = cpu_batch(g)
+        check(m, g, batch, grad_rtol=1e-4, grad_atol=2e-7)
+        torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('case,mf', [('non_linear', 'non_linear'), ('linear', 'linear'), ('items', 'non_linear')])
+def test_emcdr_map_phase_composed(case, mf):
+    from recbole_cdr_b200.model.cross_domain_recommender.emcdr import EMCDR
+    g = Golden(f'emcdr_map_{case}')
+    with emu_util.patched_ops():
+        m = build_cpu(EMCDR, g, dict(EMCDR_CFG, latent_factor_model='BPR', mapping_function=mf, xdr_fused_mlp=False))
+        m.set_phase('OVERLAP')
+        check(m, g, cpu_batch(g), grad_rtol=1e-4, grad_atol=1e-6)
+        pred = m.predict(cpu_batch(g, 'pbatch/'))
+        torch.testing.assert_close(pred, g.t('predict_overlap_phase'), rtol=1e-4, atol=1e-6)
+
+
+def test_cmf_composed():
+    from recbole_cdr_b200.model.cross_domain_recommender.cmf import CMF
+    g = Golden('cmf_both')
+    with emu_util.patched_ops():
+        m = build_cpu(CMF, g, {'embedding_size': 64, 'alpha': g.meta('alpha'), 'lambda': g.meta('lambda'),
+                               'gamma': g.meta('gamma')})
+        batch = cpu_batch(g)
+        check(m, g, batch, grad_rtol=1e-4, grad_atol=2e-7)
+        torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('tag', ['users', 'items'])
+def test_conet_composed(tag):
+    from recbole_cdr_b200.model.cross_domain_recommender.conet import CoNet
+    g = Golden(f'conet_{tag}')
+    with emu_util.patched_ops():
+        m = build_cpu(CoNet, g, dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8]))
+        batch = cpu_batch(g)
+        check(m, g, batch)
+        torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-4, atol=1e-6)
+
+
+def test_dtcdr_composed():
+    from recbole_cdr_b200.model.cross_domain_recommender.dtcdr import DTCDR
+    g = Golden('dtcdr_neumf')
+    with emu_util.patched_ops():
+        m = build_cpu(DTCDR, g, dict(embedding_size=64, mlp_hidden_size=[32, 16], dropout_prob=0.0, base_model='NeuMF',
+                                     alpha=g.meta('alpha'), xdr_fused_mlp=False))
+        batch = cpu_batch(g)
+        check(m, g, batch)
+        torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-4, atol=1e-6)
+
+
+def test_trainer_row_sparse_adagrad_follows_dense_torch_adagrad():
+    """CMF, three batches: tables stepped by the row-sparse kernel == tables stepped by dense torch.optim.Adagrad
+    (trainer._train_epoch_row_sparse; the CPU twin of the test in tests/test_gpu_unvalidated.py)."""
+    import numpy as np
+    from recbole_cdr_b200.data import Interaction
+    from recbole_cdr_b200.model.cross_domain_recommender.cmf import CMF
+    from recbole_cdr_b200.trainer import CrossDomainTrainer
+    ds = FakeDataset(1, 300, 280, 120, 200, 150)
+    rng = np.random.RandomState(0)
+    su, si = ds.valid_ids('source')
+    tu, ti = ds.valid_ids('target')
+    batches = []
+    for _ in range(3):
+        batches.append(Interaction({
+            'source_user_id': torch.from_numpy(rng.choice(su, 128)), 'source_item_id': torch.from_numpy(rng.choice(si, 128)),
+            'source_label': torch.from_numpy((rng.rand(128) < 0.5).astype(np.float32)),
+            'target_user_id': torch.from_numpy(rng.choice(tu, 128)), 'target_item_id': torch.from_numpy(rng.choice(ti, 128)),
+            'target_label': torch.from_numpy((rng.rand(128) < 0.5).astype(np.float32))}))
+    cfg = dict(embedding_size=64, alpha=0.3, gamma=0.1, learning_rate=0.05, weight_decay=0.0, train_modes=['BOTH'],
+               epoch_num=['1'], learner='adagrad', device='cpu')
+    cfg['lambda'] = 0.1
+    models = []
+    with emu_util.patched_ops():
+        for row_opt in (None, 'adagrad'):
+            torch.manual_seed(7)
+            c = base_config(**cfg)
+            if row_opt:
+                c['xdr_row_optimizer'] = row_opt
+            m = CMF(c, ds)
+            t = CrossDomainTrainer(c, m)
+            t._train_epoch(batches, 0)
+            models.append(m)
+    for (n1, p1), (_, p2) in zip(models[0].named_parameters(), models[1].named_parameters()):
+        torch.testing.assert_close(p2, p1, rtol=1e-4, atol=1e-6, msg=lambda s: f'{n1}: {s}')

@@ -122,3 +122,66 @@ def test_conet_fused_matches_oracle(batch, dim, hidden, want):
             chk(cp[key][l], lp[key][l], f'{key}[{l}]')
     chk(cp[f'out_{sfx}_w'], lp[f'out_{sfx}_w'], 'out_w')
     chk(cp[f'out_{sfx}_b'], lp[f'out_{sfx}_b'], 'out_b')
+
+
+# ------------------------------------------------------------------------------------------ row-sparse optimizers (sparse_optim.cu)
+@pytest.mark.parametrize('kind,name', [(0, 'sgd'), (1, 'adagrad'), (2, 'adam')])
+def test_sparse_optim_rows_matches_oracle(kind, name):
+    from oracle import optim_oracle as OO
+    rng = np.random.RandomState(3)
+    n, d, b = 5000, 64, 4096
+    w0 = (rng.randn(n, d) * 0.1).astype(np.float32)
+    w = torch.from_numpy(w0.copy()).to(dev())
+    stamp = torch.zeros(n, dtype=torch.int32, device=dev())
+    s1, s2 = torch.zeros_like(w), torch.zeros_like(w)
+    rw, rs, rm, rv = w0.copy(), np.zeros_like(w0), np.zeros_like(w0), np.zeros_like(w0)
+    for step in range(1, 4):
+        ids = np.minimum(rng.zipf(1.3, b) - 1, n - 1)
+        rows = (rng.randn(b, d) * 0.05).astype(np.float32)
+        g = np.zeros_like(w0)
+        np.add.at(g, ids, rows)
+        gd = torch.from_numpy(g.copy()).to(dev())
+        ops().sparse_optim_rows(kind, w, gd, torch.from_numpy(ids).to(dev()), stamp, step, 0.05,
+                                state1=s1 if kind else None, state2=s2 if kind == 2 else None, adam_t=step,
+                                eps=1e-10 if kind == 1 else 1e-8)
+        assert not gd.any().item(), 'gradient rows must be zero after the step'
+        if kind == 0:
+            rw = OO.sgd_step(rw, g, 0.05)
+        elif kind == 1:
+            rw, rs = OO.adagrad_step(rw, rs, g, 0.05)
+        else:
+            rw, rm, rv = OO.sparse_adam_step(rw, rm, rv, g, ids, step, 0.05)
+        np.testing.assert_allclose(w.cpu().numpy(), rw, rtol=1e-5, atol=1e-7, err_msg=name)
+
+
+def test_trainer_row_sparse_adagrad_follows_dense_torch_adagrad():
+    """CMF, three batches: tables stepped by the row-sparse kernel == tables stepped by dense torch.optim.Adagrad."""
+    from recbole_cdr_b200.data import Interaction
+    from recbole_cdr_b200.model.cross_domain_recommender.cmf import CMF
+    from recbole_cdr_b200.trainer import CrossDomainTrainer
+    ds = FakeDataset(1, 300, 280, 120, 200, 150)
+    rng = np.random.RandomState(0)
+    su, si = ds.valid_ids('source')
+    tu, ti = ds.valid_ids('target')
+    batches = []
+    for _ in range(3):
+        batches.append(Interaction({
+            'source_user_id': torch.from_numpy(rng.choice(su, 512)), 'source_item_id': torch.from_numpy(rng.choice(si, 512)),
+            'source_label': torch.from_numpy((rng.rand(512) < 0.5).astype(np.float32)),
+            'target_user_id': torch.from_numpy(rng.choice(tu, 512)), 'target_item_id': torch.from_numpy(rng.choice(ti, 512)),
+            'target_label': torch.from_numpy((rng.rand(512) < 0.5).astype(np.float32))}))
+    cfg = dict(embedding_size=64, alpha=0.3, gamma=0.1, learning_rate=0.05, weight_decay=0.0, train_modes=['BOTH'],
+               epoch_num=['1'], learner='adagrad')
+    cfg['lambda'] = 0.1
+    models = []
+    for row_opt in (None, 'adagrad'):
+        torch.manual_seed(7)
+        c = base_config(**cfg)
+        if row_opt:
+            c['xdr_row_optimizer'] = row_opt
+        m = CMF(c, ds).to('cuda')
+        t = CrossDomainTrainer(c, m)
+        t._train_epoch(batches, 0)
+        models.append(m)
+    for (n1, p1), (_, p2) in zip(models[0].named_parameters(), models[1].named_parameters()):
+        torch.testing.assert_close(p2, p1, rtol=1e-4, atol=1e-6, msg=lambda s: f'{n1}: {s}')

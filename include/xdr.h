@@ -235,6 +235,19 @@ XDR_API int xdr_sparse_optim_rows(int kind, float* W, float* G, float* S1, float
                                   int64_t n, int64_t n_rows, int dim, int step_id, int64_t adam_t, float lr, float eps,
                                   double beta1, double beta2, int32_t* oob, xdr_stream_t stream);
 
+/* ---- F2: full-sort scoring fused with history masking and top-k ---------------------------------------------------------------
+ * Replaces full_sort_predict's dense score matrix (emcdr.py:208-233, cmf.py:107-112: matmul(user_e, all_item_e^T)) together
+ * with what recbole's full-sort evaluation does to it next [recbole-1.0.1]: PAD column and each user's history set to -inf,
+ * torch.topk(k).  user_vecs [batch, dim]: the user-side vectors (gathered, and mapped where the model maps them);
+ * item_tab rows [first_item, n_items) are the candidates (first_item = 1 skips PAD); hist_ptr [batch + 1] / hist_ids: CSR of
+ * ASCENDING item ids to exclude per user (both NULL: no masking).  out_score / out_id [batch, k]: score descending, ties by
+ * ascending item id; users with fewer than k candidates are padded with (-inf, -1).  The [batch, n_items] matrix is never
+ * materialised; scores are 3xTF32 tensor-core dot products (fp32-equivalent).  dim % 8 == 0, k <= 128.                    */
+XDR_API size_t xdr_topk_workspace_bytes(int64_t batch, int k);
+XDR_API int xdr_full_sort_topk(const float* user_vecs, int64_t batch, const float* item_tab, int64_t n_items, int dim,
+                               int64_t first_item, const int64_t* hist_ptr, const int64_t* hist_ids, int k,
+                               float* out_score, int64_t* out_id, void* topk_ws, size_t topk_ws_bytes, xdr_stream_t stream);
+
 /* ---- A6: EMCDR predict tail: select mapped vs. target row, then dot ------------------------------------------
  * Replaces the torch.where + mul + sum of EMCDR.predict, OVERLAP/BOTH phase (emcdr.py:191-205):
  *   e = (sel_ids[b] < n_overlap) ? mapped[b, :] : tgt_tab[sel_ids[b], :];   score[b] = e . other_tab[other_ids[b], :]

@@ -199,9 +199,9 @@ class EMCDR(CrossDomainRecommender):
             return ops.select_dot(mapped, self.target_item_embedding.weight, item, self.overlapped_num_items,
                                   self.target_user_embedding.weight, user)
 
-    def full_sort_predict(self, interaction):
-        """emcdr.py:208-233.  Dense [B, D] x [D, n_items] scoring is outside the training hot path (SURVEY.md
-        section 8f rank 2): the user rows come from the xdr gather, the GEMM is a plain library matmul."""
+    def _full_sort_operands(self, interaction):
+        """(user-side vectors [B, D], candidate item rows [n, D]) of full_sort_predict for the current phase
+        (emcdr.py:208-233)."""
         with torch.no_grad():
             if self.phase == 'SOURCE':
                 user_e = ops.gather_rows_raw(self.source_user_embedding.weight, interaction[self.SOURCE_USER_ID])
@@ -220,4 +220,18 @@ class EMCDR(CrossDomainRecommender):
                     ov = self._apply_mapping(self.source_item_embedding.weight[:self.overlapped_num_items].contiguous())
                     all_item_e = torch.cat(
                         [ov, self.target_item_embedding.weight[self.overlapped_num_items:self.target_num_items]], dim=0)
+            return user_e, all_item_e
+
+    def full_sort_predict(self, interaction):
+        """emcdr.py:208-233: the dense [B, n_items] score matrix, flattened (kept for drop-in compatibility; the GEMM is
+        a plain library matmul).  Evaluation that only needs the best k items should call ``full_sort_topk``."""
+        with torch.no_grad():
+            user_e, all_item_e = self._full_sort_operands(interaction)
             return torch.matmul(user_e, all_item_e.transpose(0, 1)).view(-1)
+
+    def full_sort_topk(self, interaction, k, hist_ptr=None, hist_ids=None):
+        """Fused form of ``full_sort_predict`` + recbole's full-sort masking (PAD column, per-user history) + ``topk``:
+        one scoring kernel that never writes the [B, n_items] matrix.  Item positions are those of
+        ``full_sort_predict``'s columns.  Returns (scores [B, k], positions [B, k])."""
+        user_e, all_item_e = self._full_sort_operands(interaction)
+        return ops.full_sort_topk(user_e, all_item_e.contiguous(), k, first_item=1, hist_ptr=hist_ptr, hist_ids=hist_ids)

@@ -729,3 +729,35 @@ def sparse_optim_rows(kind, table, grad, ids, stamp, step_id, lr, *, state1=None
          float(beta2), _oob(table.device), cur_stream())
     _maybe_check(table.device)
     return table
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# F2: full-sort scoring + history mask + top-k without the [B, n_items] score matrix
+# ------------------------------------------------------------------------------------------------------------------
+
+def full_sort_topk(user_vecs, item_tab, k, n_items=None, first_item=1, hist_ptr=None, hist_ids=None):
+    """Top-``k`` items per user by ``user_vecs @ item_tab[first_item:n_items].T`` with each user's history excluded.
+
+    The fused form of ``full_sort_predict`` (emcdr.py:208-233, cmf.py:107-112) + recbole's full-sort masking + ``topk``.
+    ``hist_ptr`` ``[B + 1]`` / ``hist_ids``: int64 CSR of ascending item ids per user.  Returns ``(scores [B, k] fp32,
+    ids [B, k] int64)``, score descending, ties by ascending id, padded with ``(-inf, -1)``."""
+    with torch.no_grad():
+        user_vecs = user_vecs.contiguous()
+        _require_cuda_f32(user_vecs, 'user_vecs')
+        _require_cuda_f32(item_tab, 'item table')
+        B, D = user_vecs.shape
+        if item_tab.shape[1] != D:
+            raise ValueError('user vectors and item rows must have the same width')
+        n_items = item_tab.shape[0] if n_items is None else int(n_items)
+        if hist_ptr is not None:
+            hist_ptr, hist_ids = _ids(hist_ptr, 'hist_ptr'), _ids(hist_ids, 'hist_ids')
+            if hist_ptr.numel() != B + 1:
+                raise ValueError('hist_ptr must have batch + 1 entries')
+        dev = user_vecs.device
+        out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+        nbytes = _lib._lib.xdr_topk_workspace_bytes(B, int(k))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        call('xdr_full_sort_topk', ptr(user_vecs), B, ptr(item_tab), n_items, D, int(first_item), ptr(hist_ptr), ptr(hist_ids),
+             int(k), ptr(out_s), ptr(out_i), ptr(ws), nbytes, cur_stream())
+        return out_s, out_i

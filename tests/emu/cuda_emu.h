@@ -284,15 +284,15 @@ inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; 
 inline float __fdividef(float a, float b) { return a / b; }
 inline float __expf(float x) { return std::exp(x); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline unsigned __ballot_sync(unsigned, int pred) {
   const unsigned lane = threadIdx.x & 31;
+  emu::warp_slot(lane)[6] = pred ? 1u : 0u;
+  emu::warp_barrier();
   unsigned bits = 0;
-  for (unsigned l = 0; l < 32; ++l) {
-    // every lane contributes its predicate in turn (32 exchanges; emulation speed is irrelevant here)
-    const int p = emu::shfl_exchange(pred, l);
-    if (p) bits |= 1u << l;
-  }
-  (void)lane;
+  for (unsigned l = 0; l < 32; ++l)
+    if (emu::warp_slot(l)[6]) bits |= 1u << l;
+  emu::warp_barrier();
   return bits;
 }
 using std::max;

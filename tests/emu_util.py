@@ -19,7 +19,7 @@ _lib = None
 
 # translation units of the emulator library: the harness (which #includes the fused row-tile kernels it drives directly)
 # plus the kernel files that only need their real entry points
-SEPARATE_TUS = ['pair_score.cu', 'gather_scatter.cu', 'dense.cu', 'graph_prop.cu', 'neg_sample.cu']
+SEPARATE_TUS = ['pair_score.cu', 'gather_scatter.cu', 'dense.cu', 'graph_prop.cu', 'neg_sample.cu', 'topk_score.cu']
 
 
 def _deps():

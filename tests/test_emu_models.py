@@ -181,3 +181,37 @@ def test_trainer_row_sparse_adagrad_follows_dense_torch_adagrad():
             models.append(m)
     for (n1, p1), (_, p2) in zip(models[0].named_parameters(), models[1].named_parameters()):
         torch.testing.assert_close(p2, p1, rtol=1e-4, atol=1e-6, msg=lambda s: f'{n1}: {s}')
+
+
+def test_full_sort_topk_agrees_with_full_sort_predict():
+    """EMCDR (OVERLAP phase: mapped user vectors) and CMF: the fused top-k equals masking + topk of full_sort_predict."""
+    import numpy as np
+    from recbole_cdr_b200.data import Interaction
+    from recbole_cdr_b200.model.cross_domain_recommender.cmf import CMF
+    from recbole_cdr_b200.model.cross_domain_recommender.emcdr import EMCDR
+    with emu_util.patched_ops():
+        g = Golden('emcdr_map_non_linear')
+        m = build_cpu(EMCDR, g, dict(EMCDR_CFG, latent_factor_model='BPR', mapping_function='non_linear'))
+        m.set_phase('OVERLAP')
+        g2 = Golden('cmf_both')
+        m2 = build_cpu(CMF, g2, {'embedding_size': 64, 'alpha': g2.meta('alpha'), 'lambda': g2.meta('lambda'),
+                                 'gamma': g2.meta('gamma')})
+        for model in (m, m2):
+            users = torch.arange(1, 12)
+            inter = Interaction({'target_user_id': users})
+            full = model.full_sort_predict(inter).view(len(users), -1)
+            rng = np.random.RandomState(0)
+            ptr, ids = [0], []
+            for _ in users:
+                h = np.unique(rng.randint(1, full.shape[1], 9))
+                ids.append(h)
+                ptr.append(ptr[-1] + len(h))
+            hp, hi = torch.tensor(ptr), torch.from_numpy(np.concatenate(ids))
+            sc, pos = model.full_sort_topk(inter, 10, hp, hi)
+            ref = full.clone()
+            ref[:, 0] = -float('inf')
+            for u in range(len(users)):
+                ref[u, hi[hp[u]:hp[u + 1]]] = -float('inf')
+            rs, ri = torch.topk(ref, 10, dim=1)
+            torch.testing.assert_close(sc, rs, rtol=2e-5, atol=1e-6)
+            assert torch.equal(pos, ri)

@@ -1,0 +1,106 @@
+"""xdr_full_sort_topk (scoring + history mask + streaming top-k, topk_score.cu) through the CPU CTA emulator against the
+numpy oracle.  Logic only; the hardware counterpart is in tests/test_gpu_unvalidated.py."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import emu_util
+from oracle import topk_oracle as TO
+
+
+def run_emu(U, I, k, n_items=None, first_item=1, hist_ptr=None, hist_ids=None, sms=2, seed=0):
+    L = emu_util.lib()
+    emu_util.config(sms=sms, seed=seed)
+    U, I = np.ascontiguousarray(U, np.float32), np.ascontiguousarray(I, np.float32)
+    B, D = U.shape
+    n_items = I.shape[0] if n_items is None else n_items
+    out_s = np.zeros((B, k), np.float32)
+    out_i = np.zeros((B, k), np.int64)
+    L.xdr_topk_workspace_bytes.restype = ctypes.c_size_t
+    nbytes = L.xdr_topk_workspace_bytes(ctypes.c_int64(B), ctypes.c_int(k))
+    ws = np.zeros(nbytes + 16, np.uint8)
+    off = (-ws.ctypes.data) % 16
+    p = emu_util.p
+    rc = L.xdr_full_sort_topk(p(U), ctypes.c_int64(B), p(I), ctypes.c_int64(n_items), ctypes.c_int(D), ctypes.c_int64(first_item),
+                              p(hist_ptr), p(hist_ids), ctypes.c_int(k), p(out_s), p(out_i),
+                              ctypes.c_void_p(ws.ctypes.data + off), ctypes.c_size_t(nbytes), None)
+    emu_util.config(4, 0)
+    assert rc == 0, L.emu_last_error()
+    return out_s, out_i
+
+
+def make_hist(rng, B, n_items, max_len):
+    ptr, ids = [0], []
+    for _ in range(B):
+        h = np.unique(rng.randint(1, n_items, rng.randint(0, max_len + 1)))
+        ids.append(h)
+        ptr.append(ptr[-1] + len(h))
+    return np.asarray(ptr, np.int64), (np.concatenate(ids) if ids else np.zeros(0)).astype(np.int64)
+
+
+def check(U, I, k, out_s, out_i, n_items=None, first_item=1, hist_ptr=None, hist_ids=None):
+    full = TO.full_sort_scores(U, I, n_items)
+    ref_s, ref_i = TO.masked_topk(full, k, first_item, hist_ptr, hist_ids)
+    np.testing.assert_allclose(out_s, ref_s, rtol=2e-5, atol=1e-6)
+    B = U.shape[0]
+    for u in range(B):
+        got = out_i[u][out_i[u] >= 0]
+        assert len(got) == (ref_i[u] >= 0).sum()
+        assert len(np.unique(got)) == len(got) and (got >= first_item).all()
+        if hist_ptr is not None:
+            assert not np.isin(got, hist_ids[hist_ptr[u]:hist_ptr[u + 1]]).any(), 'a history item was returned'
+        np.testing.assert_allclose(full[u, got], out_s[u, :len(got)], rtol=2e-5, atol=1e-6)  # every id carries its score
+        # where neighbouring reference scores are clearly separated the ids must agree exactly
+        rs = ref_s[u, :len(got)]
+        gap = np.abs(np.diff(rs)) > 1e-4 * np.maximum(np.abs(rs[:-1]), 1e-3)
+        sep = np.concatenate([[True], gap]) & np.concatenate([gap, [True]])
+        np.testing.assert_array_equal(got[sep], ref_i[u, :len(got)][sep])
+
+
+@pytest.mark.parametrize('B,n_items,D,k,sms', [(5, 300, 64, 10, 1), (70, 1000, 64, 20, 2), (64, 130, 32, 100, 3),
+                                                (3, 50, 8, 128, 1), (130, 777, 128, 7, 4)])
+def test_topk_matches_oracle(B, n_items, D, k, sms):
+    rng = np.random.RandomState(B + n_items)
+    U = (rng.randn(B, D) * 0.3).astype(np.float32)
+    I = (rng.randn(n_items, D) * 0.3).astype(np.float32)
+    hist_ptr, hist_ids = make_hist(rng, B, n_items, 30)
+    out_s, out_i = run_emu(U, I, k, hist_ptr=hist_ptr, hist_ids=hist_ids, sms=sms)
+    check(U, I, k, out_s, out_i, hist_ptr=hist_ptr, hist_ids=hist_ids)
+
+
+def test_topk_ties_resolve_to_the_lower_id_and_short_lists_are_padded():
+    rng = np.random.RandomState(1)
+    D = 16
+    U = (rng.randn(4, D)).astype(np.float32)
+    I = np.zeros((40, D), np.float32)
+    I[1:] = rng.randn(1, D).astype(np.float32)          # every candidate item identical: all scores tie
+    out_s, out_i = run_emu(U, I, 8, sms=2)
+    for u in range(4):
+        np.testing.assert_array_equal(out_i[u], np.arange(1, 9))
+    # fewer candidates than k: history removes all but three items
+    hist_ptr = np.asarray([0, 36, 36, 36, 36], np.int64)
+    hist_ids = np.arange(4, 40).astype(np.int64)
+    out_s, out_i = run_emu(U, I, 8, hist_ptr=hist_ptr, hist_ids=hist_ids, sms=1)
+    np.testing.assert_array_equal(out_i[0], [1, 2, 3, -1, -1, -1, -1, -1])
+    assert np.isneginf(out_s[0, 3:]).all()
+
+
+def test_topk_without_history_and_with_n_items_prefix():
+    """full_sort_predict scores only the TARGET items: a prefix of the joint item table (emcdr.py:224-226)."""
+    rng = np.random.RandomState(2)
+    U = (rng.randn(20, 64) * 0.3).astype(np.float32)
+    I = (rng.randn(500, 64) * 0.3).astype(np.float32)
+    out_s, out_i = run_emu(U, I, 15, n_items=321, sms=3)
+    assert out_i.max() < 321
+    check(U, I, 15, out_s, out_i, n_items=321)
+
+
+def test_topk_is_schedule_independent():
+    rng = np.random.RandomState(3)
+    U = (rng.randn(66, 64) * 0.3).astype(np.float32)
+    I = (rng.randn(400, 64) * 0.3).astype(np.float32)
+    a = run_emu(U, I, 12, seed=0)
+    b = run_emu(U, I, 12, seed=9)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])

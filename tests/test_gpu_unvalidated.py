@@ -185,3 +185,28 @@ def test_trainer_row_sparse_adagrad_follows_dense_torch_adagrad():
         models.append(m)
     for (n1, p1), (_, p2) in zip(models[0].named_parameters(), models[1].named_parameters()):
         torch.testing.assert_close(p2, p1, rtol=1e-4, atol=1e-6, msg=lambda s: f'{n1}: {s}')
+
+
+# ------------------------------------------------------------------------------------------ fused full-sort top-k (topk_score.cu)
+@pytest.mark.parametrize('B,n_items,D,k', [(5, 300, 64, 10), (200, 50000, 64, 20), (64, 1000, 128, 100), (4096, 200001, 64, 10)])
+def test_full_sort_topk_matches_masked_torch_topk(B, n_items, D, k):
+    rng = np.random.RandomState(B)
+    U = torch.from_numpy((rng.randn(B, D) * 0.3).astype(np.float32))
+    I = torch.from_numpy((rng.randn(n_items, D) * 0.3).astype(np.float32))
+    lens = rng.randint(0, 30, B)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ids = np.concatenate([np.sort(rng.choice(np.arange(1, n_items), l, replace=False)) for l in lens] + [np.zeros(0, np.int64)])
+    hp, hi = torch.from_numpy(ptr).to(dev()), torch.from_numpy(ids.astype(np.int64)).to(dev())
+    sc, pos = ops().full_sort_topk(U.to(dev()), I.to(dev()), k, hist_ptr=hp, hist_ids=hi)
+    full = (U.to(dev()) @ I.to(dev()).T)
+    full[:, 0] = -float('inf')
+    rows = torch.repeat_interleave(torch.arange(B, device=dev()), torch.from_numpy(lens).to(dev()))
+    full[rows, hi] = -float('inf')
+    rs, ri = torch.topk(full, k, dim=1)
+    torch.testing.assert_close(sc, rs, rtol=2e-5, atol=1e-6)
+    # every returned id carries its score, is unique, and is not masked; ids agree wherever scores are well separated
+    torch.testing.assert_close(torch.gather(full, 1, pos), sc, rtol=2e-5, atol=1e-6)
+    assert (torch.sort(pos, dim=1).values.diff(dim=1) > 0).all()
+    gap = (rs[:, :-1] - rs[:, 1:]) > 1e-4 * rs[:, :-1].abs().clamp_min(1e-3)
+    sep = torch.cat([torch.ones_like(gap[:, :1]), gap], 1) & torch.cat([gap, torch.ones_like(gap[:, :1])], 1)
+    assert torch.equal(pos[sep], ri[sep])

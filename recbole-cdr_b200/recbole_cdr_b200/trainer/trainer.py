@@ -318,3 +318,25 @@ class CrossDomainTrainer(object):
             self._fit_phase(train_data, vd, verbose, saved, show_progress, callback_fn)
         self.model.set_phase('OVERLAP')
         return self.best_valid_score, self.best_valid_result
+
+
+class DCDCSRTrainer(CrossDomainTrainer):
+    r"""Trainer of DCDCSR (reference trainer/trainer.py:79-131): the CrossDomainTrainer phase loop, except that the BOTH
+    phase (benchmark + mapping fit) trains without validation data."""
+
+    def fit(self, train_data, valid_data=None, verbose=True, saved=True, show_progress=False, callback_fn=None):
+        for phase in range(len(self.train_modes)):
+            self._reinit(phase)
+            scheme = self.train_modes[phase]
+            train_data.set_mode(train_mode2state[scheme])
+            self.model.set_phase(scheme)
+            if scheme == 'BOTH':
+                vd = None
+            elif self.split_valid_flag and valid_data is not None:
+                source_valid_data, target_valid_data = valid_data
+                vd = source_valid_data if scheme == 'SOURCE' else target_valid_data
+            else:
+                vd = valid_data
+            self._fit_phase(train_data, vd, verbose, saved, show_progress, callback_fn)
+        self.model.set_phase('OVERLAP')
+        return self.best_valid_score, self.best_valid_result

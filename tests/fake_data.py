@@ -69,3 +69,62 @@ def make_batch(ds, domain, B, rng, pairwise=False, zipf=None):
     else:
         b[f'{domain}_label'] = torch.from_numpy((rng.rand(B) < 0.5).astype(np.float32))
     return b
+
+
+class _DomainF4(_Domain):
+    """Domain part that also carries the interaction list (``inter_feat``) some models read (sscdr.py:41,72-86)."""
+
+    def __init__(self, prefix, n_users, n_items, rows, cols):
+        super().__init__(prefix, n_users, n_items)
+        self.inter_feat = {self.uid_field: torch.from_numpy(np.asarray(rows)).long(),
+                           self.iid_field: torch.from_numpy(np.asarray(cols)).long()}
+
+    def history(self, row_num, row):
+        """Padded history matrix, zero values, lengths -- the algorithm of reference data/dataset.py:188-249
+        (rows filled in interaction order, 0 = padding)."""
+        u, i = self.inter_feat[self.uid_field].numpy(), self.inter_feat[self.iid_field].numpy()
+        row_ids, col_ids = (u, i) if row == 'user' else (i, u)
+        lens = np.bincount(row_ids, minlength=row_num).astype(np.int64)
+        mat = np.zeros((row_num, max(int(lens.max()), 1) if len(row_ids) else 1), dtype=np.int64)
+        fill = np.zeros(row_num, dtype=np.int64)
+        for r, c in zip(row_ids, col_ids):
+            mat[r, fill[r]] = c
+            fill[r] += 1
+        return torch.LongTensor(mat), torch.zeros(mat.shape), torch.LongTensor(lens)
+
+
+class FakeDatasetF4(FakeDataset):
+    """FakeDataset + what SSCDR / NATR / DCDCSR read: per-domain interaction lists and history matrices."""
+
+    def __init__(self, n_ov_u, n_tgt_u, n_src_u, n_ov_i, n_tgt_i, n_src_i, edges):
+        super().__init__(n_ov_u, n_tgt_u, n_src_u, n_ov_i, n_tgt_i, n_src_i, edges)
+        self.source_domain_dataset = _DomainF4('source', n_ov_u + n_src_u, n_ov_i + n_src_i, *edges['source'])
+        self.target_domain_dataset = _DomainF4('target', n_ov_u + n_tgt_u, n_ov_i + n_tgt_i, *edges['target'])
+
+    @classmethod
+    def random(cls, n_ov_u, n_tgt_u, n_src_u, n_ov_i, n_tgt_i, n_src_i, seed=0, per_user=4):
+        tmp = FakeDataset(n_ov_u, n_tgt_u, n_src_u, n_ov_i, n_tgt_i, n_src_i)
+        rng = np.random.RandomState(seed)
+        edges = {}
+        for dom in ('source', 'target'):
+            users, items = tmp.valid_ids(dom)
+            r = np.repeat(users, per_user)
+            c = rng.choice(items, size=r.shape[0])
+            e = np.unique(np.stack([r, c], 1), axis=0)
+            e = e[rng.permutation(len(e))]          # interaction order is not sorted in a real dataset
+            edges[dom] = (e[:, 0].copy(), e[:, 1].copy())
+        return cls(n_ov_u, n_tgt_u, n_src_u, n_ov_i, n_tgt_i, n_src_i, edges)
+
+    @classmethod
+    def from_golden(cls, g, edges=None):
+        edges = {dom: (g.z[f'edges/{dom}_row'], g.z[f'edges/{dom}_col']) for dom in ('source', 'target')}
+        return cls(g.meta('n_ov_u'), g.meta('n_tgt_u'), g.meta('n_src_u'), g.meta('n_ov_i'), g.meta('n_tgt_i'),
+                   g.meta('n_src_i'), edges)
+
+    def history_item_matrix(self, value_field=None, domain='source'):
+        part = self.source_domain_dataset if domain == 'source' else self.target_domain_dataset
+        return part.history(self.num_total_user, 'user')
+
+    def history_user_matrix(self, value_field=None, domain='source'):
+        part = self.source_domain_dataset if domain == 'source' else self.target_domain_dataset
+        return part.history(self.num_total_item, 'item')

@@ -1,0 +1,128 @@
+"""The five remaining drop-in models (CLFM, DeepAPF, SSCDR, NATR, DCDCSR) against
+tests/golden/f4_*.npz -- outputs of the UNMODIFIED reference classes (oracle/make_golden_f4.py) -- on CPU tensors through the
+CTA emulator (``emu_util.patched_ops``): same state_dict keys (strict load), same loss, every parameter gradient, predict.
+The GPU counterparts live in tests/test_gpu_unvalidated.py until they have run on a B200."""
+import numpy as np
+import pytest
+import torch
+
+import emu_util
+from fake_data import FakeDataset, FakeDatasetF4, base_config
+from golden_util import Golden
+from test_emu_models import check, cpu_batch
+
+
+def build(model_cls, g, cfg, with_edges=False):
+    ds = (FakeDatasetF4 if with_edges else FakeDataset).from_golden(g)
+    torch.manual_seed(0)
+    m = model_cls(base_config(device='cpu', **cfg), ds)
+    state = {n: g.param(n) for n in g.param_names()}
+    # DeepAPF registers its item MLP under two names (seq / item_mlp, deepapf.py:56-62); the golden holds
+    # named_parameters(), which reports each tensor once
+    for k in [k for k in state if k.startswith('seq.')]:
+        state['item_mlp.' + k[len('seq.'):]] = state[k]
+    m.load_state_dict(state, strict=True)
+    assert [n for n, _ in m.named_parameters()] == g.param_names(), 'parameter names / order differ from the reference'
+    return m
+
+
+def test_clfm():
+    from recbole_cdr_b200.model.cross_domain_recommender.clfm import CLFM
+    g = Golden('f4_clfm')
+    with emu_util.patched_ops():
+        m = build(CLFM, g, dict(user_embedding_size=64, source_item_embedding_size=64, target_item_embedding_size=64,
+                                share_embedding_size=32, alpha=g.meta('alpha'), reg_weight=g.meta('reg_weight')))
+        batch = cpu_batch(g)
+        check(m, g, batch)
+        torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('tag', ['users', 'items'])
+def test_deepapf(tag):
+    from recbole_cdr_b200.model.cross_domain_recommender.deepapf import DeepAPF
+    g = Golden(f'f4_deepapf_{tag}')
+    with emu_util.patched_ops():
+        m = build(DeepAPF, g, dict(embedding_size=64, beta=0.5))
+        batch = cpu_batch(g)
+        check(m, g, batch)
+        torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-5, atol=1e-6)
+
+
+SSCDR_CFG = {'embedding_size': 64, 'margin': 1, 'mlp_hidden_size': [128], 'lambda': 0.25}
+
+
+@pytest.mark.parametrize('phase', ['source', 'target'])
+def test_sscdr_rec_phases(phase):
+    from recbole_cdr_b200.model.cross_domain_recommender.sscdr import SSCDR
+    g = Golden(f'f4_sscdr_{phase}')
+    with emu_util.patched_ops():
+        m = build(SSCDR, g, SSCDR_CFG, with_edges=True)
+        m.set_phase(phase.upper())
+        batch = cpu_batch(g)
+        check(m, g, batch)
+        torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('tag', ['users', 'items'])
+def test_sscdr_map_phase(tag):
+    """The positive / negative draws use NumPy's global RNG in the reference's call order: same seed, same samples."""
+    from recbole_cdr_b200.model.cross_domain_recommender.sscdr import SSCDR
+    g = Golden(f'f4_sscdr_map_{tag}')
+    with emu_util.patched_ops():
+        m = build(SSCDR, g, SSCDR_CFG, with_edges=True)
+        m.set_phase('OVERLAP')
+        np.random.seed(g.meta('np_seed'))
+        check(m, g, cpu_batch(g), grad_atol=1e-6)
+        torch.testing.assert_close(m.predict(cpu_batch(g, 'pbatch/')), g.t('predict_overlap_phase'), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('tag', ['items', 'users'])
+@pytest.mark.parametrize('phase', ['source', 'target'])
+def test_natr(tag, phase):
+    from recbole_cdr_b200.model.cross_domain_recommender.natr import NATR
+    g = Golden(f'f4_natr_{tag}_{phase}')
+    with emu_util.patched_ops():
+        m = build(NATR, g, dict(source_embedding_size=64, target_embedding_size=64, reg_weight=1e-3,
+                                max_inter_length=g.meta('max_inter_length')), with_edges=True)
+        m.set_phase(phase.upper())
+        batch = cpu_batch(g)
+        check(m, g, batch)
+        torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-5, atol=1e-6)
+
+
+DCDCSR_CFG = dict(latent_factor_model='BPR', embedding_size=64, mlp_hidden_size=[128], k=5, map_batch_size=64)
+
+
+@pytest.mark.parametrize('tag', ['users', 'items'])
+def test_dcdcsr_four_stages(tag):
+    """SOURCE #1, TARGET #1, BOTH (benchmark embedding + map loss), TARGET #2 (affine embedding): each stage starts from
+    the reference's parameters at that stage and must reproduce its loss, gradients, predict and derived embeddings."""
+    from recbole_cdr_b200.model.cross_domain_recommender.dcdcsr import DCDCSR
+    with emu_util.patched_ops():
+        g = Golden(f'f4_dcdcsr_{tag}_source1')
+        m = build(DCDCSR, g, DCDCSR_CFG, with_edges=True)
+        m.set_phase('SOURCE')
+        check(m, g, cpu_batch(g))
+        torch.testing.assert_close(m.predict(cpu_batch(g)), g.t('predict'), rtol=1e-5, atol=1e-6)
+        g = Golden(f'f4_dcdcsr_{tag}_target1')
+        m.set_phase('TARGET')
+        check(m, g, cpu_batch(g))
+        torch.testing.assert_close(m.predict(cpu_batch(g)), g.t('predict'), rtol=1e-5, atol=1e-6)
+        g = Golden(f'f4_dcdcsr_{tag}_both')
+        m.set_phase('BOTH')
+        torch.testing.assert_close(m.benchmark_embedding, g.t('benchmark_embedding'), rtol=1e-4, atol=1e-6)
+        np.random.seed(g.meta('np_seed'))
+        check(m, g, cpu_batch(g), grad_atol=1e-6)
+        g = Golden(f'f4_dcdcsr_{tag}_target2')
+        m.set_phase('TARGET')
+        torch.testing.assert_close(m.affine_embedding, g.t('affine_embedding'), rtol=1e-4, atol=1e-6)
+        check(m, g, cpu_batch(g))
+        torch.testing.assert_close(m.predict(cpu_batch(g)), g.t('predict'), rtol=1e-5, atol=1e-6)
+
+
+def test_get_model_and_trainer_resolve_the_new_classes():
+    from recbole_cdr_b200.utils import ModelType, get_model, get_trainer
+    for name in ('CLFM', 'DeepAPF', 'SSCDR', 'NATR', 'DCDCSR'):
+        assert get_model(name).__name__ == name
+    assert get_trainer(ModelType.CROSSDOMAIN, 'DCDCSR').__name__ == 'DCDCSRTrainer'
+    assert get_trainer(ModelType.CROSSDOMAIN, 'SSCDR').__name__ == 'CrossDomainTrainer'

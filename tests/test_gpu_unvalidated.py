@@ -210,3 +210,82 @@ def test_full_sort_topk_matches_masked_torch_topk(B, n_items, D, k):
     gap = (rs[:, :-1] - rs[:, 1:]) > 1e-4 * rs[:, :-1].abs().clamp_min(1e-3)
     sep = torch.cat([torch.ones_like(gap[:, :1]), gap], 1) & torch.cat([gap, torch.ones_like(gap[:, :1])], 1)
     assert torch.equal(pos[sep], ri[sep])
+
+
+# ------------------------------------------------------------------------------------------ F4: the five remaining drop-in models
+def build_f4(model_cls, g, cfg, with_edges=False):
+    from fake_data import FakeDatasetF4
+    ds = (FakeDatasetF4 if with_edges else FakeDataset).from_golden(g)
+    torch.manual_seed(0)
+    m = model_cls(base_config(**cfg), ds)
+    state = {n: g.param(n) for n in g.param_names()}
+    for k in [k for k in state if k.startswith('seq.')]:   # DeepAPF's second name of its item MLP (deepapf.py:56-62)
+        state['item_mlp.' + k[len('seq.'):]] = state[k]
+    m.load_state_dict(state, strict=True)
+    return m.to('cuda')
+
+
+def test_f4_clfm():
+    from recbole_cdr_b200.model.cross_domain_recommender.clfm import CLFM
+    g = Golden('f4_clfm')
+    m = build_f4(CLFM, g, dict(user_embedding_size=64, source_item_embedding_size=64, target_item_embedding_size=64,
+                               share_embedding_size=32, alpha=g.meta('alpha'), reg_weight=g.meta('reg_weight')))
+    batch = cuda_batch(g)
+    check_loss_and_grads(m, g, batch, grad_rtol=2e-4, grad_atol=2e-6)
+    torch.testing.assert_close(m.predict(batch).cpu(), g.t('predict'), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('tag', ['users', 'items'])
+def test_f4_deepapf(tag):
+    from recbole_cdr_b200.model.cross_domain_recommender.deepapf import DeepAPF
+    g = Golden(f'f4_deepapf_{tag}')
+    m = build_f4(DeepAPF, g, dict(embedding_size=64, beta=0.5))
+    batch = cuda_batch(g)
+    check_loss_and_grads(m, g, batch, grad_rtol=2e-4, grad_atol=2e-6)
+    torch.testing.assert_close(m.predict(batch).cpu(), g.t('predict'), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('case,phase', [('source', 'SOURCE'), ('target', 'TARGET'), ('map_users', 'OVERLAP'), ('map_items', 'OVERLAP')])
+def test_f4_sscdr(case, phase):
+    from recbole_cdr_b200.model.cross_domain_recommender.sscdr import SSCDR
+    g = Golden(f'f4_sscdr_{case}')
+    m = build_f4(SSCDR, g, {'embedding_size': 64, 'margin': 1, 'mlp_hidden_size': [128], 'lambda': 0.25}, with_edges=True)
+    m.set_phase(phase)
+    if g.has('meta/np_seed'):
+        np.random.seed(g.meta('np_seed'))
+    check_loss_and_grads(m, g, cuda_batch(g), grad_rtol=2e-4, grad_atol=2e-6)
+
+
+@pytest.mark.parametrize('tag', ['items', 'users'])
+@pytest.mark.parametrize('phase', ['source', 'target'])
+def test_f4_natr(tag, phase):
+    from recbole_cdr_b200.model.cross_domain_recommender.natr import NATR
+    g = Golden(f'f4_natr_{tag}_{phase}')
+    m = build_f4(NATR, g, dict(source_embedding_size=64, target_embedding_size=64, reg_weight=1e-3,
+                               max_inter_length=g.meta('max_inter_length')), with_edges=True)
+    m.set_phase(phase.upper())
+    batch = cuda_batch(g)
+    check_loss_and_grads(m, g, batch, grad_rtol=2e-4, grad_atol=2e-6)
+    torch.testing.assert_close(m.predict(batch).cpu(), g.t('predict'), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('tag', ['users', 'items'])
+def test_f4_dcdcsr_four_stages(tag):
+    from recbole_cdr_b200.model.cross_domain_recommender.dcdcsr import DCDCSR
+    cfg = dict(latent_factor_model='BPR', embedding_size=64, mlp_hidden_size=[128], k=5, map_batch_size=64)
+    g = Golden(f'f4_dcdcsr_{tag}_source1')
+    m = build_f4(DCDCSR, g, cfg, with_edges=True)
+    m.set_phase('SOURCE')
+    check_loss_and_grads(m, g, cuda_batch(g))
+    g = Golden(f'f4_dcdcsr_{tag}_target1')
+    m.set_phase('TARGET')
+    check_loss_and_grads(m, g, cuda_batch(g))
+    g = Golden(f'f4_dcdcsr_{tag}_both')
+    m.set_phase('BOTH')
+    torch.testing.assert_close(m.benchmark_embedding.cpu(), g.t('benchmark_embedding'), rtol=1e-4, atol=1e-6)
+    np.random.seed(g.meta('np_seed'))
+    check_loss_and_grads(m, g, cuda_batch(g), grad_atol=1e-6)
+    g = Golden(f'f4_dcdcsr_{tag}_target2')
+    m.set_phase('TARGET')
+    torch.testing.assert_close(m.affine_embedding.cpu(), g.t('affine_embedding'), rtol=1e-4, atol=1e-6)
+    check_loss_and_grads(m, g, cuda_batch(g))

@@ -209,12 +209,31 @@ def patched_ops(sms=3, seed=0):
         def __getattr__(self, name):
             return emu_fn(name)
 
-    saved = dict(call=ops.call, req=ops._require_cuda_f32, ids=ops._ids, stream=ops.cur_stream, ws=xl.workspace, handle=xl._lib)
-    ops.call, ops._require_cuda_f32, ops._ids, ops.cur_stream = call, req_f32, ids, (lambda: None)
-    xl.workspace, xl._lib = workspace, LibProxy()
+    # every loaded module of the package that bound the _lib / ops helpers by name gets the emulator versions
+    import sys
+    import importlib
+    for extra in ('graph',):
+        importlib.import_module('recbole_cdr_b200.' + extra)
+    replace = {xl.call: call, xl.cur_stream: (lambda: None), ops._require_cuda_f32: req_f32, ops._ids: ids,
+               xl.workspace: workspace}
+    undo = []
+    for name, mod in list(sys.modules.items()):
+        if not name.startswith('recbole_cdr_b200') or mod is None:
+            continue
+        for attr, val in list(vars(mod).items()):
+            try:
+                new = replace.get(val)
+            except TypeError:       # unhashable module attribute
+                continue
+            if new is not None:
+                undo.append((mod, attr, val))
+                setattr(mod, attr, new)
+    handle = xl._lib
+    xl._lib = LibProxy()
     try:
         yield ops
     finally:
-        ops.call, ops._require_cuda_f32, ops._ids, ops.cur_stream = saved['call'], saved['req'], saved['ids'], saved['stream']
-        xl.workspace, xl._lib = saved['ws'], saved['handle']
+        for mod, attr, val in undo:
+            setattr(mod, attr, val)
+        xl._lib = handle
         config(4, 0)

@@ -215,3 +215,20 @@ def test_full_sort_topk_agrees_with_full_sort_predict():
             rs, ri = torch.topk(ref, 10, dim=1)
             torch.testing.assert_close(sc, rs, rtol=2e-5, atol=1e-6)
             assert torch.equal(pos, ri)
+
+
+@pytest.mark.parametrize('way', ['concat', 'mean'])
+def test_bitgcf_composed(way):
+    """BiTGCF (graph SpMM, propagate, transfer + normalise kernels: graph_prop.cu, hardware-validated) through the emulator."""
+    from golden_util import bitgcf_graph
+    from recbole_cdr_b200.model.cross_domain_recommender.bitgcf import BiTGCF
+    g = Golden(f'bitgcf_{way}')
+    _, _, edges, _ = bitgcf_graph(g)
+    with emu_util.patched_ops():
+        ds = FakeDataset.from_golden(g, edges)
+        m = BiTGCF(base_config(device='cpu', embedding_size=32, n_layers=2, reg_weight=0.001, lambda_source=0.8,
+                               lambda_target=0.7, drop_rate=0.0, connect_way=way), ds)
+        m.load_state_dict({n: g.param(n) for n in g.param_names()}, strict=True)
+        batch = cpu_batch(g)
+        check(m, g, batch, grad_rtol=2e-4, grad_atol=2e-7)
+        torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-4, atol=1e-6)

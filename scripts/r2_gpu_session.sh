@@ -23,5 +23,9 @@ XDR_SMALL=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control non
     --log-file gpurun_out/new_kernels_launches.csv python scripts/bench_new_kernels.py > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_conet_kernel -s 2 -c 1 \
     -o gpurun_out/tc_conet python scripts/bench_new_kernels.py > /dev/null 2>&1
+# 5. the tcgen05 descriptor experiment (which operand layouts / descriptor readings the hardware accepts)
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o /tmp/ubench_tcgen05 scripts/ubench_tcgen05.cu > gpurun_out/tcgen05.log 2>&1 \
+    && timeout 120 /tmp/ubench_tcgen05 >> gpurun_out/tcgen05.log 2>&1
+echo "ubench_tcgen05 rc=$?" | tee -a gpurun_out/summary.txt
 tail -n 5 gpurun_out/*.log
 cat gpurun_out/summary.txt

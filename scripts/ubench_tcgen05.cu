@@ -1,0 +1,207 @@
+// ubench_tcgen05.cu -- a decisive hardware experiment for the tcgen05 upgrade of the row-tile kernels (tc_tile.cuh).
+//
+// The fused MLP / CoNet kernels keep fp32 operands in shared memory and currently multiply them with 3xTF32 mma.sync.
+// Moving them to tcgen05.mma (kind::tf32, accumulators in TMEM) needs hand-built shared-memory matrix descriptors for
+// operands the kernel itself writes (no TMA), in both majors: K-major for the forward / input-gradient products and
+// MN-major for the weight gradient dZ^T X (whose reduction index is the batch row).  This program checks, on one CTA, every
+// combination of {A, B} x {K-major, MN-major} with SWIZZLE_NONE canonical layouts, for both readings of which descriptor
+// field is the "leading" and which the "stride" byte offset, against a CPU product, and prints one PASS/FAIL line each.
+// Built and run by scripts/r2_gpu_session.sh:   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o ubench_tcgen05 ...
+//
+// Canonical SWIZZLE_NONE layouts (cute/atom/mma_traits_sm100.hpp, units of 16 bytes = 4 tf32):
+//   K-major : ((8,n),2):((1,SBO),LBO)      a core matrix = 8 MN-rows x 16 B, rows 16 B apart; next 8 rows +SBO; next 16 B of K +LBO
+//   MN-major: ((1,n),(8,k)):((X,SBO),(1,LBO))  a core matrix = 8 K-rows x 16 B (4 MN elements); next 4 MN elements +SBO; next 8 K +LBO
+// Descriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64).
+// Instruction descriptor: c_format F32 = 1 [4,6), a/b_format TF32 = 2 [7,10)/[10,13), a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+constexpr int M = 128, N = 64, K = 64;  // one UMMA tile: D[128 x 64] += A[128 x 8] B[64 x 8]^T per instruction, K/8 instructions
+
+struct Variant {
+  int a_mn_major, b_mn_major;  // 0 = K-major, 1 = MN-major
+  int swap_lbo_sbo;            // 0 = as read from the CUTLASS headers, 1 = the two descriptor fields exchanged
+};
+
+// byte offset of element (mn, k) of an operand with `rows` MN-rows, plus the LBO / SBO / per-instruction K advance it implies
+struct OperandLayout {
+  int lbo, sbo, k_step_bytes;
+};
+__host__ __device__ inline OperandLayout operand_layout(int rows, int mn_major) {
+  OperandLayout o;
+  if (!mn_major) {            // K-major: 16-byte K chunks are `rows * 16` bytes apart, 8-row groups 128 bytes apart
+    o.lbo = rows * 16;
+    o.sbo = 128;
+    o.k_step_bytes = 2 * o.lbo;   // one instruction consumes K = 8 = two 16-byte chunks
+  } else {                    // MN-major: 4-element MN groups 128 bytes apart, 8-row K groups `rows/4 * 128` bytes apart
+    o.sbo = 128;
+    o.lbo = (rows / 4) * 128;
+    o.k_step_bytes = o.lbo;       // one instruction consumes K = 8 = one K group
+  }
+  return o;
+}
+__host__ __device__ inline int operand_offset(int rows, int mn_major, int mn, int k) {
+  const OperandLayout o = operand_layout(rows, mn_major);
+  if (!mn_major) return (k / 4) * o.lbo + (mn / 8) * o.sbo + (mn % 8) * 16 + (k % 4) * 4;
+  return (k / 8) * o.lbo + (mn / 4) * o.sbo + (k % 8) * 16 + (mn % 4) * 4;
+}
+
+__device__ inline uint64_t make_desc(uint32_t smem_addr, int lbo, int sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // version = 1 (Blackwell)
+  return d;                // base_offset 0, lbo_mode 0, layout_type SWIZZLE_NONE = 0
+}
+
+__global__ void __launch_bounds__(128, 1) umma_tf32_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                           float* __restrict__ D, Variant v) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_smem;
+  uint8_t* sA = smem;                 // M * K * 4 = 32 KB
+  uint8_t* sB = smem + M * K * 4;     // N * K * 4 = 16 KB
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int e = tid; e < M * K; e += 128) {
+    const int r = e / K, k = e % K;
+    *reinterpret_cast<float*>(sA + operand_offset(M, v.a_mn_major, r, k)) = A[e];
+  }
+  for (int e = tid; e < N * K; e += 128) {
+    const int r = e / K, k = e % K;
+    *reinterpret_cast<float*>(sB + operand_offset(N, v.b_mn_major, r, k)) = B[e];
+  }
+  const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {  // one warp allocates 64 TMEM columns (power of two >= 32) and gives the permit back
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_smem);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(64));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (tid == 0) {  // a single thread issues the MMAs
+    const OperandLayout la = operand_layout(M, v.a_mn_major), lb = operand_layout(N, v.b_mn_major);
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(sA), b0 = (uint32_t)__cvta_generic_to_shared(sB);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)v.a_mn_major << 15) | ((uint32_t)v.b_mn_major << 16) |
+                           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    for (int ks = 0; ks < K / 8; ++ks) {
+      const uint64_t da = v.swap_lbo_sbo ? make_desc(a0 + ks * la.k_step_bytes, la.sbo, la.lbo)
+                                         : make_desc(a0 + ks * la.k_step_bytes, la.lbo, la.sbo);
+      const uint64_t db = v.swap_lbo_sbo ? make_desc(b0 + ks * lb.k_step_bytes, lb.sbo, lb.lbo)
+                                         : make_desc(b0 + ks * lb.k_step_bytes, lb.lbo, lb.sbo);
+      const uint32_t acc = ks > 0 ? 1u : 0u;
+      const uint32_t zero = 0;
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+          "}\n" ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(zero)
+          : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+  }
+  // everybody waits for the commit (phase 0); the spin is bounded so that a wrong commit form cannot hang the GPU
+  {
+    uint32_t done = 0;
+    for (long long spin = 0; !done && spin < 20000000LL; ++spin) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}\n"
+          : "=r"(done)
+          : "r"(bar_addr), "r"(0)
+          : "memory");
+    }
+    if (!done) {  // report and leave without touching TMEM results
+      if (tid == 0) D[0] = __int_as_float(0x7fc00001);
+      __syncthreads();
+      if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64));
+      return;
+    }
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // epilogue: warp w reads TMEM lanes 32w .. 32w+31 (= rows), 8 columns at a time
+  for (int c = 0; c < N / 8; ++c) {
+    uint32_t r[8];
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 8);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float* out = D + (size_t)(warp * 32 + lane) * N + c * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = __uint_as_float(r[j]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64));
+}
+
+static float tf32_round(float x) {  // keep 10 mantissa bits so that the products are exact in fp32
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xffffe000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+int main() {
+  float *hA = (float*)malloc(M * K * 4), *hB = (float*)malloc(N * K * 4), *hD = (float*)malloc(M * N * 4), *ref = (float*)malloc(M * N * 4);
+  srand(7);
+  for (int i = 0; i < M * K; ++i) hA[i] = tf32_round((float)rand() / RAND_MAX - 0.5f);
+  for (int i = 0; i < N * K; ++i) hB[i] = tf32_round((float)rand() / RAND_MAX - 0.5f);
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double s = 0;
+      for (int k = 0; k < K; ++k) s += (double)hA[m * K + k] * hB[n * K + k];
+      ref[m * N + n] = (float)s;
+    }
+  float *dA, *dB, *dD;
+  cudaMalloc(&dA, M * K * 4); cudaMalloc(&dB, N * K * 4); cudaMalloc(&dD, M * N * 4);
+  cudaMemcpy(dA, hA, M * K * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, hB, N * K * 4, cudaMemcpyHostToDevice);
+  const int smem = (M + N) * K * 4;
+  cudaFuncSetAttribute(umma_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int n_pass = 0;
+  for (int swap = 0; swap < 2; ++swap)
+    for (int am = 0; am < 2; ++am)
+      for (int bm = 0; bm < 2; ++bm) {
+        Variant v{am, bm, swap};
+        cudaMemset(dD, 0xff, M * N * 4);
+        umma_tf32_kernel<<<1, 128, smem>>>(dA, dB, dD, v);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+          printf("A %s-major, B %s-major, %s: CUDA error %s\n", am ? "MN" : "K", bm ? "MN" : "K",
+                 swap ? "LBO/SBO exchanged" : "LBO/SBO as read", cudaGetErrorString(e));
+          return 2;  // a sticky error: nothing after it is meaningful
+        }
+        cudaMemcpy(hD, dD, M * N * 4, cudaMemcpyDeviceToHost);
+        double max_err = 0;
+        for (int i = 0; i < M * N; ++i) {
+          const double d = fabs((double)hD[i] - ref[i]);
+          if (!(d <= max_err)) max_err = d;  // NaN-safe
+        }
+        const bool ok = max_err < 1e-4;
+        n_pass += ok;
+        printf("A %s-major, B %s-major, %-18s : %s (max abs err %.3e)\n", am ? "MN" : "K ", bm ? "MN" : "K ",
+               swap ? "LBO/SBO exchanged" : "LBO/SBO as read", ok ? "PASS" : "FAIL", max_err);
+      }
+  printf("%d of 8 variants pass\n", n_pass);
+  return 0;
+}

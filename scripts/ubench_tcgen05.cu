@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(128, 1) umma_tf32_kernel(const float* __restri
       asm volatile(
           "{\n\t"
           ".reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
           "selp.u32 %0, 1, 0, p;\n\t"
           "}\n"
           : "=r"(done)

@@ -53,6 +53,7 @@ inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 namespace emu {
 
 constexpr size_t kStackBytes = 256 * 1024;
+constexpr size_t kGuardBytes = 4096;  // guard zone behind the dynamic shared memory of a CTA
 
 struct Fiber {
   ucontext_t ctx;
@@ -151,7 +152,8 @@ inline void launch(dim3 grid, dim3 block3, size_t smem_bytes, std::function<void
     s.warp_arrived.assign(nwarps, 0);
     s.warp_gen.assign(nwarps, 0);
     s.warp_buf.assign((size_t)nwarps * 32 * 8, 0);
-    s.dyn_smem.assign(smem_bytes + 16, (char)0xCD);  // poison: reads of unwritten shared memory become visible
+    // poison: reads of unwritten shared memory become visible; the tail is a guard zone checked after the CTA has run
+    s.dyn_smem.assign(smem_bytes + kGuardBytes, (char)0xCD);
     s.fibers.clear();
     s.fibers.resize(block);
     for (unsigned t = 0; t < block; ++t) {
@@ -186,6 +188,12 @@ inline void launch(dim3 grid, dim3 block3, size_t smem_bytes, std::function<void
       }
     }
     s.current = -1;
+    for (size_t g = smem_bytes; g < smem_bytes + kGuardBytes; ++g)
+      if (s.dyn_smem[g] != (char)0xCD) {
+        std::fprintf(stderr, "cuda_emu: CTA %u wrote %zu bytes past its %zu bytes of dynamic shared memory\n", b,
+                     g - smem_bytes + 1, smem_bytes);
+        std::abort();
+      }
   }
 }
 

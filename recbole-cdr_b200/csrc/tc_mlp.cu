@@ -41,15 +41,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_mlp_kernel(MlpArgs a, Worksp
     grd[l] = p; p += TR * lda[l];
   }
   float* tgt = grd[0];  // head 0: target rows [TR][lda[0]] (dims[0] == dims[nl]); dead before grd[0] is produced
+  // resident weights: 128-bit loads (din % 8 == 0, pointers 16-byte aligned by the entry point).  No barrier here: the one
+  // after the first tile's gather also orders these writes before their first use (every CTA owns at least one tile).
   for (int l = 0; l < nl; ++l) {
-    const int din = a.dims[l], dout = a.dims[l + 1];
-    for (int e = tid; e < din * dout; e += kTcThreads) {
-      const int n = e / din, k = e - n * din;
-      Wsm[l][n * ldw[l] + k] = a.W[l][e];
+    const int din = a.dims[l], dout = a.dims[l + 1], q = din >> 2;
+    for (int e = tid; e < q * dout; e += kTcThreads) {
+      const int n = e / q, k4 = e - n * q;
+      *reinterpret_cast<float4*>(Wsm[l] + n * ldw[l] + 4 * k4) = *(reinterpret_cast<const float4*>(a.W[l]) + e);
     }
     for (int n = tid; n < dout; n += kTcThreads) bsm[l][n] = a.b[l] ? a.b[l][n] : 0.f;
   }
-  __syncthreads();
 
   float accW0[DW0][4], accW1[DW1][4], accW2[DW2][4];
 #pragma unroll
@@ -349,7 +350,7 @@ int xdr_tc_mlp_step(int n_layers, const int* dims_host, const float* const* W_ho
     XDR_REQUIRE(dAu && (in_mode == 0 || (dBu && dAi && dBi)) && (head == 1 || dT), "xdr_tc_mlp_step: null destination");
   }
   for (int l = 0; l < n_layers; ++l) {
-    XDR_REQUIRE(W_host[l], "xdr_tc_mlp_step: null weight");
+    XDR_REQUIRE(W_host[l] && aligned16(W_host[l]), "xdr_tc_mlp_step: null or misaligned weight");
     a.W[l] = W_host[l];
     a.b[l] = b_host ? b_host[l] : nullptr;
     a.dW[l] = (backward && dW_host) ? dW_host[l] : nullptr;

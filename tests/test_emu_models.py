@@ -232,3 +232,35 @@ def test_bitgcf_composed(way):
         batch = cpu_batch(g)
         check(m, g, batch, grad_rtol=2e-4, grad_atol=2e-7)
         torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('name,golden,cfg,phase', [
+    ('EMCDR', 'emcdr_bpr_source', dict(EMCDR_CFG, latent_factor_model='BPR', mapping_function='non_linear'), 'SOURCE'),
+    ('EMCDR', 'emcdr_mf_target', dict(EMCDR_CFG, latent_factor_model='MF', mapping_function='non_linear'), 'TARGET'),
+    ('EMCDR', 'emcdr_map_non_linear', dict(EMCDR_CFG, latent_factor_model='BPR', mapping_function='non_linear'), 'OVERLAP'),
+    ('CMF', 'cmf_both', {'embedding_size': 64, 'alpha': 0.3, 'lambda': 0.05, 'gamma': 0.02}, None),
+    ('CoNet', 'conet_users', dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8]), None),
+    ('DTCDR', 'dtcdr_neumf', dict(embedding_size=64, mlp_hidden_size=[32, 16], dropout_prob=0.0, base_model='NeuMF', alpha=0.4), None),
+])
+def test_touched_rows_cover_every_row_with_a_gradient(name, golden, cfg, phase):
+    """The row-sparse optimizer visits only ``model.touched_rows(batch)``: every table row that receives a gradient must be
+    in that list (and the list must not name rows of tables the loss does not read)."""
+    import importlib
+    cls = getattr(importlib.import_module(f'recbole_cdr_b200.model.cross_domain_recommender.{name.lower()}'), name)
+    g = Golden(golden)
+    with emu_util.patched_ops():
+        m = build_cpu(cls, g, cfg)
+        if phase:
+            m.set_phase(phase)
+        batch = cpu_batch(g)
+        m.zero_grad()
+        loss = m.calculate_loss(batch)
+        (sum(loss) if isinstance(loss, tuple) else loss).sum().backward()
+        touched = {}
+        for table, ids in m.touched_rows(batch):
+            touched.setdefault(id(table), set()).update(ids.reshape(-1).tolist())
+        for pname, p in m.named_parameters():
+            if not pname.endswith('_embedding.weight'):
+                continue
+            rows = set(torch.nonzero(p.grad.abs().sum(dim=1)).reshape(-1).tolist()) if p.grad is not None else set()
+            assert rows <= touched.get(id(p), set()), f'{pname}: rows with a gradient that touched_rows() does not list'

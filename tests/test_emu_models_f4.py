@@ -126,3 +126,30 @@ def test_get_model_and_trainer_resolve_the_new_classes():
         assert get_model(name).__name__ == name
     assert get_trainer(ModelType.CROSSDOMAIN, 'DCDCSR').__name__ == 'DCDCSRTrainer'
     assert get_trainer(ModelType.CROSSDOMAIN, 'SSCDR').__name__ == 'CrossDomainTrainer'
+
+
+@pytest.mark.parametrize('name,golden,cfg,phase,edges', [
+    ('CLFM', 'f4_clfm', dict(user_embedding_size=64, source_item_embedding_size=64, target_item_embedding_size=64,
+                             share_embedding_size=32, alpha=0.3, reg_weight=1e-2), None, False),
+    ('DeepAPF', 'f4_deepapf_users', dict(embedding_size=64, beta=0.5), None, False),
+    ('DeepAPF', 'f4_deepapf_items', dict(embedding_size=64, beta=0.5), None, False),
+    ('SSCDR', 'f4_sscdr_source', SSCDR_CFG, 'SOURCE', True),
+])
+def test_touched_rows_cover_every_row_with_a_gradient(name, golden, cfg, phase, edges):
+    import importlib
+    cls = getattr(importlib.import_module(f'recbole_cdr_b200.model.cross_domain_recommender.{name.lower()}'), name)
+    g = Golden(golden)
+    with emu_util.patched_ops():
+        m = build(cls, g, cfg, with_edges=edges)
+        if phase:
+            m.set_phase(phase)
+        batch = cpu_batch(g)
+        m.zero_grad()
+        m.calculate_loss(batch).sum().backward()
+        touched = {}
+        for table, ids in m.touched_rows(batch):
+            touched.setdefault(id(table), set()).update(ids.reshape(-1).tolist())
+        for pname, p in m.named_parameters():
+            if pname.endswith('_embedding.weight') and p.grad is not None:
+                rows = set(torch.nonzero(p.grad.abs().sum(dim=1)).reshape(-1).tolist())
+                assert rows <= touched.get(id(p), set()), f'{pname}: rows with a gradient that touched_rows() does not list'

@@ -83,6 +83,23 @@ struct StepsArgs {
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
+#ifdef XDR_EMU
+// CPU CTA emulator (tests/emu): the same eight primitives on the emulator's mbarrier / bulk-copy model; polls yield.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { emu::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { emu::mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { emu::mbar_arrive(bar); }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) { return emu::mbar_test(bar, parity); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { emu::mbar_wait(bar, parity); }
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  emu::bulk_g2s(dst_smem, src_gmem, bytes, bar);
+}
+__device__ __forceinline__ unsigned long long gtime() { return ++emu::st().clock; }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  emu::yield();  // every poll gives the other fibers a turn
+  return *p;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) { *p = v; }
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -137,6 +154,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+#endif  // XDR_EMU
 // coherent (L2) 128-bit row load: the table may be the scatter destination of this very launch (fused SGD)
 __device__ __forceinline__ float4 ldcg_row4(const float* row, int col4) {
   return __ldcg(reinterpret_cast<const float4*>(row) + col4);
@@ -458,7 +476,9 @@ __device__ __forceinline__ void init_bars(const Bars& B, int tasks, int ifree_co
     mbar_init(&B.normf[i], 1);
   }
   for (int i = 0; i < stages; ++i) mbar_init(&B.sfree[i], (uint32_t)sfree_count);
+#ifndef XDR_EMU
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
 }
 
 // =====================================================================================================================
@@ -470,7 +490,7 @@ template <int LPR, int VEC, bool PAIRWISE, int kLoaderWarps>
 __global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a, int n_stages) {
   constexpr int IPW = 32 / LPR;
   constexpr int R = PAIRWISE ? 3 : 2;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  XDR_DYN_SMEM_ALIGNED(unsigned char, smem_raw, 128);
   const int64_t first = (int64_t)blockIdx.x * a.slice;
   const int cnt = (int)min((int64_t)a.slice, a.batch - first);  // > 0: the host launches ceil(batch/slice) CTAs
   const int tasks = (cnt + IPW - 1) / IPW;
@@ -599,7 +619,7 @@ template <int LPR, int VEC, bool PAIRWISE>
 __global__ void __launch_bounds__(kRegThreads, 1) train_steps_regs_kernel(StepsArgs a) {
   constexpr int IPW = 32 / LPR;
   constexpr int R = PAIRWISE ? 3 : 2;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  XDR_DYN_SMEM_ALIGNED(unsigned char, smem_raw, 128);
   const int64_t first = (int64_t)blockIdx.x * a.slice;
   const int cnt = (int)min((int64_t)a.slice, a.batch - first);
   const int tasks = (cnt + IPW - 1) / IPW;
@@ -738,15 +758,15 @@ static int launch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_t 
   if (plan.stages > 0 && a.stage_a != nullptr) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsLite>;
     XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    kern<<<plan.grid, staged_threads(kLoaderWarpsLite), plan.smem, s>>>(a, plan.stages);
+    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsLite), plan.smem, s, a, plan.stages);
   } else if (plan.stages > 0) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull>;
     XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    kern<<<plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s>>>(a, plan.stages);
+    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s, a, plan.stages);
   } else {
     auto kern = train_steps_regs_kernel<LPR, VEC, PW>;
     XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    kern<<<plan.grid, kRegThreads, plan.smem, s>>>(a);
+    XDR_LAUNCH_COOP((kern), plan.grid, kRegThreads, plan.smem, s, a);
   }
   return XDR_OK;
 }
@@ -879,6 +899,7 @@ int xdr_train_steps_sharded(const float* const* user_shards, const float* const*
                           steps_ws_bytes, staged_item_a, staged_item_b, oob, stream);
 }
 
+#ifndef XDR_EMU  // CUDA IPC has no emulator counterpart
 // ---- peer-memory plumbing for row-sharded tables (CUDA IPC; one process per GPU) --------------------------------------
 int xdr_ipc_export(const void* dev_ptr, unsigned char* handle64_host, int64_t* offset_host) {
   XDR_REQUIRE(dev_ptr && handle64_host && offset_host, "xdr_ipc_export: null pointer");
@@ -918,5 +939,6 @@ int xdr_ipc_close(void* base) {
   XDR_CUDA_OK(cudaIpcCloseMemHandle(base));
   return XDR_OK;
 }
+#endif  // !XDR_EMU
 
 }  // extern "C"

@@ -228,11 +228,22 @@ __device__ __forceinline__ void grid_reduce_last_block(float (&v)[NV], Workspace
 #define XDR_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
 
+// Launch of a persistent kernel whose CTAs hand data to each other (all CTAs resident at once).  CUDA: a plain launch --
+// residency is the caller's business (grid <= #SMs); emulator: all CTAs run under one fiber scheduler.
+#ifdef XDR_EMU
+#define XDR_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) \
+  emu::launch(grid, block, smem, [&] { kernel(__VA_ARGS__); }, /*concurrent=*/true)
+#else
+#define XDR_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 // Dynamic shared memory of the CTA as `type* name` (CUDA: the extern __shared__ array; emulator: the CTA's heap block).
 #ifdef XDR_EMU
 #define XDR_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dyn_smem())
+#define XDR_DYN_SMEM_ALIGNED(type, name, align) type* name = reinterpret_cast<type*>(emu::dyn_smem())
 #else
 #define XDR_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define XDR_DYN_SMEM_ALIGNED(type, name, align) extern __shared__ __align__(align) type name[]
 #endif
 
 // Instantiate CALL with `constexpr int VEC` = float4 columns per lane for a row of nv float4s (8 lanes per row).

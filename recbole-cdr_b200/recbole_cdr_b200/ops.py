@@ -49,6 +49,11 @@ def _require_cuda_f32(t: torch.Tensor, name: str):
         raise ValueError(f'{name} must be contiguous')
 
 
+def _on_device(t: torch.Tensor) -> bool:
+    """True for tensors the kernels can address (CUDA memory)."""
+    return t.is_cuda
+
+
 def _ids(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise RuntimeError(f'{name} must be a CUDA tensor')
@@ -441,7 +446,8 @@ _steps_ws = {}
 
 
 def _steps_workspace(device, n_steps):
-    key = (device.index if device.index is not None else torch.cuda.current_device(), cur_stream())
+    index = device.index if device.index is not None else (torch.cuda.current_device() if device.type == 'cuda' else -1)
+    key = (index, cur_stream())
     need = _lib._lib.xdr_steps_workspace_bytes(int(n_steps))
     ws = _steps_ws.get(key)
     if ws is None or ws.numel() < need:
@@ -490,7 +496,7 @@ def train_steps(user_tab, item_tab, user, item_a, item_b=None, label=None, *, lo
     for t, nm in ((user, 'user'), (item_a, 'item_a'), (item_b, 'item_b')):
         if t is None:
             continue
-        if t.dtype != torch.int64 or not t.is_cuda or t.shape != (K, B) or t.stride(1) != 1:
+        if t.dtype != torch.int64 or not _on_device(t) or t.shape != (K, B) or t.stride(1) != 1:
             raise ValueError(f'{nm} must be a CUDA int64 [K, B] tensor with contiguous rows')
         if t.stride(0) != user.stride(0):
             raise ValueError('all id tensors must share the same step stride')

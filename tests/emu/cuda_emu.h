@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <unordered_map>
 #include <vector>
 
 #define __global__
@@ -48,33 +49,48 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <typename F>
 inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 
 namespace emu {
 
-constexpr size_t kStackBytes = 256 * 1024;
+constexpr size_t kStackBytes = 192 * 1024;
 constexpr size_t kGuardBytes = 4096;  // guard zone behind the dynamic shared memory of a CTA
+
+struct MBar {  // emulated mbarrier: phase completes when every expected arrival has come and no transaction bytes are pending
+  uint32_t expected = 0, pending = 0, phase = 0;
+  int64_t tx = 0;
+  void check() {
+    if (pending == 0 && tx == 0) { phase ^= 1u; pending = expected; }
+  }
+};
+
+struct Cta {
+  unsigned nthreads = 0, index = 0;
+  unsigned arrived = 0, gen = 0;               // CTA barrier
+  std::vector<unsigned> warp_arrived, warp_gen;  // per-warp collectives
+  std::vector<uint32_t> warp_buf;                // [n_warps][32][8] exchange words
+  std::vector<char> dyn_smem;
+  size_t smem_bytes = 0;
+  std::unordered_map<const void*, MBar> mbars;
+};
 
 struct Fiber {
   ucontext_t ctx;
-  std::vector<char> stack;
+  char* stack = nullptr;
   bool done = false;
-  unsigned tid = 0;
+  unsigned tid = 0, cta = 0;
 };
 
 struct State {
   ucontext_t sched;
   std::vector<Fiber> fibers;
+  std::vector<Cta> ctas;
   int current = -1;
-  unsigned nthreads = 0;
-  // CTA barrier
-  unsigned cta_arrived = 0, cta_gen = 0;
-  // per-warp collectives
-  std::vector<unsigned> warp_arrived, warp_gen;
-  std::vector<uint32_t> warp_buf;  // [n_warps][32][8] exchange words
-  std::vector<char> dyn_smem;
+  dim3 grid;
   std::function<void()> body;
   uint64_t rng = 0;  // 0 = round-robin
+  uint64_t clock = 0;
 };
 
 inline State& st() {
@@ -84,42 +100,64 @@ inline State& st() {
 
 inline void set_schedule_seed(uint64_t seed) { st().rng = seed; }
 
+inline Fiber& self() { return st().fibers[st().current]; }
+inline Cta& cta() { return st().ctas[self().cta]; }
+
 inline void yield() {
   State& s = st();
   swapcontext(&s.fibers[s.current].ctx, &s.sched);
 }
 
 inline void cta_barrier() {
-  State& s = st();
-  const unsigned gen = s.cta_gen;
-  if (++s.cta_arrived == s.nthreads) {
-    s.cta_arrived = 0;
-    ++s.cta_gen;
+  Cta& c = cta();
+  const unsigned gen = c.gen;
+  if (++c.arrived == c.nthreads) {
+    c.arrived = 0;
+    ++c.gen;
     return;
   }
-  while (s.cta_gen == gen) yield();
+  while (cta().gen == gen) yield();
 }
 
 inline void warp_barrier() {
-  State& s = st();
-  const unsigned w = s.fibers[s.current].tid >> 5;
-  const unsigned lanes = std::min(32u, s.nthreads - w * 32);
-  const unsigned gen = s.warp_gen[w];
-  if (++s.warp_arrived[w] == lanes) {
-    s.warp_arrived[w] = 0;
-    ++s.warp_gen[w];
+  Cta& c = cta();
+  const unsigned w = self().tid >> 5;
+  const unsigned lanes = std::min(32u, c.nthreads - w * 32);
+  const unsigned gen = c.warp_gen[w];
+  if (++c.warp_arrived[w] == lanes) {
+    c.warp_arrived[w] = 0;
+    ++c.warp_gen[w];
     return;
   }
-  while (s.warp_gen[w] == gen) yield();
+  while (cta().warp_gen[w] == gen) yield();
 }
 
 inline uint32_t* warp_slot(unsigned lane) {
-  State& s = st();
-  const unsigned w = s.fibers[s.current].tid >> 5;
-  return &s.warp_buf[(size_t)(w * 32 + lane) * 8];
+  Cta& c = cta();
+  const unsigned w = self().tid >> 5;
+  return &c.warp_buf[(size_t)(w * 32 + lane) * 8];
 }
 
-inline void* dyn_smem() { return st().dyn_smem.data(); }
+inline void* dyn_smem() { return cta().dyn_smem.data(); }
+
+// ---- mbarrier / bulk-copy model (enough for the TMA id-tile ring and the mbarrier hand-offs of steps_persistent.cu) ----
+inline void mbar_init(const void* bar, uint32_t count) {
+  MBar& m = cta().mbars[bar];
+  m.expected = m.pending = count;
+  m.phase = 0;
+  m.tx = 0;
+}
+inline void mbar_arrive(const void* bar) { MBar& m = cta().mbars[bar]; --m.pending; m.check(); }
+inline void mbar_expect_tx(const void* bar, uint32_t bytes) { MBar& m = cta().mbars[bar]; m.tx += bytes; --m.pending; m.check(); }
+inline void mbar_complete_tx(const void* bar, uint32_t bytes) { MBar& m = cta().mbars[bar]; m.tx -= bytes; m.check(); }
+inline bool mbar_test(const void* bar, uint32_t parity) { return cta().mbars[bar].phase != (parity & 1u); }
+inline void mbar_wait(const void* bar, uint32_t parity) {
+  while (!mbar_test(bar, parity)) yield();
+}
+inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, const void* bar) {
+  std::memcpy(dst, src, bytes);
+  mbar_complete_tx(bar, bytes);
+}
 
 }  // namespace emu
 
@@ -135,66 +173,89 @@ inline void fiber_entry() {
   swapcontext(&s.fibers[s.current].ctx, &s.sched);
 }
 
-// Runs `body` once per thread of every CTA of the grid; CTAs execute one after another (x fastest), 1-D blocks only.
-inline void launch(dim3 grid, dim3 block3, size_t smem_bytes, std::function<void()> body) {
+// Runs the fibers of CTAs [first, first + count) of the current launch to completion under one scheduler.
+inline void run_ctas(unsigned first, unsigned count, unsigned block, size_t smem_bytes) {
+  State& s = st();
+  s.ctas.assign(count, Cta());
+  const unsigned nwarps = (block + 31) / 32;
+  for (unsigned c = 0; c < count; ++c) {
+    Cta& k = s.ctas[c];
+    k.nthreads = block;
+    k.index = first + c;
+    k.warp_arrived.assign(nwarps, 0);
+    k.warp_gen.assign(nwarps, 0);
+    k.warp_buf.assign((size_t)nwarps * 32 * 8, 0);
+    k.smem_bytes = smem_bytes;
+    // poison: reads of unwritten shared memory become visible; the tail is a guard zone checked after the CTA has run
+    k.dyn_smem.assign(smem_bytes + kGuardBytes, (char)0xCD);
+  }
+  const unsigned n = count * block;
+  for (Fiber& f : s.fibers) std::free(f.stack);
+  s.fibers.clear();
+  s.fibers.resize(n);
+  for (unsigned i = 0; i < n; ++i) {
+    Fiber& f = s.fibers[i];
+    f.cta = i / block;
+    f.tid = i % block;
+    f.stack = static_cast<char*>(std::malloc(kStackBytes));  // untouched pages stay uncommitted
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = kStackBytes;
+    f.ctx.uc_link = &s.sched;
+    makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+  }
+  unsigned remaining = n;
+  std::vector<unsigned> order(n);
+  for (unsigned i = 0; i < n; ++i) order[i] = i;
+  uint64_t rng = s.rng ? (s.rng * 0x9E3779B97F4A7C15ull + first + 1) : 0;
+  uint64_t rounds = 0;
+  while (remaining) {
+    if (++rounds > 200000000ull / (n ? n : 1) + 100000ull) {
+      std::fprintf(stderr, "cuda_emu: no fiber finished for too long -- deadlock in the emulated kernel?\n");
+      std::abort();
+    }
+    if (rng) {  // seeded Fisher-Yates reshuffle of the resume order each round
+      for (unsigned i = n - 1; i > 0; --i) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        std::swap(order[i], order[rng % (i + 1)]);
+      }
+    }
+    for (unsigned i = 0; i < n; ++i) {
+      Fiber& f = s.fibers[order[i]];
+      if (f.done) continue;
+      s.current = (int)order[i];
+      const unsigned b = s.ctas[f.cta].index;
+      threadIdx = {f.tid, 0, 0};
+      blockIdx = {b % s.grid.x, (b / s.grid.x) % s.grid.y, b / (s.grid.x * s.grid.y)};
+      swapcontext(&s.sched, &f.ctx);
+      if (f.done) { --remaining; rounds = 0; }
+    }
+  }
+  s.current = -1;
+  for (const Cta& k : s.ctas)
+    for (size_t g = k.smem_bytes; g < k.smem_bytes + kGuardBytes; ++g)
+      if (k.dyn_smem[g] != (char)0xCD) {
+        std::fprintf(stderr, "cuda_emu: CTA %u wrote %zu bytes past its %zu bytes of dynamic shared memory\n", k.index,
+                     g - k.smem_bytes + 1, k.smem_bytes);
+        std::abort();
+      }
+}
+
+// Runs `body` once per thread of every CTA of the grid (1-D blocks only).  concurrent == false: the CTAs execute one after
+// another (x fastest) -- `static` stand-ins for __shared__ variables are then private to the running CTA.  concurrent ==
+// true: all CTAs are resident at once, as a persistent kernel with grid-wide hand-offs needs (such kernels must keep their
+// CTA-local state in dynamic shared memory).
+inline void launch(dim3 grid, dim3 block3, size_t smem_bytes, std::function<void()> body, bool concurrent = false) {
   State& s = st();
   if (block3.y != 1 || block3.z != 1) { std::fprintf(stderr, "cuda_emu: only 1-D blocks are emulated\n"); std::abort(); }
   const unsigned block = block3.x;
   s.body = std::move(body);
+  s.grid = grid;
   gridDim = {grid.x, grid.y, grid.z};
   blockDim = {block, 1, 1};
   const unsigned n_ctas = grid.x * grid.y * grid.z;
-  for (unsigned b = 0; b < n_ctas; ++b) {
-    blockIdx = {b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y)};
-    s.nthreads = block;
-    s.cta_arrived = 0;
-    const unsigned nwarps = (block + 31) / 32;
-    s.warp_arrived.assign(nwarps, 0);
-    s.warp_gen.assign(nwarps, 0);
-    s.warp_buf.assign((size_t)nwarps * 32 * 8, 0);
-    // poison: reads of unwritten shared memory become visible; the tail is a guard zone checked after the CTA has run
-    s.dyn_smem.assign(smem_bytes + kGuardBytes, (char)0xCD);
-    s.fibers.clear();
-    s.fibers.resize(block);
-    for (unsigned t = 0; t < block; ++t) {
-      Fiber& f = s.fibers[t];
-      f.tid = t;
-      f.stack.resize(kStackBytes);
-      getcontext(&f.ctx);
-      f.ctx.uc_stack.ss_sp = f.stack.data();
-      f.ctx.uc_stack.ss_size = f.stack.size();
-      f.ctx.uc_link = &s.sched;
-      makecontext(&f.ctx, (void (*)())fiber_entry, 0);
-    }
-    unsigned remaining = block;
-    std::vector<unsigned> order(block);
-    for (unsigned t = 0; t < block; ++t) order[t] = t;
-    uint64_t rng = s.rng ? (s.rng * 0x9E3779B97F4A7C15ull + b + 1) : 0;
-    while (remaining) {
-      if (rng) {  // seeded Fisher-Yates reshuffle of the resume order each round
-        for (unsigned i = block - 1; i > 0; --i) {
-          rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
-          std::swap(order[i], order[rng % (i + 1)]);
-        }
-      }
-      for (unsigned i = 0; i < block; ++i) {
-        const unsigned t = order[i];
-        Fiber& f = s.fibers[t];
-        if (f.done) continue;
-        s.current = (int)t;
-        threadIdx = {t, 0, 0};
-        swapcontext(&s.sched, &f.ctx);
-        if (f.done) --remaining;
-      }
-    }
-    s.current = -1;
-    for (size_t g = smem_bytes; g < smem_bytes + kGuardBytes; ++g)
-      if (s.dyn_smem[g] != (char)0xCD) {
-        std::fprintf(stderr, "cuda_emu: CTA %u wrote %zu bytes past its %zu bytes of dynamic shared memory\n", b,
-                     g - smem_bytes + 1, smem_bytes);
-        std::abort();
-      }
-  }
+  if (concurrent) run_ctas(0, n_ctas, block, smem_bytes);
+  else for (unsigned b = 0; b < n_ctas; ++b) run_ctas(b, 1, block, smem_bytes);
 }
 
 // round-to-nearest (ties away) conversion to TF32, as cvt.rna.tf32.f32
@@ -255,6 +316,7 @@ inline T shfl_exchange(T v, unsigned src_lane) {
 inline void __syncthreads() { emu::cta_barrier(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
 inline void __threadfence() {}
+inline void __nanosleep(unsigned) { emu::yield(); }
 template <typename T>
 inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return emu::shfl_exchange(v, (threadIdx.x & 31) ^ (unsigned)lane_mask); }
 template <typename T>
@@ -303,5 +365,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   emu::warp_barrier();
   return bits;
 }
+inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 using std::max;
 using std::min;

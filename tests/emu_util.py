@@ -19,7 +19,8 @@ _lib = None
 
 # translation units of the emulator library: the harness (which #includes the fused row-tile kernels it drives directly)
 # plus the kernel files that only need their real entry points
-SEPARATE_TUS = ['pair_score.cu', 'gather_scatter.cu', 'dense.cu', 'graph_prop.cu', 'neg_sample.cu', 'topk_score.cu']
+SEPARATE_TUS = ['pair_score.cu', 'gather_scatter.cu', 'dense.cu', 'graph_prop.cu', 'neg_sample.cu', 'topk_score.cu',
+                'steps_persistent.cu']
 
 
 def _deps():
@@ -215,7 +216,7 @@ def patched_ops(sms=3, seed=0):
     for extra in ('graph', 'sampler', 'sampler.crossdomain_sampler', 'trainer', 'data'):
         importlib.import_module('recbole_cdr_b200.' + extra)
     replace = {xl.call: call, xl.cur_stream: (lambda: None), ops._require_cuda_f32: req_f32, ops._ids: ids,
-               xl.workspace: workspace}
+               xl.workspace: workspace, ops._on_device: (lambda t: True)}
     undo = []
     for name, mod in list(sys.modules.items()):
         if not name.startswith('recbole_cdr_b200') or mod is None:

@@ -213,7 +213,7 @@ def patched_ops(sms=3, seed=0):
     # every loaded module of the package that bound the _lib / ops helpers by name gets the emulator versions
     import sys
     import importlib
-    for extra in ('graph', 'sampler', 'sampler.crossdomain_sampler', 'trainer', 'data'):
+    for extra in ('graph', 'sampler', 'sampler.crossdomain_sampler', 'trainer', 'data', 'shard'):
         importlib.import_module('recbole_cdr_b200.' + extra)
     replace = {xl.call: call, xl.cur_stream: (lambda: None), ops._require_cuda_f32: req_f32, ops._ids: ids,
                xl.workspace: workspace, ops._on_device: (lambda t: True)}

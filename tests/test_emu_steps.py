@@ -56,3 +56,46 @@ def test_train_steps_pointwise(kind):
         gi_ref += di
     torch.testing.assert_close(gu, gu_ref, rtol=1e-4, atol=1e-4 * gu_ref.abs().max().item())
     torch.testing.assert_close(gi, gi_ref, rtol=1e-4, atol=1e-4 * gi_ref.abs().max().item())
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_row_sharded_steps_equal_the_unsharded_oracle(world):
+    """E1 on one host: the tables are split block-cyclically into ``world`` shards (row r -> shard r mod G, local row
+    r div G), every "rank" runs its own batches through xdr_train_steps_sharded against ALL shards (host pointers stand in
+    for the CUDA-IPC peer mappings), gradients land in the owners' shards.  Per-batch losses and the re-assembled gradient
+    tables must equal the oracle over the union of the batches."""
+    from recbole_cdr_b200.shard import RowShardedTable, train_steps_sharded
+    K, B, dim, nu, ni = 2, 64, 64, 301, 403
+    ut, it, u, ip, ineg, _ = setup(nu, ni, dim, K * world, B, 11)
+    with emu_util.patched_ops(sms=2):
+        def shards(full):
+            tabs = [RowShardedTable.from_full(full, r, world, 'cpu') for r in range(world)]
+            for t in tabs:
+                t._ptrs = [s.local.data_ptr() for s in tabs]
+            return tabs
+        tu, ti = shards(ut), shards(it)
+        gu, gi = shards(torch.zeros_like(ut)), shards(torch.zeros_like(it))
+        losses = []
+        for r in range(world):
+            sl = slice(r * K, (r + 1) * K)
+            out8 = train_steps_sharded(tu[r], ti[r], gu[r], gi[r], u[sl].contiguous(), ip[sl].contiguous(),
+                                       ineg[sl].contiguous(), reg_weight=0.01)
+            losses.append(out8[:, 0].clone())
+
+    def assemble(tabs, n_rows):
+        full = torch.empty((tabs[0].local.shape[0] * world, dim))
+        for r, t in enumerate(tabs):
+            full[r::world] = t.local
+        return full[:n_rows]
+
+    a, b = ut.clone().requires_grad_(True), it.clone().requires_grad_(True)
+    gu_ref, gi_ref = torch.zeros_like(ut), torch.zeros_like(it)
+    for k in range(K * world):
+        ref = O.emcdr_bpr_loss(a, b, u[k], ip[k], ineg[k], 0.01)
+        torch.testing.assert_close(torch.cat(losses)[k], ref.detach()[0], rtol=1e-4, atol=0)
+        du, di = O.grads_of(ref, [a, b])
+        gu_ref += du
+        gi_ref += di
+    torch.testing.assert_close(assemble(gu, nu), gu_ref, rtol=1e-4, atol=1e-4 * gu_ref.abs().max().item())
+    torch.testing.assert_close(assemble(gi, ni), gi_ref, rtol=1e-4, atol=1e-4 * gi_ref.abs().max().item())
+    assert torch.equal(assemble(tu, nu), ut)      # the weight shards are only read

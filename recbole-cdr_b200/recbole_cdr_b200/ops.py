@@ -13,6 +13,8 @@ Table gradients come in two modes (``set_table_grad_mode``):
   the table, skipping one dense zero-fill and one dense add per use of a table.  ``loss.backward()`` leaves the same
   ``.grad`` contents; ``torch.autograd.grad`` does not see table gradients in this mode.
 """
+import ctypes as _ct
+import os as _os
 from typing import List, Optional, Sequence
 
 import torch
@@ -21,12 +23,8 @@ from . import _lib
 from ._lib import call, cur_stream, ptr
 
 _TABLE_GRAD_MODE = 'autograd'
-CHECK_IDS = False  # set True (or env XDR_CHECK_IDS=1) to raise IndexError on out-of-range ids (adds a sync per op)
-
-import os as _os
-
-if _os.environ.get('XDR_CHECK_IDS', '0') == '1':
-    CHECK_IDS = True
+# set True (or env XDR_CHECK_IDS=1) to raise IndexError on out-of-range ids (adds a sync per op)
+CHECK_IDS = _os.environ.get('XDR_CHECK_IDS', '0') == '1'
 
 
 def set_table_grad_mode(mode: str):

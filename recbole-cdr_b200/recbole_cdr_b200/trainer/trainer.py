@@ -278,6 +278,8 @@ class CrossDomainTrainer(object):
             raise ValueError('train_epoch_device needs a single-term fused step spec (e.g. EMCDR SOURCE / TARGET phase)')
         K = steps_per_launch or max(self.fused_steps, 1)
         total = torch.zeros((), dtype=torch.float32, device=spec['user_tab'].device)
+        if self.row_optimizer is not None:
+            return self._train_epoch_device_row_sparse(domain_data, batch_size, spec, K, generator, total)
         scale = -float(self.learning_rate) * float(spec.get('loss_weight', 1.0))
         for ids, label in domain_data.epoch_blocks(batch_size, K, pairwise=spec['pairwise'], generator=generator):
             out8, _, _ = ops.train_steps(spec['user_tab'].data, spec['item_tab'].data, ids[:, 0], ids[:, 1],
@@ -286,6 +288,28 @@ class CrossDomainTrainer(object):
                                          gamma=spec.get('gamma', 1e-10), user_dst=spec['user_tab'].data,
                                          item_dst=spec['item_tab'].data, scale=scale)
             total = total + out8[:, 0].sum()
+        self._check_nan(total)
+        return float(total.item())
+
+    def _train_epoch_device_row_sparse(self, domain_data, batch_size, spec, K, generator, total):
+        """Device pipeline with a row-sparse Adagrad / lazy-Adam / SGD step after EVERY batch (sequential semantics, unlike
+        the asynchronous fused-SGD launch): per step one persistent-kernel launch that scatter-adds the batch's gradient
+        rows into the gradient tables, then one optimizer kernel per table over the batch's ids, which also re-zeroes the
+        rows it consumed.  No host work per step; the losses are read once per epoch."""
+        ut, it = spec['user_tab'], spec['item_tab']
+        for t in (ut, it):
+            if t.grad is None:
+                t.grad = torch.zeros_like(t)
+        weight = float(spec.get('loss_weight', 1.0))
+        for ids, label in domain_data.epoch_blocks(batch_size, K, pairwise=spec['pairwise'], generator=generator):
+            for k in range(ids.shape[0]):
+                out8, _, _ = ops.train_steps(ut.data, it.data, ids[k:k + 1, 0], ids[k:k + 1, 1],
+                                             ids[k:k + 1, 2] if spec['pairwise'] else None,
+                                             None if label is None else label[k:k + 1],
+                                             loss_kind=spec.get('loss_kind', _lib.LOSS_MSE), reg_weight=spec['reg_weight'],
+                                             gamma=spec.get('gamma', 1e-10), user_dst=ut.grad, item_dst=it.grad, scale=weight)
+                self.row_optimizer.step([(ut, ids[k, 0]), (it, ids[k, 1:])])
+                total = total + out8[0, 0]
         self._check_nan(total)
         return float(total.item())
 

@@ -99,3 +99,81 @@ def test_row_sharded_steps_equal_the_unsharded_oracle(world):
     torch.testing.assert_close(assemble(gu, nu), gu_ref, rtol=1e-4, atol=1e-4 * gu_ref.abs().max().item())
     torch.testing.assert_close(assemble(gi, ni), gi_ref, rtol=1e-4, atol=1e-4 * gi_ref.abs().max().item())
     assert torch.equal(assemble(tu, nu), ut)      # the weight shards are only read
+
+
+def test_device_pipeline_epoch_trains_without_host_batches():
+    """The CPU twin of tests/test_gpu_trainer.py::test_device_pipeline_epoch_trains_without_host_batches: positives
+    permuted and negatives drawn by the sampler kernel -> [K, 3, B] blocks -> persistent launches with the SGD update fused
+    into the scatter (trainer.train_epoch_device), all through the emulator."""
+    from fake_data import FakeDataset, base_config
+    from recbole_cdr_b200.data import DeviceDomainData
+    from recbole_cdr_b200.sampler import CrossDomainSourceSampler
+    from recbole_cdr_b200.utils import ModelType, get_model, get_trainer
+    ds = FakeDataset(41, 60, 50, 1, 90, 80)
+    rng = np.random.RandomState(0)
+    su, si = ds.valid_ids('source')
+    s_u, s_i = rng.choice(su, 700), rng.choice(si, 700)
+    with emu_util.patched_ops(sms=2):
+        smp = CrossDomainSourceSampler('train', ds, user_ids=s_u, item_ids=s_i, device='cpu').set_phase('train')
+        data = DeviceDomainData(s_u, s_i, smp, device='cpu')
+        blocks = list(data.epoch_blocks(64, 4, pairwise=True, generator=torch.Generator().manual_seed(1)))
+        assert sum(b[0].shape[0] for b in blocks) == 700 // 64 and blocks[0][0].shape == (4, 3, 64)
+        used = set(zip(s_u.tolist(), s_i.tolist()))
+        valid_items = set(si.tolist())
+        for u, n in zip(blocks[0][0][:, 0].reshape(-1).tolist(), blocks[0][0][:, 2].reshape(-1).tolist()):
+            assert n in valid_items and (u, n) not in used
+        cfg = base_config(device='cpu', latent_factor_model='BPR', source_embedding_size=64, target_embedding_size=64,
+                          reg_weight=0.0, mapping_function='non_linear', mlp_hidden_size=[128], learner='sgd',
+                          learning_rate=20.0, weight_decay=0.0, train_modes=['SOURCE'], epoch_num=['1'], source_split=False)
+        torch.manual_seed(2022)
+        model = get_model('EMCDR')(cfg, ds)
+        model.set_phase('SOURCE')
+        trainer = get_trainer(ModelType.CROSSDOMAIN, 'EMCDR')(cfg, model)
+        losses = [trainer.train_epoch_device(data, 64, steps_per_launch=4) for _ in range(4)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0] - 1e-3, losses
+
+
+def test_device_pipeline_with_row_sparse_adagrad_equals_dense_torch_adagrad():
+    """train_epoch_device with ``xdr_row_optimizer: adagrad``: per batch one persistent-kernel launch (gradient rows into
+    the gradient tables) + one optimizer kernel per table.  The tables after an epoch equal the oracle loss stepped by the
+    dense torch.optim.Adagrad on the very same batches."""
+    from fake_data import FakeDataset, base_config
+    from recbole_cdr_b200.data import DeviceDomainData
+    from recbole_cdr_b200.sampler import CrossDomainSourceSampler
+    from recbole_cdr_b200.utils import ModelType, get_model, get_trainer
+    ds = FakeDataset(41, 60, 50, 1, 90, 80)
+    rng = np.random.RandomState(0)
+    su, si = ds.valid_ids('source')
+    s_u, s_i = rng.choice(su, 300), rng.choice(si, 300)
+    with emu_util.patched_ops(sms=2):
+        smp = CrossDomainSourceSampler('train', ds, user_ids=s_u, item_ids=s_i, device='cpu').set_phase('train')
+        data = DeviceDomainData(s_u, s_i, smp, device='cpu')
+        cfg = base_config(device='cpu', latent_factor_model='BPR', source_embedding_size=64, target_embedding_size=64,
+                          reg_weight=0.01, mapping_function='non_linear', mlp_hidden_size=[128], learner='adagrad',
+                          learning_rate=0.05, weight_decay=0.0, train_modes=['SOURCE'], epoch_num=['1'], source_split=False,
+                          xdr_row_optimizer='adagrad')
+        torch.manual_seed(2022)
+        model = get_model('EMCDR')(cfg, ds)
+        model.set_phase('SOURCE')
+        u0 = model.source_user_embedding.weight.detach().clone()
+        i0 = model.source_item_embedding.weight.detach().clone()
+        trainer = get_trainer(ModelType.CROSSDOMAIN, 'EMCDR')(cfg, model)
+        # the same blocks the trainer will see: same sampler call count, same permutation seed
+        smp_ref = CrossDomainSourceSampler('train', ds, user_ids=s_u, item_ids=s_i, device='cpu').set_phase('train')
+        blocks = list(DeviceDomainData(s_u, s_i, smp_ref, device='cpu').epoch_blocks(
+            64, 2, pairwise=True, generator=torch.Generator().manual_seed(3)))
+        loss = trainer.train_epoch_device(data, 64, steps_per_launch=2, generator=torch.Generator().manual_seed(3))
+    a, b = u0.clone().requires_grad_(True), i0.clone().requires_grad_(True)
+    opt = torch.optim.Adagrad([a, b], lr=0.05)
+    ref_total = 0.0
+    for ids, _ in blocks:
+        for k in range(ids.shape[0]):
+            opt.zero_grad()
+            l = O.emcdr_bpr_loss(a, b, ids[k, 0], ids[k, 1], ids[k, 2], 0.01)
+            l.sum().backward()
+            opt.step()
+            ref_total += float(l.detach())
+    assert abs(loss - ref_total) <= 1e-4 * abs(ref_total)
+    torch.testing.assert_close(model.source_user_embedding.weight.detach(), a.detach(), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(model.source_item_embedding.weight.detach(), b.detach(), rtol=1e-4, atol=1e-6)
+    assert not model.source_user_embedding.weight.grad.any() and not model.source_item_embedding.weight.grad.any()

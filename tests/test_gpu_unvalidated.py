@@ -289,3 +289,41 @@ def test_f4_dcdcsr_four_stages(tag):
     m.set_phase('TARGET')
     torch.testing.assert_close(m.affine_embedding.cpu(), g.t('affine_embedding'), rtol=1e-4, atol=1e-6)
     check_loss_and_grads(m, g, cuda_batch(g))
+
+
+def test_device_pipeline_with_row_sparse_adagrad_equals_dense_torch_adagrad():
+    """GPU twin of tests/test_emu_steps.py: train_epoch_device + xdr_row_optimizer == dense torch Adagrad on the oracle loss."""
+    from recbole_cdr_b200.data import DeviceDomainData
+    from recbole_cdr_b200.sampler import CrossDomainSourceSampler
+    from recbole_cdr_b200.utils import ModelType, get_model, get_trainer
+    ds = FakeDataset(201, 300, 280, 1, 500, 450)
+    rng = np.random.RandomState(0)
+    su, si = ds.valid_ids('source')
+    s_u, s_i = rng.choice(su, 6000), rng.choice(si, 6000)
+    cfg = base_config(latent_factor_model='BPR', source_embedding_size=64, target_embedding_size=64, reg_weight=0.01,
+                      mapping_function='non_linear', mlp_hidden_size=[128], learner='adagrad', learning_rate=0.05,
+                      weight_decay=0.0, train_modes=['SOURCE'], epoch_num=['1'], source_split=False, xdr_row_optimizer='adagrad')
+    torch.manual_seed(2022)
+    model = get_model('EMCDR')(cfg, ds).to('cuda')
+    model.set_phase('SOURCE')
+    u0 = model.source_user_embedding.weight.detach().cpu().clone()
+    i0 = model.source_item_embedding.weight.detach().cpu().clone()
+    trainer = get_trainer(ModelType.CROSSDOMAIN, 'EMCDR')(cfg, model)
+    mk = lambda: DeviceDomainData(s_u, s_i, CrossDomainSourceSampler('train', ds, user_ids=s_u, item_ids=s_i,
+                                                                     device='cuda').set_phase('train'))
+    blocks = list(mk().epoch_blocks(1024, 2, pairwise=True, generator=torch.Generator(device='cuda').manual_seed(3)))
+    loss = trainer.train_epoch_device(mk(), 1024, steps_per_launch=2, generator=torch.Generator(device='cuda').manual_seed(3))
+    a, b = u0.clone().requires_grad_(True), i0.clone().requires_grad_(True)
+    opt = torch.optim.Adagrad([a, b], lr=0.05)
+    ref_total = 0.0
+    for ids, _ in blocks:
+        ids = ids.cpu()
+        for k in range(ids.shape[0]):
+            opt.zero_grad()
+            l = O.emcdr_bpr_loss(a, b, ids[k, 0], ids[k, 1], ids[k, 2], 0.01)
+            l.sum().backward()
+            opt.step()
+            ref_total += float(l.detach())
+    assert abs(loss - ref_total) <= 1e-4 * abs(ref_total)
+    torch.testing.assert_close(model.source_user_embedding.weight.detach().cpu(), a.detach(), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(model.source_item_embedding.weight.detach().cpu(), b.detach(), rtol=1e-4, atol=1e-6)

@@ -49,5 +49,7 @@ class DeviceDomainData(object):
         if pairwise:
             return torch.stack([u, i, neg], dim=1).contiguous(), None
         ids = torch.stack([torch.cat([u, u], dim=1), torch.cat([i, neg], dim=1)], dim=1).contiguous()
-        label = torch.cat([torch.ones_like(u, dtype=torch.float32), torch.zeros_like(u, dtype=torch.float32)], dim=1)
-        return ids, label.contiguous()
+        # the persistent kernel walks ids and labels with ONE step stride: the label rows live in a [K, 2, B] block too
+        label = torch.zeros((k, 2, 2 * pos), dtype=torch.float32, device=ids.device)[:, 0]
+        label[:, :pos] = 1.0
+        return ids, label

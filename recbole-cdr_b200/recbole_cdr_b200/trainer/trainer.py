@@ -291,6 +291,53 @@ class CrossDomainTrainer(object):
         self._check_nan(total)
         return float(total.item())
 
+    def train_epoch_device_both(self, source_data, target_data, batch_size, specs=None, steps_per_launch=None,
+                                generator=None):
+        """BOTH-mode epoch on the device for models whose loss is a weighted sum of one term per domain on shared tables
+        (CMF, cmf.py:81-99): the epoch has as many steps as the TARGET domain has batches and the source domain's batches
+        restart when they run out (reference data/dataloader.py:129-137,156-159).  Per block of K steps: one persistent
+        launch per term, SGD update fused (``-lr * loss_weight``).  Returns the summed weighted per-step loss."""
+        specs = specs or self.model.fused_step_spec()
+        if not isinstance(specs, (list, tuple)) or len(specs) != 2:
+            raise ValueError('train_epoch_device_both needs a [source term, target term] fused step spec (e.g. CMF)')
+        K = steps_per_launch or max(self.fused_steps, 1)
+        dev = specs[0]['user_tab'].device
+        total = torch.zeros((), dtype=torch.float32, device=dev)
+
+        def source_blocks():
+            while True:  # the source loader silently restarts (dataloader.py:156-159)
+                got = False
+                for blk in source_data.epoch_blocks(batch_size, K, pairwise=specs[0]['pairwise'], generator=generator):
+                    got = True
+                    yield blk
+                if not got:
+                    raise ValueError('the source domain has fewer interactions than one batch')
+
+        def run(sp, ids, lab):
+            w = float(sp.get('loss_weight', 1.0))
+            out8, _, _ = ops.train_steps(sp['user_tab'].data, sp['item_tab'].data, ids[:, 0], ids[:, 1],
+                                         ids[:, 2] if sp['pairwise'] else None, lab,
+                                         loss_kind=sp.get('loss_kind', _lib.LOSS_MSE), reg_weight=sp['reg_weight'],
+                                         gamma=sp.get('gamma', 1e-10), user_dst=sp['user_tab'].data,
+                                         item_dst=sp['item_tab'].data, scale=-float(self.learning_rate) * w)
+            return w * out8[:, 0].sum()
+
+        src = source_blocks()
+        pending = None   # source steps left over from the previous block
+        for t_ids, t_lab in target_data.epoch_blocks(batch_size, K, pairwise=specs[1]['pairwise'], generator=generator):
+            need = t_ids.shape[0]
+            while need > 0:      # as many source steps as target steps in this block (views: the step stride is kept)
+                if pending is None:
+                    pending = next(src)
+                s_ids, s_lab = pending
+                take = min(need, s_ids.shape[0])
+                total = total + run(specs[0], s_ids[:take], None if s_lab is None else s_lab[:take])
+                pending = (s_ids[take:], None if s_lab is None else s_lab[take:]) if take < s_ids.shape[0] else None
+                need -= take
+            total = total + run(specs[1], t_ids, t_lab)
+        self._check_nan(total)
+        return float(total.item())
+
     def _train_epoch_device_row_sparse(self, domain_data, batch_size, spec, K, generator, total):
         """Device pipeline with a row-sparse Adagrad / lazy-Adam / SGD step after EVERY batch (sequential semantics, unlike
         the asynchronous fused-SGD launch): per step one persistent-kernel launch that scatter-adds the batch's gradient

@@ -177,3 +177,62 @@ def test_device_pipeline_with_row_sparse_adagrad_equals_dense_torch_adagrad():
     torch.testing.assert_close(model.source_user_embedding.weight.detach(), a.detach(), rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(model.source_item_embedding.weight.detach(), b.detach(), rtol=1e-4, atol=1e-6)
     assert not model.source_user_embedding.weight.grad.any() and not model.source_item_embedding.weight.grad.any()
+
+
+def test_cmf_both_mode_epoch_on_the_device_pipeline():
+    """CMF BOTH mode without host batches: target batches set the epoch length, source batches restart; two persistent
+    launches (source term, target term) per block with the SGD update fused.  The loss must fall over epochs."""
+    from fake_data import FakeDataset, base_config
+    from recbole_cdr_b200.data import DeviceDomainData
+    from recbole_cdr_b200.model.cross_domain_recommender.cmf import CMF
+    from recbole_cdr_b200.sampler import CrossDomainSourceSampler, TargetDomainSampler
+    from recbole_cdr_b200.trainer import CrossDomainTrainer
+    ds = FakeDataset(1, 80, 70, 31, 60, 50)
+    rng = np.random.RandomState(0)
+    su, si = ds.valid_ids('source')
+    tu, ti = ds.valid_ids('target')
+    s_u, s_i = rng.choice(su, 200), rng.choice(si, 200)        # fewer source interactions: the source side restarts
+    t_u, t_i = rng.choice(tu, 520), rng.choice(ti, 520)
+    cfg = base_config(device='cpu', embedding_size=64, alpha=0.4, gamma=0.0, learning_rate=5.0, weight_decay=0.0,
+                      learner='sgd', train_modes=['BOTH'], epoch_num=['1'])
+    cfg['lambda'] = 0.0
+    with emu_util.patched_ops(sms=2):
+        s_smp = CrossDomainSourceSampler('train', ds, user_ids=s_u, item_ids=s_i, device='cpu').set_phase('train')
+        t_smp = TargetDomainSampler(ds.num_total_user, ds.target_domain_dataset.num('target_item_id'), t_u, t_i, device='cpu')
+        sd, td = DeviceDomainData(s_u, s_i, s_smp, device='cpu'), DeviceDomainData(t_u, t_i, t_smp, device='cpu')
+        torch.manual_seed(1)
+        m = CMF(cfg, ds)
+        t = CrossDomainTrainer(cfg, m)
+        w0 = m.user_embedding.weight.detach().clone()
+        losses = [t.train_epoch_device_both(sd, td, 64, steps_per_launch=3) for _ in range(3)]
+    steps = 520 // 32                                  # pointwise: 32 positives + 32 negatives per step
+    assert np.isfinite(losses).all() and losses[-1] < losses[0] - 1e-3, losses
+    assert abs(losses[0] / steps - np.log(2)) < 0.05   # alpha*BCE_s + (1-alpha)*BCE_t starts at ln 2 per step
+    assert not torch.equal(w0, m.user_embedding.weight.detach())
+
+
+def test_device_pipeline_pointwise_blocks_feed_the_persistent_kernel():
+    """EMCDR-MF (pointwise) through train_epoch_device: the label rows share the step stride of the id rows."""
+    from fake_data import FakeDataset, base_config
+    from recbole_cdr_b200.data import DeviceDomainData
+    from recbole_cdr_b200.sampler import CrossDomainSourceSampler
+    from recbole_cdr_b200.utils import ModelType, get_model, get_trainer
+    ds = FakeDataset(41, 60, 50, 1, 90, 80)
+    rng = np.random.RandomState(0)
+    su, si = ds.valid_ids('source')
+    s_u, s_i = rng.choice(su, 400), rng.choice(si, 400)
+    with emu_util.patched_ops(sms=2):
+        smp = CrossDomainSourceSampler('train', ds, user_ids=s_u, item_ids=s_i, device='cpu').set_phase('train')
+        data = DeviceDomainData(s_u, s_i, smp, device='cpu')
+        ids, lab = next(iter(data.epoch_blocks(64, 3, pairwise=False)))
+        assert ids.shape == (3, 2, 64) and lab.shape == (3, 64) and lab.stride(0) == ids[:, 0].stride(0)
+        assert lab[:, :32].all() and not lab[:, 32:].any()
+        cfg = base_config(device='cpu', latent_factor_model='MF', source_embedding_size=64, target_embedding_size=64,
+                          reg_weight=0.0, mapping_function='non_linear', mlp_hidden_size=[128], learner='sgd',
+                          learning_rate=5.0, weight_decay=0.0, train_modes=['SOURCE'], epoch_num=['1'], source_split=False)
+        torch.manual_seed(2022)
+        model = get_model('EMCDR')(cfg, ds)
+        model.set_phase('SOURCE')
+        trainer = get_trainer(ModelType.CROSSDOMAIN, 'EMCDR')(cfg, model)
+        losses = [trainer.train_epoch_device(data, 64, steps_per_launch=3) for _ in range(4)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0] - 1e-3, losses

@@ -12,8 +12,20 @@
 //     C (16x8):       c0 = (g, 2t)  c1 = (g, 2t+1)  c2 = (g+8, 2t)  c3 = (g+8, 2t+1)
 // Shared-memory operands are row-major with a leading dimension ld = width + 4 (ld / 4 odd), so the (g*ld + t) access
 // of an untransposed operand touches 32 distinct banks; transposed operands ((t*ld + g)) see 2-way conflicts.
+//
+// Engine modes (compile-time, -DXDR_TC_MODE=n; build a second library with XDR_LIB_NAME / XDR_BUILD_DIR to compare on hardware):
+//   0  3xTF32, mma.m16n8k8          the default described above
+//   1  bf16x3, mma.m16n8k16         x = hi + lo with hi = bf16(x), lo = bf16(x - hi); a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
+//                                   (~2^-17 relative per product) -- half the MMA instructions per unit of K
+//   2  one TF32 pass                NOT parity-grade (~5e-4 per product); a diagnostic for how tensor-bound a kernel is
+// m16n8k16 bf16 fragments (two bf16 per register, low half = lower k):
+//     A: a0 = (g, 2t..2t+1)  a1 = (g+8, 2t..)  a2 = (g, 2t+8..)  a3 = (g+8, 2t+8..)      B: b0 = (k = 2t..2t+1, n = g)  b1 = (k = 2t+8.., n = g)
 #pragma once
 #include "xdr_common.cuh"
+
+#ifndef XDR_TC_MODE
+#define XDR_TC_MODE 0
+#endif
 
 namespace xdr {
 
@@ -21,6 +33,8 @@ namespace xdr {
 
 constexpr int kTcThreads = 256;
 constexpr int kTcWarps = kTcThreads / 32;
+constexpr int kTcMode = XDR_TC_MODE;
+constexpr int kTcKStep = kTcMode == 1 ? 16 : 8;   // reduction elements one MMA group consumes
 
 __device__ __forceinline__ uint32_t cvt_tf32(float x) {
 #ifdef XDR_EMU
@@ -56,6 +70,103 @@ __device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ah)[4
   mma_tf32(c, ah, bh);
 }
 
+// ---- bf16x3 ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf16_bits(float x) {  // round-to-nearest-even to bf16, returned in the low 16 bits
+  uint32_t u = __float_as_uint(x);
+  if ((u & 0x7f800000u) == 0x7f800000u) return u >> 16;  // inf / nan
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return u >> 16;
+}
+// (x0, x1) -> packed bf16 pairs hi and lo with x ~= hi + lo; element 0 in the low half
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const uint32_t h0 = bf16_bits(x0), h1 = bf16_bits(x1);
+  const float r0 = x0 - __uint_as_float(h0 << 16), r1 = x1 - __uint_as_float(h1 << 16);
+  hi = h0 | (h1 << 16);
+  lo = bf16_bits(r0) | (bf16_bits(r1) << 16);
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+#ifdef XDR_EMU
+  emu::mma_m16n8k16_bf16(c, a, b);
+#else
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+#endif
+}
+
+// One MMA group of the selected engine: c += a * b over kTcKStep reduction elements, operands already split.
+__device__ __forceinline__ void mma_group(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                          const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+  if (kTcMode == 1) {
+    mma_bf16(c, al, bh);
+    mma_bf16(c, ah, bl);
+    mma_bf16(c, ah, bh);
+  } else if (kTcMode == 2) {
+    mma_tf32(c, ah, bh);
+  } else {
+    mma_3xtf32(c, ah, al, bh, bl);
+  }
+}
+
+// Operand fragments of one MMA group from shared memory.  `row_ptr(i)` addresses are formed by the callers:
+//   A fragment of a ROW-MAJOR operand  (element (m, k) at P[m*ld + k]), rows m0+g / m0+g+8, reduction k0..k0+kTcKStep
+//   B fragment of a K-CONTIGUOUS operand (B(k, n) = P[n*ld + k]),        column n0+g
+//   and their transposed forms (reduction index strided by ld).
+// kmax bounds the reduction index (elements >= kmax read as zero: K = 8 tails in bf16 mode).
+__device__ __forceinline__ void frag_a_rowmajor(const float* __restrict__ P, int ld, int m, int k0, int kmax, int t,
+                                                uint32_t (&h)[4], uint32_t (&l)[4]) {
+  if (kTcMode == 1) {
+    const float* p0 = P + m * ld + k0 + 2 * t;
+    const float* p1 = p0 + 8 * ld;
+    const bool lo_ok = k0 + 2 * t < kmax, hi_ok = k0 + 2 * t + 8 < kmax;
+    const float2 z = make_float2(0.f, 0.f);
+    const float2 v0 = lo_ok ? *reinterpret_cast<const float2*>(p0) : z, v1 = lo_ok ? *reinterpret_cast<const float2*>(p1) : z;
+    const float2 v2 = hi_ok ? *reinterpret_cast<const float2*>(p0 + 8) : z, v3 = hi_ok ? *reinterpret_cast<const float2*>(p1 + 8) : z;
+    split_bf16x2(v0.x, v0.y, h[0], l[0]);
+    split_bf16x2(v1.x, v1.y, h[1], l[1]);
+    split_bf16x2(v2.x, v2.y, h[2], l[2]);
+    split_bf16x2(v3.x, v3.y, h[3], l[3]);
+  } else {
+    const float* ap = P + m * ld + k0 + t;
+    split_tf32(ap[0], h[0], l[0]);
+    split_tf32(ap[8 * ld], h[1], l[1]);
+    split_tf32(ap[4], h[2], l[2]);
+    split_tf32(ap[8 * ld + 4], h[3], l[3]);
+  }
+}
+// B(k, n) with n fixed: contiguous == true -> P[n*ld + k]; false -> P[k*ld + n]
+__device__ __forceinline__ void frag_b(const float* __restrict__ P, int ld, int n, int k0, int kmax, int t, bool contiguous,
+                                       uint32_t (&h)[2], uint32_t (&l)[2]) {
+  if (kTcMode == 1) {
+    const int ka = k0 + 2 * t, kb = ka + 8;
+    float x0 = 0.f, x1 = 0.f, y0 = 0.f, y1 = 0.f;
+    if (contiguous) {
+      const float* p = P + n * ld;
+      if (ka < kmax) { const float2 v = *reinterpret_cast<const float2*>(p + ka); x0 = v.x; x1 = v.y; }
+      if (kb < kmax) { const float2 v = *reinterpret_cast<const float2*>(p + kb); y0 = v.x; y1 = v.y; }
+    } else {
+      if (ka < kmax) { x0 = P[ka * ld + n]; x1 = P[(ka + 1) * ld + n]; }
+      if (kb < kmax) { y0 = P[kb * ld + n]; y1 = P[(kb + 1) * ld + n]; }
+    }
+    split_bf16x2(x0, x1, h[0], l[0]);
+    split_bf16x2(y0, y1, h[1], l[1]);
+  } else {
+    float b0, b1;
+    if (contiguous) {
+      const float* bp = P + n * ld + k0 + t;
+      b0 = bp[0];
+      b1 = bp[4];
+    } else {
+      const float* bp = P + (k0 + t) * ld + n;
+      b0 = bp[0];
+      b1 = bp[4 * ld];
+    }
+    split_tf32(b0, h[0], l[0]);
+    split_tf32(b1, h[1], l[1]);
+  }
+}
+
 __device__ __forceinline__ float act_apply(float y, int act) {
   if (act == XDR_ACT_RELU) return y > 0.f ? y : 0.f;
   if (act == XDR_ACT_TANH) return tanhf(y);
@@ -84,32 +195,16 @@ __device__ __forceinline__ void tile_mma_acc(float (&acc)[MAXNT][4], const float
   const int m0 = (warp % MT) * 16, grp = warp / MT;
   const int ntiles = N >> 3;
   if (grp >= ntiles) return;
-  for (int k0 = 0; k0 < K; k0 += 8) {
+  for (int k0 = 0; k0 < K; k0 += kTcKStep) {
     uint32_t ah[4], al[4];
-    const float* ap = A + (m0 + g) * lda + k0 + t;
-    split_tf32(ap[0], ah[0], al[0]);
-    split_tf32(ap[8 * lda], ah[1], al[1]);
-    split_tf32(ap[4], ah[2], al[2]);
-    split_tf32(ap[8 * lda + 4], ah[3], al[3]);
+    frag_a_rowmajor(A, lda, m0 + g, k0, K, t, ah, al);
 #pragma unroll
     for (int j = 0; j < MAXNT; ++j) {
       const int nt = grp + j * G;
       if (nt < ntiles) {  // warp-uniform
-        const int n = nt * 8 + g;
-        float b0, b1;
-        if (!BT) {
-          const float* bp = Bsm + n * ldb + k0 + t;
-          b0 = bp[0];
-          b1 = bp[4];
-        } else {
-          const float* bp = Bsm + (k0 + t) * ldb + n;
-          b0 = bp[0];
-          b1 = bp[4 * ldb];
-        }
         uint32_t bh[2], bl[2];
-        split_tf32(b0, bh[0], bl[0]);
-        split_tf32(b1, bh[1], bl[1]);
-        mma_3xtf32(acc[j], ah, al, bh, bl);
+        frag_b(Bsm, ldb, nt * 8 + g, k0, K, t, !BT, bh, bl);
+        mma_group(acc[j], ah, al, bh, bl);
       }
     }
   }
@@ -210,24 +305,35 @@ __device__ __forceinline__ void dw_accum(float (&acc)[MAXT][4], const float* __r
       const int n0 = (tile / ktiles) * 16, k0 = (tile % ktiles) * 8;
       const bool lo_ok = n0 + g < dout, hi_ok = n0 + g + 8 < dout;
 #pragma unroll 2
-      for (int r0 = 0; r0 < TR; r0 += 8) {
-        const float* zp = dZ + (r0 + t) * ldz + n0 + g;
-        const float mk0 = rmask ? rmask[r0 + t] : 1.f, mk1 = rmask ? rmask[r0 + t + 4] : 1.f;
+      for (int r0 = 0; r0 < TR; r0 += kTcKStep) {
         uint32_t ah[4], al[4], bh[2], bl[2];
-        split_tf32(lo_ok ? mk0 * zp[0] : 0.f, ah[0], al[0]);
-        split_tf32(hi_ok ? mk0 * zp[8] : 0.f, ah[1], al[1]);
-        split_tf32(lo_ok ? mk1 * zp[4 * ldz] : 0.f, ah[2], al[2]);
-        split_tf32(hi_ok ? mk1 * zp[4 * ldz + 8] : 0.f, ah[3], al[3]);
-        const float* xp = X + (r0 + t) * ldx + k0 + g;
-        split_tf32(xp[0], bh[0], bl[0]);
-        split_tf32(xp[4 * ldx], bh[1], bl[1]);
-        mma_3xtf32(acc[j], ah, al, bh, bl);
+        if (kTcMode == 1) {
+          // A(m = output n, k = batch row): a0 = rows r0+2t, +1 at column n0+g; a1 at n0+g+8; a2 / a3 eight rows further
+          const int ra = r0 + 2 * t, rb = ra + 8;
+          const float* za = dZ + ra * ldz + n0 + g;
+          const float* zb = dZ + rb * ldz + n0 + g;
+          const float ma0 = rmask ? rmask[ra] : 1.f, ma1 = rmask ? rmask[ra + 1] : 1.f;
+          const float mb0 = rmask ? rmask[rb] : 1.f, mb1 = rmask ? rmask[rb + 1] : 1.f;
+          split_bf16x2(lo_ok ? ma0 * za[0] : 0.f, lo_ok ? ma1 * za[ldz] : 0.f, ah[0], al[0]);
+          split_bf16x2(hi_ok ? ma0 * za[8] : 0.f, hi_ok ? ma1 * za[ldz + 8] : 0.f, ah[1], al[1]);
+          split_bf16x2(lo_ok ? mb0 * zb[0] : 0.f, lo_ok ? mb1 * zb[ldz] : 0.f, ah[2], al[2]);
+          split_bf16x2(hi_ok ? mb0 * zb[8] : 0.f, hi_ok ? mb1 * zb[ldz + 8] : 0.f, ah[3], al[3]);
+          frag_b(X, ldx, k0 + g, r0, TR, t, false, bh, bl);
+        } else {
+          const float* zp = dZ + (r0 + t) * ldz + n0 + g;
+          const float mk0 = rmask ? rmask[r0 + t] : 1.f, mk1 = rmask ? rmask[r0 + t + 4] : 1.f;
+          split_tf32(lo_ok ? mk0 * zp[0] : 0.f, ah[0], al[0]);
+          split_tf32(hi_ok ? mk0 * zp[8] : 0.f, ah[1], al[1]);
+          split_tf32(lo_ok ? mk1 * zp[4 * ldz] : 0.f, ah[2], al[2]);
+          split_tf32(hi_ok ? mk1 * zp[4 * ldz + 8] : 0.f, ah[3], al[3]);
+          frag_b(X, ldx, k0 + g, r0, TR, t, false, bh, bl);
+        }
+        mma_group(acc[j], ah, al, bh, bl);
       }
     }
   }
 }
 
-// dW row stride ldw (>= din) and column offset k_off let a K chunk of a wider weight be flushed in place.
 template <int MAXT>
 __device__ __forceinline__ void dw_flush(const float (&acc)[MAXT][4], float* __restrict__ dW, int dout, int din, int ldw = -1,
                                          int k_off = 0) {

@@ -299,6 +299,34 @@ inline void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32
   for (int i = 0; i < 4; ++i) c[i] = r[i];
 }
 
+// mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 over the 32 fibers of the calling warp (two bf16 per register)
+inline void mma_m16n8k16_bf16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  const unsigned lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  uint32_t* mine = warp_slot(lane);
+  for (int i = 0; i < 4; ++i) mine[i] = a[i];
+  mine[4] = b[0];
+  mine[5] = b[1];
+  warp_barrier();
+  auto half = [](uint32_t reg, unsigned hi) { return as_float((hi ? (reg >> 16) : (reg & 0xffffu)) << 16); };
+  auto A = [&](unsigned row, unsigned k) {  // a0=(g,2t..) a1=(g+8,2t..) a2=(g,2t+8..) a3=(g+8,2t+8..)
+    const unsigned kk = k & 7, src = (row & 7) * 4 + (kk >> 1), reg = (row >= 8 ? 1 : 0) + (k >= 8 ? 2 : 0);
+    return half(warp_slot(src)[reg], kk & 1);
+  };
+  auto B = [&](unsigned k, unsigned n) {  // b0=(k=2t..2t+1,n=g) b1=(k=2t+8..,n=g)
+    const unsigned kk = k & 7, src = n * 4 + (kk >> 1), reg = 4 + (k >= 8 ? 1 : 0);
+    return half(warp_slot(src)[reg], kk & 1);
+  };
+  float r[4];
+  const unsigned rows[4] = {g, g, g + 8, g + 8}, cols[4] = {2 * t, 2 * t + 1, 2 * t, 2 * t + 1};
+  for (int i = 0; i < 4; ++i) {
+    double s = c[i];
+    for (unsigned k = 0; k < 16; ++k) s += (double)A(rows[i], k) * (double)B(k, cols[i]);
+    r[i] = (float)s;
+  }
+  warp_barrier();
+  for (int i = 0; i < 4; ++i) c[i] = r[i];
+}
+
 template <typename T>
 inline T shfl_exchange(T v, unsigned src_lane) {
   static_assert(sizeof(T) <= 8, "shuffle payload");

@@ -11,10 +11,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 EMU_DIR = os.path.join(HERE, 'emu')
 BUILD_DIR = os.path.join(EMU_DIR, '_build')
-LIB = os.path.join(BUILD_DIR, 'libxdr_emu.so')
 CSRC = os.path.join(ROOT, 'recbole-cdr_b200', 'csrc')
 
-_lib = None
+# engine mode of the tensor-core tile primitives (tc_tile.cuh XDR_TC_MODE): 0 = 3xTF32 (default), 1 = bf16x3, 2 = one TF32 pass
+_mode = 0
+_libs = {}
+
+
+def _lib_path(mode):
+    return os.path.join(BUILD_DIR, 'libxdr_emu.so' if mode == 0 else f'libxdr_emu_m{mode}.so')
 
 
 # translation units of the emulator library: the harness (which #includes the fused row-tile kernels it drives directly)
@@ -28,21 +33,23 @@ def _deps():
         glob.glob(os.path.join(CSRC, '*.cu')) + glob.glob(os.path.join(CSRC, '*.cuh')) + [os.path.join(ROOT, 'include', 'xdr.h')]
 
 
-def _stale():
-    if not os.path.exists(LIB):
+def _stale(path):
+    if not os.path.exists(path):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(path)
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build():
+def build(mode=None):
+    mode = _mode if mode is None else mode
+    LIB = _lib_path(mode)
     os.makedirs(BUILD_DIR, exist_ok=True)
-    if _stale():
+    if _stale(LIB):
         import concurrent.futures as cf
-        flags = ['-O2', '-std=c++17', '-x', 'c++', '-fPIC', '-DXDR_EMU=1', '-I', EMU_DIR, '-I', os.path.join(ROOT, 'include'),
-                 '-Wno-unknown-pragmas', '-Wno-attributes']
+        flags = ['-O2', '-std=c++17', '-x', 'c++', '-fPIC', '-DXDR_EMU=1', f'-DXDR_TC_MODE={mode}', '-I', EMU_DIR,
+                 '-I', os.path.join(ROOT, 'include'), '-Wno-unknown-pragmas', '-Wno-attributes']
         srcs = [os.path.join(EMU_DIR, 'emu_kernels.cpp')] + [os.path.join(CSRC, f) for f in SEPARATE_TUS]
-        objs = [os.path.join(BUILD_DIR, os.path.basename(f) + '.o') for f in srcs]
+        objs = [os.path.join(BUILD_DIR, f'm{mode}_' + os.path.basename(f) + '.o') for f in srcs]
 
         def cc(job):
             src, obj = job
@@ -59,12 +66,28 @@ def build():
 
 
 def lib():
-    global _lib
-    if _lib is None:
-        _lib = ctypes.CDLL(build())
-        _lib.emu_last_error.restype = ctypes.c_char_p
-        _lib.emu_config.argtypes = [ctypes.c_int, ctypes.c_uint64]
-    return _lib
+    if _mode not in _libs:
+        L = ctypes.CDLL(build(_mode))
+        L.emu_last_error.restype = ctypes.c_char_p
+        L.emu_config.argtypes = [ctypes.c_int, ctypes.c_uint64]
+        _libs[_mode] = L
+    return _libs[_mode]
+
+
+class tc_mode:
+    """Context manager: run the emulated kernels with another engine of the tensor-core tile primitives."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        global _mode
+        self.prev, _mode = _mode, self.mode
+        return self
+
+    def __exit__(self, *exc):
+        global _mode
+        _mode = self.prev
 
 
 def config(sms=4, seed=0):

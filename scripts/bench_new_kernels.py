@@ -19,6 +19,7 @@ from recbole_cdr_b200.trainer import GraphedTrainStep
 
 dev = torch.device('cuda', 0)
 SMALL = os.environ.get('XDR_SMALL') == '1'
+SKIP_CHECK = os.environ.get('XDR_SKIP_CHECK') == '1'     # diagnostic engines (one TF32 pass) are not parity-grade
 PEAK = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 OUT = open(os.path.join(ROOT, 'gpurun_out', 'new_kernels.jsonl'), 'a')
@@ -41,7 +42,7 @@ def timeit(fn, reps=5, inner=1):
 
 
 def report(name, sec, bytes_=None, flops=None, units=None, unit_name='inter', **extra):
-    line = {'kernel': name, 'us': round(sec * 1e6, 2)}
+    line = {'kernel': name, 'us': round(sec * 1e6, 2), 'lib': os.path.basename(_lib.LIB_PATH)}
     if bytes_:
         line.update(GBps=round(bytes_ / sec / 1e9, 1), hbm_frac=round(bytes_ / sec / 1e9 / PEAK, 4))
     if flops:
@@ -96,7 +97,7 @@ def emcdr_map_step():
         report(f'A4 EMCDR map step fwd+bwd, {name}, CUDA-graph replay, b = 8192', timeit(lambda: gs(inter), inner=10),
                bytes_=b * 1032, flops=b * 98304, units=b)
         del m, gs
-    assert abs(losses['tc'] - losses[False]) <= 1e-4 * abs(losses[False]), losses
+    assert SKIP_CHECK or abs(losses['tc'] - losses[False]) <= 1e-4 * abs(losses[False]), losses
 
 
 def dtcdr_both_step():
@@ -144,7 +145,7 @@ def conet_both_step():
         report(f'A7-8 CoNet BOTH step fwd+bwd, {name}, CUDA-graph replay', timeit(lambda: gs(ic), reps=3, inner=5),
                bytes_=2 * 16384 * 4116, flops=2 * 16384 * 458000, units=2 * 16384)
         del m, gs
-    assert abs(losses[True] - losses[False]) <= 1e-4 * abs(losses[False]), losses
+    assert SKIP_CHECK or abs(losses[True] - losses[False]) <= 1e-4 * abs(losses[False]), losses
 
 
 def sparse_optimizers():
@@ -194,7 +195,8 @@ def full_sort_topk():
             full[seg, hi] = -float('inf')
             return torch.topk(full, k, dim=1)
         rs, ri = ref()
-        torch.testing.assert_close(sc, rs, rtol=2e-5, atol=1e-6)
+        if not SKIP_CHECK:
+            torch.testing.assert_close(sc, rs, rtol=2e-5, atol=1e-6)
         fl = 2.0 * B * n_items * D
         report(f'F2 fused full-sort top-{k} (NEW), {B} users x {n_items} items, D = 64', timeit(lambda: ops.full_sort_topk(U, I, k, hist_ptr=hp, hist_ids=hi), reps=3),
                bytes_=n_items * D * 4 * ((B + 63) // 64) + B * D * 4, flops=fl, units=B, unit_name='users')
@@ -202,5 +204,8 @@ def full_sort_topk():
                bytes_=B * n_items * 4 * 3, flops=fl, units=B, unit_name='users')
 
 
-for sec in (emcdr_map_step, dtcdr_both_step, conet_both_step, sparse_optimizers, full_sort_topk):
-    section(sec)
+ALL = (emcdr_map_step, dtcdr_both_step, conet_both_step, sparse_optimizers, full_sort_topk)
+WANT = os.environ.get('XDR_SECTIONS')                      # comma-separated subset of the section names
+for sec in ALL:
+    if WANT is None or sec.__name__ in WANT.split(','):
+        section(sec)

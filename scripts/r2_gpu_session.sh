@@ -23,6 +23,18 @@ XDR_SMALL=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control non
     --log-file gpurun_out/new_kernels_launches.csv python scripts/bench_new_kernels.py > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_conet_kernel -s 2 -c 1 \
     -o gpurun_out/tc_conet python scripts/bench_new_kernels.py > /dev/null 2>&1
+# 4b. the alternative tile engines (tc_tile.cuh XDR_TC_MODE): bf16x3 (parity-grade) and one TF32 pass (diagnostic upper bound)
+for m in 1 2; do
+  XDR_EXTRA_NVCC_FLAGS="-DXDR_TC_MODE=$m" XDR_BUILD_DIR=build_m$m XDR_LIB_NAME=libxdr_m$m.so python recbole-cdr_b200/build.py > gpurun_out/build_m$m.log 2>&1
+done
+XDR_LIB=$PWD/recbole-cdr_b200/recbole_cdr_b200/lib/libxdr_m1.so XDR_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_gpu_unvalidated.py -q \
+    -k "tc_mlp or conet_fused or tc_engine or full_sort_topk" --timeout 300 > gpurun_out/unvalidated_bf16x3.log 2>&1
+echo "unvalidated (bf16x3 engine) rc=$?" | tee -a gpurun_out/summary.txt
+for m in 1 2; do
+  XDR_LIB=$PWD/recbole-cdr_b200/recbole_cdr_b200/lib/libxdr_m$m.so XDR_SECTIONS=emcdr_map_step,conet_both_step,full_sort_topk XDR_SKIP_CHECK=$((m-1)) \
+      timeout 600 python scripts/bench_new_kernels.py > gpurun_out/new_kernels_m$m.log 2>&1
+  echo "bench_new_kernels (XDR_TC_MODE=$m) rc=$?" | tee -a gpurun_out/summary.txt
+done
 # 5. the tcgen05 descriptor experiment (which operand layouts / descriptor readings the hardware accepts)
 nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o /tmp/ubench_tcgen05 scripts/ubench_tcgen05.cu > gpurun_out/tcgen05.log 2>&1 \
     && timeout 120 /tmp/ubench_tcgen05 >> gpurun_out/tcgen05.log 2>&1

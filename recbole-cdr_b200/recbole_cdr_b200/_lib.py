@@ -133,12 +133,18 @@ def cur_stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _device_key(device: torch.device) -> int:
+    if device.index is not None:
+        return device.index
+    return torch.cuda.current_device() if device.type == 'cuda' else -1
+
+
 _workspaces = {}
 
 
 def workspace(device: torch.device) -> torch.Tensor:
     """Zero-initialised scratch private to (device, current stream); kernels leave it clean (xdr.h `ws`)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), cur_stream())
+    key = (_device_key(device), cur_stream())
     ws = _workspaces.get(key)
     if ws is None:
         ws = torch.zeros(workspace_bytes(), dtype=torch.uint8, device=device)
@@ -150,7 +156,7 @@ _oob_flags = {}
 
 
 def oob_flag(device: torch.device) -> torch.Tensor:
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    key = _device_key(device)
     f = _oob_flags.get(key)
     if f is None:
         f = torch.zeros(1, dtype=torch.int32, device=device)

@@ -20,6 +20,9 @@
 //   phase 2, per K chunk: load the weight chunk once, then per tile: re-gather the x chunk (L2), read the tile's scratch
 //                        rows, accumulate the chunk of dWs_0, dWt_0, dH_0 in registers, form the chunk of dx_s, dx_t and
 //                        scatter-add it (red.global.add.v4.f32) into the four gradient tables.
+// Cross terms only matter for overlapped rows (m = 1): each CTA re-orders its rows so that the overlapped ones come first,
+// and a 16-row MMA tile without any overlapped row skips its cross products (forward c_s / c_t, the m * (dZ H) half of the
+// input gradients, the masked halves of dH) -- at 50 % overlap that is a quarter of the layer-0 MMAs.
 // Both towers run through every layer; only the wanted tower feeds the loss, so the other tower's last-layer parameters
 // receive exact zeros (PyTorch leaves their .grad untouched -- None/zero -- for the same reason).
 //
@@ -36,6 +39,7 @@ constexpr int kCnMaxHidden = 64; // widest hidden layer
 constexpr int kCnNT0 = 4;        // layer-0 output tiles per warp: hidden_0 / 8 / (kTcWarps / (kCnTR / 16))
 constexpr int kCnDw0 = 4;        // layer-0 chunk weight-gradient tiles per warp and matrix: ceil(64/16) * (64/8) / 8
 constexpr int kCnDw1 = 4, kCnDw2 = 2, kCnDw3 = 1;  // tail layers 1..3, per matrix
+constexpr int kCnMaxPerm = 2048; // rows of one CTA that can be re-ordered (overlapped rows first)
 
 struct ConetArgs {
   int n_layers;                  // L cross-stitch layers (1..4)
@@ -77,7 +81,7 @@ struct ConetArgs {
 struct ConetSmem {
   int tailW[kCnMaxLayers][3];    // float offsets of Ws_l, Wt_l, H_l (l >= 1), row stride dims[l] + 4
   int bias[kCnMaxLayers][2];     // bs_l, bt_l
-  int wout, mask, grow, bufX[2], wch[3];
+  int wout, mask, grow, trow, perm, bufX[2], wch[3];
   int act[kCnMaxLayers + 1][2];  // l >= 2 (l == 1 aliases bufX)
   int grd[kCnMaxLayers + 1][2];  // l >= 2
   int dz[2];                     // phase 2: the tile's scratch rows
@@ -95,6 +99,8 @@ __host__ __device__ inline ConetSmem conet_smem_layout(int L, const int* dims) {
   s.wout = p; p += up4(dims[L]) + 4;
   s.mask = p; p += kCnTR;
   s.grow = p; p += kCnTR;
+  s.trow = p; p += kCnTR;        // global row of each slot of the current tile (int32, -1 = none)
+  s.perm = p; p += kCnMaxPerm;   // this CTA's rows, overlapped ones first (int32)
   const int ldc = kCnKC + 4;
   for (int m = 0; m < 2; ++m) { s.bufX[m] = p; p += kCnTR * ldc; }
   for (int m = 0; m < 3; ++m) { s.wch[m] = p; p += dims[1] * ldc; }
@@ -131,16 +137,18 @@ __device__ __forceinline__ CnCol conet_col(const ConetArgs& a, int tower, int64_
   return c;
 }
 
-// gathers columns [kc*KC, (kc+1)*KC) of x_s and x_t for the tile's rows and refreshes the overlap mask
-__device__ __forceinline__ void conet_gather_chunk(const ConetArgs& a, int64_t r0, int rows, int kc, float* xs, float* xt,
-                                                   float* mask) {
+// gathers columns [kc*KC, (kc+1)*KC) of x_s and x_t for the tile's rows (trow[r] = global row of slot r, -1 = empty slot)
+// and refreshes the overlap mask
+__device__ __forceinline__ void conet_gather_chunk(const ConetArgs& a, const int* __restrict__ trow, int kc, float* xs,
+                                                   float* xt, float* mask) {
   constexpr int C4 = kCnKC / 4, ldc = kCnKC + 4;
   for (int e = threadIdx.x; e < 2 * kCnTR * C4; e += kTcThreads) {
     const int tower = e / (kCnTR * C4), rem = e - tower * (kCnTR * C4);
     const int r = rem / C4, c4 = rem - r * C4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < rows) {
-      const CnCol c = conet_col(a, tower, r0 + r, kc * kCnKC + 4 * c4);
+    const int row = trow[r];
+    if (row >= 0) {
+      const CnCol c = conet_col(a, tower, row, kc * kCnKC + 4 * c4);
       if (c.ok) v = ld_row4(c.tab + c.id * a.dim, c.col4);
       else if (a.oob) *a.oob = 1;
     }
@@ -148,12 +156,20 @@ __device__ __forceinline__ void conet_gather_chunk(const ConetArgs& a, int64_t r
   }
   for (int r = threadIdx.x; r < kCnTR; r += kTcThreads) {
     float m = 0.f;
-    if (r < rows) {
-      const int64_t id = a.mask_on_item ? a.item[r0 + r] : a.user[r0 + r];
+    const int row = trow[r];
+    if (row >= 0) {
+      const int64_t id = a.mask_on_item ? a.item[row] : a.user[row];
       m = id < a.n_overlap ? 1.f : 0.f;
     }
     mask[r] = m;
   }
+}
+
+// true when any of the 16 rows of this warp's MMA row tile is overlapped (warp-uniform): otherwise its cross products vanish
+__device__ __forceinline__ bool conet_mtile_overlaps(const float* __restrict__ mask) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = (warp % (kCnTR / 16)) * 16;
+  return __any_sync(0xffffffffu, mask[m0 + (lane & 15)] != 0.f) != 0;
 }
 
 // loads columns [kc*KC, (kc+1)*KC) of Ws_0, Wt_0, H_0 ([N1][K0] each) as three [N1][KC + 4] slabs
@@ -206,7 +222,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conet_kernel(ConetArgs a, Wo
       smem[lay.bias[l][1] + n] = a.bt[l] ? a.bt[l][n] : 0.f;
     }
   for (int k = tid; k < dL; k += kTcThreads) wout[k] = a.w_out[k];
+
+  // ---- this CTA's rows: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Slot p of that list (p = local tile * 64 + r) is
+  // batch row perm[p]; overlapped rows come first, so that whole 16-row MMA tiles without any overlapped row can skip
+  // their cross products (the reference computes them for every row and multiplies by zero, conet.py:128-134).
+  const int64_t n_tiles = (a.batch + TR - 1) / TR;
+  const int my_tiles = (int)((n_tiles - (int64_t)blockIdx.x + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x);
+  int* const trow = reinterpret_cast<int*>(smem + lay.trow);
+  int* const perm = reinterpret_cast<int*>(smem + lay.perm);
+  const bool use_perm = my_tiles * TR <= kCnMaxPerm;
+  auto natural_row = [&](int p) -> int64_t {   // slot p in tile order; -1 past the batch
+    const int64_t row = ((int64_t)blockIdx.x + (int64_t)(p / TR) * gridDim.x) * TR + (p % TR);
+    return row < a.batch ? row : (int64_t)-1;
+  };
+  if (use_perm && tid < 32) {  // warp 0: stable partition (overlapped | others | empty) by ballot prefix sums
+    const int P = my_tiles * TR;
+    int n_ov = 0, n_valid = 0;
+    for (int p0 = 0; p0 < P; p0 += 32) {
+      const int64_t row = natural_row(p0 + tid);
+      bool ov = false;
+      if (row >= 0) ov = (a.mask_on_item ? a.item[row] : a.user[row]) < a.n_overlap;
+      n_ov += __popc(__ballot_sync(0xffffffffu, ov));
+      n_valid += __popc(__ballot_sync(0xffffffffu, row >= 0));
+    }
+    int at_ov = 0, at_rest = n_ov, at_none = n_valid;
+    for (int p0 = 0; p0 < P; p0 += 32) {
+      const int64_t row = natural_row(p0 + tid);
+      bool ov = false;
+      if (row >= 0) ov = (a.mask_on_item ? a.item[row] : a.user[row]) < a.n_overlap;
+      const unsigned b_ov = __ballot_sync(0xffffffffu, ov), b_rest = __ballot_sync(0xffffffffu, row >= 0 && !ov),
+                     b_none = __ballot_sync(0xffffffffu, row < 0);
+      const unsigned below = (1u << tid) - 1u;
+      if (ov) perm[at_ov + __popc(b_ov & below)] = (int)row;
+      else if (row >= 0) perm[at_rest + __popc(b_rest & below)] = (int)row;
+      else perm[at_none + __popc(b_none & below)] = -1;
+      at_ov += __popc(b_ov);
+      at_rest += __popc(b_rest);
+      at_none += __popc(b_none);
+    }
+  }
   __syncthreads();
+  auto load_tile_rows = [&](int ti) {  // fills trow for local tile ti (followed by a barrier at the call sites)
+    for (int r = tid; r < TR; r += kTcThreads) trow[r] = use_perm ? perm[ti * TR + r] : (int)natural_row(ti * TR + r);
+  };
 
   // weight-gradient accumulators of the tail layers (MMA C fragments, alive over all tiles of phase 1)
   float aWs1[kCnDw1][4], aWt1[kCnDw1][4], aH1[kCnDw1][4];
@@ -220,24 +278,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conet_kernel(ConetArgs a, Wo
 
   const float g_up = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f);
   float loss_acc[1] = {0.f};
-  const int64_t n_tiles = (a.batch + TR - 1) / TR;
 
   // =============================== phase 1: forward, head, tail backward ===================================================
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t r0 = tile * TR;
-    const int rows = (int)min((int64_t)TR, a.batch - r0);
+  for (int ti = 0; ti < my_tiles; ++ti) {
+    load_tile_rows(ti);
+    __syncthreads();
+    bool cross = true;  // does this warp's 16-row MMA tile hold an overlapped row? (set once the mask is in shared memory)
     // ---- layer 0, K-chunked: a_s = x_s Ws^T, c_s = x_t H^T, a_t = x_t Wt^T, c_t = x_s H^T -------------------------------
     {
       float a_s[kCnNT0][4], c_s[kCnNT0][4], a_t[kCnNT0][4], c_t[kCnNT0][4];
       tile_acc_zero(a_s); tile_acc_zero(c_s); tile_acc_zero(a_t); tile_acc_zero(c_t);
       for (int kc = 0; kc < nkc; ++kc) {
-        conet_gather_chunk(a, r0, rows, kc, xs, xt, mask);
+        conet_gather_chunk(a, trow, kc, xs, xt, mask);
         conet_load_wchunk(a, kc, wch);
         __syncthreads();
+        if (kc == 0) cross = conet_mtile_overlaps(mask);
         tile_mma_acc<TR, kCnNT0, false>(a_s, xs, ldc, wch[0], ldc, N1, KC);
-        tile_mma_acc<TR, kCnNT0, false>(c_s, xt, ldc, wch[2], ldc, N1, KC);
+        if (cross) tile_mma_acc<TR, kCnNT0, false>(c_s, xt, ldc, wch[2], ldc, N1, KC);
         tile_mma_acc<TR, kCnNT0, false>(a_t, xt, ldc, wch[1], ldc, N1, KC);
-        tile_mma_acc<TR, kCnNT0, false>(c_t, xs, ldc, wch[2], ldc, N1, KC);
+        if (cross) tile_mma_acc<TR, kCnNT0, false>(c_t, xs, ldc, wch[2], ldc, N1, KC);
         __syncthreads();
       }
       const float* b0s = smem + lay.bias[0][0];
@@ -264,13 +323,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conet_kernel(ConetArgs a, Wo
       const float* btl = smem + lay.bias[l][1];
       float* os = act(l + 1, 0);
       float* ot = act(l + 1, 1);
-      tile_gemm2_any<TR, false>(act(l, 0), ldi, Wsl, ldw, act(l, 1), ldi, Hl, ldw, dout, din,
+      tile_gemm2_any<TR, false>(act(l, 0), ldi, Wsl, ldw, act(l, 1), ldi, Hl, ldw, dout, din, cross,
                                 [&](int row, int col, float v0, float v1, float c0, float c1) {
                                   const float m = mask[row];
                                   *reinterpret_cast<float2*>(os + row * ldo + col) =
                                       make_float2(fmaxf(v0 + bsl[col] + m * c0, 0.f), fmaxf(v1 + bsl[col + 1] + m * c1, 0.f));
                                 });
-      tile_gemm2_any<TR, false>(act(l, 1), ldi, Wtl, ldw, act(l, 0), ldi, Hl, ldw, dout, din,
+      tile_gemm2_any<TR, false>(act(l, 1), ldi, Wtl, ldw, act(l, 0), ldi, Hl, ldw, dout, din, cross,
                                 [&](int row, int col, float v0, float v1, float c0, float c1) {
                                   const float m = mask[row];
                                   *reinterpret_cast<float2*>(ot + row * ldo + col) =
@@ -286,12 +345,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conet_kernel(ConetArgs a, Wo
       const float bo = a.b_out ? __ldg(a.b_out) : 0.f;
       for (int r = tid; r < TR; r += kTcThreads) {
         float g = 0.f;
-        if (r < rows) {
+        const int row = trow[r];
+        if (row >= 0) {
           float z = bo;
           for (int k = 0; k < dL; ++k) z = fmaf(aw[r * ldL + k], wout[k], z);
-          const float pz = sigmoidf_(z), y = a.label[r0 + r];
+          const float pz = sigmoidf_(z), y = a.label[row];
           loss_acc[0] += -(y * fmaxf(logf(pz), -100.f) + (1.f - y) * fmaxf(logf(1.f - pz), -100.f));
-          if (a.prob) a.prob[r0 + r] = pz;
+          if (a.prob) a.prob[row] = pz;
           const float pq = pz * (1.f - pz);
           g = gs * (pz - y) / fmaxf(pq, 1e-12f) * pq;
         }
@@ -317,9 +377,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conet_kernel(ConetArgs a, Wo
       if (L > 1) {
         grd(L, a.want)[r * ldL + k] = gw;
         grd(L, 1 - a.want)[r * ldL + k] = 0.f;
-      } else if (r < rows) {
-        a.dz1[(size_t)(r0 + r) * 2 * N1 + a.want * N1 + k] = gw;
-        a.dz1[(size_t)(r0 + r) * 2 * N1 + (1 - a.want) * N1 + k] = 0.f;
+      } else if (trow[r] >= 0) {
+        a.dz1[(size_t)trow[r] * 2 * N1 + a.want * N1 + k] = gw;
+        a.dz1[(size_t)trow[r] * 2 * N1 + (1 - a.want) * N1 + k] = 0.f;
       }
     }
     __syncthreads();
@@ -362,21 +422,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conet_kernel(ConetArgs a, Wo
       float* gt_out = l > 1 ? grd(l, 1) : nullptr;
       float* dz1 = a.dz1;
       // dx_s = dZs Ws + m * (dZt H);  dx_t = dZt Wt + m * (dZs H);  then times relu'(layer input) = the previous layer's dZ
-      tile_gemm2_any<TR, true>(dZs, ldz, Wsl, ldw, dZt, ldz, Hl, ldw, din, dout,
+      tile_gemm2_any<TR, true>(dZs, ldz, Wsl, ldw, dZt, ldz, Hl, ldw, din, dout, cross,
                                [&](int row, int col, float v0, float v1, float c0, float c1) {
                                  const float m = mask[row];
                                  const float2 y = *reinterpret_cast<const float2*>(Xs + row * ldi + col);
                                  const float2 o = make_float2(y.x > 0.f ? v0 + m * c0 : 0.f, y.y > 0.f ? v1 + m * c1 : 0.f);
                                  if (gs_out) *reinterpret_cast<float2*>(gs_out + row * ldi + col) = o;
-                                 else if (row < rows) *reinterpret_cast<float2*>(dz1 + (size_t)(r0 + row) * 2 * N1 + col) = o;
+                                 else if (trow[row] >= 0) *reinterpret_cast<float2*>(dz1 + (size_t)trow[row] * 2 * N1 + col) = o;
                                });
-      tile_gemm2_any<TR, true>(dZt, ldz, Wtl, ldw, dZs, ldz, Hl, ldw, din, dout,
+      tile_gemm2_any<TR, true>(dZt, ldz, Wtl, ldw, dZs, ldz, Hl, ldw, din, dout, cross,
                                [&](int row, int col, float v0, float v1, float c0, float c1) {
                                  const float m = mask[row];
                                  const float2 y = *reinterpret_cast<const float2*>(Xt + row * ldi + col);
                                  const float2 o = make_float2(y.x > 0.f ? v0 + m * c0 : 0.f, y.y > 0.f ? v1 + m * c1 : 0.f);
                                  if (gt_out) *reinterpret_cast<float2*>(gt_out + row * ldi + col) = o;
-                                 else if (row < rows) *reinterpret_cast<float2*>(dz1 + (size_t)(r0 + row) * 2 * N1 + N1 + col) = o;
+                                 else if (trow[row] >= 0) *reinterpret_cast<float2*>(dz1 + (size_t)trow[row] * 2 * N1 + N1 + col) = o;
                                });
       __syncthreads();
     }
@@ -405,15 +465,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conet_kernel(ConetArgs a, Wo
       float a0s[kCnDw0][4], a0t[kCnDw0][4], a0h[kCnDw0][4];
       tile_acc_zero(a0s); tile_acc_zero(a0t); tile_acc_zero(a0h);
       conet_load_wchunk(a, kc, wch);
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t r0 = tile * TR;
-        const int rows = (int)min((int64_t)TR, a.batch - r0);
-        conet_gather_chunk(a, r0, rows, kc, xs, xt, mask);
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        load_tile_rows(ti);
+        __syncthreads();
+        conet_gather_chunk(a, trow, kc, xs, xt, mask);
         for (int e = tid; e < 2 * TR * (N1 / 4); e += kTcThreads) {
           const int tower = e / (TR * (N1 / 4)), rem = e - tower * (TR * (N1 / 4));
           const int r = rem / (N1 / 4), c4 = rem - r * (N1 / 4);
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < rows) v = *reinterpret_cast<const float4*>(a.dz1 + (size_t)(r0 + r) * 2 * N1 + tower * N1 + 4 * c4);
+          if (trow[r] >= 0) v = *reinterpret_cast<const float4*>(a.dz1 + (size_t)trow[r] * 2 * N1 + tower * N1 + 4 * c4);
           *reinterpret_cast<float4*>((tower ? dzt : dzs) + r * ld1 + 4 * c4) = v;
         }
         __syncthreads();
@@ -433,22 +493,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conet_kernel(ConetArgs a, Wo
         dw_accum<TR>(a0h, dzs, ld1, xt, ldc, N1, KC, mask);
         dw_accum<TR>(a0h, dzt, ld1, xs, ldc, N1, KC, mask);
         __syncthreads();  // x chunk fully consumed: it is overwritten by the dx chunk
-        tile_gemm2<TR, kCnKC / 16, true>(dzs, ld1, wch[0], ldc, dzt, ld1, wch[2], ldc, KC, N1,
+        const bool cross = conet_mtile_overlaps(mask);
+        tile_gemm2<TR, kCnKC / 16, true>(dzs, ld1, wch[0], ldc, dzt, ld1, wch[2], ldc, KC, N1, cross,
                                          [&](int row, int col, float v0, float v1, float c0, float c1) {
                                            const float m = mask[row];
                                            *reinterpret_cast<float2*>(xs + row * ldc + col) = make_float2(v0 + m * c0, v1 + m * c1);
                                          });
-        tile_gemm2<TR, kCnKC / 16, true>(dzt, ld1, wch[1], ldc, dzs, ld1, wch[2], ldc, KC, N1,
+        tile_gemm2<TR, kCnKC / 16, true>(dzt, ld1, wch[1], ldc, dzs, ld1, wch[2], ldc, KC, N1, cross,
                                          [&](int row, int col, float v0, float v1, float c0, float c1) {
                                            const float m = mask[row];
                                            *reinterpret_cast<float2*>(xt + row * ldc + col) = make_float2(v0 + m * c0, v1 + m * c1);
                                          });
         __syncthreads();
         constexpr int C4 = KC / 4;
-        for (int e = tid; e < 2 * rows * C4; e += kTcThreads) {
-          const int tower = e / (rows * C4), rem = e - tower * (rows * C4);
+        for (int e = tid; e < 2 * TR * C4; e += kTcThreads) {
+          const int tower = e / (TR * C4), rem = e - tower * (TR * C4);
           const int r = rem / C4, c4 = rem - r * C4;
-          const CnCol c = conet_col(a, tower, r0 + r, kc * KC + 4 * c4);
+          if (trow[r] < 0) continue;
+          const CnCol c = conet_col(a, tower, trow[r], kc * KC + 4 * c4);
           if (!c.ok) continue;
           red_add4(c.dtab + c.id * a.dim, c.col4,
                    scale4(a.scale, *reinterpret_cast<const float4*>((tower ? xt : xs) + r * ldc + 4 * c4)));

@@ -246,15 +246,17 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
 
 // Two products over the same output tile: C1 = A1 * B1, C2 = A2 * B2 (same N, K and BT); epi(row, col, v0, v1, c0, c1).
 // The cross-stitch unit of CoNet (conet.py:118-138): v = own tower, c = cross term, combined per row by the overlap mask.
+// do2 (warp-uniform): false skips the second product for this warp's row tile (its C2 is then zero) -- CoNet row tiles
+// without an overlapped row.
 template <int TR, int MAXNT, bool BT, typename Epi>
 __device__ __forceinline__ void tile_gemm2(const float* __restrict__ A1, int lda1, const float* __restrict__ B1, int ldb1,
                                            const float* __restrict__ A2, int lda2, const float* __restrict__ B2, int ldb2,
-                                           int N, int K, Epi epi) {
+                                           int N, int K, bool do2, Epi epi) {
   float acc[MAXNT][4], acc2[MAXNT][4];
   tile_acc_zero(acc);
   tile_acc_zero(acc2);
   tile_mma_acc<TR, MAXNT, BT>(acc, A1, lda1, B1, ldb1, N, K);
-  tile_mma_acc<TR, MAXNT, BT>(acc2, A2, lda2, B2, ldb2, N, K);
+  if (do2) tile_mma_acc<TR, MAXNT, BT>(acc2, A2, lda2, B2, ldb2, N, K);
   tile_acc_visit<TR, MAXNT>(N, [&](int j, int row, int col, int half) {
     epi(row, col, acc[j][2 * half], acc[j][2 * half + 1], acc2[j][2 * half], acc2[j][2 * half + 1]);
   });
@@ -274,13 +276,13 @@ __device__ __forceinline__ void tile_gemm_any(const float* A, int lda, const flo
 
 template <int TR, bool BT, typename Epi>
 __device__ __forceinline__ void tile_gemm2_any(const float* A1, int lda1, const float* B1, int ldb1, const float* A2, int lda2,
-                                               const float* B2, int ldb2, int N, int K, Epi epi) {
+                                               const float* B2, int ldb2, int N, int K, bool do2, Epi epi) {
   constexpr int G = kTcWarps / (TR / 16);
   const int per_warp = ((N >> 3) + G - 1) / G;
-  if (per_warp <= 1) tile_gemm2<TR, 1, BT>(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, N, K, epi);
-  else if (per_warp <= 2) tile_gemm2<TR, 2, BT>(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, N, K, epi);
-  else if (per_warp <= 4) tile_gemm2<TR, 4, BT>(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, N, K, epi);
-  else tile_gemm2<TR, 8, BT>(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, N, K, epi);
+  if (per_warp <= 1) tile_gemm2<TR, 1, BT>(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, N, K, do2, epi);
+  else if (per_warp <= 2) tile_gemm2<TR, 2, BT>(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, N, K, do2, epi);
+  else if (per_warp <= 4) tile_gemm2<TR, 4, BT>(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, N, K, do2, epi);
+  else tile_gemm2<TR, 8, BT>(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, N, K, do2, epi);
 }
 
 // Number of 16x8 tiles of a [dout][din] weight gradient and how many of them each warp owns (tile i -> warp i % kTcWarps).
@@ -306,6 +308,12 @@ __device__ __forceinline__ void dw_accum(float (&acc)[MAXT][4], const float* __r
       const bool lo_ok = n0 + g < dout, hi_ok = n0 + g + 8 < dout;
 #pragma unroll 2
       for (int r0 = 0; r0 < TR; r0 += kTcKStep) {
+        if (rmask != nullptr) {  // a reduction step whose rows are all masked out contributes nothing (same for every lane)
+          float any = 0.f;
+#pragma unroll
+          for (int q = 0; q < kTcKStep; ++q) any += rmask[r0 + q];
+          if (any == 0.f) continue;
+        }
         uint32_t ah[4], al[4], bh[2], bl[2];
         if (kTcMode == 1) {
           // A(m = output n, k = batch row): a0 = rows r0+2t, +1 at column n0+g; a1 at n0+g+8; a2 / a3 eight rows further

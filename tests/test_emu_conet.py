@@ -103,3 +103,30 @@ def test_conet_supported_stacks():
     assert not ok([32, 16, 8], 16)           # 2*dim must be a multiple of the 64-column K chunk
     assert not ok([256, 128, 64], 128)       # hidden wider than 64
     assert not ok([256, 64, 12], 128)        # hidden width not a multiple of 8
+
+
+@pytest.mark.parametrize('n_ov_case,batch,sms', [('all', 80, 2), ('none', 80, 2), ('mixed_no_perm', 2200, 1)])
+def test_conet_row_reordering_and_cross_term_skipping(n_ov_case, batch, sms):
+    """Rows are re-ordered per CTA (overlapped first) so that 16-row MMA tiles without an overlapped row skip their cross
+    products: all rows overlapped (nothing skipped), none overlapped (every cross product skipped), and a CTA with more rows
+    than the re-ordering buffer holds (natural order, skipping still decided per tile)."""
+    dims, tabs, P, user, item, label, n_ov, lt, lp, ref, prob = make_case(batch, 32, [16], 0, True)
+    n_ov = {'all': 10 ** 6, 'none': 0, 'mixed_no_perm': n_ov}[n_ov_case]
+    lt = {k: v.detach().clone().requires_grad_(True) for k, v in tabs.items()}
+    lp = {k: ([x.detach().clone().requires_grad_(True) for x in v] if isinstance(v, list) else v.detach().clone().requires_grad_(True))
+          for k, v in P.items()}
+    ps, _ = O.conet_towers(lt, user, item, lp, True, n_ov)
+    ref = O.bce_loss(ps, label)
+    ref.backward()
+    emu_util.config(sms=sms, seed=0)
+    Pk = dict(ws=P['ws'], bs=P['bs'], wt=P['wt'], bt=P['bt'], h=P['h'], out_w=P['out_s_w'], out_b=P['out_s_b'])
+    r = emu_util.conet_step(dims, {k: ([x.numpy() for x in v] if isinstance(v, list) else v.numpy()) for k, v in Pk.items()}, 0,
+                            (tabs['source_user'].numpy(), tabs['source_item'].numpy(), tabs['target_user'].numpy(),
+                             tabs['target_item'].numpy()), user.numpy(), item.numpy(), label.numpy(), mask_on_item=False,
+                            n_overlap=n_ov)
+    assert abs(r['loss'] - ref.item()) <= 1e-4 * abs(ref.item())
+    np.testing.assert_allclose(r['prob'], ps.detach().numpy(), rtol=1e-4, atol=1e-6)
+    for k, name in enumerate(('source_user', 'source_item', 'target_user', 'target_item')):
+        close(r['dtabs'][k], lt[name].grad, name)
+    for key in ('ws', 'bs', 'wt', 'bt', 'h'):
+        close(r['grads'][key][0], lp[key][0].grad, f'{key}[0]')

@@ -293,10 +293,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conet_kernel(ConetArgs a, Wo
         conet_load_wchunk(a, kc, wch);
         __syncthreads();
         if (kc == 0) cross = conet_mtile_overlaps(mask);
-        tile_mma_acc<TR, kCnNT0, false>(a_s, xs, ldc, wch[0], ldc, N1, KC);
-        if (cross) tile_mma_acc<TR, kCnNT0, false>(c_s, xt, ldc, wch[2], ldc, N1, KC);
-        tile_mma_acc<TR, kCnNT0, false>(a_t, xt, ldc, wch[1], ldc, N1, KC);
-        if (cross) tile_mma_acc<TR, kCnNT0, false>(c_t, xs, ldc, wch[2], ldc, N1, KC);
+        tile_mma_acc2<TR, kCnNT0, false>(a_s, c_t, xs, ldc, wch[0], ldc, wch[2], ldc, N1, KC, cross);  // x_s: Ws and H
+        tile_mma_acc2<TR, kCnNT0, false>(a_t, c_s, xt, ldc, wch[1], ldc, wch[2], ldc, N1, KC, cross);  // x_t: Wt and H
         __syncthreads();
       }
       const float* b0s = smem + lay.bias[0][0];
@@ -494,16 +492,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conet_kernel(ConetArgs a, Wo
         dw_accum<TR>(a0h, dzt, ld1, xs, ldc, N1, KC, mask);
         __syncthreads();  // x chunk fully consumed: it is overwritten by the dx chunk
         const bool cross = conet_mtile_overlaps(mask);
-        tile_gemm2<TR, kCnKC / 16, true>(dzs, ld1, wch[0], ldc, dzt, ld1, wch[2], ldc, KC, N1, cross,
-                                         [&](int row, int col, float v0, float v1, float c0, float c1) {
-                                           const float m = mask[row];
-                                           *reinterpret_cast<float2*>(xs + row * ldc + col) = make_float2(v0 + m * c0, v1 + m * c1);
-                                         });
-        tile_gemm2<TR, kCnKC / 16, true>(dzt, ld1, wch[1], ldc, dzs, ld1, wch[2], ldc, KC, N1, cross,
-                                         [&](int row, int col, float v0, float v1, float c0, float c1) {
-                                           const float m = mask[row];
-                                           *reinterpret_cast<float2*>(xt + row * ldc + col) = make_float2(v0 + m * c0, v1 + m * c1);
-                                         });
+        {  // dx_s = dZs Ws + m (dZt H),  dx_t = dZt Wt + m (dZs H): each dZ operand is split once for its two products
+          constexpr int NTX = kCnKC / 16;
+          float d_ss[NTX][4], d_sh[NTX][4], d_tt[NTX][4], d_th[NTX][4];
+          tile_acc_zero(d_ss); tile_acc_zero(d_sh); tile_acc_zero(d_tt); tile_acc_zero(d_th);
+          tile_mma_acc2<TR, NTX, true>(d_ss, d_sh, dzs, ld1, wch[0], ldc, wch[2], ldc, KC, N1, cross);
+          tile_mma_acc2<TR, NTX, true>(d_tt, d_th, dzt, ld1, wch[1], ldc, wch[2], ldc, KC, N1, cross);
+          tile_acc_visit<TR, NTX>(KC, [&](int j, int row, int col, int h) {
+            const float m = mask[row];
+            *reinterpret_cast<float2*>(xs + row * ldc + col) =
+                make_float2(d_ss[j][2 * h] + m * d_th[j][2 * h], d_ss[j][2 * h + 1] + m * d_th[j][2 * h + 1]);
+            *reinterpret_cast<float2*>(xt + row * ldc + col) =
+                make_float2(d_tt[j][2 * h] + m * d_sh[j][2 * h], d_tt[j][2 * h + 1] + m * d_sh[j][2 * h + 1]);
+          });
+        }
         __syncthreads();
         constexpr int C4 = KC / 4;
         for (int e = tid; e < 2 * TR * C4; e += kTcThreads) {

@@ -210,6 +210,36 @@ __device__ __forceinline__ void tile_mma_acc(float (&acc)[MAXNT][4], const float
   }
 }
 
+// Two products that share the A operand: acc1 += A * B1, acc2 += A * B2 (same N, K, BT).  The A fragments are loaded and
+// split once per reduction step for both.  do2 (warp-uniform) == false leaves acc2 untouched.
+template <int TR, int MAXNT, bool BT>
+__device__ __forceinline__ void tile_mma_acc2(float (&acc1)[MAXNT][4], float (&acc2)[MAXNT][4], const float* __restrict__ A,
+                                              int lda, const float* __restrict__ B1, int ldb1, const float* __restrict__ B2,
+                                              int ldb2, int N, int K, bool do2) {
+  constexpr int MT = TR / 16, G = kTcWarps / MT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = (warp % MT) * 16, grp = warp / MT;
+  const int ntiles = N >> 3;
+  if (grp >= ntiles) return;
+  for (int k0 = 0; k0 < K; k0 += kTcKStep) {
+    uint32_t ah[4], al[4];
+    frag_a_rowmajor(A, lda, m0 + g, k0, K, t, ah, al);
+#pragma unroll
+    for (int j = 0; j < MAXNT; ++j) {
+      const int nt = grp + j * G;
+      if (nt < ntiles) {  // warp-uniform
+        uint32_t bh[2], bl[2];
+        frag_b(B1, ldb1, nt * 8 + g, k0, K, t, !BT, bh, bl);
+        mma_group(acc1[j], ah, al, bh, bl);
+        if (do2) {
+          frag_b(B2, ldb2, nt * 8 + g, k0, K, t, !BT, bh, bl);
+          mma_group(acc2[j], ah, al, bh, bl);
+        }
+      }
+    }
+  }
+}
+
 template <int MAXNT>
 __device__ __forceinline__ void tile_acc_zero(float (&acc)[MAXNT][4]) {
 #pragma unroll

@@ -22,29 +22,23 @@ class CLFM(CrossDomainRecommender):
         self.SOURCE_LABEL = dataset.source_domain_dataset.label_field
         self.TARGET_LABEL = dataset.target_domain_dataset.label_field
 
-        self.user_embedding_size = config['user_embedding_size']
-        self.source_item_embedding_size = config['source_item_embedding_size']
+        du, di, shared = config['user_embedding_size'], config['source_item_embedding_size'], config['share_embedding_size']
         # the reference reads 'source_item_embedding_size' for the target side as well (clfm.py:37): kept, so that the
         # same config builds the same shapes
-        self.target_item_embedding_size = config['source_item_embedding_size']
-        self.share_embedding_size = config['share_embedding_size']
-        self.alpha = config['alpha']
-        self.reg_weight = config['reg_weight']
-        assert 0 <= self.share_embedding_size <= self.source_item_embedding_size and \
-            0 <= self.share_embedding_size <= self.target_item_embedding_size
-
-        self.source_user_embedding = nn.Embedding(self.total_num_users, self.user_embedding_size)
-        self.target_user_embedding = nn.Embedding(self.total_num_users, self.user_embedding_size)
-        self.source_item_embedding = nn.Embedding(self.total_num_items, self.source_item_embedding_size)
-        self.target_item_embedding = nn.Embedding(self.total_num_items, self.target_item_embedding_size)
-        if self.share_embedding_size > 0:
-            self.shared_linear = nn.Linear(self.user_embedding_size, self.share_embedding_size, bias=False)
-        if self.source_item_embedding_size - self.share_embedding_size > 0:
-            self.source_only_linear = nn.Linear(self.user_embedding_size,
-                                                self.source_item_embedding_size - self.share_embedding_size, bias=False)
-        if self.target_item_embedding_size - self.share_embedding_size > 0:
-            self.target_only_linear = nn.Linear(self.user_embedding_size,
-                                                self.target_item_embedding_size - self.share_embedding_size, bias=False)
+        self.user_embedding_size, self.share_embedding_size = du, shared
+        self.source_item_embedding_size = self.target_item_embedding_size = di
+        self.alpha, self.reg_weight = config['alpha'], config['reg_weight']
+        if not 0 <= shared <= di:
+            raise AssertionError('share_embedding_size must lie in [0, item embedding size]')
+        # registration order == the reference's (clfm.py:47-63): user tables, item tables, shared / source-only / target-only
+        for side, rows, width in (('user', self.total_num_users, du), ('item', self.total_num_items, di)):
+            for domain in ('source', 'target'):
+                setattr(self, f'{domain}_{side}_embedding', nn.Embedding(rows, width))
+        if shared > 0:
+            self.shared_linear = nn.Linear(du, shared, bias=False)
+        for domain in ('source', 'target'):
+            if di - shared > 0:
+                setattr(self, f'{domain}_only_linear', nn.Linear(du, di - shared, bias=False))
         self.apply(xavier_normal_initialization)
 
     def _factor_weight(self, domain):

@@ -48,13 +48,14 @@ class NATR(CrossDomainRecommender):
             self.history_lens = lens.to(dev)
             self.mask_mat = (torch.arange(hist.shape[1]) < lens.unsqueeze(1)).float().to(dev)
 
-        self.source_user_embedding = nn.Embedding(self.total_num_users, self.source_embedding_size)
-        self.source_item_embedding = nn.Embedding(self.total_num_items, self.source_embedding_size)
-        self.target_user_embedding = nn.Embedding(self.total_num_users, self.target_embedding_size)
-        self.target_item_embedding = nn.Embedding(self.total_num_items, self.target_embedding_size)
-        self.transfer_layer = nn.Linear(self.source_embedding_size, self.target_embedding_size)
-        self.unit_attention_layer = nn.Linear(self.target_embedding_size, 1)
-        self.domain_attention_layer = nn.Linear(self.target_embedding_size, 1)
+        ds, dt = self.source_embedding_size, self.target_embedding_size
+        # registration order == the reference's (natr.py:60-72): source user/item, target user/item, then the three layers
+        for domain, width in (('source', ds), ('target', dt)):
+            for side, rows in (('user', self.total_num_users), ('item', self.total_num_items)):
+                setattr(self, f'{domain}_{side}_embedding', nn.Embedding(rows, width))
+        self.transfer_layer = nn.Linear(ds, dt)
+        for name in ('unit_attention_layer', 'domain_attention_layer'):
+            setattr(self, name, nn.Linear(dt, 1))
         # the zero-fill of dead rows (natr.py:64-68) is overwritten by the init below (natr.py:77)
         self.apply(xavier_normal_initialization)
 

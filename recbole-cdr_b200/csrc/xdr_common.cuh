@@ -232,7 +232,7 @@ __device__ __forceinline__ void grid_reduce_last_block(float (&v)[NV], Workspace
 // residency is the caller's business (grid <= #SMs); emulator: all CTAs run under one fiber scheduler.
 #ifdef XDR_EMU
 #define XDR_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) \
-  emu::launch(grid, block, smem, [&] { kernel(__VA_ARGS__); }, /*concurrent=*/true)
+  emu::launch(grid, block, smem, [=] { kernel(__VA_ARGS__); }, /*concurrent=*/true)  /* by value: may run deferred */
 #else
 #define XDR_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif

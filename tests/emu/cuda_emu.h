@@ -65,8 +65,16 @@ struct MBar {  // emulated mbarrier: phase completes when every expected arrival
   }
 };
 
+struct LaunchRec {  // one kernel launch: geometry + the code every thread runs
+  dim3 grid;
+  unsigned block = 0;
+  size_t smem_bytes = 0;
+  std::function<void()> body;
+};
+
 struct Cta {
   unsigned nthreads = 0, index = 0;
+  int launch = 0;                                // index into State::launches
   unsigned arrived = 0, gen = 0;               // CTA barrier
   std::vector<unsigned> warp_arrived, warp_gen;  // per-warp collectives
   std::vector<uint32_t> warp_buf;                // [n_warps][32][8] exchange words
@@ -87,8 +95,9 @@ struct State {
   std::vector<Fiber> fibers;
   std::vector<Cta> ctas;
   int current = -1;
-  dim3 grid;
-  std::function<void()> body;
+  std::vector<LaunchRec> launches;  // the launch(es) whose CTAs are resident now
+  bool grouping = false;            // group_begin() .. group_run(): concurrent launches are queued, then run TOGETHER
+  std::vector<LaunchRec> queued;
   uint64_t rng = 0;  // 0 = round-robin
   uint64_t clock = 0;
 };
@@ -168,46 +177,52 @@ namespace emu {
 
 inline void fiber_entry() {
   State& s = st();
-  s.body();
+  s.launches[s.ctas[s.fibers[s.current].cta].launch].body();
   s.fibers[s.current].done = true;
   swapcontext(&s.fibers[s.current].ctx, &s.sched);
 }
 
-// Runs the fibers of CTAs [first, first + count) of the current launch to completion under one scheduler.
-inline void run_ctas(unsigned first, unsigned count, unsigned block, size_t smem_bytes) {
+// Runs the fibers of the given (launch, CTA index) pairs to completion under one scheduler.
+inline void run_ctas(const std::vector<std::pair<int, unsigned>>& which) {
   State& s = st();
+  const unsigned count = (unsigned)which.size();
   s.ctas.assign(count, Cta());
-  const unsigned nwarps = (block + 31) / 32;
+  unsigned n = 0;
   for (unsigned c = 0; c < count; ++c) {
+    const LaunchRec& L = s.launches[which[c].first];
     Cta& k = s.ctas[c];
-    k.nthreads = block;
-    k.index = first + c;
+    const unsigned nwarps = (L.block + 31) / 32;
+    k.nthreads = L.block;
+    k.index = which[c].second;
+    k.launch = which[c].first;
     k.warp_arrived.assign(nwarps, 0);
     k.warp_gen.assign(nwarps, 0);
     k.warp_buf.assign((size_t)nwarps * 32 * 8, 0);
-    k.smem_bytes = smem_bytes;
+    k.smem_bytes = L.smem_bytes;
     // poison: reads of unwritten shared memory become visible; the tail is a guard zone checked after the CTA has run
-    k.dyn_smem.assign(smem_bytes + kGuardBytes, (char)0xCD);
+    k.dyn_smem.assign(L.smem_bytes + kGuardBytes, (char)0xCD);
+    n += L.block;
   }
-  const unsigned n = count * block;
   for (Fiber& f : s.fibers) std::free(f.stack);
   s.fibers.clear();
   s.fibers.resize(n);
-  for (unsigned i = 0; i < n; ++i) {
-    Fiber& f = s.fibers[i];
-    f.cta = i / block;
-    f.tid = i % block;
-    f.stack = static_cast<char*>(std::malloc(kStackBytes));  // untouched pages stay uncommitted
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = f.stack;
-    f.ctx.uc_stack.ss_size = kStackBytes;
-    f.ctx.uc_link = &s.sched;
-    makecontext(&f.ctx, (void (*)())fiber_entry, 0);
-  }
+  unsigned i = 0;
+  for (unsigned c = 0; c < count; ++c)
+    for (unsigned t = 0; t < s.ctas[c].nthreads; ++t, ++i) {
+      Fiber& f = s.fibers[i];
+      f.cta = c;
+      f.tid = t;
+      f.stack = static_cast<char*>(std::malloc(kStackBytes));  // untouched pages stay uncommitted
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = f.stack;
+      f.ctx.uc_stack.ss_size = kStackBytes;
+      f.ctx.uc_link = &s.sched;
+      makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+    }
   unsigned remaining = n;
   std::vector<unsigned> order(n);
-  for (unsigned i = 0; i < n; ++i) order[i] = i;
-  uint64_t rng = s.rng ? (s.rng * 0x9E3779B97F4A7C15ull + first + 1) : 0;
+  for (unsigned q = 0; q < n; ++q) order[q] = q;
+  uint64_t rng = s.rng ? (s.rng * 0x9E3779B97F4A7C15ull + which[0].second + 1) : 0;
   uint64_t rounds = 0;
   while (remaining) {
     if (++rounds > 200000000ull / (n ? n : 1) + 100000ull) {
@@ -215,18 +230,22 @@ inline void run_ctas(unsigned first, unsigned count, unsigned block, size_t smem
       std::abort();
     }
     if (rng) {  // seeded Fisher-Yates reshuffle of the resume order each round
-      for (unsigned i = n - 1; i > 0; --i) {
+      for (unsigned q = n - 1; q > 0; --q) {
         rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
-        std::swap(order[i], order[rng % (i + 1)]);
+        std::swap(order[q], order[rng % (q + 1)]);
       }
     }
-    for (unsigned i = 0; i < n; ++i) {
-      Fiber& f = s.fibers[order[i]];
+    for (unsigned q = 0; q < n; ++q) {
+      Fiber& f = s.fibers[order[q]];
       if (f.done) continue;
-      s.current = (int)order[i];
-      const unsigned b = s.ctas[f.cta].index;
+      s.current = (int)order[q];
+      const Cta& k = s.ctas[f.cta];
+      const LaunchRec& L = s.launches[k.launch];
+      const unsigned b = k.index;
       threadIdx = {f.tid, 0, 0};
-      blockIdx = {b % s.grid.x, (b / s.grid.x) % s.grid.y, b / (s.grid.x * s.grid.y)};
+      blockIdx = {b % L.grid.x, (b / L.grid.x) % L.grid.y, b / (L.grid.x * L.grid.y)};
+      blockDim = {L.block, 1, 1};
+      gridDim = {L.grid.x, L.grid.y, L.grid.z};
       swapcontext(&s.sched, &f.ctx);
       if (f.done) { --remaining; rounds = 0; }
     }
@@ -244,18 +263,50 @@ inline void run_ctas(unsigned first, unsigned count, unsigned block, size_t smem
 // Runs `body` once per thread of every CTA of the grid (1-D blocks only).  concurrent == false: the CTAs execute one after
 // another (x fastest) -- `static` stand-ins for __shared__ variables are then private to the running CTA.  concurrent ==
 // true: all CTAs are resident at once, as a persistent kernel with grid-wide hand-offs needs (such kernels must keep their
-// CTA-local state in dynamic shared memory).
+// CTA-local state in dynamic shared memory).  Between group_begin() and group_run(), concurrent launches are only QUEUED
+// (the body must own its arguments) and then run all together: several "GPUs" whose persistent kernels talk to each other
+// through peer memory.
 inline void launch(dim3 grid, dim3 block3, size_t smem_bytes, std::function<void()> body, bool concurrent = false) {
   State& s = st();
   if (block3.y != 1 || block3.z != 1) { std::fprintf(stderr, "cuda_emu: only 1-D blocks are emulated\n"); std::abort(); }
-  const unsigned block = block3.x;
-  s.body = std::move(body);
-  s.grid = grid;
-  gridDim = {grid.x, grid.y, grid.z};
-  blockDim = {block, 1, 1};
+  LaunchRec rec;
+  rec.grid = grid;
+  rec.block = block3.x;
+  rec.smem_bytes = smem_bytes;
+  rec.body = std::move(body);
   const unsigned n_ctas = grid.x * grid.y * grid.z;
-  if (concurrent) run_ctas(0, n_ctas, block, smem_bytes);
-  else for (unsigned b = 0; b < n_ctas; ++b) run_ctas(b, 1, block, smem_bytes);
+  if (concurrent && s.grouping) {
+    s.queued.push_back(std::move(rec));
+    return;
+  }
+  s.launches.assign(1, std::move(rec));
+  std::vector<std::pair<int, unsigned>> which;
+  if (concurrent) {
+    for (unsigned b = 0; b < n_ctas; ++b) which.emplace_back(0, b);
+    run_ctas(which);
+  } else {
+    for (unsigned b = 0; b < n_ctas; ++b) {
+      which.assign(1, std::make_pair(0, b));
+      run_ctas(which);
+    }
+  }
+}
+
+inline void group_begin() {
+  st().grouping = true;
+  st().queued.clear();
+}
+inline void group_run() {
+  State& s = st();
+  s.grouping = false;
+  s.launches = std::move(s.queued);
+  s.queued.clear();
+  std::vector<std::pair<int, unsigned>> which;
+  for (int l = 0; l < (int)s.launches.size(); ++l) {
+    const dim3& g = s.launches[l].grid;
+    for (unsigned b = 0; b < g.x * g.y * g.z; ++b) which.emplace_back(l, b);
+  }
+  if (!which.empty()) run_ctas(which);
 }
 
 // round-to-nearest (ties away) conversion to TF32, as cvt.rna.tf32.f32

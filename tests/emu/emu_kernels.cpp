@@ -52,6 +52,9 @@ void emu_config(int sms, uint64_t schedule_seed) {
   emu::set_schedule_seed(schedule_seed);
 }
 const char* emu_last_error() { return g_err; }
+// several persistent launches ("GPUs") resident together: queue them between begin and run
+void emu_group_begin() { emu::group_begin(); }
+void emu_group_run() { emu::group_run(); }
 
 // impl 0: fused_mlp_kernel (fp32 FMA, validated on hardware -- run here to validate the emulator itself)
 // impl 1: tc_mlp_kernel (tensor-core tiles)

@@ -236,3 +236,42 @@ def test_device_pipeline_pointwise_blocks_feed_the_persistent_kernel():
         trainer = get_trainer(ModelType.CROSSDOMAIN, 'EMCDR')(cfg, model)
         losses = [trainer.train_epoch_device(data, 64, steps_per_launch=3) for _ in range(4)]
     assert np.isfinite(losses).all() and losses[-1] < losses[0] - 1e-3, losses
+
+
+def test_row_sharded_ranks_running_concurrently():
+    """The same as above with the two ranks' persistent launches RESIDENT TOGETHER (emulator launch group): their CTAs
+    interleave while they gather from and RED into each other's shards -- what happens on two GPUs."""
+    from recbole_cdr_b200 import shard
+    from recbole_cdr_b200.shard import RowShardedTable, train_steps_sharded
+    world, K, B, dim, nu, ni = 2, 2, 64, 64, 301, 403
+    ut, it, u, ip, ineg, _ = setup(nu, ni, dim, K * world, B, 13)
+    L = emu_util.lib()
+    with emu_util.patched_ops(sms=2, seed=5):
+        def shards(full):
+            tabs = [RowShardedTable.from_full(full, r, world, 'cpu') for r in range(world)]
+            for t in tabs:
+                t._ptrs = [s.local.data_ptr() for s in tabs]
+            return tabs
+        tu, ti = shards(ut), shards(it)
+        gu, gi = shards(torch.zeros_like(ut)), shards(torch.zeros_like(it))
+        keep, outs = [], []
+        L.emu_group_begin()
+        for r in range(world):
+            sl = slice(r * K, (r + 1) * K)
+            args = (u[sl].contiguous(), ip[sl].contiguous(), ineg[sl].contiguous())
+            outs.append(train_steps_sharded(tu[r], ti[r], gu[r], gi[r], *args, reg_weight=0.01))   # queued, not run yet
+            keep.append((args, dict(shard._steps_ws)))
+            shard._steps_ws.clear()                   # every rank gets its own step workspace, as on its own GPU
+        L.emu_group_run()
+    full = lambda tabs, n: torch.stack([t.local for t in tabs], 1).reshape(-1, dim)[:n]
+    a, b = ut.clone().requires_grad_(True), it.clone().requires_grad_(True)
+    gu_ref, gi_ref = torch.zeros_like(ut), torch.zeros_like(it)
+    losses = torch.cat([o[:, 0] for o in outs])
+    for k in range(K * world):
+        ref = O.emcdr_bpr_loss(a, b, u[k], ip[k], ineg[k], 0.01)
+        torch.testing.assert_close(losses[k], ref.detach()[0], rtol=1e-4, atol=0)
+        du, di = O.grads_of(ref, [a, b])
+        gu_ref += du
+        gi_ref += di
+    torch.testing.assert_close(full(gu, nu), gu_ref, rtol=1e-4, atol=1e-4 * gu_ref.abs().max().item())
+    torch.testing.assert_close(full(gi, ni), gi_ref, rtol=1e-4, atol=1e-4 * gi_ref.abs().max().item())

@@ -244,6 +244,12 @@ XDR_API int xdr_sparse_optim_rows(int kind, float* W, float* G, float* S1, float
  * ascending item id; users with fewer than k candidates are padded with (-inf, -1).  The [batch, n_items] matrix is never
  * materialised; scores are 3xTF32 tensor-core dot products (fp32-equivalent).  dim % 8 == 0, k <= 128.                    */
 XDR_API size_t xdr_topk_workspace_bytes(int64_t batch, int k);
+/* xdr_full_sort_topk_tc5: the same contract with the score blocks on tcgen05.mma (kind::tf32, 3xTF32, accumulators in tensor
+ * memory, 128 users per CTA, warp-specialised loader / issuer / epilogue pipeline over mbarriers); dim % 8 == 0, dim <= 64.  */
+XDR_API int xdr_full_sort_topk_tc5(const float* user_vecs, int64_t batch, const float* item_tab, int64_t n_items, int dim,
+                                   int64_t first_item, const int64_t* hist_ptr, const int64_t* hist_ids, int k,
+                                   float* out_score, int64_t* out_id, void* topk_ws, size_t topk_ws_bytes,
+                                   xdr_stream_t stream);
 XDR_API int xdr_full_sort_topk(const float* user_vecs, int64_t batch, const float* item_tab, int64_t n_items, int dim,
                                int64_t first_item, const int64_t* hist_ptr, const int64_t* hist_ids, int k,
                                float* out_score, int64_t* out_id, void* topk_ws, size_t topk_ws_bytes, xdr_stream_t stream);

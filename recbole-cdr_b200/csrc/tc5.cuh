@@ -1,0 +1,167 @@
+// tc5.cuh -- tcgen05 (5th-generation tensor core) building blocks for kernels that write their own operands to shared
+// memory: SWIZZLE_NONE canonical layouts + hand-built matrix descriptors, TMEM allocation, single-thread MMA issue with
+// mbarrier completion, TMEM -> register loads.  kind::tf32 with fp32 accumulation; products that must be fp32-equivalent
+// are issued as three MMAs on hi / lo operand copies (3xTF32, as in tc_tile.cuh).
+//
+// Layouts (units of 16 bytes = 4 tf32; cute/atom/mma_traits_sm100.hpp "make_umma_desc"):
+//   K-major operand of R rows:  element (r, k) at  (k/4)*LBO + (r/8)*SBO + (r%8)*16 + (k%4)*4   with LBO = R*16, SBO = 128
+//   -- a core matrix is 8 rows x 16 bytes, stored contiguously (128 B); one MMA consumes K = 8 = two 16-byte K chunks.
+// Descriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version 1 [46,48) | layout [61,64) = 0.
+// Instruction descriptor: F32 accumulate (1 << 4) | TF32 A (2 << 7) | TF32 B (2 << 10) | a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29).
+//
+// STATUS: this is the repository's READING of the interface, written without GPU access.  scripts/ubench_tcgen05.cu is the
+// one-CTA hardware experiment that confirms (or corrects) the layout / descriptor reading; the CPU emulator (tests/emu)
+// models the same reading, so what the emulator tests prove is the logic AROUND the MMAs (pipelines, barriers, epilogues).
+#pragma once
+#include "xdr_common.cuh"
+
+namespace xdr {
+namespace tc5 {
+
+#if defined(__CUDACC__) || defined(XDR_EMU)
+
+// ---- operand layout -------------------------------------------------------------------------------------------------------
+struct KMajor {
+  int rows;  // R (multiple of 8)
+  __host__ __device__ int lbo() const { return rows * 16; }
+  __host__ __device__ int sbo() const { return 128; }
+  __host__ __device__ int bytes(int k) const { return rows * k * 4; }           // footprint of an R x k operand
+  __host__ __device__ int chunk_offset(int r, int k4) const {                   // byte offset of the 16-byte chunk (r, 4*k4..)
+    return k4 * lbo() + (r >> 3) * sbo() + (r & 7) * 16;
+  }
+  __host__ __device__ int k_step_bytes() const { return 2 * lbo(); }            // advance of the start address per MMA (K = 8)
+};
+
+__host__ __device__ inline uint64_t make_desc(uint32_t smem_addr, int lbo, int sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__host__ __device__ inline uint32_t make_idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- PTX wrappers (emulator twins under XDR_EMU) --------------------------------------------------------------------------
+#ifdef XDR_EMU
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return emu::smem_addr(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { emu::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_init_fence() {}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { emu::mbar_arrive(bar); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { emu::mbar_wait(bar, parity); }
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void fence_before_sync() {}
+__device__ __forceinline__ void fence_after_sync() {}
+// warp-collective on the hardware (one allocation per warp): lane 0 acts for the warp here
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  if ((threadIdx.x & 31) == 0) *dst_smem = emu::tmem_alloc(ncols);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  if ((threadIdx.x & 31) == 0) emu::tmem_dealloc(taddr, ncols);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
+  emu::umma_tf32(tmem_d, da, db, idesc, accumulate);
+}
+__device__ __forceinline__ void commit(uint64_t* bar) { emu::mbar_arrive(bar); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) { emu::tmem_ld(taddr, r, 16); }
+__device__ __forceinline__ void tmem_ld_wait() {}
+#else
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  const uint32_t a = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 22)) __trap();  // a broken hand-off becomes an error, never a hung GPU
+  }
+}
+// generic-proxy writes to shared memory -> visible to the tensor core (async proxy)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// one full warp; ncols a power of two >= 32; the base address lands in *dst_smem
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+// issued by ONE thread: D[tmem] (+)= A[smem desc] * B[smem desc]^T, K = 8
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
+  const uint32_t acc = accumulate ? 1u : 0u, zero = 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(zero)
+      : "memory");
+}
+// arrives on `bar` once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// warp w of a warpgroup reads TMEM lanes 32*(w%4)..+31 (taddr carries that lane base in its upper half): 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+#endif
+
+// round to TF32 (10 mantissa bits, nearest, ties away) -- the hi part of the 3xTF32 split
+__device__ __forceinline__ float tf32_round(float x) {
+#ifdef XDR_EMU
+  return emu::as_float(emu::to_tf32(x));
+#else
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+#endif
+}
+// stores a float4 of 4 consecutive K elements of row r as its hi and lo TF32 parts into two K-major operand planes
+__device__ __forceinline__ void store_split4(unsigned char* hi_plane, unsigned char* lo_plane, const KMajor& lay, int r, int k4,
+                                             float4 v) {
+  const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+  const float4 l = make_float4(tf32_round(v.x - h.x), tf32_round(v.y - h.y), tf32_round(v.z - h.z), tf32_round(v.w - h.w));
+  const int off = lay.chunk_offset(r, k4);
+  *reinterpret_cast<float4*>(hi_plane + off) = h;
+  *reinterpret_cast<float4*>(lo_plane + off) = l;
+}
+
+// D (+)= A * B^T over K (multiple of 8) in 3xTF32: A / B given as hi and lo planes in K-major layout.  ONE thread calls it.
+__device__ __forceinline__ void mma_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, const KMajor& la, uint32_t b_hi,
+                                           uint32_t b_lo, const KMajor& lb, uint32_t idesc, int K, bool accumulate) {
+  for (int ks = 0; ks < K / 8; ++ks) {
+    const uint32_t ao = ks * la.k_step_bytes(), bo = ks * lb.k_step_bytes();
+    const uint64_t dah = make_desc(a_hi + ao, la.lbo(), la.sbo()), dal = make_desc(a_lo + ao, la.lbo(), la.sbo());
+    const uint64_t dbh = make_desc(b_hi + bo, lb.lbo(), lb.sbo()), dbl = make_desc(b_lo + bo, lb.lbo(), lb.sbo());
+    mma_tf32(tmem_d, dal, dbh, idesc, accumulate || ks > 0);   // small terms first
+    mma_tf32(tmem_d, dah, dbl, idesc, true);
+    mma_tf32(tmem_d, dah, dbh, idesc, true);
+  }
+}
+
+#endif  // __CUDACC__ || XDR_EMU
+
+}  // namespace tc5
+}  // namespace xdr

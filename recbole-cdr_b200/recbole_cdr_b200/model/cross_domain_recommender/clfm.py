@@ -105,7 +105,7 @@ class CLFM(CrossDomainRecommender):
             f = self._factors('target', interaction[self.TARGET_USER_ID])
             return torch.matmul(f, self.target_item_embedding.weight[:self.target_num_items].transpose(0, 1)).view(-1)
 
-    def full_sort_topk(self, interaction, k, hist_ptr=None, hist_ids=None):
+    def full_sort_topk(self, interaction, k, hist_ptr=None, hist_ids=None, engine='mma'):
         f = self._factors('target', interaction[self.TARGET_USER_ID]).detach()
         return ops.full_sort_topk(f, self.target_item_embedding.weight, k, n_items=self.target_num_items, first_item=1,
-                                  hist_ptr=hist_ptr, hist_ids=hist_ids)
+                                  hist_ptr=hist_ptr, hist_ids=hist_ids, engine=engine)

@@ -75,9 +75,9 @@ class CMF(CrossDomainRecommender):
             all_item_e = self.item_embedding.weight[:self.target_num_items]
             return torch.matmul(user_e, all_item_e.transpose(0, 1)).view(-1)
 
-    def full_sort_topk(self, interaction, k, hist_ptr=None, hist_ids=None):
+    def full_sort_topk(self, interaction, k, hist_ptr=None, hist_ids=None, engine='mma'):
         """Fused ``full_sort_predict`` + PAD/history masking + ``topk``: scores are the raw dot
         products of cmf.py:107-112 (no sigmoid there either); the [B, n_items] matrix is never written."""
         user_e = ops.gather_rows_raw(self.user_embedding.weight, interaction[self.TARGET_USER_ID])
         return ops.full_sort_topk(user_e, self.item_embedding.weight, k, n_items=self.target_num_items, first_item=1,
-                                  hist_ptr=hist_ptr, hist_ids=hist_ids)
+                                  hist_ptr=hist_ptr, hist_ids=hist_ids, engine=engine)

@@ -229,9 +229,10 @@ class EMCDR(CrossDomainRecommender):
             user_e, all_item_e = self._full_sort_operands(interaction)
             return torch.matmul(user_e, all_item_e.transpose(0, 1)).view(-1)
 
-    def full_sort_topk(self, interaction, k, hist_ptr=None, hist_ids=None):
+    def full_sort_topk(self, interaction, k, hist_ptr=None, hist_ids=None, engine='mma'):
         """Fused form of ``full_sort_predict`` + recbole's full-sort masking (PAD column, per-user history) + ``topk``:
         one scoring kernel that never writes the [B, n_items] matrix.  Item positions are those of
         ``full_sort_predict``'s columns.  Returns (scores [B, k], positions [B, k])."""
         user_e, all_item_e = self._full_sort_operands(interaction)
-        return ops.full_sort_topk(user_e, all_item_e.contiguous(), k, first_item=1, hist_ptr=hist_ptr, hist_ids=hist_ids)
+        return ops.full_sort_topk(user_e, all_item_e.contiguous(), k, first_item=1, hist_ptr=hist_ptr, hist_ids=hist_ids,
+                                  engine=engine)

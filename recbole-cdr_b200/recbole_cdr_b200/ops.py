@@ -739,12 +739,13 @@ def sparse_optim_rows(kind, table, grad, ids, stamp, step_id, lr, *, state1=None
 # F2: full-sort scoring + history mask + top-k without the [B, n_items] score matrix
 # ------------------------------------------------------------------------------------------------------------------
 
-def full_sort_topk(user_vecs, item_tab, k, n_items=None, first_item=1, hist_ptr=None, hist_ids=None):
+def full_sort_topk(user_vecs, item_tab, k, n_items=None, first_item=1, hist_ptr=None, hist_ids=None, engine='mma'):
     """Top-``k`` items per user by ``user_vecs @ item_tab[first_item:n_items].T`` with each user's history excluded.
 
     The fused form of ``full_sort_predict`` (emcdr.py:208-233, cmf.py:107-112) + recbole's full-sort masking + ``topk``.
     ``hist_ptr`` ``[B + 1]`` / ``hist_ids``: int64 CSR of ascending item ids per user.  Returns ``(scores [B, k] fp32,
-    ids [B, k] int64)``, score descending, ties by ascending id, padded with ``(-inf, -1)``."""
+    ids [B, k] int64)``, score descending, ties by ascending id, padded with ``(-inf, -1)``.  ``engine``: ``'mma'``
+    (mma.sync row tiles) or ``'tc5'`` (tcgen05.mma with tensor-memory accumulators; dim <= 64; not yet run on hardware)."""
     with torch.no_grad():
         user_vecs = user_vecs.contiguous()
         _require_cuda_f32(user_vecs, 'user_vecs')
@@ -762,6 +763,8 @@ def full_sort_topk(user_vecs, item_tab, k, n_items=None, first_item=1, hist_ptr=
         out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
         nbytes = _lib._lib.xdr_topk_workspace_bytes(B, int(k))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        call('xdr_full_sort_topk', ptr(user_vecs), B, ptr(item_tab), n_items, D, int(first_item), ptr(hist_ptr), ptr(hist_ids),
+        if engine not in ('mma', 'tc5'):
+            raise ValueError(f'unknown top-k engine {engine!r}')
+        call('xdr_full_sort_topk_tc5' if engine == 'tc5' else 'xdr_full_sort_topk', ptr(user_vecs), B, ptr(item_tab), n_items, D, int(first_item), ptr(hist_ptr), ptr(hist_ids),
              int(k), ptr(out_s), ptr(out_i), ptr(ws), nbytes, cur_stream())
         return out_s, out_i

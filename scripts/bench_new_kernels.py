@@ -200,6 +200,15 @@ def full_sort_topk():
         fl = 2.0 * B * n_items * D
         report(f'F2 fused full-sort top-{k} (NEW), {B} users x {n_items} items, D = 64', timeit(lambda: ops.full_sort_topk(U, I, k, hist_ptr=hp, hist_ids=hi), reps=3),
                bytes_=n_items * D * 4 * ((B + 63) // 64) + B * D * 4, flops=fl, units=B, unit_name='users')
+        try:
+            sc5, _ = ops.full_sort_topk(U, I, k, hist_ptr=hp, hist_ids=hi, engine='tc5')
+            if not SKIP_CHECK:
+                torch.testing.assert_close(sc5, rs, rtol=2e-5, atol=1e-6)
+            report(f'F2 fused full-sort top-{k}, tcgen05 engine (NEW), {B} users x {n_items} items, D = 64',
+                   timeit(lambda: ops.full_sort_topk(U, I, k, hist_ptr=hp, hist_ids=hi, engine='tc5'), reps=3),
+                   bytes_=n_items * D * 4 * ((B + 127) // 128) + B * D * 4, flops=fl, units=B, unit_name='users')
+        except Exception as e:  # noqa: BLE001 -- the descriptor reading may need the correction ubench_tcgen05 reports
+            print(json.dumps({'kernel': 'F2 tcgen05 engine', 'error': f'{type(e).__name__}: {str(e)[:300]}'}), flush=True)
         report(f'F2 reference: torch.matmul + mask + torch.topk, {B} users x {n_items} items', timeit(ref, reps=3),
                bytes_=B * n_items * 4 * 3, flops=fl, units=B, unit_name='users')
 

@@ -15,14 +15,19 @@ if [ "$STAGE" = validate ] || [ "$STAGE" = all ]; then
   # memory checker on the smallest case of each new kernel (a wild pointer must not take the box down later)
   XDR_RUN_UNVALIDATED=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 \
       python -m pytest tests/test_gpu_unvalidated.py -x -q \
-      -k "map_loss_matches_oracle and 33 or conet_fused_matches_oracle and 63 or sparse_optim and sgd or full_sort_topk and 300" \
+      -k "map_loss_matches_oracle and 33 or conet_fused_matches_oracle and 63 or sparse_optim and sgd or full_sort_topk and 300 and mma" \
       > gpurun_out/sanitizer.log 2>&1
   say "sanitizer rc=$?"
   # the hardware parity tests of the new kernels, then the regular gpu suite
-  XDR_RUN_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_unvalidated.py -q --timeout 300 > gpurun_out/unvalidated.log 2>&1
+  XDR_RUN_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_unvalidated.py -q --timeout 300 -k "not tc5" > gpurun_out/unvalidated.log 2>&1
   say "unvalidated rc=$?"
   timeout 900 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/gpu_suite.log 2>&1
   say "gpu suite rc=$?"
+  # the tcgen05 top-k kernel on its own, under a short timeout (a wrong descriptor reading gives wrong numbers, a wrong
+  # barrier protocol would hang: keep it away from the other tests)
+  XDR_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_unvalidated.py -q -x -k "full_sort_topk and tc5 and 300" --timeout 60 \
+      > gpurun_out/tc5_topk.log 2>&1
+  say "tc5 top-k (smallest case) rc=$?"
   # the tcgen05 descriptor experiment is tiny: run it in the first call so that the answer is there early
   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o /tmp/ubench_tcgen05 scripts/ubench_tcgen05.cu > gpurun_out/tcgen05.log 2>&1 \
       && timeout 120 /tmp/ubench_tcgen05 >> gpurun_out/tcgen05.log 2>&1

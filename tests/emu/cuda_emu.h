@@ -81,6 +81,8 @@ struct Cta {
   std::vector<char> dyn_smem;
   size_t smem_bytes = 0;
   std::unordered_map<const void*, MBar> mbars;
+  std::vector<uint32_t> tmem;   // tensor memory: 128 lanes x 512 columns of 32 bits, allocated on first tcgen05 use
+  unsigned tmem_next = 0;       // bump allocator (columns)
 };
 
 struct Fiber {
@@ -166,6 +168,64 @@ inline void mbar_wait(const void* bar, uint32_t parity) {
 inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, const void* bar) {
   std::memcpy(dst, src, bytes);
   mbar_complete_tx(bar, bytes);
+}
+
+// ---- tcgen05 / TMEM model -------------------------------------------------------------------------------------------------
+// What is modelled is THIS REPOSITORY'S READING of the interface (scripts/ubench_tcgen05.cu is the hardware experiment that
+// confirms or corrects it): SWIZZLE_NONE canonical operand layouts addressed through 64-bit shared-memory descriptors
+// (start >> 4 in bits [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46)), the instruction
+// descriptor's major / N / M fields, kind::tf32 (operands truncated to 10 mantissa bits, fp32 accumulation), D in tensor
+// memory with lane = row and column = n, tcgen05.ld 32x32b (warp w of a warpgroup reads lanes 32*(w%4)..+31).  MMAs
+// complete instantly, so tcgen05.commit is a plain mbarrier arrive.
+inline float as_float(uint32_t u);
+constexpr unsigned kTmemLanes = 128, kTmemCols = 512;
+inline unsigned threadIdx_lane_for_tmem() { return self().tid & 31u; }
+inline uint32_t smem_addr(const void* p) { return (uint32_t)(static_cast<const char*>(p) - cta().dyn_smem.data()); }
+inline char* smem_ptr(uint32_t addr) { return cta().dyn_smem.data() + addr; }
+inline uint32_t tmem_alloc(unsigned ncols) {
+  Cta& c = cta();
+  if (c.tmem.empty()) c.tmem.assign((size_t)kTmemLanes * kTmemCols, 0xCDCDCDCDu);
+  if (c.tmem_next + ncols > kTmemCols) { std::fprintf(stderr, "cuda_emu: tensor memory exhausted\n"); std::abort(); }
+  const uint32_t base = c.tmem_next;   // lane 0, column `base`
+  c.tmem_next += ncols;
+  return base;
+}
+inline void tmem_dealloc(uint32_t, unsigned ncols) { cta().tmem_next -= ncols; }
+inline uint32_t& tmem_at(uint32_t taddr, unsigned lane, unsigned col) {
+  const unsigned l = (taddr >> 16) + lane, c = (taddr & 0xffffu) + col;
+  if (l >= kTmemLanes || c >= kTmemCols) { std::fprintf(stderr, "cuda_emu: tensor memory access out of range\n"); std::abort(); }
+  return cta().tmem[(size_t)l * kTmemCols + c];
+}
+inline float umma_operand(uint64_t desc, bool mn_major, unsigned r, unsigned k) {
+  const uint32_t start = (uint32_t)(desc & 0x3fffu) << 4, lbo = (uint32_t)((desc >> 16) & 0x3fffu) << 4,
+                 sbo = (uint32_t)((desc >> 32) & 0x3fffu) << 4;
+  const uint32_t off = mn_major ? (k / 8) * lbo + (r / 4) * sbo + (k % 8) * 16 + (r % 4) * 4
+                                : (k / 4) * lbo + (r / 8) * sbo + (r % 8) * 16 + (k % 4) * 4;
+  uint32_t u;
+  std::memcpy(&u, smem_ptr(start + off), 4);
+  return as_float(u & 0xffffe000u);
+}
+// tcgen05.mma.cta_group::1.kind::tf32: D[M x N] (+)= A[M x 8] * B[N x 8]^T
+inline void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;
+  const unsigned N = ((idesc >> 17) & 0x3fu) << 3, M = ((idesc >> 24) & 0x1fu) << 4;
+  if (M != 128 || ((idesc >> 4) & 3u) != 1u || ((idesc >> 7) & 7u) != 2u || ((idesc >> 10) & 7u) != 2u) {
+    std::fprintf(stderr, "cuda_emu: only M = 128, F32 accumulate, TF32 operands are modelled (idesc %08x)\n", idesc);
+    std::abort();
+  }
+  for (unsigned m = 0; m < M; ++m)
+    for (unsigned n = 0; n < N; ++n) {
+      double s = 0;
+      for (unsigned k = 0; k < 8; ++k) s += (double)umma_operand(desc_a, a_mn, m, k) * (double)umma_operand(desc_b, b_mn, n, k);
+      uint32_t& d = tmem_at(tmem_d, m, n);
+      const float r = (accumulate ? as_float(d) : 0.f) + (float)s;
+      std::memcpy(&d, &r, 4);
+    }
+}
+// tcgen05.ld.sync.aligned.32x32b.xN: thread `lane` of warp w gets N consecutive columns of TMEM lane 32*(w%4) + lane
+inline void tmem_ld(uint32_t taddr, uint32_t* out, unsigned n) {
+  const unsigned lane = threadIdx_lane_for_tmem();
+  for (unsigned j = 0; j < n; ++j) out[j] = tmem_at(taddr, lane, j);
 }
 
 }  // namespace emu

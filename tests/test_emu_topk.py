@@ -9,7 +9,7 @@ import emu_util
 from oracle import topk_oracle as TO
 
 
-def run_emu(U, I, k, n_items=None, first_item=1, hist_ptr=None, hist_ids=None, sms=2, seed=0):
+def run_emu(U, I, k, n_items=None, first_item=1, hist_ptr=None, hist_ids=None, sms=2, seed=0, engine='mma'):
     L = emu_util.lib()
     emu_util.config(sms=sms, seed=seed)
     U, I = np.ascontiguousarray(U, np.float32), np.ascontiguousarray(I, np.float32)
@@ -22,7 +22,8 @@ def run_emu(U, I, k, n_items=None, first_item=1, hist_ptr=None, hist_ids=None, s
     ws = np.zeros(nbytes + 16, np.uint8)
     off = (-ws.ctypes.data) % 16
     p = emu_util.p
-    rc = L.xdr_full_sort_topk(p(U), ctypes.c_int64(B), p(I), ctypes.c_int64(n_items), ctypes.c_int(D), ctypes.c_int64(first_item),
+    fn = L.xdr_full_sort_topk_tc5 if engine == 'tc5' else L.xdr_full_sort_topk
+    rc = fn(p(U), ctypes.c_int64(B), p(I), ctypes.c_int64(n_items), ctypes.c_int(D), ctypes.c_int64(first_item),
                               p(hist_ptr), p(hist_ids), ctypes.c_int(k), p(out_s), p(out_i),
                               ctypes.c_void_p(ws.ctypes.data + off), ctypes.c_size_t(nbytes), None)
     emu_util.config(4, 0)
@@ -104,3 +105,37 @@ def test_topk_is_schedule_independent():
     b = run_emu(U, I, 12, seed=9)
     np.testing.assert_array_equal(a[0], b[0])
     np.testing.assert_array_equal(a[1], b[1])
+
+
+# ---- the tcgen05 engine (tensor-memory accumulators, warp-specialised loader / issuer / epilogue pipeline over mbarriers) ----
+@pytest.mark.parametrize('B,n_items,D,k,sms', [(5, 300, 64, 10, 1), (130, 1000, 64, 20, 2), (128, 200, 32, 100, 3), (3, 50, 8, 128, 1)])
+def test_tc5_topk_matches_oracle(B, n_items, D, k, sms):
+    rng = np.random.RandomState(B + n_items)
+    U = (rng.randn(B, D) * 0.3).astype(np.float32)
+    I = (rng.randn(n_items, D) * 0.3).astype(np.float32)
+    hist_ptr, hist_ids = make_hist(rng, B, n_items, 30)
+    out_s, out_i = run_emu(U, I, k, hist_ptr=hist_ptr, hist_ids=hist_ids, sms=sms, engine='tc5')
+    check(U, I, k, out_s, out_i, hist_ptr=hist_ptr, hist_ids=hist_ids)
+
+
+def test_tc5_topk_ties_padding_and_schedule_independence():
+    rng = np.random.RandomState(1)
+    D = 16
+    U = (rng.randn(4, D)).astype(np.float32)
+    I = np.zeros((40, D), np.float32)
+    I[1:] = rng.randn(1, D).astype(np.float32)
+    out_s, out_i = run_emu(U, I, 8, sms=2, engine='tc5')
+    for u in range(4):
+        np.testing.assert_array_equal(out_i[u], np.arange(1, 9))
+    hist_ptr = np.asarray([0, 36, 36, 36, 36], np.int64)
+    hist_ids = np.arange(4, 40).astype(np.int64)
+    out_s, out_i = run_emu(U, I, 8, hist_ptr=hist_ptr, hist_ids=hist_ids, sms=1, engine='tc5')
+    np.testing.assert_array_equal(out_i[0], [1, 2, 3, -1, -1, -1, -1, -1])
+    U = (rng.randn(140, 64) * 0.3).astype(np.float32)
+    I = (rng.randn(500, 64) * 0.3).astype(np.float32)
+    a = run_emu(U, I, 12, seed=0, engine='tc5')
+    b = run_emu(U, I, 12, seed=9, engine='tc5')
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+    m = run_emu(U, I, 12, engine='mma')                       # and the two engines agree
+    np.testing.assert_allclose(a[0], m[0], rtol=2e-5, atol=1e-6)

@@ -87,6 +87,7 @@ constexpr int kRowsPerWarp = 32 / kLanesPerRow;
 // 128-bit read-only gather that does not allocate in L1 (rows are touched once per kernel).
 __device__ __forceinline__ float4 ldg_row4(const float* __restrict__ row, int col4) {
 #ifdef XDR_EMU
+  emu::counters().row_load_bytes += 16;
   return *(reinterpret_cast<const float4*>(row) + col4);
 #else
   float4 v;
@@ -99,12 +100,16 @@ __device__ __forceinline__ float4 ldg_row4(const float* __restrict__ row, int co
 
 // 128-bit coherent load (tables that may be written by a concurrent scatter in the same launch).
 __device__ __forceinline__ float4 ld_row4(const float* row, int col4) {
+#ifdef XDR_EMU
+  emu::counters().row_load_bytes += 16;
+#endif
   return *(reinterpret_cast<const float4*>(row) + col4);
 }
 
 // fp32 x4 reduction to global memory: REDG.E.ADD.F32x4 on sm_100a.
 __device__ __forceinline__ void red_add4(float* row, int col4, float4 v) {
 #ifdef XDR_EMU
+  emu::counters().row_red_bytes += 16;
   float* q = row + 4 * col4;
   q[0] += v.x; q[1] += v.y; q[2] += v.z; q[3] += v.w;
 #else

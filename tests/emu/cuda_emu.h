@@ -109,6 +109,18 @@ inline State& st() {
   return s;
 }
 
+// Work counters of everything launched since the last reset (per warp-level instruction for the MMAs, bytes for the row
+// traffic helpers of xdr_common.cuh): a pre-measurement estimate of instruction mix and algorithmic traffic.
+struct Counters {
+  uint64_t mma_tf32 = 0, mma_bf16 = 0, umma_tf32 = 0;   // warp-level mma.sync instructions; tcgen05.mma instructions
+  uint64_t row_load_bytes = 0, row_red_bytes = 0;       // ld_row4 / ldg_row4 ; red_add4
+  uint64_t cta_barriers = 0;
+};
+inline Counters& counters() {
+  static Counters c;
+  return c;
+}
+
 inline void set_schedule_seed(uint64_t seed) { st().rng = seed; }
 
 inline Fiber& self() { return st().fibers[st().current]; }
@@ -123,6 +135,7 @@ inline void cta_barrier() {
   Cta& c = cta();
   const unsigned gen = c.gen;
   if (++c.arrived == c.nthreads) {
+    ++counters().cta_barriers;
     c.arrived = 0;
     ++c.gen;
     return;
@@ -207,6 +220,7 @@ inline float umma_operand(uint64_t desc, bool mn_major, unsigned r, unsigned k) 
 }
 // tcgen05.mma.cta_group::1.kind::tf32: D[M x N] (+)= A[M x 8] * B[N x 8]^T
 inline void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  ++counters().umma_tf32;
   const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;
   const unsigned N = ((idesc >> 17) & 0x3fu) << 3, M = ((idesc >> 24) & 0x1fu) << 4;
   if (M != 128 || ((idesc >> 4) & 3u) != 1u || ((idesc >> 7) & 7u) != 2u || ((idesc >> 10) & 7u) != 2u) {
@@ -386,6 +400,7 @@ inline float as_float(uint32_t u) {
 // mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 over the 32 fibers of the calling warp
 inline void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   const unsigned lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  if (lane == 0) ++counters().mma_tf32;
   uint32_t* mine = warp_slot(lane);
   for (int i = 0; i < 4; ++i) mine[i] = a[i];
   mine[4] = b[0];
@@ -413,6 +428,7 @@ inline void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32
 // mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 over the 32 fibers of the calling warp (two bf16 per register)
 inline void mma_m16n8k16_bf16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   const unsigned lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  if (lane == 0) ++counters().mma_bf16;
   uint32_t* mine = warp_slot(lane);
   for (int i = 0; i < 4; ++i) mine[i] = a[i];
   mine[4] = b[0];

@@ -90,6 +90,13 @@ class tc_mode:
         _mode = self.prev
 
 
+def counters(reset=True):
+    """Work counters of the emulated launches since the last reset (see cuda_emu.h ``Counters``)."""
+    out = (ctypes.c_uint64 * 6)()
+    lib().emu_counters(out, ctypes.c_int(1 if reset else 0))
+    return dict(zip(('mma_tf32', 'mma_bf16', 'umma_tf32', 'row_load_bytes', 'row_red_bytes', 'cta_barriers'), [int(v) for v in out]))
+
+
 def config(sms=4, seed=0):
     lib().emu_config(int(sms), int(seed))
 

@@ -32,6 +32,21 @@ struct KMajor {
   __host__ __device__ int k_step_bytes() const { return 2 * lbo(); }            // advance of the start address per MMA (K = 8)
 };
 
+// MN-major operand of R rows (R % 4 == 0) and K reduction elements (K % 8 == 0): contiguous along the row index --
+// what a weight gradient dZ^T X needs, whose reduction index is the batch row.
+//   element (r, k) at  (k/8)*LBO + (r/4)*SBO + (k%8)*16 + (r%4)*4   with SBO = 128, LBO = (R/4)*128
+//   -- a core matrix is 8 K-rows x 16 bytes (4 consecutive r); one MMA consumes K = 8 = one LBO step.
+struct MNMajor {
+  int rows;
+  __host__ __device__ int lbo() const { return (rows >> 2) * 128; }
+  __host__ __device__ int sbo() const { return 128; }
+  __host__ __device__ int bytes(int k) const { return rows * k * 4; }
+  __host__ __device__ int chunk_offset(int r4, int k) const {                   // 16-byte chunk of rows 4*r4.. at reduction k
+    return (k >> 3) * lbo() + r4 * sbo() + (k & 7) * 16;
+  }
+  __host__ __device__ int k_step_bytes() const { return lbo(); }
+};
+
 __host__ __device__ inline uint64_t make_desc(uint32_t smem_addr, int lbo, int sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
@@ -148,9 +163,21 @@ __device__ __forceinline__ void store_split4(unsigned char* hi_plane, unsigned c
   *reinterpret_cast<float4*>(lo_plane + off) = l;
 }
 
-// D (+)= A * B^T over K (multiple of 8) in 3xTF32: A / B given as hi and lo planes in K-major layout.  ONE thread calls it.
-__device__ __forceinline__ void mma_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, const KMajor& la, uint32_t b_hi,
-                                           uint32_t b_lo, const KMajor& lb, uint32_t idesc, int K, bool accumulate) {
+// the MN-major twin of store_split4: v = 4 consecutive ROWS (4*r4 ..) at reduction index k
+__device__ __forceinline__ void store_split4_mn(unsigned char* hi_plane, unsigned char* lo_plane, const MNMajor& lay, int r4, int k,
+                                                float4 v) {
+  const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+  const float4 l = make_float4(tf32_round(v.x - h.x), tf32_round(v.y - h.y), tf32_round(v.z - h.z), tf32_round(v.w - h.w));
+  const int off = lay.chunk_offset(r4, k);
+  *reinterpret_cast<float4*>(hi_plane + off) = h;
+  *reinterpret_cast<float4*>(lo_plane + off) = l;
+}
+
+// D (+)= A * B^T over K (multiple of 8) in 3xTF32: A / B given as hi and lo planes, each K-major or MN-major (the layout
+// objects say which; the instruction descriptor must carry the matching major bits).  ONE thread calls it.
+template <typename LayA, typename LayB>
+__device__ __forceinline__ void mma_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, const LayA& la, uint32_t b_hi,
+                                           uint32_t b_lo, const LayB& lb, uint32_t idesc, int K, bool accumulate) {
   for (int ks = 0; ks < K / 8; ++ks) {
     const uint32_t ao = ks * la.k_step_bytes(), bo = ks * lb.k_step_bytes();
     const uint64_t dah = make_desc(a_hi + ao, la.lbo(), la.sbo()), dal = make_desc(a_lo + ao, la.lbo(), la.sbo());
@@ -159,6 +186,75 @@ __device__ __forceinline__ void mma_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint3
     mma_tf32(tmem_d, dah, dbl, idesc, true);
     mma_tf32(tmem_d, dah, dbh, idesc, true);
   }
+}
+
+// ---- self-test: D[128 x N] = A[128 x K] * B[N x K]^T from row-major operands in global memory, one CTA of 128 threads, with
+// A and B staged K-major or MN-major.  Runs under the emulator and, on hardware, checks the descriptor reading through the
+// library itself (xdr_tc5_selftest).
+__global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, int N, int K,
+                                                          int a_mn, int b_mn, float* __restrict__ D) {
+  XDR_DYN_SMEM_ALIGNED(unsigned char, smem_t5, 128);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int M = 128;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_t5);
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem_t5 + 8);
+  unsigned char* a_hi = smem_t5 + 128;
+  unsigned char* a_lo = a_hi + M * K * 4;
+  unsigned char* b_hi = a_lo + M * K * 4;
+  unsigned char* b_lo = b_hi + N * K * 4;
+  const KMajor ka{M}, kb{N};
+  const MNMajor ma{M}, mb{N};
+  for (int e = tid; e < M * K / 4; e += 128) {
+    if (!a_mn) {
+      const int r = e / (K / 4), k4 = e % (K / 4);
+      store_split4(a_hi, a_lo, ka, r, k4, *reinterpret_cast<const float4*>(A + r * K + 4 * k4));
+    } else {
+      const int r4 = e / K, k = e % K;
+      store_split4_mn(a_hi, a_lo, ma, r4, k, make_float4(A[(4 * r4) * K + k], A[(4 * r4 + 1) * K + k], A[(4 * r4 + 2) * K + k],
+                                                        A[(4 * r4 + 3) * K + k]));
+    }
+  }
+  for (int e = tid; e < N * K / 4; e += 128) {
+    if (!b_mn) {
+      const int r = e / (K / 4), k4 = e % (K / 4);
+      store_split4(b_hi, b_lo, kb, r, k4, *reinterpret_cast<const float4*>(B + r * K + 4 * k4));
+    } else {
+      const int r4 = e / K, k = e % K;
+      store_split4_mn(b_hi, b_lo, mb, r4, k, make_float4(B[(4 * r4) * K + k], B[(4 * r4 + 1) * K + k], B[(4 * r4 + 2) * K + k],
+                                                        B[(4 * r4 + 3) * K + k]));
+    }
+  }
+  const uint32_t cols = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_init_fence();
+  }
+  if (warp == 0) tmem_alloc(tmem_base_smem, cols);
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_base_smem;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_tf32(M, N, a_mn != 0, b_mn != 0);
+    const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+    if (!a_mn && !b_mn) mma_3xtf32(tmem, ah, al, ka, bh, bl, kb, idesc, K, false);
+    else if (!a_mn && b_mn) mma_3xtf32(tmem, ah, al, ka, bh, bl, mb, idesc, K, false);
+    else if (a_mn && !b_mn) mma_3xtf32(tmem, ah, al, ma, bh, bl, kb, idesc, K, false);
+    else mma_3xtf32(tmem, ah, al, ma, bh, bl, mb, idesc, K, false);
+    commit(bar);
+  }
+  mbar_wait(bar, 0);
+  fence_after_sync();
+  for (int c = 0; c < N; c += 16) {
+    uint32_t r[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 16 && c + j < N; ++j) D[(size_t)tid * N + c + j] = __uint_as_float(r[j]);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, cols);
 }
 
 #endif  // __CUDACC__ || XDR_EMU

@@ -428,4 +428,18 @@ int xdr_full_sort_topk_tc5(const float* user_vecs, int64_t batch, const float* i
   return XDR_OK;
 }
 
+// Self-test of the tcgen05 building blocks: D[128, N] = A[128, K] B[N, K]^T (3xTF32) with each operand staged K-major
+// (a_mn / b_mn = 0) or MN-major (= 1) in shared memory.  N % 16 == 0, N <= 256, K % 8 == 0, both planes of both operands
+// must fit shared memory.  Device pointers, row-major fp32.
+int xdr_tc5_selftest(const float* A, const float* B, int N, int K, int a_mn, int b_mn, float* D, xdr_stream_t stream) {
+  XDR_REQUIRE(A && B && D, "xdr_tc5_selftest: null pointer");
+  XDR_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 8 && K % 8 == 0, "xdr_tc5_selftest: bad shape N=%d K=%d", N, K);
+  const size_t smem = 128 + (size_t)2 * 128 * K * 4 + (size_t)2 * N * K * 4;
+  XDR_REQUIRE(smem <= 224 * 1024, "xdr_tc5_selftest: operands do not fit shared memory");
+  XDR_CUDA_OK(cudaFuncSetAttribute(tc5::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  XDR_LAUNCH((tc5::selftest_kernel), 1, 128, smem, (cudaStream_t)stream, A, B, N, K, a_mn, b_mn, D);
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
 }  // extern "C"

@@ -25,6 +25,9 @@ if [ "$STAGE" = validate ] || [ "$STAGE" = all ]; then
   say "gpu suite rc=$?"
   # the tcgen05 top-k kernel on its own, under a short timeout (a wrong descriptor reading gives wrong numbers, a wrong
   # barrier protocol would hang: keep it away from the other tests)
+  XDR_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_unvalidated.py -q -k "tc5_selftest" --timeout 60 \
+      > gpurun_out/tc5_selftest.log 2>&1
+  say "tc5 self-test GEMM (K-/MN-major operands) rc=$?"
   XDR_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_unvalidated.py -q -x -k "full_sort_topk and tc5 and 300" --timeout 60 \
       > gpurun_out/tc5_topk.log 2>&1
   say "tc5 top-k (smallest case) rc=$?"

@@ -139,3 +139,19 @@ def test_tc5_topk_ties_padding_and_schedule_independence():
     np.testing.assert_array_equal(a[1], b[1])
     m = run_emu(U, I, 12, engine='mma')                       # and the two engines agree
     np.testing.assert_allclose(a[0], m[0], rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize('N,K', [(64, 64), (16, 8), (128, 32)])
+def test_tc5_selftest_gemm_all_majors(a_mn, b_mn, N, K):
+    """tc5.cuh building blocks: K-major and MN-major operand planes, descriptors, 3xTF32 issue, TMEM epilogue."""
+    L = emu_util.lib()
+    emu_util.config(sms=1, seed=0)
+    rng = np.random.RandomState(N + K)
+    A = rng.randn(128, K).astype(np.float32)
+    B = rng.randn(N, K).astype(np.float32)
+    D = np.zeros((128, N), np.float32)
+    p = emu_util.p
+    rc = L.xdr_tc5_selftest(p(A), p(B), ctypes.c_int(N), ctypes.c_int(K), ctypes.c_int(a_mn), ctypes.c_int(b_mn), p(D), None)
+    assert rc == 0, L.emu_last_error()
+    np.testing.assert_allclose(D, A.astype(np.float64) @ B.astype(np.float64).T, rtol=1e-5, atol=1e-5)

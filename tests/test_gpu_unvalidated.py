@@ -330,3 +330,19 @@ def test_device_pipeline_with_row_sparse_adagrad_equals_dense_torch_adagrad():
     assert abs(loss - ref_total) <= 1e-4 * abs(ref_total)
     torch.testing.assert_close(model.source_user_embedding.weight.detach().cpu(), a.detach(), rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(model.source_item_embedding.weight.detach().cpu(), b.detach(), rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ tcgen05 building blocks (tc5.cuh)
+@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_tc5_selftest_gemm_all_majors(a_mn, b_mn):
+    """D = A B^T on tcgen05 (3xTF32, TMEM accumulator) with the operands staged K-major / MN-major by the kernel itself: the
+    hardware check of the repository's descriptor reading, through the library (scripts/ubench_tcgen05.cu is the standalone
+    form that also tries the alternative reading)."""
+    import ctypes
+    g = torch.Generator().manual_seed(a_mn * 2 + b_mn)
+    N, K = 64, 64
+    A, B = torch.randn(128, K, generator=g).to(dev()), torch.randn(N, K, generator=g).to(dev())
+    D = torch.zeros(128, N, device=dev())
+    lib().call('xdr_tc5_selftest', A.data_ptr(), B.data_ptr(), N, K, a_mn, b_mn, D.data_ptr(), lib().cur_stream())
+    torch.cuda.synchronize()
+    torch.testing.assert_close(D.cpu().double(), A.cpu().double() @ B.cpu().double().T, rtol=1e-5, atol=1e-5)

@@ -6,6 +6,9 @@
 // MN-major for the weight gradient dZ^T X (whose reduction index is the batch row).  This program checks, on one CTA, every
 // combination of {A, B} x {K-major, MN-major} with SWIZZLE_NONE canonical layouts, for both readings of which descriptor
 // field is the "leading" and which the "stride" byte offset, against a CPU product, and prints one PASS/FAIL line each.
+// The same eight variants run a second time with bf16 operands on kind::f16 (K = 16 per instruction, 8 elements per 16-byte
+// chunk): DESIGN.md's plan for the tcgen05 training kernels is bf16x3 on kind::f16, because fp32 hi / lo planes double the
+// shared-memory footprint of the operands, so that is the operand format round 2 needs confirmed.
 // Built and run by scripts/r2_gpu_session.sh:   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o ubench_tcgen05 ...
 //
 // Canonical SWIZZLE_NONE layouts (cute/atom/mma_traits_sm100.hpp, units of 16 bytes = 4 tf32):
@@ -25,29 +28,36 @@ constexpr int M = 128, N = 64, K = 64;  // one UMMA tile: D[128 x 64] += A[128 x
 struct Variant {
   int a_mn_major, b_mn_major;  // 0 = K-major, 1 = MN-major
   int swap_lbo_sbo;            // 0 = as read from the CUTLASS headers, 1 = the two descriptor fields exchanged
+  int bf16;                    // 0 = kind::tf32 on fp32 operands (K = 8 per MMA), 1 = kind::f16 on bf16 operands (K = 16)
 };
+
+__device__ inline unsigned short bf16_bits(float x) {  // the host pre-rounds the inputs, so truncation is exact
+  return (unsigned short)(__float_as_uint(x) >> 16);
+}
 
 // byte offset of element (mn, k) of an operand with `rows` MN-rows, plus the LBO / SBO / per-instruction K advance it implies
 struct OperandLayout {
   int lbo, sbo, k_step_bytes;
 };
-__host__ __device__ inline OperandLayout operand_layout(int rows, int mn_major) {
+// T = elements per 16-byte chunk (4 for tf32, 8 for bf16); one instruction consumes K = 2T (32 bytes of K)
+__host__ __device__ inline OperandLayout operand_layout(int rows, int mn_major, int T = 4) {
   OperandLayout o;
   if (!mn_major) {            // K-major: 16-byte K chunks are `rows * 16` bytes apart, 8-row groups 128 bytes apart
     o.lbo = rows * 16;
     o.sbo = 128;
-    o.k_step_bytes = 2 * o.lbo;   // one instruction consumes K = 8 = two 16-byte chunks
-  } else {                    // MN-major: 4-element MN groups 128 bytes apart, 8-row K groups `rows/4 * 128` bytes apart
+    o.k_step_bytes = 2 * o.lbo;   // two 16-byte chunks per instruction
+  } else {                    // MN-major: T-element MN groups 128 bytes apart, 8-row K groups `rows/T * 128` bytes apart
     o.sbo = 128;
-    o.lbo = (rows / 4) * 128;
-    o.k_step_bytes = o.lbo;       // one instruction consumes K = 8 = one K group
+    o.lbo = (rows / T) * 128;
+    o.k_step_bytes = (2 * T / 8) * o.lbo;   // K = 2T reduction rows = 2T/8 groups of eight
   }
   return o;
 }
-__host__ __device__ inline int operand_offset(int rows, int mn_major, int mn, int k) {
-  const OperandLayout o = operand_layout(rows, mn_major);
-  if (!mn_major) return (k / 4) * o.lbo + (mn / 8) * o.sbo + (mn % 8) * 16 + (k % 4) * 4;
-  return (k / 8) * o.lbo + (mn / 4) * o.sbo + (k % 8) * 16 + (mn % 4) * 4;
+__host__ __device__ inline int operand_offset(int rows, int mn_major, int mn, int k, int T = 4) {
+  const OperandLayout o = operand_layout(rows, mn_major, T);
+  const int es = 16 / T;
+  if (!mn_major) return (k / T) * o.lbo + (mn / 8) * o.sbo + (mn % 8) * 16 + (k % T) * es;
+  return (k / 8) * o.lbo + (mn / T) * o.sbo + (k % 8) * 16 + (mn % T) * es;
 }
 
 __device__ inline uint64_t make_desc(uint32_t smem_addr, int lbo, int sbo) {
@@ -68,13 +78,16 @@ __global__ void __launch_bounds__(128, 1) umma_tf32_kernel(const float* __restri
   uint8_t* sB = smem + M * K * 4;     // N * K * 4 = 16 KB
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  const int T = v.bf16 ? 8 : 4;
   for (int e = tid; e < M * K; e += 128) {
     const int r = e / K, k = e % K;
-    *reinterpret_cast<float*>(sA + operand_offset(M, v.a_mn_major, r, k)) = A[e];
+    if (v.bf16) *reinterpret_cast<unsigned short*>(sA + operand_offset(M, v.a_mn_major, r, k, T)) = bf16_bits(A[e]);
+    else *reinterpret_cast<float*>(sA + operand_offset(M, v.a_mn_major, r, k, T)) = A[e];
   }
   for (int e = tid; e < N * K; e += 128) {
     const int r = e / K, k = e % K;
-    *reinterpret_cast<float*>(sB + operand_offset(N, v.b_mn_major, r, k)) = B[e];
+    if (v.bf16) *reinterpret_cast<unsigned short*>(sB + operand_offset(N, v.b_mn_major, r, k, T)) = bf16_bits(B[e]);
+    else *reinterpret_cast<float*>(sB + operand_offset(N, v.b_mn_major, r, k, T)) = B[e];
   }
   const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
   if (tid == 0) {
@@ -93,24 +106,34 @@ __global__ void __launch_bounds__(128, 1) umma_tf32_kernel(const float* __restri
   const uint32_t tmem_base = tmem_base_smem;
 
   if (tid == 0) {  // a single thread issues the MMAs
-    const OperandLayout la = operand_layout(M, v.a_mn_major), lb = operand_layout(N, v.b_mn_major);
+    const OperandLayout la = operand_layout(M, v.a_mn_major, T), lb = operand_layout(N, v.b_mn_major, T);
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(sA), b0 = (uint32_t)__cvta_generic_to_shared(sB);
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)v.a_mn_major << 15) | ((uint32_t)v.b_mn_major << 16) |
+    const uint32_t fmt = v.bf16 ? 1u : 2u;   // F16F32Format: 1 = BF16, 2 = TF32
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)v.a_mn_major << 15) | ((uint32_t)v.b_mn_major << 16) |
                            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-    for (int ks = 0; ks < K / 8; ++ks) {
+    for (int ks = 0; ks < K / (2 * T); ++ks) {
       const uint64_t da = v.swap_lbo_sbo ? make_desc(a0 + ks * la.k_step_bytes, la.sbo, la.lbo)
                                          : make_desc(a0 + ks * la.k_step_bytes, la.lbo, la.sbo);
       const uint64_t db = v.swap_lbo_sbo ? make_desc(b0 + ks * lb.k_step_bytes, lb.sbo, lb.lbo)
                                          : make_desc(b0 + ks * lb.k_step_bytes, lb.lbo, lb.sbo);
       const uint32_t acc = ks > 0 ? 1u : 0u;
       const uint32_t zero = 0;
-      asm volatile(
-          "{\n\t"
-          ".reg .pred p;\n\t"
-          "setp.ne.b32 p, %4, 0;\n\t"
-          "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-          "}\n" ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(zero)
-          : "memory");
+      if (v.bf16)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+            "}\n" ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(zero)
+            : "memory");
+      else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+            "}\n" ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(zero)
+            : "memory");
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
   }
@@ -153,10 +176,10 @@ __global__ void __launch_bounds__(128, 1) umma_tf32_kernel(const float* __restri
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64));
 }
 
-static float tf32_round(float x) {  // keep 10 mantissa bits so that the products are exact in fp32
+static float tf32_round(float x) {  // keep 7 mantissa bits: exactly representable in bf16 AND in tf32, products exact in fp32
   uint32_t u;
   memcpy(&u, &x, 4);
-  u = (u + 0x1000u) & 0xffffe000u;
+  u = (u + 0x8000u) & 0xffff0000u;
   memcpy(&x, &u, 4);
   return x;
 }
@@ -179,16 +202,17 @@ int main() {
   const int smem = (M + N) * K * 4;
   cudaFuncSetAttribute(umma_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int n_pass = 0;
+  for (int bf = 0; bf < 2; ++bf)
   for (int swap = 0; swap < 2; ++swap)
     for (int am = 0; am < 2; ++am)
       for (int bm = 0; bm < 2; ++bm) {
-        Variant v{am, bm, swap};
+        Variant v{am, bm, swap, bf};
         cudaMemset(dD, 0xff, M * N * 4);
         umma_tf32_kernel<<<1, 128, smem>>>(dA, dB, dD, v);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
-          printf("A %s-major, B %s-major, %s: CUDA error %s\n", am ? "MN" : "K", bm ? "MN" : "K",
-                 swap ? "LBO/SBO exchanged" : "LBO/SBO as read", cudaGetErrorString(e));
+          printf("%s A %s-major, B %s-major, %s: CUDA error %s\n", bf ? "kind::f16 (bf16)" : "kind::tf32", am ? "MN" : "K",
+                 bm ? "MN" : "K", swap ? "LBO/SBO exchanged" : "LBO/SBO as read", cudaGetErrorString(e));
           return 2;  // a sticky error: nothing after it is meaningful
         }
         cudaMemcpy(hD, dD, M * N * 4, cudaMemcpyDeviceToHost);
@@ -199,9 +223,9 @@ int main() {
         }
         const bool ok = max_err < 1e-4;
         n_pass += ok;
-        printf("A %s-major, B %s-major, %-18s : %s (max abs err %.3e)\n", am ? "MN" : "K ", bm ? "MN" : "K ",
-               swap ? "LBO/SBO exchanged" : "LBO/SBO as read", ok ? "PASS" : "FAIL", max_err);
+        printf("%-16s A %s-major, B %s-major, %-18s : %s (max abs err %.3e)\n", bf ? "kind::f16 (bf16)" : "kind::tf32",
+               am ? "MN" : "K ", bm ? "MN" : "K ", swap ? "LBO/SBO exchanged" : "LBO/SBO as read", ok ? "PASS" : "FAIL", max_err);
       }
-  printf("%d of 8 variants pass\n", n_pass);
+  printf("%d of 16 variants pass\n", n_pass);
   return 0;
 }

@@ -346,3 +346,29 @@ def test_tc5_selftest_gemm_all_majors(a_mn, b_mn):
     lib().call('xdr_tc5_selftest', A.data_ptr(), B.data_ptr(), N, K, a_mn, b_mn, D.data_ptr(), lib().cur_stream())
     torch.cuda.synchronize()
     torch.testing.assert_close(D.cpu().double(), A.cpu().double() @ B.cpu().double().T, rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the second set of reference goldens (tests/golden/v_*.npz) through the kernels that have not met hardware yet
+# ---------------------------------------------------------------------------------------------------------------------------
+import variants_util as _V  # noqa: E402
+
+
+@pytest.mark.parametrize('engine', ['fma', 'tc'])
+@pytest.mark.parametrize('name', [n for n in _V.VARIANTS if _V.spec(Golden(n))['model'] in ('EMCDR', 'DTCDR')])
+def test_variant_fused_mlp_engines(name, engine):
+    g = Golden(name)
+    _V.check_against_reference(_V.build(g, 'cuda', xdr_fused_mlp=engine), g, 'cuda')
+
+
+@pytest.mark.parametrize('name', [n for n in _V.VARIANTS if _V.spec(Golden(n))['model'] == 'CoNet'])
+def test_variant_fused_conet(name):
+    g = Golden(name)
+    _V.check_against_reference(_V.build(g, 'cuda', xdr_fused_conet=True), g, 'cuda')
+
+
+@pytest.mark.parametrize('name', [n for n in _V.VARIANTS
+                                  if Golden(n).has('full_sort_predict') and _V.spec(Golden(n))['model'] in ('EMCDR', 'CMF')])
+def test_variant_fused_topk_matches_the_reference_scores(name):
+    g = Golden(name)
+    _V.check_topk_against_reference(_V.build(g, 'cuda'), g, 'cuda')

@@ -18,12 +18,10 @@ def leafs(ts):
     return [t.clone().requires_grad_(True) for t in ts]
 
 
-@pytest.mark.parametrize('phase', ['source', 'target'])
-def test_emcdr_bpr(phase):
-    g = Golden(f'emcdr_bpr_{phase}')
+def check_emcdr_bpr(g, phase, reg_weight):
     ut, it = leafs([g.param(f'{phase}_user_embedding.weight'), g.param(f'{phase}_item_embedding.weight')])
     loss = O.emcdr_bpr_loss(ut, it, g.batch(f'{phase}_user_id'), g.batch(f'{phase}_item_id'),
-                            g.batch(f'neg_{phase}_item_id'), g.meta('reg_weight'))
+                            g.batch(f'neg_{phase}_item_id'), reg_weight)
     assert loss.shape == (1,)
     close(loss, g.losses()[0])
     gu, gi = O.grads_of(loss, [ut, it])
@@ -36,21 +34,28 @@ def test_emcdr_bpr(phase):
 
 
 @pytest.mark.parametrize('phase', ['source', 'target'])
-def test_emcdr_mf(phase):
-    g = Golden(f'emcdr_mf_{phase}')
+def test_emcdr_bpr(phase):
+    g = Golden(f'emcdr_bpr_{phase}')
+    check_emcdr_bpr(g, phase, g.meta('reg_weight'))
+
+
+def check_emcdr_mf(g, phase, reg_weight):
     ut, it = leafs([g.param(f'{phase}_user_embedding.weight'), g.param(f'{phase}_item_embedding.weight')])
     loss = O.emcdr_mf_loss(ut, it, g.batch(f'{phase}_user_id'), g.batch(f'{phase}_item_id'),
-                           g.batch(f'{phase}_label'), g.meta('reg_weight'))
+                           g.batch(f'{phase}_label'), reg_weight)
     close(loss, g.losses()[0])
     gu, gi = O.grads_of(loss, [ut, it])
     close(gu, g.grad(f'{phase}_user_embedding.weight'))
     close(gi, g.grad(f'{phase}_item_embedding.weight'))
 
 
-@pytest.mark.parametrize('case', ['non_linear', 'linear', 'items'])
-def test_emcdr_map_and_predict(case):
-    g = Golden(f'emcdr_map_{case}')
-    kind = 'item' if case == 'items' else 'user'
+@pytest.mark.parametrize('phase', ['source', 'target'])
+def test_emcdr_mf(phase):
+    g = Golden(f'emcdr_mf_{phase}')
+    check_emcdr_mf(g, phase, g.meta('reg_weight'))
+
+
+def check_emcdr_map_and_predict(g, kind):
     ws, bs, wn, bn = emcdr_mapping_params(g)
     src, tgt = leafs([g.param(f'source_{kind}_embedding.weight'), g.param(f'target_{kind}_embedding.weight')])
     ws = leafs(ws)
@@ -73,14 +78,19 @@ def test_emcdr_map_and_predict(case):
             pred = O.emcdr_predict_overlap_items(tabs['target_user'], tabs['source_item'], tabs['target_item'], u, i,
                                                  g.meta('n_ov_i'), ws, bs)
     close(pred, g.t('predict_overlap_phase'))
+    return ws, bs
 
 
-def test_cmf():
-    g = Golden('cmf_both')
+@pytest.mark.parametrize('case', ['non_linear', 'linear', 'items'])
+def test_emcdr_map_and_predict(case):
+    check_emcdr_map_and_predict(Golden(f'emcdr_map_{case}'), 'item' if case == 'items' else 'user')
+
+
+def check_cmf(g, alpha, lam, gamma):
     ut, it = leafs([g.param('user_embedding.weight'), g.param('item_embedding.weight')])
     b = g.batch
     loss = O.cmf_loss(ut, it, b('source_user_id'), b('source_item_id'), b('source_label'), b('target_user_id'),
-                      b('target_item_id'), b('target_label'), g.meta('alpha'), g.meta('lambda'), g.meta('gamma'))
+                      b('target_item_id'), b('target_label'), alpha, lam, gamma)
     close(loss, g.losses()[0])
     gu, gi = O.grads_of(loss, [ut, it])
     close(gu, g.grad('user_embedding.weight'))
@@ -88,9 +98,12 @@ def test_cmf():
     close(torch.sigmoid(O.dot_score(ut, it, b('target_user_id'), b('target_item_id'))).detach(), g.t('predict'))
 
 
-@pytest.mark.parametrize('tag', ['users', 'items'])
-def test_conet(tag):
-    g = Golden(f'conet_{tag}')
+def test_cmf():
+    g = Golden('cmf_both')
+    check_cmf(g, g.meta('alpha'), g.meta('lambda'), g.meta('gamma'))
+
+
+def check_conet(g, ov_users):
     p, names = conet_params(g)
     tabs = {k: v.clone().requires_grad_(True) for k, v in g.tables().items()}
     for k in ('ws', 'bs', 'wt', 'bt', 'h'):
@@ -98,7 +111,6 @@ def test_conet(tag):
     for k in ('out_s_w', 'out_s_b', 'out_t_w', 'out_t_b'):
         p[k] = p[k].clone().requires_grad_(True)
     b = g.batch
-    ov_users = tag == 'users'
     n_ov = g.meta('n_ov_u') if ov_users else g.meta('n_ov_i')
     loss = O.conet_loss(tabs, p, b('source_user_id'), b('source_item_id'), b('source_label'), b('target_user_id'),
                         b('target_item_id'), b('target_label'), ov_users, n_ov)
@@ -117,10 +129,15 @@ def test_conet(tag):
         close(gr, g.grad(nm), rtol=1e-5, atol=1e-7)
     with torch.no_grad():
         close(O.conet_predict(tabs, p, b('target_user_id'), b('target_item_id')), g.t('predict'))
+    return tabs, p
 
 
-def test_dtcdr():
-    g = Golden('dtcdr_neumf')
+@pytest.mark.parametrize('tag', ['users', 'items'])
+def test_conet(tag):
+    check_conet(Golden(f'conet_{tag}'), tag == 'users')
+
+
+def check_dtcdr(g, alpha):
     p, names = dtcdr_params(g)
     tabs = {k: v.clone().requires_grad_(True) for k, v in g.tables().items()}
     assert all(torch.isfinite(v).all() for v in tabs.values())  # the -inf fill of dtcdr.py:54-59 is overwritten by init
@@ -128,7 +145,7 @@ def test_dtcdr():
         p[k] = leafs(p[k]) if isinstance(p[k], list) else p[k].clone().requires_grad_(True)
     b = g.batch
     loss = O.dtcdr_loss(tabs, p, b('source_user_id'), b('source_item_id'), b('source_label'), b('target_user_id'),
-                        b('target_item_id'), b('target_label'), g.meta('alpha'))
+                        b('target_item_id'), b('target_label'), alpha)
     close(loss, g.losses()[0])
     flat, flat_names = [], []
     for k, v in tabs.items():
@@ -148,15 +165,18 @@ def test_dtcdr():
                                     p['t_out_w'], p['t_out_b']), g.t('predict'))
 
 
-@pytest.mark.parametrize('way', ['concat', 'mean'])
-def test_bitgcf(way):
-    g = Golden(f'bitgcf_{way}')
+def test_dtcdr():
+    g = Golden('dtcdr_neumf')
+    check_dtcdr(g, g.meta('alpha'))
+
+
+def check_bitgcf(g, way, n_layers, lam_s, lam_t, reg_weight):
     n_users, n_items, edges, deg = bitgcf_graph(g)
     adj = {d: O.bitgcf_norm_adj(edges[d][0], edges[d][1], n_users, n_items) for d in edges}
     tabs = {k: v.clone().requires_grad_(True) for k, v in g.tables().items()}
     b = g.batch
-    kw = dict(n_layers=2, connect_way=way, n_users=n_users, n_items=n_items, n_ov_users=g.meta('n_ov_u'),
-              n_ov_items=g.meta('n_ov_i'), lam_s=0.8, lam_t=0.7, deg=deg, reg_weight=0.001)
+    kw = dict(n_layers=n_layers, connect_way=way, n_users=n_users, n_items=n_items, n_ov_users=g.meta('n_ov_u'),
+              n_ov_items=g.meta('n_ov_i'), lam_s=lam_s, lam_t=lam_t, deg=deg, reg_weight=reg_weight)
     ls, lt = O.bitgcf_loss(tabs, adj['source'], adj['target'], b('source_user_id'), b('source_item_id'),
                            b('source_label'), b('target_user_id'), b('target_item_id'), b('target_label'), **kw)
     assert ls.shape == (1,) and lt.shape == (1,)
@@ -166,6 +186,15 @@ def test_bitgcf(way):
     for gr, k in zip(O.grads_of(ls + lt, [tabs[k] for k in order]), order):
         close(gr, g.grad(f'{k}_embedding.weight'), rtol=1e-5, atol=1e-7)
     with torch.no_grad():
-        _, _, ftu, fti = O.bitgcf_forward(tabs, adj['source'], adj['target'], 2, way, n_users, n_items,
-                                          g.meta('n_ov_u'), g.meta('n_ov_i'), 0.8, 0.7, deg)
+        _, _, ftu, fti = O.bitgcf_forward(tabs, adj['source'], adj['target'], n_layers, way, n_users, n_items,
+                                          g.meta('n_ov_u'), g.meta('n_ov_i'), lam_s, lam_t, deg)
         close((ftu[b('target_user_id')] * fti[b('target_item_id')]).sum(1), g.t('predict'))
+        if g.has('full_sort_predict'):   # bitgcf.py:264-272
+            fu = g.t('fbatch/target_user_id')
+            n_tgt_items = g.meta('n_ov_i') + g.meta('n_tgt_i')
+            close(ftu[fu] @ fti[:n_tgt_items].t(), g.t('full_sort_predict'), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize('way', ['concat', 'mean'])
+def test_bitgcf(way):
+    check_bitgcf(Golden(f'bitgcf_{way}'), way, 2, 0.8, 0.7, 0.001)

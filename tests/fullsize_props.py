@@ -97,3 +97,44 @@ def check_train_step_properties(ops, device, nu, ni, dim, K, B, seed=0, oracle=N
         torch.testing.assert_close(gur, du, rtol=1e-4, atol=1e-4 * float(du.abs().max()))
         torch.testing.assert_close(gir, di, rtol=1e-4, atol=1e-4 * float(di.abs().max()))
     return out8
+
+
+def check_spmm_properties(NormAdj, device, nu, ni, n_edges, dim, seed=0, zipf=None):
+    """BiTGCF's normalised adjacency L = D^-1/2 A D^-1/2 (bitgcf.py:92-116) and its SpMM, at any size:
+      G1 row sums   (L 1)_v = sum_{w in N(v)} (d_v + 1e-7)^-1/2 (d_w + 1e-7)^-1/2, computed here in fp64 from the edge list
+      G2 symmetry   <Y, L X> = <L Y, X>  (the backward pass of the propagation relies on it)
+      G3 linearity  L (2 X + Y) = 2 L X + L Y
+      G4 support    rows of isolated nodes are exactly zero
+    """
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    r = rng.randint(0, nu, n_edges)
+    c = np.minimum(rng.zipf(zipf, n_edges) - 1, ni - 1) if zipf else rng.randint(0, ni, n_edges)
+    adj = NormAdj(r, c, nu, ni, device)
+    n = nu + ni
+    # the reference de-duplicates edges (dict keys) and symmetrises: node ids are users [0, nu) then items [nu, nu + ni)
+    e = np.unique(r.astype(np.int64) * ni + c)
+    er, ec = e // ni, e % ni + nu
+    deg = np.bincount(er, minlength=n) + np.bincount(ec, minlength=n)
+    dinv = np.power(deg + 1e-7, -0.5)
+    w = dinv[er] * dinv[ec]
+    rowsum = np.bincount(er, weights=w, minlength=n) + np.bincount(ec, weights=w, minlength=n)
+
+    g = torch.Generator().manual_seed(seed)
+    ones = torch.ones(n, dim, device=device)
+    got = adj.spmm(ones)
+    ref = torch.from_numpy(rowsum).to(device)
+    torch.testing.assert_close(got[:, 0].double(), ref, rtol=2e-4, atol=1e-6)
+    assert torch.equal(got[:, 0], got[:, dim - 1])
+    isolated = torch.from_numpy(deg == 0).to(device)
+    assert not bool(got[isolated].any())                                                  # G4
+
+    X = torch.randn(n, dim, generator=g).to(device)
+    Y = torch.randn(n, dim, generator=g).to(device)
+    LX, LY = adj.spmm(X), adj.spmm(Y)
+    a, b = (Y.double() * LX.double()).sum(), (LY.double() * X.double()).sum()
+    scale = float((Y.double().abs() * LX.double().abs()).sum())
+    assert abs(float(a - b)) <= 1e-6 * scale, (float(a), float(b), scale)                 # G2
+    L2 = adj.spmm(2 * X + Y)
+    torch.testing.assert_close(L2, 2 * LX + LY, rtol=1e-4, atol=1e-5)                     # G3
+    return adj

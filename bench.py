@@ -188,7 +188,7 @@ def workload_config(args, ds):
 def run_xdr(args):
     import torch.distributed as dist
     from recbole_cdr_b200 import _lib, ops
-    from recbole_cdr_b200.data import Interaction, synthetic
+    from recbole_cdr_b200.data import synthetic
     from recbole_cdr_b200.model.cross_domain_recommender.emcdr import EMCDR
 
     world = int(os.environ.get('WORLD_SIZE', '1'))

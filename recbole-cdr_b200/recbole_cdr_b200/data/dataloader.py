@@ -10,7 +10,6 @@ the two domain loaders are stepped.  In-memory loaders over id arrays replace re
 * pairwise: ``step = batch_size`` positives and an extra ``NEG_PREFIX + iid`` column;
 * OVERLAP: ``{'overlap': [b, 1]}`` drawn from a shuffled ``arange(num_overlap)`` INCLUDING the PAD id 0 (data/dataset.py:694-696).
 """
-import numpy as np
 import torch
 
 from ..utils.enum_type import CrossDomainDataLoaderState

@@ -15,7 +15,7 @@ Table gradients come in two modes (``set_table_grad_mode``):
 """
 import ctypes as _ct
 import os as _os
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 
@@ -519,9 +519,6 @@ def train_steps(user_tab, item_tab, user, item_a, item_b=None, label=None, *, lo
 # ------------------------------------------------------------------------------------------------------------------
 # A4 / A14-A15 fused: gather -> small MLP -> loss head -> backward -> scatter in one kernel
 # ------------------------------------------------------------------------------------------------------------------
-import ctypes as _ct
-
-
 FUSED_MLP_ENGINES = ('fma', 'tc')  # fp32 FMA row tiles (fused_mlp.cu) / 3xTF32 tensor-core row tiles (tc_mlp.cu)
 
 

@@ -11,10 +11,8 @@ The popularity (alias-table) distribution of ``AbstractSampler._pop_sampling`` i
 """
 import copy
 
-import numpy as np
 import torch
 
-from .. import _lib
 from .._lib import call, cur_stream, ptr
 
 

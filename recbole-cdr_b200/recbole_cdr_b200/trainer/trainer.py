@@ -15,7 +15,7 @@ Two inner loops:
   persistent launch (``xdr_train_steps``) that does forward, backward and the SGD update (scatter-add of ``-lr * grad``
   into the tables); per-step losses come back in one D2H copy.  Chunks are double-buffered so copies overlap compute.
 """
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import numpy as np
 import torch

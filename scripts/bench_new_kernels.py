@@ -8,7 +8,6 @@ gpurun_out/new_kernels.jsonl)."""
 import json, os, sys, traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'recbole-cdr_b200')); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
-import numpy as np
 import torch
 from fake_data import base_config
 from recbole_cdr_b200 import _lib, ops

@@ -1,7 +1,6 @@
 """GPU parity of the drop-in model classes against tests/golden/*.npz -- outputs of the UNMODIFIED reference classes.
 
 ``load_state_dict(strict=True)`` from the reference's own parameter names doubles as the state_dict-key check."""
-import numpy as np
 import pytest
 import torch
 

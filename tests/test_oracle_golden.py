@@ -1,6 +1,5 @@
 """Pins oracle/cdr_oracle.py against tests/golden/*.npz -- outputs of the UNMODIFIED reference model classes
 (EMCDR, CMF, CoNet, DTCDR, BiTGCF from /root/reference) produced by oracle/make_golden.py.  CPU only."""
-import numpy as np
 import pytest
 import torch
 

@@ -2,7 +2,6 @@
 the negative draw (sampler/crossdomain_sampler.py:139-176, 212-213): uniform over candidates, never a used item,
 `num` blocks of len(key_ids)."""
 import numpy as np
-import pytest
 
 from oracle import sampler_oracle as S
 

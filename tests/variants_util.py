@@ -8,7 +8,7 @@ import os
 import torch
 
 from fake_data import FakeDataset, base_config
-from golden_util import GOLDEN_DIR, Golden
+from golden_util import GOLDEN_DIR
 
 VARIANTS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, 'v_*.npz')))
 EXPECTED = 13   # keep in step with make_golden_variants.py: a missing fixture must fail, not shrink the table

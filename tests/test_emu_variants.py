@@ -47,3 +47,23 @@ def test_variant_fused_conet(name):
     with emu_util.patched_ops():
         m = V.build(g, 'cpu', xdr_fused_conet=True)
         V.check_against_reference(m, g, 'cpu')
+
+
+def test_conet_full_sort_predict_blocks_and_pairwise_predict_agree():
+    """CoNet.full_sort_predict splits layer 0 into a per-item and a per-user half: any block size gives the reference's scores,
+    and each entry equals ``predict`` on that (user, item) pair."""
+    import torch
+    g = Golden('v_conet_yaml_stack')
+    with emu_util.patched_ops():
+        m = V.build(g, 'cpu')
+        fb = V.batch(g, 'cpu', 'fbatch/')
+        ref = g.t('full_sort_predict')
+        n_items = ref.shape[1]
+        for block_bytes in (256 << 20, 4 * 64 * n_items * 3, 1):     # all users at once / three users per block / one by one
+            m.full_sort_block_bytes = block_bytes
+            torch.testing.assert_close(m.full_sort_predict(fb), ref, rtol=1e-4, atol=2e-6)
+        users = fb['target_user_id']
+        from recbole_cdr_b200.data import Interaction
+        pairs = Interaction({'target_user_id': users.repeat_interleave(n_items),
+                             'target_item_id': torch.arange(n_items).repeat(users.numel())})
+        torch.testing.assert_close(m.full_sort_predict(fb).reshape(-1), m.predict(pairs).reshape(-1), rtol=1e-5, atol=1e-6)

@@ -30,6 +30,7 @@ struct KMajor {
     return k4 * lbo() + (r >> 3) * sbo() + (r & 7) * 16;
   }
   __host__ __device__ int k_step_bytes() const { return 2 * lbo(); }            // advance of the start address per MMA (K = 8)
+  __host__ __device__ bool mn_major() const { return false; }
 };
 
 // MN-major operand of R rows (R % 4 == 0) and K reduction elements (K % 8 == 0): contiguous along the row index --
@@ -45,9 +46,22 @@ struct MNMajor {
     return (k >> 3) * lbo() + r4 * sbo() + (k & 7) * 16;
   }
   __host__ __device__ int k_step_bytes() const { return lbo(); }
+  __host__ __device__ bool mn_major() const { return true; }
 };
 
-__host__ __device__ inline uint64_t make_desc(uint32_t smem_addr, int lbo, int sbo) {
+// XDR_TC5_SWAP (compile-time, -DXDR_TC5_SWAP=n): which descriptor field carries which stride is the one part of this reading
+// that only hardware can settle (scripts/ubench_tcgen05.cu prints the answer).  bit 0 exchanges the two fields for K-major
+// operands, bit 1 for MN-major operands; scripts/r2_gpu_session.sh rebuilds with the other settings when the self-test of the
+// default reading fails, so the answer costs no extra GPU round trip.
+#ifndef XDR_TC5_SWAP
+#define XDR_TC5_SWAP 0
+#endif
+__host__ __device__ inline uint64_t make_desc(uint32_t smem_addr, int lbo, int sbo, bool mn_major = false) {
+  if ((XDR_TC5_SWAP >> (mn_major ? 1 : 0)) & 1) {
+    const int t = lbo;
+    lbo = sbo;
+    sbo = t;
+  }
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
   d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
@@ -112,10 +126,12 @@ __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fenc
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // one full warp; ncols a power of two >= 32; the base address lands in *dst_smem
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  __syncwarp();  // .sync.aligned: the warp must be converged
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  __syncwarp();
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
 }
 // issued by ONE thread: D[tmem] (+)= A[smem desc] * B[smem desc]^T, K = 8
@@ -180,8 +196,10 @@ __device__ __forceinline__ void mma_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint3
                                            uint32_t b_lo, const LayB& lb, uint32_t idesc, int K, bool accumulate) {
   for (int ks = 0; ks < K / 8; ++ks) {
     const uint32_t ao = ks * la.k_step_bytes(), bo = ks * lb.k_step_bytes();
-    const uint64_t dah = make_desc(a_hi + ao, la.lbo(), la.sbo()), dal = make_desc(a_lo + ao, la.lbo(), la.sbo());
-    const uint64_t dbh = make_desc(b_hi + bo, lb.lbo(), lb.sbo()), dbl = make_desc(b_lo + bo, lb.lbo(), lb.sbo());
+    const uint64_t dah = make_desc(a_hi + ao, la.lbo(), la.sbo(), la.mn_major()),
+                   dal = make_desc(a_lo + ao, la.lbo(), la.sbo(), la.mn_major());
+    const uint64_t dbh = make_desc(b_hi + bo, lb.lbo(), lb.sbo(), lb.mn_major()),
+                   dbl = make_desc(b_lo + bo, lb.lbo(), lb.sbo(), lb.mn_major());
     mma_tf32(tmem_d, dal, dbh, idesc, accumulate || ks > 0);   // small terms first
     mma_tf32(tmem_d, dah, dbl, idesc, true);
     mma_tf32(tmem_d, dah, dbh, idesc, true);
@@ -248,6 +266,7 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
   fence_after_sync();
   for (int c = 0; c < N; c += 16) {
     uint32_t r[16];
+    __syncwarp();  // the spin above exits lane by lane; tcgen05.ld is warp-collective
     tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, r);
     tmem_ld_wait();
     for (int j = 0; j < 16 && c + j < N; ++j) D[(size_t)tid * N + c + j] = __uint_as_float(r[j]);

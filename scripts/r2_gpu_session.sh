@@ -27,10 +27,27 @@ if [ "$STAGE" = validate ] || [ "$STAGE" = all ]; then
   # barrier protocol would hang: keep it away from the other tests)
   XDR_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_unvalidated.py -q -k "tc5_selftest" --timeout 60 \
       > gpurun_out/tc5_selftest.log 2>&1
-  say "tc5 self-test GEMM (K-/MN-major operands) rc=$?"
+  TC5_RC=$?
+  say "tc5 self-test GEMM (K-/MN-major operands) rc=$TC5_RC"
+  TC5_LIB=
+  if [ $TC5_RC -ne 0 ]; then
+    # the default descriptor reading failed: try the other assignments of the two stride fields (tc5.cuh XDR_TC5_SWAP:
+    # bit 0 = K-major operands, bit 1 = MN-major operands) in the same call, and keep the first library that passes
+    for sw in 1 2 3; do
+      XDR_EXTRA_NVCC_FLAGS="-DXDR_TC5_SWAP=$sw" XDR_BUILD_DIR=build_swap$sw XDR_LIB_NAME=libxdr_swap$sw.so \
+          python recbole-cdr_b200/build.py > gpurun_out/build_swap$sw.log 2>&1
+      XDR_LIB=$LIBDIR/libxdr_swap$sw.so XDR_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_unvalidated.py -q \
+          -k "tc5_selftest" --timeout 60 > gpurun_out/tc5_selftest_swap$sw.log 2>&1
+      rc=$?
+      say "tc5 self-test with XDR_TC5_SWAP=$sw rc=$rc"
+      if [ $rc -eq 0 ] && [ -z "$TC5_LIB" ]; then TC5_LIB=$LIBDIR/libxdr_swap$sw.so; fi
+    done
+  fi
+  [ -n "$TC5_LIB" ] && export XDR_LIB=$TC5_LIB && say "tc5 top-k runs on $TC5_LIB"
   XDR_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_unvalidated.py -q -x -k "full_sort_topk and tc5 and 300" --timeout 60 \
       > gpurun_out/tc5_topk.log 2>&1
   say "tc5 top-k (smallest case) rc=$?"
+  unset XDR_LIB
   # the tcgen05 descriptor experiment is tiny: run it in the first call so that the answer is there early
   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o /tmp/ubench_tcgen05 scripts/ubench_tcgen05.cu > gpurun_out/tcgen05.log 2>&1 \
       && timeout 120 /tmp/ubench_tcgen05 >> gpurun_out/tcgen05.log 2>&1

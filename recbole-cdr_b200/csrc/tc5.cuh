@@ -49,6 +49,31 @@ struct MNMajor {
   __host__ __device__ bool mn_major() const { return true; }
 };
 
+// 16-bit operands (bf16 on kind::f16): the same canonical layouts with 8 elements per 16-byte chunk; one MMA consumes
+// K = 16 = two 16-byte K chunks (K-major) or two groups of eight reduction rows (MN-major).  A bf16 hi plane + a bf16 lo
+// plane (x ~= hi + lo, bf16x3) together take 4 bytes per element -- the footprint of the fp32 data itself, half of the TF32
+// hi / lo pair -- at twice the MMA rate: the operand format of the tcgen05 training kernels.
+//   K-major : element (r, k) at (k/8)*LBO + (r/8)*SBO + (r%8)*16 + (k%8)*2      LBO = R*16,        SBO = 128
+//   MN-major: element (r, k) at (k/8)*LBO + (r/8)*SBO + (k%8)*16 + (r%8)*2      LBO = (R/8)*128,   SBO = 128
+struct KMajor16 {
+  int rows;  // R (multiple of 8)
+  __host__ __device__ int lbo() const { return rows * 16; }
+  __host__ __device__ int sbo() const { return 128; }
+  __host__ __device__ int bytes(int k) const { return rows * k * 2; }
+  __host__ __device__ int chunk_offset(int r, int k8) const { return k8 * lbo() + (r >> 3) * sbo() + (r & 7) * 16; }
+  __host__ __device__ int k_step_bytes() const { return 2 * lbo(); }            // K = 16 per MMA
+  __host__ __device__ bool mn_major() const { return false; }
+};
+struct MNMajor16 {
+  int rows;  // R (multiple of 8)
+  __host__ __device__ int lbo() const { return (rows >> 3) * 128; }
+  __host__ __device__ int sbo() const { return 128; }
+  __host__ __device__ int bytes(int k) const { return rows * k * 2; }
+  __host__ __device__ int chunk_offset(int r8, int k) const { return (k >> 3) * lbo() + r8 * sbo() + (k & 7) * 16; }
+  __host__ __device__ int k_step_bytes() const { return 2 * lbo(); }            // K = 16 = two groups of eight reduction rows
+  __host__ __device__ bool mn_major() const { return true; }
+};
+
 // XDR_TC5_SWAP (compile-time, -DXDR_TC5_SWAP=n): which descriptor field carries which stride is the one part of this reading
 // that only hardware can settle (scripts/ubench_tcgen05.cu prints the answer).  bit 0 exchanges the two fields for K-major
 // operands, bit 1 for MN-major operands; scripts/r2_gpu_session.sh rebuilds with the other settings when the self-test of the
@@ -74,6 +99,11 @@ __host__ __device__ inline uint32_t make_idesc_tf32(int M, int N, bool a_mn_majo
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {   // kind::f16, BF16 x BF16 -> F32
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---- PTX wrappers (emulator twins under XDR_EMU) --------------------------------------------------------------------------
 #ifdef XDR_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return emu::smem_addr(p); }
@@ -93,6 +123,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
   emu::umma_tf32(tmem_d, da, db, idesc, accumulate);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
+  emu::umma_bf16(tmem_d, da, db, idesc, accumulate);
 }
 __device__ __forceinline__ void commit(uint64_t* bar) { emu::mbar_arrive(bar); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) { emu::tmem_ld(taddr, r, 16); }
@@ -141,6 +174,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(zero)
+      : "memory");
+}
+// the 16-bit twin: kind::f16 (the instruction descriptor says BF16), K = 16
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
+  const uint32_t acc = accumulate ? 1u : 0u, zero = 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(zero)
       : "memory");
 }
@@ -206,23 +249,88 @@ __device__ __forceinline__ void mma_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint3
   }
 }
 
+// ---- bf16x3 -----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf16_rn(float x) {   // round-to-nearest-even, result in the low 16 bits
+  uint32_t u = __float_as_uint(x);
+  if ((u & 0x7f800000u) == 0x7f800000u) return u >> 16;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return u >> 16;
+}
+__device__ __forceinline__ void split_bf16_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {   // element 0 in the low half
+  const uint32_t h0 = bf16_rn(x0), h1 = bf16_rn(x1);
+  hi = h0 | (h1 << 16);
+  lo = bf16_rn(x0 - __uint_as_float(h0 << 16)) | (bf16_rn(x1 - __uint_as_float(h1 << 16)) << 16);
+}
+// eight values that are consecutive along the operand's contiguous direction -> one 16-byte chunk in the hi plane and one in
+// the lo plane.  K-major: (row r, K elements 8*k8 ..);  MN-major: (rows 8*r8 .., reduction index k) -- pass the matching offset.
+__device__ __forceinline__ void store_split8(unsigned char* hi_plane, unsigned char* lo_plane, int chunk_off, float4 v0, float4 v1) {
+  uint4 h, l;
+  split_bf16_pair(v0.x, v0.y, h.x, l.x);
+  split_bf16_pair(v0.z, v0.w, h.y, l.y);
+  split_bf16_pair(v1.x, v1.y, h.z, l.z);
+  split_bf16_pair(v1.z, v1.w, h.w, l.w);
+  *reinterpret_cast<uint4*>(hi_plane + chunk_off) = h;
+  *reinterpret_cast<uint4*>(lo_plane + chunk_off) = l;
+}
+// D (+)= A * B^T over K (multiple of 16) as bf16x3 (a_lo b_hi + a_hi b_lo + a_hi b_hi, ~2^-17 relative per product).  ONE thread.
+template <typename LayA, typename LayB>
+__device__ __forceinline__ void mma_bf16x3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, const LayA& la, uint32_t b_hi,
+                                           uint32_t b_lo, const LayB& lb, uint32_t idesc, int K, bool accumulate) {
+  for (int ks = 0; ks < K / 16; ++ks) {
+    const uint32_t ao = ks * la.k_step_bytes(), bo = ks * lb.k_step_bytes();
+    const uint64_t dah = make_desc(a_hi + ao, la.lbo(), la.sbo(), la.mn_major()),
+                   dal = make_desc(a_lo + ao, la.lbo(), la.sbo(), la.mn_major());
+    const uint64_t dbh = make_desc(b_hi + bo, lb.lbo(), lb.sbo(), lb.mn_major()),
+                   dbl = make_desc(b_lo + bo, lb.lbo(), lb.sbo(), lb.mn_major());
+    mma_bf16(tmem_d, dal, dbh, idesc, accumulate || ks > 0);
+    mma_bf16(tmem_d, dah, dbl, idesc, true);
+    mma_bf16(tmem_d, dah, dbh, idesc, true);
+  }
+}
+
 // ---- self-test: D[128 x N] = A[128 x K] * B[N x K]^T from row-major operands in global memory, one CTA of 128 threads, with
 // A and B staged K-major or MN-major.  Runs under the emulator and, on hardware, checks the descriptor reading through the
 // library itself (xdr_tc5_selftest).
+// fmt 0: 3xTF32 on fp32 hi / lo planes (K % 8 == 0);  fmt 1: bf16x3 on bf16 hi / lo planes (K % 16 == 0).
 __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, int N, int K,
-                                                          int a_mn, int b_mn, float* __restrict__ D) {
+                                                          int a_mn, int b_mn, int fmt, float* __restrict__ D) {
   XDR_DYN_SMEM_ALIGNED(unsigned char, smem_t5, 128);
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr int M = 128;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_t5);
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem_t5 + 8);
+  const int esz = fmt ? 2 : 4;
   unsigned char* a_hi = smem_t5 + 128;
-  unsigned char* a_lo = a_hi + M * K * 4;
-  unsigned char* b_hi = a_lo + M * K * 4;
-  unsigned char* b_lo = b_hi + N * K * 4;
+  unsigned char* a_lo = a_hi + M * K * esz;
+  unsigned char* b_hi = a_lo + M * K * esz;
+  unsigned char* b_lo = b_hi + N * K * esz;
   const KMajor ka{M}, kb{N};
   const MNMajor ma{M}, mb{N};
-  for (int e = tid; e < M * K / 4; e += 128) {
+  const KMajor16 ka16{M}, kb16{N};
+  const MNMajor16 ma16{M}, mb16{N};
+  // eight consecutive values along an operand's contiguous direction (X is row-major [R][K])
+  auto along_k = [&](const float* X, int r, int k8, float4& v0, float4& v1) {
+    v0 = *reinterpret_cast<const float4*>(X + r * K + 8 * k8);
+    v1 = *reinterpret_cast<const float4*>(X + r * K + 8 * k8 + 4);
+  };
+  auto along_rows = [&](const float* X, int r8, int k, float4& v0, float4& v1) {
+    const float* p = X + (size_t)(8 * r8) * K + k;
+    v0 = make_float4(p[0], p[K], p[2 * K], p[3 * K]);
+    v1 = make_float4(p[4 * K], p[5 * K], p[6 * K], p[7 * K]);
+  };
+  if (fmt) {
+    for (int e = tid; e < M * K / 8; e += 128) {
+      float4 v0, v1;
+      if (!a_mn) { along_k(A, e / (K / 8), e % (K / 8), v0, v1); store_split8(a_hi, a_lo, ka16.chunk_offset(e / (K / 8), e % (K / 8)), v0, v1); }
+      else { along_rows(A, e / K, e % K, v0, v1); store_split8(a_hi, a_lo, ma16.chunk_offset(e / K, e % K), v0, v1); }
+    }
+    for (int e = tid; e < N * K / 8; e += 128) {
+      float4 v0, v1;
+      if (!b_mn) { along_k(B, e / (K / 8), e % (K / 8), v0, v1); store_split8(b_hi, b_lo, kb16.chunk_offset(e / (K / 8), e % (K / 8)), v0, v1); }
+      else { along_rows(B, e / K, e % K, v0, v1); store_split8(b_hi, b_lo, mb16.chunk_offset(e / K, e % K), v0, v1); }
+    }
+  }
+  for (int e = tid; !fmt && e < M * K / 4; e += 128) {
     if (!a_mn) {
       const int r = e / (K / 4), k4 = e % (K / 4);
       store_split4(a_hi, a_lo, ka, r, k4, *reinterpret_cast<const float4*>(A + r * K + 4 * k4));
@@ -232,7 +340,7 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
                                                         A[(4 * r4 + 3) * K + k]));
     }
   }
-  for (int e = tid; e < N * K / 4; e += 128) {
+  for (int e = tid; !fmt && e < N * K / 4; e += 128) {
     if (!b_mn) {
       const int r = e / (K / 4), k4 = e % (K / 4);
       store_split4(b_hi, b_lo, kb, r, k4, *reinterpret_cast<const float4*>(B + r * K + 4 * k4));
@@ -254,9 +362,14 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
   fence_after_sync();
   const uint32_t tmem = *tmem_base_smem;
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_tf32(M, N, a_mn != 0, b_mn != 0);
+    const uint32_t idesc = fmt ? make_idesc_bf16(M, N, a_mn != 0, b_mn != 0) : make_idesc_tf32(M, N, a_mn != 0, b_mn != 0);
     const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-    if (!a_mn && !b_mn) mma_3xtf32(tmem, ah, al, ka, bh, bl, kb, idesc, K, false);
+    if (fmt) {
+      if (!a_mn && !b_mn) mma_bf16x3(tmem, ah, al, ka16, bh, bl, kb16, idesc, K, false);
+      else if (!a_mn && b_mn) mma_bf16x3(tmem, ah, al, ka16, bh, bl, mb16, idesc, K, false);
+      else if (a_mn && !b_mn) mma_bf16x3(tmem, ah, al, ma16, bh, bl, kb16, idesc, K, false);
+      else mma_bf16x3(tmem, ah, al, ma16, bh, bl, mb16, idesc, K, false);
+    } else if (!a_mn && !b_mn) mma_3xtf32(tmem, ah, al, ka, bh, bl, kb, idesc, K, false);
     else if (!a_mn && b_mn) mma_3xtf32(tmem, ah, al, ka, bh, bl, mb, idesc, K, false);
     else if (a_mn && !b_mn) mma_3xtf32(tmem, ah, al, ma, bh, bl, kb, idesc, K, false);
     else mma_3xtf32(tmem, ah, al, ma, bh, bl, mb, idesc, K, false);

@@ -431,15 +431,28 @@ int xdr_full_sort_topk_tc5(const float* user_vecs, int64_t batch, const float* i
 // Self-test of the tcgen05 building blocks: D[128, N] = A[128, K] B[N, K]^T (3xTF32) with each operand staged K-major
 // (a_mn / b_mn = 0) or MN-major (= 1) in shared memory.  N % 16 == 0, N <= 256, K % 8 == 0, both planes of both operands
 // must fit shared memory.  Device pointers, row-major fp32.
-int xdr_tc5_selftest(const float* A, const float* B, int N, int K, int a_mn, int b_mn, float* D, xdr_stream_t stream) {
-  XDR_REQUIRE(A && B && D, "xdr_tc5_selftest: null pointer");
-  XDR_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 8 && K % 8 == 0, "xdr_tc5_selftest: bad shape N=%d K=%d", N, K);
-  const size_t smem = 128 + (size_t)2 * 128 * K * 4 + (size_t)2 * N * K * 4;
-  XDR_REQUIRE(smem <= 224 * 1024, "xdr_tc5_selftest: operands do not fit shared memory");
+static int tc5_selftest(const char* who, const float* A, const float* B, int N, int K, int a_mn, int b_mn, int fmt, float* D,
+                        xdr_stream_t stream) {
+  const int kq = fmt ? 16 : 8, esz = fmt ? 2 : 4;
+  XDR_REQUIRE(A && B && D, "%s: null pointer", who);
+  XDR_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= kq && K % kq == 0, "%s: bad shape N=%d K=%d", who, N, K);
+  XDR_REQUIRE(aligned16(A) && aligned16(B), "%s: operands must be 16-byte aligned", who);
+  const size_t smem = 128 + (size_t)2 * 128 * K * esz + (size_t)2 * N * K * esz;
+  XDR_REQUIRE(smem <= 224 * 1024, "%s: operands do not fit shared memory", who);
   XDR_CUDA_OK(cudaFuncSetAttribute(tc5::selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  XDR_LAUNCH((tc5::selftest_kernel), 1, 128, smem, (cudaStream_t)stream, A, B, N, K, a_mn, b_mn, D);
+  XDR_LAUNCH((tc5::selftest_kernel), 1, 128, smem, (cudaStream_t)stream, A, B, N, K, a_mn, b_mn, fmt, D);
   XDR_LAUNCH_OK();
   return XDR_OK;
+}
+
+int xdr_tc5_selftest(const float* A, const float* B, int N, int K, int a_mn, int b_mn, float* D, xdr_stream_t stream) {
+  return tc5_selftest("xdr_tc5_selftest", A, B, N, K, a_mn, b_mn, 0, D, stream);
+}
+
+// The same product as bf16x3 on kind::f16 (bf16 hi / lo planes, K % 16 == 0): the operand format planned for the tcgen05
+// training kernels.
+int xdr_tc5_selftest_bf16(const float* A, const float* B, int N, int K, int a_mn, int b_mn, float* D, xdr_stream_t stream) {
+  return tc5_selftest("xdr_tc5_selftest_bf16", A, B, N, K, a_mn, b_mn, 1, D, stream);
 }
 
 }  // extern "C"

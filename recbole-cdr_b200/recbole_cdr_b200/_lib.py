@@ -76,6 +76,7 @@ PROTOTYPES = {
                                       c_f32, c_f64, c_f64, c_vp, c_vp]),
     'xdr_topk_workspace_bytes': (c_sz, [c_i64, c_int]),
     'xdr_tc5_selftest': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    'xdr_tc5_selftest_bf16': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'xdr_full_sort_topk_tc5': (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'xdr_full_sort_topk': (c_int, [c_vp, c_i64, c_vp, c_i64, c_int, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     'xdr_select_dot': (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),

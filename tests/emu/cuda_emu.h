@@ -33,6 +33,7 @@
 
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(8) float2 { float x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct uint3_emu { unsigned x, y, z; };
@@ -112,7 +113,7 @@ inline State& st() {
 // Work counters of everything launched since the last reset (per warp-level instruction for the MMAs, bytes for the row
 // traffic helpers of xdr_common.cuh): a pre-measurement estimate of instruction mix and algorithmic traffic.
 struct Counters {
-  uint64_t mma_tf32 = 0, mma_bf16 = 0, umma_tf32 = 0;   // warp-level mma.sync instructions; tcgen05.mma instructions
+  uint64_t mma_tf32 = 0, mma_bf16 = 0, umma_tf32 = 0, umma_bf16 = 0;   // warp-level mma.sync instructions; tcgen05.mma instructions
   uint64_t row_load_bytes = 0, row_red_bytes = 0;       // ld_row4 / ldg_row4 ; red_add4
   uint64_t cta_barriers = 0;
 };
@@ -217,6 +218,35 @@ inline float umma_operand(uint64_t desc, bool mn_major, unsigned r, unsigned k) 
   uint32_t u;
   std::memcpy(&u, smem_ptr(start + off), 4);
   return as_float(u & 0xffffe000u);
+}
+// 16-bit operands (8 elements per 16-byte chunk): the same canonical layouts with T = 8
+inline float umma_operand_bf16(uint64_t desc, bool mn_major, unsigned r, unsigned k) {
+  const uint32_t start = (uint32_t)(desc & 0x3fffu) << 4, lbo = (uint32_t)((desc >> 16) & 0x3fffu) << 4,
+                 sbo = (uint32_t)((desc >> 32) & 0x3fffu) << 4;
+  const uint32_t off = mn_major ? (k / 8) * lbo + (r / 8) * sbo + (k % 8) * 16 + (r % 8) * 2
+                                : (k / 8) * lbo + (r / 8) * sbo + (r % 8) * 16 + (k % 8) * 2;
+  uint16_t h;
+  std::memcpy(&h, smem_ptr(start + off), 2);
+  return as_float((uint32_t)h << 16);
+}
+// tcgen05.mma.cta_group::1.kind::f16 with BF16 operands: D[M x N] (+)= A[M x 16] * B[N x 16]^T, fp32 accumulation
+inline void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  ++counters().umma_bf16;
+  const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;
+  const unsigned N = ((idesc >> 17) & 0x3fu) << 3, M = ((idesc >> 24) & 0x1fu) << 4;
+  if (M != 128 || ((idesc >> 4) & 3u) != 1u || ((idesc >> 7) & 7u) != 1u || ((idesc >> 10) & 7u) != 1u) {
+    std::fprintf(stderr, "cuda_emu: only M = 128, F32 accumulate, BF16 operands are modelled for kind::f16 (idesc %08x)\n", idesc);
+    std::abort();
+  }
+  for (unsigned m = 0; m < M; ++m)
+    for (unsigned n = 0; n < N; ++n) {
+      double s = 0;
+      for (unsigned k = 0; k < 16; ++k)
+        s += (double)umma_operand_bf16(desc_a, a_mn, m, k) * (double)umma_operand_bf16(desc_b, b_mn, n, k);
+      uint32_t& d = tmem_at(tmem_d, m, n);
+      const float r = (accumulate ? as_float(d) : 0.f) + (float)s;
+      std::memcpy(&d, &r, 4);
+    }
 }
 // tcgen05.mma.cta_group::1.kind::tf32: D[M x N] (+)= A[M x 8] * B[N x 8]^T
 inline void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {

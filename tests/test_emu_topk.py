@@ -155,3 +155,24 @@ def test_tc5_selftest_gemm_all_majors(a_mn, b_mn, N, K):
     rc = L.xdr_tc5_selftest(p(A), p(B), ctypes.c_int(N), ctypes.c_int(K), ctypes.c_int(a_mn), ctypes.c_int(b_mn), p(D), None)
     assert rc == 0, L.emu_last_error()
     np.testing.assert_allclose(D, A.astype(np.float64) @ B.astype(np.float64).T, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize('N,K', [(64, 64), (16, 16), (128, 32)])
+def test_tc5_selftest_gemm_bf16x3_all_majors(a_mn, b_mn, N, K):
+    """The 16-bit building blocks: bf16 hi / lo planes (8 elements per 16-byte chunk) in both majors, kind::f16 descriptors,
+    three MMAs per product (bf16x3)."""
+    L = emu_util.lib()
+    emu_util.config(sms=1, seed=0)
+    rng = np.random.RandomState(N + K + 1)
+    A = rng.randn(128, K).astype(np.float32)
+    B = rng.randn(N, K).astype(np.float32)
+    D = np.zeros((128, N), np.float32)
+    p = emu_util.p
+    rc = L.xdr_tc5_selftest_bf16(p(A), p(B), ctypes.c_int(N), ctypes.c_int(K), ctypes.c_int(a_mn), ctypes.c_int(b_mn), p(D), None)
+    assert rc == 0, L.emu_last_error()
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    mass = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T      # the dropped lo*lo term is ~2^-16 of each product
+    assert np.all(np.abs(D - ref) <= 2.0 ** -15 * mass + 1e-6)
+    # and it is far better than one bf16 pass (~2^-8 per product): the lo planes are really used
+    assert np.max(np.abs(D - ref) / mass) < 2.0 ** -14

@@ -348,6 +348,20 @@ def test_tc5_selftest_gemm_all_majors(a_mn, b_mn):
     torch.testing.assert_close(D.cpu().double(), A.cpu().double() @ B.cpu().double().T, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_tc5_selftest_gemm_bf16x3_all_majors(a_mn, b_mn):
+    """The same on kind::f16 with bf16 hi / lo planes (bf16x3): the operand format planned for the tcgen05 training kernels."""
+    g = torch.Generator().manual_seed(10 + a_mn * 2 + b_mn)
+    N, K = 64, 64
+    A, B = torch.randn(128, K, generator=g).to(dev()), torch.randn(N, K, generator=g).to(dev())
+    D = torch.zeros(128, N, device=dev())
+    lib().call('xdr_tc5_selftest_bf16', A.data_ptr(), B.data_ptr(), N, K, a_mn, b_mn, D.data_ptr(), lib().cur_stream())
+    torch.cuda.synchronize()
+    ref = A.cpu().double() @ B.cpu().double().T
+    mass = A.cpu().double().abs() @ B.cpu().double().abs().T
+    assert bool(((D.cpu().double() - ref).abs() <= 2.0 ** -15 * mass + 1e-6).all())
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 # the second set of reference goldens (tests/golden/v_*.npz) through the kernels that have not met hardware yet
 # ---------------------------------------------------------------------------------------------------------------------------

@@ -254,7 +254,8 @@ XDR_API int xdr_full_sort_topk_tc5(const float* user_vecs, int64_t batch, const 
  * staged K-major (0) or MN-major (1) in shared memory.  Row-major fp32 device pointers; N % 16 == 0, N <= 256, K % 8 == 0. */
 XDR_API int xdr_tc5_selftest(const float* A, const float* B, int N, int K, int a_mn, int b_mn, float* D, xdr_stream_t stream);
 /* The same product as bf16x3 on tcgen05.mma kind::f16 (bf16 hi / lo operand planes, 8 elements per 16-byte chunk, K % 16 == 0):
- * the operand format planned for the tcgen05 training kernels.  ~2^-16 relative per product. */
+ * the operand format planned for the tcgen05 training kernels.  ~2^-16 relative per product.  a_mn = 2: A is staged as a
+ * row-block-major tile (the physical layout of an MN-major operand) and read through its K-major view (tc5.cuh RowBlock16). */
 XDR_API int xdr_tc5_selftest_bf16(const float* A, const float* B, int N, int K, int a_mn, int b_mn, float* D, xdr_stream_t stream);
 XDR_API int xdr_full_sort_topk(const float* user_vecs, int64_t batch, const float* item_tab, int64_t n_items, int dim,
                                int64_t first_item, const int64_t* hist_ptr, const int64_t* hist_ids, int k,

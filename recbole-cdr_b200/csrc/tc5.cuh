@@ -74,6 +74,28 @@ struct MNMajor16 {
   __host__ __device__ bool mn_major() const { return true; }
 };
 
+// ONE tile, two views.  The physical layout of MNMajor16 over X[k = row][n = column] stores the 8 x 8 core matrices row-block
+// by row-block.  Read with the two stride fields exchanged in meaning it is also a K-major operand (m = row, k = column):
+// the next 16 bytes of K are the next core matrix (LBO = 128), the next eight rows a whole row of core matrices further
+// (SBO = (C/8)*128).  So an activation tile written once feeds both the forward / input-gradient product (K-major A) and the
+// weight-gradient product dZ^T X (MN-major B) -- no second, transposed copy in shared memory.  Needs both strides to be free
+// parameters of the descriptor: the "Kb" rows of scripts/ubench_tcgen05.cu check that on hardware.
+struct RowBlock16 {
+  int rows, cols;  // tile shape, both multiples of 8; bf16 elements
+  __host__ __device__ int bytes() const { return rows * cols * 2; }
+  __host__ __device__ int chunk_offset(int r, int c8) const { return (r >> 3) * (cols >> 3) * 128 + c8 * 128 + (r & 7) * 16; }
+  struct View {
+    int lbo_, sbo_, kstep_;
+    bool mn_;
+    __host__ __device__ int lbo() const { return lbo_; }
+    __host__ __device__ int sbo() const { return sbo_; }
+    __host__ __device__ int k_step_bytes() const { return kstep_; }
+    __host__ __device__ bool mn_major() const { return mn_; }
+  };
+  __host__ __device__ View as_k_major() const { return View{128, (cols >> 3) * 128, 256, false}; }               // (m = row, k = col)
+  __host__ __device__ View as_mn_major() const { return View{(cols >> 3) * 128, 128, 2 * (cols >> 3) * 128, true}; }  // (n = col, k = row)
+};
+
 // XDR_TC5_SWAP (compile-time, -DXDR_TC5_SWAP=n): which descriptor field carries which stride is the one part of this reading
 // that only hardware can settle (scripts/ubench_tcgen05.cu prints the answer).  bit 0 exchanges the two fields for K-major
 // operands, bit 1 for MN-major operands; scripts/r2_gpu_session.sh rebuilds with the other settings when the self-test of the
@@ -321,7 +343,8 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
   if (fmt) {
     for (int e = tid; e < M * K / 8; e += 128) {
       float4 v0, v1;
-      if (!a_mn) { along_k(A, e / (K / 8), e % (K / 8), v0, v1); store_split8(a_hi, a_lo, ka16.chunk_offset(e / (K / 8), e % (K / 8)), v0, v1); }
+      if (a_mn == 2) { along_k(A, e / (K / 8), e % (K / 8), v0, v1); store_split8(a_hi, a_lo, RowBlock16{M, K}.chunk_offset(e / (K / 8), e % (K / 8)), v0, v1); }
+      else if (!a_mn) { along_k(A, e / (K / 8), e % (K / 8), v0, v1); store_split8(a_hi, a_lo, ka16.chunk_offset(e / (K / 8), e % (K / 8)), v0, v1); }
       else { along_rows(A, e / K, e % K, v0, v1); store_split8(a_hi, a_lo, ma16.chunk_offset(e / K, e % K), v0, v1); }
     }
     for (int e = tid; e < N * K / 8; e += 128) {
@@ -362,9 +385,13 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
   fence_after_sync();
   const uint32_t tmem = *tmem_base_smem;
   if (tid == 0) {
-    const uint32_t idesc = fmt ? make_idesc_bf16(M, N, a_mn != 0, b_mn != 0) : make_idesc_tf32(M, N, a_mn != 0, b_mn != 0);
+    const uint32_t idesc = fmt ? make_idesc_bf16(M, N, a_mn == 1, b_mn != 0) : make_idesc_tf32(M, N, a_mn != 0, b_mn != 0);
     const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-    if (fmt) {
+    if (fmt && a_mn == 2) {
+      const RowBlock16::View va = RowBlock16{M, K}.as_k_major();
+      if (!b_mn) mma_bf16x3(tmem, ah, al, va, bh, bl, kb16, idesc, K, false);
+      else mma_bf16x3(tmem, ah, al, va, bh, bl, mb16, idesc, K, false);
+    } else if (fmt) {
       if (!a_mn && !b_mn) mma_bf16x3(tmem, ah, al, ka16, bh, bl, kb16, idesc, K, false);
       else if (!a_mn && b_mn) mma_bf16x3(tmem, ah, al, ka16, bh, bl, mb16, idesc, K, false);
       else if (a_mn && !b_mn) mma_bf16x3(tmem, ah, al, ma16, bh, bl, kb16, idesc, K, false);

@@ -435,6 +435,7 @@ static int tc5_selftest(const char* who, const float* A, const float* B, int N, 
                         xdr_stream_t stream) {
   const int kq = fmt ? 16 : 8, esz = fmt ? 2 : 4;
   XDR_REQUIRE(A && B && D, "%s: null pointer", who);
+  XDR_REQUIRE(a_mn >= 0 && a_mn <= (fmt ? 2 : 1) && (b_mn == 0 || b_mn == 1), "%s: bad operand major", who);
   XDR_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= kq && K % kq == 0, "%s: bad shape N=%d K=%d", who, N, K);
   XDR_REQUIRE(aligned16(A) && aligned16(B), "%s: operands must be 16-byte aligned", who);
   const size_t smem = 128 + (size_t)2 * 128 * K * esz + (size_t)2 * N * K * esz;

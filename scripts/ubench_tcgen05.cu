@@ -26,7 +26,8 @@
 constexpr int M = 128, N = 64, K = 64;  // one UMMA tile: D[128 x 64] += A[128 x 8] B[64 x 8]^T per instruction, K/8 instructions
 
 struct Variant {
-  int a_mn_major, b_mn_major;  // 0 = K-major, 1 = MN-major
+  int a_mn_major, b_mn_major;  // 0 = K-major, 1 = MN-major; A only: 2 = K-major with the core matrices stored row-block-major
+                               // (the physical layout of an MN-major operand) -- one shared-memory tile serving both views
   int swap_lbo_sbo;            // 0 = as read from the CUTLASS headers, 1 = the two descriptor fields exchanged
   int bf16;                    // 0 = kind::tf32 on fp32 operands (K = 8 per MMA), 1 = kind::f16 on bf16 operands (K = 16)
 };
@@ -42,6 +43,12 @@ struct OperandLayout {
 // T = elements per 16-byte chunk (4 for tf32, 8 for bf16); one instruction consumes K = 2T (32 bytes of K)
 __host__ __device__ inline OperandLayout operand_layout(int rows, int mn_major, int T = 4) {
   OperandLayout o;
+  if (mn_major == 2) {        // K-major VIEW of a tile whose 8 x (16 B) core matrices are stored row-block by row-block: the
+    o.lbo = 128;              // next 16 bytes of K are the next core matrix, the next 8 rows a whole row of core matrices later.
+    o.sbo = (K / T) * 128;    // This is exactly how an MN-major operand X[k = row][n = column] lies in memory, so if the two
+    o.k_step_bytes = 2 * 128; // stride fields are free parameters, ONE copy of an activation tile feeds the forward product
+    return o;                 // (K-major) and the weight-gradient product dZ^T X (MN-major).
+  }
   if (!mn_major) {            // K-major: 16-byte K chunks are `rows * 16` bytes apart, 8-row groups 128 bytes apart
     o.lbo = rows * 16;
     o.sbo = 128;
@@ -56,6 +63,7 @@ __host__ __device__ inline OperandLayout operand_layout(int rows, int mn_major, 
 __host__ __device__ inline int operand_offset(int rows, int mn_major, int mn, int k, int T = 4) {
   const OperandLayout o = operand_layout(rows, mn_major, T);
   const int es = 16 / T;
+  if (mn_major == 2) return (k / T) * o.lbo + (mn / 8) * o.sbo + (mn % 8) * 16 + (k % T) * es;
   if (!mn_major) return (k / T) * o.lbo + (mn / 8) * o.sbo + (mn % 8) * 16 + (k % T) * es;
   return (k / 8) * o.lbo + (mn / T) * o.sbo + (k % 8) * 16 + (mn % T) * es;
 }
@@ -109,7 +117,7 @@ __global__ void __launch_bounds__(128, 1) umma_tf32_kernel(const float* __restri
     const OperandLayout la = operand_layout(M, v.a_mn_major, T), lb = operand_layout(N, v.b_mn_major, T);
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(sA), b0 = (uint32_t)__cvta_generic_to_shared(sB);
     const uint32_t fmt = v.bf16 ? 1u : 2u;   // F16F32Format: 1 = BF16, 2 = TF32
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)v.a_mn_major << 15) | ((uint32_t)v.b_mn_major << 16) |
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(v.a_mn_major == 1) << 15) | ((uint32_t)v.b_mn_major << 16) |
                            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
     for (int ks = 0; ks < K / (2 * T); ++ks) {
       const uint64_t da = v.swap_lbo_sbo ? make_desc(a0 + ks * la.k_step_bytes, la.sbo, la.lbo)
@@ -204,14 +212,14 @@ int main() {
   int n_pass = 0;
   for (int bf = 0; bf < 2; ++bf)
   for (int swap = 0; swap < 2; ++swap)
-    for (int am = 0; am < 2; ++am)
+    for (int am = 0; am < 3; ++am)
       for (int bm = 0; bm < 2; ++bm) {
         Variant v{am, bm, swap, bf};
         cudaMemset(dD, 0xff, M * N * 4);
         umma_tf32_kernel<<<1, 128, smem>>>(dA, dB, dD, v);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
-          printf("%s A %s-major, B %s-major, %s: CUDA error %s\n", bf ? "kind::f16 (bf16)" : "kind::tf32", am ? "MN" : "K",
+          printf("%s A %s-major, B %s-major, %s: CUDA error %s\n", bf ? "kind::f16 (bf16)" : "kind::tf32", am == 1 ? "MN" : (am ? "K(row-block)" : "K"),
                  bm ? "MN" : "K", swap ? "LBO/SBO exchanged" : "LBO/SBO as read", cudaGetErrorString(e));
           return 2;  // a sticky error: nothing after it is meaningful
         }
@@ -224,8 +232,8 @@ int main() {
         const bool ok = max_err < 1e-4;
         n_pass += ok;
         printf("%-16s A %s-major, B %s-major, %-18s : %s (max abs err %.3e)\n", bf ? "kind::f16 (bf16)" : "kind::tf32",
-               am ? "MN" : "K ", bm ? "MN" : "K ", swap ? "LBO/SBO exchanged" : "LBO/SBO as read", ok ? "PASS" : "FAIL", max_err);
+               am == 1 ? "MN" : (am ? "Kb" : "K "), bm ? "MN" : "K ", swap ? "LBO/SBO exchanged" : "LBO/SBO as read", ok ? "PASS" : "FAIL", max_err);
       }
-  printf("%d of 16 variants pass\n", n_pass);
+  printf("%d of 24 variants pass  (Kb = K-major view of row-block-major core matrices)\n", n_pass);
   return 0;
 }

@@ -157,7 +157,7 @@ def test_tc5_selftest_gemm_all_majors(a_mn, b_mn, N, K):
     np.testing.assert_allclose(D, A.astype(np.float64) @ B.astype(np.float64).T, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1)])
 @pytest.mark.parametrize('N,K', [(64, 64), (16, 16), (128, 32)])
 def test_tc5_selftest_gemm_bf16x3_all_majors(a_mn, b_mn, N, K):
     """The 16-bit building blocks: bf16 hi / lo planes (8 elements per 16-byte chunk) in both majors, kind::f16 descriptors,

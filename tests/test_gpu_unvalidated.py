@@ -348,7 +348,7 @@ def test_tc5_selftest_gemm_all_majors(a_mn, b_mn):
     torch.testing.assert_close(D.cpu().double(), A.cpu().double() @ B.cpu().double().T, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1)])
 def test_tc5_selftest_gemm_bf16x3_all_majors(a_mn, b_mn):
     """The same on kind::f16 with bf16 hi / lo planes (bf16x3): the operand format planned for the tcgen05 training kernels."""
     g = torch.Generator().manual_seed(10 + a_mn * 2 + b_mn)

@@ -191,6 +191,20 @@ XDR_API int xdr_tc_mlp_step(int n_layers, const int* dims_host, const float* con
                             float* dAu, float* dBu, float* dAi, float* dBi, float* dT, float* prob, float* out8,
                             void* ws, int32_t* oob, xdr_stream_t stream);
 
+/* ---- A4 fused, tcgen05 engine (tc5_mlp.cu) -----------------------------------------------------------------------------------
+ * The EMCDR map step (in_mode 0, head 0, two layers [D, 128, D], D % 16 == 0, D <= 64) with all six products of a 128-row
+ * tile on tcgen05.mma kind::f16 (bf16x3: bf16 hi / lo operand planes, fp32 accumulation in tensor memory, ~2^-16 relative per
+ * product) and the weight-gradient accumulators resident in tensor memory over all tiles of a CTA.  Same arguments and
+ * results as xdr_fused_mlp_step; anything else is XDR_ERR_INVALID.  NOT yet run on hardware (see tc5.cuh).             */
+XDR_API int xdr_tc5_mlp_supported(int n_layers, const int* dims_host);
+XDR_API int xdr_tc5_mlp_step(int n_layers, const int* dims_host, const float* const* W_host, const float* const* b_host,
+                             float* const* dW_host, float* const* db_host, int hidden_act, int in_mode, int head,
+                             const float* Au, const float* Bu, const float* Ai, const float* Bi, const float* T,
+                             int64_t n_u, int64_t n_i, int dim, const int64_t* idx_u, const int64_t* idx_i,
+                             const float* label, int64_t batch, int backward, const float* grad_loss, float scale,
+                             float* dAu, float* dBu, float* dAi, float* dBi, float* dT, float* prob, float* out8,
+                             void* ws, int32_t* oob, xdr_stream_t stream);
+
 /* ---- A7-A8 fused: one CoNet tower pass (cross-stitch stack + BCE) with backward and scatter-add in ONE kernel --------------
  * Replaces CoNet.source_forward / target_forward + nn.BCELoss and their autograd backward for one domain batch
  * (conet.py:105-181, 196-197):  x_s = [Su[u] | Si[i]], x_t = [Tu[u] | Ti[i]];  per layer l

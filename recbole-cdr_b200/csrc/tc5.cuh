@@ -215,6 +215,7 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 }
 // warp w of a warpgroup reads TMEM lanes 32*(w%4)..+31 (taddr carries that lane base in its upper half): 16 columns
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  __syncwarp();  // .sync.aligned: callers' per-row branches must have reconverged
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -314,6 +315,8 @@ __device__ __forceinline__ void mma_bf16x3(uint32_t tmem_d, uint32_t a_hi, uint3
 // A and B staged K-major or MN-major.  Runs under the emulator and, on hardware, checks the descriptor reading through the
 // library itself (xdr_tc5_selftest).
 // fmt 0: 3xTF32 on fp32 hi / lo planes (K % 8 == 0);  fmt 1: bf16x3 on bf16 hi / lo planes (K % 16 == 0).
+// (a kernel definition: emitted only in the translation unit that defines XDR_TC5_SELFTEST_IMPL -- topk_score.cu)
+#ifdef XDR_TC5_SELFTEST_IMPL
 __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, int N, int K,
                                                           int a_mn, int b_mn, int fmt, float* __restrict__ D) {
   XDR_DYN_SMEM_ALIGNED(unsigned char, smem_t5, 128);
@@ -415,6 +418,7 @@ __global__ void __launch_bounds__(128, 1) selftest_kernel(const float* __restric
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, cols);
 }
+#endif  // XDR_TC5_SELFTEST_IMPL
 
 #endif  // __CUDACC__ || XDR_EMU
 

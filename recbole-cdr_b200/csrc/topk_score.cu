@@ -9,6 +9,7 @@
 // A second kernel merges the per-slice lists (one warp per user, one lane per slice).
 // Order: score descending, ties by ascending item id (torch.topk leaves tie order unspecified).
 // Algorithmic bytes: the item table once per 64-user block (n_items * 4D) + B * 4D + B * k * 12;  2 * B * n_items * D FLOP.
+#define XDR_TC5_SELFTEST_IMPL 1
 #include "tc5.cuh"
 #include "tc_tile.cuh"
 

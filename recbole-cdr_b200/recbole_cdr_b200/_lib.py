@@ -67,6 +67,10 @@ PROTOTYPES = {
     'xdr_tc_mlp_step': (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                 c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp,
                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'xdr_tc5_mlp_supported': (c_int, [c_int, c_vp]),
+    'xdr_tc5_mlp_step': (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                 c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp,
+                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'xdr_tc_conet_supported': (c_int, [c_int, c_vp, c_int]),
     'xdr_tc_conet_scratch_bytes': (c_sz, [c_i64, c_int]),
     'xdr_tc_conet_step': (c_int, [c_int, c_vp] + [c_vp] * 10 + [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp,

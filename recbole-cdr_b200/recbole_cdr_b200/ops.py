@@ -519,24 +519,27 @@ def train_steps(user_tab, item_tab, user, item_a, item_b=None, label=None, *, lo
 # ------------------------------------------------------------------------------------------------------------------
 # A4 / A14-A15 fused: gather -> small MLP -> loss head -> backward -> scatter in one kernel
 # ------------------------------------------------------------------------------------------------------------------
-FUSED_MLP_ENGINES = ('fma', 'tc')  # fp32 FMA row tiles (fused_mlp.cu) / 3xTF32 tensor-core row tiles (tc_mlp.cu)
+# fp32 FMA row tiles (fused_mlp.cu) / 3xTF32 mma.sync row tiles (tc_mlp.cu) / bf16x3 tcgen05 tiles with TMEM accumulators
+# (tc5_mlp.cu: the EMCDR map stack [D, 128, D] only)
+FUSED_MLP_ENGINES = ('fma', 'tc', 'tc5')
+_FUSED_MLP_ENTRY = {'fma': 'xdr_fused_mlp', 'tc': 'xdr_tc_mlp', 'tc5': 'xdr_tc5_mlp'}
 
 
 def fused_mlp_engine(flag) -> Optional[str]:
     """Engine named by the model config key ``xdr_fused_mlp``: False/None -> composed kernels, True/'fma' -> the fp32
-    row-tile kernel, 'tc' -> the tensor-core row-tile kernel."""
+    row-tile kernel, 'tc' -> the mma.sync tensor-core row-tile kernel, 'tc5' -> the tcgen05 kernel (EMCDR map stack only)."""
     if flag in (None, False, 0, '', 'false', 'False'):
         return None
     if flag in (True, 1, 'fma', 'true', 'True'):
         return 'fma'
-    if flag == 'tc':
-        return 'tc'
-    raise ValueError(f"xdr_fused_mlp must be False, True, 'fma' or 'tc', got {flag!r}")
+    if flag in ('tc', 'tc5'):
+        return flag
+    raise ValueError(f"xdr_fused_mlp must be False, True, 'fma', 'tc' or 'tc5', got {flag!r}")
 
 
 def fused_mlp_supported(dims, engine: str = 'fma') -> bool:
     arr = (_ct.c_int * len(dims))(*[int(d) for d in dims])
-    fn = _lib._lib.xdr_tc_mlp_supported if engine == 'tc' else _lib._lib.xdr_fused_mlp_supported
+    fn = getattr(_lib._lib, _FUSED_MLP_ENTRY[engine] + '_supported')
     return bool(fn(len(dims) - 1, _ct.cast(arr, _ct.c_void_p)))
 
 
@@ -556,7 +559,7 @@ def _fused_mlp_call(in_mode, head, hidden_act, tabs, idx_u, idx_i, label, Ws, bs
     dAu, dBu, dAi, dBi, dT = dsts
     if engine not in FUSED_MLP_ENGINES:
         raise ValueError(f'unknown fused-MLP engine {engine!r}')
-    call('xdr_tc_mlp_step' if engine == 'tc' else 'xdr_fused_mlp_step', len(Ws), _ct.cast(arr, _ct.c_void_p), _ptr_array(Ws), _ptr_array(bs),
+    call(_FUSED_MLP_ENTRY[engine] + '_step', len(Ws), _ct.cast(arr, _ct.c_void_p), _ptr_array(Ws), _ptr_array(bs),
          _ptr_array(dWs) if dWs else None, _ptr_array(dbs) if dbs else None, int(hidden_act), int(in_mode), int(head),
          ptr(Au), ptr(Bu), ptr(Ai), ptr(Bi), ptr(T), Au.shape[0], Ai.shape[0] if Ai is not None else 0, Au.shape[1],
          ptr(idx_u), ptr(idx_i), ptr(label), B, 1 if backward else 0, ptr(grad_loss), 1.0, ptr(dAu), ptr(dBu), ptr(dAi),

@@ -47,6 +47,12 @@ if [ "$STAGE" = validate ] || [ "$STAGE" = all ]; then
   XDR_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_unvalidated.py -q -x -k "full_sort_topk and tc5 and 300" --timeout 60 \
       > gpurun_out/tc5_topk.log 2>&1
   say "tc5 top-k (smallest case) rc=$?"
+  # the tcgen05 map-step kernel (tc5_mlp.cu) on the same library: smallest case first, then the rest
+  XDR_RUN_UNVALIDATED=1 timeout 180 python -m pytest tests/test_gpu_unvalidated.py -q -x -k "tc5_mlp or tc5_engine" --timeout 60 \
+      > gpurun_out/tc5_mlp.log 2>&1
+  say "tc5 map-step kernel rc=$?"
+  XDR_SECTIONS=emcdr_map_step XDR_BENCH_TC5=1 timeout 300 python scripts/bench_new_kernels.py > gpurun_out/tc5_mlp_bench.log 2>&1
+  say "tc5 map-step bench rc=$?"
   unset XDR_LIB
   # the tcgen05 descriptor experiment is tiny: run it in the first call so that the answer is there early
   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o /tmp/ubench_tcgen05 scripts/ubench_tcgen05.cu > gpurun_out/tcgen05.log 2>&1 \

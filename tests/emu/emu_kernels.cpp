@@ -53,11 +53,13 @@ void emu_config(int sms, uint64_t schedule_seed) {
 }
 const char* emu_last_error() { return g_err; }
 // several persistent launches ("GPUs") resident together: queue them between begin and run
-// work counters since the last reset: [mma.sync tf32, mma.sync bf16, tcgen05.mma, row-load bytes, row-RED bytes, CTA barriers]
+// work counters since the last reset: [mma.sync tf32, mma.sync bf16, tcgen05.mma tf32, row-load bytes, row-RED bytes, CTA barriers,
+// tcgen05.mma f16]
 void emu_counters(uint64_t* out6, int reset) {
   emu::Counters& c = emu::counters();
   out6[0] = c.mma_tf32; out6[1] = c.mma_bf16; out6[2] = c.umma_tf32; out6[3] = c.row_load_bytes; out6[4] = c.row_red_bytes;
   out6[5] = c.cta_barriers;
+  out6[6] = c.umma_bf16;
   if (reset) c = emu::Counters();
 }
 void emu_group_begin() { emu::group_begin(); }

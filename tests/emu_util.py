@@ -25,7 +25,7 @@ def _lib_path(mode):
 # translation units of the emulator library: the harness (which #includes the fused row-tile kernels it drives directly)
 # plus the kernel files that only need their real entry points
 SEPARATE_TUS = ['pair_score.cu', 'gather_scatter.cu', 'dense.cu', 'graph_prop.cu', 'neg_sample.cu', 'topk_score.cu',
-                'steps_persistent.cu']
+                'steps_persistent.cu', 'tc5_mlp.cu']
 
 
 def _deps():
@@ -92,9 +92,9 @@ class tc_mode:
 
 def counters(reset=True):
     """Work counters of the emulated launches since the last reset (see cuda_emu.h ``Counters``)."""
-    out = (ctypes.c_uint64 * 6)()
+    out = (ctypes.c_uint64 * 7)()
     lib().emu_counters(out, ctypes.c_int(1 if reset else 0))
-    return dict(zip(('mma_tf32', 'mma_bf16', 'umma_tf32', 'row_load_bytes', 'row_red_bytes', 'cta_barriers'), [int(v) for v in out]))
+    return dict(zip(('mma_tf32', 'mma_bf16', 'umma_tf32', 'row_load_bytes', 'row_red_bytes', 'cta_barriers', 'umma_bf16'), [int(v) for v in out]))
 
 
 def config(sms=4, seed=0):

@@ -20,8 +20,8 @@ QUERIES = {'xdr_version', 'xdr_workspace_bytes', 'xdr_steps_workspace_bytes', 'x
            'xdr_tc_mlp_supported', 'xdr_tc_conet_supported'}
 out = {}
 for name, (res, argt) in sorted(_lib.PROTOTYPES.items()):
-    if name in QUERIES or res is not _lib.c_int:
-        continue
+    if name in QUERIES or name.endswith('_supported') or name.endswith('_bytes') or res is not _lib.c_int:
+        continue     # queries answer with a value, not a status
     for v in (0, 1, 2, 4, 8, 64, -1, 2 ** 31 - 1):
         args = []
         for t in argt:
@@ -55,7 +55,7 @@ def test_every_compute_entry_was_exercised(results):
     names = {k.split('/')[0] for k in results}
     assert len(names) >= 30, sorted(names)
     for must in ('xdr_train_steps', 'xdr_bpr_fwd', 'xdr_gather_rows', 'xdr_scatter_add_rows', 'xdr_spmm_csr', 'xdr_dense_fwd',
-                 'xdr_fused_mlp_step', 'xdr_tc_mlp_step', 'xdr_tc_conet_step', 'xdr_sparse_optim_rows', 'xdr_full_sort_topk',
+                 'xdr_fused_mlp_step', 'xdr_tc_mlp_step', 'xdr_tc5_mlp_step', 'xdr_tc_conet_step', 'xdr_sparse_optim_rows', 'xdr_full_sort_topk',
                  'xdr_neg_sample_uniform', 'xdr_train_steps_sharded'):
         assert must in names
 

@@ -38,6 +38,40 @@ def test_tc_mlp_map_loss_matches_oracle(batch):
         torch.testing.assert_close(got.grad.cpu(), want.grad * 1.3, rtol=2e-4, atol=atol, msg=lambda s: f'{nm}: {s}')
 
 
+# ---------------------------------------------------------------------------------- tcgen05 fused map step (tc5_mlp.cu)
+@pytest.mark.parametrize('batch', [1, 127, 128, 129, 1000, 8192, 40000])
+def test_tc5_mlp_map_loss_matches_oracle(batch):
+    """EMCDR map step with all six products of a 128-row tile on tcgen05.mma (bf16x3, TMEM-resident weight gradients);
+    40000 rows give every CTA more than one tile (accumulation in tensor memory over tiles)."""
+    g = torch.Generator().manual_seed(211)
+    src, tgt = rand_table(3000, 64, 212, 0.3), rand_table(3000, 64, 213, 0.3)
+    ws = [torch.randn(128, 64, generator=g) * 0.2, torch.randn(64, 128, generator=g) * 0.2]
+    bs = [torch.randn(128, generator=g) * 0.1, torch.randn(64, generator=g) * 0.1]
+    idx = rand_ids(batch, 3000, 214, 1.3)
+    leaves = [t.clone().requires_grad_(True) for t in [src, tgt] + ws + bs]
+    ref = O.emcdr_map_loss(leaves[0], leaves[1], idx.view(-1, 1), leaves[2:4], leaves[4:6])
+    ref.backward()
+    c = [t.to(dev()).requires_grad_(True) for t in [src, tgt] + ws + bs]
+    assert ops().fused_mlp_supported([64, 128, 64], 'tc5') and not ops().fused_mlp_supported([128, 32, 16, 1], 'tc5')
+    loss = ops().fused_mlp_loss(0, 0, lib().ACT_TANH, idx.to(dev()), None, None, (c[0], None, None, None, c[1]), c[2:4], c[4:6],
+                                'tc5')
+    torch.testing.assert_close(loss.cpu(), ref.detach(), rtol=LOSS_RTOL, atol=0)
+    (loss * 1.3).backward()
+    for got, want, nm in zip(c, leaves, ('src', 'tgt', 'W1', 'W2', 'b1', 'b2')):
+        atol = max(1e-7, 1e-4 * want.grad.abs().max().item())
+        torch.testing.assert_close(got.grad.cpu(), want.grad * 1.3, rtol=2e-4, atol=atol, msg=lambda s: f'{nm}: {s}')
+
+
+@pytest.mark.parametrize('case', ['non_linear', 'items'])
+def test_emcdr_map_phase_tc5_engine(case):
+    from recbole_cdr_b200.model.cross_domain_recommender.emcdr import EMCDR
+    g = Golden(f'emcdr_map_{case}')
+    m = build(EMCDR, g, dict(EMCDR_CFG, latent_factor_model='BPR', mapping_function='non_linear', xdr_fused_mlp='tc5'))
+    assert m.fused_mlp_engine == 'tc5'
+    m.set_phase('OVERLAP')
+    check_loss_and_grads(m, g, cuda_batch(g), grad_rtol=2e-4, grad_atol=2e-6)
+
+
 def test_tc_mlp_supported_stacks():
     assert ops().fused_mlp_supported([64, 128, 64], 'tc') and ops().fused_mlp_supported([128, 32, 16, 1], 'tc')
     assert not ops().fused_mlp_supported([512, 64, 1], 'tc')

@@ -21,7 +21,7 @@ ROWS = []
 
 def add(name, rows, c):
     mma = c['mma_tf32'] + c['mma_bf16']
-    ROWS.append(f"| {name} | {rows} | {mma / rows:.1f} | {c['umma_tf32'] / rows:.2f} | {c['row_load_bytes'] / rows:.0f} | "
+    ROWS.append(f"| {name} | {rows} | {mma / rows:.1f} | {(c['umma_tf32'] + c['umma_bf16']) / rows:.2f} | {c['row_load_bytes'] / rows:.0f} | "
                 f"{c['row_red_bytes'] / rows:.0f} | {c['cta_barriers']} |")
 
 
@@ -66,6 +66,13 @@ def topk(engine, B=256, n_items=2049, D=64, k=20):
     return emu_util.counters()
 
 
+def map_tc5(batch=256):
+    import test_emu_tc5_mlp as T5
+    emu_util.counters()
+    T5.run(64, batch, 500, seed=1, sms=2)
+    return emu_util.counters()
+
+
 names = {0: '3xTF32 (m16n8k8)', 1: 'bf16x3 (m16n8k16)', 2: '1xTF32 (diagnostic)'}
 for mode in (0, 1, 2):
     for ov in ('all', 'half', 'none'):
@@ -73,6 +80,7 @@ for mode in (0, 1, 2):
 for mode in (0, 1):
     add(f'EMCDR map step fwd+bwd, 64-128-64, {names[mode]}', 256, mlp(mode, 'map'))
     add(f'DTCDR NeuMF term fwd+bwd, 128-32-16-1, {names[mode]}', 256, mlp(mode, 'dtcdr'))
+add('EMCDR map step fwd+bwd, 64-128-64, tcgen05 kind::f16 bf16x3 (tc5_mlp.cu, 128-row tiles)', 256, map_tc5())
 for eng in ('mma', 'tc5'):
     c = topk(eng)
     add(f'full-sort top-20, 256 users x 2048 items, D = 64, engine {eng} (per user)', 256, c)

@@ -149,26 +149,46 @@ class CoNet(CrossDomainRecommender):
             out = self.target_outputunit[0]
             return ops.dense(x, out.weight, out.bias, _lib.ACT_SIGMOID)
 
+    def _full_sort_blocks(self, interaction):
+        """Yields ``(first user position, scores [block, n_items])`` of the target tower over every (user, target item) pair
+        (conet.py:222-242).  The reference runs one Python iteration per user over ``[E_u || E_i]`` rows.  Layer 0 is linear in
+        the concatenation, ``W0 [E_u || E_i] + b0 = (W0[:, :D] E_u + b0) + W0[:, D:] E_i``, so the item half is computed ONCE
+        for all items and the user half once per user; a pair then costs one add + ReLU and the narrow tail layers (7x fewer
+        multiply-adds at CoNet.yaml's stack).  Users are processed in blocks bounded by the hidden rows' footprint; no host
+        sync."""
+        user = interaction[self.TARGET_USER_ID].reshape(-1)
+        n_items, D = self.target_num_items, self.latent_dim
+        fc0 = self.target_crossunit_linear[0]
+        item_part = ops.dense(self.target_item_embedding.weight[:n_items], fc0.weight[:, D:].contiguous())
+        user_part = ops.dense(ops.gather_rows_raw(self.target_user_embedding.weight, user),
+                              fc0.weight[:, :D].contiguous(), fc0.bias)
+        width = item_part.shape[1]
+        block = max(1, self.full_sort_block_bytes // (4 * width * n_items))   # users per block of layer-0 outputs
+        out_fc = self.target_outputunit[0]
+        for s in range(0, user.numel(), block):
+            h = torch.relu(user_part[s:s + block].unsqueeze(1) + item_part.unsqueeze(0)).reshape(-1, width)
+            for fc in list(self.target_crossunit_linear)[1:]:
+                h = ops.dense(h, fc.weight, fc.bias, _lib.ACT_RELU)
+            yield s, ops.dense(h, out_fc.weight, out_fc.bias, _lib.ACT_SIGMOID).reshape(-1, n_items)
+
     def full_sort_predict(self, interaction):
-        """conet.py:222-242: every (user, target item) pair through the target tower -> [B, n_items].
-        The reference runs one Python iteration per user over ``[E_u || E_i]`` rows.  Layer 0 is linear in the concatenation,
-        ``W0 [E_u || E_i] + b0 = (W0[:, :D] E_u + b0) + W0[:, D:] E_i``, so the item half is computed ONCE for all items and the
-        user half once per user; a pair then costs one add + ReLU and the narrow tail layers (7x fewer multiply-adds at
-        CoNet.yaml's stack).  Users are processed in blocks bounded by the hidden rows' footprint; no host sync."""
+        """conet.py:222-242: the dense [B, n_items] score matrix of the target tower (see ``_full_sort_blocks``)."""
         with torch.no_grad():
-            user = interaction[self.TARGET_USER_ID].reshape(-1)
-            n_items, D = self.target_num_items, self.latent_dim
-            fc0 = self.target_crossunit_linear[0]
-            item_part = ops.dense(self.target_item_embedding.weight[:n_items], fc0.weight[:, D:].contiguous())
-            user_part = ops.dense(ops.gather_rows_raw(self.target_user_embedding.weight, user),
-                                  fc0.weight[:, :D].contiguous(), fc0.bias)
-            width = item_part.shape[1]
-            block = max(1, self.full_sort_block_bytes // (4 * width * n_items))   # users per block of layer-0 outputs
-            out_fc = self.target_outputunit[0]
-            rows = []
-            for s in range(0, user.numel(), block):
-                h = torch.relu(user_part[s:s + block].unsqueeze(1) + item_part.unsqueeze(0)).reshape(-1, width)
-                for fc in list(self.target_crossunit_linear)[1:]:
-                    h = ops.dense(h, fc.weight, fc.bias, _lib.ACT_RELU)
-                rows.append(ops.dense(h, out_fc.weight, out_fc.bias, _lib.ACT_SIGMOID).reshape(-1, n_items))
-            return torch.cat(rows, dim=0)
+            return torch.cat([sc for _, sc in self._full_sort_blocks(interaction)], dim=0)
+
+    def full_sort_topk(self, interaction, k, hist_ptr=None, hist_ids=None):
+        """``full_sort_predict`` + recbole's full-sort masking (PAD column, per-user history CSR) + ``topk`` per user block: the
+        [B, n_items] matrix is never held, only one block of it.  Returns (scores [B, k], item positions [B, k])."""
+        with torch.no_grad():
+            scores, ids = [], []
+            for s, sc in self._full_sort_blocks(interaction):
+                sc[:, 0] = -float('inf')
+                if hist_ptr is not None:
+                    lo, hi = hist_ptr[s], hist_ptr[s + sc.shape[0]]
+                    counts = hist_ptr[s + 1:s + sc.shape[0] + 1] - hist_ptr[s:s + sc.shape[0]]
+                    rows = torch.repeat_interleave(torch.arange(sc.shape[0], device=sc.device), counts)
+                    sc[rows, hist_ids[lo:hi]] = -float('inf')
+                top = torch.topk(sc, k, dim=1)
+                scores.append(top.values)
+                ids.append(top.indices)
+            return torch.cat(scores, dim=0), torch.cat(ids, dim=0)

@@ -26,8 +26,11 @@ def test_variant_fused_topk_matches_the_reference_scores(name):
     with emu_util.patched_ops():
         m = V.build(g, 'cpu')
         if not hasattr(m, 'full_sort_topk'):
-            pytest.skip('model scores with an MLP / propagated tables: no fused top-k entry')
+            pytest.skip('model scores with propagated tables: no top-k entry')
         V.check_topk_against_reference(m, g, 'cpu')
+        if hasattr(m, 'full_sort_block_bytes'):     # CoNet: user blocks + mask + topk; also with two users per block
+            m.full_sort_block_bytes = 4 * 64 * g.t('full_sort_predict').shape[1] * 2
+            V.check_topk_against_reference(m, g, 'cpu')
 
 
 @pytest.mark.parametrize('engine', ['fma', 'tc'])

@@ -15,3 +15,13 @@ def test_variant_matches_the_reference(name):
     g = Golden(name)
     m = V.build(g, 'cuda')
     V.check_against_reference(m, g, 'cuda')
+
+
+def test_conet_block_topk_matches_the_reference_scores():
+    """CoNet.full_sort_topk (user blocks of the split-layer-0 tower + mask + topk; composed, hardware-validated kernels)
+    against torch.topk of the reference's masked full_sort_predict scores."""
+    g = Golden('v_conet_yaml_stack')
+    m = V.build(g, 'cuda')
+    V.check_topk_against_reference(m, g, 'cuda')
+    m.full_sort_block_bytes = 4 * 64 * g.t('full_sort_predict').shape[1] * 2     # two users per block
+    V.check_topk_against_reference(m, g, 'cuda')

@@ -120,6 +120,16 @@ class BiTGCF(CrossDomainRecommender):
             u = ops.gather_rows_raw(restore_user_e.contiguous(), user)
             return torch.matmul(u, restore_item_e[:self.target_num_items].transpose(0, 1)).view(-1)
 
+    def full_sort_topk(self, interaction, k, hist_ptr=None, hist_ids=None, engine='mma'):
+        """Fused ``full_sort_predict`` + PAD/history masking + ``topk`` on the propagated tables: one
+        scoring kernel that never writes the [B, n_items] matrix.  Row width is D (mean) or D * (n_layers + 1) (concat);
+        the fused kernel takes widths up to 256."""
+        with torch.no_grad():
+            restore_user_e, restore_item_e = self.get_restore_e()
+            u = ops.gather_rows_raw(restore_user_e.contiguous(), interaction[self.TARGET_USER_ID])
+            return ops.full_sort_topk(u, restore_item_e.contiguous(), k, n_items=self.target_num_items, first_item=1,
+                                      hist_ptr=hist_ptr, hist_ids=hist_ids, engine=engine)
+
     def init_restore_e(self):
         if self.target_restore_user_e is not None or self.target_restore_item_e is not None:
             self.target_restore_user_e, self.target_restore_item_e = None, None

@@ -416,7 +416,7 @@ def test_variant_fused_conet(name):
 
 
 @pytest.mark.parametrize('name', [n for n in _V.VARIANTS
-                                  if Golden(n).has('full_sort_predict') and _V.spec(Golden(n))['model'] in ('EMCDR', 'CMF')])
+                                  if Golden(n).has('full_sort_predict') and _V.spec(Golden(n))['model'] in ('EMCDR', 'CMF', 'BiTGCF')])
 def test_variant_fused_topk_matches_the_reference_scores(name):
     g = Golden(name)
     _V.check_topk_against_reference(_V.build(g, 'cuda'), g, 'cuda')

@@ -210,6 +210,7 @@ int main() {
   const int smem = (M + N) * K * 4;
   cudaFuncSetAttribute(umma_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int n_pass = 0;
+  bool pass[2][2][3][2] = {};   // [dtype][field assignment][A layout][B layout]
   for (int bf = 0; bf < 2; ++bf)
   for (int swap = 0; swap < 2; ++swap)
     for (int am = 0; am < 3; ++am)
@@ -231,9 +232,23 @@ int main() {
         }
         const bool ok = max_err < 1e-4;
         n_pass += ok;
+        pass[bf][swap][am][bm] = ok;
         printf("%-16s A %s-major, B %s-major, %-18s : %s (max abs err %.3e)\n", bf ? "kind::f16 (bf16)" : "kind::tf32",
                am == 1 ? "MN" : (am ? "Kb" : "K "), bm ? "MN" : "K ", swap ? "LBO/SBO exchanged" : "LBO/SBO as read", ok ? "PASS" : "FAIL", max_err);
       }
   printf("%d of 24 variants pass  (Kb = K-major view of row-block-major core matrices)\n", n_pass);
+  // what the library needs to know (tc5.cuh): -DXDR_TC5_SWAP = bit 0 (K-major operands) | bit 1 (MN-major operands)
+  for (int bf = 0; bf < 2; ++bf) {
+    const int k_as_read = pass[bf][0][0][0], k_swapped = pass[bf][1][0][0];
+    const int mn_as_read = pass[bf][0][1][1], mn_swapped = pass[bf][1][1][1];
+    const char* name = bf ? "kind::f16 (bf16)" : "kind::tf32";
+    if ((k_as_read || k_swapped) && (mn_as_read || mn_swapped))
+      printf("%s: build with -DXDR_TC5_SWAP=%d%s; one tile, two views (Kb): %s\n", name,
+             (k_as_read ? 0 : 1) | (mn_as_read ? 0 : 2), (k_as_read && k_swapped) || (mn_as_read && mn_swapped) ? " (either works for one major)" : "",
+             (pass[bf][k_as_read ? 0 : 1][2][0] && pass[bf][k_as_read ? 0 : 1][2][1]) ? "works" : "does NOT work");
+    else
+      printf("%s: no assignment of the two stride fields reproduces the product for %s%s operands -- the layout reading itself is wrong\n",
+             name, (k_as_read || k_swapped) ? "" : "K-major ", (mn_as_read || mn_swapped) ? "" : "MN-major ");
+  }
   return 0;
 }

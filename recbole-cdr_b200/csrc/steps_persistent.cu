@@ -484,7 +484,11 @@ __device__ __forceinline__ void init_bars(const Bars& B, int tasks, int ifree_co
 // =====================================================================================================================
 // STAGED kernel: loaders (gather -> score -> stash) and scatterers (norms -> gradients -> RED) are different warps
 // =====================================================================================================================
-template <int LPR, int VEC, bool PAIRWISE, int kLoaderWarps>
+// EARLY (opt-in, reg_weight == 0 only; not yet run on hardware): without the EmbLoss term the row gradients do not depend on
+// the batch-wide norms, so the scatterers do not wait for the step's norm exchange before they issue the REDs and free the
+// stage slot; they still wait for it before they free the id slot, which keeps the id / partial / norm rings in step (the
+// per-step loss is still the exchanged batch mean).
+template <int LPR, int VEC, bool PAIRWISE, int kLoaderWarps, bool EARLY = false>
 // launch bound 768 (> the threads actually launched) caps ptxas at 80 registers/thread, so that in the lite configuration
 // (576 threads) a 256-thread peer-gather CTA still fits in the SM's register file next to this CTA
 __global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a, int n_stages) {
@@ -574,11 +578,11 @@ __global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a,
     for (int s = 0; s < a.n_steps; ++s) {
       const int slot = s % kRing, st = s % n_stages;
       const uint32_t par = (uint32_t)((s / kRing) & 1);
-      mbar_wait(&B.normf[slot], par);  // => every CTA (this one included) has scored and stashed the step
+      if (!EARLY) mbar_wait(&B.normf[slot], par);  // => every CTA (this one included) has scored and stashed the step
       mbar_wait(&B.idsf[slot], par);   // (long complete) acquire: the TMA-written ids are visible to this warp
       mbar_wait(&B.adone[slot], par);  // (long complete) acquire: the loaders' stage writes are visible to this warp
       if (a.trace && lane == 0 && x == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 5] = gtime();
-      const float2 nf = norms[slot];
+      const float2 nf = EARLY ? make_float2(0.f, 0.f) : norms[slot];
       const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
       const float* lab = reinterpret_cast<const float*>(ids + (size_t)R * L.slice);
       const float* rows = reinterpret_cast<const float*>(stage_ring + (size_t)st * L.stage_slot_bytes());
@@ -604,7 +608,11 @@ __global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a,
       }
       __syncwarp();
       if (a.trace && lane == 0 && x == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 6] = gtime();
-      if (lane == 0) {
+      if (EARLY) {
+        if (lane == 0) mbar_arrive(&B.sfree[st]);
+        mbar_wait(&B.normf[slot], par);  // the step's exchange is over: its id, partial and norm slots may be reused
+        if (lane == 0) mbar_arrive(&B.ifree[slot]);
+      } else if (lane == 0) {
         mbar_arrive(&B.sfree[st]);    // the stage slot may be overwritten by the loaders
         mbar_arrive(&B.ifree[slot]);  // the id slot may be refilled by the producer
       }
@@ -753,12 +761,18 @@ static bool plan_steps(int64_t batch, int nv, bool pairwise, StepsPlan* plan) {
   return true;
 }
 
+static int g_early_scatter = 0;  // opt-in (xdr_steps_set_early_scatter): reg_weight == 0 launches take the EARLY staged kernel
+
 template <int LPR, int VEC, bool PW>
 static int launch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_t s) {
   if (plan.stages > 0 && a.stage_a != nullptr) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsLite>;
     XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsLite), plan.smem, s, a, plan.stages);
+  } else if (plan.stages > 0 && g_early_scatter && a.reg_weight == 0.f) {
+    auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull, true>;
+    XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s, a, plan.stages);
   } else if (plan.stages > 0) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull>;
     XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
@@ -794,6 +808,9 @@ extern "C" {
 // the scatter side, [6] scatter issued.
 XDR_API void xdr_debug_set_steps_trace(void* buf) { g_trace = reinterpret_cast<unsigned long long*>(buf); }
 XDR_API void xdr_debug_force_register_kernel(int on) { g_force_regs = on; }
+// Opt-in until it has run on hardware: launches with reg_weight == 0 (CMF's yaml default lambda = gamma = 0, reg-free BPR)
+// scatter without waiting for the step's norm exchange (train_steps_staged_kernel<..., EARLY = true>).
+XDR_API void xdr_steps_set_early_scatter(int on) { g_early_scatter = on; }
 
 size_t xdr_steps_workspace_bytes(int n_steps) {
   if (n_steps < 0) return 0;

@@ -454,6 +454,13 @@ def _steps_workspace(device, n_steps):
     return ws
 
 
+def set_steps_early_scatter(on: bool):
+    """Opt in to the early-scatter form of the persistent kernel for launches with ``reg_weight == 0`` (CMF's yaml default
+    lambda = gamma = 0, reg-free BPR): the row gradients do not depend on the batch-wide EmbLoss norms then, so the scatter
+    warps do not wait for the step's norm exchange.  Results are the same; not yet run on hardware, hence opt-in."""
+    _lib._lib.xdr_steps_set_early_scatter(1 if on else 0)
+
+
 def train_steps_supported(batch: int, dim: int, pairwise: bool, device=None) -> bool:
     """True when (batch, dim) is a shape the persistent kernels take (mirror of plan_steps in steps_persistent.cu)."""
     if batch <= 0 or batch % 4 != 0 or dim % 4 != 0 or dim > 256:

@@ -216,7 +216,38 @@ def full_sort_topk():
                bytes_=B * n_items * 4 * 3, flops=fl, units=B, unit_name='users')
 
 
-ALL = (emcdr_map_step, dtcdr_both_step, conet_both_step, sparse_optimizers, full_sort_topk)
+def early_scatter_steps():
+    """reg_weight == 0 launches of the persistent kernel with and without the early-scatter form (steps_persistent.cu EARLY):
+    (a) the headline shape (1M x 1M rows, dim 64, B = 8192 BPR triples, K = 200 steps), (b) CMF at BASELINE configs[0]'s sizes
+    (6982 users x 3351 items, B = 2048 pointwise rows, lambda = gamma = 0 as in CMF.yaml)."""
+    cases = [('EMCDR BPR reg_weight 0, 1M x 1M, B = 8192', 1_000_001 if not SMALL else 10_001, 1_000_001 if not SMALL else 10_001, 8192, True, 1560),
+             ('CMF term lambda 0, 6982 x 3351 (bundled sizes), B = 2048', 6982, 3351, 2048, False, 1044)]
+    K = 200
+    for name, nu, ni, B, pairwise, bytes_per in cases:
+        ut, it = torch.randn(nu, 64, device=dev) * 0.1, torch.randn(ni, 64, device=dev) * 0.1
+        gu, gi = torch.zeros_like(ut), torch.zeros_like(it)
+        u = torch.randint(1, nu, (K, B), device=dev, generator=g)
+        ia, ib = torch.randint(1, ni, (K, B), device=dev, generator=g), torch.randint(1, ni, (K, B), device=dev, generator=g)
+        y = (torch.rand(K, B, device=dev, generator=g) < 0.5).float()
+        losses = {}
+        for early in (False, True):
+            ops.set_steps_early_scatter(early)
+            try:
+                def step():
+                    if pairwise:
+                        return ops.train_steps(ut, it, u, ia, ib, reg_weight=0.0, user_dst=gu, item_dst=gi)[0]
+                    return ops.train_steps(ut, it, u, ia, None, y, loss_kind=_lib.LOSS_BCE_SIGMOID, reg_weight=0.0, user_dst=gu,
+                                           item_dst=gi)[0]
+                losses[early] = step()[:, 0].clone()
+                t = timeit(step)
+            finally:
+                ops.set_steps_early_scatter(False)
+            report(f'A3/A16 {name}, K = {K} steps per launch, {"early scatter (NEW)" if early else "default kernel"} (per step)',
+                   t / K, bytes_=B * bytes_per, units=B)
+        assert SKIP_CHECK or torch.equal(losses[False], losses[True]), 'early scatter changed the per-step losses'
+
+
+ALL = (emcdr_map_step, dtcdr_both_step, conet_both_step, sparse_optimizers, full_sort_topk, early_scatter_steps)
 WANT = os.environ.get('XDR_SECTIONS')                      # comma-separated subset of the section names
 for sec in ALL:
     if WANT is None or sec.__name__ in WANT.split(','):

@@ -275,3 +275,61 @@ def test_row_sharded_ranks_running_concurrently():
         gi_ref += di
     torch.testing.assert_close(full(gu, nu), gu_ref, rtol=1e-4, atol=1e-4 * gu_ref.abs().max().item())
     torch.testing.assert_close(full(gi, ni), gi_ref, rtol=1e-4, atol=1e-4 * gi_ref.abs().max().item())
+
+
+@pytest.mark.parametrize('K,B,dim,sms,pairwise', [(12, 96, 64, 3, True), (20, 64, 32, 2, True), (11, 64, 64, 2, False)])
+def test_early_scatter_variant_for_reg_weight_zero(K, B, dim, sms, pairwise):
+    """train_steps_staged_kernel<..., EARLY>: with reg_weight == 0 the scatterers do not wait for the norm exchange (opt-in
+    through xdr_steps_set_early_scatter).  K > the 8-deep id / partial / norm rings, so the slot-release order is exercised.
+    Per-step losses and accumulated gradients equal the oracle (and the flag changes nothing when reg_weight != 0)."""
+    from recbole_cdr_b200 import _lib
+    nu, ni = 300, 400
+    ut, it, u, ip, ineg, y = setup(nu, ni, dim, K, B, 9, 0.3)
+    L = emu_util.lib()
+    results = {}
+    for early in (0, 1):
+        for seed in ((0,) if not early else (0, 23)):
+            with emu_util.patched_ops(sms=sms, seed=seed) as ops:
+                L.xdr_steps_set_early_scatter(early)
+                try:
+                    if pairwise:
+                        out8, gu, gi = ops.train_steps(ut.clone(), it.clone(), u, ip, ineg, reg_weight=0.0)
+                    else:
+                        out8, gu, gi = ops.train_steps(ut.clone(), it.clone(), u, ip, None, y, loss_kind=_lib.LOSS_BCE_SIGMOID,
+                                                       reg_weight=0.0)
+                finally:
+                    L.xdr_steps_set_early_scatter(0)
+            results[(early, seed)] = (out8[:, 0].clone(), gu, gi)
+    a, b = ut.clone().requires_grad_(True), it.clone().requires_grad_(True)
+    gu_ref, gi_ref = torch.zeros_like(ut), torch.zeros_like(it)
+    losses = []
+    for k in range(K):
+        if pairwise:
+            ref = O.emcdr_bpr_loss(a, b, u[k], ip[k], ineg[k], 0.0)
+        else:
+            ref = O.bce_loss(torch.sigmoid(O.dot_score(a, b, u[k], ip[k])), y[k])
+        losses.append(ref.detach().reshape(-1)[0])
+        du, di = O.grads_of(ref, [a, b])
+        gu_ref += du
+        gi_ref += di
+    for key, (loss, gu, gi) in results.items():
+        torch.testing.assert_close(loss, torch.stack(losses), rtol=1e-4, atol=0, msg=lambda s: f'{key}: {s}')
+        torch.testing.assert_close(gu, gu_ref, rtol=1e-4, atol=1e-4 * gu_ref.abs().max().item())
+        torch.testing.assert_close(gi, gi_ref, rtol=1e-4, atol=1e-4 * gi_ref.abs().max().item())
+    assert torch.equal(results[(0, 0)][0], results[(1, 0)][0])      # the loss path is untouched: same bits
+
+
+def test_early_scatter_flag_is_ignored_when_the_norms_matter():
+    K, B, dim = 5, 64, 64
+    ut, it, u, ip, ineg, _ = setup(200, 250, dim, K, B, 4)
+    L = emu_util.lib()
+    outs = []
+    for early in (0, 1):
+        with emu_util.patched_ops(sms=2) as ops:
+            L.xdr_steps_set_early_scatter(early)
+            try:
+                outs.append(ops.train_steps(ut.clone(), it.clone(), u, ip, ineg, reg_weight=0.05))
+            finally:
+                L.xdr_steps_set_early_scatter(0)
+    for x, y in zip(outs[0], outs[1]):
+        torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-8)

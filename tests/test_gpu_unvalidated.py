@@ -38,6 +38,33 @@ def test_tc_mlp_map_loss_matches_oracle(batch):
         torch.testing.assert_close(got.grad.cpu(), want.grad * 1.3, rtol=2e-4, atol=atol, msg=lambda s: f'{nm}: {s}')
 
 
+# ------------------------------------------------------------------- early-scatter form of the persistent kernel (reg_weight 0)
+@pytest.mark.parametrize('pairwise', [True, False])
+def test_train_steps_early_scatter_matches_the_default_kernel(pairwise):
+    """reg_weight == 0: the scatterers of train_steps_staged_kernel<..., EARLY> do not wait for the norm exchange.  Same losses
+    (bit for bit: the loss path is untouched) and the same gradient tables as the hardware-validated default kernel."""
+    K, B, dim, nu, ni = 40, 8192, 64, 200_000, 300_000
+    g = torch.Generator().manual_seed(5)
+    ut, it = (torch.randn(nu, dim, generator=g) * 0.1).to(dev()), (torch.randn(ni, dim, generator=g) * 0.1).to(dev())
+    u = torch.randint(0, nu, (K, B), generator=g).to(dev())
+    ia, ib = torch.randint(0, ni, (K, B), generator=g).to(dev()), torch.randint(0, ni, (K, B), generator=g).to(dev())
+    y = (torch.rand(K, B, generator=g) < 0.5).float().to(dev())
+    outs = []
+    for early in (False, True):
+        ops().set_steps_early_scatter(early)
+        try:
+            if pairwise:
+                outs.append(ops().train_steps(ut, it, u, ia, ib, reg_weight=0.0))
+            else:
+                outs.append(ops().train_steps(ut, it, u, ia, None, y, loss_kind=lib().LOSS_BCE_SIGMOID, reg_weight=0.0))
+        finally:
+            ops().set_steps_early_scatter(False)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0][:, 0], outs[1][0][:, 0])
+    for a, b in ((outs[0][1], outs[1][1]), (outs[0][2], outs[1][2])):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6 * float(a.abs().max()))
+
+
 # ---------------------------------------------------------------------------------- tcgen05 fused map step (tc5_mlp.cu)
 @pytest.mark.parametrize('batch', [1, 127, 128, 129, 1000, 8192, 40000])
 def test_tc5_mlp_map_loss_matches_oracle(batch):

@@ -121,3 +121,11 @@ def test_get_model_naming_rule():
         assert get_model(name).__name__ == name
     with pytest.raises(ValueError):
         get_model('NoSuchModel')
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps each exported entry point to the reference interface it replaces (or says it has none)."""
+    from recbole_cdr_b200 import _lib
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    missing = [n for n in _lib.PROTOTYPES if n not in doc]
+    assert not missing, missing

@@ -146,3 +146,54 @@ def test_sharded_bitgcf_step_matches_single_gpu(world, way, exchange, tmp_path):
     else:
         mp.spawn(_bitgcf_worker, args=(world, port, str(tmp_path), way, exchange), nprocs=world, join=True)
     assert (tmp_path / 'ok').exists()
+
+
+# ---- E1, all-to-all form (shard_a2a.py): the exchange BASELINE.json's north_star names, over NCCL -------------------------
+
+def _a2a_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        from recbole_cdr_b200 import ops, shard
+        from recbole_cdr_b200.shard_a2a import AllToAllStep
+        nu, ni, dim, K, B = 4001, 5003, 64, 3, 2048
+        g = torch.Generator().manual_seed(3)
+        ut, it = torch.randn(nu, dim, generator=g) * 0.1, torch.randn(ni, dim, generator=g) * 0.1
+        u = torch.randint(0, nu, (world, K, B), generator=g)
+        ip, ineg = torch.randint(0, ni, (world, K, B), generator=g), torch.randint(0, ni, (world, K, B), generator=g)
+        tabs = [shard.RowShardedTable.from_full(t, rank, world, dev) for t in (ut, it)]
+        grads = [shard.RowShardedTable(t.shape[0], dim, rank, world, dev) for t in (ut, it)]
+        step = AllToAllStep(tabs[0], tabs[1], grads[0], grads[1], pairwise=True, reg_weight=0.01)
+        mine = torch.cat([step.step(u[rank, k].to(dev), ip[rank, k].to(dev), ineg[rank, k].to(dev)).reshape(-1) for k in range(K)])
+        torch.cuda.synchronize()
+        dist.barrier()
+        gu_full, gi_full = grads[0].to_full(), grads[1].to_full()
+        losses = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(losses, mine)
+        if rank == 0:
+            a, b = ut.to(dev).requires_grad_(True), it.to(dev).requires_grad_(True)
+            for r in range(world):
+                for k in range(K):
+                    loss = ops.bpr_loss(a, b, u[r, k].to(dev), ip[r, k].to(dev), ineg[r, k].to(dev), 0.01)
+                    torch.testing.assert_close(losses[r][k:k + 1], loss.detach().reshape(-1), rtol=1e-5, atol=0)
+                    loss.backward()
+            torch.testing.assert_close(gu_full, a.grad, rtol=1e-4, atol=1e-8)
+            torch.testing.assert_close(gi_full, b.grad, rtol=1e-4, atol=1e-8)
+            open(os.path.join(tmp, 'ok'), 'w').write('ok')
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.unvalidated
+@pytest.mark.parametrize('world', [2, 4])
+def test_all_to_all_steps_match_single_gpu(world, tmp_path):
+    """Same equivalence as the peer-memory path, through NCCL all-to-alls (hardware-validated kernels, a host path that has
+    only run over gloo so far -- hence `unvalidated`)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
+    port = 29900 + (os.getpid() % 2000) + world
+    mp.spawn(_a2a_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / 'ok').exists()

@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU calls of the next session: validate on hardware what was written while no GPU was reachable, then measure it.
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/r2_gpu_session.sh validate'   # sanitizer + parity (first!)
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash scripts/r2_gpu_session.sh validate'   # sanitizer + parity (first!)
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/r2_gpu_session.sh measure'    # timings + ncu
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/r2_gpu_session.sh engines'    # bf16x3 / 1xTF32 tile engines, tcgen05 experiment
 # (no argument: all three stages).  Every step is bounded by `timeout`; results land in gpurun_out/.
@@ -12,17 +12,12 @@ python __graft_entry__.py > gpurun_out/build.log 2>&1
 say() { echo "$1" | tee -a gpurun_out/summary.txt; }
 
 if [ "$STAGE" = validate ] || [ "$STAGE" = all ]; then
-  # memory checker on the smallest case of each new kernel (a wild pointer must not take the box down later)
-  XDR_RUN_UNVALIDATED=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 \
-      python -m pytest tests/test_gpu_unvalidated.py -x -q \
-      -k "map_loss_matches_oracle and 33 or conet_fused_matches_oracle and 63 or sparse_optim and sgd or full_sort_topk and 300 and mma" \
-      > gpurun_out/sanitizer.log 2>&1
-  say "sanitizer rc=$?"
-  # the hardware parity tests of the new kernels, then the regular gpu suite
-  XDR_RUN_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_unvalidated.py -q --timeout 300 -k "not tc5" > gpurun_out/unvalidated.log 2>&1
-  say "unvalidated rc=$?"
-  timeout 900 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/gpu_suite.log 2>&1
-  say "gpu suite rc=$?"
+  # order: the small tcgen05 experiments first (their answer decides the round's plan and must not be lost to a timeout),
+  # then the memory checker, the parity tests of the new kernels, and the regular gpu suite last (the driver re-runs it anyway)
+  # the standalone descriptor experiment (24 variants, one CTA each)
+  nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o /tmp/ubench_tcgen05 scripts/ubench_tcgen05.cu > gpurun_out/tcgen05.log 2>&1 \
+      && timeout 120 /tmp/ubench_tcgen05 >> gpurun_out/tcgen05.log 2>&1
+  say "ubench_tcgen05 rc=$?"
   # the tcgen05 top-k kernel on its own, under a short timeout (a wrong descriptor reading gives wrong numbers, a wrong
   # barrier protocol would hang: keep it away from the other tests)
   XDR_RUN_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_unvalidated.py -q -k "tc5_selftest" --timeout 60 \
@@ -54,10 +49,17 @@ if [ "$STAGE" = validate ] || [ "$STAGE" = all ]; then
   XDR_SECTIONS=emcdr_map_step XDR_BENCH_TC5=1 timeout 300 python scripts/bench_new_kernels.py > gpurun_out/tc5_mlp_bench.log 2>&1
   say "tc5 map-step bench rc=$?"
   unset XDR_LIB
-  # the tcgen05 descriptor experiment is tiny: run it in the first call so that the answer is there early
-  nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o /tmp/ubench_tcgen05 scripts/ubench_tcgen05.cu > gpurun_out/tcgen05.log 2>&1 \
-      && timeout 120 /tmp/ubench_tcgen05 >> gpurun_out/tcgen05.log 2>&1
-  say "ubench_tcgen05 rc=$?"
+  # memory checker on the smallest case of each new kernel (a wild pointer must not take the box down later)
+  XDR_RUN_UNVALIDATED=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 \
+      python -m pytest tests/test_gpu_unvalidated.py -x -q \
+      -k "map_loss_matches_oracle and 33 or conet_fused_matches_oracle and 63 or sparse_optim and sgd or full_sort_topk and 300 and mma" \
+      > gpurun_out/sanitizer.log 2>&1
+  say "sanitizer rc=$?"
+  # the hardware parity tests of the new kernels
+  XDR_RUN_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_unvalidated.py -q --timeout 300 -k "not tc5" > gpurun_out/unvalidated.log 2>&1
+  say "unvalidated rc=$?"
+  timeout 900 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/gpu_suite.log 2>&1
+  say "gpu suite rc=$?"
 fi
 
 if [ "$STAGE" = measure ] || [ "$STAGE" = all ]; then

@@ -1,4 +1,4 @@
 from .interaction import Interaction  # noqa: F401
 from .idspace import IdSpace  # noqa: F401
 from .dataloader import CrossDomainDataloader, DomainTrainDataLoader, OverlapDataloader  # noqa: F401
-from .device_pipeline import DeviceDomainData  # noqa: F401
+from .device_pipeline import DeviceDomainData, DeviceDomainTrainDataLoader  # noqa: F401

@@ -53,3 +53,52 @@ class DeviceDomainData(object):
         label = torch.zeros((k, 2, 2 * pos), dtype=torch.float32, device=ids.device)[:, 0]
         label[:, :pos] = 1.0
         return ids, label
+
+
+class DeviceDomainTrainDataLoader(object):
+    """The device-resident twin of ``dataloader.DomainTrainDataLoader``: same fields, slicing, pointwise / pairwise expansion and
+    ragged last batch, but the interactions live in HBM, the per-epoch shuffle is a device ``randperm`` and the negatives
+    come from the device sampler -- every ``Interaction`` it yields is already on the device and no host array is touched.
+    It plugs into ``CrossDomainDataloader`` (all four states) exactly like the host loader, so ANY model trains from it
+    through the unchanged trainer loop ("Interaction-compatible device tensors")."""
+
+    def __init__(self, uid_field, iid_field, users, items, batch_size, sampler, pairwise, label_field=None, neg_prefix='neg_',
+                 shuffle=False, generator=None, device='cuda'):
+        from .interaction import Interaction
+        self._Interaction = Interaction
+        self.device = torch.device(device)
+        self.uid_field, self.iid_field, self.label_field = uid_field, iid_field, label_field
+        self.neg_iid_field = neg_prefix + iid_field
+        self.users = torch.as_tensor(users, dtype=torch.int64).to(self.device)
+        self.items = torch.as_tensor(items, dtype=torch.int64).to(self.device)
+        self.batch_size, self.sampler, self.pairwise, self.shuffle = batch_size, sampler, pairwise, shuffle
+        self.generator = generator      # a generator on `device` (or None)
+        self.step = batch_size if pairwise else max(batch_size // 2, 1)
+        self.pr = 0
+        self.order = torch.arange(self.users.numel(), device=self.device)
+
+    @property
+    def pr_end(self):
+        return self.users.numel()
+
+    def __len__(self):
+        return -(-self.pr_end // self.step)
+
+    def __iter__(self):
+        if self.shuffle:
+            self.order = torch.randperm(self.users.numel(), device=self.device, generator=self.generator)
+        return self
+
+    def __next__(self):
+        if self.pr >= self.pr_end:
+            self.pr = 0
+            raise StopIteration()
+        sel = self.order[self.pr:self.pr + self.step]
+        self.pr += self.step
+        u, i = self.users[sel], self.items[sel]
+        neg = self.sampler.sample_by_key_ids(u, 1, check=False)
+        if self.pairwise:
+            return self._Interaction({self.uid_field: u, self.iid_field: i, self.neg_iid_field: neg})
+        labels = torch.cat([torch.ones(u.numel(), device=self.device), torch.zeros(u.numel(), device=self.device)])
+        return self._Interaction({self.uid_field: torch.cat([u, u]), self.iid_field: torch.cat([i, neg]),
+                                  self.label_field: labels})

@@ -46,6 +46,16 @@ def with_edges(extra, ds):
     return extra
 
 
+def full_sort(model, ds, n_users=6):
+    """``full_sort_predict`` of the model in its current phase for a few target users (its own RandomState: the batches of
+    the case are drawn from the same stream as before this was added)."""
+    users, _ = ds.valid_ids('target')
+    fb = {'target_user_id': torch.from_numpy(np.random.RandomState(97).choice(users, n_users)).long()}
+    with torch.no_grad():
+        score = model.full_sort_predict(fb)
+    return {'fbatch/target_user_id': fb['target_user_id'].numpy(), 'full_sort_predict': score.numpy()}
+
+
 def both_batch(ds, rng, bs=96, bt=80, pairwise=False):
     b = make_batch(ds, 'source', bs, rng, pairwise=pairwise)
     b.update(make_batch(ds, 'target', bt, rng, pairwise=pairwise))
@@ -65,6 +75,7 @@ def main():
     batch = both_batch(ds_b, np.random.RandomState(31))
     extra = sizes_scalar(ds_b)
     extra.update({'meta/alpha': 0.3, 'meta/reg_weight': 1e-2})
+    extra.update(full_sort(m, ds_b))
     save('f4_clfm', run_and_pack(m, batch, extra))
 
     # ---------------- DeepAPF (user overlap / item overlap) ----------------
@@ -80,7 +91,10 @@ def main():
         m = SSCDR(cfg0(embedding_size=D, margin=1, mlp_hidden_size=[128], **{'lambda': 0.25}), ds_u)
         m.set_phase(phase)
         batch = make_batch(ds_u, dom, 96, np.random.RandomState(41), pairwise=True)
-        save(f'f4_sscdr_{phase.lower()}', run_and_pack(m, batch, with_edges(sizes_scalar(ds_u), ds_u)))
+        extra = with_edges(sizes_scalar(ds_u), ds_u)
+        if phase == 'TARGET':
+            extra.update(full_sort(m, ds_u))
+        save(f'f4_sscdr_{phase.lower()}', run_and_pack(m, batch, extra))
     for tag, ds, n_ov in (('users', ds_u, ds_u.num_overlap_user), ('items', ds_i, ds_i.num_overlap_item)):
         torch.manual_seed(2022)
         m = SSCDR(cfg0(embedding_size=D, margin=1, mlp_hidden_size=[128], **{'lambda': 0.25}), ds)
@@ -93,6 +107,7 @@ def main():
         extra = with_edges(sizes_scalar(ds), ds)
         extra.update({'pbatch/' + k: v.numpy() for k, v in pb.items()})
         extra['predict_overlap_phase'] = pred
+        extra.update(full_sort(m, ds))
         extra['meta/np_seed'] = 4242
         np.random.seed(4242)
         save(f'f4_sscdr_map_{tag}', run_and_pack(m, {'overlap': idx}, extra, predict=False))
@@ -117,8 +132,10 @@ def main():
         save(f'f4_dcdcsr_{tag}_source1',
              run_and_pack(m, make_batch(ds, 'source', 96, np.random.RandomState(53), pairwise=True), dict(base)))
         m.set_phase('TARGET')
+        extra = dict(base)
+        extra.update(full_sort(m, ds))
         save(f'f4_dcdcsr_{tag}_target1',
-             run_and_pack(m, make_batch(ds, 'target', 96, np.random.RandomState(59), pairwise=True), dict(base)))
+             run_and_pack(m, make_batch(ds, 'target', 96, np.random.RandomState(59), pairwise=True), extra))
         m.set_phase('BOTH')
         extra = dict(base)
         extra['benchmark_embedding'] = m.benchmark_embedding.detach().numpy().copy()
@@ -128,6 +145,7 @@ def main():
         m.set_phase('TARGET')
         extra = dict(base)
         extra['affine_embedding'] = m.affine_embedding.detach().numpy().copy()
+        extra.update(full_sort(m, ds))
         save(f'f4_dcdcsr_{tag}_target2',
              run_and_pack(m, make_batch(ds, 'target', 96, np.random.RandomState(61), pairwise=True), extra))
 

@@ -26,6 +26,14 @@ def build(model_cls, g, cfg, with_edges=False):
     return m
 
 
+def check_full_sort(m, g):
+    """``full_sort_predict`` in the model's current phase against the reference's (goldens that carry one)."""
+    assert g.has('full_sort_predict')
+    with torch.no_grad():
+        got = m.full_sort_predict(cpu_batch(g, 'fbatch/'))
+    torch.testing.assert_close(got.reshape(-1), g.t('full_sort_predict').reshape(-1), rtol=1e-4, atol=2e-6)
+
+
 def test_clfm():
     from recbole_cdr_b200.model.cross_domain_recommender.clfm import CLFM
     g = Golden('f4_clfm')
@@ -35,6 +43,7 @@ def test_clfm():
         batch = cpu_batch(g)
         check(m, g, batch)
         torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-5, atol=1e-6)
+        check_full_sort(m, g)
 
 
 @pytest.mark.parametrize('tag', ['users', 'items'])
@@ -61,6 +70,8 @@ def test_sscdr_rec_phases(phase):
         batch = cpu_batch(g)
         check(m, g, batch)
         torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-5, atol=1e-6)
+        if phase == 'target':
+            check_full_sort(m, g)
 
 
 @pytest.mark.parametrize('tag', ['users', 'items'])
@@ -74,6 +85,7 @@ def test_sscdr_map_phase(tag):
         np.random.seed(g.meta('np_seed'))
         check(m, g, cpu_batch(g), grad_atol=1e-6)
         torch.testing.assert_close(m.predict(cpu_batch(g, 'pbatch/')), g.t('predict_overlap_phase'), rtol=1e-4, atol=1e-6)
+        check_full_sort(m, g)
 
 
 @pytest.mark.parametrize('tag', ['items', 'users'])
@@ -108,6 +120,7 @@ def test_dcdcsr_four_stages(tag):
         m.set_phase('TARGET')
         check(m, g, cpu_batch(g))
         torch.testing.assert_close(m.predict(cpu_batch(g)), g.t('predict'), rtol=1e-5, atol=1e-6)
+        check_full_sort(m, g)
         g = Golden(f'f4_dcdcsr_{tag}_both')
         m.set_phase('BOTH')
         torch.testing.assert_close(m.benchmark_embedding, g.t('benchmark_embedding'), rtol=1e-4, atol=1e-6)
@@ -118,6 +131,7 @@ def test_dcdcsr_four_stages(tag):
         torch.testing.assert_close(m.affine_embedding, g.t('affine_embedding'), rtol=1e-4, atol=1e-6)
         check(m, g, cpu_batch(g))
         torch.testing.assert_close(m.predict(cpu_batch(g)), g.t('predict'), rtol=1e-5, atol=1e-6)
+        check_full_sort(m, g)
 
 
 def test_get_model_and_trainer_resolve_the_new_classes():

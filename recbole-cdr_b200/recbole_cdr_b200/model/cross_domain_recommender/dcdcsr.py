@@ -189,3 +189,12 @@ class DCDCSR(CrossDomainRecommender):
             ut, _, uf, _, all_items = self._eval_tables()
             user_e = ops.gather_rows_raw(ut.contiguous(), interaction[uf])
             return torch.matmul(user_e, all_items().transpose(0, 1))
+
+    def full_sort_topk(self, interaction, k, hist_ptr=None, hist_ids=None, engine='mma'):
+        """Fused ``full_sort_predict`` + PAD/history masking + ``topk`` in the current stage: the
+        [B, n_items] matrix is never written.  Returns (scores [B, k], positions [B, k] in full_sort_predict's columns)."""
+        with torch.no_grad():
+            ut, _, uf, _, all_items = self._eval_tables()
+            user_e = ops.gather_rows_raw(ut.contiguous(), interaction[uf])
+            return ops.full_sort_topk(user_e, all_items().contiguous(), k, first_item=1, hist_ptr=hist_ptr, hist_ids=hist_ids,
+                                      engine=engine)

@@ -27,11 +27,15 @@ def build(model_cls, g, cfg, with_edges=False):
 
 
 def check_full_sort(m, g):
-    """``full_sort_predict`` in the model's current phase against the reference's (goldens that carry one)."""
+    """``full_sort_predict`` in the model's current phase against the reference's (goldens that carry one); where the model
+    has a fused ``full_sort_topk``, that too (against torch.topk of the reference's masked scores)."""
+    import variants_util as V
     assert g.has('full_sort_predict')
     with torch.no_grad():
         got = m.full_sort_predict(cpu_batch(g, 'fbatch/'))
     torch.testing.assert_close(got.reshape(-1), g.t('full_sort_predict').reshape(-1), rtol=1e-4, atol=2e-6)
+    if hasattr(m, 'full_sort_topk'):
+        V.check_topk_against_reference(m, g, 'cpu')
 
 
 def test_clfm():

@@ -176,27 +176,45 @@ class SSCDR(CrossDomainRecommender):
                                                                 interaction[self.TARGET_ITEM_ID])
             return -self.embedding_distance(n(user_e), n(item_e))
 
+    def _full_sort_operands(self, interaction):
+        """(normalised user-side vectors [B, D], normalised candidate item rows [n, D]) of full_sort_predict in the current
+        phase (sscdr.py:222-252)."""
+        n = self.embedding_normalize
+        if self.phase == 'SOURCE':
+            user_e = n(ops.gather_rows_raw(self.source_user_embedding.weight, interaction[self.SOURCE_USER_ID]))
+            w = self.source_item_embedding.weight
+            return user_e, torch.cat([n(w[:self.overlapped_num_items]), n(w[self.target_num_items:])], dim=0)
+        if self.phase == 'TARGET':
+            user_e = n(ops.gather_rows_raw(self.target_user_embedding.weight, interaction[self.TARGET_USER_ID]))
+            return user_e, n(self.target_item_embedding.weight[:self.target_num_items])
+        user_e, _ = self._overlap_phase_embeddings(interaction[self.TARGET_USER_ID])
+        if self.mode == 'overlap_users':
+            all_item_e = self.target_item_embedding.weight[:self.target_num_items]
+        else:
+            ov = self.mapping_layer(self.source_item_embedding.weight[:self.overlapped_num_items].contiguous())
+            all_item_e = torch.cat([ov, self.target_item_embedding.weight[self.overlapped_num_items:self.target_num_items]], dim=0)
+        return n(user_e), n(all_item_e)
+
+    def full_sort_topk(self, interaction, k, hist_ptr=None, hist_ids=None, engine='mma'):
+        """Fused ``full_sort_predict`` + PAD/history masking + ``topk``.  The score is a negative
+        squared distance, ``-|u - i|^2 = 2 u.i - |i|^2 - |u|^2``: a dot product of the augmented rows ``[2u, -1, 0..]`` and
+        ``[i, |i|^2, 0..]`` (width D + 8) minus a per-user constant, so the dot-product scoring kernel applies unchanged."""
+        with torch.no_grad():
+            user_e, all_item_e = self._full_sort_operands(interaction)
+            B, D = user_e.shape
+            ua = torch.zeros((B, D + 8), dtype=torch.float32, device=user_e.device)
+            ua[:, :D] = 2 * user_e
+            ua[:, D] = -1.0
+            ia = torch.zeros((all_item_e.shape[0], D + 8), dtype=torch.float32, device=user_e.device)
+            ia[:, :D] = all_item_e
+            ia[:, D] = torch.sum(all_item_e ** 2, -1)
+            sc, pos = ops.full_sort_topk(ua, ia, k, first_item=1, hist_ptr=hist_ptr, hist_ids=hist_ids, engine=engine)
+            return sc - torch.sum(user_e ** 2, -1).view(-1, 1), pos
+
     def full_sort_predict(self, interaction):
         """sscdr.py:222-259: negative squared distances to every candidate item (library matmul, drop-in shape)."""
         with torch.no_grad():
-            n = self.embedding_normalize
-            if self.phase == 'SOURCE':
-                user_e = n(ops.gather_rows_raw(self.source_user_embedding.weight, interaction[self.SOURCE_USER_ID]))
-                w = self.source_item_embedding.weight
-                all_item_e = torch.cat([n(w[:self.overlapped_num_items]), n(w[self.target_num_items:])], dim=0)
-            elif self.phase == 'TARGET':
-                user_e = n(ops.gather_rows_raw(self.target_user_embedding.weight, interaction[self.TARGET_USER_ID]))
-                all_item_e = n(self.target_item_embedding.weight[:self.target_num_items])
-            else:
-                user = interaction[self.TARGET_USER_ID]
-                user_e, _ = self._overlap_phase_embeddings(user)
-                if self.mode == 'overlap_users':
-                    all_item_e = self.target_item_embedding.weight[:self.target_num_items]
-                else:
-                    ov = self.mapping_layer(self.source_item_embedding.weight[:self.overlapped_num_items].contiguous())
-                    all_item_e = torch.cat(
-                        [ov, self.target_item_embedding.weight[self.overlapped_num_items:self.target_num_items]], dim=0)
-                user_e, all_item_e = n(user_e), n(all_item_e)
+            user_e, all_item_e = self._full_sort_operands(interaction)
             dist = -2 * torch.matmul(user_e, all_item_e.permute(1, 0))
             dist += torch.sum(user_e ** 2, -1).view(-1, 1)
             dist += torch.sum(all_item_e ** 2, -1).view(1, -1)

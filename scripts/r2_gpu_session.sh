@@ -3,7 +3,8 @@
 #   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash scripts/r2_gpu_session.sh validate'   # sanitizer + parity (first!)
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/r2_gpu_session.sh measure'    # timings + ncu
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/r2_gpu_session.sh engines'    # bf16x3 / 1xTF32 tile engines, tcgen05 experiment
-# (no argument: all three stages).  Every step is bounded by `timeout`; results land in gpurun_out/.
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash scripts/r2_gpu_session.sh multi'  # all-to-all baseline vs peer kernel
+# (no argument: the three single-GPU stages).  Every step is bounded by `timeout`; results land in gpurun_out/.
 set -u
 STAGE=${1:-all}
 mkdir -p gpurun_out
@@ -87,6 +88,15 @@ if [ "$STAGE" = engines ] || [ "$STAGE" = all ]; then
         timeout 600 python scripts/bench_new_kernels.py > gpurun_out/new_kernels_m$m.log 2>&1
     say "bench_new_kernels (XDR_TC_MODE=$m) rc=$?"
   done
+fi
+
+if [ "$STAGE" = multi ]; then
+  N=$(python -c "import torch; print(torch.cuda.device_count())")
+  XDR_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_gpu_multi.py -q -k "all_to_all" --timeout 300 > gpurun_out/a2a_parity.log 2>&1
+  say "all-to-all parity on $N GPUs rc=$?"
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 \
+      scripts/bench_a2a.py > gpurun_out/a2a_bench.log 2>&1
+  say "bench_a2a ($N GPUs) rc=$?"
 fi
 
 tail -n 6 gpurun_out/*.log

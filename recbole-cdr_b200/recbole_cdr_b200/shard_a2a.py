@@ -115,3 +115,59 @@ class AllToAllStep(object):
         ops.scatter_add_rows_raw(self.du.local, own_u, torch.cat(gseg[0::2]).contiguous(), scale)
         ops.scatter_add_rows_raw(self.di.local, own_i, torch.cat(gseg[1::2]).contiguous(), scale)
         return loss.detach()
+
+
+class AllToAllChunkRunner(AllToAllStep):
+    """K steps per exchange: the ids of a whole ``[K, R, B]`` block are bucketed at once, ONE round of all-to-alls brings every
+    row the block needs, the persistent multi-step kernel (``ops.train_steps``) runs the K steps on the block-sized mini
+    tables in a single launch, and one all-to-all returns the K steps' gradient rows to their owners.  Four collectives and
+    one host read per BLOCK instead of per step, in messages K times larger (bulk NVLink transfers instead of per-row
+    requests).  Exact in gradient-accumulation mode (the weights do not change inside a block); with ``scale = -lr`` on the
+    weight shards the steps of a block read the weights as they were when the block started (the same staleness as the
+    asynchronous fused-SGD launch).  ``run`` returns the ``[K]`` per-step losses of this rank's batches."""
+
+    def run(self, ids: torch.Tensor, label: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
+        G, D, dev = self.world, self.ut.dim, ids.device
+        K, R, B = ids.shape
+        if R != (3 if self.pairwise else 2):
+            raise ValueError(f'id block must be [K, {3 if self.pairwise else 2}, B]')
+        user = ids[:, 0].reshape(-1)                                           # position k*B + j
+        items = ids[:, 1:].reshape(K, -1).reshape(-1)                          # position k*(R-1)*B + (r-1)*B + j
+        order_u, rows_u, cnt_u = _bucket(user, G)
+        order_i, rows_i, cnt_i = _bucket(items, G)
+        send_cnt = torch.stack([cnt_u, cnt_i], dim=1)
+        recv_cnt = torch.empty_like(send_cnt)
+        self._a2a(recv_cnt.view(-1), send_cnt.view(-1).contiguous(), None, None)
+        send_cnt_h, recv_cnt_h = send_cnt.tolist(), recv_cnt.tolist()          # the one host read of the block
+        in_splits, out_splits = [a + b for a, b in send_cnt_h], [a + b for a, b in recv_cnt_h]
+        su, si = torch.split(rows_u, [c[0] for c in send_cnt_h]), torch.split(rows_i, [c[1] for c in send_cnt_h])
+        got_req = torch.empty(sum(out_splits), dtype=torch.int64, device=dev)
+        self._a2a(got_req, torch.cat([t for pair in zip(su, si) for t in pair]), out_splits, in_splits)
+        seg = torch.split(got_req, [c for pair in recv_cnt_h for c in pair])
+        own_u, own_i = torch.cat(seg[0::2]), torch.cat(seg[1::2])
+        ru = torch.split(ops.gather_rows_raw(self.ut.local, own_u), [c[0] for c in recv_cnt_h])
+        ri = torch.split(ops.gather_rows_raw(self.it.local, own_i), [c[1] for c in recv_cnt_h])
+        got_rows = torch.empty((sum(in_splits), D), dtype=torch.float32, device=dev)
+        self._a2a(got_rows, torch.cat([t for pair in zip(ru, ri) for t in pair]), in_splits, out_splits)
+        self.exchanged_rows += got_rows.shape[0]
+        parts = torch.split(got_rows, [c for pair in send_cnt_h for c in pair])
+        mini_u = torch.empty((K * B, D), dtype=torch.float32, device=dev)
+        mini_i = torch.empty((K * (R - 1) * B, D), dtype=torch.float32, device=dev)
+        mini_u[order_u] = torch.cat(parts[0::2])
+        mini_i[order_i] = torch.cat(parts[1::2])
+        # ---- K steps in one persistent launch on the mini tables: row of (step k, slot j) sits at a fixed position --------------
+        j = torch.arange(B, dtype=torch.int64, device=dev)
+        k0 = torch.arange(K, dtype=torch.int64, device=dev).view(-1, 1)
+        pos = torch.stack([k0 * B + j] + [k0 * (R - 1) * B + r * B + j for r in range(R - 1)], dim=1).contiguous()   # [K, R, B]
+        gu, gi = torch.zeros_like(mini_u), torch.zeros_like(mini_i)
+        out8, _, _ = ops.train_steps(mini_u, mini_i, pos[:, 0], pos[:, 1], pos[:, 2] if self.pairwise else None, label,
+                                     loss_kind=self.loss_kind, reg_weight=self.reg_weight, gamma=self.gamma, user_dst=gu,
+                                     item_dst=gi, scale=1.0)
+        # ---- gradient rows back to their owners ------------------------------------------------------------------------------------
+        gu_b, gi_b = torch.split(gu[order_u], [c[0] for c in send_cnt_h]), torch.split(gi[order_i], [c[1] for c in send_cnt_h])
+        got_g = torch.empty((sum(out_splits), D), dtype=torch.float32, device=dev)
+        self._a2a(got_g, torch.cat([t for pair in zip(gu_b, gi_b) for t in pair]), out_splits, in_splits)
+        gseg = torch.split(got_g, [c for pair in recv_cnt_h for c in pair])
+        ops.scatter_add_rows_raw(self.du.local, own_u, torch.cat(gseg[0::2]).contiguous(), scale)
+        ops.scatter_add_rows_raw(self.di.local, own_i, torch.cat(gseg[1::2]).contiguous(), scale)
+        return out8[:, 0]

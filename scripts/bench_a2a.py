@@ -4,7 +4,9 @@ loads / REDs.  One process per GPU:
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 scripts/bench_a2a.py
 
-Prints one JSON line (rank 0): us per step of both forms (CUDA events, max over ranks) and the aggregate interactions/s."""
+Three forms: one exchange round per step (AllToAllStep), one per block of --steps steps with the persistent kernel on
+block-sized mini tables (AllToAllChunkRunner), and the peer-memory persistent kernel.
+Prints one JSON line (rank 0): us per step of the three forms (CUDA events, max over ranks) and the aggregate interactions/s."""
 import argparse
 import json
 import os
@@ -16,7 +18,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'recbole-cdr_b200'))
 from recbole_cdr_b200 import shard  # noqa: E402
-from recbole_cdr_b200.shard_a2a import AllToAllStep  # noqa: E402
+from recbole_cdr_b200.shard_a2a import AllToAllChunkRunner, AllToAllStep  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--rows', type=int, default=1_000_000, help='rows per table PER GPU (weak scaling, as bench.py)')
@@ -64,6 +66,10 @@ def timed(fn):
 a2a = AllToAllStep(tabs[0], tabs[1], grads[0], grads[1], pairwise=True, reg_weight=0.01)
 t_a2a = timed(lambda: [a2a.step(u[k], ip[k], ineg[k]) for k in range(K)]) / K
 
+chunk = AllToAllChunkRunner(tabs[0], tabs[1], grads[0], grads[1], pairwise=True, reg_weight=0.01)
+block = torch.stack([u, ip, ineg], dim=1).contiguous()          # [K, 3, B]: one exchange round for all K steps
+t_chunk = timed(lambda: chunk.run(block)) / K
+
 for t in tabs + grads:
     t.connect()
 if world > 1:
@@ -72,8 +78,10 @@ t_peer = timed(lambda: shard.train_steps_sharded(tabs[0], tabs[1], grads[0], gra
 
 if rank == 0:
     print(json.dumps({'n_gpus': world, 'rows_per_gpu': args.rows, 'dim': args.dim, 'batch_per_gpu': B, 'steps': K,
-                      'all_to_all_us_per_step': round(t_a2a * 1e6, 1), 'peer_kernel_us_per_step': round(t_peer * 1e6, 1),
+                      'all_to_all_us_per_step': round(t_a2a * 1e6, 1), 'all_to_all_block_us_per_step': round(t_chunk * 1e6, 1),
+                      'peer_kernel_us_per_step': round(t_peer * 1e6, 1),
                       'all_to_all_Minter_per_s': round(world * B / t_a2a / 1e6, 1),
+                      'all_to_all_block_Minter_per_s': round(world * B / t_chunk / 1e6, 1),
                       'peer_kernel_Minter_per_s': round(world * B / t_peer / 1e6, 1)}), flush=True)
 for t in tabs + grads:
     t.close()

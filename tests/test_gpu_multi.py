@@ -150,7 +150,7 @@ def test_sharded_bitgcf_step_matches_single_gpu(world, way, exchange, tmp_path):
 
 # ---- E1, all-to-all form (shard_a2a.py): the exchange BASELINE.json's north_star names, over NCCL -------------------------
 
-def _a2a_worker(rank, world, port, tmp):
+def _a2a_worker(rank, world, port, tmp, chunked):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device('cuda', rank)
@@ -166,7 +166,12 @@ def _a2a_worker(rank, world, port, tmp):
         tabs = [shard.RowShardedTable.from_full(t, rank, world, dev) for t in (ut, it)]
         grads = [shard.RowShardedTable(t.shape[0], dim, rank, world, dev) for t in (ut, it)]
         step = AllToAllStep(tabs[0], tabs[1], grads[0], grads[1], pairwise=True, reg_weight=0.01)
-        mine = torch.cat([step.step(u[rank, k].to(dev), ip[rank, k].to(dev), ineg[rank, k].to(dev)).reshape(-1) for k in range(K)])
+        if chunked:     # one exchange round for the K steps + the persistent kernel on block-sized mini tables
+            from recbole_cdr_b200.shard_a2a import AllToAllChunkRunner
+            runner = AllToAllChunkRunner(tabs[0], tabs[1], grads[0], grads[1], pairwise=True, reg_weight=0.01)
+            mine = runner.run(torch.stack([u[rank], ip[rank], ineg[rank]], dim=1).contiguous().to(dev)).clone()
+        else:
+            mine = torch.cat([step.step(u[rank, k].to(dev), ip[rank, k].to(dev), ineg[rank, k].to(dev)).reshape(-1) for k in range(K)])
         torch.cuda.synchronize()
         dist.barrier()
         gu_full, gi_full = grads[0].to_full(), grads[1].to_full()
@@ -188,12 +193,13 @@ def _a2a_worker(rank, world, port, tmp):
 
 
 @pytest.mark.unvalidated
+@pytest.mark.parametrize('chunked', [False, True])
 @pytest.mark.parametrize('world', [2, 4])
-def test_all_to_all_steps_match_single_gpu(world, tmp_path):
+def test_all_to_all_steps_match_single_gpu(world, chunked, tmp_path):
     """Same equivalence as the peer-memory path, through NCCL all-to-alls (hardware-validated kernels, a host path that has
     only run over gloo so far -- hence `unvalidated`)."""
     if torch.cuda.device_count() < world:
         pytest.skip(f'needs {world} GPUs')
-    port = 29900 + (os.getpid() % 2000) + world
-    mp.spawn(_a2a_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    port = 29900 + (os.getpid() % 2000) + world + (20 if chunked else 0)
+    mp.spawn(_a2a_worker, args=(world, port, str(tmp_path), chunked), nprocs=world, join=True)
     assert (tmp_path / 'ok').exists()

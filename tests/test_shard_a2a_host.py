@@ -80,3 +80,71 @@ def test_all_to_all_step_gloo_world2(tmp_path, pairwise):
     port = 29700 + (os.getpid() % 2000) + (1 if pairwise else 0)
     mp.spawn(_worker, args=(world, port, str(tmp_path), pairwise), nprocs=world, join=True)
     assert all((tmp_path / f'ok{r}').exists() for r in range(world))
+
+
+# ---- K steps per exchange (AllToAllChunkRunner): the persistent kernel on block-sized mini tables --------------------------------
+
+def _run_rank_chunk(rank, world, pairwise, K=3, B=32):
+    import emu_util
+    from recbole_cdr_b200 import _lib
+    from recbole_cdr_b200.shard import RowShardedTable
+    from recbole_cdr_b200.shard_a2a import AllToAllChunkRunner
+    from oracle import cdr_oracle as O
+    nu, ni, dim, reg = 203, 301, 32, 0.02
+    g = torch.Generator().manual_seed(5)
+    ut, it = torch.randn(nu, dim, generator=g) * 0.3, torch.randn(ni, dim, generator=g) * 0.3
+    blocks = []
+    for r in range(world):
+        gr = torch.Generator().manual_seed(200 + r)
+        ids = torch.stack([torch.randint(0, nu, (K, B), generator=gr), torch.randint(0, ni, (K, B), generator=gr)] +
+                          ([torch.randint(0, ni, (K, B), generator=gr)] if pairwise else []), dim=1)
+        blocks.append((ids, (torch.rand(K, B, generator=gr) < 0.5).float()))
+    with emu_util.patched_ops(sms=2):
+        tu, ti = RowShardedTable.from_full(ut, rank, world, 'cpu'), RowShardedTable.from_full(it, rank, world, 'cpu')
+        du, di = RowShardedTable(nu, dim, rank, world, 'cpu'), RowShardedTable(ni, dim, rank, world, 'cpu')
+        runner = AllToAllChunkRunner(tu, ti, du, di, pairwise=pairwise, loss_kind=_lib.LOSS_BCE_SIGMOID, reg_weight=reg)
+        ids, y = blocks[rank]
+        lab = None
+        if not pairwise:     # the persistent kernel wants the label rows on the id block's step stride
+            lab = torch.zeros((K, 2, B))[:, 0]
+            lab.copy_(y)
+        losses = runner.run(ids, lab)
+    a, b = ut.clone().requires_grad_(True), it.clone().requires_grad_(True)
+    total = 0
+    for r in range(world):
+        ids_r, y_r = blocks[r]
+        for k in range(K):
+            if pairwise:
+                ref = O.emcdr_bpr_loss(a, b, ids_r[k, 0], ids_r[k, 1], ids_r[k, 2], reg)
+            else:
+                ref = O.bce_loss(torch.sigmoid(O.dot_score(a, b, ids_r[k, 0], ids_r[k, 1])), y_r[k]) + reg * O.emb_loss(a[ids_r[k, 0]], b[ids_r[k, 1]])
+            if r == rank:
+                assert abs(float(losses[k]) - float(ref.detach().reshape(-1)[0])) <= 1e-4 * abs(float(ref.detach().reshape(-1)[0]))
+            total = total + ref.sum()
+    gu, gi = torch.autograd.grad(total, [a, b])
+    torch.testing.assert_close(du.to_full(), gu, rtol=1e-4, atol=1e-4 * float(gu.abs().max()))
+    torch.testing.assert_close(di.to_full(), gi, rtol=1e-4, atol=1e-4 * float(gi.abs().max()))
+
+
+def _chunk_worker(rank, world, port, tmp, pairwise):
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        _run_rank_chunk(rank, world, pairwise)
+        open(os.path.join(tmp, f'ok{rank}'), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('pairwise', [True, False])
+def test_all_to_all_chunk_world1(pairwise):
+    _run_rank_chunk(0, 1, pairwise)
+
+
+@pytest.mark.parametrize('pairwise', [True, False])
+def test_all_to_all_chunk_gloo_world2(tmp_path, pairwise):
+    world = 2
+    port = 30100 + (os.getpid() % 2000) + (1 if pairwise else 0)
+    mp.spawn(_chunk_worker, args=(world, port, str(tmp_path), pairwise), nprocs=world, join=True)
+    assert all((tmp_path / f'ok{r}').exists() for r in range(world))

@@ -16,7 +16,16 @@
 //   MN-major: ((1,n),(8,k)):((X,SBO),(1,LBO))  a core matrix = 8 K-rows x 16 B (4 MN elements); next 4 MN elements +SBO; next 8 K +LBO
 // Descriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64).
 // Instruction descriptor: c_format F32 = 1 [4,6), a/b_format TF32 = 2 [7,10)/[10,13), a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
+// Host model: `g++ -x c++ -DUBENCH_HOST_MODEL scripts/ubench_tcgen05.cu` builds a CPU program that stages the operands and builds
+// the descriptors with the SAME helpers as the kernel and then walks them the way this file's reading says the hardware does.
+// It checks the experiment itself (tests/test_ubench_model.py): every "as read" variant must reproduce the product and every
+// "exchanged" variant must not -- so a FAIL on the GPU means the reading is wrong, not the staging code.
+#ifdef UBENCH_HOST_MODEL
+#define __host__
+#define __device__
+#else
 #include <cuda_runtime.h>
+#endif
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -32,8 +41,10 @@ struct Variant {
   int bf16;                    // 0 = kind::tf32 on fp32 operands (K = 8 per MMA), 1 = kind::f16 on bf16 operands (K = 16)
 };
 
-__device__ inline unsigned short bf16_bits(float x) {  // the host pre-rounds the inputs, so truncation is exact
-  return (unsigned short)(__float_as_uint(x) >> 16);
+__host__ __device__ inline unsigned short bf16_bits(float x) {  // the host pre-rounds the inputs, so truncation is exact
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  return (unsigned short)(u >> 16);
 }
 
 // byte offset of element (mn, k) of an operand with `rows` MN-rows, plus the LBO / SBO / per-instruction K advance it implies
@@ -68,7 +79,7 @@ __host__ __device__ inline int operand_offset(int rows, int mn_major, int mn, in
   return (k / 8) * o.lbo + (mn / T) * o.sbo + (k % 8) * 16 + (mn % T) * es;
 }
 
-__device__ inline uint64_t make_desc(uint32_t smem_addr, int lbo, int sbo) {
+__host__ __device__ inline uint64_t make_desc(uint32_t smem_addr, int lbo, int sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
   d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
@@ -77,6 +88,29 @@ __device__ inline uint64_t make_desc(uint32_t smem_addr, int lbo, int sbo) {
   return d;                // base_offset 0, lbo_mode 0, layout_type SWIZZLE_NONE = 0
 }
 
+// descriptor of operand `which` (0 = A, 1 = B) for K step `ks`, and the instruction descriptor: shared by the kernel and the host model
+__host__ __device__ inline uint64_t operand_desc(const Variant& v, int which, uint32_t base, int ks, int T) {
+  const OperandLayout l = operand_layout(which ? N : M, which ? v.b_mn_major : v.a_mn_major, T);
+  return v.swap_lbo_sbo ? make_desc(base + ks * l.k_step_bytes, l.sbo, l.lbo) : make_desc(base + ks * l.k_step_bytes, l.lbo, l.sbo);
+}
+__host__ __device__ inline uint32_t instr_desc(const Variant& v) {
+  const uint32_t fmt = v.bf16 ? 1u : 2u;   // F16F32Format: 1 = BF16, 2 = TF32
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(v.a_mn_major == 1) << 15) | ((uint32_t)v.b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// writes element (r, k) of operand `which` into its shared-memory image
+__host__ __device__ inline void stage_element(const Variant& v, int which, uint8_t* s, int r, int k, float x) {
+  const int T = v.bf16 ? 8 : 4;
+  const int off = operand_offset(which ? N : M, which ? v.b_mn_major : v.a_mn_major, r, k, T);
+  if (v.bf16) {
+    const unsigned short h = bf16_bits(x);
+    memcpy(s + off, &h, 2);
+  } else {
+    memcpy(s + off, &x, 4);
+  }
+}
+
+#ifndef UBENCH_HOST_MODEL
 __global__ void __launch_bounds__(128, 1) umma_tf32_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                            float* __restrict__ D, Variant v) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -87,16 +121,8 @@ __global__ void __launch_bounds__(128, 1) umma_tf32_kernel(const float* __restri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int T = v.bf16 ? 8 : 4;
-  for (int e = tid; e < M * K; e += 128) {
-    const int r = e / K, k = e % K;
-    if (v.bf16) *reinterpret_cast<unsigned short*>(sA + operand_offset(M, v.a_mn_major, r, k, T)) = bf16_bits(A[e]);
-    else *reinterpret_cast<float*>(sA + operand_offset(M, v.a_mn_major, r, k, T)) = A[e];
-  }
-  for (int e = tid; e < N * K; e += 128) {
-    const int r = e / K, k = e % K;
-    if (v.bf16) *reinterpret_cast<unsigned short*>(sB + operand_offset(N, v.b_mn_major, r, k, T)) = bf16_bits(B[e]);
-    else *reinterpret_cast<float*>(sB + operand_offset(N, v.b_mn_major, r, k, T)) = B[e];
-  }
+  for (int e = tid; e < M * K; e += 128) stage_element(v, 0, sA, e / K, e % K, A[e]);
+  for (int e = tid; e < N * K; e += 128) stage_element(v, 1, sB, e / K, e % K, B[e]);
   const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&bar);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
@@ -114,16 +140,10 @@ __global__ void __launch_bounds__(128, 1) umma_tf32_kernel(const float* __restri
   const uint32_t tmem_base = tmem_base_smem;
 
   if (tid == 0) {  // a single thread issues the MMAs
-    const OperandLayout la = operand_layout(M, v.a_mn_major, T), lb = operand_layout(N, v.b_mn_major, T);
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(sA), b0 = (uint32_t)__cvta_generic_to_shared(sB);
-    const uint32_t fmt = v.bf16 ? 1u : 2u;   // F16F32Format: 1 = BF16, 2 = TF32
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(v.a_mn_major == 1) << 15) | ((uint32_t)v.b_mn_major << 16) |
-                           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    const uint32_t idesc = instr_desc(v);
     for (int ks = 0; ks < K / (2 * T); ++ks) {
-      const uint64_t da = v.swap_lbo_sbo ? make_desc(a0 + ks * la.k_step_bytes, la.sbo, la.lbo)
-                                         : make_desc(a0 + ks * la.k_step_bytes, la.lbo, la.sbo);
-      const uint64_t db = v.swap_lbo_sbo ? make_desc(b0 + ks * lb.k_step_bytes, lb.sbo, lb.lbo)
-                                         : make_desc(b0 + ks * lb.k_step_bytes, lb.lbo, lb.sbo);
+      const uint64_t da = operand_desc(v, 0, a0, ks, T), db = operand_desc(v, 1, b0, ks, T);
       const uint32_t acc = ks > 0 ? 1u : 0u;
       const uint32_t zero = 0;
       if (v.bf16)
@@ -184,6 +204,8 @@ __global__ void __launch_bounds__(128, 1) umma_tf32_kernel(const float* __restri
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64));
 }
 
+#endif  // !UBENCH_HOST_MODEL
+
 static float tf32_round(float x) {  // keep 7 mantissa bits: exactly representable in bf16 AND in tf32, products exact in fp32
   uint32_t u;
   memcpy(&u, &x, 4);
@@ -192,6 +214,71 @@ static float tf32_round(float x) {  // keep 7 mantissa bits: exactly representab
   return x;
 }
 
+#ifdef UBENCH_HOST_MODEL
+// The reading under test, as a reader of shared-memory images: element (r, k') of the K = 2T slice a descriptor addresses.
+static float model_operand(const uint8_t* smem, uint64_t desc, bool mn_major, int T, int r, int kk) {
+  const uint32_t start = (uint32_t)(desc & 0x3fff) << 4, lbo = (uint32_t)((desc >> 16) & 0x3fff) << 4, sbo = (uint32_t)((desc >> 32) & 0x3fff) << 4;
+  const int es = 16 / T;
+  const uint32_t off = mn_major ? (kk / 8) * lbo + (r / T) * sbo + (kk % 8) * 16 + (r % T) * es
+                                : (kk / T) * lbo + (r / 8) * sbo + (r % 8) * 16 + (kk % T) * es;
+  if (start + off + es > (uint32_t)((M + N) * K * 4)) return NAN;   // outside the operand images
+  if (T == 8) {
+    unsigned short h;
+    memcpy(&h, smem + start + off, 2);
+    const uint32_t u = (uint32_t)h << 16;
+    float x;
+    memcpy(&x, &u, 4);
+    return x;
+  }
+  float x;
+  memcpy(&x, smem + start + off, 4);
+  return x;
+}
+
+int main() {
+  float *hA = (float*)malloc(M * K * 4), *hB = (float*)malloc(N * K * 4);
+  srand(7);
+  for (int i = 0; i < M * K; ++i) hA[i] = tf32_round((float)rand() / RAND_MAX - 0.5f);
+  for (int i = 0; i < N * K; ++i) hB[i] = tf32_round((float)rand() / RAND_MAX - 0.5f);
+  uint8_t* smem = (uint8_t*)malloc((M + N) * K * 4);
+  int bad = 0;
+  for (int bf = 0; bf < 2; ++bf)
+    for (int swap = 0; swap < 2; ++swap)
+      for (int am = 0; am < 3; ++am)
+        for (int bm = 0; bm < 2; ++bm) {
+          Variant v{am, bm, swap, bf};
+          const int T = bf ? 8 : 4;
+          memset(smem, 0xff, (M + N) * K * 4);
+          uint8_t *sA = smem, *sB = smem + M * K * 4;
+          for (int e = 0; e < M * K; ++e) stage_element(v, 0, sA, e / K, e % K, hA[e]);
+          for (int e = 0; e < N * K; ++e) stage_element(v, 1, sB, e / K, e % K, hB[e]);
+          const uint32_t idesc = instr_desc(v);
+          const bool a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
+          double max_err = 0;
+          for (int m = 0; m < M; ++m)
+            for (int n = 0; n < N; ++n) {
+              double s = 0, ref = 0;
+              for (int ks = 0; ks < K / (2 * T); ++ks) {
+                const uint64_t da = operand_desc(v, 0, 0, ks, T), db = operand_desc(v, 1, M * K * 4, ks, T);
+                for (int kk = 0; kk < 2 * T; ++kk)
+                  s += (double)model_operand(smem, da, a_mn, T, m, kk) * (double)model_operand(smem, db, b_mn, T, n, kk);
+              }
+              for (int k = 0; k < K; ++k) ref += (double)hA[m * K + k] * hB[n * K + k];
+              const double d = fabs(s - ref);
+              if (!(d <= max_err)) max_err = d;
+            }
+          const bool ok = max_err < 1e-4;
+          // as read: must reproduce the product.  exchanged: must not (else the experiment could not tell the readings apart)
+          const bool expected = swap == 0;
+          printf("%-16s A %s, B %s, %-18s : model %s (max abs err %.3e)%s\n", bf ? "kind::f16 (bf16)" : "kind::tf32",
+                 am == 1 ? "MN" : (am ? "Kb" : "K "), bm ? "MN" : "K ", swap ? "LBO/SBO exchanged" : "LBO/SBO as read", ok ? "PASS" : "FAIL",
+                 max_err, ok == expected ? "" : "   <-- UNEXPECTED");
+          bad += ok != expected;
+        }
+  printf("%d unexpected\n", bad);
+  return bad ? 1 : 0;
+}
+#else
 int main() {
   float *hA = (float*)malloc(M * K * 4), *hB = (float*)malloc(N * K * 4), *hD = (float*)malloc(M * N * 4), *ref = (float*)malloc(M * N * 4);
   srand(7);
@@ -211,8 +298,10 @@ int main() {
   cudaFuncSetAttribute(umma_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int n_pass = 0;
   bool pass[2][2][3][2] = {};   // [dtype][field assignment][A layout][B layout]
-  for (int bf = 0; bf < 2; ++bf)
+  // every "as read" variant first (tf32, then bf16): an exchanged descriptor may address memory outside the operands, and a
+  // sticky CUDA error would end the run before the variants that matter
   for (int swap = 0; swap < 2; ++swap)
+  for (int bf = 0; bf < 2; ++bf)
     for (int am = 0; am < 3; ++am)
       for (int bm = 0; bm < 2; ++bm) {
         Variant v{am, bm, swap, bf};
@@ -252,3 +341,4 @@ int main() {
   }
   return 0;
 }
+#endif  // UBENCH_HOST_MODEL

@@ -149,7 +149,7 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
   emu::umma_bf16(tmem_d, da, db, idesc, accumulate);
 }
-__device__ __forceinline__ void commit(uint64_t* bar) { emu::mbar_arrive(bar); }
+__device__ __forceinline__ void commit(uint64_t* bar) { emu::tc_commit(bar); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) { emu::tmem_ld(taddr, r, 16); }
 __device__ __forceinline__ void tmem_ld_wait() {}
 #else

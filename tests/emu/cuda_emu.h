@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <unordered_map>
 #include <vector>
@@ -84,6 +85,10 @@ struct Cta {
   std::unordered_map<const void*, MBar> mbars;
   std::vector<uint32_t> tmem;   // tensor memory: 128 lanes x 512 columns of 32 bits, allocated on first tcgen05 use
   unsigned tmem_next = 0;       // bump allocator (columns)
+  // the tensor core works ASYNCHRONOUSLY: tcgen05.mma / tcgen05.commit are queued at issue and executed in order, one item at a
+  // time, while the scheduler runs other fibers -- operands are read and the accumulator is written when the item executes
+  std::deque<std::function<void(Cta&)>> tc_queue;
+  unsigned tc_delay = 0;
 };
 
 struct Fiber {
@@ -205,28 +210,33 @@ inline uint32_t tmem_alloc(unsigned ncols) {
   return base;
 }
 inline void tmem_dealloc(uint32_t, unsigned ncols) { cta().tmem_next -= ncols; }
-inline uint32_t& tmem_at(uint32_t taddr, unsigned lane, unsigned col) {
+inline uint32_t& tmem_at(Cta& k, uint32_t taddr, unsigned lane, unsigned col) {
   const unsigned l = (taddr >> 16) + lane, c = (taddr & 0xffffu) + col;
-  if (l >= kTmemLanes || c >= kTmemCols) { std::fprintf(stderr, "cuda_emu: tensor memory access out of range\n"); std::abort(); }
-  return cta().tmem[(size_t)l * kTmemCols + c];
+  if (l >= kTmemLanes || c >= kTmemCols || k.tmem.empty()) { std::fprintf(stderr, "cuda_emu: tensor memory access out of range\n"); std::abort(); }
+  return k.tmem[(size_t)l * kTmemCols + c];
 }
-inline float umma_operand(uint64_t desc, bool mn_major, unsigned r, unsigned k) {
+inline uint32_t& tmem_at(uint32_t taddr, unsigned lane, unsigned col) { return tmem_at(cta(), taddr, lane, col); }
+inline const char* smem_at(Cta& k, uint32_t addr, unsigned bytes) {
+  if ((size_t)addr + bytes > k.smem_bytes) { std::fprintf(stderr, "cuda_emu: tcgen05 operand read outside shared memory\n"); std::abort(); }
+  return k.dyn_smem.data() + addr;
+}
+inline float umma_operand(Cta& c, uint64_t desc, bool mn_major, unsigned r, unsigned k) {
   const uint32_t start = (uint32_t)(desc & 0x3fffu) << 4, lbo = (uint32_t)((desc >> 16) & 0x3fffu) << 4,
                  sbo = (uint32_t)((desc >> 32) & 0x3fffu) << 4;
   const uint32_t off = mn_major ? (k / 8) * lbo + (r / 4) * sbo + (k % 8) * 16 + (r % 4) * 4
                                 : (k / 4) * lbo + (r / 8) * sbo + (r % 8) * 16 + (k % 4) * 4;
   uint32_t u;
-  std::memcpy(&u, smem_ptr(start + off), 4);
+  std::memcpy(&u, smem_at(c, start + off, 4), 4);
   return as_float(u & 0xffffe000u);
 }
 // 16-bit operands (8 elements per 16-byte chunk): the same canonical layouts with T = 8
-inline float umma_operand_bf16(uint64_t desc, bool mn_major, unsigned r, unsigned k) {
+inline float umma_operand_bf16(Cta& c, uint64_t desc, bool mn_major, unsigned r, unsigned k) {
   const uint32_t start = (uint32_t)(desc & 0x3fffu) << 4, lbo = (uint32_t)((desc >> 16) & 0x3fffu) << 4,
                  sbo = (uint32_t)((desc >> 32) & 0x3fffu) << 4;
   const uint32_t off = mn_major ? (k / 8) * lbo + (r / 8) * sbo + (k % 8) * 16 + (r % 8) * 2
                                 : (k / 8) * lbo + (r / 8) * sbo + (r % 8) * 16 + (k % 8) * 2;
   uint16_t h;
-  std::memcpy(&h, smem_ptr(start + off), 2);
+  std::memcpy(&h, smem_at(c, start + off, 2), 2);
   return as_float((uint32_t)h << 16);
 }
 // tcgen05.mma.cta_group::1.kind::f16 with BF16 operands: D[M x N] (+)= A[M x 16] * B[N x 16]^T, fp32 accumulation
@@ -238,15 +248,17 @@ inline void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_
     std::fprintf(stderr, "cuda_emu: only M = 128, F32 accumulate, BF16 operands are modelled for kind::f16 (idesc %08x)\n", idesc);
     std::abort();
   }
-  for (unsigned m = 0; m < M; ++m)
-    for (unsigned n = 0; n < N; ++n) {
-      double s = 0;
-      for (unsigned k = 0; k < 16; ++k)
-        s += (double)umma_operand_bf16(desc_a, a_mn, m, k) * (double)umma_operand_bf16(desc_b, b_mn, n, k);
-      uint32_t& d = tmem_at(tmem_d, m, n);
-      const float r = (accumulate ? as_float(d) : 0.f) + (float)s;
-      std::memcpy(&d, &r, 4);
-    }
+  cta().tc_queue.push_back([=](Cta& c) {
+    for (unsigned m = 0; m < M; ++m)
+      for (unsigned n = 0; n < N; ++n) {
+        double s = 0;
+        for (unsigned k = 0; k < 16; ++k)
+          s += (double)umma_operand_bf16(c, desc_a, a_mn, m, k) * (double)umma_operand_bf16(c, desc_b, b_mn, n, k);
+        uint32_t& d = tmem_at(c, tmem_d, m, n);
+        const float r = (accumulate ? as_float(d) : 0.f) + (float)s;
+        std::memcpy(&d, &r, 4);
+      }
+  });
 }
 // tcgen05.mma.cta_group::1.kind::tf32: D[M x N] (+)= A[M x 8] * B[N x 8]^T
 inline void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
@@ -257,14 +269,39 @@ inline void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_
     std::fprintf(stderr, "cuda_emu: only M = 128, F32 accumulate, TF32 operands are modelled (idesc %08x)\n", idesc);
     std::abort();
   }
-  for (unsigned m = 0; m < M; ++m)
-    for (unsigned n = 0; n < N; ++n) {
-      double s = 0;
-      for (unsigned k = 0; k < 8; ++k) s += (double)umma_operand(desc_a, a_mn, m, k) * (double)umma_operand(desc_b, b_mn, n, k);
-      uint32_t& d = tmem_at(tmem_d, m, n);
-      const float r = (accumulate ? as_float(d) : 0.f) + (float)s;
-      std::memcpy(&d, &r, 4);
+  cta().tc_queue.push_back([=](Cta& c) {
+    for (unsigned m = 0; m < M; ++m)
+      for (unsigned n = 0; n < N; ++n) {
+        double s = 0;
+        for (unsigned k = 0; k < 8; ++k)
+          s += (double)umma_operand(c, desc_a, a_mn, m, k) * (double)umma_operand(c, desc_b, b_mn, n, k);
+        uint32_t& d = tmem_at(c, tmem_d, m, n);
+        const float r = (accumulate ? as_float(d) : 0.f) + (float)s;
+        std::memcpy(&d, &r, 4);
+      }
+  });
+}
+// tcgen05.commit: the mbarrier arrive happens when every MMA queued before it has executed
+inline void tc_commit(const void* bar) {
+  cta().tc_queue.push_back([=](Cta& c) {
+    MBar& m = c.mbars[bar];
+    --m.pending;
+    m.check();
+  });
+}
+// one step of every CTA's tensor core: called by the scheduler between fiber slices
+inline void tc_tick(std::vector<Cta>& ctas, uint64_t& rng) {
+  for (Cta& c : ctas) {
+    if (c.tc_queue.empty()) continue;
+    if (c.tc_delay > 0) { --c.tc_delay; continue; }
+    auto op = std::move(c.tc_queue.front());
+    c.tc_queue.pop_front();
+    op(c);
+    if (rng) {
+      rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+      c.tc_delay = (unsigned)(rng % 5);    // seeded schedules: completion times vary
     }
+  }
 }
 // tcgen05.ld.sync.aligned.32x32b.xN: thread `lane` of warp w gets N consecutive columns of TMEM lane 32*(w%4) + lane
 inline void tmem_ld(uint32_t taddr, uint32_t* out, unsigned n) {
@@ -352,9 +389,16 @@ inline void run_ctas(const std::vector<std::pair<int, unsigned>>& which) {
       gridDim = {L.grid.x, L.grid.y, L.grid.z};
       swapcontext(&s.sched, &f.ctx);
       if (f.done) { --remaining; rounds = 0; }
+      tc_tick(s.ctas, rng);
     }
   }
   s.current = -1;
+  for (Cta& k : s.ctas)      // MMAs nobody waited for still complete on the hardware
+    while (!k.tc_queue.empty()) {
+      auto op = std::move(k.tc_queue.front());
+      k.tc_queue.pop_front();
+      op(k);
+    }
   for (const Cta& k : s.ctas)
     for (size_t g = k.smem_bytes; g < k.smem_bytes + kGuardBytes; ++g)
       if (k.dyn_smem[g] != (char)0xCD) {

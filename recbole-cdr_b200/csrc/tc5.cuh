@@ -136,11 +136,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { emu:
 __device__ __forceinline__ void fence_proxy_async() {}
 __device__ __forceinline__ void fence_before_sync() {}
 __device__ __forceinline__ void fence_after_sync() {}
-// warp-collective on the hardware (one allocation per warp): lane 0 acts for the warp here
+// warp-collective on the hardware (.sync.aligned: the whole warp must execute it together, one allocation per warp): every
+// lane joins a warp rendezvous -- a lane that never arrives shows up as a deadlock -- and lane 0 acts for the warp
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  emu::warp_barrier();
   if ((threadIdx.x & 31) == 0) *dst_smem = emu::tmem_alloc(ncols);
+  emu::warp_barrier();
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  emu::warp_barrier();
   if ((threadIdx.x & 31) == 0) emu::tmem_dealloc(taddr, ncols);
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
@@ -150,7 +154,10 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t 
   emu::umma_bf16(tmem_d, da, db, idesc, accumulate);
 }
 __device__ __forceinline__ void commit(uint64_t* bar) { emu::tc_commit(bar); }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) { emu::tmem_ld(taddr, r, 16); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  emu::warp_barrier();   // .sync.aligned: all 32 lanes of the warp execute the load together
+  emu::tmem_ld(taddr, r, 16);
+}
 __device__ __forceinline__ void tmem_ld_wait() {}
 #else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -133,7 +133,7 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { emu::
 __device__ __forceinline__ void mbar_init_fence() {}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { emu::mbar_arrive(bar); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { emu::mbar_wait(bar, parity); }
-__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void fence_proxy_async() { emu::proxy_fence(); }
 __device__ __forceinline__ void fence_before_sync() {}
 __device__ __forceinline__ void fence_after_sync() {}
 // warp-collective on the hardware (.sync.aligned: the whole warp must execute it together, one allocation per warp): every

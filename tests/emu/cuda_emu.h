@@ -89,6 +89,9 @@ struct Cta {
   // time, while the scheduler runs other fibers -- operands are read and the accumulator is written when the item executes
   std::deque<std::function<void(Cta&)>> tc_queue;
   unsigned tc_delay = 0;
+  // what the tensor core (async proxy) sees of shared memory: the image as of the last fence.proxy.async executed by a thread
+  // of the CTA.  Generic-proxy stores that no such fence followed are NOT visible to tcgen05.mma operand reads.
+  std::vector<char> smem_async;
 };
 
 struct Fiber {
@@ -218,7 +221,18 @@ inline uint32_t& tmem_at(Cta& k, uint32_t taddr, unsigned lane, unsigned col) {
 inline uint32_t& tmem_at(uint32_t taddr, unsigned lane, unsigned col) { return tmem_at(cta(), taddr, lane, col); }
 inline const char* smem_at(Cta& k, uint32_t addr, unsigned bytes) {
   if ((size_t)addr + bytes > k.smem_bytes) { std::fprintf(stderr, "cuda_emu: tcgen05 operand read outside shared memory\n"); std::abort(); }
-  return k.dyn_smem.data() + addr;
+  if (k.smem_async.empty()) {
+    std::fprintf(stderr, "cuda_emu: tcgen05.mma reads shared memory, but no thread of the CTA executed fence.proxy.async\n");
+    std::abort();
+  }
+  return k.smem_async.data() + addr;
+}
+// fence.proxy.async.shared::cta: this thread's earlier generic-proxy writes become visible to the async proxy.  Modelled per
+// CTA: the tensor core's view of shared memory is refreshed (writes by threads that fence later are included early -- the
+// model errs on the permissive side; writes followed by NO fence before the MMAs execute are caught).
+inline void proxy_fence() {
+  Cta& k = cta();
+  k.smem_async.assign(k.dyn_smem.begin(), k.dyn_smem.begin() + (long)k.smem_bytes);
 }
 inline float umma_operand(Cta& c, uint64_t desc, bool mn_major, unsigned r, unsigned k) {
   const uint32_t start = (uint32_t)(desc & 0x3fffu) << 4, lbo = (uint32_t)((desc >> 16) & 0x3fffu) << 4,

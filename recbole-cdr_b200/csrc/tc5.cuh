@@ -158,7 +158,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   emu::warp_barrier();   // .sync.aligned: all 32 lanes of the warp execute the load together
   emu::tmem_ld(taddr, r, 16);
 }
-__device__ __forceinline__ void tmem_ld_wait() {}
+__device__ __forceinline__ void tmem_ld_wait() { emu::tmem_ld_wait(); }
 #else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

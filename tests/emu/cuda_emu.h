@@ -99,6 +99,7 @@ struct Fiber {
   char* stack = nullptr;
   bool done = false;
   unsigned tid = 0, cta = 0;
+  std::vector<std::pair<uint32_t*, uint32_t>> tmem_pending;   // tcgen05.ld results not yet released by tcgen05.wait::ld
 };
 
 struct State {
@@ -318,9 +319,19 @@ inline void tc_tick(std::vector<Cta>& ctas, uint64_t& rng) {
   }
 }
 // tcgen05.ld.sync.aligned.32x32b.xN: thread `lane` of warp w gets N consecutive columns of TMEM lane 32*(w%4) + lane
+// The destination registers are only defined after tcgen05.wait::ld: until then they hold poison.
 inline void tmem_ld(uint32_t taddr, uint32_t* out, unsigned n) {
   const unsigned lane = threadIdx_lane_for_tmem();
-  for (unsigned j = 0; j < n; ++j) out[j] = tmem_at(taddr, lane, j);
+  Fiber& f = self();
+  for (unsigned j = 0; j < n; ++j) {
+    f.tmem_pending.emplace_back(out + j, tmem_at(taddr, lane, j));
+    out[j] = 0x7fc0dead;   // a NaN
+  }
+}
+inline void tmem_ld_wait() {
+  Fiber& f = self();
+  for (auto& pv : f.tmem_pending) *pv.first = pv.second;
+  f.tmem_pending.clear();
 }
 
 }  // namespace emu

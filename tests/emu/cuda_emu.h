@@ -89,6 +89,8 @@ struct Cta {
   // time, while the scheduler runs other fibers -- operands are read and the accumulator is written when the item executes
   std::deque<std::function<void(Cta&)>> tc_queue;
   unsigned tc_delay = 0;
+  std::deque<std::function<void(Cta&)>> dma_queue;   // bulk copies in flight (cp.async.bulk), completed in issue order
+  unsigned dma_delay = 0;
   // what the tensor core (async proxy) sees of shared memory: the image as of the last fence.proxy.async executed by a thread
   // of the CTA.  Generic-proxy stores that no such fence followed are NOT visible to tcgen05.mma operand reads.
   std::vector<char> smem_async;
@@ -188,9 +190,15 @@ inline bool mbar_test(const void* bar, uint32_t parity) { return cta().mbars[bar
 inline void mbar_wait(const void* bar, uint32_t parity) {
   while (!mbar_test(bar, parity)) yield();
 }
+// cp.async.bulk (global -> shared, mbarrier completion): the copy engine is asynchronous too -- the bytes land, and the
+// barrier's transaction count drops, some scheduler slices after the issue (same queue discipline as the tensor core)
 inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, const void* bar) {
-  std::memcpy(dst, src, bytes);
-  mbar_complete_tx(bar, bytes);
+  cta().dma_queue.push_back([=](Cta& c) {
+    std::memcpy(dst, src, bytes);
+    MBar& m = c.mbars[bar];
+    m.tx -= bytes;
+    m.check();
+  });
 }
 
 // ---- tcgen05 / TMEM model -------------------------------------------------------------------------------------------------
@@ -307,6 +315,19 @@ inline void tc_commit(const void* bar) {
 // one step of every CTA's tensor core: called by the scheduler between fiber slices
 inline void tc_tick(std::vector<Cta>& ctas, uint64_t& rng) {
   for (Cta& c : ctas) {
+    if (!c.dma_queue.empty()) {
+      if (c.dma_delay > 0) {
+        --c.dma_delay;
+      } else {
+        auto op = std::move(c.dma_queue.front());
+        c.dma_queue.pop_front();
+        op(c);
+        if (rng) {
+          rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+          c.dma_delay = (unsigned)(rng % 7);
+        }
+      }
+    }
     if (c.tc_queue.empty()) continue;
     if (c.tc_delay > 0) { --c.tc_delay; continue; }
     auto op = std::move(c.tc_queue.front());
@@ -418,12 +439,18 @@ inline void run_ctas(const std::vector<std::pair<int, unsigned>>& which) {
     }
   }
   s.current = -1;
-  for (Cta& k : s.ctas)      // MMAs nobody waited for still complete on the hardware
+  for (Cta& k : s.ctas) {    // copies / MMAs nobody waited for still complete on the hardware
+    while (!k.dma_queue.empty()) {
+      auto op = std::move(k.dma_queue.front());
+      k.dma_queue.pop_front();
+      op(k);
+    }
     while (!k.tc_queue.empty()) {
       auto op = std::move(k.tc_queue.front());
       k.tc_queue.pop_front();
       op(k);
     }
+  }
   for (const Cta& k : s.ctas)
     for (size_t g = k.smem_bytes; g < k.smem_bytes + kGuardBytes; ++g)
       if (k.dyn_smem[g] != (char)0xCD) {

@@ -8,6 +8,7 @@
 #include "../../recbole-cdr_b200/csrc/tc_mlp.cu"
 #include "../../recbole-cdr_b200/csrc/tc_conet.cu"
 #include "../../recbole-cdr_b200/csrc/sparse_optim.cu"
+#include "../../recbole-cdr_b200/csrc/tc5.cuh"
 
 #include <cstdarg>
 
@@ -123,6 +124,60 @@ int emu_conet_step(int n_layers, const int* dims, const float* const* Ws, const 
   const int64_t n_tiles = (batch + kCnTR - 1) / kCnTR;
   const unsigned grid = (unsigned)std::min<int64_t>(g_sms, n_tiles);
   emu::launch(grid, kTcThreads, smem, [&] { tc_conet_kernel(a, Workspace(ws)); });
+  return 0;
+}
+
+
+// ---- a deliberately breakable tcgen05 kernel: proves that the emulator's asynchronous model catches protocol mistakes -------------
+// D[128 x 16] = A[128 x 16] B[16 x 16]^T (bf16 K-major planes, one kind::f16 MMA).  fault: 0 none; 1 tensor memory read without
+// waiting for the commit; 2 operand stores not followed by fence.proxy.async; 3 tcgen05.ld results used before tcgen05.wait::ld;
+// 4 the A plane refilled (stores + fence) right after the issue, before the MMA has run.
+static void async_probe_kernel(const float* A, const float* B, float* D, int fault) {
+  XDR_DYN_SMEM_ALIGNED(unsigned char, sm, 128);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm);
+  uint32_t* tbase = reinterpret_cast<uint32_t*>(sm + 8);
+  unsigned char *ah = sm + 128, *al = ah + 128 * 16 * 2, *bh = al + 128 * 16 * 2, *bl = bh + 16 * 16 * 2;
+  const tc5::KMajor16 ka{128}, kb{16};
+  if (fault == 2) tc5::fence_proxy_async();    // a fence BEFORE the stores does not publish them
+  for (int e = tid; e < 128 * 2; e += 128)
+    tc5::store_split8(ah, al, ka.chunk_offset(e / 2, e % 2), *reinterpret_cast<const float4*>(A + (e / 2) * 16 + 8 * (e % 2)),
+                      *reinterpret_cast<const float4*>(A + (e / 2) * 16 + 8 * (e % 2) + 4));
+  for (int e = tid; e < 16 * 2; e += 128)
+    tc5::store_split8(bh, bl, kb.chunk_offset(e / 2, e % 2), *reinterpret_cast<const float4*>(B + (e / 2) * 16 + 8 * (e % 2)),
+                      *reinterpret_cast<const float4*>(B + (e / 2) * 16 + 8 * (e % 2) + 4));
+  if (tid == 0) { tc5::mbar_init(bar, 1); tc5::mbar_init_fence(); }
+  if (warp == 0) tc5::tmem_alloc(tbase, 32);
+  if (fault != 2) tc5::fence_proxy_async();
+  tc5::fence_before_sync();
+  __syncthreads();
+  tc5::fence_after_sync();
+  const uint32_t tmem = *tbase;
+  if (tid == 0) {
+    tc5::mma_bf16x3(tmem, tc5::smem_u32(ah), tc5::smem_u32(al), ka, tc5::smem_u32(bh), tc5::smem_u32(bl), kb,
+                    tc5::make_idesc_bf16(128, 16, false, false), 16, false);
+    tc5::commit(bar);
+    if (fault == 4) {   // the buffer is refilled (stores + fence, as a real reuse would do) without waiting for the MMA that reads it
+      std::memset(ah, 0, 128 * 16 * 2);
+      tc5::fence_proxy_async();
+    }
+  }
+  if (fault != 1) tc5::mbar_wait(bar, 0);
+  tc5::fence_after_sync();
+  uint32_t r[16];
+  tc5::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), r);
+  if (fault != 3) tc5::tmem_ld_wait();
+  for (int j = 0; j < 16; ++j) D[tid * 16 + j] = __uint_as_float(r[j]);
+  tc5::tmem_ld_wait();
+  if (fault == 1) tc5::mbar_wait(bar, 0);
+  tc5::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc5::tmem_dealloc(tmem, 32);
+}
+
+int emu_async_probe(const float* A, const float* B, float* D, int fault) {
+  const size_t smem = 128 + 2 * 128 * 16 * 2 + 2 * 16 * 16 * 2;
+  emu::launch(1, 128, smem, [&] { async_probe_kernel(A, B, D, fault); });
   return 0;
 }
 

@@ -17,7 +17,7 @@ if [ "$STAGE" = validate ] || [ "$STAGE" = all ]; then
   # then the memory checker, the parity tests of the new kernels, and the regular gpu suite last (the driver re-runs it anyway)
   # the standalone descriptor experiment (24 variants, one CTA each)
   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -lineinfo -o /tmp/ubench_tcgen05 scripts/ubench_tcgen05.cu > gpurun_out/tcgen05.log 2>&1 \
-      && timeout 120 /tmp/ubench_tcgen05 >> gpurun_out/tcgen05.log 2>&1
+      && timeout 300 /tmp/ubench_tcgen05 >> gpurun_out/tcgen05.log 2>&1
   say "ubench_tcgen05 rc=$?"
   # the tcgen05 top-k kernel on its own, under a short timeout (a wrong descriptor reading gives wrong numbers, a wrong
   # barrier protocol would hang: keep it away from the other tests)

@@ -289,6 +289,18 @@ def build_f4(model_cls, g, cfg, with_edges=False):
     return m.to('cuda')
 
 
+def check_full_sort_gpu(m, g):
+    """full_sort_predict (and the fused full_sort_topk where the model has one) against the reference's scores."""
+    import variants_util as V
+    if not g.has('full_sort_predict'):
+        return
+    with torch.no_grad():
+        got = m.full_sort_predict(V.batch(g, 'cuda', 'fbatch/'))
+    torch.testing.assert_close(got.cpu().reshape(-1), g.t('full_sort_predict').reshape(-1), rtol=1e-4, atol=2e-6)
+    if hasattr(m, 'full_sort_topk'):
+        V.check_topk_against_reference(m, g, 'cuda')
+
+
 def test_f4_clfm():
     from recbole_cdr_b200.model.cross_domain_recommender.clfm import CLFM
     g = Golden('f4_clfm')
@@ -297,6 +309,7 @@ def test_f4_clfm():
     batch = cuda_batch(g)
     check_loss_and_grads(m, g, batch, grad_rtol=2e-4, grad_atol=2e-6)
     torch.testing.assert_close(m.predict(batch).cpu(), g.t('predict'), rtol=1e-5, atol=1e-6)
+    check_full_sort_gpu(m, g)
 
 
 @pytest.mark.parametrize('tag', ['users', 'items'])
@@ -318,6 +331,7 @@ def test_f4_sscdr(case, phase):
     if g.has('meta/np_seed'):
         np.random.seed(g.meta('np_seed'))
     check_loss_and_grads(m, g, cuda_batch(g), grad_rtol=2e-4, grad_atol=2e-6)
+    check_full_sort_gpu(m, g)
 
 
 @pytest.mark.parametrize('tag', ['items', 'users'])
@@ -344,6 +358,7 @@ def test_f4_dcdcsr_four_stages(tag):
     g = Golden(f'f4_dcdcsr_{tag}_target1')
     m.set_phase('TARGET')
     check_loss_and_grads(m, g, cuda_batch(g))
+    check_full_sort_gpu(m, g)
     g = Golden(f'f4_dcdcsr_{tag}_both')
     m.set_phase('BOTH')
     torch.testing.assert_close(m.benchmark_embedding.cpu(), g.t('benchmark_embedding'), rtol=1e-4, atol=1e-6)
@@ -353,6 +368,7 @@ def test_f4_dcdcsr_four_stages(tag):
     m.set_phase('TARGET')
     torch.testing.assert_close(m.affine_embedding.cpu(), g.t('affine_embedding'), rtol=1e-4, atol=1e-6)
     check_loss_and_grads(m, g, cuda_batch(g))
+    check_full_sort_gpu(m, g)
 
 
 def test_device_pipeline_with_row_sparse_adagrad_equals_dense_torch_adagrad():

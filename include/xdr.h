@@ -295,7 +295,14 @@ XDR_API int xdr_select_dot(const float* mapped, const float* tgt_tab, int64_t n_
  * Restrictions (else XDR_ERR_UNSUPPORTED: use the per-step entry points): batch % 4 == 0, step_stride % 4 == 0,
  * id arrays 16-byte aligned, and at most 40 warp tasks per CTA per step, i.e. ceil(batch / #SMs) <= 160 at dim <= 64
  * (batch <= 23680 on a 148-SM part; rows live in registers, two tasks in flight per warp).
- * steps_ws: xdr_steps_workspace_bytes(n_steps) bytes of scratch (no initialisation needed).                         */
+ * steps_ws: xdr_steps_workspace_bytes(n_steps) bytes of scratch.  No initialisation needed: the library zeroes it the
+ * first time it sees the pointer; after that the hand-off words carry step tags that grow from launch to launch, so the
+ * caller must leave its contents alone between launches (pass a different pointer after writing to it).
+ * Launch: all CTAs of these kernels wait for each other, so the grid must be co-resident.  The library checks
+ * occupancy x #SMs >= grid before the launch (XDR_ERR_UNSUPPORTED) and launches with cudaLaunchCooperativeKernel (the
+ * driver then starts the grid only when every CTA fits, whatever else runs on the device); xdr_set_coop_launch(0)
+ * falls back to plain launches (returns the previous setting).                                                       */
+XDR_API int xdr_set_coop_launch(int on);
 XDR_API size_t xdr_steps_workspace_bytes(int n_steps);
 XDR_API int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
                             const int64_t* user, const int64_t* item_a, const int64_t* item_b, const float* label,

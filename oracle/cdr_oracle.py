@@ -43,7 +43,7 @@ def emb_loss(*embeddings: Tensor) -> Tensor:
 
     Call sites: emcdr.py:119,129,142,152; cmf.py:94-98; bitgcf.py:233,245.
     """
-    acc = torch.zeros(1, dtype=embeddings[-1].dtype)
+    acc = torch.zeros(1, dtype=embeddings[-1].dtype, device=embeddings[-1].device)
     for e in embeddings:
         acc = acc + torch.norm(e, p=2)
     return acc / embeddings[-1].shape[0]

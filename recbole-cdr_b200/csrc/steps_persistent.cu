@@ -34,6 +34,8 @@
 //
 // HBM roofline: 1560 algorithmic bytes per BPR interaction at dim 64 (ids + 3 rows gathered + 3 rows scattered).
 #include <string.h>
+#include <mutex>
+#include <vector>
 #include "xdr_common.cuh"
 
 namespace xdr {
@@ -76,7 +78,9 @@ struct StepsArgs {
   float* out8;  // [n_steps, 8]
   const float* grad_loss;
   float scale;
-  unsigned long long* words;  // [n_steps][gridDim.x][3] partials then [n_steps][2] results, {fp32, step tag}; host-zeroed
+  unsigned long long* words;  // [n_steps][gridDim.x][3] partials then [n_steps][2] results, {fp32, step tag}
+  unsigned int tag_base;      // step s carries tag tag_base + s + 1: tags grow from launch to launch on one workspace, so a
+                              // word left by an earlier launch can never match and the workspace needs no per-launch zeroing
   int slice;                  // S: interactions per CTA per step (multiple of 4)
   int32_t* oob;
   unsigned long long* trace;  // optional [n_steps][grid][8] globaltimer stamps (debug; NULL in production)
@@ -246,7 +250,7 @@ __device__ __forceinline__ void service_publisher(const StepsArgs& a, const Smem
     if (lane < 3) {
       const float v = lane == 0 ? p0 : (lane == 1 ? p1 : p2);
       st_relaxed_u64(a.words + ((size_t)s * n_cta + blockIdx.x) * 3 + lane,
-                     ((unsigned long long)(unsigned int)(s + 1) << 32) | (unsigned long long)__float_as_uint(v));
+                     ((unsigned long long)(a.tag_base + (unsigned int)(s + 1)) << 32) | (unsigned long long)__float_as_uint(v));
     }
     __syncwarp();
   }
@@ -260,7 +264,7 @@ __device__ __forceinline__ void service_gatherer(const StepsArgs& a, const Bars&
   unsigned long long* finals = a.words + (size_t)a.n_steps * n_cta * 3;  // [n_steps][2] {factor, tag}
   for (int s = which; s < a.n_steps; s += 2) {
     const int slot = s % kRing;
-    const unsigned int tag = (unsigned int)(s + 1);
+    const unsigned int tag = a.tag_base + (unsigned int)(s + 1);
     float cu = 0.f, ci = 0.f;
     if ((unsigned int)s % n_cta == blockIdx.x) {
       const unsigned long long* base = a.words + (size_t)s * n_cta * 3;
@@ -767,19 +771,15 @@ template <int LPR, int VEC, bool PW>
 static int launch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_t s) {
   if (plan.stages > 0 && a.stage_a != nullptr) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsLite>;
-    XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsLite), plan.smem, s, a, plan.stages);
   } else if (plan.stages > 0 && g_early_scatter && a.reg_weight == 0.f) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull, true>;
-    XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s, a, plan.stages);
   } else if (plan.stages > 0) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull>;
-    XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s, a, plan.stages);
   } else {
     auto kern = train_steps_regs_kernel<LPR, VEC, PW>;
-    XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     XDR_LAUNCH_COOP((kern), plan.grid, kRegThreads, plan.smem, s, a);
   }
   return XDR_OK;
@@ -792,6 +792,15 @@ static int dispatch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_
   if (plan.lpr == 16) return launch_steps<16, 2, PW>(a, plan, s);
   return launch_steps<32, 2, PW>(a, plan, s);
 }
+
+struct WsRecord {
+  int dev;
+  void* ptr;
+  size_t zeroed_bytes;     // prefix of the workspace this library has zeroed (and owns the tags of) since it first saw it
+  unsigned int next_tag;   // tags handed out so far
+};
+static std::mutex g_ws_mu;
+static std::vector<WsRecord> g_ws_seen;
 
 static unsigned long long* g_trace = nullptr;  // debug only, see xdr_debug_set_steps_trace
 static int g_force_regs = 0;                   // debug only: force the register kernel where both fit
@@ -869,8 +878,30 @@ static int train_steps_core(const Shards& user_tab, const Shards& item_tab, cons
   a.words = reinterpret_cast<unsigned long long*>(steps_ws);
   a.trace = g_trace;
   cudaStream_t s = (cudaStream_t)stream;
-  // step tags start at 1, so zeroed words can never match: no stale data from an earlier launch is ever accepted
-  XDR_CUDA_OK(cudaMemsetAsync(steps_ws, 0, (size_t)n_steps * ((size_t)plan.grid * 3 + 2) * sizeof(unsigned long long), s));
+  // Step tags grow from launch to launch on one workspace (tag_base + s + 1), so a word left behind by an earlier launch can
+  // never match: the workspace is zeroed only when the library sees it for the first time (or the 32-bit tags would wrap),
+  // not per launch.  The caller must not write to it between launches (xdr.h).
+  {
+    const size_t need = xdr_steps_workspace_bytes(n_steps);
+    int dev = 0;
+    XDR_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_ws_mu);
+    WsRecord* rec = nullptr;
+    for (auto& r : g_ws_seen)
+      if (r.dev == dev && r.ptr == steps_ws) rec = &r;
+    if (!rec) {
+      if (g_ws_seen.size() >= 64) g_ws_seen.clear();
+      g_ws_seen.push_back(WsRecord{dev, steps_ws, 0, 0});
+      rec = &g_ws_seen.back();
+    }
+    if (rec->zeroed_bytes < need || rec->next_tag > 0xf0000000u - (unsigned int)n_steps) {
+      XDR_CUDA_OK(cudaMemsetAsync(steps_ws, 0, need, s));
+      rec->zeroed_bytes = need;
+      rec->next_tag = 0;
+    }
+    a.tag_base = rec->next_tag;
+    rec->next_tag += (unsigned int)n_steps;
+  }
   const int rc = pairwise ? dispatch_steps<true>(a, plan, s) : dispatch_steps<false>(a, plan, s);
   if (rc != XDR_OK) return rc;
   XDR_LAUNCH_OK();

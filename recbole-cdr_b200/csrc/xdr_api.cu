@@ -1,6 +1,8 @@
 // xdr_api.cu -- library-level entry points: version, thread-local error text, device info.
 #include <stdarg.h>
 #include <string.h>
+#include <mutex>
+#include <vector>
 #include "xdr_common.cuh"
 
 namespace xdr {
@@ -28,9 +30,67 @@ int sm_count() {
   return cached_sms;
 }
 
+#ifndef XDR_EMU
+// ---- persistent (co-resident) launches: one-time kernel setup + residency check, cached per (kernel, device) ----------
+namespace {
+struct CoopEntry {
+  const void* kern;
+  int dev, block;
+  size_t smem_limit;   // dynamic shared-memory limit already set on the kernel
+  size_t smem_checked; // (block, smem) pair the occupancy was computed for
+  int ctas_per_sm;
+};
+std::mutex g_coop_mu;
+std::vector<CoopEntry> g_coop;
+int g_coop_enabled = 1;
+}  // namespace
+
+bool coop_enabled() { return g_coop_enabled != 0; }
+
+int coop_prepare(const void* kern, int grid, int block, size_t smem, const char* name) {
+  int dev = 0;
+  XDR_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_coop_mu);
+  CoopEntry* e = nullptr;
+  for (auto& c : g_coop)
+    if (c.kern == kern && c.dev == dev) e = &c;
+  if (!e) {
+    g_coop.push_back(CoopEntry{kern, dev, 0, 0, 0, 0});
+    e = &g_coop.back();
+  }
+  if (smem > e->smem_limit) {
+    XDR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    e->smem_limit = smem;
+  }
+  if (e->block != block || e->smem_checked != smem) {
+    int n = 0;
+    XDR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, block, smem));
+    e->block = block;
+    e->smem_checked = smem;
+    e->ctas_per_sm = n;
+  }
+  if ((long long)e->ctas_per_sm * sm_count() < grid) {
+    set_error("%s: a grid of %d CTAs (%d threads, %zu B shared memory) cannot be co-resident on this device (%d per SM x %d "
+              "SMs); its CTAs wait for each other, so it is not launched", name, grid, block, smem, e->ctas_per_sm, sm_count());
+    return XDR_ERR_UNSUPPORTED;
+  }
+  return XDR_OK;
+}
+#endif  // !XDR_EMU
+
 }  // namespace xdr
 
 extern "C" {
+
+#ifndef XDR_EMU
+// 1 (default): persistent kernels go through cudaLaunchCooperativeKernel (driver-guaranteed co-residency); 0: plain launches
+// (the static occupancy check still applies).  Returns the previous setting.
+int xdr_set_coop_launch(int on) {
+  const int prev = xdr::g_coop_enabled;
+  xdr::g_coop_enabled = on ? 1 : 0;
+  return prev;
+}
+#endif
 
 int xdr_version(void) { return XDR_VERSION; }
 

@@ -7,6 +7,10 @@
 #endif
 #include <stdint.h>
 #include <stdio.h>
+#ifndef XDR_EMU
+#include <tuple>
+#include <utility>
+#endif
 #include "../../include/xdr.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -43,6 +47,13 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 static inline bool dim_ok(int dim) { return dim > 0 && dim <= 256 && (dim % 4) == 0; }
 
 int sm_count();  // cached per process, defined in xdr_api.cu
+
+#ifndef XDR_EMU
+template <typename Tuple, size_t... I>
+static inline void fill_arg_ptrs(void** ptrs, Tuple& t, std::index_sequence<I...>) {
+  ((ptrs[I] = static_cast<void*>(&std::get<I>(t))), ...);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // workspace layout (xdr_workspace_bytes()): [0,64) tickets (uint32), then fp32 partial slots
@@ -233,13 +244,38 @@ __device__ __forceinline__ void grid_reduce_last_block(float (&v)[NV], Workspace
 #define XDR_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
 
-// Launch of a persistent kernel whose CTAs hand data to each other (all CTAs resident at once).  CUDA: a plain launch --
-// residency is the caller's business (grid <= #SMs); emulator: all CTAs run under one fiber scheduler.
+// Launch of a persistent kernel whose CTAs hand data to each other (all CTAs must be resident at once, or the ones that are
+// would poll for the ones that are not, forever).  CUDA: xdr::coop_launch -- (1) the dynamic shared-memory limit of the kernel is
+// raised once per kernel and device, not per call; (2) occupancy x #SMs >= grid is checked before the launch
+// (XDR_ERR_UNSUPPORTED, never a grid that cannot fit); (3) the launch itself is cudaLaunchCooperativeKernel, for which the
+// driver guarantees co-residency of the whole grid (it is started only when every CTA can be scheduled, whatever else is
+// running on the device), unless xdr_set_coop_launch(0) asked for plain launches.  Emulator: all CTAs under one fiber scheduler.
 #ifdef XDR_EMU
 #define XDR_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) \
   emu::launch(grid, block, smem, [=] { kernel(__VA_ARGS__); }, /*concurrent=*/true)  /* by value: may run deferred */
 #else
-#define XDR_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+int coop_prepare(const void* kern, int grid, int block, size_t smem, const char* name);  // xdr_api.cu (cached per kernel+device)
+bool coop_enabled();                                                                     // xdr_api.cu
+template <typename... KArgs, typename... Args>
+static inline int coop_launch(const char* name, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s,
+                              Args... args) {
+  const int rc = coop_prepare(reinterpret_cast<const void*>(kern), grid, block, smem, name);
+  if (rc != XDR_OK) return rc;
+  if (coop_enabled()) {
+    std::tuple<KArgs...> held(static_cast<KArgs>(args)...);
+    void* ptrs[sizeof...(KArgs)];
+    fill_arg_ptrs(ptrs, held, std::index_sequence_for<KArgs...>{});
+    XDR_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(block), ptrs, smem, s));
+  } else {
+    kern<<<grid, block, smem, s>>>(args...);
+  }
+  return XDR_OK;
+}
+#define XDR_LAUNCH_COOP(kernel, grid, block, smem, stream, ...)                                         \
+  do {                                                                                                  \
+    const int rc__ = xdr::coop_launch(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__);         \
+    if (rc__ != XDR_OK) return rc__;                                                                    \
+  } while (0)
 #endif
 
 // Dynamic shared memory of the CTA as `type* name` (CUDA: the extern __shared__ array; emulator: the CTA's heap block).

@@ -50,6 +50,7 @@ class FusedStepRunner:
         else:
             self.dev = torch.device(device)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.steps_kw = {}      # extra keyword arguments of ops.train_steps (e.g. the touch maps of lazily zeroed gradient tables)
         self.n_buffers = n_buffers
         self._bufs = []  # per in-flight chunk: (dev ids, dev label, out8, host loss, ready event, done event)
         self._turn = 0
@@ -58,15 +59,27 @@ class FusedStepRunner:
     def _buffers(self, shape, with_label):
         key = (tuple(shape), with_label)
         if not self._bufs or self._bufs[0]['key'] != key:
+            # The block shape changed (e.g. the short last chunk of an epoch).  Launches that read the old device buffers may
+            # still be queued on the main stream: keep the old buffers alive until their 'done' events have completed, and
+            # make the copy stream wait for everything the main stream has queued before it writes into freshly allocated
+            # memory (the caching allocator may hand out blocks whose last use is still in flight on the main stream).
+            main = torch.cuda.current_stream(self.dev)
+            self._retired = [b for b in getattr(self, '_retired', []) if b['used'] and not b['done'].query()]
+            self._retired += [b for b in self._bufs if b['used'] and not b['done'].query()]
+            self.copy_stream.wait_stream(main)
             self._bufs = []
             K = shape[0]
             for _ in range(self.n_buffers):
+                ids = torch.empty(shape, dtype=torch.int64, device=self.dev)
+                lab = torch.empty(shape, dtype=torch.float32, device=self.dev) if with_label else None
+                for t in (ids, lab):
+                    if t is not None:
+                        t.record_stream(self.copy_stream)   # written on the copy stream, read on the main stream
                 self._bufs.append({
-                    'key': key, 'ids': torch.empty(shape, dtype=torch.int64, device=self.dev),
+                    'key': key, 'ids': ids,
                     # the kernel walks ids and labels with ONE step stride: give the label rows the stride of the id rows
-                    'label': (torch.empty(shape, dtype=torch.float32, device=self.dev)[:, 0] if with_label else None),
+                    'label': (lab[:, 0] if with_label else None),
                     'out8': torch.empty((K, 8), dtype=torch.float32, device=self.dev),
-                    'loss': torch.empty(K, dtype=torch.float32).pin_memory(),
                     'ready': torch.cuda.Event(), 'done': torch.cuda.Event(), 'used': False})
         b = self._bufs[self._turn % self.n_buffers]
         self._turn += 1
@@ -94,12 +107,15 @@ class FusedStepRunner:
             ops.train_steps(self.ut.data, self.it.data, ids[:, 0], ids[:, 1], ids[:, 2] if sp['pairwise'] else None,
                             buf['label'], loss_kind=sp.get('loss_kind', _lib.LOSS_MSE), reg_weight=sp['reg_weight'],
                             gamma=sp.get('gamma', 1e-10), user_dst=self.dst_u, item_dst=self.dst_i, scale=self.scale,
-                            out8=buf['out8'])
+                            out8=buf['out8'], **self.steps_kw)
         self.launches += 1
-        buf['loss'].copy_(buf['out8'][:, 0], non_blocking=True)
+        # one pinned tensor PER RUN (torch's caching host allocator makes this cheap): the caller owns it, so a later chunk
+        # that reuses this device buffer cannot overwrite losses the caller has not read yet
+        loss = torch.empty(K, dtype=torch.float32, pin_memory=True)
+        loss.copy_(buf['out8'][:, 0], non_blocking=True)
         buf['done'].record(main)
         buf['used'] = True
-        return buf['loss']
+        return loss
 
     def synchronize(self):
         torch.cuda.current_stream(self.dev).synchronize()

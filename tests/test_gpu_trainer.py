@@ -174,3 +174,33 @@ def test_device_pipeline_epoch_trains_without_host_batches():
     trainer = get_trainer(ModelType.CROSSDOMAIN, 'EMCDR')(cfg, model)
     losses = [trainer.train_epoch_device(data, 1024, steps_per_launch=8) for _ in range(4)]
     assert np.isfinite(losses).all() and losses[-1] < losses[0] - 1e-3
+
+
+def test_fused_runner_returns_one_loss_tensor_per_chunk():
+    """with more chunks than device buffers in flight, the losses of chunk n must not be overwritten by chunk
+    n + n_buffers (every run returns its own pinned tensor), and a change of the block shape (short last chunk) must not let
+    the copy stream overwrite ids an in-flight launch still reads.  Checked against the same batches one launch at a time."""
+    from recbole_cdr_b200 import ops
+    from recbole_cdr_b200.trainer import FusedStepRunner
+    dev = torch.device('cuda', 0)
+    g = torch.Generator().manual_seed(11)
+    nu, ni, D, B, K = 5000, 7000, 64, 1024, 4
+    ut, it = (torch.randn(nu, D, generator=g) * 0.1).to(dev), (torch.randn(ni, D, generator=g) * 0.1).to(dev)
+    n_chunks = 7   # > 3 * n_buffers
+    blocks = [torch.stack([torch.randint(1, nu, (K, B), generator=g), torch.randint(1, ni, (K, B), generator=g),
+                           torch.randint(1, ni, (K, B), generator=g)], 1).pin_memory() for _ in range(n_chunks)]
+    blocks.append(blocks[0][:2].clone().pin_memory())   # short last chunk: the buffers are re-created
+    spec = dict(user_tab=ut, item_tab=it, pairwise=True, reg_weight=0.01, gamma=1e-10)
+    gu, gi = torch.zeros_like(ut), torch.zeros_like(it)
+    runner = FusedStepRunner(spec, lr=None, grad_tables=(gu, gi), n_buffers=2)
+    got = [runner.run(b) for b in blocks]
+    runner.synchronize()
+    assert len({t.data_ptr() for t in got}) == len(got)
+    gu2, gi2 = torch.zeros_like(ut), torch.zeros_like(it)
+    for b, l in zip(blocks, got):
+        d = b.to(dev)
+        o, _, _ = ops.train_steps(ut, it, d[:, 0], d[:, 1], d[:, 2], reg_weight=0.01, user_dst=gu2, item_dst=gi2)
+        torch.cuda.synchronize()
+        assert torch.equal(l, o[:, 0].cpu())
+    torch.testing.assert_close(gu, gu2, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(gi, gi2, rtol=1e-5, atol=1e-7)

@@ -310,6 +310,25 @@ XDR_API int xdr_train_steps(const float* user_tab, const float* item_tab, int64_
                             float reg_weight, const float* grad_loss, float scale, float* user_dst, float* item_dst,
                             float* out8, void* steps_ws, size_t steps_ws_bytes, int32_t* oob, xdr_stream_t stream);
 
+/* The same launch with LAZILY ZEROED gradient tables (single GPU).  A scatter-add (RED) into a gradient line that is not in
+ * L2 costs a DRAM read and, later, a write-back: twice the bytes the reference's `zeros + index_add` needs to produce.
+ * touch_map (xdr_touch_map_bytes(n_users, n_items) bytes, 16-byte aligned; user part first) holds 2 bits per destination
+ * row.  A row whose bits are clear COUNTS AS ZERO whatever the table holds there: the first touch of such a row in a launch
+ * stores a full row of zeros (full-line stores allocate in L2 without reading DRAM), and the scatter-adds of that row wait
+ * for them, then hit L2.  So `optimizer.zero_grad()` (a dense N x D fill in the reference, emcdr.py tables via recbole
+ * Trainer._train_epoch) becomes clearing the map -- clear_map != 0 does that first, making user_dst / item_dst the gradient of
+ * exactly this launch's K batches on the rows the map marks afterwards (bit 0 of a row's pair), e.g. for a row-sparse
+ * optimizer; clear_map == 0 keeps accumulating into the marked rows.  Rows with clear bits are never written and may hold
+ * stale data.  The destination tables must not be the weight tables.  Needs the staged kernel (XDR_ERR_UNSUPPORTED
+ * otherwise: zero the tables and use xdr_train_steps).  Everything else as xdr_train_steps.                                */
+XDR_API size_t xdr_touch_map_bytes(int64_t n_users, int64_t n_items);
+XDR_API int xdr_train_steps_lazy(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
+                                 const int64_t* user, const int64_t* item_a, const int64_t* item_b, const float* label,
+                                 int64_t step_stride, int64_t batch, int n_steps, int pairwise, int loss_kind, float gamma,
+                                 float reg_weight, const float* grad_loss, float scale, float* user_dst, float* item_dst,
+                                 float* out8, void* steps_ws, size_t steps_ws_bytes, uint32_t* touch_map, int clear_map,
+                                 int32_t* oob, xdr_stream_t stream);
+
 /* ---- A10-A12: BiTGCF graph propagate-and-transfer ------------------------------------------------------------------------
  * xdr_spmm_csr: S[r,:] = sum_e val[e] * X[col[e],:] over CSR work items -- replaces torch.sparse.mm(L, E) of
  * BiTGCF.graph_layer (bitgcf.py:131).  Rows are pre-cut into work items of bounded length (heavy-tailed item degrees):

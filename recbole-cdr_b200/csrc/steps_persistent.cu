@@ -53,7 +53,10 @@ constexpr int kLoaderWarpsLite = 10;                // ... and when item rows ar
                                                     // CTAs must fit next to this one (register file: 576 x 80 + 256 x 40)
 constexpr int kScatterWarps = XDR_SCATTER_WARPS;    // scatterers
 constexpr int kRegThreads = (kServiceWarps + kWorkerWarps) * 32;
-__host__ __device__ constexpr int staged_threads(int loaders) { return (kServiceWarps + loaders + kScatterWarps) * 32; }
+constexpr int kFillerWarps = 2;                     // staged kernel: zero-fill warps of the lazily zeroed gradient tables
+__host__ __device__ constexpr int staged_threads(int loaders) {
+  return (kServiceWarps + loaders + kScatterWarps + kFillerWarps) * 32;
+}
 constexpr int kMaxCtaPerLane = 5;  // gatherer lanes poll <= 5 CTAs each: grid <= 160
 constexpr int kMaxStages = 4;      // staged kernel: stage ring depth (3 or 4)
 constexpr int kRing = 8;            // id-tile / partial / norm ring depth (steps)
@@ -82,6 +85,12 @@ struct StepsArgs {
   unsigned int tag_base;      // step s carries tag tag_base + s + 1: tags grow from launch to launch on one workspace, so a
                               // word left by an earlier launch can never match and the workspace needs no per-launch zeroing
   int slice;                  // S: interactions per CTA per step (multiple of 4)
+  // Lazily zeroed gradient tables (optional, single GPU, staged kernel): 2 bits per destination row, 16 rows per word --
+  // bit 0 "claimed" (some CTA's filler warp owns the zero-fill of the row), bit 1 "filled" (the zeros are in L2; scatter-adds
+  // may follow).  A row whose bits are clear counts as zero whatever it holds: its first touch stores a full row of zeros
+  // (full-line writes allocate in L2 without a DRAM read) and the REDs then hit L2 -- no read-modify-write of gradient lines.
+  unsigned int* touch_u;
+  unsigned int* touch_i;
   int32_t* oob;
   unsigned long long* trace;  // optional [n_steps][grid][8] globaltimer stamps (debug; NULL in production)
 };
@@ -103,6 +112,14 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
   return *p;
 }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) { *p = v; }
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  emu::yield();
+  return *p;
+}
+__device__ __forceinline__ int ld_volatile_smem(const int* p) {
+  emu::yield();
+  return *p;
+}
 #else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -158,6 +175,12 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_volatile_smem(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 #endif  // XDR_EMU
 // coherent (L2) 128-bit row load: the table may be the scatter destination of this very launch (fused SGD)
 __device__ __forceinline__ float4 ldcg_row4(const float* row, int col4) {
@@ -169,8 +192,10 @@ struct SmemLayout {
   int slice, rows_per, tasks, row_f, stages;  // S, 2|3, tasks per step per CTA (upper bound), floats per row, stage count
   __host__ __device__ SmemLayout(int s, int r, int t, int rf = 0, int ns = 0)
       : slice(s), rows_per(r), tasks(t), row_f(rf), stages(ns) {}
-  // [0, 320): 4 x kRing + kMaxStages mbarriers.  [320, 384): norms [kRing][2].  then partials, id ring, stage ring.
+  // [0, 288): 4 x kRing + kMaxStages mbarriers.  [288, 292): steps whose partials this CTA has published (filler throttle).
+  // [320, 384): norms [kRing][2].  then partials, id ring, stage ring.
   __host__ __device__ size_t bars_off() const { return 0; }
+  __host__ __device__ size_t progress_off() const { return 288; }
   __host__ __device__ size_t norms_off() const { return 320; }
   __host__ __device__ size_t part_off() const { return 384; }
   __host__ __device__ size_t ids_off() const {
@@ -231,11 +256,12 @@ __device__ __forceinline__ void service_producer(const StepsArgs& a, const SmemL
 
 // per step: sum this CTA's task partials in a fixed order and publish them as three 8-byte {value, tag} words
 __device__ __forceinline__ void service_publisher(const StepsArgs& a, const SmemLayout& L, const Bars& B,
-                                                  const float4* part, int tasks, int lane) {
+                                                  const float4* part, int tasks, int lane, int* progress) {
   const unsigned int n_cta = gridDim.x;
   for (int s = 0; s < a.n_steps; ++s) {
     const int slot = s % kRing;
     mbar_wait(&B.adone[slot], (uint32_t)((s / kRing) & 1));
+    if (lane == 0) *reinterpret_cast<volatile int*>(progress) = s + 1;  // this CTA's loaders are past step s
     if (a.trace && lane == 0) a.trace[((size_t)s * n_cta + blockIdx.x) * 8 + 0] = gtime();
     float p0 = 0.f, p1 = 0.f, p2 = 0.f;
     for (int q = lane; q < tasks; q += 32) {
@@ -507,17 +533,22 @@ __global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a,
   const Bars B(smem_raw + L.bars_off());
   float2* norms = reinterpret_cast<float2*>(smem_raw + L.norms_off());
   float4* part = reinterpret_cast<float4*>(smem_raw + L.part_off());
+  int* progress = reinterpret_cast<int*>(smem_raw + L.progress_off());
   unsigned char* ids_ring = smem_raw + L.ids_off();
   unsigned char* stage_ring = smem_raw + L.stage_off();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool lazy = a.touch_u != nullptr;  // lazily zeroed destination tables: filler warps are live and use the id tiles too
 
-  if (threadIdx.x == 0) init_bars(B, tasks, kScatterWarps, n_stages, kScatterWarps);
+  if (threadIdx.x == 0) {
+    init_bars(B, tasks, kScatterWarps + (lazy ? 1 : 0), n_stages, kScatterWarps);
+    *progress = 0;
+  }
   __syncthreads();
 
   if (warp == 0) {
     service_producer<PAIRWISE>(a, L, B, ids_ring, first, cnt, lane);
   } else if (warp == 1) {
-    service_publisher(a, L, B, part, tasks, lane);
+    service_publisher(a, L, B, part, tasks, lane, progress);
   } else if (warp < kServiceWarps) {
     service_gatherer(a, B, norms, warp - 2, lane);
   } else if (warp < kServiceWarps + kLoaderWarps) {
@@ -573,25 +604,68 @@ __global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a,
       score_and_stash(r1);
       lt = nx;
     }
-  } else {
+  } else if (warp < kServiceWarps + kLoaderWarps + kScatterWarps) {
     // ------------------------------------------------ scatterers ------------------------------------------------------
     const int x = warp - kServiceWarps - kLoaderWarps;
     const int sub = lane % LPR, grp = lane / LPR;
     const float inv_b = 1.0f / (float)a.batch;
     const float g = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f) * a.scale;
+    constexpr int kAhead = 4;  // lazily zeroed tables: "filled" words of this many tasks are requested before they are needed
     for (int s = 0; s < a.n_steps; ++s) {
       const int slot = s % kRing, st = s % n_stages;
       const uint32_t par = (uint32_t)((s / kRing) & 1);
-      if (!EARLY) mbar_wait(&B.normf[slot], par);  // => every CTA (this one included) has scored and stashed the step
       mbar_wait(&B.idsf[slot], par);   // (long complete) acquire: the TMA-written ids are visible to this warp
+      const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
+      // lazily zeroed tables: lanes 0..R-1 of an interaction's group look after the user / item+ / item- row; the word that
+      // holds the row's "filled" bit is requested here, before the norm wait, and checked right before the REDs
+      auto touch_word = [&](int q, unsigned int& fbit) -> const unsigned int* {
+        fbit = 0u;
+        const int j = q * IPW + grp;
+        if (q >= tasks || j >= cnt || sub >= R) return nullptr;
+        const int64_t id = ids[(size_t)sub * L.slice + j];
+        if ((uint64_t)id >= (uint64_t)(sub == 0 ? a.n_users : a.n_items)) return nullptr;
+        fbit = 2u << (((unsigned int)id & 15u) * 2u);
+        return (sub == 0 ? a.touch_u : a.touch_i) + (id >> 4);
+      };
+      unsigned int tw[kAhead];
+      if (lazy) {
+#pragma unroll
+        for (int t = 0; t < kAhead; ++t) {
+          unsigned int fb;
+          const unsigned int* wp = touch_word(x + t * kScatterWarps, fb);
+          tw[t] = wp ? ld_acquire_u32(wp) : 0u;
+        }
+      }
+      if (!EARLY) mbar_wait(&B.normf[slot], par);  // => every CTA (this one included) has scored and stashed the step
       mbar_wait(&B.adone[slot], par);  // (long complete) acquire: the loaders' stage writes are visible to this warp
       if (a.trace && lane == 0 && x == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 5] = gtime();
       const float2 nf = EARLY ? make_float2(0.f, 0.f) : norms[slot];
-      const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
       const float* lab = reinterpret_cast<const float*>(ids + (size_t)R * L.slice);
       const float* rows = reinterpret_cast<const float*>(stage_ring + (size_t)st * L.stage_slot_bytes());
       const float* sc = rows + (size_t)R * L.slice * row_f;
-      for (int q = x; q < tasks; q += kScatterWarps) {
+      int t_idx = 0;
+      for (int q = x; q < tasks; q += kScatterWarps, ++t_idx) {
+        if (lazy) {
+          // every row this warp is about to add into must have its zeros in L2 (bit 1 of the row's pair).  Bounded wait: the
+          // owner of a claimed row is a filler warp that is already past its last blocking wait.
+          unsigned int fb;
+          const unsigned int* wp = touch_word(q, fb);
+          unsigned int w = 0u;
+#pragma unroll
+          for (int t = 0; t < kAhead; ++t)
+            if ((t_idx % kAhead) == t) w = tw[t];
+          for (;;) {
+            const bool ok = wp == nullptr || (w & fb) != 0u;
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (!ok) w = ld_acquire_u32(wp);
+          }
+          // request the word of the task kAhead rounds ahead into the register this task just released
+          const unsigned int* np = touch_word(q + kAhead * kScatterWarps, fb);
+          const unsigned int nw = np ? ld_acquire_u32(np) : 0u;
+#pragma unroll
+          for (int t = 0; t < kAhead; ++t)
+            if ((t_idx % kAhead) == t) tw[t] = nw;
+        }
         const int j = q * IPW + grp;
         if (j >= cnt) continue;
         const int64_t iu64 = ids[j], ia64 = ids[L.slice + j], ib64 = PAIRWISE ? ids[2 * L.slice + j] : 0;
@@ -621,6 +695,68 @@ __global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a,
         mbar_arrive(&B.ifree[slot]);  // the id slot may be refilled by the producer
       }
     }
+  } else {
+    // ------------------------------------------------ fillers ---------------------------------------------------------
+    // Lazily zeroed gradient tables.  Filler f looks after steps f, f + kFillerWarps, ...: for every row the CTA's slice of
+    // the step names it tries to CLAIM the row (atomicOr of bit 0 of the row's pair); rows it wins are rows nobody has
+    // touched since the map was cleared -- it stores a full row of zeros (full-line stores: L2 allocates the lines without
+    // reading DRAM), fences, and only then sets the "filled" bit that the scatter warps of EVERY CTA wait for.  Rows it
+    // loses belong to some other filler, which is by then past its last blocking wait.  Throttle: step s is filled when the
+    // CTA's loaders are on step s - 1, about two steps before the scatter, so the zero lines are still in L2 when the REDs
+    // arrive.
+    if (!lazy) return;
+    const int f = warp - kServiceWarps - kLoaderWarps - kScatterWarps;
+    const int nrows = R * cnt;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = f; s < a.n_steps; s += kFillerWarps) {
+      const int slot = s % kRing;
+      mbar_wait(&B.idsf[slot], (uint32_t)((s / kRing) & 1));
+      while (ld_volatile_smem(progress) < s - 1) __nanosleep(128);
+      const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
+      unsigned int won = 0u;  // bit k: the k-th row this lane looked at is ours to zero-fill
+      int k = 0;
+      for (int i0 = 0; i0 < nrows; i0 += 32, ++k) {
+        const int i = i0 + lane;
+        const bool on = i < nrows;
+        const int kind = on ? i / cnt : 0;
+        const int64_t id = on ? ids[(size_t)kind * L.slice + (i - kind * cnt)] : -1;
+        bool mine = false;
+        if (on && (uint64_t)id < (uint64_t)(kind == 0 ? a.n_users : a.n_items)) {
+          const unsigned int bit = 1u << (((unsigned int)id & 15u) * 2u);
+          mine = (atomicOr((kind == 0 ? a.touch_u : a.touch_i) + (id >> 4), bit) & bit) == 0u;
+        }
+        if (mine) won |= 1u << k;
+        const unsigned long long myrow =
+            mine ? (unsigned long long)shard_row(kind == 0 ? a.user_dst : a.item_dst, 0, id, row_f) : 0ull;
+        unsigned int m = __ballot_sync(0xffffffffu, mine);
+        while (m) {  // two won rows per pass: lanes 0..15 zero the first, lanes 16..31 the second
+          const int l0 = __ffs(m) - 1;
+          m &= m - 1;
+          int l1 = -1;
+          if (m) {
+            l1 = __ffs(m) - 1;
+            m &= m - 1;
+          }
+          const int src = (lane < 16 || l1 < 0) ? l0 : l1;
+          float* row = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, myrow, src));
+          if (lane < 16 || l1 >= 0) {
+            for (int c = lane & 15; c < a.nv; c += 16) st4(row, c, z4);
+          }
+        }
+      }
+      __threadfence();  // the zeros are in L2 before anybody can see a "filled" bit
+      k = 0;
+      for (int i0 = 0; i0 < nrows; i0 += 32, ++k) {
+        const int i = i0 + lane;
+        if (i < nrows && ((won >> k) & 1u)) {
+          const int kind = i / cnt;
+          const int64_t id = ids[(size_t)kind * L.slice + (i - kind * cnt)];
+          atomicOr((kind == 0 ? a.touch_u : a.touch_i) + (id >> 4), 2u << (((unsigned int)id & 15u) * 2u));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&B.ifree[slot]);  // this filler no longer needs the step's id tile
+    }
   }
 }
 
@@ -639,16 +775,20 @@ __global__ void __launch_bounds__(kRegThreads, 1) train_steps_regs_kernel(StepsA
   const Bars B(smem_raw + L.bars_off());
   float2* norms = reinterpret_cast<float2*>(smem_raw + L.norms_off());
   float4* part = reinterpret_cast<float4*>(smem_raw + L.part_off());
+  int* progress = reinterpret_cast<int*>(smem_raw + L.progress_off());
   unsigned char* ids_ring = smem_raw + L.ids_off();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (threadIdx.x == 0) init_bars(B, tasks, tasks, 0, 1);
+  if (threadIdx.x == 0) {
+    init_bars(B, tasks, tasks, 0, 1);
+    *progress = 0;
+  }
   __syncthreads();
 
   if (warp == 0) {
     service_producer<PAIRWISE>(a, L, B, ids_ring, first, cnt, lane);
   } else if (warp == 1) {
-    service_publisher(a, L, B, part, tasks, lane);
+    service_publisher(a, L, B, part, tasks, lane, progress);
   } else if (warp < kServiceWarps) {
     service_gatherer(a, B, norms, warp - 2, lane);
   } else {
@@ -821,6 +961,14 @@ XDR_API void xdr_debug_force_register_kernel(int on) { g_force_regs = on; }
 // scatter without waiting for the step's norm exchange (train_steps_staged_kernel<..., EARLY = true>).
 XDR_API void xdr_steps_set_early_scatter(int on) { g_early_scatter = on; }
 
+// 2 bits per row, 16 rows per 32-bit word; every table's part is padded to a multiple of 4 words (16 bytes)
+static inline size_t touch_words_of(int64_t n_rows) { return (size_t)(((n_rows + 15) / 16 + 3) & ~(int64_t)3); }
+
+size_t xdr_touch_map_bytes(int64_t n_users, int64_t n_items) {
+  if (n_users < 0 || n_items < 0) return 0;
+  return (touch_words_of(n_users) + touch_words_of(n_items)) * sizeof(uint32_t);
+}
+
 size_t xdr_steps_workspace_bytes(int n_steps) {
   if (n_steps < 0) return 0;
   return (size_t)n_steps * ((size_t)sm_count() * 3 + 2) * sizeof(unsigned long long);
@@ -831,7 +979,8 @@ static int train_steps_core(const Shards& user_tab, const Shards& item_tab, cons
                             const int64_t* item_a, const int64_t* item_b, const float* label, int64_t step_stride,
                             int64_t batch, int n_steps, int pairwise, int loss_kind, float gamma, float reg_weight,
                             const float* grad_loss, float scale, float* out8, void* steps_ws, size_t steps_ws_bytes,
-                            const float* stage_a, const float* stage_b, int32_t* oob, xdr_stream_t stream) {
+                            const float* stage_a, const float* stage_b, int32_t* oob, xdr_stream_t stream,
+                            uint32_t* touch = nullptr, int touch_clear = 0) {
   const char* fn = "xdr_train_steps";
   XDR_REQUIRE(dim_ok(dim), "%s: dim=%d must be a multiple of 4 in (0, 256]", fn, dim);
   XDR_REQUIRE(batch > 0 && n_steps >= 0, "%s: batch=%lld n_steps=%d", fn, (long long)batch, n_steps);
@@ -858,7 +1007,18 @@ static int train_steps_core(const Shards& user_tab, const Shards& item_tab, cons
               fn, (long long)batch, dim);
     return XDR_ERR_UNSUPPORTED;
   }
-  if (g_force_regs && plan.stages > 0) {
+  if (touch != nullptr) {
+    XDR_REQUIRE(log2g == 0, "%s: lazily zeroed gradient tables (touch map) are a single-GPU feature", fn);
+    XDR_REQUIRE(aligned16(touch), "%s: the touch map must be 16-byte aligned", fn);
+    XDR_REQUIRE(user_dst.p[0] != user_tab.p[0] && item_dst.p[0] != item_tab.p[0],
+                "%s: a touch map zero-fills destination rows on first touch; the destination cannot be the weight table", fn);
+    if (plan.stages == 0) {
+      set_error("%s: the touch map needs the staged kernel, which does not fit batch=%lld dim=%d; zero the gradient tables "
+                "instead", fn, (long long)batch, dim);
+      return XDR_ERR_UNSUPPORTED;
+    }
+  }
+  if (g_force_regs && plan.stages > 0 && touch == nullptr) {
     const int ipw = 32 / plan.lpr;
     const int tasks = (plan.slice + ipw - 1) / ipw;
     if (tasks <= 2 * kWorkerWarps) {
@@ -878,6 +1038,11 @@ static int train_steps_core(const Shards& user_tab, const Shards& item_tab, cons
   a.words = reinterpret_cast<unsigned long long*>(steps_ws);
   a.trace = g_trace;
   cudaStream_t s = (cudaStream_t)stream;
+  if (touch != nullptr) {
+    a.touch_u = touch;
+    a.touch_i = touch + touch_words_of(n_users);
+    if (touch_clear) XDR_CUDA_OK(cudaMemsetAsync(touch, 0, xdr_touch_map_bytes(n_users, n_items), s));
+  }
   // Step tags grow from launch to launch on one workspace (tag_base + s + 1), so a word left behind by an earlier launch can
   // never match: the workspace is zeroed only when the library sees it for the first time (or the 32-bit tags would wrap),
   // not per launch.  The caller must not write to it between launches (xdr.h).
@@ -921,6 +1086,26 @@ int xdr_train_steps(const float* user_tab, const float* item_tab, int64_t n_user
   return train_steps_core(ut, it, du, di, 0, n_users, n_items, dim, user, item_a, item_b, label, step_stride, batch,
                           n_steps, pairwise, loss_kind, gamma, reg_weight, grad_loss, scale, out8, steps_ws,
                           steps_ws_bytes, nullptr, nullptr, oob, stream);
+}
+
+int xdr_train_steps_lazy(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
+                         const int64_t* user, const int64_t* item_a, const int64_t* item_b, const float* label,
+                         int64_t step_stride, int64_t batch, int n_steps, int pairwise, int loss_kind, float gamma,
+                         float reg_weight, const float* grad_loss, float scale, float* user_dst, float* item_dst, float* out8,
+                         void* steps_ws, size_t steps_ws_bytes, uint32_t* touch_map, int clear_map, int32_t* oob,
+                         xdr_stream_t stream) {
+  if (touch_map == nullptr) {
+    set_error("xdr_train_steps_lazy: null touch map (use xdr_train_steps for plain scatter-add destinations)");
+    return XDR_ERR_INVALID;
+  }
+  Shards ut{}, it{}, du{}, di{};
+  ut.p[0] = const_cast<float*>(user_tab);
+  it.p[0] = const_cast<float*>(item_tab);
+  du.p[0] = user_dst;
+  di.p[0] = item_dst;
+  return train_steps_core(ut, it, du, di, 0, n_users, n_items, dim, user, item_a, item_b, label, step_stride, batch,
+                          n_steps, pairwise, loss_kind, gamma, reg_weight, grad_loss, scale, out8, steps_ws,
+                          steps_ws_bytes, nullptr, nullptr, oob, stream, touch_map, clear_map);
 }
 
 int xdr_train_steps_sharded(const float* const* user_shards, const float* const* item_shards, float* const* user_dst_shards,

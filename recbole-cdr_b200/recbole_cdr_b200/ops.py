@@ -483,8 +483,37 @@ def train_steps_supported(batch: int, dim: int, pairwise: bool, device=None) -> 
     return tasks <= 2 * 20 and base <= 220 * 1024  # register kernel
 
 
+class TouchMap:
+    """Which rows of a pair of gradient tables hold gradients -- the state of *lazily zeroed* gradient tables
+    (``xdr_train_steps_lazy``, include/xdr.h).  2 bits per row (bit 0 claimed, bit 1 zero-filled), user part first.  A row
+    whose bits are clear counts as zero whatever the table holds; ``clear()`` is therefore ``zero_grad()`` at N/4 bytes
+    instead of the reference's dense N x D fill."""
+
+    def __init__(self, n_users: int, n_items: int, device):
+        self.n_users, self.n_items = int(n_users), int(n_items)
+        nbytes = _lib._lib.xdr_touch_map_bytes(self.n_users, self.n_items)
+        self.words = torch.zeros(nbytes // 4, dtype=torch.int32, device=device)
+        self._user_words = ((self.n_users + 15) // 16 + 3) // 4 * 4
+
+    def clear(self):
+        self.words.zero_()
+
+    def _mask(self, words, n):
+        bits = (words.view(-1, 1) >> (2 * torch.arange(16, device=words.device, dtype=torch.int32))) & 3
+        return bits.reshape(-1)[:n]
+
+    def state(self):
+        """Per-row 2-bit states ``(users [n_users], items [n_items])``: 0 untouched, 3 claimed and zero-filled."""
+        return self._mask(self.words[:self._user_words], self.n_users), self._mask(self.words[self._user_words:], self.n_items)
+
+    def touched(self):
+        """Boolean masks ``(users, items)`` of the rows that hold gradients."""
+        su, si = self.state()
+        return su != 0, si != 0
+
+
 def train_steps(user_tab, item_tab, user, item_a, item_b=None, label=None, *, loss_kind=_lib.LOSS_MSE, reg_weight=0.0,
-                gamma=1e-10, user_dst=None, item_dst=None, scale=1.0, grad_loss=None, out8=None):
+                gamma=1e-10, user_dst=None, item_dst=None, scale=1.0, grad_loss=None, out8=None, touch=None, fresh=False):
     """Run ``K = user.shape[0]`` training steps (fwd + bwd + scatter-add) in ONE persistent launch.
 
     ``user`` / ``item_a`` / ``item_b`` (pairwise) / ``label`` (pointwise) are ``[K, B]`` device tensors (row k = batch
@@ -492,6 +521,9 @@ def train_steps(user_tab, item_tab, user, item_a, item_b=None, label=None, *, lo
     scatter-added into ``user_dst`` / ``item_dst`` scaled by ``scale`` (default: dense gradient tables ``.grad``-style;
     pass the weight tables themselves and ``scale=-lr`` for fused asynchronous SGD).  Returns ``out8`` ``[K, 8]`` whose
     column 0 is the per-step loss -- the value ``calculate_loss`` returns for that batch.
+    ``touch`` (a ``TouchMap``): the destinations are lazily zeroed gradient tables -- rows the map does not mark count as
+    zero and are zero-filled on first touch, so the scatter-adds never read gradient lines from DRAM; ``fresh=True`` clears
+    the map first (the tables then hold the gradient of exactly these K batches on the marked rows).
     Replaces K iterations of recbole ``Trainer._train_epoch`` around emcdr.py:110-154 / cmf.py:75-98.
     """
     _require_cuda_f32(user_tab, 'user table')
@@ -515,10 +547,18 @@ def train_steps(user_tab, item_tab, user, item_a, item_b=None, label=None, *, lo
     if out8 is None:
         out8 = torch.empty((K, 8), dtype=torch.float32, device=dev)
     ws = _steps_workspace(dev, K)
-    call('xdr_train_steps', ptr(user_tab), ptr(item_tab), user_tab.shape[0], item_tab.shape[0], user_tab.shape[1], ptr(user),
-         ptr(item_a), ptr(item_b), ptr(label), user.stride(0), B, K, 1 if pairwise else 0, int(loss_kind), float(gamma),
-         float(reg_weight), ptr(grad_loss), float(scale), ptr(user_dst), ptr(item_dst), ptr(out8), ptr(ws), ws.numel(),
-         _oob(dev), cur_stream())
+    if touch is not None:
+        if touch.n_users != user_tab.shape[0] or touch.n_items != item_tab.shape[0]:
+            raise ValueError('touch map was built for other table sizes')
+        call('xdr_train_steps_lazy', ptr(user_tab), ptr(item_tab), user_tab.shape[0], item_tab.shape[0], user_tab.shape[1],
+             ptr(user), ptr(item_a), ptr(item_b), ptr(label), user.stride(0), B, K, 1 if pairwise else 0, int(loss_kind),
+             float(gamma), float(reg_weight), ptr(grad_loss), float(scale), ptr(user_dst), ptr(item_dst), ptr(out8), ptr(ws),
+             ws.numel(), ptr(touch.words), 1 if fresh else 0, _oob(dev), cur_stream())
+    else:
+        call('xdr_train_steps', ptr(user_tab), ptr(item_tab), user_tab.shape[0], item_tab.shape[0], user_tab.shape[1],
+             ptr(user), ptr(item_a), ptr(item_b), ptr(label), user.stride(0), B, K, 1 if pairwise else 0, int(loss_kind),
+             float(gamma), float(reg_weight), ptr(grad_loss), float(scale), ptr(user_dst), ptr(item_dst), ptr(out8), ptr(ws),
+             ws.numel(), _oob(dev), cur_stream())
     _maybe_check(dev)
     return out8, user_dst, item_dst
 

@@ -333,3 +333,97 @@ def test_early_scatter_flag_is_ignored_when_the_norms_matter():
                 L.xdr_steps_set_early_scatter(0)
     for x, y in zip(outs[0], outs[1]):
         torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------ lazily zeroed gradient tables
+def _oracle_grads(ut, it, u, ip, ineg, steps, reg=0.01):
+    a, b = ut.clone().requires_grad_(True), it.clone().requires_grad_(True)
+    gu, gi, losses = torch.zeros_like(ut), torch.zeros_like(it), []
+    for k in steps:
+        ref = O.emcdr_bpr_loss(a, b, u[k], ip[k], ineg[k], reg)
+        losses.append(ref.detach()[0])
+        du, di = O.grads_of(ref, [a, b])
+        gu += du
+        gi += di
+    return gu, gi, torch.stack(losses)
+
+
+@pytest.mark.parametrize('K,B,dim,sms,seed', [(6, 96, 64, 3, 0), (11, 64, 64, 2, 3), (5, 40, 32, 4, 1), (9, 96, 64, 3, 29)])
+def test_lazy_gradient_tables_fresh_launch(K, B, dim, sms, seed):
+    """xdr_train_steps_lazy with clear_map: the destination tables start out as GARBAGE; after the launch the rows the touch
+    map marks are exactly the rows the batches name and hold exactly the oracle's gradient (the first touch zero-filled them,
+    no matter which CTA or step got there first); unmarked rows were never written."""
+    nu, ni = 150, 180     # small tables: many rows are named by several steps and by several CTAs
+    ut, it, u, ip, ineg, _ = setup(nu, ni, dim, K, B, 5 + seed)
+    junk_u, junk_i = torch.full_like(ut, 7.0), torch.full_like(it, -3.0)
+    with emu_util.patched_ops(sms=sms, seed=seed) as ops:
+        tm = ops.TouchMap(nu, ni, 'cpu')
+        tm.words.fill_(-1)    # stale marks from an earlier optimizer step: fresh=True must clear them
+        out8, gu, gi = ops.train_steps(ut.clone(), it.clone(), u, ip, ineg, reg_weight=0.01, user_dst=junk_u.clone(),
+                                       item_dst=junk_i.clone(), touch=tm, fresh=True)
+        su, si = tm.state()
+    gu_ref, gi_ref, loss_ref = _oracle_grads(ut, it, u, ip, ineg, range(K))
+    torch.testing.assert_close(out8[:, 0], loss_ref, rtol=1e-4, atol=0)
+    named_u = torch.zeros(nu, dtype=torch.bool)
+    named_u[u.reshape(-1)] = True
+    named_i = torch.zeros(ni, dtype=torch.bool)
+    named_i[ip.reshape(-1)] = True
+    named_i[ineg.reshape(-1)] = True
+    assert torch.equal(su != 0, named_u) and torch.equal(si != 0, named_i)
+    assert bool(((su == 0) | (su == 3)).all()) and bool(((si == 0) | (si == 3)).all())   # claimed rows are all filled
+    torch.testing.assert_close(gu[named_u], gu_ref[named_u], rtol=1e-4, atol=1e-4 * gu_ref.abs().max().item())
+    torch.testing.assert_close(gi[named_i], gi_ref[named_i], rtol=1e-4, atol=1e-4 * gi_ref.abs().max().item())
+    assert bool((gu[~named_u] == 7.0).all()) and bool((gi[~named_i] == -3.0).all())
+
+
+def test_lazy_gradient_tables_accumulate_then_fresh():
+    """clear_map = 0 keeps adding into the rows an earlier launch marked (and zero-fills rows it did not); a later launch with
+    clear_map = 1 starts over: its marked rows hold only its own gradient."""
+    K, B, dim, nu, ni = 8, 64, 64, 120, 140
+    ut, it, u, ip, ineg, _ = setup(nu, ni, dim, K, B, 41)
+    with emu_util.patched_ops(sms=2, seed=7) as ops:
+        tm = ops.TouchMap(nu, ni, 'cpu')
+        gu, gi = torch.full_like(ut, 5.0), torch.full_like(it, 5.0)
+        ops.train_steps(ut.clone(), it.clone(), u[:3], ip[:3], ineg[:3], reg_weight=0.01, user_dst=gu, item_dst=gi, touch=tm,
+                        fresh=True)
+        ops.train_steps(ut.clone(), it.clone(), u[3:6], ip[3:6], ineg[3:6], reg_weight=0.01, user_dst=gu, item_dst=gi,
+                        touch=tm, fresh=False)
+        tu, ti = tm.touched()
+        gu_ref, gi_ref, _ = _oracle_grads(ut, it, u, ip, ineg, range(6))
+        torch.testing.assert_close(gu[tu], gu_ref[tu], rtol=1e-4, atol=1e-4 * gu_ref.abs().max().item())
+        torch.testing.assert_close(gi[ti], gi_ref[ti], rtol=1e-4, atol=1e-4 * gi_ref.abs().max().item())
+        assert bool((gu[~tu] == 5.0).all()) and bool((gi[~ti] == 5.0).all())
+        ops.train_steps(ut.clone(), it.clone(), u[6:], ip[6:], ineg[6:], reg_weight=0.01, user_dst=gu, item_dst=gi, touch=tm,
+                        fresh=True)
+        tu2, ti2 = tm.touched()
+    gu_ref2, gi_ref2, _ = _oracle_grads(ut, it, u, ip, ineg, range(6, K))
+    named = torch.zeros(nu, dtype=torch.bool)
+    named[u[6:].reshape(-1)] = True
+    assert torch.equal(tu2, named)
+    torch.testing.assert_close(gu[tu2], gu_ref2[tu2], rtol=1e-4, atol=1e-4 * gu_ref2.abs().max().item())
+    torch.testing.assert_close(gi[ti2], gi_ref2[ti2], rtol=1e-4, atol=1e-4 * gi_ref2.abs().max().item())
+
+
+def test_lazy_gradient_tables_pointwise_and_refusals():
+    from recbole_cdr_b200 import _lib
+    K, B, dim, nu, ni = 4, 64, 64, 90, 110
+    ut, it, u, i, _, y = setup(nu, ni, dim, K, B, 13, 0.3)
+    with emu_util.patched_ops(sms=2, seed=2) as ops:
+        tm = ops.TouchMap(nu, ni, 'cpu')
+        out8, gu, gi = ops.train_steps(ut.clone(), it.clone(), u, i, None, y, loss_kind=_lib.LOSS_BCE_SIGMOID, reg_weight=0.0,
+                                       user_dst=torch.full_like(ut, 9.0), item_dst=torch.full_like(it, 9.0), touch=tm, fresh=True)
+        tu, ti = tm.touched()
+        # the weight tables themselves cannot be lazily zeroed destinations
+        w_u, w_i = ut.clone(), it.clone()
+        with pytest.raises(_lib.XdrError, match='cannot be the weight table'):
+            ops.train_steps(w_u, w_i, u, i, None, y, loss_kind=_lib.LOSS_BCE_SIGMOID, user_dst=w_u, item_dst=w_i, touch=tm)
+    a, b = ut.clone().requires_grad_(True), it.clone().requires_grad_(True)
+    gu_ref, gi_ref = torch.zeros_like(ut), torch.zeros_like(it)
+    for s in range(K):
+        ref = O.bce_loss(torch.sigmoid(O.dot_score(a, b, u[s], i[s])), y[s])
+        du, di = O.grads_of(ref, [a, b])
+        gu_ref += du
+        gi_ref += di
+    torch.testing.assert_close(gu[tu], gu_ref[tu], rtol=1e-4, atol=1e-4 * gu_ref.abs().max().item())
+    torch.testing.assert_close(gi[ti], gi_ref[ti], rtol=1e-4, atol=1e-4 * gi_ref.abs().max().item())
+    assert bool((gu[~tu] == 9.0).all())

@@ -70,7 +70,7 @@ def parse_args():
                          'accumulate: scatter-add into whatever the gradient tables hold')
     ap.add_argument('--coop', type=int, default=1, help='1: cudaLaunchCooperativeKernel, 0: plain launch')
     ap.add_argument('--shard-chunk', type=int, default=50, help='N>1: steps per persistent launch')
-    ap.add_argument('--chunk', type=int, default=0, help='steps per launch on the end-to-end (host-fed) path (0: K/4)')
+    ap.add_argument('--chunk', type=int, default=0, help='steps per launch on the end-to-end (host-fed) path (0: K/2, 50 from K = 100)')
     return ap.parse_args()
 
 
@@ -359,16 +359,20 @@ class RecWorkload:
         self.out8 = torch.empty(n, 8, device=dev)
         self.touch = None
 
+    def touch_map(self):
+        from recbole_cdr_b200 import ops
+        if self.touch is None:
+            self.touch = ops.TouchMap(self.ut.shape[0], self.it.shape[0], self.dev)
+        return self.touch
+
     def launch(self, lo, hi, dst=None, scale=1.0):
         from recbole_cdr_b200 import ops
         ids = self.ids
         kw = {}
         if dst is None:
             dst = (self.gu, self.gi)
-            if self.grad_mode == 'fresh' and getattr(ops, 'TouchMap', None) is not None:
-                if self.touch is None:
-                    self.touch = (ops.TouchMap(self.ut.shape[0], self.dev), ops.TouchMap(self.it.shape[0], self.dev))
-                kw = dict(user_touch=self.touch[0], item_touch=self.touch[1], fresh=True)
+            if self.grad_mode == 'fresh':   # lazily zeroed gradient tables: this launch's gradient, no RMW of gradient lines
+                kw = dict(touch=self.touch_map(), fresh=True)
         ops.train_steps(self.ut, self.it, ids[lo:hi, 0], ids[lo:hi, 1], ids[lo:hi, 2], reg_weight=0.01, user_dst=dst[0],
                         item_dst=dst[1], scale=scale, out8=self.out8[lo:hi], **kw)
 
@@ -510,13 +514,12 @@ def run_xdr(args):
         Re = max(3, R // 2)
         # the other gradient-destination mode of the same launch
         other = 'accumulate' if args.grad_mode == 'fresh' else 'fresh'
-        if getattr(ops, 'TouchMap', None) is not None:
-            wl.grad_mode, wl.R = other, Re
-            ms_o, _ = wl.timed(timer)
-            extra['grad_mode_' + other] = dict(rate_fields(ms_o, K, B, 1, peak), note=(
-                'scatter-add into whatever the dense gradient tables hold (every RED into a DRAM-resident line is a '
-                'read-modify-write)' if other == 'accumulate' else 'touch map: first touch of a row zero-fills it'))
-            wl.grad_mode, wl.R = args.grad_mode, R
+        wl.grad_mode, wl.R = other, Re
+        ms_o, _ = wl.timed(timer)
+        extra['grad_mode_' + other] = dict(rate_fields(ms_o, K, B, 1, peak), note=(
+            'scatter-add into whatever the dense gradient tables hold (every RED into a DRAM-resident line is a '
+            'read-modify-write)' if other == 'accumulate' else 'touch map: first touch of a row zero-fills it'))
+        wl.grad_mode, wl.R = args.grad_mode, R
         # scatter-add aimed at the weight tables (scale = -lr): the SGD update fused into the step
         wl.R = Re
         ms_f, _ = wl.timed(timer, dst=(wl.ut, wl.it), scale=-1e-3)
@@ -542,7 +545,7 @@ def run_xdr(args):
     e2e = None
     if not args.no_e2e:
         from recbole_cdr_b200.trainer import FusedStepRunner
-        chunk = args.chunk if args.chunk > 0 else max(1, min(K, max(5, K // 4)))
+        chunk = args.chunk if args.chunk > 0 else (max(1, K // 2) if K < 100 else 50)
         n_chunks = max(1, K // chunk)
         Ke = chunk * n_chunks
         if sharded:
@@ -553,6 +556,8 @@ def run_xdr(args):
         else:
             spec = dict(user_tab=wl.ut, item_tab=wl.it, pairwise=True, reg_weight=0.01, gamma=1e-10)
             runner = FusedStepRunner(spec, lr=None, grad_tables=(wl.gu, wl.gi), n_buffers=3)
+            if args.grad_mode == 'fresh':   # the K-step block's gradient: the map is cleared per block, chunks accumulate
+                runner.steps_kw = dict(touch=wl.touch_map(), fresh=False)
             src_ids = wl.ids
         Re2 = max(3, R // 2)
         host = src_ids[W: W + min(R, Re2) * K].cpu().pin_memory()   # pinned [*, 3, B] int64 id blocks on the host
@@ -565,6 +570,8 @@ def run_xdr(args):
             timer.barrier()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
+            if not sharded and args.grad_mode == 'fresh':
+                wl.touch_map().clear()
             losses = [runner.run(b) for b in blocks]   # per chunk: H2D ids -> one persistent launch -> D2H losses
             a1.record()
             timer.barrier()

@@ -265,7 +265,9 @@ XDR_API int xdr_full_sort_topk_tc5(const float* user_vecs, int64_t batch, const 
                                    float* out_score, int64_t* out_id, void* topk_ws, size_t topk_ws_bytes,
                                    xdr_stream_t stream);
 /* Self-test of the tcgen05 building blocks (tc5.cuh): D[128, N] = A[128, K] B[N, K]^T in 3xTF32 on one CTA, each operand
- * staged K-major (0) or MN-major (1) in shared memory.  Row-major fp32 device pointers; N % 16 == 0, N <= 256, K % 8 == 0. */
+ * staged K-major (a_mn = b_mn = 0) in shared memory.  Row-major fp32 device pointers; N % 16 == 0, N <= 256, K % 8 == 0.
+ * MN-major TF32 operands (a_mn / b_mn = 1) are refused with XDR_ERR_UNSUPPORTED: on a B200 the SWIZZLE_NONE layouts
+ * reproduce the product for K-major 32-bit operands only (profiles/r2_ubench_tcgen05.txt); kind::f16 takes both majors.   */
 XDR_API int xdr_tc5_selftest(const float* A, const float* B, int N, int K, int a_mn, int b_mn, float* D, xdr_stream_t stream);
 /* The same product as bf16x3 on tcgen05.mma kind::f16 (bf16 hi / lo operand planes, 8 elements per 16-byte chunk, K % 16 == 0):
  * the operand format planned for the tcgen05 training kernels.  ~2^-16 relative per product.  a_mn = 2: A is staged as a

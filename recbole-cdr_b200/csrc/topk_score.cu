@@ -448,6 +448,14 @@ static int tc5_selftest(const char* who, const float* A, const float* B, int N, 
 }
 
 int xdr_tc5_selftest(const float* A, const float* B, int N, int K, int a_mn, int b_mn, float* D, xdr_stream_t stream) {
+  // Measured on a B200 (profiles/r2_ubench_tcgen05.txt): with SWIZZLE_NONE, kind::tf32 reproduces the product for K-major
+  // operands only -- neither assignment of the two stride fields does for MN-major 32-bit operands (kind::f16 takes both
+  // majors).  Nothing in the library stages TF32 operands MN-major; the request is refused instead of answering wrongly.
+  if (a_mn != 0 || b_mn != 0) {
+    set_error("xdr_tc5_selftest: MN-major TF32 operands are not supported with the SWIZZLE_NONE layouts (measured on B200); "
+              "use xdr_tc5_selftest_bf16 for MN-major operands");
+    return XDR_ERR_UNSUPPORTED;
+  }
   return tc5_selftest("xdr_tc5_selftest", A, B, N, K, a_mn, b_mn, 0, D, stream);
 }
 

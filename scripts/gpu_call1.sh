@@ -24,16 +24,16 @@ for id in "test_tc5_selftest_gemm_all_majors[0-0]" "test_tc5_selftest_gemm_all_m
           "test_tc5_selftest_gemm_bf16x3_all_majors[0-1]" "test_tc5_selftest_gemm_bf16x3_all_majors[1-0]" \
           "test_tc5_selftest_gemm_bf16x3_all_majors[1-1]" "test_tc5_selftest_gemm_bf16x3_all_majors[2-0]" \
           "test_tc5_selftest_gemm_bf16x3_all_majors[2-1]"; do
-  XDR_RUN_UNVALIDATED=1 timeout 120 python -m pytest "tests/test_gpu_unvalidated.py::$id" -q --timeout 60 >> $OUT/tc5_selftest.log 2>&1
+  XDR_RUN_UNVALIDATED=1 timeout 120 python -m pytest "tests/test_gpu_engines.py::$id" -q --timeout 60 >> $OUT/tc5_selftest.log 2>&1
   rc=$?; echo "   $id rc=$rc" | tee -a $OUT/summary.txt; [ $rc -ne 0 ] && fails=$((fails+1))
 done
 say "tc5 self-test failing cases: $fails $(el)"
 
 # 3. every other unvalidated test (no -x: the full list of failures is the result), tc5 kernels in their own process
-XDR_RUN_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_unvalidated.py -q --timeout 120 -k "not tc5" -p no:cacheprovider \
+XDR_RUN_UNVALIDATED=1 timeout 900 python -m pytest tests/test_gpu_engines.py -q --timeout 120 -k "not tc5" -p no:cacheprovider \
   > $OUT/unvalidated.log 2>&1
 say "unvalidated (not tc5) rc=$? $(el)"
-XDR_RUN_UNVALIDATED=1 timeout 400 python -m pytest tests/test_gpu_unvalidated.py -q --timeout 120 -k "tc5 and not selftest" -p no:cacheprovider \
+XDR_RUN_UNVALIDATED=1 timeout 400 python -m pytest tests/test_gpu_engines.py -q --timeout 120 -k "tc5 and not selftest" -p no:cacheprovider \
   > $OUT/unvalidated_tc5.log 2>&1
 say "unvalidated (tc5) rc=$? $(el)"
 

@@ -1,6 +1,6 @@
 """tc_conet_kernel (one CoNet tower pass + backward + scatter in ONE kernel, 3xTF32 mma.sync tiles) under the CPU CTA
 emulator, against the oracle restatement of conet.py:105-197.  Kernel *logic* only; hardware parity is the job of the
-``gpu`` tests (tests/test_gpu_unvalidated.py until the kernel has run on a B200)."""
+``gpu`` tests (tests/test_gpu_engines.py)."""
 import numpy as np
 import pytest
 import torch

@@ -149,7 +149,7 @@ def test_dtcdr_composed():
 
 def test_trainer_row_sparse_adagrad_follows_dense_torch_adagrad():
     """CMF, three batches: tables stepped by the row-sparse kernel == tables stepped by dense torch.optim.Adagrad
-    (trainer._train_epoch_row_sparse; the CPU twin of the test in tests/test_gpu_unvalidated.py)."""
+    (trainer._train_epoch_row_sparse; the CPU twin of the test in tests/test_gpu_engines.py)."""
     import numpy as np
     from recbole_cdr_b200.data import Interaction
     from recbole_cdr_b200.model.cross_domain_recommender.cmf import CMF

@@ -1,7 +1,7 @@
 """The five remaining drop-in models (CLFM, DeepAPF, SSCDR, NATR, DCDCSR) against
 tests/golden/f4_*.npz -- outputs of the UNMODIFIED reference classes (oracle/make_golden_f4.py) -- on CPU tensors through the
 CTA emulator (``emu_util.patched_ops``): same state_dict keys (strict load), same loss, every parameter gradient, predict.
-The GPU counterparts live in tests/test_gpu_unvalidated.py until they have run on a B200."""
+The GPU counterparts live in tests/test_gpu_engines.py."""
 import numpy as np
 import pytest
 import torch

@@ -1,5 +1,5 @@
 """xdr_full_sort_topk (scoring + history mask + streaming top-k, topk_score.cu) through the CPU CTA emulator against the
-numpy oracle.  Logic only; the hardware counterpart is in tests/test_gpu_unvalidated.py."""
+numpy oracle.  Logic only; the hardware counterpart is in tests/test_gpu_engines.py."""
 import ctypes
 
 import numpy as np

@@ -1,7 +1,8 @@
-"""GPU parity tests of kernels written while no GPU was reachable (marker ``unvalidated``: skipped unless
-XDR_RUN_UNVALIDATED=1).  Their logic already runs under the CPU CTA emulator (tests/test_emu_*.py); these are the hardware
-counterparts, at the tolerances of tests/test_gpu_kernels.py / test_gpu_models.py.  Once a test here has passed on a B200 it
-moves to the regular ``gpu`` files."""
+"""GPU parity tests of the second-generation kernels: tensor-core row-tile MLPs (mma.sync and tcgen05), the fused CoNet tower
+pass, row-sparse optimizers, fused score + top-k (both engines), early scatter, the five further models.  All of them were
+written in round 1 without GPU access (logic under the CPU CTA emulator, tests/test_emu_*.py) and ran on a B200 for the first
+time in round 2's first GPU call (profiles/r2_call1_summary.txt): every test of this file passed there except the ones
+whose docstrings say what was changed since."""
 import numpy as np
 import pytest
 import torch
@@ -12,7 +13,7 @@ from oracle import cdr_oracle as O
 from test_gpu_kernels import LOSS_RTOL, dev, lib, ops, rand_ids, rand_table
 from test_gpu_models import EMCDR_CFG, build, check_loss_and_grads, cuda_batch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.unvalidated]
+pytestmark = pytest.mark.gpu
 
 
 # ------------------------------------------------------------------------------------------ tensor-core fused MLP (tc_mlp.cu)
@@ -405,24 +406,37 @@ def test_device_pipeline_with_row_sparse_adagrad_equals_dense_torch_adagrad():
             opt.step()
             ref_total += float(l.detach())
     assert abs(loss - ref_total) <= 1e-4 * abs(ref_total)
-    torch.testing.assert_close(model.source_user_embedding.weight.detach().cpu(), a.detach(), rtol=1e-4, atol=1e-6)
-    torch.testing.assert_close(model.source_item_embedding.weight.detach().cpu(), b.detach(), rtol=1e-4, atol=1e-6)
+    # Adagrad's FIRST update of an element is lr * g / (|g| + 1e-10): +-lr whatever |g| is -- unless |g| is within a few
+    # orders of magnitude of 1e-10, where the ratio amplifies the last bits of g (the scatter-add sums a row's duplicates in
+    # another order than index_add).  Round 2, call 1: 27 of 49 984 elements differed by up to 1.3e-4 = lr * 2.6e-3 for that
+    # reason.  So: every element within lr * 1e-2, and all but a handful at the usual tolerance.
+    for got, want in ((model.source_user_embedding.weight.detach().cpu(), a.detach()),
+                      (model.source_item_embedding.weight.detach().cpu(), b.detach())):
+        err = (got - want).abs()
+        assert float(err.max()) <= 0.05 * 1e-2
+        assert float((err > 1e-6 + 1e-4 * want.abs()).float().mean()) <= 2e-3
 
 
 # ------------------------------------------------------------------------------------------ tcgen05 building blocks (tc5.cuh)
-@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 0), (1, 1)])
-def test_tc5_selftest_gemm_all_majors(a_mn, b_mn):
-    """D = A B^T on tcgen05 (3xTF32, TMEM accumulator) with the operands staged K-major / MN-major by the kernel itself: the
-    hardware check of the repository's descriptor reading, through the library (scripts/ubench_tcgen05.cu is the standalone
-    form that also tries the alternative reading)."""
-    import ctypes
-    g = torch.Generator().manual_seed(a_mn * 2 + b_mn)
+def test_tc5_selftest_gemm_tf32_k_major():
+    """D = A B^T on tcgen05 (3xTF32, TMEM accumulator) with the operands staged K-major by the kernel itself: the hardware
+    check of the descriptor reading, through the library (scripts/ubench_tcgen05.cu is the standalone form)."""
+    g = torch.Generator().manual_seed(0)
     N, K = 64, 64
     A, B = torch.randn(128, K, generator=g).to(dev()), torch.randn(N, K, generator=g).to(dev())
     D = torch.zeros(128, N, device=dev())
-    lib().call('xdr_tc5_selftest', A.data_ptr(), B.data_ptr(), N, K, a_mn, b_mn, D.data_ptr(), lib().cur_stream())
+    lib().call('xdr_tc5_selftest', A.data_ptr(), B.data_ptr(), N, K, 0, 0, D.data_ptr(), lib().cur_stream())
     torch.cuda.synchronize()
     torch.testing.assert_close(D.cpu().double(), A.cpu().double() @ B.cpu().double().T, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('a_mn,b_mn', [(0, 1), (1, 0), (1, 1)])
+def test_tc5_selftest_refuses_mn_major_tf32(a_mn, b_mn):
+    """Round 2, call 1: with SWIZZLE_NONE neither stride-field assignment reproduces the product for MN-major 32-bit operands
+    on a B200 (profiles/r2_ubench_tcgen05.txt).  No kernel of the library uses them; the self-test now refuses the request."""
+    A, B, D = torch.zeros(128, 64, device=dev()), torch.zeros(64, 64, device=dev()), torch.zeros(128, 64, device=dev())
+    with pytest.raises(lib().XdrError, match='MN-major TF32'):
+        lib().call('xdr_tc5_selftest', A.data_ptr(), B.data_ptr(), 64, 64, a_mn, b_mn, D.data_ptr(), lib().cur_stream())
 
 
 @pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1)])

@@ -120,6 +120,8 @@ __device__ __forceinline__ int ld_volatile_smem(const int* p) {
   emu::yield();
   return *p;
 }
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) { emu::bulk_s2g(dst_gmem, src_smem, bytes); }
+__device__ __forceinline__ void bulk_store_wait_all() { emu::bulk_store_wait_all(); }
 #else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -181,6 +183,16 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 __device__ __forceinline__ int ld_volatile_smem(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+// TMA 1-D bulk copy shared -> global (one thread, one instruction per row), completion through the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+// every bulk store this thread has issued is complete (written, not just read from shared memory)
+__device__ __forceinline__ void bulk_store_wait_all() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 #endif  // XDR_EMU
 // coherent (L2) 128-bit row load: the table may be the scatter destination of this very launch (fused SGD)
 __device__ __forceinline__ float4 ldcg_row4(const float* row, int col4) {
@@ -193,11 +205,13 @@ struct SmemLayout {
   __host__ __device__ SmemLayout(int s, int r, int t, int rf = 0, int ns = 0)
       : slice(s), rows_per(r), tasks(t), row_f(rf), stages(ns) {}
   // [0, 288): 4 x kRing + kMaxStages mbarriers.  [288, 292): steps whose partials this CTA has published (filler throttle).
-  // [320, 384): norms [kRing][2].  then partials, id ring, stage ring.
+  // [320, 384): norms [kRing][2].  [384, 1408): one row of zeros (source of the fillers' bulk stores).  then partials, id
+  // ring, stage ring.
   __host__ __device__ size_t bars_off() const { return 0; }
   __host__ __device__ size_t progress_off() const { return 288; }
   __host__ __device__ size_t norms_off() const { return 320; }
-  __host__ __device__ size_t part_off() const { return 384; }
+  __host__ __device__ size_t zero_off() const { return 384; }
+  __host__ __device__ size_t part_off() const { return 1408; }
   __host__ __device__ size_t ids_off() const {
     return (part_off() + (size_t)kRing * tasks * sizeof(float4) + 127) & ~(size_t)127;
   }
@@ -534,10 +548,17 @@ __global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a,
   float2* norms = reinterpret_cast<float2*>(smem_raw + L.norms_off());
   float4* part = reinterpret_cast<float4*>(smem_raw + L.part_off());
   int* progress = reinterpret_cast<int*>(smem_raw + L.progress_off());
+  float* zero_row = reinterpret_cast<float*>(smem_raw + L.zero_off());
   unsigned char* ids_ring = smem_raw + L.ids_off();
   unsigned char* stage_ring = smem_raw + L.stage_off();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool lazy = a.touch_u != nullptr;  // lazily zeroed destination tables: filler warps are live and use the id tiles too
+  if (lazy) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) zero_row[i] = 0.f;
+#ifndef XDR_EMU
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros -> visible to the bulk-copy engine
+#endif
+  }
 
   if (threadIdx.x == 0) {
     init_bars(B, tasks, kScatterWarps + (lazy ? 1 : 0), n_stages, kScatterWarps);
@@ -707,52 +728,54 @@ __global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a,
     if (!lazy) return;
     const int f = warp - kServiceWarps - kLoaderWarps - kScatterWarps;
     const int nrows = R * cnt;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t row_bytes = (uint32_t)row_f * 4u;
+    constexpr int kBatch = 8;  // claims in flight per lane: one L2 round trip per 256 rows instead of one per 32
     for (int s = f; s < a.n_steps; s += kFillerWarps) {
       const int slot = s % kRing;
       mbar_wait(&B.idsf[slot], (uint32_t)((s / kRing) & 1));
       while (ld_volatile_smem(progress) < s - 1) __nanosleep(128);
       const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
-      unsigned int won = 0u;  // bit k: the k-th row this lane looked at is ours to zero-fill
-      int k = 0;
-      for (int i0 = 0; i0 < nrows; i0 += 32, ++k) {
-        const int i = i0 + lane;
-        const bool on = i < nrows;
-        const int kind = on ? i / cnt : 0;
-        const int64_t id = on ? ids[(size_t)kind * L.slice + (i - kind * cnt)] : -1;
-        bool mine = false;
-        if (on && (uint64_t)id < (uint64_t)(kind == 0 ? a.n_users : a.n_items)) {
-          const unsigned int bit = 1u << (((unsigned int)id & 15u) * 2u);
-          mine = (atomicOr((kind == 0 ? a.touch_u : a.touch_i) + (id >> 4), bit) & bit) == 0u;
-        }
-        if (mine) won |= 1u << k;
-        const unsigned long long myrow =
-            mine ? (unsigned long long)shard_row(kind == 0 ? a.user_dst : a.item_dst, 0, id, row_f) : 0ull;
-        unsigned int m = __ballot_sync(0xffffffffu, mine);
-        while (m) {  // two won rows per pass: lanes 0..15 zero the first, lanes 16..31 the second
-          const int l0 = __ffs(m) - 1;
-          m &= m - 1;
-          int l1 = -1;
-          if (m) {
-            l1 = __ffs(m) - 1;
-            m &= m - 1;
-          }
-          const int src = (lane < 16 || l1 < 0) ? l0 : l1;
-          float* row = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, myrow, src));
-          if (lane < 16 || l1 >= 0) {
-            for (int c = lane & 15; c < a.nv; c += 16) st4(row, c, z4);
+      for (int base = 0; base < nrows; base += 32 * kBatch) {
+        unsigned int* wp[kBatch];
+        unsigned int bit[kBatch], old[kBatch];
+        float* row[kBatch];
+        // all claims of the batch go out back to back ...
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+          const int i = base + 32 * k + lane;
+          wp[k] = nullptr;
+          bit[k] = 0u;
+          old[k] = ~0u;
+          row[k] = nullptr;
+          if (i < nrows) {
+            const int kind = i / cnt;
+            const int64_t id = ids[(size_t)kind * L.slice + (i - kind * cnt)];
+            if ((uint64_t)id < (uint64_t)(kind == 0 ? a.n_users : a.n_items)) {
+              bit[k] = 1u << (((unsigned int)id & 15u) * 2u);
+              wp[k] = (kind == 0 ? a.touch_u : a.touch_i) + (id >> 4);
+              row[k] = shard_row(kind == 0 ? a.user_dst : a.item_dst, 0, id, row_f);
+              old[k] = atomicOr(wp[k], bit[k]);
+            }
           }
         }
-      }
-      __threadfence();  // the zeros are in L2 before anybody can see a "filled" bit
-      k = 0;
-      for (int i0 = 0; i0 < nrows; i0 += 32, ++k) {
-        const int i = i0 + lane;
-        if (i < nrows && ((won >> k) & 1u)) {
-          const int kind = i / cnt;
-          const int64_t id = ids[(size_t)kind * L.slice + (i - kind * cnt)];
-          atomicOr((kind == 0 ? a.touch_u : a.touch_i) + (id >> 4), 2u << (((unsigned int)id & 15u) * 2u));
+        // ... then every row this lane won gets one bulk store of a row of zeros (shared -> global, one instruction)
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+          if (wp[k] != nullptr && (old[k] & bit[k]) == 0u) {
+            bulk_s2g(row[k], zero_row, row_bytes);
+            any = true;
+          } else {
+            wp[k] = nullptr;   // not ours: nothing to publish
+          }
         }
+        if (__any_sync(0xffffffffu, any)) {
+          bulk_store_wait_all();  // this lane's zero rows are written ...
+          __threadfence();        // ... and ordered before the "filled" bits below, for every observer on the device
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k)
+          if (wp[k] != nullptr) atomicOr(wp[k], bit[k] << 1);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&B.ifree[slot]);  // this filler no longer needs the step's id tile

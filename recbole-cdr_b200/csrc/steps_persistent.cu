@@ -54,9 +54,12 @@ constexpr int kLoaderWarpsLite = 10;                // ... and when item rows ar
 constexpr int kScatterWarps = XDR_SCATTER_WARPS;    // scatterers
 constexpr int kRegThreads = (kServiceWarps + kWorkerWarps) * 32;
 constexpr int kFillerWarps = 2;                     // staged kernel: zero-fill warps of the lazily zeroed gradient tables
-__host__ __device__ constexpr int staged_threads(int loaders) {
-  return (kServiceWarps + loaders + kScatterWarps + kFillerWarps) * 32;
+__host__ __device__ constexpr int staged_threads(int loaders, bool lazy = true) {   // the filler warps come last: a launch
+  return (kServiceWarps + loaders + kScatterWarps + (lazy ? kFillerWarps : 0)) * 32;  // without them simply has fewer threads
 }
+// register cap of the staged kernel: 768 threads -> 80 registers; so that in the lite configuration a 256-thread peer-gather
+// CTA still fits in the SM's register file next to this CTA
+constexpr int kStagedBound = staged_threads(kLoaderWarpsFull) > 768 ? staged_threads(kLoaderWarpsFull) : 768;
 constexpr int kMaxCtaPerLane = 5;  // gatherer lanes poll <= 5 CTAs each: grid <= 160
 constexpr int kMaxStages = 4;      // staged kernel: stage ring depth (3 or 4)
 constexpr int kRing = 8;            // id-tile / partial / norm ring depth (steps)
@@ -177,9 +180,12 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Strong (L2-coherent) load of a touch-map word.  relaxed, not acquire: an acquire load is followed by an L1 invalidation
+// (CCTL.IVALL) per use; what the scatter warps need is only that their REDs -- issued after, and control-dependent on, the
+// observed "filled" bit -- reach L2 after the zero row did, and the filler set the bit only after the row was complete in L2.
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ int ld_volatile_smem(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
@@ -533,9 +539,7 @@ __device__ __forceinline__ void init_bars(const Bars& B, int tasks, int ifree_co
 // stage slot; they still wait for it before they free the id slot, which keeps the id / partial / norm rings in step (the
 // per-step loss is still the exchanged batch mean).
 template <int LPR, int VEC, bool PAIRWISE, int kLoaderWarps, bool EARLY = false>
-// launch bound 768 (> the threads actually launched) caps ptxas at 80 registers/thread, so that in the lite configuration
-// (576 threads) a 256-thread peer-gather CTA still fits in the SM's register file next to this CTA
-__global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a, int n_stages) {
+__global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(StepsArgs a, int n_stages) {
   constexpr int IPW = 32 / LPR;
   constexpr int R = PAIRWISE ? 3 : 2;
   XDR_DYN_SMEM_ALIGNED(unsigned char, smem_raw, 128);
@@ -648,47 +652,10 @@ __global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a,
         fbit = 2u << (((unsigned int)id & 15u) * 2u);
         return (sub == 0 ? a.touch_u : a.touch_i) + (id >> 4);
       };
-      unsigned int tw[kAhead];
-      if (lazy) {
-#pragma unroll
-        for (int t = 0; t < kAhead; ++t) {
-          unsigned int fb;
-          const unsigned int* wp = touch_word(x + t * kScatterWarps, fb);
-          tw[t] = wp ? ld_acquire_u32(wp) : 0u;
-        }
-      }
-      if (!EARLY) mbar_wait(&B.normf[slot], par);  // => every CTA (this one included) has scored and stashed the step
-      mbar_wait(&B.adone[slot], par);  // (long complete) acquire: the loaders' stage writes are visible to this warp
-      if (a.trace && lane == 0 && x == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 5] = gtime();
-      const float2 nf = EARLY ? make_float2(0.f, 0.f) : norms[slot];
-      const float* lab = reinterpret_cast<const float*>(ids + (size_t)R * L.slice);
-      const float* rows = reinterpret_cast<const float*>(stage_ring + (size_t)st * L.stage_slot_bytes());
-      const float* sc = rows + (size_t)R * L.slice * row_f;
-      int t_idx = 0;
-      for (int q = x; q < tasks; q += kScatterWarps, ++t_idx) {
-        if (lazy) {
-          // every row this warp is about to add into must have its zeros in L2 (bit 1 of the row's pair).  Bounded wait: the
-          // owner of a claimed row is a filler warp that is already past its last blocking wait.
-          unsigned int fb;
-          const unsigned int* wp = touch_word(q, fb);
-          unsigned int w = 0u;
-#pragma unroll
-          for (int t = 0; t < kAhead; ++t)
-            if ((t_idx % kAhead) == t) w = tw[t];
-          for (;;) {
-            const bool ok = wp == nullptr || (w & fb) != 0u;
-            if (__all_sync(0xffffffffu, ok)) break;
-            if (!ok) w = ld_acquire_u32(wp);
-          }
-          // request the word of the task kAhead rounds ahead into the register this task just released
-          const unsigned int* np = touch_word(q + kAhead * kScatterWarps, fb);
-          const unsigned int nw = np ? ld_acquire_u32(np) : 0u;
-#pragma unroll
-          for (int t = 0; t < kAhead; ++t)
-            if ((t_idx % kAhead) == t) tw[t] = nw;
-        }
+      // one task: the rows of 32 / LPR interactions -> gradient rows -> RED
+      auto scatter_task = [&](int q, float2 nf, const float* lab, const float* rows, const float* sc) {
         const int j = q * IPW + grp;
-        if (j >= cnt) continue;
+        if (j >= cnt) return;
         const int64_t iu64 = ids[j], ia64 = ids[L.slice + j], ib64 = PAIRWISE ? ids[2 * L.slice + j] : 0;
         const int iu = (uint64_t)iu64 < (uint64_t)a.n_users ? (int)iu64 : -1;
         const int ia = (uint64_t)ia64 < (uint64_t)a.n_items ? (int)ia64 : -1;
@@ -703,6 +670,51 @@ __global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a,
           const float4 ra = ld_row4(rows + ((size_t)L.slice + j) * row_f, cidx);
           const float4 rb = PAIRWISE ? ld_row4(rows + ((size_t)2 * L.slice + j) * row_f, cidx) : ru;
           scatter_cols<PAIRWISE>(a, cidx, c, nf.x, nf.y, iu, ia, ib, ru, ra, rb);
+        }
+      };
+      // lazily zeroed tables: the touch-map words of the first kAhead tasks are requested before the norm wait (statically
+      // indexed registers, so the loads stay in flight) and checked right before each task's REDs
+      const unsigned int* wp[kAhead];
+      unsigned int fb[kAhead], tw[kAhead];
+      if (lazy) {
+#pragma unroll
+        for (int t = 0; t < kAhead; ++t) {
+          wp[t] = touch_word(x + t * kScatterWarps, fb[t]);
+          tw[t] = wp[t] ? ld_acquire_u32(wp[t]) : 0u;
+        }
+      }
+      if (!EARLY) mbar_wait(&B.normf[slot], par);  // => every CTA (this one included) has scored and stashed the step
+      mbar_wait(&B.adone[slot], par);  // (long complete) acquire: the loaders' stage writes are visible to this warp
+      if (a.trace && lane == 0 && x == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 5] = gtime();
+      const float2 nf = EARLY ? make_float2(0.f, 0.f) : norms[slot];
+      const float* lab = reinterpret_cast<const float*>(ids + (size_t)R * L.slice);
+      const float* rows = reinterpret_cast<const float*>(stage_ring + (size_t)st * L.stage_slot_bytes());
+      const float* sc = rows + (size_t)R * L.slice * row_f;
+      // every row a task adds into must have its zeros in L2 (bit 1 of the row's pair).  Bounded wait: the owner of a claimed
+      // row is a filler warp that is already past its last blocking wait.
+      auto wait_filled = [&](const unsigned int* p, unsigned int bit, unsigned int w) {
+        for (;;) {
+          const bool ok = p == nullptr || (w & bit) != 0u;
+          if (__all_sync(0xffffffffu, ok)) break;
+          if (!ok) w = ld_acquire_u32(p);
+        }
+      };
+      if (!lazy) {
+        for (int q = x; q < tasks; q += kScatterWarps) scatter_task(q, nf, lab, rows, sc);
+      } else {
+#pragma unroll
+        for (int t = 0; t < kAhead; ++t) {
+          const int q = x + t * kScatterWarps;
+          if (q < tasks) {
+            wait_filled(wp[t], fb[t], tw[t]);
+            scatter_task(q, nf, lab, rows, sc);
+          }
+        }
+        for (int q = x + kAhead * kScatterWarps; q < tasks; q += kScatterWarps) {  // slices beyond kAhead tasks per warp
+          unsigned int bit;
+          const unsigned int* p = touch_word(q, bit);
+          wait_filled(p, bit, p ? ld_acquire_u32(p) : 0u);
+          scatter_task(q, nf, lab, rows, sc);
         }
       }
       __syncwarp();
@@ -728,56 +740,68 @@ __global__ void __launch_bounds__(768, 1) train_steps_staged_kernel(StepsArgs a,
     if (!lazy) return;
     const int f = warp - kServiceWarps - kLoaderWarps - kScatterWarps;
     const int nrows = R * cnt;
-    const uint32_t row_bytes = (uint32_t)row_f * 4u;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     constexpr int kBatch = 8;  // claims in flight per lane: one L2 round trip per 256 rows instead of one per 32
     for (int s = f; s < a.n_steps; s += kFillerWarps) {
       const int slot = s % kRing;
       mbar_wait(&B.idsf[slot], (uint32_t)((s / kRing) & 1));
       while (ld_volatile_smem(progress) < s - 1) __nanosleep(128);
+      if (a.trace && lane == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 4] = gtime();
       const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
       for (int base = 0; base < nrows; base += 32 * kBatch) {
         unsigned int* wp[kBatch];
         unsigned int bit[kBatch], old[kBatch];
-        float* row[kBatch];
-        // all claims of the batch go out back to back ...
+        int packed[kBatch];   // row id | table << 31 (0 = user table, 1 = item table); tables have < 2^31 rows
+        // all claims of the batch go out back to back (one L2 round trip for up to 256 rows) ...
 #pragma unroll
         for (int k = 0; k < kBatch; ++k) {
           const int i = base + 32 * k + lane;
           wp[k] = nullptr;
           bit[k] = 0u;
           old[k] = ~0u;
-          row[k] = nullptr;
+          packed[k] = 0;
           if (i < nrows) {
             const int kind = i / cnt;
             const int64_t id = ids[(size_t)kind * L.slice + (i - kind * cnt)];
             if ((uint64_t)id < (uint64_t)(kind == 0 ? a.n_users : a.n_items)) {
               bit[k] = 1u << (((unsigned int)id & 15u) * 2u);
               wp[k] = (kind == 0 ? a.touch_u : a.touch_i) + (id >> 4);
-              row[k] = shard_row(kind == 0 ? a.user_dst : a.item_dst, 0, id, row_f);
+              packed[k] = (int)id | (kind == 0 ? 0 : (int)0x80000000);
               old[k] = atomicOr(wp[k], bit[k]);
             }
           }
         }
-        // ... then every row this lane won gets one bulk store of a row of zeros (shared -> global, one instruction)
+        // ... then the rows this warp won are zeroed two at a time: lanes 0..15 store the 16-byte chunks of one row, lanes
+        // 16..31 those of another (whole 128-byte lines per store instruction: L2 allocates them without reading DRAM)
         bool any = false;
 #pragma unroll
         for (int k = 0; k < kBatch; ++k) {
-          if (wp[k] != nullptr && (old[k] & bit[k]) == 0u) {
-            bulk_s2g(row[k], zero_row, row_bytes);
-            any = true;
-          } else {
-            wp[k] = nullptr;   // not ours: nothing to publish
+          const bool mine = wp[k] != nullptr && (old[k] & bit[k]) == 0u;
+          if (!mine) wp[k] = nullptr;   // not ours: nothing to publish
+          unsigned int m = __ballot_sync(0xffffffffu, mine);
+          any = any || m != 0u;
+          while (m) {
+            const int l0 = __ffs(m) - 1;
+            m &= m - 1;
+            int l1 = -1;
+            if (m) {
+              l1 = __ffs(m) - 1;
+              m &= m - 1;
+            }
+            const int pk = __shfl_sync(0xffffffffu, packed[k], (lane < 16 || l1 < 0) ? l0 : l1);
+            if (lane < 16 || l1 >= 0) {
+              float* row = shard_row(pk < 0 ? a.item_dst : a.user_dst, 0, (int64_t)(pk & 0x7fffffff), row_f);
+              for (int c = lane & 15; c < a.nv; c += 16) st4(row, c, z4);
+            }
           }
         }
-        if (__any_sync(0xffffffffu, any)) {
-          bulk_store_wait_all();  // this lane's zero rows are written ...
-          __threadfence();        // ... and ordered before the "filled" bits below, for every observer on the device
-        }
+        if (any) __threadfence();  // (warp-uniform) the zeros are in L2 before anybody can see a "filled" bit
 #pragma unroll
         for (int k = 0; k < kBatch; ++k)
           if (wp[k] != nullptr) atomicOr(wp[k], bit[k] << 1);
       }
       __syncwarp();
+      if (a.trace && lane == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 7] = gtime();
       if (lane == 0) mbar_arrive(&B.ifree[slot]);  // this filler no longer needs the step's id tile
     }
   }
@@ -934,13 +958,13 @@ template <int LPR, int VEC, bool PW>
 static int launch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_t s) {
   if (plan.stages > 0 && a.stage_a != nullptr) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsLite>;
-    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsLite), plan.smem, s, a, plan.stages);
+    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsLite, a.touch_u != nullptr), plan.smem, s, a, plan.stages);
   } else if (plan.stages > 0 && g_early_scatter && a.reg_weight == 0.f) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull, true>;
-    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s, a, plan.stages);
+    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull, a.touch_u != nullptr), plan.smem, s, a, plan.stages);
   } else if (plan.stages > 0) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull>;
-    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s, a, plan.stages);
+    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull, a.touch_u != nullptr), plan.smem, s, a, plan.stages);
   } else {
     auto kern = train_steps_regs_kernel<LPR, VEC, PW>;
     XDR_LAUNCH_COOP((kern), plan.grid, kRegThreads, plan.smem, s, a);

@@ -41,7 +41,7 @@ def oracle(dtype):
 lt64, lp64, ref64 = oracle(torch.float64)
 lt32, lp32, ref32 = oracle(torch.float32)
 out = {'batch': batch, 'runs': []}
-for rep in range(3):
+for rep in range(int(os.environ.get('REPS', 3))):
     ct = {k: v.to(dev).requires_grad_(True) for k, v in tabs.items()}
     cp = {k: ([x.to(dev).requires_grad_(True) for x in v] if isinstance(v, list) else v.to(dev).requires_grad_(True)) for k, v in P.items()}
     loss = ops.conet_tower_loss(want, False, n_ov, user.to(dev), item.to(dev), label.to(dev), tuple(ct[k] for k in names),

@@ -137,6 +137,23 @@ def test_conet_fused_tower_kernel(tag):
     check_loss_and_grads(m, g, cuda_batch(g), grad_rtol=2e-4, grad_atol=2e-6)
 
 
+def _relu_knife_edges(tabs, P, user, item, n_ov, eps=1e-5):
+    """[B] bool: interactions with some cross-stitch pre-activation |z| < eps (fp64 forward of conet.py:105-142)."""
+    import torch.nn.functional as F
+    d = torch.float64
+    x_s = torch.cat([tabs['source_user'][user], tabs['source_item'][item]], 1).to(d)
+    x_t = torch.cat([tabs['target_user'][user], tabs['target_item'][item]], 1).to(d)
+    m = (user < n_ov).to(d).unsqueeze(1)
+    edge = torch.zeros(user.shape[0], dtype=torch.bool)
+    for l in range(len(P['ws'])):
+        cross = P['h'][l].to(d).t()
+        zs = F.linear(x_s, P['ws'][l].to(d), P['bs'][l].to(d)) + m * (x_t @ cross)
+        zt = F.linear(x_t, P['wt'][l].to(d), P['bt'][l].to(d)) + m * (x_s @ cross)
+        edge |= (torch.cat([zs, zt], 1).abs() < eps).any(1)
+        x_s, x_t = torch.relu(zs), torch.relu(zt)
+    return edge
+
+
 @pytest.mark.parametrize('batch,dim,hidden,want', [(1, 32, [16], 0), (63, 32, [32, 16, 8], 1), (1000, 64, [64, 32, 16, 8], 0),
                                                    (16384, 128, [64, 32, 16, 8], 1)])
 def test_conet_fused_matches_oracle(batch, dim, hidden, want):
@@ -153,6 +170,16 @@ def test_conet_fused_matches_oracle(batch, dim, hidden, want):
              out_s_w=mk(dims[-1], 1, 0.5), out_s_b=torch.randn(1, generator=gen) * 0.1,
              out_t_w=mk(dims[-1], 1, 0.5), out_t_b=torch.randn(1, generator=gen) * 0.1)
     user, item = rand_ids(batch, n_u, 7, 1.3), rand_ids(batch, n_i, 8)
+    # ReLU is not differentiable at 0: an interaction with a pre-activation within rounding distance of 0 gets a different
+    # (equally valid) sub-gradient from any implementation whose dot products round differently.  Round 2, call 2: with
+    # 16384 rows one interaction (position 2938, layer-2 pre-activation 2.9e-7 in fp64) made the 3xTF32 kernel differ from the
+    # fp32 oracle by exactly that interaction's gradient (scripts/diag_conet_hot.py; no race: compute-sanitizer racecheck clean,
+    # bit-reproducible, the CPU emulator agrees with the oracle).  Such interactions get another item.
+    for _ in range(8):
+        edge = _relu_knife_edges(tabs, P, user, item, n_ov)
+        if not bool(edge.any()):
+            break
+        item = torch.where(edge, (item + 1) % n_i, item)
     label = (torch.rand(batch, generator=gen) < 0.5).float()
     lt = {k: v.clone().requires_grad_(True) for k, v in tabs.items()}
     lp = {k: ([x.clone().requires_grad_(True) for x in v] if isinstance(v, list) else v.clone().requires_grad_(True))

@@ -55,11 +55,14 @@ def test_lazy_tables_equal_the_plain_scatter_add(nu, ni, dim, K, B, zipf):
     torch.testing.assert_close(gu[nu_m], gu_ref[nu_m], rtol=1e-5, atol=max(atol_u, 1e-9))
     torch.testing.assert_close(gi[ni_m], gi_ref[ni_m], rtol=1e-5, atol=max(atol_i, 1e-9))
     assert bool((gu[~nu_m] == 7.0).all()) and bool((gi[~ni_m] == -3.0).all())
-    # a second launch without clearing keeps accumulating: twice the gradient on the marked rows
+    # a second launch without clearing keeps accumulating: twice the gradient on the marked rows.  Tolerance: adding a row's
+    # contributions a second time ON TOP of their sum rounds differently from doubling the sum -- measured on a B200
+    # (scripts/diag_accum_noise.py, Zipf ids, 33 000 duplicates of one row): 1.8e-6 absolute = 1e-4 of the table's maximum,
+    # identically for plain and lazily zeroed destinations.
     ops.train_steps(ut, it, u, ip, ineg, reg_weight=0.01, user_dst=gu, item_dst=gi, touch=tm, fresh=False)
     torch.cuda.synchronize()
-    torch.testing.assert_close(gu[nu_m], 2 * gu_ref[nu_m], rtol=1e-5, atol=max(2 * atol_u, 1e-9))
-    torch.testing.assert_close(gi[ni_m], 2 * gi_ref[ni_m], rtol=1e-5, atol=max(2 * atol_i, 1e-9))
+    torch.testing.assert_close(gu[nu_m], 2 * gu_ref[nu_m], rtol=1e-5, atol=max(2e-4 * float(gu_ref.abs().max()), 1e-9))
+    torch.testing.assert_close(gi[ni_m], 2 * gi_ref[ni_m], rtol=1e-5, atol=max(2e-4 * float(gi_ref.abs().max()), 1e-9))
 
 
 def test_lazy_tables_match_the_oracle_and_pointwise_kinds():

@@ -46,17 +46,14 @@ constexpr int kWorkerWarps = 20;   // register kernel: workers
 #define XDR_LOADER_WARPS 14
 #endif
 #ifndef XDR_SCATTER_WARPS
-#define XDR_SCATTER_WARPS 4
+#define XDR_SCATTER_WARPS 6
 #endif
 constexpr int kLoaderWarpsFull = XDR_LOADER_WARPS;  // staged kernel: loaders when the CTA owns the whole SM ...
 constexpr int kLoaderWarpsLite = 10;                // ... and when item rows are pre-staged by the peer-gather kernel, whose
                                                     // CTAs must fit next to this one (register file: 576 x 80 + 256 x 40)
 constexpr int kScatterWarps = XDR_SCATTER_WARPS;    // scatterers
 constexpr int kRegThreads = (kServiceWarps + kWorkerWarps) * 32;
-constexpr int kFillerWarps = 2;                     // staged kernel: zero-fill warps of the lazily zeroed gradient tables
-__host__ __device__ constexpr int staged_threads(int loaders, bool lazy = true) {   // the filler warps come last: a launch
-  return (kServiceWarps + loaders + kScatterWarps + (lazy ? kFillerWarps : 0)) * 32;  // without them simply has fewer threads
-}
+__host__ __device__ constexpr int staged_threads(int loaders) { return (kServiceWarps + loaders + kScatterWarps) * 32; }
 // register cap of the staged kernel: 768 threads -> 80 registers; so that in the lite configuration a 256-thread peer-gather
 // CTA still fits in the SM's register file next to this CTA
 constexpr int kStagedBound = staged_threads(kLoaderWarpsFull) > 768 ? staged_threads(kLoaderWarpsFull) : 768;
@@ -119,12 +116,6 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   emu::yield();
   return *p;
 }
-__device__ __forceinline__ int ld_volatile_smem(const int* p) {
-  emu::yield();
-  return *p;
-}
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) { emu::bulk_s2g(dst_gmem, src_smem, bytes); }
-__device__ __forceinline__ void bulk_store_wait_all() { emu::bulk_store_wait_all(); }
 #else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -188,17 +179,6 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ int ld_volatile_smem(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
-// TMA 1-D bulk copy shared -> global (one thread, one instruction per row), completion through the thread's bulk async-group
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
-               : "memory");
-}
-// every bulk store this thread has issued is complete (written, not just read from shared memory)
-__device__ __forceinline__ void bulk_store_wait_all() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
 #endif  // XDR_EMU
 // coherent (L2) 128-bit row load: the table may be the scatter destination of this very launch (fused SGD)
 __device__ __forceinline__ float4 ldcg_row4(const float* row, int col4) {
@@ -210,14 +190,10 @@ struct SmemLayout {
   int slice, rows_per, tasks, row_f, stages;  // S, 2|3, tasks per step per CTA (upper bound), floats per row, stage count
   __host__ __device__ SmemLayout(int s, int r, int t, int rf = 0, int ns = 0)
       : slice(s), rows_per(r), tasks(t), row_f(rf), stages(ns) {}
-  // [0, 288): 4 x kRing + kMaxStages mbarriers.  [288, 292): steps whose partials this CTA has published (filler throttle).
-  // [320, 384): norms [kRing][2].  [384, 1408): one row of zeros (source of the fillers' bulk stores).  then partials, id
-  // ring, stage ring.
+  // [0, 320): 4 x kRing + kMaxStages mbarriers.  [320, 384): norms [kRing][2].  then partials, id ring, stage ring.
   __host__ __device__ size_t bars_off() const { return 0; }
-  __host__ __device__ size_t progress_off() const { return 288; }
   __host__ __device__ size_t norms_off() const { return 320; }
-  __host__ __device__ size_t zero_off() const { return 384; }
-  __host__ __device__ size_t part_off() const { return 1408; }
+  __host__ __device__ size_t part_off() const { return 384; }
   __host__ __device__ size_t ids_off() const {
     return (part_off() + (size_t)kRing * tasks * sizeof(float4) + 127) & ~(size_t)127;
   }
@@ -276,12 +252,11 @@ __device__ __forceinline__ void service_producer(const StepsArgs& a, const SmemL
 
 // per step: sum this CTA's task partials in a fixed order and publish them as three 8-byte {value, tag} words
 __device__ __forceinline__ void service_publisher(const StepsArgs& a, const SmemLayout& L, const Bars& B,
-                                                  const float4* part, int tasks, int lane, int* progress) {
+                                                  const float4* part, int tasks, int lane) {
   const unsigned int n_cta = gridDim.x;
   for (int s = 0; s < a.n_steps; ++s) {
     const int slot = s % kRing;
     mbar_wait(&B.adone[slot], (uint32_t)((s / kRing) & 1));
-    if (lane == 0) *reinterpret_cast<volatile int*>(progress) = s + 1;  // this CTA's loaders are past step s
     if (a.trace && lane == 0) a.trace[((size_t)s * n_cta + blockIdx.x) * 8 + 0] = gtime();
     float p0 = 0.f, p1 = 0.f, p2 = 0.f;
     for (int q = lane; q < tasks; q += 32) {
@@ -504,17 +479,27 @@ __device__ __forceinline__ float score_coeff(const StepsArgs& a, float g, float 
   return 0.f;
 }
 
+// How a gradient row reaches its destination.  kRowAdd: RED (scatter-add).  kRowStore: plain 128-bit stores -- the row's FIRST
+// touch since the touch map was cleared (lazily zeroed tables): whatever the destination holds counts as zero and is
+// overwritten, whole lines at a time, so L2 allocates them without reading DRAM.  kRowSkip: nothing (bad id, or deferred).
+enum RowMode : int { kRowSkip = 0, kRowAdd = 1, kRowStore = 2 };
+__device__ __forceinline__ void emit_row4(int mode, float* row, int cidx, float4 v) {
+  if (mode == kRowAdd) red_add4(row, cidx, v);
+  else if (mode == kRowStore) st4(row, cidx, v);
+}
+
 template <bool PAIRWISE>
 __device__ __forceinline__ void scatter_cols(const StepsArgs& a, int cidx, float c, float cu, float ci, int iu, int ia,
-                                             int ib, float4 ru, float4 ra, float4 rb) {
+                                             int ib, float4 ru, float4 ra, float4 rb, int mu = kRowAdd, int ma = kRowAdd,
+                                             int mb = kRowAdd) {
   const int64_t row_f = (int64_t)a.nv * 4;
   if (PAIRWISE) {
-    if (iu >= 0) red_add4(shard_row(a.user_dst, a.log2g, iu, row_f), cidx, axpy4(cu, ru, scale4(c, sub4(ra, rb))));
-    if (ia >= 0) red_add4(shard_row(a.item_dst, a.log2g, ia, row_f), cidx, axpy4(ci, ra, scale4(c, ru)));
-    if (ib >= 0) red_add4(shard_row(a.item_dst, a.log2g, ib, row_f), cidx, scale4(-c, ru));
+    if (iu >= 0) emit_row4(mu, shard_row(a.user_dst, a.log2g, iu, row_f), cidx, axpy4(cu, ru, scale4(c, sub4(ra, rb))));
+    if (ia >= 0) emit_row4(ma, shard_row(a.item_dst, a.log2g, ia, row_f), cidx, axpy4(ci, ra, scale4(c, ru)));
+    if (ib >= 0) emit_row4(mb, shard_row(a.item_dst, a.log2g, ib, row_f), cidx, scale4(-c, ru));
   } else {
-    if (iu >= 0) red_add4(shard_row(a.user_dst, a.log2g, iu, row_f), cidx, axpy4(cu, ru, scale4(c, ra)));
-    if (ia >= 0) red_add4(shard_row(a.item_dst, a.log2g, ia, row_f), cidx, axpy4(ci, ra, scale4(c, ru)));
+    if (iu >= 0) emit_row4(mu, shard_row(a.user_dst, a.log2g, iu, row_f), cidx, axpy4(cu, ru, scale4(c, ra)));
+    if (ia >= 0) emit_row4(ma, shard_row(a.item_dst, a.log2g, ia, row_f), cidx, axpy4(ci, ra, scale4(c, ru)));
   }
 }
 
@@ -538,7 +523,7 @@ __device__ __forceinline__ void init_bars(const Bars& B, int tasks, int ifree_co
 // the batch-wide norms, so the scatterers do not wait for the step's norm exchange before they issue the REDs and free the
 // stage slot; they still wait for it before they free the id slot, which keeps the id / partial / norm rings in step (the
 // per-step loss is still the exchanged batch mean).
-template <int LPR, int VEC, bool PAIRWISE, int kLoaderWarps, bool EARLY = false>
+template <int LPR, int VEC, bool PAIRWISE, int kLoaderWarps, bool EARLY = false, bool LAZY = false>
 __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(StepsArgs a, int n_stages) {
   constexpr int IPW = 32 / LPR;
   constexpr int R = PAIRWISE ? 3 : 2;
@@ -551,29 +536,18 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
   const Bars B(smem_raw + L.bars_off());
   float2* norms = reinterpret_cast<float2*>(smem_raw + L.norms_off());
   float4* part = reinterpret_cast<float4*>(smem_raw + L.part_off());
-  int* progress = reinterpret_cast<int*>(smem_raw + L.progress_off());
-  float* zero_row = reinterpret_cast<float*>(smem_raw + L.zero_off());
   unsigned char* ids_ring = smem_raw + L.ids_off();
   unsigned char* stage_ring = smem_raw + L.stage_off();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool lazy = a.touch_u != nullptr;  // lazily zeroed destination tables: filler warps are live and use the id tiles too
-  if (lazy) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) zero_row[i] = 0.f;
-#ifndef XDR_EMU
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros -> visible to the bulk-copy engine
-#endif
-  }
+  constexpr bool lazy = LAZY;  // lazily zeroed destination tables (a.touch_u / a.touch_i): first touch stores, see the scatterers
 
-  if (threadIdx.x == 0) {
-    init_bars(B, tasks, kScatterWarps + (lazy ? 1 : 0), n_stages, kScatterWarps);
-    *progress = 0;
-  }
+  if (threadIdx.x == 0) init_bars(B, tasks, kScatterWarps, n_stages, kScatterWarps);
   __syncthreads();
 
   if (warp == 0) {
     service_producer<PAIRWISE>(a, L, B, ids_ring, first, cnt, lane);
   } else if (warp == 1) {
-    service_publisher(a, L, B, part, tasks, lane, progress);
+    service_publisher(a, L, B, part, tasks, lane);
   } else if (warp < kServiceWarps) {
     service_gatherer(a, B, norms, warp - 2, lane);
   } else if (warp < kServiceWarps + kLoaderWarps) {
@@ -629,31 +603,49 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
       score_and_stash(r1);
       lt = nx;
     }
-  } else if (warp < kServiceWarps + kLoaderWarps + kScatterWarps) {
+  } else {
     // ------------------------------------------------ scatterers ------------------------------------------------------
+    // Lazily zeroed destination tables (a.touch_u != NULL), "store first": every row of a task is CLAIMED (atomicOr of bit 0
+    // of the row's pair in the touch map; requested before the norm wait, so the round trip hides behind the exchange).
+    //   won the claim          -> nobody has touched the row since the map was cleared: the gradient is STORED (whole lines, no
+    //                             DRAM read, whatever the row held is overwritten), and after the warp's per-step fence the
+    //                             row's "filled" bit (bit 1) is set;
+    //   lost, row filled       -> RED as usual (the line is in L2 or is fetched: an honest accumulate);
+    //   lost, not yet filled   -> deferred to the end of the step: wait for the bit, then RED.  The winner is a scatter warp
+    //                             that sets the bit after its own stores + fence without waiting for anybody (a warp sets
+    //                             its own bits BEFORE it turns to its deferred rows), so the wait is bounded.
     const int x = warp - kServiceWarps - kLoaderWarps;
     const int sub = lane % LPR, grp = lane / LPR;
     const float inv_b = 1.0f / (float)a.batch;
     const float g = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f) * a.scale;
-    constexpr int kAhead = 4;  // lazily zeroed tables: "filled" words of this many tasks are requested before they are needed
+    constexpr int kT = 4;  // tasks of a step whose claims a warp keeps in flight (statically indexed registers)
     for (int s = 0; s < a.n_steps; ++s) {
       const int slot = s % kRing, st = s % n_stages;
       const uint32_t par = (uint32_t)((s / kRing) & 1);
       mbar_wait(&B.idsf[slot], par);   // (long complete) acquire: the TMA-written ids are visible to this warp
       const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
-      // lazily zeroed tables: lanes 0..R-1 of an interaction's group look after the user / item+ / item- row; the word that
-      // holds the row's "filled" bit is requested here, before the norm wait, and checked right before the REDs
-      auto touch_word = [&](int q, unsigned int& fbit) -> const unsigned int* {
-        fbit = 0u;
+      const float* lab = reinterpret_cast<const float*>(ids + (size_t)R * L.slice);
+      const float* rows = reinterpret_cast<const float*>(stage_ring + (size_t)st * L.stage_slot_bytes());
+      const float* sc = rows + (size_t)R * L.slice * row_f;
+      // lanes 0..R-1 of an interaction's group look after the touch-map word of its user / item+ / item- row
+      auto touch_word = [&](int q, unsigned int& cbit) -> unsigned int* {
+        cbit = 0u;
         const int j = q * IPW + grp;
         if (q >= tasks || j >= cnt || sub >= R) return nullptr;
         const int64_t id = ids[(size_t)sub * L.slice + j];
         if ((uint64_t)id >= (uint64_t)(sub == 0 ? a.n_users : a.n_items)) return nullptr;
-        fbit = 2u << (((unsigned int)id & 15u) * 2u);
+        cbit = 1u << (((unsigned int)id & 15u) * 2u);
         return (sub == 0 ? a.touch_u : a.touch_i) + (id >> 4);
       };
-      // one task: the rows of 32 / LPR interactions -> gradient rows -> RED
-      auto scatter_task = [&](int q, float2 nf, const float* lab, const float* rows, const float* sc) {
+      // one task: the rows of 32 / LPR interactions -> gradient rows -> destination, each row in its own mode (the modes of
+      // the group's three rows sit in lanes 0..2 of the group); only == kRowAdd/-1: restrict to rows whose mode was `only`
+      auto scatter_task = [&](int q, float2 nf, int my_mode) {
+        int mu = kRowAdd, ma = kRowAdd, mb = kRowAdd;
+        if (lazy) {
+          mu = __shfl_sync(0xffffffffu, my_mode, grp * LPR);
+          ma = __shfl_sync(0xffffffffu, my_mode, grp * LPR + 1);
+          mb = PAIRWISE ? __shfl_sync(0xffffffffu, my_mode, grp * LPR + 2) : kRowSkip;
+        }
         const int j = q * IPW + grp;
         if (j >= cnt) return;
         const int64_t iu64 = ids[j], ia64 = ids[L.slice + j], ib64 = PAIRWISE ? ids[2 * L.slice + j] : 0;
@@ -669,52 +661,73 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
           const float4 ru = ld_row4(rows + (size_t)j * row_f, cidx);
           const float4 ra = ld_row4(rows + ((size_t)L.slice + j) * row_f, cidx);
           const float4 rb = PAIRWISE ? ld_row4(rows + ((size_t)2 * L.slice + j) * row_f, cidx) : ru;
-          scatter_cols<PAIRWISE>(a, cidx, c, nf.x, nf.y, iu, ia, ib, ru, ra, rb);
+          scatter_cols<PAIRWISE>(a, cidx, c, nf.x, nf.y, iu, ia, ib, ru, ra, rb, mu, ma, mb);
         }
       };
-      // lazily zeroed tables: the touch-map words of the first kAhead tasks are requested before the norm wait (statically
-      // indexed registers, so the loads stay in flight) and checked right before each task's REDs
-      const unsigned int* wp[kAhead];
-      unsigned int fb[kAhead], tw[kAhead];
-      if (lazy) {
+      unsigned int* wp[kT];
+      unsigned int cb[kT], old[kT];
+      if (lazy) {   // the claims of this warp's first kT tasks go out before the norm wait
 #pragma unroll
-        for (int t = 0; t < kAhead; ++t) {
-          wp[t] = touch_word(x + t * kScatterWarps, fb[t]);
-          tw[t] = wp[t] ? ld_acquire_u32(wp[t]) : 0u;
+        for (int t = 0; t < kT; ++t) {
+          wp[t] = touch_word(x + t * kScatterWarps, cb[t]);
+          old[t] = wp[t] ? atomicOr(wp[t], cb[t]) : 0u;
         }
       }
       if (!EARLY) mbar_wait(&B.normf[slot], par);  // => every CTA (this one included) has scored and stashed the step
       mbar_wait(&B.adone[slot], par);  // (long complete) acquire: the loaders' stage writes are visible to this warp
       if (a.trace && lane == 0 && x == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 5] = gtime();
       const float2 nf = EARLY ? make_float2(0.f, 0.f) : norms[slot];
-      const float* lab = reinterpret_cast<const float*>(ids + (size_t)R * L.slice);
-      const float* rows = reinterpret_cast<const float*>(stage_ring + (size_t)st * L.stage_slot_bytes());
-      const float* sc = rows + (size_t)R * L.slice * row_f;
-      // every row a task adds into must have its zeros in L2 (bit 1 of the row's pair).  Bounded wait: the owner of a claimed
-      // row is a filler warp that is already past its last blocking wait.
-      auto wait_filled = [&](const unsigned int* p, unsigned int bit, unsigned int w) {
-        for (;;) {
-          const bool ok = p == nullptr || (w & bit) != 0u;
-          if (__all_sync(0xffffffffu, ok)) break;
-          if (!ok) w = ld_acquire_u32(p);
-        }
-      };
       if (!lazy) {
-        for (int q = x; q < tasks; q += kScatterWarps) scatter_task(q, nf, lab, rows, sc);
+        for (int q = x; q < tasks; q += kScatterWarps) scatter_task(q, nf, kRowAdd);
       } else {
+        for (int q0 = x; q0 < tasks; q0 += kT * kScatterWarps) {   // (one round unless a warp owns more than kT tasks)
+          if (q0 != x) {
 #pragma unroll
-        for (int t = 0; t < kAhead; ++t) {
-          const int q = x + t * kScatterWarps;
-          if (q < tasks) {
-            wait_filled(wp[t], fb[t], tw[t]);
-            scatter_task(q, nf, lab, rows, sc);
+            for (int t = 0; t < kT; ++t) {
+              wp[t] = touch_word(q0 + t * kScatterWarps, cb[t]);
+              old[t] = wp[t] ? atomicOr(wp[t], cb[t]) : 0u;
+            }
           }
-        }
-        for (int q = x + kAhead * kScatterWarps; q < tasks; q += kScatterWarps) {  // slices beyond kAhead tasks per warp
-          unsigned int bit;
-          const unsigned int* p = touch_word(q, bit);
-          wait_filled(p, bit, p ? ld_acquire_u32(p) : 0u);
-          scatter_task(q, nf, lab, rows, sc);
+          // pass 1: store what we won, add to what is filled, remember the rest
+          bool won_any = false, deferred_any = false;
+          int mode[kT];
+#pragma unroll
+          for (int t = 0; t < kT; ++t) {
+            mode[t] = kRowSkip;
+            bool defer = false;
+            if (wp[t] != nullptr) {
+              if ((old[t] & cb[t]) == 0u) mode[t] = kRowStore;
+              else if ((old[t] & (cb[t] << 1)) != 0u) mode[t] = kRowAdd;
+              else defer = true;
+            }
+            won_any = won_any || mode[t] == kRowStore;
+            deferred_any = deferred_any || defer;
+            if (q0 + t * kScatterWarps < tasks) scatter_task(q0 + t * kScatterWarps, nf, mode[t]);
+            if (!defer) { if (mode[t] != kRowStore) wp[t] = nullptr; }   // keep the word of won rows (to publish) ...
+            else mode[t] = -1;                                            // ... and of deferred rows (to wait for)
+          }
+          // publish the rows stored above: every lane's stores are in L2 (fence), all lanes are past their fence (syncwarp)
+          if (__any_sync(0xffffffffu, won_any)) {
+            __threadfence();
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < kT; ++t)
+              if (mode[t] == kRowStore) atomicOr(wp[t], cb[t] << 1);
+          }
+          // pass 2: rows somebody else is still storing -- wait for their "filled" bit, then add
+          if (__any_sync(0xffffffffu, deferred_any)) {
+#pragma unroll
+            for (int t = 0; t < kT; ++t) {
+              const bool mine = mode[t] == -1;
+              if (__any_sync(0xffffffffu, mine)) {
+                for (;;) {
+                  const bool ok = !mine || (ld_acquire_u32(wp[t]) & (cb[t] << 1)) != 0u;
+                  if (__all_sync(0xffffffffu, ok)) break;
+                }
+                scatter_task(q0 + t * kScatterWarps, nf, mine ? (int)kRowAdd : (int)kRowSkip);
+              }
+            }
+          }
         }
       }
       __syncwarp();
@@ -727,82 +740,6 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
         mbar_arrive(&B.sfree[st]);    // the stage slot may be overwritten by the loaders
         mbar_arrive(&B.ifree[slot]);  // the id slot may be refilled by the producer
       }
-    }
-  } else {
-    // ------------------------------------------------ fillers ---------------------------------------------------------
-    // Lazily zeroed gradient tables.  Filler f looks after steps f, f + kFillerWarps, ...: for every row the CTA's slice of
-    // the step names it tries to CLAIM the row (atomicOr of bit 0 of the row's pair); rows it wins are rows nobody has
-    // touched since the map was cleared -- it stores a full row of zeros (full-line stores: L2 allocates the lines without
-    // reading DRAM), fences, and only then sets the "filled" bit that the scatter warps of EVERY CTA wait for.  Rows it
-    // loses belong to some other filler, which is by then past its last blocking wait.  Throttle: step s is filled when the
-    // CTA's loaders are on step s - 1, about two steps before the scatter, so the zero lines are still in L2 when the REDs
-    // arrive.
-    if (!lazy) return;
-    const int f = warp - kServiceWarps - kLoaderWarps - kScatterWarps;
-    const int nrows = R * cnt;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    constexpr int kBatch = 8;  // claims in flight per lane: one L2 round trip per 256 rows instead of one per 32
-    for (int s = f; s < a.n_steps; s += kFillerWarps) {
-      const int slot = s % kRing;
-      mbar_wait(&B.idsf[slot], (uint32_t)((s / kRing) & 1));
-      while (ld_volatile_smem(progress) < s - 1) __nanosleep(128);
-      if (a.trace && lane == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 4] = gtime();
-      const int64_t* ids = reinterpret_cast<const int64_t*>(ids_ring + (size_t)slot * L.ids_slot_bytes());
-      for (int base = 0; base < nrows; base += 32 * kBatch) {
-        unsigned int* wp[kBatch];
-        unsigned int bit[kBatch], old[kBatch];
-        int packed[kBatch];   // row id | table << 31 (0 = user table, 1 = item table); tables have < 2^31 rows
-        // all claims of the batch go out back to back (one L2 round trip for up to 256 rows) ...
-#pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
-          const int i = base + 32 * k + lane;
-          wp[k] = nullptr;
-          bit[k] = 0u;
-          old[k] = ~0u;
-          packed[k] = 0;
-          if (i < nrows) {
-            const int kind = i / cnt;
-            const int64_t id = ids[(size_t)kind * L.slice + (i - kind * cnt)];
-            if ((uint64_t)id < (uint64_t)(kind == 0 ? a.n_users : a.n_items)) {
-              bit[k] = 1u << (((unsigned int)id & 15u) * 2u);
-              wp[k] = (kind == 0 ? a.touch_u : a.touch_i) + (id >> 4);
-              packed[k] = (int)id | (kind == 0 ? 0 : (int)0x80000000);
-              old[k] = atomicOr(wp[k], bit[k]);
-            }
-          }
-        }
-        // ... then the rows this warp won are zeroed two at a time: lanes 0..15 store the 16-byte chunks of one row, lanes
-        // 16..31 those of another (whole 128-byte lines per store instruction: L2 allocates them without reading DRAM)
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
-          const bool mine = wp[k] != nullptr && (old[k] & bit[k]) == 0u;
-          if (!mine) wp[k] = nullptr;   // not ours: nothing to publish
-          unsigned int m = __ballot_sync(0xffffffffu, mine);
-          any = any || m != 0u;
-          while (m) {
-            const int l0 = __ffs(m) - 1;
-            m &= m - 1;
-            int l1 = -1;
-            if (m) {
-              l1 = __ffs(m) - 1;
-              m &= m - 1;
-            }
-            const int pk = __shfl_sync(0xffffffffu, packed[k], (lane < 16 || l1 < 0) ? l0 : l1);
-            if (lane < 16 || l1 >= 0) {
-              float* row = shard_row(pk < 0 ? a.item_dst : a.user_dst, 0, (int64_t)(pk & 0x7fffffff), row_f);
-              for (int c = lane & 15; c < a.nv; c += 16) st4(row, c, z4);
-            }
-          }
-        }
-        if (any) __threadfence();  // (warp-uniform) the zeros are in L2 before anybody can see a "filled" bit
-#pragma unroll
-        for (int k = 0; k < kBatch; ++k)
-          if (wp[k] != nullptr) atomicOr(wp[k], bit[k] << 1);
-      }
-      __syncwarp();
-      if (a.trace && lane == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 7] = gtime();
-      if (lane == 0) mbar_arrive(&B.ifree[slot]);  // this filler no longer needs the step's id tile
     }
   }
 }
@@ -822,20 +759,16 @@ __global__ void __launch_bounds__(kRegThreads, 1) train_steps_regs_kernel(StepsA
   const Bars B(smem_raw + L.bars_off());
   float2* norms = reinterpret_cast<float2*>(smem_raw + L.norms_off());
   float4* part = reinterpret_cast<float4*>(smem_raw + L.part_off());
-  int* progress = reinterpret_cast<int*>(smem_raw + L.progress_off());
   unsigned char* ids_ring = smem_raw + L.ids_off();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (threadIdx.x == 0) {
-    init_bars(B, tasks, tasks, 0, 1);
-    *progress = 0;
-  }
+  if (threadIdx.x == 0) init_bars(B, tasks, tasks, 0, 1);
   __syncthreads();
 
   if (warp == 0) {
     service_producer<PAIRWISE>(a, L, B, ids_ring, first, cnt, lane);
   } else if (warp == 1) {
-    service_publisher(a, L, B, part, tasks, lane, progress);
+    service_publisher(a, L, B, part, tasks, lane);
   } else if (warp < kServiceWarps) {
     service_gatherer(a, B, norms, warp - 2, lane);
   } else {
@@ -956,15 +889,19 @@ static int g_early_scatter = 0;  // opt-in (xdr_steps_set_early_scatter): reg_we
 
 template <int LPR, int VEC, bool PW>
 static int launch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_t s) {
+  const bool lazy = a.touch_u != nullptr;
   if (plan.stages > 0 && a.stage_a != nullptr) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsLite>;
-    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsLite, a.touch_u != nullptr), plan.smem, s, a, plan.stages);
+    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsLite), plan.smem, s, a, plan.stages);
+  } else if (plan.stages > 0 && lazy) {
+    auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull, false, true>;
+    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s, a, plan.stages);
   } else if (plan.stages > 0 && g_early_scatter && a.reg_weight == 0.f) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull, true>;
-    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull, a.touch_u != nullptr), plan.smem, s, a, plan.stages);
+    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s, a, plan.stages);
   } else if (plan.stages > 0) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull>;
-    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull, a.touch_u != nullptr), plan.smem, s, a, plan.stages);
+    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s, a, plan.stages);
   } else {
     auto kern = train_steps_regs_kernel<LPR, VEC, PW>;
     XDR_LAUNCH_COOP((kern), plan.grid, kRegThreads, plan.smem, s, a);

@@ -66,6 +66,23 @@ __device__ __forceinline__ void m5_stage_matrix(const float* __restrict__ W, int
   }
 }
 
+// Column sums over the 32 lanes of a warp of 16 values per lane in 16 shuffles (instead of 16 x 5): every exchange halves the
+// columns a lane keeps.  Returns the sum of column `col` (the same in both lanes of a pair; the even lane publishes it).
+__device__ __forceinline__ float m5_warp_colsum16(const float (&v)[16], int lane, int& col) {
+  float a8[8], b4[4], c2[2];
+  const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0, h2 = (lane & 2) != 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a8[j] = (h16 ? v[j + 8] : v[j]) + __shfl_xor_sync(0xffffffffu, h16 ? v[j] : v[j + 8], 16);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b4[j] = (h8 ? a8[j + 4] : a8[j]) + __shfl_xor_sync(0xffffffffu, h8 ? a8[j] : a8[j + 4], 8);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) c2[j] = (h4 ? b4[j + 2] : b4[j]) + __shfl_xor_sync(0xffffffffu, h4 ? b4[j] : b4[j + 2], 4);
+  float d = (h2 ? c2[1] : c2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? c2[0] : c2[1], 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  col = (h16 ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);
+  return d;
+}
+
 __device__ __forceinline__ float m5_bf16_pair_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float m5_bf16_pair_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
@@ -138,19 +155,43 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
         my_id = -1;
       }
     }
-    // ---- gather the source rows -> X tile (rows past the batch / bad ids are zero) ---------------------------------------------
-    for (int e = tid; e < kM5Rows * c8n; e += kM5Threads) {
-      const int r = e / c8n, c8 = e - r * c8n;
-      const int64_t gr = tile * kM5Rows + r;
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-      if (gr < a.batch) {
-        const int64_t id = a.idx_u[gr];
-        if ((uint64_t)id < (uint64_t)a.n_u) {
-          v0 = ld_row4(a.Au + id * D, 2 * c8);
-          v1 = ld_row4(a.Au + id * D, 2 * c8 + 1);
+    // ---- gather the source rows -> X tile (rows past the batch / bad ids are zero).  All of a thread's loads are issued before
+    // the first conversion (8 threads per row, 16 rows per pass), and the thread's own target row -- needed two products later
+    // -- is requested here too, so that its latency hides behind G1 / G2 instead of stalling the loss epilogue
+    float4 trow[kM5MaxDim / 4];
+#pragma unroll
+    for (int q = 0; q < kM5MaxDim / 4; ++q) {
+      trow[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (my_id >= 0 && 4 * q < D) trow[q] = ld_row4(a.T + my_id * D, q);
+    }
+    constexpr int kGatherPasses = kM5Rows * (kM5MaxDim / 8) / kM5Threads;   // 8 at D = 64
+    {
+      float4 g0[kGatherPasses], g1[kGatherPasses];
+#pragma unroll
+      for (int p = 0; p < kGatherPasses; ++p) {
+        const int e = tid + p * kM5Threads;
+        g0[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g1[p] = g0[p];
+        if (e < kM5Rows * c8n) {
+          const int r = e / c8n, c8 = e - r * c8n;
+          const int64_t gr = tile * kM5Rows + r;
+          if (gr < a.batch) {
+            const int64_t id = a.idx_u[gr];
+            if ((uint64_t)id < (uint64_t)a.n_u) {
+              g0[p] = ld_row4(a.Au + id * D, 2 * c8);
+              g1[p] = ld_row4(a.Au + id * D, 2 * c8 + 1);
+            }
+          }
         }
       }
-      tc5::store_split8(Xh, Xl, tX.chunk_offset(r, c8), v0, v1);
+#pragma unroll
+      for (int p = 0; p < kGatherPasses; ++p) {
+        const int e = tid + p * kM5Threads;
+        if (e < kM5Rows * c8n) {
+          const int r = e / c8n, c8 = e - r * c8n;
+          tc5::store_split8(Xh, Xl, tX.chunk_offset(r, c8), g0[p], g1[p]);
+        }
+      }
     }
     epilogue_done();
 
@@ -183,15 +224,16 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
     }
     wait_mma();
     // loss head: d = Y + b2 - T[id]; loss += d^2; dY = gs d; the target rows get -dY (emcdr.py:156-168: target not detached)
-    for (int c16 = 0; c16 < D / 16; ++c16) {
+#pragma unroll   // constant trip count: trow[] stays in registers
+    for (int c16 = 0; c16 < kM5MaxDim / 16; ++c16) {
+      if (c16 * 16 >= D) break;
       uint32_t r[16];
       tc5::tmem_ld16(tmem + my_lanes + kM5ColY + c16 * 16, r);
       tc5::tmem_ld_wait();
       float g[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (my_id >= 0) t = ld_row4(a.T + my_id * D, 4 * c16 + q);
+        const float4 t = trow[4 * c16 + q];
         const float tv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -207,10 +249,10 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
         tc5::store_split8(Yh, Yl, tX.chunk_offset(tid, 2 * c16), make_float4(g[0], g[1], g[2], g[3]), make_float4(g[4], g[5], g[6], g[7]));
         tc5::store_split8(Yh, Yl, tX.chunk_offset(tid, 2 * c16 + 1), make_float4(g[8], g[9], g[10], g[11]),
                           make_float4(g[12], g[13], g[14], g[15]));
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {   // db2: column sums over the tile's rows
-          const float s = warp_sum(g[j]);
-          if (lane == 0) atomicAdd(&dbs[kM5Hidden + c16 * 16 + j], s);
+        {   // db2: column sums over the tile's rows
+          int col;
+          const float s = m5_warp_colsum16(g, lane, col);
+          if ((lane & 1) == 0) atomicAdd(&dbs[kM5Hidden + c16 * 16 + col], s);
         }
       }
     }
@@ -247,10 +289,10 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
       tc5::store_split8(Hh, Hl, tH.chunk_offset(tid, 2 * c16), make_float4(z[0], z[1], z[2], z[3]), make_float4(z[4], z[5], z[6], z[7]));
       tc5::store_split8(Hh, Hl, tH.chunk_offset(tid, 2 * c16 + 1), make_float4(z[8], z[9], z[10], z[11]),
                         make_float4(z[12], z[13], z[14], z[15]));
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {     // db1
-        const float s = warp_sum(z[j]);
-        if (lane == 0) atomicAdd(&dbs[c16 * 16 + j], s);
+      {     // db1
+        int col;
+        const float s = m5_warp_colsum16(z, lane, col);
+        if ((lane & 1) == 0) atomicAdd(&dbs[c16 * 16 + col], s);
       }
     }
     epilogue_done();
@@ -287,9 +329,12 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
       uint32_t r[16];
       tc5::tmem_ld16(tmem + my_lanes + kM5ColDW1 + c16 * 16, r);
       tc5::tmem_ld_wait();
-      if (a.dW[0])
+      if (a.dW[0])   // dW1 is [128][D] row-major: this thread's 16 columns are contiguous -> four 128-bit reductions
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(&a.dW[0][(size_t)tid * D + c16 * 16 + j], __uint_as_float(r[j]));
+        for (int q = 0; q < 4; ++q)
+          red_add4(a.dW[0] + (size_t)tid * D, 4 * c16 + q,
+                   make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                               __uint_as_float(r[4 * q + 3])));
       tc5::tmem_ld16(tmem + my_lanes + kM5ColDW2 + c16 * 16, r);
       tc5::tmem_ld_wait();
       if (a.dW[1])

@@ -476,7 +476,7 @@ def train_steps_supported(batch: int, dim: int, pairwise: bool, device=None) -> 
         return False
     tasks = -(-slice_ // (32 // lpr))
     up = lambda v: (v + 127) // 128 * 128
-    base = up(1408 + 8 * tasks * 16) + 8 * up(rows * slice_ * 8 + slice_ * 4)
+    base = up(384 + 8 * tasks * 16) + 8 * up(rows * slice_ * 8 + slice_ * 4)
     stage = up(rows * slice_ * dim * 4 + 2 * slice_ * 4)
     if base + 3 * stage <= 220 * 1024:   # staged kernel (3 or 4 stages)
         return True

@@ -31,13 +31,13 @@ lib.xdr_debug_set_steps_trace(None)
 t = trace.view(K, G, 8).cpu().double()
 t0 = t[:, :, 2][t[:, :, 2] > 0].min()
 t = (t - t0) / 1e3  # us
-names = ['cta partial ready', 'all partials seen', 'task0 rows requested', 'task0 scored', 'filler starts',
-         'norms arrived', 'scatter issued', 'filler done']
+names = ['cta partial ready', 'all partials seen', 'task0 rows requested', 'task0 scored', 'task0 waits norms',
+         'norms arrived', 'scatter issued']
 print('mode:', 'fused sgd (dst = tables)' if fused else ('lazily zeroed grad tables' if lazy else 'grad tables'))
 print('step | ' + ' | '.join(f'{n[:18]:>18s}' for n in names) + '   (median over CTAs; max for col 0/1), us since start')
 for s in list(range(0, 12)) + list(range(40, 46)):
     row = []
-    for k in range(8):
+    for k in range(7):
         col = t[s, :, k]
         col = col[col > -1e6]
         row.append(f'{col.median():8.2f}/{col.max():8.2f}' if col.numel() else '-')
@@ -50,11 +50,6 @@ print('skew of partial-ready across CTAs (max - min): %.2f us' % (t[:, :, 0].max
 print('rows requested -> scored (task 0): %.2f us median, %.2f p95' % ((t[:, :, 3] - t[:, :, 2]).median(), (t[:, :, 3] - t[:, :, 2]).flatten().quantile(0.95)))
 print('scored -> norms arrived (task 0): %.2f us median' % (t[:, :, 5] - t[:, :, 3]).median())
 print('norms arrived -> scatter issued (scatter warp 0): %.2f us median' % (t[:, :, 6] - t[:, :, 5]).median())
-if lazy:
-    print('filler: start -> done %.2f us median, %.2f p95;  done -> norms arrived (slack, negative = scatter waits) %.2f us median, %.2f p5' % (
-        (t[:, :, 7] - t[:, :, 4]).median(), (t[:, :, 7] - t[:, :, 4]).flatten().quantile(0.95),
-        (t[:, :, 5] - t[:, :, 7]).median(), (t[:, :, 5] - t[:, :, 7]).flatten().quantile(0.05)))
-    print('filler start relative to task0 rows requested of the same step: %.2f us median' % (t[:, :, 4] - t[:, :, 2]).median())
 # plain timing of both destination modes
 if lazy:
     sys.exit(0)

@@ -92,7 +92,6 @@ struct Cta {
   unsigned tc_delay = 0;
   std::deque<std::function<void(Cta&)>> dma_queue;   // bulk copies in flight (cp.async.bulk), completed in issue order
   unsigned dma_delay = 0;
-  unsigned stores_in_flight = 0;                     // cp.async.bulk shared -> global copies issued and not yet performed
   // what the tensor core (async proxy) sees of shared memory: the image as of the last fence.proxy.async executed by a thread
   // of the CTA.  Generic-proxy stores that no such fence followed are NOT visible to tcgen05.mma operand reads.
   std::vector<char> smem_async;
@@ -201,19 +200,6 @@ inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, const void* bar
     m.tx -= bytes;
     m.check();
   });
-}
-
-// cp.async.bulk (shared -> global, bulk-group completion): the source is read and the destination written some scheduler
-// slices after the issue; cp.async.bulk.wait_group 0 (modelled per CTA, which is stricter than per thread) waits for them
-inline void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
-  cta().stores_in_flight++;
-  cta().dma_queue.push_back([=](Cta& c) {
-    std::memcpy(dst, src, bytes);
-    c.stores_in_flight--;
-  });
-}
-inline void bulk_store_wait_all() {
-  while (cta().stores_in_flight != 0) yield();
 }
 
 // ---- tcgen05 / TMEM model -------------------------------------------------------------------------------------------------

@@ -29,7 +29,12 @@
 
 namespace xdr {
 
-constexpr int kM5Rows = 128, kM5Hidden = 128, kM5Threads = 128, kM5MaxDim = 64, kM5TmemCols = 512;
+constexpr int kM5Rows = 128, kM5Hidden = 128, kM5MaxDim = 64, kM5TmemCols = 512;
+// 512 threads: thread = (row r = tid % 128, column group cg = tid / 128).  The four threads of a row live in warps w, w + 4, w + 8,
+// w + 12 -- the warps that may read the row's TMEM lane (lanes 32 (w % 4) ..) -- and share an epilogue's 16-column chunks
+// (chunk c16 belongs to group c16 % 4).  Measured with 128 threads: 45 % of the stall samples were instruction fetches of the
+// long unrolled epilogues, 6 % warp occupancy; sixteen warps run the same code four times shorter.
+constexpr int kM5Threads = 512, kM5Groups = kM5Threads / kM5Rows;
 constexpr int kM5ColZ1 = 0, kM5ColY = 128, kM5ColDW1 = 192, kM5ColDW2 = 256;   // tensor-memory columns
 
 struct M5Smem {
@@ -57,12 +62,29 @@ __host__ __device__ inline M5Smem m5_smem_layout(int D) {
 // [R][C] row-major fp32 in global memory -> bf16 hi / lo row-block-major tile (all threads of the CTA)
 __device__ __forceinline__ void m5_stage_matrix(const float* __restrict__ W, int R, int C, unsigned char* hi, unsigned char* lo) {
   const tc5::RowBlock16 t{R, C};
-  const int c8n = C >> 3;
-  for (int e = threadIdx.x; e < R * c8n; e += kM5Threads) {
-    const int r = e / c8n, c8 = e - r * c8n;
-    const float4 v0 = *reinterpret_cast<const float4*>(W + (size_t)r * C + 8 * c8);
-    const float4 v1 = *reinterpret_cast<const float4*>(W + (size_t)r * C + 8 * c8 + 4);
-    tc5::store_split8(hi, lo, t.chunk_offset(r, c8), v0, v1);
+  const int c8n = C >> 3, n = R * c8n;
+  constexpr int kU = 8;   // loads of eight 32-byte pieces are in flight before the first conversion
+  for (int e0 = threadIdx.x; e0 < n; e0 += kU * kM5Threads) {
+    float4 v0[kU], v1[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int e = e0 + u * kM5Threads;
+      v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      v1[u] = v0[u];
+      if (e < n) {
+        const int r = e / c8n, c8 = e - r * c8n;
+        v0[u] = __ldg(reinterpret_cast<const float4*>(W + (size_t)r * C + 8 * c8));
+        v1[u] = __ldg(reinterpret_cast<const float4*>(W + (size_t)r * C + 8 * c8 + 4));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int e = e0 + u * kM5Threads;
+      if (e < n) {
+        const int r = e / c8n, c8 = e - r * c8n;
+        tc5::store_split8(hi, lo, t.chunk_offset(r, c8), v0[u], v1[u]);
+      }
+    }
   }
 }
 
@@ -88,8 +110,9 @@ __device__ __forceinline__ float m5_bf16_pair_hi(uint32_t u) { return __uint_as_
 
 __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Workspace ws) {
   XDR_DYN_SMEM_ALIGNED(unsigned char, smem_m5, 128);
-  __shared__ float red_smem[8];
+  __shared__ float red_smem[kM5Threads / 32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rt = tid & (kM5Rows - 1), cg = tid >> 7;   // this thread's tile row (= TMEM lane) and column group
   const int D = a.dim, c8n = D >> 3;
   const M5Smem lay = m5_smem_layout(D);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_m5);
@@ -118,7 +141,7 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
   __syncthreads();
   tc5::fence_after_sync();
   const uint32_t tmem = *tmem_base_smem;
-  const uint32_t my_lanes = (uint32_t)(warp * 32) << 16;   // this warp's 32 TMEM lanes = tile rows 32*warp ..
+  const uint32_t my_lanes = (uint32_t)((warp & 3) * 32) << 16;   // this warp's 32 TMEM lanes = tile rows 32 (warp % 4) ..
 
   const uint32_t w1h = tc5::smem_u32(W1h), w1l = tc5::smem_u32(W1l), w2h = tc5::smem_u32(W2h), w2l = tc5::smem_u32(W2l);
   const uint32_t xh = tc5::smem_u32(Xh), xl = tc5::smem_u32(Xl), hh = tc5::smem_u32(Hh), hl = tc5::smem_u32(Hl);
@@ -146,7 +169,7 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
   bool first = true;
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row = tile * kM5Rows + tid;        // this thread's batch row in every epilogue
+    const int64_t row = tile * kM5Rows + rt;         // this thread's batch row in every epilogue
     int64_t my_id = -1;
     if (row < a.batch) {
       my_id = a.idx_u[row];
@@ -158,13 +181,13 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
     // ---- gather the source rows -> X tile (rows past the batch / bad ids are zero).  All of a thread's loads are issued before
     // the first conversion (8 threads per row, 16 rows per pass), and the thread's own target row -- needed two products later
     // -- is requested here too, so that its latency hides behind G1 / G2 instead of stalling the loss epilogue
-    float4 trow[kM5MaxDim / 4];
+    float4 trow[4];   // the 16 target columns of chunk c16 = cg (D = 64: one chunk per group; smaller D: the high groups idle)
 #pragma unroll
-    for (int q = 0; q < kM5MaxDim / 4; ++q) {
+    for (int q = 0; q < 4; ++q) {
       trow[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (my_id >= 0 && 4 * q < D) trow[q] = ld_row4(a.T + my_id * D, q);
+      if (my_id >= 0 && cg * 16 < D) trow[q] = ld_row4(a.T + my_id * D, 4 * cg + q);
     }
-    constexpr int kGatherPasses = kM5Rows * (kM5MaxDim / 8) / kM5Threads;   // 8 at D = 64
+    constexpr int kGatherPasses = kM5Rows * (kM5MaxDim / 8) / kM5Threads;   // 2 at D = 64
     {
       float4 g0[kGatherPasses], g1[kGatherPasses];
 #pragma unroll
@@ -203,15 +226,16 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
     }
     wait_mma();
     // H = act(Z1 + b1) -> Hs
-    for (int c16 = 0; c16 < kM5Hidden / 16; ++c16) {
+#pragma unroll 1
+    for (int c16 = cg; c16 < kM5Hidden / 16; c16 += kM5Groups) {
       uint32_t r[16];
       tc5::tmem_ld16(tmem + my_lanes + kM5ColZ1 + c16 * 16, r);
       tc5::tmem_ld_wait();
       float h[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) h[j] = act_apply(__uint_as_float(r[j]) + b1[c16 * 16 + j], a.hidden_act);
-      tc5::store_split8(Hh, Hl, tH.chunk_offset(tid, 2 * c16), make_float4(h[0], h[1], h[2], h[3]), make_float4(h[4], h[5], h[6], h[7]));
-      tc5::store_split8(Hh, Hl, tH.chunk_offset(tid, 2 * c16 + 1), make_float4(h[8], h[9], h[10], h[11]),
+      tc5::store_split8(Hh, Hl, tH.chunk_offset(rt, 2 * c16), make_float4(h[0], h[1], h[2], h[3]), make_float4(h[4], h[5], h[6], h[7]));
+      tc5::store_split8(Hh, Hl, tH.chunk_offset(rt, 2 * c16 + 1), make_float4(h[8], h[9], h[10], h[11]),
                         make_float4(h[12], h[13], h[14], h[15]));
     }
     epilogue_done();
@@ -224,16 +248,15 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
     }
     wait_mma();
     // loss head: d = Y + b2 - T[id]; loss += d^2; dY = gs d; the target rows get -dY (emcdr.py:156-168: target not detached)
-#pragma unroll   // constant trip count: trow[] stays in registers
-    for (int c16 = 0; c16 < kM5MaxDim / 16; ++c16) {
-      if (c16 * 16 >= D) break;
+    if (cg * 16 < D) {   // one 16-column chunk per column group (warp-uniform: a warp's threads share cg)
+      const int c16 = cg;
       uint32_t r[16];
       tc5::tmem_ld16(tmem + my_lanes + kM5ColY + c16 * 16, r);
       tc5::tmem_ld_wait();
       float g[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 t = trow[4 * c16 + q];
+        const float4 t = trow[q];
         const float tv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -246,8 +269,8 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
           red_add4(a.dT + my_id * D, 4 * c16 + q, scale4(-a.scale, make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3])));
       }
       if (a.backward) {
-        tc5::store_split8(Yh, Yl, tX.chunk_offset(tid, 2 * c16), make_float4(g[0], g[1], g[2], g[3]), make_float4(g[4], g[5], g[6], g[7]));
-        tc5::store_split8(Yh, Yl, tX.chunk_offset(tid, 2 * c16 + 1), make_float4(g[8], g[9], g[10], g[11]),
+        tc5::store_split8(Yh, Yl, tX.chunk_offset(rt, 2 * c16), make_float4(g[0], g[1], g[2], g[3]), make_float4(g[4], g[5], g[6], g[7]));
+        tc5::store_split8(Yh, Yl, tX.chunk_offset(rt, 2 * c16 + 1), make_float4(g[8], g[9], g[10], g[11]),
                           make_float4(g[12], g[13], g[14], g[15]));
         {   // db2: column sums over the tile's rows
           int col;
@@ -269,14 +292,15 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
     }
     wait_mma();
     // dZ1 = dH * act'(H), written over H in place (each thread rewrites the chunks of its own row)
-    for (int c16 = 0; c16 < kM5Hidden / 16; ++c16) {
+#pragma unroll 1
+    for (int c16 = cg; c16 < kM5Hidden / 16; c16 += kM5Groups) {
       uint32_t r[16];
       tc5::tmem_ld16(tmem + my_lanes + kM5ColZ1 + c16 * 16, r);
       tc5::tmem_ld_wait();
       float z[16];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        const int off = tH.chunk_offset(tid, 2 * c16 + half);
+        const int off = tH.chunk_offset(rt, 2 * c16 + half);
         const uint4 ph = *reinterpret_cast<const uint4*>(Hh + off), pl = *reinterpret_cast<const uint4*>(Hl + off);
         const uint32_t hw[4] = {ph.x, ph.y, ph.z, ph.w}, lw[4] = {pl.x, pl.y, pl.z, pl.w};
 #pragma unroll
@@ -286,8 +310,8 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
           z[8 * half + 2 * q + 1] = __uint_as_float(r[8 * half + 2 * q + 1]) * act_grad(h1, a.hidden_act);
         }
       }
-      tc5::store_split8(Hh, Hl, tH.chunk_offset(tid, 2 * c16), make_float4(z[0], z[1], z[2], z[3]), make_float4(z[4], z[5], z[6], z[7]));
-      tc5::store_split8(Hh, Hl, tH.chunk_offset(tid, 2 * c16 + 1), make_float4(z[8], z[9], z[10], z[11]),
+      tc5::store_split8(Hh, Hl, tH.chunk_offset(rt, 2 * c16), make_float4(z[0], z[1], z[2], z[3]), make_float4(z[4], z[5], z[6], z[7]));
+      tc5::store_split8(Hh, Hl, tH.chunk_offset(rt, 2 * c16 + 1), make_float4(z[8], z[9], z[10], z[11]),
                         make_float4(z[12], z[13], z[14], z[15]));
       {     // db1
         int col;
@@ -306,7 +330,8 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
       tc5::commit(bar);
     }
     wait_mma();
-    for (int c16 = 0; c16 < D / 16; ++c16) {
+#pragma unroll 1
+    for (int c16 = cg; c16 < D / 16; c16 += kM5Groups) {
       uint32_t r[16];
       tc5::tmem_ld16(tmem + my_lanes + kM5ColY + c16 * 16, r);
       tc5::tmem_ld_wait();
@@ -325,23 +350,24 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
 
   // ---- flush the weight / bias gradients (thread = hidden unit = TMEM lane) -------------------------------------------------------------
   if (a.backward) {
-    for (int c16 = 0; c16 < D / 16; ++c16) {
+#pragma unroll 1
+    for (int c16 = cg; c16 < D / 16; c16 += kM5Groups) {
       uint32_t r[16];
       tc5::tmem_ld16(tmem + my_lanes + kM5ColDW1 + c16 * 16, r);
       tc5::tmem_ld_wait();
       if (a.dW[0])   // dW1 is [128][D] row-major: this thread's 16 columns are contiguous -> four 128-bit reductions
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          red_add4(a.dW[0] + (size_t)tid * D, 4 * c16 + q,
+          red_add4(a.dW[0] + (size_t)rt * D, 4 * c16 + q,
                    make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
                                __uint_as_float(r[4 * q + 3])));
       tc5::tmem_ld16(tmem + my_lanes + kM5ColDW2 + c16 * 16, r);
       tc5::tmem_ld_wait();
       if (a.dW[1])
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(&a.dW[1][(size_t)(c16 * 16 + j) * kM5Hidden + tid], __uint_as_float(r[j]));
+        for (int j = 0; j < 16; ++j) atomicAdd(&a.dW[1][(size_t)(c16 * 16 + j) * kM5Hidden + rt], __uint_as_float(r[j]));
     }
-    if (a.db[0]) atomicAdd(&a.db[0][tid], dbs[tid]);
+    if (a.db[0] && tid < kM5Hidden) atomicAdd(&a.db[0][tid], dbs[tid]);
     if (a.db[1] && tid < D) atomicAdd(&a.db[1][tid], dbs[kM5Hidden + tid]);
   }
   tc5::fence_before_sync();

@@ -51,7 +51,10 @@ def test_lazy_tables_equal_the_plain_scatter_add(nu, ni, dim, K, B, zipf):
     nu_m, ni_m = named(nu, u), named(ni, ip, ineg)
     assert torch.equal(su != 0, nu_m) and torch.equal(si != 0, ni_m)
     assert bool(((su == 0) | (su == 3)).all()) and bool(((si == 0) | (si == 3)).all())
-    atol_u, atol_i = 1e-6 * float(gu_ref.abs().max()), 1e-6 * float(gi_ref.abs().max())
+    # rows named thousands of times (the Zipf case: 33 000 duplicates of one row) are summed in another order than by the
+    # plain launch: 4e-8 absolute on a 0.018 row was measured between two correct runs (scripts/diag_accum_noise.py)
+    tol = 1e-5 if zipf else 1e-6
+    atol_u, atol_i = tol * float(gu_ref.abs().max()), tol * float(gi_ref.abs().max())
     torch.testing.assert_close(gu[nu_m], gu_ref[nu_m], rtol=1e-5, atol=max(atol_u, 1e-9))
     torch.testing.assert_close(gi[ni_m], gi_ref[ni_m], rtol=1e-5, atol=max(atol_i, 1e-9))
     assert bool((gu[~nu_m] == 7.0).all()) and bool((gi[~ni_m] == -3.0).all())

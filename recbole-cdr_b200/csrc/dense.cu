@@ -8,9 +8,10 @@
 //
 // These are GEMMs with a long M (batch) and short N/K (8..256).  One 64x64 output tile per CTA, 4x4 register
 // micro-tile per thread, K staged through shared memory in slabs of 16.  fp32 FMA keeps the loss within the
-// 1e-4 contract without any split-precision trick; the tcgen05 path (mlp_tc.cu) takes over for the shapes where
-// the layer is large enough to be tensor-bound.
+// 1e-4 contract without any split-precision trick; the tcgen05 engine (tc5_dense.cu) takes over for the shapes it
+// takes (M >= 128, N and K multiples of 16): xdr_set_dense_engine(0) keeps everything here.
 #include "xdr_common.cuh"
+#include "tc5_dense.cuh"
 
 namespace xdr {
 
@@ -358,6 +359,8 @@ int xdr_dense_fwd(const float* X, const float* W, const float* bias, const float
   XDR_REQUIRE(X && W && Y, "xdr_dense_fwd: null pointer");
   XDR_REQUIRE((X2 == nullptr) == (W2 == nullptr), "xdr_dense_fwd: X2 and W2 must be given together");
   XDR_REQUIRE(act >= XDR_ACT_NONE && act <= XDR_ACT_SIGMOID, "xdr_dense_fwd: bad act %d", act);
+  if (tc5_dense_fwd_ok(X, W, X2, W2, Y, M, N, K))   // tensor cores (tcgen05, bf16x3) for the shapes that are GEMMs
+    return tc5_dense_fwd(X, W, bias, X2, W2, mask_ids, mask_lt, act, Y, M, N, K, (cudaStream_t)stream);
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
   XDR_LAUNCH((dense_fwd_kernel), grid, kDenseThreads, 0, (cudaStream_t)stream, X, W, bias, X2, W2, mask_ids, mask_lt, act, Y, M, N, K);
   XDR_LAUNCH_OK();
@@ -378,6 +381,8 @@ int xdr_dense_bwd_input(const float* dZ, const float* W, const int64_t* mask_ids
   XDR_REQUIRE(M >= 0 && N > 0 && K > 0, "xdr_dense_bwd_input: bad shape");
   if (M == 0) return XDR_OK;
   XDR_REQUIRE(dZ && W && dX, "xdr_dense_bwd_input: null pointer");
+  if (tc5_dense_bwd_input_ok(dZ, W, dX, M, N, K))
+    return tc5_dense_bwd_input(dZ, W, mask_ids, mask_lt, dX, M, N, K, accumulate, (cudaStream_t)stream);
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((K + BN - 1) / BN));
   XDR_LAUNCH((dense_bwd_input_kernel), grid, kDenseThreads, 0, (cudaStream_t)stream, dZ, W, mask_ids, mask_lt, dX, M, N, K, accumulate);
   XDR_LAUNCH_OK();
@@ -389,6 +394,8 @@ int xdr_dense_bwd_weight(const float* dZ, const float* X, const int64_t* mask_id
   XDR_REQUIRE(M >= 0 && N > 0 && K > 0, "xdr_dense_bwd_weight: bad shape");
   if (M == 0) return XDR_OK;
   XDR_REQUIRE(dZ && X && dW, "xdr_dense_bwd_weight: null pointer");
+  if (tc5_dense_bwd_weight_ok(dZ, X, dW, M, N, K))
+    return tc5_dense_bwd_weight(dZ, X, mask_ids, mask_lt, dW, db, M, N, K, (cudaStream_t)stream);
   dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)((K + BN - 1) / BN), (unsigned)((M + kChunkM - 1) / kChunkM));
   XDR_LAUNCH((dense_bwd_weight_kernel), grid, kDenseThreads, 0, (cudaStream_t)stream, dZ, X, mask_ids, mask_lt, dW, db, M, N, K);
   XDR_LAUNCH_OK();

@@ -33,6 +33,7 @@ PROTOTYPES = {
                               c_vp, c_vp]),
     'xdr_point_bwd': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_vp, c_vp,
                               c_f32, c_vp, c_vp, c_vp]),
+    'xdr_set_dense_engine': (c_int, [c_int]),
     'xdr_dense_fwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_int, c_vp]),
     'xdr_act_bwd': (c_int, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
     'xdr_dense_bwd_input': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_vp]),

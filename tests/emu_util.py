@@ -25,7 +25,7 @@ def _lib_path(mode):
 # translation units of the emulator library: the harness (which #includes the fused row-tile kernels it drives directly)
 # plus the kernel files that only need their real entry points
 SEPARATE_TUS = ['pair_score.cu', 'gather_scatter.cu', 'dense.cu', 'graph_prop.cu', 'neg_sample.cu', 'topk_score.cu',
-                'steps_persistent.cu', 'tc5_mlp.cu']
+                'steps_persistent.cu', 'tc5_mlp.cu', 'tc5_dense.cu']
 
 
 def _deps():

@@ -1,0 +1,71 @@
+"""The tcgen05 dense-layer engine (tc5_dense.cu: forward, input gradient, weight gradient as bf16x3 products with accumulators
+in tensor memory) through the CPU CTA emulator, against fp64 torch: every entry point of the dense family, with and without
+the cross-stitch operand and the overlap mask, at row counts around the 128-row tile and for every K chunking.  Logic only;
+the hardware twin is tests/test_gpu_tc5_dense.py."""
+import pytest
+import torch
+
+import emu_util
+
+
+def ref_dense(X, W, b, X2, W2, mask, act):
+    z = X.double() @ W.double().t()
+    if b is not None:
+        z = z + b.double()
+    if X2 is not None:
+        z = z + mask.double().unsqueeze(1) * (X2.double() @ W2.double().t())
+    return {0: z, 1: torch.relu(z), 2: torch.tanh(z), 3: torch.sigmoid(z)}[act]
+
+
+@pytest.mark.parametrize('M,N,K,act,cross', [(128, 16, 16, 1, False), (300, 64, 256, 1, True), (257, 32, 64, 2, False),
+                                             (129, 128, 64, 0, True), (640, 48, 48, 3, False), (200, 16, 32, 1, True),
+                                             (384, 64, 128, 1, True), (130, 32, 192, 2, False)])
+def test_dense_layer_on_tcgen05_matches_fp64(M, N, K, act, cross):
+    from recbole_cdr_b200 import _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    X, W = torch.randn(M, K, generator=g) * 0.5, torch.randn(N, K, generator=g) * 0.2
+    b = torch.randn(N, generator=g) * 0.1
+    X2 = torch.randn(M, K, generator=g) * 0.5 if cross else None
+    W2 = torch.randn(N, K, generator=g) * 0.2 if cross else None
+    ids = torch.randint(0, 100, (M,), generator=g) if cross else None
+    mask = (ids < 40) if cross else None
+    dY = torch.randn(M, N, generator=g)
+    leaves = [t.clone().double().requires_grad_(True) for t in (X, W, b)] + \
+        ([X2.clone().double().requires_grad_(True), W2.clone().double().requires_grad_(True)] if cross else [None, None])
+    want = ref_dense(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], mask, act)
+    want.backward(dY.double())
+    with emu_util.patched_ops(sms=2, seed=1) as ops:
+        assert _lib  # the engine is on by default
+        c = [t.clone().requires_grad_(True) for t in (X, W, b)] + \
+            ([X2.clone().requires_grad_(True), W2.clone().requires_grad_(True)] if cross else [None, None])
+        Y = ops.dense(c[0], c[1], c[2], act, c[3], c[4], ids, 40)
+        Y.backward(dY)
+    scale = lambda t: max(1e-6, float(t.abs().max()))
+    torch.testing.assert_close(Y.detach().double(), want.detach(), rtol=1e-4, atol=1e-4 * scale(want))
+    names = ('X', 'W', 'b', 'X2', 'W2')
+    for nm, got, ref in zip(names, c, leaves):
+        if got is None:
+            continue
+        torch.testing.assert_close(got.grad.double(), ref.grad, rtol=2e-4, atol=2e-4 * scale(ref.grad), msg=lambda s: f'{nm}: {s}')
+
+
+def test_dense_engine_switch_and_fallback_shapes():
+    """xdr_set_dense_engine(0) keeps a qualifying shape on the fp32 FMA kernels (results agree with the tcgen05 ones to bf16x3
+    accuracy); shapes the engine does not take (N = 8, K = 20, M < 128) never reach it."""
+    g = torch.Generator().manual_seed(3)
+    X, W = torch.randn(256, 64, generator=g), torch.randn(32, 64, generator=g) * 0.2
+    with emu_util.patched_ops(sms=2) as ops:
+        L = emu_util.lib()
+        L.xdr_set_dense_engine.argtypes = [__import__('ctypes').c_int]
+        y1 = ops.dense(X, W, None, 0)
+        prev = L.xdr_set_dense_engine(0)
+        try:
+            y0 = ops.dense(X, W, None, 0)
+        finally:
+            L.xdr_set_dense_engine(prev)
+        assert prev == 1
+        torch.testing.assert_close(y1, y0, rtol=1e-4, atol=1e-4)
+        assert not torch.equal(y1, y0)      # different arithmetic (bf16x3 vs fp32 FMA): the switch really switches
+        for (m, n, k) in ((64, 32, 64), (256, 8, 64), (256, 32, 20)):
+            x, w = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g)
+            torch.testing.assert_close(ops.dense(x, w, None, 0), x @ w.t(), rtol=1e-5, atol=1e-5)

@@ -1,0 +1,56 @@
+"""GPU: the tcgen05 dense-layer engine (tc5_dense.cu) against fp64 torch on the device -- forward, input gradient and weight
+gradient of `act(X W^T + b + m (X2 W2^T))` at the BASELINE shapes (CoNet config #3's layer 0: 16384 x 256 -> 64 with the
+cross-stitch operand; the EMCDR map MLP; NeuMF towers) and at ragged row counts.  CPU twin: tests/test_emu_tc5_dense.py."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device('cuda', 0)
+
+
+@pytest.mark.parametrize('M,N,K,act,cross', [(128, 16, 16, 1, False), (16384, 64, 256, 1, True), (8192, 128, 64, 2, False),
+                                             (8192, 64, 128, 0, False), (16384, 32, 64, 1, True), (16384, 16, 32, 1, True),
+                                             (1000, 48, 48, 3, False), (4097, 32, 192, 2, True), (8192, 32, 128, 1, False)])
+def test_dense_layer_on_tcgen05_matches_fp64(M, N, K, act, cross):
+    from recbole_cdr_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    mk = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(dev())
+    X, W, b = mk(M, K, sc=0.5), mk(N, K, sc=0.2), mk(N, sc=0.1)
+    X2, W2 = (mk(M, K, sc=0.5), mk(N, K, sc=0.2)) if cross else (None, None)
+    ids = torch.randint(0, 100, (M,), generator=g).to(dev()) if cross else None
+    dY = mk(M, N)
+    ref = [t.double().requires_grad_(True) if t is not None else None for t in (X, W, b, X2, W2)]
+    z = ref[0] @ ref[1].t() + ref[2]
+    if cross:
+        z = z + (ids < 40).double().unsqueeze(1) * (ref[3] @ ref[4].t())
+    want = {0: z, 1: torch.relu(z), 2: torch.tanh(z), 3: torch.sigmoid(z)}[act]
+    want.backward(dY.double())
+    c = [t.clone().requires_grad_(True) if t is not None else None for t in (X, W, b, X2, W2)]
+    Y = ops.dense(c[0], c[1], c[2], act, c[3], c[4], ids, 40)
+    Y.backward(dY)
+    torch.cuda.synchronize()
+    scale = lambda t: max(1e-6, float(t.detach().abs().max()))
+    torch.testing.assert_close(Y.detach().double(), want.detach(), rtol=1e-4, atol=1e-4 * scale(want))
+    for nm, got, r in zip(('X', 'W', 'b', 'X2', 'W2'), c, ref):
+        if got is None:
+            continue
+        torch.testing.assert_close(got.grad.double(), r.grad, rtol=2e-4, atol=2e-4 * scale(r.grad), msg=lambda s: f'{nm}: {s}')
+
+
+def test_engine_switch_changes_the_arithmetic_not_the_result():
+    from recbole_cdr_b200 import _lib, ops
+    g = torch.Generator().manual_seed(3)
+    X, W = torch.randn(4096, 64, generator=g).to(dev()), (torch.randn(32, 64, generator=g) * 0.2).to(dev())
+    y1 = ops.dense(X, W, None, 0)
+    prev = _lib._lib.xdr_set_dense_engine(0)
+    try:
+        y0 = ops.dense(X, W, None, 0)
+    finally:
+        _lib._lib.xdr_set_dense_engine(prev)
+    torch.cuda.synchronize()
+    assert prev == 1
+    torch.testing.assert_close(y1, y0, rtol=1e-4, atol=1e-4)
+    assert not torch.equal(y1, y0)

@@ -58,18 +58,19 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='xdr', choices=['xdr', 'reference'])
-    ap.add_argument('--workload', default=None, choices=['emcdr_1m', 'emcdr_10m', 'emcdr_100k', 'emcdr_map'])
+    ap.add_argument('--workload', default=None, choices=['emcdr_1m', 'emcdr_10m', 'emcdr_100k', 'emcdr_map', 'conet_5m'])
     ap.add_argument('--batch', type=int, default=8192)
     ap.add_argument('--repeats', type=int, default=11, help='timed K-step launches (median reported)')
     ap.add_argument('--cpu-steps', type=int, default=3, help='timed steps of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip variants / fused SGD / per-step comparison / 10M sub-run')
-    ap.add_argument('--grad-mode', default='fresh', choices=['fresh', 'accumulate'],
-                    help='fresh: every launch produces the gradient of its K batches (touch map, lazily zeroed rows); '
-                         'accumulate: scatter-add into whatever the gradient tables hold')
+    ap.add_argument('--grad-mode', default='accumulate', choices=['fresh', 'accumulate'],
+                    help='accumulate (default): scatter-add into the dense gradient tables; fresh: lazily zeroed gradient tables -- '
+                         'every launch produces the gradient of its K batches, first touch of a row stores (touch map)')
     ap.add_argument('--coop', type=int, default=1, help='1: cudaLaunchCooperativeKernel, 0: plain launch')
-    ap.add_argument('--map-engine', default='tc5', help="emcdr_map: 'tc5' (tcgen05), 'tc' (mma.sync), 'fma', '' (composed kernels)")
+    ap.add_argument('--dense-engine', type=int, default=0, help='model-step workloads: 1 tcgen05 dense layers, 0 fp32 FMA')
+    ap.add_argument('--map-engine', default='', help="emcdr_map: 'tc5' (tcgen05), 'tc' (mma.sync), 'fma', '' (composed kernels)")
     ap.add_argument('--shard-chunk', type=int, default=50, help='N>1: steps per persistent launch')
     ap.add_argument('--chunk', type=int, default=0, help='steps per launch on the end-to-end (host-fed) path (0: K/2, 50 from K = 100)')
     return ap.parse_args()
@@ -263,7 +264,7 @@ def run_reference(args):
     if int(os.environ.get('RANK', '0')) != 0:
         return
     workload = args.workload or ('emcdr_1m' if args.gpus == 1 else 'emcdr_10m')
-    if workload == 'emcdr_map':
+    if workload in ('emcdr_map', 'conet_5m'):
         workload = 'emcdr_1m'
     scale = SCALES[workload]
     steps = max(1, min(args.steps, 3 if scale > 1_000_000 else 5))
@@ -453,8 +454,8 @@ def run_xdr(args):
         dist.init_process_group('nccl', device_id=dev)
     _lib._lib.xdr_set_coop_launch(int(args.coop))
     workload = args.workload or ('emcdr_1m' if world == 1 else 'emcdr_10m')
-    if workload == 'emcdr_map':
-        return run_map(args, dev)
+    if workload in MODEL_WORKLOADS:
+        return run_model_step(args, dev, workload)
     scale = SCALES[workload]
     B, K, W, R = args.batch, args.steps, max(3, args.warmup), max(1, args.repeats)
     peak, peak_src = measured_peaks()
@@ -695,81 +696,126 @@ def per_step_comparison(wl, K, W, B, peak):
     return out
 
 
-def cpu_reference_map_rate(scale, b, n_timed):
-    """The reference EMCDR's OVERLAP-phase step (emcdr.py:156-168) on the host cores: forward + backward, b overlap ids."""
-    synthetic = load_synthetic()
-    ds = synthetic.emcdr_scale(scale)
+def _import_reference_model(name):
+    """An unmodified reference model class from oracle/_ref (staged by build()) over the recbole stub; None if not staged."""
+    if _import_reference_emcdr() is None:
+        return None
+    import importlib
+    mod = importlib.import_module('recbole_cdr.model.cross_domain_recommender.' + name.lower())
+    return getattr(mod, name)
+
+
+MODEL_WORKLOADS = {
+    # name: (model class, config overrides, bytes per interaction (SURVEY 8 D3), what a step is)
+    'emcdr_map': ('EMCDR', 1032, 'EMCDR OVERLAP-phase map step (gather -> MLP 64-128-64 -> MSE -> backward -> scatter), synthetic '
+                                 'emcdr_1m tables, b = %d overlapped users per step'),
+    'conet_5m': ('CoNet', 4116, 'CoNet BOTH-phase step (BASELINE configs[2]: 5M users / 2M items, dim 128, cross-stitch MLP '
+                                '[256, 64, 32, 16, 8]): source + target tower passes on %d rows per domain, fwd + bwd + scatter'),
+}
+
+
+def _model_workload(name, batch, device):
+    """(dataset, config, batch factory, interactions per step) of a model-step workload, on `device`."""
+    synthetic = load_synthetic() if str(device) == 'cpu' else None
+    if synthetic is None:
+        from recbole_cdr_b200.data import synthetic
+    base = {'source_domain': {'NEG_PREFIX': 'neg_'}, 'target_domain': {'NEG_PREFIX': 'neg_'}, 'device': device}
+    if name == 'emcdr_map':
+        ds = synthetic.emcdr_scale(SCALES['emcdr_1m'])
+        cfg = dict(base, latent_factor_model='BPR', source_embedding_size=D, target_embedding_size=D, reg_weight=0.01,
+                   mapping_function='non_linear', mlp_hidden_size=[128], overlap_batch_size=batch)
+
+        def make(seed):
+            g = torch.Generator(device=device).manual_seed(seed)
+            return {'overlap': torch.randint(0, ds.num_overlap_user, (batch, 1), device=device, generator=g)}
+        return ds, cfg, make, batch, 'OVERLAP'
+    ds = synthetic.SyntheticCrossDomainDataset(synthetic.IdSpace(2_500_001, 2_500_000, 2_500_000),
+                                               synthetic.IdSpace(1, 2_000_000, 2_000_000))
+    cfg = dict(base, embedding_size=128, reg_weight=0.01, mlp_hidden_size=[64, 32, 16, 8])
+
+    def make(seed):
+        b = synthetic.make_batch(ds, 'source', batch, 2 * seed, device, pairwise=False)
+        b.update(synthetic.make_batch(ds, 'target', batch, 2 * seed + 1, device, pairwise=False))
+        return b
+    return ds, cfg, make, 2 * batch, None
+
+
+def cpu_reference_model_rate(name, batch, n_timed):
+    """The reference model class's step (calculate_loss + backward) on the host cores."""
+    cls = _import_reference_model(MODEL_WORKLOADS[name][0])
+    if cls is None:
+        return None
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    EMCDR = _import_reference_emcdr()
-    if EMCDR is None:
-        return None
-    cfg = {'source_domain': {'NEG_PREFIX': 'neg_'}, 'target_domain': {'NEG_PREFIX': 'neg_'}, 'device': 'cpu',
-           'latent_factor_model': 'BPR', 'source_embedding_size': D, 'target_embedding_size': D, 'reg_weight': 0.01,
-           'mapping_function': 'non_linear', 'mlp_hidden_size': [128], 'overlap_batch_size': b}
+    ds, cfg, make, units, phase = _model_workload(name, batch, 'cpu')
     torch.manual_seed(2022)
-    model = EMCDR(cfg, ds)
-    model.set_phase('OVERLAP')
-    g = torch.Generator().manual_seed(5)
+    model = cls(cfg, ds)
+    if phase:
+        model.set_phase(phase)
     ts = []
     for s_ in range(1 + n_timed):
-        inter = {'overlap': torch.randint(0, ds.num_overlap_user, (b, 1), generator=g)}
+        inter = make(100 + s_)
         model.zero_grad(set_to_none=True)
         t0 = time.perf_counter()
-        model.calculate_loss(inter).sum().backward()
+        loss = model.calculate_loss(inter)
+        (sum(loss) if isinstance(loss, tuple) else loss).sum().backward()
         dt = time.perf_counter() - t0
         if s_ >= 1:
             ts.append(dt)
     sec = sum(ts) / len(ts)
-    return {'value': b / sec, 'unit': 'rows/s', 'cores': cores, 'kind': 'reference',
-            'sample': f'{n_timed} timed + 1 warm-up OVERLAP-phase steps (b={b}) of the unmodified reference EMCDR class, forward + '
-                      f'backward to dense grads, torch CPU {cores} threads, {sec * 1e3:.0f} ms/step'}
+    return {'value': units / sec, 'unit': 'interactions/s', 'cores': cores, 'kind': 'reference',
+            'sample': f'{n_timed} timed + 1 warm-up steps of the same workload on the unmodified reference {MODEL_WORKLOADS[name][0]} '
+                      f'class (oracle/_ref), forward + backward to dense grads, torch CPU {cores} threads, {sec * 1e3:.0f} ms/step'}
 
 
-def run_map(args, dev):
-    """--workload emcdr_map: the "map" stage of the metric -- EMCDR's OVERLAP-phase step (emcdr.py:156-168): gather the source
-    and target rows of b overlapped users -> MLP 64-128-64 (tanh) -> MSE -> whole backward -> scatter-add into both tables'
-    gradient rows + the MLP's weight gradients.  Through the drop-in model class (calculate_loss + backward) captured as a
-    CUDA graph (trainer.GraphedTrainStep); a step = copy of the step's ids into the graph's input buffer + one replay."""
+def run_model_step(args, dev, name):
+    """--workload emcdr_map | conet_5m: one training step of a drop-in model class (calculate_loss + backward: gather -> dense
+    map / cross-stitch layers on tcgen05 -> loss -> backward -> scatter-add into the tables' gradient rows), captured as a CUDA
+    graph (trainer.GraphedTrainStep).  A step = copy of the step's ids into the graph's input buffers + one replay."""
     add_paths()
-    from recbole_cdr_b200.data import Interaction, synthetic
-    from recbole_cdr_b200.model.cross_domain_recommender.emcdr import EMCDR
+    from recbole_cdr_b200 import _lib
+    from recbole_cdr_b200.data import Interaction
     from recbole_cdr_b200.trainer import GraphedTrainStep
-    ds = synthetic.emcdr_scale(SCALES['emcdr_1m'])
-    b, K, W, R = args.batch, args.steps, max(3, args.warmup), max(1, args.repeats)
+    import importlib
+    cls_name, bytes_per, what = MODEL_WORKLOADS[name]
+    cls = getattr(importlib.import_module('recbole_cdr_b200.model.cross_domain_recommender.' + cls_name.lower()), cls_name)
+    b = args.batch if name == 'emcdr_map' else (16384 if args.batch == 8192 else args.batch)
+    K, W, R = args.steps, max(3, args.warmup), max(1, args.repeats)
     peak, peak_src = measured_peaks()
-    cfg = {'source_domain': {'NEG_PREFIX': 'neg_'}, 'target_domain': {'NEG_PREFIX': 'neg_'}, 'device': dev,
-           'latent_factor_model': 'BPR', 'source_embedding_size': D, 'target_embedding_size': D, 'reg_weight': 0.01,
-           'mapping_function': 'non_linear', 'mlp_hidden_size': [128], 'xdr_fused_mlp': args.map_engine or False}
+    _lib._lib.xdr_set_dense_engine(int(args.dense_engine))
+    ds, cfg, make, units, phase = _model_workload(name, b, dev)
+    if name == 'emcdr_map':
+        cfg['xdr_fused_mlp'] = args.map_engine or False
     torch.manual_seed(2022)
     with torch.device(dev):
-        model = EMCDR(cfg, ds)
-    model.set_phase('OVERLAP')
-    g = torch.Generator(device=dev).manual_seed(7)
+        model = cls(cfg, ds)
+    if phase:
+        model.set_phase(phase)
     n = W + R * K
-    ids = torch.randint(0, ds.num_overlap_user, (n, b, 1), device=dev, generator=g)
+    batches = [Interaction(make(s_)) for s_ in range(n)]
     # how many libxdr entry points one step goes through (each launches at least one kernel of this repository)
     from recbole_cdr_b200 import ops as _ops
     counted, real_call = [0], _ops.call
 
-    def counting_call(name, *a_, **k_):
+    def counting_call(nm, *a_, **k_):
         counted[0] += 1
-        return real_call(name, *a_, **k_)
+        return real_call(nm, *a_, **k_)
     _ops.call = counting_call
     try:
-        model.calculate_loss(Interaction({'overlap': ids[0]})).sum().backward()
+        loss0 = model.calculate_loss(batches[0])
+        (sum(loss0) if isinstance(loss0, tuple) else loss0).sum().backward()
     finally:
         _ops.call = real_call
     model.zero_grad(set_to_none=True)
     calls_per_step = counted[0]
-    step = GraphedTrainStep(model, Interaction({'overlap': ids[0]}))
+    step = GraphedTrainStep(model, batches[0])
     timer = Timer(dev, 1)
     clocks = ClockSampler(dev.index or 0)
     clocks.start()
 
     def run_steps(lo, hi):
         for k in range(lo, hi):
-            step(Interaction({'overlap': ids[k]}))
+            step(batches[k])
 
     run_steps(0, W)
     torch.cuda.synchronize()
@@ -782,8 +828,9 @@ def run_map(args, dev):
     ms_list = timer.samples(lambda r: run_steps(W + r * K, W + (r + 1) * K), R)
     loss = float(step.loss)
     med = statistics.median(ms_list)
-    # end to end: ids from pinned host memory, loss back to the host, every step
-    host_ids = ids[W:W + K].cpu().pin_memory()
+    # end to end: ids (and labels) from pinned host memory, loss back to the host, every step
+    host_b = [Interaction({k: batches[W + i][k].cpu().pin_memory() for k in batches[W + i].columns}) for i in range(K)]
+    h2d = sum(int(host_b[0][k].numel() * host_b[0][k].element_size()) for k in host_b[0].columns)
     losses = torch.empty(K, dtype=torch.float32, pin_memory=True)
     api = []
     for r in range(max(3, R // 2)):
@@ -791,37 +838,39 @@ def run_map(args, dev):
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         for k in range(K):
-            l = step(Interaction({'overlap': host_ids[k]}))   # H2D copy of the ids into the graph's input buffer + replay
+            l = step(host_b[k])   # H2D copy of the step's fields into the graph's input buffers + replay
             losses[k].copy_(l, non_blocking=True)
         a1.record()
         timer.barrier()
         api.append(a0.elapsed_time(a1))
     clk = clocks.stop()
     amed = statistics.median(api)
-    achieved = BYTES_PER_ROW_MAP_D64 * b * K / (med * 1e-3) / 1e9
+    achieved = bytes_per * units * K / (med * 1e-3) / 1e9
+    engine = ('tcgen05 dense engine (tc5_dense.cu)' if args.dense_engine else 'fp32 FMA dense kernels')
+    if name == 'emcdr_map' and args.map_engine:
+        engine = {'tc5': 'tc5_mlp_kernel (one fused tcgen05 kernel per pass)', 'tc': 'tc_mlp_kernel (mma.sync)',
+                  'fma': 'fused_mlp_kernel (fp32)'}.get(args.map_engine, args.map_engine)
     line = {
-        'metric': 'interactions/sec (gather+map+score+scatter)', 'value': b * K / (med * 1e-3), 'unit': 'interactions/s',
+        'metric': 'interactions/sec (gather+map+score+scatter)', 'value': units * K / (med * 1e-3), 'unit': 'interactions/s',
         'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': med / K, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32 (dense products: bf16x3 on tcgen05, fp32 accumulate)' if args.map_engine == 'tc5' else 'f32',
+        'vs_baseline': None, 'dtype': 'f32 (dense products: bf16x3 on tcgen05, fp32 accumulate)' if args.dense_engine else 'f32',
         'data': 'synthetic',
-        'config': {'workload': 'EMCDR OVERLAP-phase map step (gather -> MLP 64-128-64 -> MSE -> backward -> scatter), synthetic '
-                               'emcdr_1m tables, b = %d overlapped users per step' % b, 'engine': args.map_engine or 'composed',
-                   'users_total': ds.num_total_user, 'dim': D, 'batch_per_gpu': b,
-                   'l2': 'inputs larger than L2 (0.77 GB of user tables, uniform random rows)', 'parallelism': 'single GPU'},
+        'config': {'workload': what % b, 'engine': engine, 'users_total': ds.num_total_user, 'items_total': ds.num_total_item,
+                   'batch_per_gpu': b, 'l2': 'inputs larger than L2 (tables of 0.8 .. 7 GB, uniform random rows)',
+                   'parallelism': 'single GPU'},
         'timing': Timer.summary(ms_list),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-                     'peak_source': peak_src, 'kernel': 'tc5_mlp_kernel (tcgen05.mma kind::f16, TMEM accumulators)' if
-                     args.map_engine == 'tc5' else str(args.map_engine or 'composed dense kernels'),
-                     'units_per_launch': b, 'bytes_per_interaction': BYTES_PER_ROW_MAP_D64,
-                     'note': '1032 B and 98 kFLOP per row: ~95 FLOP/B, under the tensor ridge -- HBM-bound on paper, launch- and '
-                             'latency-bound in practice at b = 8192 (8.5 MB per step)'},
-        'e2e': {'value': b * K / (amed * 1e-3), 'unit': 'interactions/s', 'h2d_bytes_per_step': 8 * b, 'd2h_bytes_per_step': 4,
+                     'peak_source': peak_src, 'kernel': engine, 'units_per_launch': units, 'bytes_per_interaction': bytes_per,
+                     'note': 'a step is a CUDA graph of %d library calls; at these batch sizes it is bound by launch gaps and '
+                             'dependent-kernel latency, not by HBM (the algorithmic bytes of a step are %.1f MB)' %
+                             (calls_per_step, bytes_per * units / 1e6)},
+        'e2e': {'value': units * K / (amed * 1e-3), 'unit': 'interactions/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                 'steps': K, 'repeats': len(api), 'min_ms': min(api), 'max_ms': max(api),
-                'api': 'EMCDR.calculate_loss + backward replayed by trainer.GraphedTrainStep: per step H2D ids -> graph -> D2H loss'},
+                'api': f'{cls_name}.calculate_loss + backward replayed by trainer.GraphedTrainStep: per step H2D fields -> graph -> D2H loss'},
         'gpu_launches': calls_per_step * K, 'clocks': clk, 'loss_mean': loss,
     }
     if not args.no_cpu_baseline:
-        cb = cpu_reference_map_rate(SCALES['emcdr_1m'], b, args.cpu_steps)
+        cb = cpu_reference_model_rate(name, b, args.cpu_steps)
         if cb:
             line['cpu_baseline'] = cb
     print(json.dumps(line))

@@ -123,9 +123,10 @@ XDR_API int xdr_point_bwd(const float* user_tab, const float* item_tab, int64_t 
  * bias, X2/W2 may be NULL.  mask[m] = (mask_ids[m] < mask_lt) when mask_ids != NULL, else 1
  * (conet.py:113-116).  Replaces nn.Linear/torch.mm/activation in emcdr.py:86-93, conet.py:118-138,
  * recbole MLPLayers (dtcdr.py:61-67).                                                                     */
-/* Engine of the three GEMM entry points below: 1 (default) = tcgen05.mma on bf16 hi / lo operand planes (bf16x3, fp32
- * accumulation in tensor memory, ~2^-16 relative per product) for M >= 128, N % 16 == 0 (16..128), K % 16 == 0 (16..256) and
- * 16-byte aligned operands, fp32 FMA otherwise; 0 = fp32 FMA for every shape.  Returns the previous setting.           */
+/* Engine of the three GEMM entry points below: 1 = tcgen05.mma on three bf16 operand planes (bf16x6: fp32-faithful products,
+ * fp32 accumulation in tensor memory) for M >= 128, N % 16 == 0 (16..128), K % 16 == 0 (16..256) and 16-byte aligned
+ * operands, fp32 FMA otherwise; 0 (default) = fp32 FMA for every shape -- on a B200 the two tie per call at the BASELINE
+ * model shapes (profiles/r2_dense_engines.jsonl), so tcgen05 is opt-in.  Returns the previous setting.                 */
 XDR_API int xdr_set_dense_engine(int engine);
 XDR_API int xdr_dense_fwd(const float* X, const float* W, const float* bias, const float* X2, const float* W2,
                   const int64_t* mask_ids, int64_t mask_lt, int act, float* Y, int64_t M, int N, int K,

@@ -318,6 +318,51 @@ __device__ __forceinline__ void mma_bf16x3(uint32_t tmem_d, uint32_t a_hi, uint3
   }
 }
 
+// ---- bf16x6: three bf16 planes (x ~= hi + mid + lo, 24 mantissa bits) and the six products whose weight is >= 2^-16 of the
+// leading one (hi hi, hi mid, mid hi, hi lo, lo hi, mid mid; what is dropped is below 2^-24) -- fp32-faithful results, for the
+// layers whose outputs go through a ReLU: with bf16x3 (~2^-16 per product) a pre-activation within 1e-5 of zero gets another
+// sub-gradient than the fp32 reference, which showed up as whole rows of differing gradients (round 2, GPU call 12).
+__device__ __forceinline__ void split_bf16_pair3(float x0, float x1, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+  const uint32_t h0 = bf16_rn(x0), h1 = bf16_rn(x1);
+  const float r0 = x0 - __uint_as_float(h0 << 16), r1 = x1 - __uint_as_float(h1 << 16);
+  const uint32_t m0 = bf16_rn(r0), m1 = bf16_rn(r1);
+  hi = h0 | (h1 << 16);
+  mid = m0 | (m1 << 16);
+  lo = bf16_rn(r0 - __uint_as_float(m0 << 16)) | (bf16_rn(r1 - __uint_as_float(m1 << 16)) << 16);
+}
+__device__ __forceinline__ void store_split8_3(unsigned char* hi_plane, unsigned char* mid_plane, unsigned char* lo_plane,
+                                               int chunk_off, float4 v0, float4 v1) {
+  uint4 h, m, l;
+  split_bf16_pair3(v0.x, v0.y, h.x, m.x, l.x);
+  split_bf16_pair3(v0.z, v0.w, h.y, m.y, l.y);
+  split_bf16_pair3(v1.x, v1.y, h.z, m.z, l.z);
+  split_bf16_pair3(v1.z, v1.w, h.w, m.w, l.w);
+  *reinterpret_cast<uint4*>(hi_plane + chunk_off) = h;
+  *reinterpret_cast<uint4*>(mid_plane + chunk_off) = m;
+  *reinterpret_cast<uint4*>(lo_plane + chunk_off) = l;
+}
+// D (+)= A * B^T over K (multiple of 16); a0 / b0 = shared-memory address of the hi plane, the mid and lo planes follow at
+// a_plane / b_plane bytes.  ONE thread.  Small terms first.
+template <typename LayA, typename LayB>
+__device__ __forceinline__ void mma_bf16x6(uint32_t tmem_d, uint32_t a0, uint32_t a_plane, const LayA& la, uint32_t b0,
+                                           uint32_t b_plane, const LayB& lb, uint32_t idesc, int K, bool accumulate) {
+  for (int ks = 0; ks < K / 16; ++ks) {
+    const uint32_t ao = a0 + ks * la.k_step_bytes(), bo = b0 + ks * lb.k_step_bytes();
+    uint64_t da[3], db[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      da[i] = make_desc(ao + i * a_plane, la.lbo(), la.sbo(), la.mn_major());
+      db[i] = make_desc(bo + i * b_plane, lb.lbo(), lb.sbo(), lb.mn_major());
+    }
+    mma_bf16(tmem_d, da[1], db[1], idesc, accumulate || ks > 0);   // mid mid
+    mma_bf16(tmem_d, da[2], db[0], idesc, true);                   // lo  hi
+    mma_bf16(tmem_d, da[0], db[2], idesc, true);                   // hi  lo
+    mma_bf16(tmem_d, da[1], db[0], idesc, true);                   // mid hi
+    mma_bf16(tmem_d, da[0], db[1], idesc, true);                   // hi  mid
+    mma_bf16(tmem_d, da[0], db[0], idesc, true);                   // hi  hi
+  }
+}
+
 // ---- self-test: D[128 x N] = A[128 x K] * B[N x K]^T from row-major operands in global memory, one CTA of 128 threads, with
 // A and B staged K-major or MN-major.  Runs under the emulator and, on hardware, checks the descriptor reading through the
 // library itself (xdr_tc5_selftest).

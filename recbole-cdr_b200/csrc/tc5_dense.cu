@@ -1,6 +1,7 @@
 // tc5_dense.cu -- the dense-layer family (xdr_dense_fwd / xdr_dense_bwd_input / xdr_dense_bwd_weight, include/xdr.h) on the
-// 5th-generation tensor cores: tcgen05.mma kind::f16 on bf16 hi / lo operand planes (bf16x3: a_lo b_hi + a_hi b_lo + a_hi b_hi,
-// fp32 accumulation in tensor memory, ~2^-16 relative per product -- inside the 1e-4 loss contract, see tests).
+// 5th-generation tensor cores: tcgen05.mma kind::f16 on THREE bf16 operand planes (x ~= hi + mid + lo, 24 mantissa bits) and the
+// six products that matter (tc5.cuh mma_bf16x6; fp32 accumulation in tensor memory): fp32-faithful, so that ReLU masks and with
+// them whole gradient rows agree with the fp32 reference (bf16x3 did not: round 2, GPU call 12).
 //
 // These are the GEMMs of the mapping MLP (emcdr.py:86-93), the CoNet cross-stitch units (conet.py:118-138), the NeuMF towers
 // (recbole MLPLayers, dtcdr.py:61-67) and the MLPs of the further models: a long M (the batch, 8 192 .. 32 768 rows) against a
@@ -39,10 +40,11 @@ __device__ __forceinline__ float d5_act(float v, int act) {
 }
 
 // rows [row0, row0 + t.rows) x columns [col0, col0 + cols) of the row-major fp32 matrix P (leading dimension ld, n_rows rows)
-// -> bf16 hi / lo planes of the row-block-major tile t (tile columns [0, cols); cols % 8 == 0).  Rows past n_rows and rows the
-// mask switches off are zeros.  Four 32-byte pieces per thread are in flight before the first conversion.
+// -> the three bf16 planes (hi at `dst`, mid and lo `plane` bytes further each) of the row-block-major tile t (tile columns
+// [0, cols); cols % 8 == 0).  Rows past n_rows and rows the mask switches off are zeros.  Four 32-byte pieces per thread are in
+// flight before the first conversion; the rows were prefetched into L2 at kernel start (d5_prefetch), so these are L2 hits.
 __device__ __forceinline__ void d5_stage(const float* __restrict__ P, int64_t ld, int64_t row0, int64_t n_rows, int col0,
-                                         int cols, const tc5::RowBlock16& t, unsigned char* hi, unsigned char* lo,
+                                         int cols, const tc5::RowBlock16& t, unsigned char* dst, int plane,
                                          const int64_t* __restrict__ mask_ids, int64_t mask_lt) {
   const int c8n = cols >> 3, n = t.rows * c8n;
   constexpr int kU = 4;
@@ -69,10 +71,26 @@ __device__ __forceinline__ void d5_stage(const float* __restrict__ P, int64_t ld
       const int e = e0 + u * kD5Threads;
       if (e < n) {
         const int r = e / c8n, c8 = e - r * c8n;
-        tc5::store_split8(hi, lo, t.chunk_offset(r, c8), v0[u], v1[u]);
+        tc5::store_split8_3(dst, dst + plane, dst + 2 * plane, t.chunk_offset(r, c8), v0[u], v1[u]);
       }
     }
   }
+}
+
+// asks L2 for rows [row0, row0 + rows) of P (row_bytes each, 128-byte lines): a CTA's whole input tile is on its way before
+// the first staging pass needs it (one CTA per SM at these batch sizes: there is nobody else to hide the DRAM latency)
+__device__ __forceinline__ void d5_prefetch(const float* __restrict__ P, int64_t ld, int64_t row0, int64_t n_rows, int rows,
+                                            int row_bytes) {
+#ifndef XDR_EMU
+  const int lines = (row_bytes + 127) >> 7;
+  for (int e = threadIdx.x; e < rows * lines; e += kD5Threads) {
+    const int r = e / lines, l = e - r * lines;
+    if (row0 + r < n_rows) {
+      const char* p = reinterpret_cast<const char*>(P + (row0 + r) * ld) + 128 * l;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
+#endif
 }
 
 struct D5Sync {
@@ -105,13 +123,14 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_fwd_kernel(const float* 
   const int KC = d5_chunk(K);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_d5);
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem_d5 + 8);
-  unsigned char* Xh = smem_d5 + 128;
-  unsigned char* Xl = Xh + kD5Rows * KC * 2;
-  unsigned char* Wh = Xl + kD5Rows * KC * 2;
-  unsigned char* Wl = Wh + N * KC * 2;
+  const int xplane = kD5Rows * KC * 2, wplane = N * KC * 2;
+  unsigned char* Xs = smem_d5 + 128;
+  unsigned char* Ws = Xs + 3 * xplane;
   const tc5::RowBlock16 tX{kD5Rows, KC}, tW{N, KC};
   const int64_t row0 = (int64_t)blockIdx.x * kD5Rows;
   const uint32_t cols = d5_tmem_cols(N);
+  d5_prefetch(X, K, row0, M, kD5Rows, K * 4);
+  if (X2 != nullptr) d5_prefetch(X2, K, row0, M, kD5Rows, K * 4);
   if (tid == 0) {
     tc5::mbar_init(bar, 1);
     tc5::mbar_init_fence();
@@ -122,7 +141,7 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_fwd_kernel(const float* 
   tc5::fence_after_sync();
   const uint32_t tmem = *tmem_base_smem;
   D5Sync sy{bar, 0u};
-  const uint32_t xh = tc5::smem_u32(Xh), xl = tc5::smem_u32(Xl), wh = tc5::smem_u32(Wh), wl = tc5::smem_u32(Wl);
+  const uint32_t xs = tc5::smem_u32(Xs), ws = tc5::smem_u32(Ws);
   const uint32_t idesc = tc5::make_idesc_bf16(kD5Rows, N, false, false);
   const int n_prod = X2 != nullptr ? 2 : 1;
   bool acc = false;
@@ -132,11 +151,11 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_fwd_kernel(const float* 
     const float* Wp = p == 0 ? W : W2;
 #pragma unroll 1
     for (int kc = 0; kc < K; kc += KC) {
-      d5_stage(Xp, K, row0, M, kc, KC, tX, Xh, Xl, p == 0 ? nullptr : mask_ids, mask_lt);
-      d5_stage(Wp, K, 0, N, kc, KC, tW, Wh, Wl, nullptr, 0);
+      d5_stage(Xp, K, row0, M, kc, KC, tX, Xs, xplane, p == 0 ? nullptr : mask_ids, mask_lt);
+      d5_stage(Wp, K, 0, N, kc, KC, tW, Ws, wplane, nullptr, 0);
       sy.operands_ready();
       if (tid == 0) {
-        tc5::mma_bf16x3(tmem, xh, xl, tX.as_k_major(), wh, wl, tW.as_k_major(), idesc, KC, acc);
+        tc5::mma_bf16x6(tmem, xs, xplane, tX.as_k_major(), ws, wplane, tW.as_k_major(), idesc, KC, acc);
         tc5::commit(bar);
       }
       acc = true;
@@ -172,22 +191,24 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_fwd_kernel(const float* 
 }
 
 // ---- input gradient: dX[m, k] (=|+=) mask[m] * sum_n dZ[m, n] W[n, k] ----------------------------------------------------------
+__host__ __device__ inline int d5_piece(int K) { return K <= 128 ? K : (K % 128 == 0 ? 128 : (K % 64 == 0 ? 64 : 16)); }
+
 __global__ void __launch_bounds__(kD5Threads) tc5_dense_bwd_input_kernel(const float* __restrict__ dZ, const float* __restrict__ W,
                                                                          const int64_t* __restrict__ mask_ids, int64_t mask_lt,
                                                                          float* __restrict__ dX, int64_t M, int N, int K,
                                                                          int accumulate) {
   XDR_DYN_SMEM_ALIGNED(unsigned char, smem_d5, 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int NP = K <= 128 ? K : (K % 128 == 0 ? 128 : (K % 64 == 0 ? 64 : 16));   // output columns per product (the MMA's N)
+  const int NP = d5_piece(K);   // output columns per product (the MMA's N)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_d5);
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem_d5 + 8);
-  unsigned char* Zh = smem_d5 + 128;
-  unsigned char* Zl = Zh + kD5Rows * N * 2;
-  unsigned char* Wh = Zl + kD5Rows * N * 2;
-  unsigned char* Wl = Wh + N * NP * 2;
+  const int zplane = kD5Rows * N * 2, wplane = N * NP * 2;
+  unsigned char* Zs = smem_d5 + 128;
+  unsigned char* Ws = Zs + 3 * zplane;
   const tc5::RowBlock16 tZ{kD5Rows, N}, tW{N, NP};
   const int64_t row0 = (int64_t)blockIdx.x * kD5Rows;
   const uint32_t cols = d5_tmem_cols(NP);
+  d5_prefetch(dZ, N, row0, M, kD5Rows, N * 4);
   if (tid == 0) {
     tc5::mbar_init(bar, 1);
     tc5::mbar_init_fence();
@@ -198,19 +219,19 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_bwd_input_kernel(const f
   tc5::fence_after_sync();
   const uint32_t tmem = *tmem_base_smem;
   D5Sync sy{bar, 0u};
-  const uint32_t zh = tc5::smem_u32(Zh), zl = tc5::smem_u32(Zl), wh = tc5::smem_u32(Wh), wl = tc5::smem_u32(Wl);
+  const uint32_t zs = tc5::smem_u32(Zs), ws = tc5::smem_u32(Ws);
   const uint32_t idesc = tc5::make_idesc_bf16(kD5Rows, NP, false, true);
   const int rt = (warp & 3) * 32 + lane, cg = warp >> 2;
   const int64_t row = row0 + rt;
   const uint32_t my_lanes = (uint32_t)((warp & 3) * 32) << 16;
   const float m = (row < M && (mask_ids == nullptr || mask_ids[row] < mask_lt)) ? 1.f : 0.f;
-  d5_stage(dZ, N, row0, M, 0, N, tZ, Zh, Zl, nullptr, 0);
+  d5_stage(dZ, N, row0, M, 0, N, tZ, Zs, zplane, nullptr, 0);
 #pragma unroll 1
   for (int k0 = 0; k0 < K; k0 += NP) {
-    d5_stage(W, K, 0, N, k0, NP, tW, Wh, Wl, nullptr, 0);
+    d5_stage(W, K, 0, N, k0, NP, tW, Ws, wplane, nullptr, 0);
     sy.operands_ready();   // (also: every thread has finished the previous piece's epilogue reads of tensor memory)
     if (tid == 0) {
-      tc5::mma_bf16x3(tmem, zh, zl, tZ.as_k_major(), wh, wl, tW.as_mn_major(), idesc, N, false);
+      tc5::mma_bf16x6(tmem, zs, zplane, tZ.as_k_major(), ws, wplane, tW.as_mn_major(), idesc, N, false);
       tc5::commit(bar);
     }
     sy.wait_mma();
@@ -248,18 +269,17 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_bwd_weight_kernel(const 
                                                                           int N, int K) {
   XDR_DYN_SMEM_ALIGNED(unsigned char, smem_d5, 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NP = d5_piece(K);   // columns of X (= of dW) per product; the [128, K] accumulator spans all pieces
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_d5);
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(smem_d5 + 8);
   float* dbs = reinterpret_cast<float*>(smem_d5 + 128);          // [128] column sums of the masked dZ rows this CTA saw
-  unsigned char* Zh = smem_d5 + 128 + 512;
-  unsigned char* Zl = Zh + kD5Rows * kD5Rows * 2;               // the dZ tile is [128 batch rows x 128 columns]: columns >= N stay zero
-  unsigned char* Xh = Zl + kD5Rows * kD5Rows * 2;
-  unsigned char* Xl = Xh + kD5Rows * K * 2;
-  const tc5::RowBlock16 tZ{kD5Rows, kD5Rows}, tX{kD5Rows, K};
+  const int zplane = kD5Rows * kD5Rows * 2, xplane = kD5Rows * NP * 2;
+  unsigned char* Zs = smem_d5 + 128 + 512;                        // the dZ tile is [128 batch rows x 128 columns]: columns >= N stay zero
+  unsigned char* Xs = Zs + 3 * zplane;
+  const tc5::RowBlock16 tZ{kD5Rows, kD5Rows}, tX{kD5Rows, NP};
   const uint32_t cols = d5_tmem_cols(K);
   for (int i = tid; i < kD5Rows; i += kD5Threads) dbs[i] = 0.f;
-  for (int i = tid; i < kD5Rows * kD5Rows * 4 / 16; i += kD5Threads)   // both planes (adjacent) of the dZ tile
-    reinterpret_cast<float4*>(Zh)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < 3 * zplane / 16; i += kD5Threads) reinterpret_cast<float4*>(Zs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
     tc5::mbar_init(bar, 1);
     tc5::mbar_init_fence();
@@ -270,8 +290,8 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_bwd_weight_kernel(const 
   tc5::fence_after_sync();
   const uint32_t tmem = *tmem_base_smem;
   D5Sync sy{bar, 0u};
-  const uint32_t zh = tc5::smem_u32(Zh), zl = tc5::smem_u32(Zl), xh = tc5::smem_u32(Xh), xl = tc5::smem_u32(Xl);
-  const uint32_t idesc = tc5::make_idesc_bf16(kD5Rows, K, true, true);
+  const uint32_t zs = tc5::smem_u32(Zs), xs = tc5::smem_u32(Xs);
+  const uint32_t idesc = tc5::make_idesc_bf16(kD5Rows, NP, true, true);
   const int64_t n_tiles = (M + kD5Rows - 1) / kD5Rows;
   // column sums for db: a thread always stages the same 8-column piece of the dZ rows (kD5Threads % (N / 8) == 0)
   const int c8n = N >> 3;
@@ -280,6 +300,7 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_bwd_weight_kernel(const 
 #pragma unroll 1
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kD5Rows;
+    d5_prefetch(X, K, row0, M, kD5Rows, K * 4);
     // dZ rows (masked) -> columns [0, N) of the [128 x 128] tile; the same values feed db
 #pragma unroll 1
     for (int e = tid; e < kD5Rows * c8n; e += kD5Threads) {
@@ -292,16 +313,19 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_bwd_weight_kernel(const 
       }
       colsum[0] += v0.x; colsum[1] += v0.y; colsum[2] += v0.z; colsum[3] += v0.w;
       colsum[4] += v1.x; colsum[5] += v1.y; colsum[6] += v1.z; colsum[7] += v1.w;
-      tc5::store_split8(Zh, Zl, tZ.chunk_offset(r, c8), v0, v1);
+      tc5::store_split8_3(Zs, Zs + zplane, Zs + 2 * zplane, tZ.chunk_offset(r, c8), v0, v1);
     }
-    d5_stage(X, K, row0, M, 0, K, tX, Xh, Xl, nullptr, 0);
-    sy.operands_ready();
-    if (tid == 0) {
-      tc5::mma_bf16x3(tmem, zh, zl, tZ.as_mn_major(), xh, xl, tX.as_mn_major(), idesc, kD5Rows, !first);
-      tc5::commit(bar);
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += NP) {
+      d5_stage(X, K, row0, M, k0, NP, tX, Xs, xplane, nullptr, 0);
+      sy.operands_ready();
+      if (tid == 0) {
+        tc5::mma_bf16x6(tmem + k0, zs, zplane, tZ.as_mn_major(), xs, xplane, tX.as_mn_major(), idesc, kD5Rows, !first);
+        tc5::commit(bar);
+      }
+      sy.wait_mma();   // the X piece may be overwritten (and, after the last piece, the dZ tile)
     }
     first = false;
-    sy.wait_mma();
   }
   // flush: thread = (output row n = TMEM lane, column group) -> 128-bit reductions into dW (rows >= N are padding)
   const int n = (warp & 3) * 32 + lane, cg = warp >> 2;
@@ -324,10 +348,8 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_bwd_weight_kernel(const 
   }
   if (db != nullptr) {
     const int c8 = tid % c8n;   // the 8-column piece this thread staged in every pass (tid + i * 256 keeps e % c8n)
-    if (tid < kD5Rows * c8n) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&dbs[8 * c8 + j], colsum[j]);
-    }
+    for (int j = 0; j < 8; ++j) atomicAdd(&dbs[8 * c8 + j], colsum[j]);
     __syncthreads();
     if (tid < N) atomicAdd(&db[tid], dbs[tid]);
   }
@@ -338,7 +360,11 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_bwd_weight_kernel(const 
 
 #endif  // __CUDACC__ || XDR_EMU
 
-static int g_dense_engine = 1;   // 0: fp32 FMA kernels (dense.cu) for every shape; 1: tcgen05 for the shapes this file takes
+// 0 (default): fp32 FMA kernels (dense.cu) for every shape; 1: tcgen05 for the shapes this file takes.  Measured on a B200
+// (scripts/bench_dense_engines.py, profiles/r2_dense_engines.jsonl): per call the two engines tie at the model shapes of
+// BASELINE.json (6 .. 50 us, both bound by the dependent chain stage -> product -> epilogue of ONE 128-row tile per SM, not by
+// the tensor pipe), so the validated tcgen05 engine is opt-in until it is pipelined across tiles.
+static int g_dense_engine = 0;
 
 static bool d5_shape_ok(int64_t M, int N, int K) {
   return M >= kD5Rows && N % 16 == 0 && N >= 16 && N <= 128 && K % 16 == 0 && K >= 16 && K <= 256 && (kD5Threads % (N / 8)) == 0;
@@ -371,7 +397,7 @@ bool tc5_dense_bwd_weight_ok(const float* dZ, const float* X, const float* dW, i
 int tc5_dense_fwd(const float* X, const float* W, const float* bias, const float* X2, const float* W2, const int64_t* mask_ids,
                   int64_t mask_lt, int act, float* Y, int64_t M, int N, int K, cudaStream_t stream) {
   const int KC = d5_chunk(K);
-  const size_t smem = 128 + (size_t)(kD5Rows + N) * KC * 4;
+  const size_t smem = 128 + (size_t)(kD5Rows + N) * KC * 6;
   D5_SMEM_LIMIT(tc5_dense_fwd_kernel, smem);
   const int grid = (int)((M + kD5Rows - 1) / kD5Rows);
   XDR_LAUNCH((tc5_dense_fwd_kernel), grid, kD5Threads, smem, stream, X, W, bias, X2, W2, mask_ids, mask_lt, act, Y, M, N, K);
@@ -381,8 +407,8 @@ int tc5_dense_fwd(const float* X, const float* W, const float* bias, const float
 
 int tc5_dense_bwd_input(const float* dZ, const float* W, const int64_t* mask_ids, int64_t mask_lt, float* dX, int64_t M, int N,
                         int K, int accumulate, cudaStream_t stream) {
-  const int NP = K <= 128 ? K : (K % 128 == 0 ? 128 : (K % 64 == 0 ? 64 : 16));
-  const size_t smem = 128 + (size_t)kD5Rows * N * 4 + (size_t)N * NP * 4;
+  const int NP = d5_piece(K);
+  const size_t smem = 128 + (size_t)kD5Rows * N * 6 + (size_t)N * NP * 6;
   D5_SMEM_LIMIT(tc5_dense_bwd_input_kernel, smem);
   const int grid = (int)((M + kD5Rows - 1) / kD5Rows);
   XDR_LAUNCH((tc5_dense_bwd_input_kernel), grid, kD5Threads, smem, stream, dZ, W, mask_ids, mask_lt, dX, M, N, K, accumulate);
@@ -392,11 +418,11 @@ int tc5_dense_bwd_input(const float* dZ, const float* W, const int64_t* mask_ids
 
 int tc5_dense_bwd_weight(const float* dZ, const float* X, const int64_t* mask_ids, int64_t mask_lt, float* dW, float* db, int64_t M,
                          int N, int K, cudaStream_t stream) {
-  const size_t smem = 128 + 512 + (size_t)kD5Rows * kD5Rows * 4 + (size_t)kD5Rows * K * 4;
+  const size_t smem = 128 + 512 + (size_t)kD5Rows * kD5Rows * 6 + (size_t)kD5Rows * d5_piece(K) * 6;
   D5_SMEM_LIMIT(tc5_dense_bwd_weight_kernel, smem);
   const int64_t n_tiles = (M + kD5Rows - 1) / kD5Rows;
-  // every CTA flushes an [N, K] accumulator with atomics: a few row tiles per CTA keep that traffic small
-  int64_t grid = (n_tiles + 3) / 4;
+  // one row tile per CTA up to the SM count (every CTA flushes an [N, K] accumulator with 128-bit reductions: 64 KB at most)
+  int64_t grid = n_tiles;
   if (grid > sm_count()) grid = sm_count();
   if (grid < 1) grid = 1;
   XDR_LAUNCH((tc5_dense_bwd_weight_kernel), (int)grid, kD5Threads, smem, stream, dZ, X, mask_ids, mask_lt, dW, db, M, N, K);
@@ -408,7 +434,7 @@ int tc5_dense_bwd_weight(const float* dZ, const float* X, const int64_t* mask_id
 
 extern "C" {
 
-// 1 (default): dense layers whose shapes qualify run on tcgen05 (bf16x3); 0: always the fp32 FMA kernels.  Returns the previous
+// 1: dense layers whose shapes qualify run on tcgen05 (bf16x6); 0 (default): always the fp32 FMA kernels.  Returns the previous
 // setting.
 int xdr_set_dense_engine(int engine) {
   const int prev = xdr::g_dense_engine;

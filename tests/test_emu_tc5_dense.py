@@ -8,6 +8,22 @@ import torch
 import emu_util
 
 
+class _engine:
+    """xdr_set_dense_engine(e) of the emulator library for the duration of a with block."""
+
+    def __init__(self, e):
+        self.e = e
+
+    def __enter__(self):
+        import ctypes
+        self.L = emu_util.lib()
+        self.L.xdr_set_dense_engine.argtypes = [ctypes.c_int]
+        self.prev = self.L.xdr_set_dense_engine(self.e)
+
+    def __exit__(self, *exc):
+        self.L.xdr_set_dense_engine(self.prev)
+
+
 def ref_dense(X, W, b, X2, W2, mask, act):
     z = X.double() @ W.double().t()
     if b is not None:
@@ -34,38 +50,31 @@ def test_dense_layer_on_tcgen05_matches_fp64(M, N, K, act, cross):
         ([X2.clone().double().requires_grad_(True), W2.clone().double().requires_grad_(True)] if cross else [None, None])
     want = ref_dense(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], mask, act)
     want.backward(dY.double())
-    with emu_util.patched_ops(sms=2, seed=1) as ops:
-        assert _lib  # the engine is on by default
+    with emu_util.patched_ops(sms=2, seed=1) as ops, _engine(1):
         c = [t.clone().requires_grad_(True) for t in (X, W, b)] + \
             ([X2.clone().requires_grad_(True), W2.clone().requires_grad_(True)] if cross else [None, None])
         Y = ops.dense(c[0], c[1], c[2], act, c[3], c[4], ids, 40)
         Y.backward(dY)
     scale = lambda t: max(1e-6, float(t.abs().max()))
-    torch.testing.assert_close(Y.detach().double(), want.detach(), rtol=1e-4, atol=1e-4 * scale(want))
+    torch.testing.assert_close(Y.detach().double(), want.detach(), rtol=1e-4, atol=2e-5 * scale(want))
     names = ('X', 'W', 'b', 'X2', 'W2')
     for nm, got, ref in zip(names, c, leaves):
         if got is None:
             continue
-        torch.testing.assert_close(got.grad.double(), ref.grad, rtol=2e-4, atol=2e-4 * scale(ref.grad), msg=lambda s: f'{nm}: {s}')
+        torch.testing.assert_close(got.grad.double(), ref.grad, rtol=2e-4, atol=5e-5 * scale(ref.grad), msg=lambda s: f'{nm}: {s}')
 
 
 def test_dense_engine_switch_and_fallback_shapes():
-    """xdr_set_dense_engine(0) keeps a qualifying shape on the fp32 FMA kernels (results agree with the tcgen05 ones to bf16x3
-    accuracy); shapes the engine does not take (N = 8, K = 20, M < 128) never reach it."""
+    """xdr_set_dense_engine(1) moves a qualifying shape from the fp32 FMA kernels to tcgen05 (results agree); shapes the
+    engine does not take (N = 8, K = 20, M < 128) never reach it."""
     g = torch.Generator().manual_seed(3)
     X, W = torch.randn(256, 64, generator=g), torch.randn(32, 64, generator=g) * 0.2
     with emu_util.patched_ops(sms=2) as ops:
-        L = emu_util.lib()
-        L.xdr_set_dense_engine.argtypes = [__import__('ctypes').c_int]
-        y1 = ops.dense(X, W, None, 0)
-        prev = L.xdr_set_dense_engine(0)
-        try:
-            y0 = ops.dense(X, W, None, 0)
-        finally:
-            L.xdr_set_dense_engine(prev)
-        assert prev == 1
+        y0 = ops.dense(X, W, None, 0)       # default engine: fp32 FMA
+        with _engine(1):
+            y1 = ops.dense(X, W, None, 0)
+            for (m, n, k) in ((64, 32, 64), (256, 8, 64), (256, 32, 20)):   # shapes the engine does not take
+                x, w = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g)
+                torch.testing.assert_close(ops.dense(x, w, None, 0), x @ w.t(), rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(y1, y0, rtol=1e-4, atol=1e-4)
-        assert not torch.equal(y1, y0)      # different arithmetic (bf16x3 vs fp32 FMA): the switch really switches
-        for (m, n, k) in ((64, 32, 64), (256, 8, 64), (256, 32, 20)):
-            x, w = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g)
-            torch.testing.assert_close(ops.dense(x, w, None, 0), x @ w.t(), rtol=1e-5, atol=1e-5)
+        assert not torch.equal(y1, y0)      # different arithmetic (bf16x6 on tensor cores vs fp32 FMA): the switch switches

@@ -231,11 +231,14 @@ def test_dense_fwd_bwd(M, N, K, act):
     (yr * G).sum().backward()
     xc, wc, bc = (t.to(dev()).requires_grad_(True) for t in (X, W, bias))
     yc = ops().dense(xc, wc, bc, L.ACT_BY_NAME[act])
-    torch.testing.assert_close(yc.cpu(), yr.detach(), rtol=1e-4, atol=1e-5)
+    # GEMM-shaped layers may run on the tcgen05 engine (tc5_dense.cu, when it is switched on): fp32 accumulation in tensor
+    # memory rounds differently from an FMA chain -- a few 1e-5 absolute on sums of 64 .. 8192 terms (round 2, GPU call 13)
+    big = M >= 128
+    torch.testing.assert_close(yc.cpu(), yr.detach(), rtol=1e-4, atol=3e-5 if big else 1e-5)
     (yc * G.to(dev())).sum().backward()
-    torch.testing.assert_close(xc.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(wc.grad.cpu(), wr.grad, rtol=2e-4, atol=1e-4)
-    torch.testing.assert_close(bc.grad.cpu(), br.grad, rtol=2e-4, atol=1e-4)
+    torch.testing.assert_close(xc.grad.cpu(), xr.grad, rtol=1e-4, atol=3e-5 if big else 1e-5)
+    torch.testing.assert_close(wc.grad.cpu(), wr.grad, rtol=2e-4, atol=3e-4 if big else 1e-4)
+    torch.testing.assert_close(bc.grad.cpu(), br.grad, rtol=2e-4, atol=3e-4 if big else 1e-4)
 
 
 def test_dense_cross_stitch_unit():
@@ -253,7 +256,7 @@ def test_dense_cross_stitch_unit():
     (yr * G).sum().backward()
     tc = [t.to(dev()).requires_grad_(True) for t in (X, W, bias, X2, H)]
     yc = ops().dense(tc[0], tc[1], tc[2], L.ACT_RELU, tc[3], tc[4], ids.to(dev()), 40)
-    torch.testing.assert_close(yc.cpu(), yr.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(yc.cpu(), yr.detach(), rtol=1e-4, atol=3e-5)   # (tensor-memory accumulation, see test_dense_fwd_bwd)
     (yc * G.to(dev())).sum().backward()
     for a, b, nm in zip(tc, ts, ('dX', 'dW', 'db', 'dX2', 'dH')):
         torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=2e-4, atol=2e-4, msg=lambda s: f'{nm}: {s}')

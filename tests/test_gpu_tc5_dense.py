@@ -11,6 +11,15 @@ def dev():
     return torch.device('cuda', 0)
 
 
+@pytest.fixture(autouse=True)
+def tcgen05_engine():
+    """The engine is opt-in (xdr_set_dense_engine): switch it on for the tests of this file."""
+    from recbole_cdr_b200 import _lib
+    prev = _lib._lib.xdr_set_dense_engine(1)
+    yield
+    _lib._lib.xdr_set_dense_engine(prev)
+
+
 @pytest.mark.parametrize('M,N,K,act,cross', [(128, 16, 16, 1, False), (16384, 64, 256, 1, True), (8192, 128, 64, 2, False),
                                              (8192, 64, 128, 0, False), (16384, 32, 64, 1, True), (16384, 16, 32, 1, True),
                                              (1000, 48, 48, 3, False), (4097, 32, 192, 2, True), (8192, 32, 128, 1, False)])
@@ -22,10 +31,17 @@ def test_dense_layer_on_tcgen05_matches_fp64(M, N, K, act, cross):
     X2, W2 = (mk(M, K, sc=0.5), mk(N, K, sc=0.2)) if cross else (None, None)
     ids = torch.randint(0, 100, (M,), generator=g).to(dev()) if cross else None
     dY = mk(M, N)
+    def pre(xs):
+        z_ = xs[0] @ xs[1].t() + xs[2]
+        return z_ + (ids < 40).double().unsqueeze(1) * (xs[3] @ xs[4].t()) if cross else z_
+    if act == 1:   # ReLU is not differentiable at 0: rows with a pre-activation within rounding distance of it are rescaled
+        for _ in range(6):
+            edge = (pre([t.double() if t is not None else None for t in (X, W, b, X2, W2)]).abs() < 1e-4).any(1)
+            if not bool(edge.any()):
+                break
+            X[edge] *= 1.37
     ref = [t.double().requires_grad_(True) if t is not None else None for t in (X, W, b, X2, W2)]
-    z = ref[0] @ ref[1].t() + ref[2]
-    if cross:
-        z = z + (ids < 40).double().unsqueeze(1) * (ref[3] @ ref[4].t())
+    z = pre(ref)
     want = {0: z, 1: torch.relu(z), 2: torch.tanh(z), 3: torch.sigmoid(z)}[act]
     want.backward(dY.double())
     c = [t.clone().requires_grad_(True) if t is not None else None for t in (X, W, b, X2, W2)]
@@ -33,11 +49,11 @@ def test_dense_layer_on_tcgen05_matches_fp64(M, N, K, act, cross):
     Y.backward(dY)
     torch.cuda.synchronize()
     scale = lambda t: max(1e-6, float(t.detach().abs().max()))
-    torch.testing.assert_close(Y.detach().double(), want.detach(), rtol=1e-4, atol=1e-4 * scale(want))
+    torch.testing.assert_close(Y.detach().double(), want.detach(), rtol=1e-4, atol=2e-5 * scale(want))
     for nm, got, r in zip(('X', 'W', 'b', 'X2', 'W2'), c, ref):
         if got is None:
             continue
-        torch.testing.assert_close(got.grad.double(), r.grad, rtol=2e-4, atol=2e-4 * scale(r.grad), msg=lambda s: f'{nm}: {s}')
+        torch.testing.assert_close(got.grad.double(), r.grad, rtol=2e-4, atol=5e-5 * scale(r.grad), msg=lambda s: f'{nm}: {s}')
 
 
 def test_engine_switch_changes_the_arithmetic_not_the_result():
@@ -51,6 +67,6 @@ def test_engine_switch_changes_the_arithmetic_not_the_result():
     finally:
         _lib._lib.xdr_set_dense_engine(prev)
     torch.cuda.synchronize()
-    assert prev == 1
+    assert prev == 1   # (the fixture switched it on)
     torch.testing.assert_close(y1, y0, rtol=1e-4, atol=1e-4)
     assert not torch.equal(y1, y0)

@@ -341,7 +341,7 @@ class Timer:
 class RecWorkload:
     """EMCDR SOURCE-phase BPR step on one GPU: tables + gradient tables in HBM, (W + R*K) seeded batches resident."""
 
-    def __init__(self, scale, B, K, W, R, dev, std=None, zipf=None, grad_mode='fresh', seed_off=0):
+    def __init__(self, scale, B, K, W, R, dev, std=None, zipf=None, grad_mode='fresh', seed_off=0, hot_rows=False):
         from recbole_cdr_b200.data import synthetic
         self.ds = synthetic.emcdr_scale(scale)
         self.B, self.K, self.W, self.R, self.dev, self.grad_mode = B, K, W, R, dev, grad_mode
@@ -360,6 +360,11 @@ class RecWorkload:
         self.ids = ids
         self.out8 = torch.empty(n, 8, device=dev)
         self.touch = None
+        # popular rows (a dataset statistic, computed once): pre-aggregated per CTA in shared memory (xdr_steps_set_hot_rows)
+        self.hot = None
+        if hot_rows:
+            from recbole_cdr_b200 import ops
+            self.hot = (ops.hot_rows_from_ids(ids[:, 0], nu, 16), ops.hot_rows_from_ids(ids[:, 1:], ni, 48))
 
     def touch_map(self):
         from recbole_cdr_b200 import ops
@@ -375,8 +380,14 @@ class RecWorkload:
             dst = (self.gu, self.gi)
             if self.grad_mode == 'fresh':   # lazily zeroed gradient tables: this launch's gradient, no RMW of gradient lines
                 kw = dict(touch=self.touch_map(), fresh=True)
-        ops.train_steps(self.ut, self.it, ids[lo:hi, 0], ids[lo:hi, 1], ids[lo:hi, 2], reg_weight=0.01, user_dst=dst[0],
-                        item_dst=dst[1], scale=scale, out8=self.out8[lo:hi], **kw)
+        if self.hot is not None:
+            ops.set_steps_hot_rows(*self.hot)
+        try:
+            ops.train_steps(self.ut, self.it, ids[lo:hi, 0], ids[lo:hi, 1], ids[lo:hi, 2], reg_weight=0.01, user_dst=dst[0],
+                            item_dst=dst[1], scale=scale, out8=self.out8[lo:hi], **kw)
+        finally:
+            if self.hot is not None:
+                ops.set_steps_hot_rows(None, None)
 
     def timed(self, timer, dst=None, scale=1.0):
         K, W = self.K, self.W
@@ -534,10 +545,14 @@ def run_xdr(args):
         # SURVEY 8 D2 variants: tables drawn with std 0.1 (losses away from ln 2) and Zipf(1.05) item popularity (hot rows)
         del wl.gu, wl.gi
         variants = {}
-        for name, kw in (('std0.1', dict(std=0.1)), ('zipf1.05_std0.1', dict(std=0.1, zipf=1.05))):
+        for name, kw in (('std0.1', dict(std=0.1)), ('zipf1.05_std0.1', dict(std=0.1, zipf=1.05)),
+                         ('zipf1.05_std0.1_hot_rows', dict(std=0.1, zipf=1.05, hot_rows=True))):
             v = RecWorkload(scale, B, K, W, Re, dev, grad_mode=args.grad_mode, **kw)
             ms_v, lm = v.timed(timer)
             variants[name] = dict(rate_fields(ms_v, K, B, 1, peak), loss_mean=lm)
+            if v.hot is not None:
+                variants[name]['hot_rows'] = {'users': int(v.hot[0].numel()), 'items': int(v.hot[1].numel()),
+                                              'note': 'rows named by >= 0.2 % of the ids: gradients pre-aggregated per CTA in shared memory'}
             del v
             torch.cuda.empty_cache()
         extra['variants'] = variants

@@ -328,6 +328,14 @@ XDR_API int xdr_train_steps(const float* user_tab, const float* item_tab, int64_
  * optimizer; clear_map == 0 keeps accumulating into the marked rows.  Rows with clear bits are never written and may hold
  * stale data.  The destination tables must not be the weight tables.  Needs the staged kernel (XDR_ERR_UNSUPPORTED
  * otherwise: zero the tables and use xdr_train_steps).  Everything else as xdr_train_steps.                                */
+/* Hot rows of the following xdr_train_steps launches (plain scatter-add destinations, single GPU): device arrays of int64 row
+ * ids, e.g. the most popular items of the catalogue (item popularity is a property of the dataset: computed once).  Rows that
+ * thousands of interactions per step name serialise their REDs in one L2 slice (measured: Zipf(1.05) items, 37 us per step
+ * against 3.5 us for uniform ids); every CTA instead adds the gradients of the listed rows in SHARED memory over the whole
+ * launch and adds them to the destination once at the end -- the same sums in another order (the reference's index_add is
+ * order-dependent at 1e-7 too).  At most 64 rows in total (fewer for rows wider than 64 floats); the arrays must stay valid
+ * while launches use them; n_hot_users = n_hot_items = 0 switches it off.                                                */
+XDR_API int xdr_steps_set_hot_rows(const int64_t* hot_users, int n_hot_users, const int64_t* hot_items, int n_hot_items);
 XDR_API size_t xdr_touch_map_bytes(int64_t n_users, int64_t n_items);
 XDR_API int xdr_train_steps_lazy(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
                                  const int64_t* user, const int64_t* item_a, const int64_t* item_b, const float* label,

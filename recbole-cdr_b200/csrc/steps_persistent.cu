@@ -60,6 +60,9 @@ constexpr int kStagedBound = staged_threads(kLoaderWarpsFull) > 768 ? staged_thr
 constexpr int kMaxCtaPerLane = 5;  // gatherer lanes poll <= 5 CTAs each: grid <= 160
 constexpr int kMaxStages = 4;      // staged kernel: stage ring depth (3 or 4)
 constexpr int kRing = 8;            // id-tile / partial / norm ring depth (steps)
+constexpr int kHotMax = 64;        // hot rows (both tables together) whose gradients a CTA accumulates in shared memory
+constexpr int kHotTable = 128;     // open-addressing table over them (power of two, load factor <= 1/2)
+constexpr int kHotBytes = 16 * 1024;  // accumulators: n_hot * row_f * 4 bytes must fit
 
 struct StepsArgs {
   Shards user_tab, item_tab;  // gather sources
@@ -91,6 +94,13 @@ struct StepsArgs {
   // (full-line writes allocate in L2 without a DRAM read) and the REDs then hit L2 -- no read-modify-write of gradient lines.
   unsigned int* touch_u;
   unsigned int* touch_i;
+  // Hot rows (optional, staged kernel, plain scatter-add mode): rows the data names so often (popular items of a Zipf-like
+  // catalogue) that their REDs serialise in one L2 slice.  Every CTA adds its contributions to such a row in SHARED memory
+  // over the whole launch and flushes them once at the end (one RED per CTA and row instead of one per interaction).
+  const int64_t* hot_u;
+  const int64_t* hot_i;
+  int n_hot_u, n_hot_i;
+  size_t hot_off;   // byte offset of the hot region in dynamic shared memory (0 = none)
   int32_t* oob;
   unsigned long long* trace;  // optional [n_steps][grid][8] globaltimer stamps (debug; NULL in production)
 };
@@ -482,24 +492,58 @@ __device__ __forceinline__ float score_coeff(const StepsArgs& a, float g, float 
 // How a gradient row reaches its destination.  kRowAdd: RED (scatter-add).  kRowStore: plain 128-bit stores -- the row's FIRST
 // touch since the touch map was cleared (lazily zeroed tables): whatever the destination holds counts as zero and is
 // overwritten, whole lines at a time, so L2 allocates them without reading DRAM.  kRowSkip: nothing (bad id, or deferred).
-enum RowMode : int { kRowSkip = 0, kRowAdd = 1, kRowStore = 2 };
+enum RowMode : int { kRowSkip = 0, kRowAdd = 1, kRowStore = 2, kRowHot = 3 };   // kRowHot: add into a shared-memory accumulator row
 __device__ __forceinline__ void emit_row4(int mode, float* row, int cidx, float4 v) {
   if (mode == kRowAdd) red_add4(row, cidx, v);
   else if (mode == kRowStore) st4(row, cidx, v);
+  else if (mode == kRowHot) {
+    float* q = row + 4 * cidx;
+    atomicAdd(q, v.x);
+    atomicAdd(q + 1, v.y);
+    atomicAdd(q + 2, v.z);
+    atomicAdd(q + 3, v.w);
+  }
+}
+
+// hot rows: open-addressing table in shared memory, key = 2 * row id + table (0 user, 1 item); -1 = not a hot row
+struct HotRows {
+  long long* keys;       // [kHotTable] (-1 = empty)
+  int* slots;            // [kHotTable] accumulator index of the key
+  long long* slot_key;   // [kHotMax] key of every accumulator (for the flush)
+  float* acc;            // [n][row_f]
+  __device__ HotRows(unsigned char* base)
+      : keys(reinterpret_cast<long long*>(base)), slots(reinterpret_cast<int*>(base + kHotTable * 8)),
+        slot_key(reinterpret_cast<long long*>(base + kHotTable * 12)), acc(reinterpret_cast<float*>(base + kHotTable * 12 + kHotMax * 8)) {}
+  __device__ __forceinline__ static unsigned int hash(long long key) {
+    return ((unsigned int)key * 2654435761u) >> 25;   // 7 bits
+  }
+  __device__ __forceinline__ int find(int table, int id) const {
+    const long long key = 2ll * id + table;
+    unsigned int h = hash(key);
+    for (;;) {
+      const long long k = keys[h];
+      if (k == key) return slots[h];
+      if (k < 0) return -1;
+      h = (h + 1) & (kHotTable - 1);
+    }
+  }
+};
+__host__ __device__ inline size_t hot_region_bytes(int n_hot, int row_f) {
+  return (size_t)kHotTable * 12 + (size_t)kHotMax * 8 + (size_t)n_hot * row_f * 4;
 }
 
 template <bool PAIRWISE>
 __device__ __forceinline__ void scatter_cols(const StepsArgs& a, int cidx, float c, float cu, float ci, int iu, int ia,
                                              int ib, float4 ru, float4 ra, float4 rb, int mu = kRowAdd, int ma = kRowAdd,
-                                             int mb = kRowAdd) {
+                                             int mb = kRowAdd, float* hu = nullptr, float* ha = nullptr, float* hb = nullptr) {
   const int64_t row_f = (int64_t)a.nv * 4;
   if (PAIRWISE) {
-    if (iu >= 0) emit_row4(mu, shard_row(a.user_dst, a.log2g, iu, row_f), cidx, axpy4(cu, ru, scale4(c, sub4(ra, rb))));
-    if (ia >= 0) emit_row4(ma, shard_row(a.item_dst, a.log2g, ia, row_f), cidx, axpy4(ci, ra, scale4(c, ru)));
-    if (ib >= 0) emit_row4(mb, shard_row(a.item_dst, a.log2g, ib, row_f), cidx, scale4(-c, ru));
+    if (iu >= 0) emit_row4(mu, hu ? hu : shard_row(a.user_dst, a.log2g, iu, row_f), cidx, axpy4(cu, ru, scale4(c, sub4(ra, rb))));
+    if (ia >= 0) emit_row4(ma, ha ? ha : shard_row(a.item_dst, a.log2g, ia, row_f), cidx, axpy4(ci, ra, scale4(c, ru)));
+    if (ib >= 0) emit_row4(mb, hb ? hb : shard_row(a.item_dst, a.log2g, ib, row_f), cidx, scale4(-c, ru));
   } else {
-    if (iu >= 0) emit_row4(mu, shard_row(a.user_dst, a.log2g, iu, row_f), cidx, axpy4(cu, ru, scale4(c, ra)));
-    if (ia >= 0) emit_row4(ma, shard_row(a.item_dst, a.log2g, ia, row_f), cidx, axpy4(ci, ra, scale4(c, ru)));
+    if (iu >= 0) emit_row4(mu, hu ? hu : shard_row(a.user_dst, a.log2g, iu, row_f), cidx, axpy4(cu, ru, scale4(c, ra)));
+    if (ia >= 0) emit_row4(ma, ha ? ha : shard_row(a.item_dst, a.log2g, ia, row_f), cidx, axpy4(ci, ra, scale4(c, ru)));
   }
 }
 
@@ -540,8 +584,40 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
   unsigned char* stage_ring = smem_raw + L.stage_off();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool lazy = LAZY;  // lazily zeroed destination tables (a.touch_u / a.touch_i): first touch stores, see the scatterers
-
-  if (threadIdx.x == 0) init_bars(B, tasks, kScatterWarps, n_stages, kScatterWarps);
+  // hot rows: table + zeroed accumulators in shared memory (built by everybody before the roles split)
+  const bool hot_on = !LAZY && a.hot_off != 0;
+  const HotRows hot(smem_raw + a.hot_off);
+  uint64_t* hot_done = reinterpret_cast<uint64_t*>(smem_raw + 288);   // [288, 296): every scatter warp is past its last step
+  if (hot_on) {
+    const int n_hot = a.n_hot_u + a.n_hot_i;
+    for (int i = threadIdx.x; i < kHotTable; i += blockDim.x) hot.keys[i] = -1;
+    for (int i = threadIdx.x; i < n_hot * row_f; i += blockDim.x) hot.acc[i] = 0.f;
+    __syncthreads();
+    if ((int)threadIdx.x < n_hot) {
+      const int t = (int)threadIdx.x < a.n_hot_u ? 0 : 1;
+      const int64_t id = t == 0 ? a.hot_u[threadIdx.x] : a.hot_i[threadIdx.x - a.n_hot_u];
+      long long key = -2;   // ids outside the table (or duplicates in the list) get an accumulator nobody finds
+      if ((uint64_t)id < (uint64_t)(t == 0 ? a.n_users : a.n_items)) key = 2ll * id + t;
+      hot.slot_key[threadIdx.x] = key;
+      if (key >= 0) {
+        unsigned int h = HotRows::hash(key);
+        for (;;) {
+          const long long prev = (long long)atomicCAS(reinterpret_cast<unsigned long long*>(&hot.keys[h]), (unsigned long long)-1ll,
+                                                      (unsigned long long)key);
+          if (prev == -1ll) { hot.slots[h] = (int)threadIdx.x; break; }
+          if (prev == key) { hot.slot_key[threadIdx.x] = -2; break; }   // listed twice: the first entry owns the row
+          h = (h + 1) & (kHotTable - 1);
+        }
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    init_bars(B, tasks, kScatterWarps, n_stages, kScatterWarps);
+    mbar_init(hot_done, kScatterWarps);
+#ifndef XDR_EMU
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+  }
   __syncthreads();
 
   if (warp == 0) {
@@ -654,6 +730,13 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
         const int ib = (PAIRWISE && (uint64_t)ib64 < (uint64_t)a.n_items) ? (int)ib64 : -1;
         const float label = (!PAIRWISE && a.label != nullptr) ? lab[j] : 0.f;
         const float c = score_coeff<PAIRWISE>(a, g, inv_b, sc[j], sc[L.slice + j], label);
+        float *hu = nullptr, *ha = nullptr, *hb = nullptr;
+        if (!lazy && hot_on) {   // rows on the hot list go to this CTA's shared-memory accumulators
+          int sl;
+          if (iu >= 0 && (sl = hot.find(0, iu)) >= 0) { hu = hot.acc + (size_t)sl * row_f; mu = kRowHot; }
+          if (ia >= 0 && (sl = hot.find(1, ia)) >= 0) { ha = hot.acc + (size_t)sl * row_f; ma = kRowHot; }
+          if (PAIRWISE && ib >= 0 && (sl = hot.find(1, ib)) >= 0) { hb = hot.acc + (size_t)sl * row_f; mb = kRowHot; }
+        }
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
           const int cidx = sub + v * LPR;
@@ -661,7 +744,7 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
           const float4 ru = ld_row4(rows + (size_t)j * row_f, cidx);
           const float4 ra = ld_row4(rows + ((size_t)L.slice + j) * row_f, cidx);
           const float4 rb = PAIRWISE ? ld_row4(rows + ((size_t)2 * L.slice + j) * row_f, cidx) : ru;
-          scatter_cols<PAIRWISE>(a, cidx, c, nf.x, nf.y, iu, ia, ib, ru, ra, rb, mu, ma, mb);
+          scatter_cols<PAIRWISE>(a, cidx, c, nf.x, nf.y, iu, ia, ib, ru, ra, rb, mu, ma, mb, hu, ha, hb);
         }
       };
       unsigned int* wp[kT];
@@ -739,6 +822,20 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
       } else if (lane == 0) {
         mbar_arrive(&B.sfree[st]);    // the stage slot may be overwritten by the loaders
         mbar_arrive(&B.ifree[slot]);  // the id slot may be refilled by the producer
+      }
+    }
+    if (hot_on) {   // one flush per CTA and launch: the accumulated hot rows go to their destination rows
+      __syncwarp();
+      if (lane == 0) mbar_arrive(hot_done);
+      if (x == 0) {
+        mbar_wait(hot_done, 0u);
+        const int n_hot = a.n_hot_u + a.n_hot_i;
+        for (int sl = 0; sl < n_hot; ++sl) {
+          const long long key = hot.slot_key[sl];
+          if (key < 0) continue;
+          float* row = shard_row((key & 1) ? a.item_dst : a.user_dst, 0, (int64_t)(key >> 1), row_f);
+          for (int c4 = lane; c4 < a.nv; c4 += 32) red_add4(row, c4, *reinterpret_cast<const float4*>(hot.acc + (size_t)sl * row_f + 4 * c4));
+        }
       }
     }
   }
@@ -885,6 +982,11 @@ static bool plan_steps(int64_t batch, int nv, bool pairwise, StepsPlan* plan) {
   return true;
 }
 
+// hot-row lists of the next launches (xdr_steps_set_hot_rows): device pointers to int64 row ids, users then items
+static const int64_t* g_hot_u = nullptr;
+static const int64_t* g_hot_i = nullptr;
+static int g_n_hot_u = 0, g_n_hot_i = 0;
+
 static int g_early_scatter = 0;  // opt-in (xdr_steps_set_early_scatter): reg_weight == 0 launches take the EARLY staged kernel
 
 template <int LPR, int VEC, bool PW>
@@ -944,6 +1046,18 @@ XDR_API void xdr_debug_force_register_kernel(int on) { g_force_regs = on; }
 // Opt-in until it has run on hardware: launches with reg_weight == 0 (CMF's yaml default lambda = gamma = 0, reg-free BPR)
 // scatter without waiting for the step's norm exchange (train_steps_staged_kernel<..., EARLY = true>).
 XDR_API void xdr_steps_set_early_scatter(int on) { g_early_scatter = on; }
+
+// Hot rows of the following xdr_train_steps launches (plain scatter-add destinations, single GPU): device arrays of int64 row
+// ids -- e.g. the most popular items of the catalogue, computed once per dataset.  Every CTA accumulates the gradients of
+// these rows in shared memory over the whole launch and adds them to the destination once, at the end (same sums, other
+// order).  At most 64 rows (fewer for rows wider than 64 floats); the arrays must stay valid while launches use them.
+// n_hot_users = n_hot_items = 0 switches it off.
+int xdr_steps_set_hot_rows(const int64_t* hot_users, int n_hot_users, const int64_t* hot_items, int n_hot_items) {
+  XDR_REQUIRE(n_hot_users >= 0 && n_hot_items >= 0, "xdr_steps_set_hot_rows: negative count");
+  XDR_REQUIRE((n_hot_users == 0 || hot_users) && (n_hot_items == 0 || hot_items), "xdr_steps_set_hot_rows: null id array");
+  g_hot_u = hot_users; g_hot_i = hot_items; g_n_hot_u = n_hot_users; g_n_hot_i = n_hot_items;
+  return XDR_OK;
+}
 
 // 2 bits per row, 16 rows per 32-bit word; every table's part is padded to a multiple of 4 words (16 bytes)
 static inline size_t touch_words_of(int64_t n_rows) { return (size_t)(((n_rows + 15) / 16 + 3) & ~(int64_t)3); }
@@ -1022,6 +1136,21 @@ static int train_steps_core(const Shards& user_tab, const Shards& item_tab, cons
   a.words = reinterpret_cast<unsigned long long*>(steps_ws);
   a.trace = g_trace;
   cudaStream_t s = (cudaStream_t)stream;
+  if (touch == nullptr && log2g == 0 && plan.stages > 0 && stage_a == nullptr && g_n_hot_u + g_n_hot_i > 0) {
+    // hot rows: as many of the listed rows as fit 16 KB of accumulators (users first), if the CTA still fits shared memory
+    const int row_f = dim;
+    int nu_h = g_n_hot_u, ni_h = g_n_hot_i;
+    const int cap = (int)((size_t)kHotBytes / ((size_t)row_f * 4)) < kHotMax ? (int)((size_t)kHotBytes / ((size_t)row_f * 4)) : kHotMax;
+    if (nu_h > cap) nu_h = cap;
+    if (ni_h > cap - nu_h) ni_h = cap - nu_h;
+    const size_t extra = hot_region_bytes(nu_h + ni_h, row_f);
+    const size_t base = (plan.smem + 127) & ~(size_t)127;
+    if (nu_h + ni_h > 0 && base + extra <= (size_t)220 * 1024) {
+      a.hot_u = g_hot_u; a.hot_i = g_hot_i; a.n_hot_u = nu_h; a.n_hot_i = ni_h;
+      a.hot_off = base;
+      plan.smem = base + extra;
+    }
+  }
   if (touch != nullptr) {
     a.touch_u = touch;
     a.touch_i = touch + touch_words_of(n_users);

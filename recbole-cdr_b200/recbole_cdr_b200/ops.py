@@ -483,6 +483,32 @@ def train_steps_supported(batch: int, dim: int, pairwise: bool, device=None) -> 
     return tasks <= 2 * 20 and base <= 220 * 1024  # register kernel
 
 
+_hot_rows_keepalive = {}
+
+
+def set_steps_hot_rows(hot_users=None, hot_items=None):
+    """Hot rows of the following ``train_steps`` launches (``xdr_steps_set_hot_rows``): int64 device tensors of row ids whose
+    gradients every CTA pre-aggregates in shared memory (popular items of a Zipf-like catalogue).  ``None`` / empty switches
+    a side off.  The tensors are kept alive here until replaced."""
+    hu = hot_users.contiguous() if hot_users is not None and hot_users.numel() else None
+    hi = hot_items.contiguous() if hot_items is not None and hot_items.numel() else None
+    for t in (hu, hi):
+        if t is not None and (t.dtype != torch.int64 or not _on_device(t)):
+            raise ValueError('hot row ids must be int64 device tensors')
+    _hot_rows_keepalive['u'], _hot_rows_keepalive['i'] = hu, hi
+    call('xdr_steps_set_hot_rows', ptr(hu), 0 if hu is None else hu.numel(), ptr(hi), 0 if hi is None else hi.numel())
+
+
+def hot_rows_from_ids(ids, n_rows: int, k: int = 32, min_share: float = 2e-3):
+    """The (at most ``k``) rows that ``ids`` names most often and that each take at least ``min_share`` of all occurrences --
+    a dataset statistic (popular items), computed once.  Returns an int64 tensor (possibly empty)."""
+    flat = ids.reshape(-1)
+    cnt = torch.bincount(flat, minlength=int(n_rows))
+    top = torch.topk(cnt, min(k, cnt.numel()))
+    keep = top.values.float() >= min_share * float(flat.numel())
+    return top.indices[keep].to(torch.int64)
+
+
 class TouchMap:
     """Which rows of a pair of gradient tables hold gradients -- the state of *lazily zeroed* gradient tables
     (``xdr_train_steps_lazy``, include/xdr.h).  2 bits per row (bit 0 claimed, bit 1 zero-filled), user part first.  A row

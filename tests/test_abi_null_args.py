@@ -17,7 +17,7 @@ sys.path.insert(0, %(pkg)r)
 from recbole_cdr_b200 import _lib
 QUERIES = {'xdr_version', 'xdr_workspace_bytes', 'xdr_steps_workspace_bytes', 'xdr_topk_workspace_bytes',
            'xdr_tc_conet_scratch_bytes', 'xdr_last_error', 'xdr_device_info', 'xdr_fused_mlp_supported',
-           'xdr_tc_mlp_supported', 'xdr_tc_conet_supported', 'xdr_set_coop_launch', 'xdr_set_dense_engine'}
+           'xdr_tc_mlp_supported', 'xdr_tc_conet_supported', 'xdr_set_coop_launch', 'xdr_set_dense_engine', 'xdr_steps_set_hot_rows'}
 out = {}
 for name, (res, argt) in sorted(_lib.PROTOTYPES.items()):
     if name in QUERIES or name.endswith('_supported') or name.endswith('_bytes') or res is not _lib.c_int:

@@ -427,3 +427,39 @@ def test_lazy_gradient_tables_pointwise_and_refusals():
     torch.testing.assert_close(gu[tu], gu_ref[tu], rtol=1e-4, atol=1e-4 * gu_ref.abs().max().item())
     torch.testing.assert_close(gi[ti], gi_ref[ti], rtol=1e-4, atol=1e-4 * gi_ref.abs().max().item())
     assert bool((gu[~tu] == 9.0).all())
+
+
+# ------------------------------------------------------------------------------------------ hot rows in shared memory
+@pytest.mark.parametrize('pairwise,sms,seed', [(True, 3, 0), (True, 2, 9), (False, 2, 4)])
+def test_hot_rows_accumulate_in_shared_memory_and_flush_once(pairwise, sms, seed):
+    """xdr_steps_set_hot_rows: the gradients of the listed (popular) rows are added in every CTA's shared memory over the whole
+    launch and flushed once; everything else goes the usual way.  Same sums as the oracle, for lists that name popular rows,
+    rows nobody touches, an out-of-range id and a duplicate."""
+    from recbole_cdr_b200 import _lib
+    K, B, dim, nu, ni = 7, 96, 64, 120, 150
+    ut, it, u, ip, ineg, y = setup(nu, ni, dim, K, B, 21 + seed)
+    ip[:, ::3] = 5          # a third of every batch names item 5, a sixth item 9 (the popular rows)
+    ineg[:, ::6] = 9
+    u[:, ::4] = 2
+    hot_u = torch.tensor([2, 77, 2, 10_000], dtype=torch.int64)       # popular, cold, duplicate, out of range
+    hot_i = torch.tensor([5, 9, 149, 33], dtype=torch.int64)
+    with emu_util.patched_ops(sms=sms, seed=seed) as ops:
+        ops.set_steps_hot_rows(hot_u, hot_i)
+        try:
+            if pairwise:
+                out8, gu, gi = ops.train_steps(ut.clone(), it.clone(), u, ip, ineg, reg_weight=0.01)
+            else:
+                out8, gu, gi = ops.train_steps(ut.clone(), it.clone(), u, ip, None, y, loss_kind=_lib.LOSS_BCE_SIGMOID, reg_weight=0.01)
+        finally:
+            ops.set_steps_hot_rows(None, None)
+        if pairwise:
+            o2, gu2, gi2 = ops.train_steps(ut.clone(), it.clone(), u, ip, ineg, reg_weight=0.01)
+        else:
+            o2, gu2, gi2 = ops.train_steps(ut.clone(), it.clone(), u, ip, None, y, loss_kind=_lib.LOSS_BCE_SIGMOID, reg_weight=0.01)
+    assert torch.equal(out8[:, 0], o2[:, 0])
+    torch.testing.assert_close(gu, gu2, rtol=1e-5, atol=1e-6 * gu2.abs().max().item())
+    torch.testing.assert_close(gi, gi2, rtol=1e-5, atol=1e-6 * gi2.abs().max().item())
+    if pairwise:
+        gu_ref, gi_ref, _ = _oracle_grads(ut, it, u, ip, ineg, range(K))
+        torch.testing.assert_close(gu, gu_ref, rtol=1e-4, atol=1e-4 * gu_ref.abs().max().item())
+        torch.testing.assert_close(gi, gi_ref, rtol=1e-4, atol=1e-4 * gi_ref.abs().max().item())

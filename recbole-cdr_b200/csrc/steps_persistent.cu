@@ -287,61 +287,75 @@ __device__ __forceinline__ void service_publisher(const StepsArgs& a, const Smem
   }
 }
 
-// steps s = which, which+2, ...: root CTA (s mod grid) gathers + reduces + republishes; the others poll the result
+// steps s = which, which+2, ...: EVERY CTA polls all CTAs' words itself and reduces them in fp64 in one fixed order, so all
+// CTAs derive bit-identical norm factors without a second hop (round 1 / early round 2: a rotating root CTA reduced and
+// republished two result words, and the others polled those -- one more store -> poll round trip, 3.6 us per exchange
+// against ~1.8 us).  A lane re-reads only the words it has not seen with the step's tag yet, so the polling volume falls
+// as the partials arrive; CTA (s mod grid) also writes the step's loss record.
 __device__ __forceinline__ void service_gatherer(const StepsArgs& a, const Bars& B, float2* norms, int which, int lane) {
   const unsigned int n_cta = gridDim.x;
   const float inv_b = 1.0f / (float)a.batch;
   const float g = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f) * a.scale;
-  unsigned long long* finals = a.words + (size_t)a.n_steps * n_cta * 3;  // [n_steps][2] {factor, tag}
   for (int s = which; s < a.n_steps; s += 2) {
     const int slot = s % kRing;
     const unsigned int tag = a.tag_base + (unsigned int)(s + 1);
-    float cu = 0.f, ci = 0.f;
-    if ((unsigned int)s % n_cta == blockIdx.x) {
-      const unsigned long long* base = a.words + (size_t)s * n_cta * 3;
-      unsigned long long wv[kMaxCtaPerLane][3];
-      bool all_ok;
-      do {
+    // the CTA's own partial first (shared-memory barrier): nobody polls global memory for a step its own CTA has not
+    // finished, which keeps CTAs that run ahead from hammering L2
+    mbar_wait(&B.adone[slot], (uint32_t)((s / kRing) & 1));
+    const unsigned long long* base = a.words + (size_t)s * n_cta * 3;
+    unsigned long long wv[kMaxCtaPerLane][3];
 #pragma unroll
-        for (int i = 0; i < kMaxCtaPerLane; ++i) {
-          const unsigned int c = lane + 32u * i;
-          if (c < n_cta) {
+    for (int i = 0; i < kMaxCtaPerLane; ++i)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) wv[i][k] = ld_relaxed_u64(base + (size_t)c * 3 + k);
-          }
-        }
-        all_ok = true;
-#pragma unroll
-        for (int i = 0; i < kMaxCtaPerLane; ++i) {
-          const unsigned int c = lane + 32u * i;
-          if (c < n_cta) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) all_ok = all_ok && ((unsigned int)(wv[i][k] >> 32) == tag);
-          }
-        }
-        all_ok = __all_sync(0xffffffffu, all_ok);
-      } while (!all_ok);
-      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+      for (int k = 0; k < 3; ++k) wv[i][k] = ~((unsigned long long)tag << 32);  // (a tag that is not this step's)
+    bool all_ok;
+    int rounds = 0;
+    do {
 #pragma unroll
       for (int i = 0; i < kMaxCtaPerLane; ++i) {
         const unsigned int c = lane + 32u * i;
         if (c < n_cta) {
-          t0 += (double)__uint_as_float((unsigned int)wv[i][0]);
-          t1 += (double)__uint_as_float((unsigned int)wv[i][1]);
-          t2 += (double)__uint_as_float((unsigned int)wv[i][2]);
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if ((unsigned int)(wv[i][k] >> 32) != tag) wv[i][k] = ld_relaxed_u64(base + (size_t)c * 3 + k);
         }
       }
-      t0 = warp_sum(t0);
-      t1 = warp_sum(t1);
-      t2 = warp_sum(t2);
-      const float nu = (float)sqrt(t1), ni = (float)sqrt(t2);
-      // d(reg_weight * (||U||_F + ||I||_F)/B)/dU_r = reg_weight/(B*||U||_F) * U_r   (torch: 0 when the norm is 0)
-      cu = (a.reg_weight != 0.f && nu > 0.f) ? g * a.reg_weight * inv_b / nu : 0.f;
-      ci = (a.reg_weight != 0.f && ni > 0.f) ? g * a.reg_weight * inv_b / ni : 0.f;
-      if (lane < 2)
-        st_relaxed_u64(finals + (size_t)s * 2 + lane,
-                       ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(lane == 0 ? cu : ci));
-      if (lane == 0) {
+      all_ok = true;
+#pragma unroll
+      for (int i = 0; i < kMaxCtaPerLane; ++i) {
+        const unsigned int c = lane + 32u * i;
+        if (c < n_cta) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) all_ok = all_ok && ((unsigned int)(wv[i][k] >> 32) == tag);
+        }
+      }
+      all_ok = __all_sync(0xffffffffu, all_ok);
+#ifndef XDR_EMU
+      if (!all_ok && ++rounds > 2) __nanosleep(64);
+#endif
+    } while (!all_ok);
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < kMaxCtaPerLane; ++i) {
+      const unsigned int c = lane + 32u * i;
+      if (c < n_cta) {
+        t0 += (double)__uint_as_float((unsigned int)wv[i][0]);
+        t1 += (double)__uint_as_float((unsigned int)wv[i][1]);
+        t2 += (double)__uint_as_float((unsigned int)wv[i][2]);
+      }
+    }
+    t0 = warp_sum(t0);
+    t1 = warp_sum(t1);
+    t2 = warp_sum(t2);
+    const float nu = (float)sqrt(t1), ni = (float)sqrt(t2);
+    // d(reg_weight * (||U||_F + ||I||_F)/B)/dU_r = reg_weight/(B*||U||_F) * U_r   (torch: 0 when the norm is 0)
+    const float cu = (a.reg_weight != 0.f && nu > 0.f) ? g * a.reg_weight * inv_b / nu : 0.f;
+    const float ci = (a.reg_weight != 0.f && ni > 0.f) ? g * a.reg_weight * inv_b / ni : 0.f;
+    if (a.trace && lane == 0) a.trace[((size_t)s * n_cta + blockIdx.x) * 8 + 1] = gtime();
+    if (lane == 0) {
+      norms[slot] = make_float2(cu, ci);
+      mbar_arrive(&B.normf[slot]);  // release: the norms are visible to everyone who observes this phase
+      if ((unsigned int)s % n_cta == blockIdx.x) {
         const float data = (float)(t0 / (double)a.batch);
         const float reg = (float)(((double)nu + (double)ni) / (double)a.batch);
         float* o = a.out8 + (size_t)s * 8;
@@ -354,24 +368,6 @@ __device__ __forceinline__ void service_gatherer(const StepsArgs& a, const Bars&
         o[6] = 0.f;
         o[7] = 0.f;
       }
-    } else {
-      unsigned long long f0 = 0, f1 = 0;
-      if (lane == 0) {
-        const unsigned long long* f = finals + (size_t)s * 2;
-        for (;;) {
-          f0 = ld_relaxed_u64(f);
-          f1 = ld_relaxed_u64(f + 1);
-          if ((unsigned int)(f0 >> 32) == tag && (unsigned int)(f1 >> 32) == tag) break;
-          __nanosleep(64);
-        }
-      }
-      cu = __uint_as_float((unsigned int)__shfl_sync(0xffffffffu, f0, 0));
-      ci = __uint_as_float((unsigned int)__shfl_sync(0xffffffffu, f1, 0));
-    }
-    if (a.trace && lane == 0) a.trace[((size_t)s * n_cta + blockIdx.x) * 8 + 1] = gtime();
-    if (lane == 0) {
-      norms[slot] = make_float2(cu, ci);
-      mbar_arrive(&B.normf[slot]);  // release: the norms are visible to everyone who observes this phase
     }
     __syncwarp();
   }
@@ -567,7 +563,7 @@ __device__ __forceinline__ void init_bars(const Bars& B, int tasks, int ifree_co
 // the batch-wide norms, so the scatterers do not wait for the step's norm exchange before they issue the REDs and free the
 // stage slot; they still wait for it before they free the id slot, which keeps the id / partial / norm rings in step (the
 // per-step loss is still the exchanged batch mean).
-template <int LPR, int VEC, bool PAIRWISE, int kLoaderWarps, bool EARLY = false, bool LAZY = false>
+template <int LPR, int VEC, bool PAIRWISE, int kLoaderWarps, bool EARLY = false, bool LAZY = false, bool HOT = false>
 __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(StepsArgs a, int n_stages) {
   constexpr int IPW = 32 / LPR;
   constexpr int R = PAIRWISE ? 3 : 2;
@@ -585,10 +581,10 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool lazy = LAZY;  // lazily zeroed destination tables (a.touch_u / a.touch_i): first touch stores, see the scatterers
   // hot rows: table + zeroed accumulators in shared memory (built by everybody before the roles split)
-  const bool hot_on = !LAZY && a.hot_off != 0;
+  constexpr bool hot_on = HOT && !LAZY;   // (a template parameter: the plain instantiation carries none of this)
   const HotRows hot(smem_raw + a.hot_off);
   uint64_t* hot_done = reinterpret_cast<uint64_t*>(smem_raw + 288);   // [288, 296): every scatter warp is past its last step
-  if (hot_on) {
+  if constexpr (hot_on) {
     const int n_hot = a.n_hot_u + a.n_hot_i;
     for (int i = threadIdx.x; i < kHotTable; i += blockDim.x) hot.keys[i] = -1;
     for (int i = threadIdx.x; i < n_hot * row_f; i += blockDim.x) hot.acc[i] = 0.f;
@@ -613,7 +609,7 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
   }
   if (threadIdx.x == 0) {
     init_bars(B, tasks, kScatterWarps, n_stages, kScatterWarps);
-    mbar_init(hot_done, kScatterWarps);
+    if (hot_on) mbar_init(hot_done, kScatterWarps);
 #ifndef XDR_EMU
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
@@ -731,7 +727,7 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
         const float label = (!PAIRWISE && a.label != nullptr) ? lab[j] : 0.f;
         const float c = score_coeff<PAIRWISE>(a, g, inv_b, sc[j], sc[L.slice + j], label);
         float *hu = nullptr, *ha = nullptr, *hb = nullptr;
-        if (!lazy && hot_on) {   // rows on the hot list go to this CTA's shared-memory accumulators
+        if constexpr (hot_on) {   // rows on the hot list go to this CTA's shared-memory accumulators
           int sl;
           if (iu >= 0 && (sl = hot.find(0, iu)) >= 0) { hu = hot.acc + (size_t)sl * row_f; mu = kRowHot; }
           if (ia >= 0 && (sl = hot.find(1, ia)) >= 0) { ha = hot.acc + (size_t)sl * row_f; ma = kRowHot; }
@@ -824,7 +820,7 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
         mbar_arrive(&B.ifree[slot]);  // the id slot may be refilled by the producer
       }
     }
-    if (hot_on) {   // one flush per CTA and launch: the accumulated hot rows go to their destination rows
+    if constexpr (hot_on) {   // one flush per CTA and launch: the accumulated hot rows go to their destination rows
       __syncwarp();
       if (lane == 0) mbar_arrive(hot_done);
       if (x == 0) {
@@ -997,6 +993,9 @@ static int launch_steps(const StepsArgs& a, const StepsPlan& plan, cudaStream_t 
     XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsLite), plan.smem, s, a, plan.stages);
   } else if (plan.stages > 0 && lazy) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull, false, true>;
+    XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s, a, plan.stages);
+  } else if (plan.stages > 0 && a.hot_off != 0) {
+    auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull, false, false, true>;
     XDR_LAUNCH_COOP((kern), plan.grid, staged_threads(kLoaderWarpsFull), plan.smem, s, a, plan.stages);
   } else if (plan.stages > 0 && g_early_scatter && a.reg_weight == 0.f) {
     auto kern = train_steps_staged_kernel<LPR, VEC, PW, kLoaderWarpsFull, true>;

@@ -153,6 +153,11 @@ def test_tc5_selftest_gemm_all_majors(a_mn, b_mn, N, K):
     D = np.zeros((128, N), np.float32)
     p = emu_util.p
     rc = L.xdr_tc5_selftest(p(A), p(B), ctypes.c_int(N), ctypes.c_int(K), ctypes.c_int(a_mn), ctypes.c_int(b_mn), p(D), None)
+    if a_mn or b_mn:
+        # the B200 refused MN-major TF32 operands in the SWIZZLE_NONE layouts (round 2, call 1): the entry point says so instead of
+        # issuing them; MN-major operands go through the 16-bit planes (next test)
+        assert rc == -3 and b'MN-major' in L.emu_last_error()
+        return
     assert rc == 0, L.emu_last_error()
     np.testing.assert_allclose(D, A.astype(np.float64) @ B.astype(np.float64).T, rtol=1e-5, atol=1e-5)
 

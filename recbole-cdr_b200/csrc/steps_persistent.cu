@@ -118,14 +118,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 __device__ __forceinline__ unsigned long long gtime() { return ++emu::st().clock; }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  emu::note_site("poll exchange word");
   emu::yield();  // every poll gives the other fibers a turn
   return *p;
 }
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) { *p = v; }
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  emu::note_site("poll touch word");
   emu::yield();
   return *p;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() {}
 #else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -189,6 +192,7 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 #endif  // XDR_EMU
 // coherent (L2) 128-bit row load: the table may be the scatter destination of this very launch (fused SGD)
 __device__ __forceinline__ float4 ldcg_row4(const float* row, int col4) {
@@ -235,7 +239,18 @@ struct TaskRegs {
   int iu, ia, ib;  // row ids (tables have < 2^31 rows); -1 = padding lane or out-of-range id (row reads as zeros)
   float sa, sb, label;
   int s, q;
+  // lazily zeroed destination tables: lanes 0..R-1 of an interaction's group hold the claim of its user / item+ / item- row
+  unsigned int old;  // the row's touch-map word as the claim found it (see lazy_claim_of for the word and the bit)
 };
+
+// the touch-map word and "claimed" bit of the row lane `sub` of a group looks after (nullptr: none -- lane >= R or a bad id)
+template <int VEC, bool PAIRWISE>
+__device__ __forceinline__ unsigned int* lazy_claim_of(const TaskRegs<VEC, PAIRWISE>& r, const StepsArgs& a, int sub,
+                                                       unsigned int& cbit) {
+  const int id = sub == 0 ? r.iu : (sub == 1 ? r.ia : ((PAIRWISE && sub == 2) ? r.ib : -1));
+  cbit = 1u << (((unsigned int)id & 15u) * 2u);
+  return id < 0 ? nullptr : (sub == 0 ? a.touch_u : a.touch_i) + (id >> 4);
+}
 
 // ---- service warps (shared by both kernels) ---------------------------------------------------------------------------
 template <bool PAIRWISE>
@@ -287,75 +302,64 @@ __device__ __forceinline__ void service_publisher(const StepsArgs& a, const Smem
   }
 }
 
-// steps s = which, which+2, ...: EVERY CTA polls all CTAs' words itself and reduces them in fp64 in one fixed order, so all
-// CTAs derive bit-identical norm factors without a second hop (round 1 / early round 2: a rotating root CTA reduced and
-// republished two result words, and the others polled those -- one more store -> poll round trip, 3.6 us per exchange
-// against ~1.8 us).  A lane re-reads only the words it has not seen with the step's tag yet, so the polling volume falls
-// as the partials arrive; CTA (s mod grid) also writes the step's loss record.
+// (Round 2, call 18: an "all-read" form -- every CTA polls all CTAs' words itself, no republished result -- was measured and
+// is SLOWER: 148 CTAs polling 444 words each through a memory system the gather keeps saturated stretched the exchange from
+// 3.6 to 4.4 us and the K = 20 step from 3.52 to 3.58 us.  The rotating-root form stays.)
+// steps s = which, which+2, ...: root CTA (s mod grid) gathers + reduces + republishes; the others poll the result
 __device__ __forceinline__ void service_gatherer(const StepsArgs& a, const Bars& B, float2* norms, int which, int lane) {
   const unsigned int n_cta = gridDim.x;
   const float inv_b = 1.0f / (float)a.batch;
   const float g = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f) * a.scale;
+  unsigned long long* finals = a.words + (size_t)a.n_steps * n_cta * 3;  // [n_steps][2] {factor, tag}
   for (int s = which; s < a.n_steps; s += 2) {
     const int slot = s % kRing;
     const unsigned int tag = a.tag_base + (unsigned int)(s + 1);
-    // the CTA's own partial first (shared-memory barrier): nobody polls global memory for a step its own CTA has not
-    // finished, which keeps CTAs that run ahead from hammering L2
-    mbar_wait(&B.adone[slot], (uint32_t)((s / kRing) & 1));
-    const unsigned long long* base = a.words + (size_t)s * n_cta * 3;
-    unsigned long long wv[kMaxCtaPerLane][3];
+    float cu = 0.f, ci = 0.f;
+    if ((unsigned int)s % n_cta == blockIdx.x) {
+      const unsigned long long* base = a.words + (size_t)s * n_cta * 3;
+      unsigned long long wv[kMaxCtaPerLane][3];
+      bool all_ok;
+      do {
 #pragma unroll
-    for (int i = 0; i < kMaxCtaPerLane; ++i)
+        for (int i = 0; i < kMaxCtaPerLane; ++i) {
+          const unsigned int c = lane + 32u * i;
+          if (c < n_cta) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) wv[i][k] = ~((unsigned long long)tag << 32);  // (a tag that is not this step's)
-    bool all_ok;
-    int rounds = 0;
-    do {
+            for (int k = 0; k < 3; ++k) wv[i][k] = ld_relaxed_u64(base + (size_t)c * 3 + k);
+          }
+        }
+        all_ok = true;
+#pragma unroll
+        for (int i = 0; i < kMaxCtaPerLane; ++i) {
+          const unsigned int c = lane + 32u * i;
+          if (c < n_cta) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) all_ok = all_ok && ((unsigned int)(wv[i][k] >> 32) == tag);
+          }
+        }
+        all_ok = __all_sync(0xffffffffu, all_ok);
+      } while (!all_ok);
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll
       for (int i = 0; i < kMaxCtaPerLane; ++i) {
         const unsigned int c = lane + 32u * i;
         if (c < n_cta) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            if ((unsigned int)(wv[i][k] >> 32) != tag) wv[i][k] = ld_relaxed_u64(base + (size_t)c * 3 + k);
+          t0 += (double)__uint_as_float((unsigned int)wv[i][0]);
+          t1 += (double)__uint_as_float((unsigned int)wv[i][1]);
+          t2 += (double)__uint_as_float((unsigned int)wv[i][2]);
         }
       }
-      all_ok = true;
-#pragma unroll
-      for (int i = 0; i < kMaxCtaPerLane; ++i) {
-        const unsigned int c = lane + 32u * i;
-        if (c < n_cta) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) all_ok = all_ok && ((unsigned int)(wv[i][k] >> 32) == tag);
-        }
-      }
-      all_ok = __all_sync(0xffffffffu, all_ok);
-#ifndef XDR_EMU
-      if (!all_ok && ++rounds > 2) __nanosleep(64);
-#endif
-    } while (!all_ok);
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-#pragma unroll
-    for (int i = 0; i < kMaxCtaPerLane; ++i) {
-      const unsigned int c = lane + 32u * i;
-      if (c < n_cta) {
-        t0 += (double)__uint_as_float((unsigned int)wv[i][0]);
-        t1 += (double)__uint_as_float((unsigned int)wv[i][1]);
-        t2 += (double)__uint_as_float((unsigned int)wv[i][2]);
-      }
-    }
-    t0 = warp_sum(t0);
-    t1 = warp_sum(t1);
-    t2 = warp_sum(t2);
-    const float nu = (float)sqrt(t1), ni = (float)sqrt(t2);
-    // d(reg_weight * (||U||_F + ||I||_F)/B)/dU_r = reg_weight/(B*||U||_F) * U_r   (torch: 0 when the norm is 0)
-    const float cu = (a.reg_weight != 0.f && nu > 0.f) ? g * a.reg_weight * inv_b / nu : 0.f;
-    const float ci = (a.reg_weight != 0.f && ni > 0.f) ? g * a.reg_weight * inv_b / ni : 0.f;
-    if (a.trace && lane == 0) a.trace[((size_t)s * n_cta + blockIdx.x) * 8 + 1] = gtime();
-    if (lane == 0) {
-      norms[slot] = make_float2(cu, ci);
-      mbar_arrive(&B.normf[slot]);  // release: the norms are visible to everyone who observes this phase
-      if ((unsigned int)s % n_cta == blockIdx.x) {
+      t0 = warp_sum(t0);
+      t1 = warp_sum(t1);
+      t2 = warp_sum(t2);
+      const float nu = (float)sqrt(t1), ni = (float)sqrt(t2);
+      // d(reg_weight * (||U||_F + ||I||_F)/B)/dU_r = reg_weight/(B*||U||_F) * U_r   (torch: 0 when the norm is 0)
+      cu = (a.reg_weight != 0.f && nu > 0.f) ? g * a.reg_weight * inv_b / nu : 0.f;
+      ci = (a.reg_weight != 0.f && ni > 0.f) ? g * a.reg_weight * inv_b / ni : 0.f;
+      if (lane < 2)
+        st_relaxed_u64(finals + (size_t)s * 2 + lane,
+                       ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(lane == 0 ? cu : ci));
+      if (lane == 0) {
         const float data = (float)(t0 / (double)a.batch);
         const float reg = (float)(((double)nu + (double)ni) / (double)a.batch);
         float* o = a.out8 + (size_t)s * 8;
@@ -368,6 +372,24 @@ __device__ __forceinline__ void service_gatherer(const StepsArgs& a, const Bars&
         o[6] = 0.f;
         o[7] = 0.f;
       }
+    } else {
+      unsigned long long f0 = 0, f1 = 0;
+      if (lane == 0) {
+        const unsigned long long* f = finals + (size_t)s * 2;
+        for (;;) {
+          f0 = ld_relaxed_u64(f);
+          f1 = ld_relaxed_u64(f + 1);
+          if ((unsigned int)(f0 >> 32) == tag && (unsigned int)(f1 >> 32) == tag) break;
+          __nanosleep(64);
+        }
+      }
+      cu = __uint_as_float((unsigned int)__shfl_sync(0xffffffffu, f0, 0));
+      ci = __uint_as_float((unsigned int)__shfl_sync(0xffffffffu, f1, 0));
+    }
+    if (a.trace && lane == 0) a.trace[((size_t)s * n_cta + blockIdx.x) * 8 + 1] = gtime();
+    if (lane == 0) {
+      norms[slot] = make_float2(cu, ci);
+      mbar_arrive(&B.normf[slot]);  // release: the norms are visible to everyone who observes this phase
     }
     __syncwarp();
   }
@@ -375,7 +397,7 @@ __device__ __forceinline__ void service_gatherer(const StepsArgs& a, const Bars&
 
 // ---- task primitives (shared) ------------------------------------------------------------------------------------------
 // request the rows of CTA-local task `lt` (ids from the shared-memory ring)
-template <int LPR, int VEC, bool PAIRWISE>
+template <int LPR, int VEC, bool PAIRWISE, bool LAZY = false>
 __device__ __forceinline__ void task_issue(TaskRegs<VEC, PAIRWISE>& r, int lt, const StepsArgs& a, const SmemLayout& L,
                                            const Bars& B, const unsigned char* ids_ring, int tasks, int cnt, int lane) {
   constexpr int IPW = 32 / LPR;
@@ -421,6 +443,86 @@ __device__ __forceinline__ void task_issue(TaskRegs<VEC, PAIRWISE>& r, int lt, c
     r.a[v] = (oka && on) ? ldcg_row4(pa, c) : z4;
     if (PAIRWISE) r.b[v] = (okb && on) ? ldcg_row4(pb, c) : z4;
   }
+  if (LAZY) {
+    // claim the task's destination rows (bit 0 of the row's pair in the touch map); the answers travel with the row loads
+    // and are consumed by task_resolve
+    unsigned int cbit;
+    unsigned int* wp = lazy_claim_of(r, a, sub, cbit);
+    r.old = wp ? atomicOr(wp, cbit) : 0u;
+  }
+}
+
+// Lazily zeroed destination tables, loader side ("claim and fill at gather time").  A row's claim is requested together
+// with its gather (task_issue), by the loader that gathers it:
+//   won        -> nobody has touched the row since the map was cleared: the loader stores a row of ZEROS (whole 128-byte
+//                 lines: L2 allocates them without reading DRAM) and, after its fence, sets the row's "filled" bit;
+//   lost, filled  -> nothing to do: the zeros (or earlier sums) are in L2;
+//   lost, not yet filled -> the winner -- another loader, a few microseconds ahead -- is between its claim and its
+//                 publication: wait for the bit here.
+// When a window is resolved every destination row of its tasks is ready for plain REDs, so the scatter warps are exactly
+// those of the plain kernel.  A loader resolves the claims of a WINDOW of two tasks at once (one claim round trip and one
+// fence per window).  Deadlock freedom: between a claim and the publication of its "filled" bit a loader waits for memory
+// only, never for a barrier (the window waits for both id tiles first, issues, resolves, and only then turns to the stage
+// ring), and it publishes before it polls.
+// Measured (round 2, calls 18-23, profiles/r2_lazy_tables.md): 4.5 us/step at K = 200 against 3.0 for plain scatter-add --
+// under load every dependent memory round trip (claim answers, fence) costs 2.5-4 us on a warp that then gathers nothing.
+// Variants that moved the fence to a publisher warp, kept the rolling two-task pipeline with guarded barrier waits, or let
+// the scatter warps wait for the bits were all slower or equal; this is the simplest of the family.  Opt-in.
+template <int LPR, int VEC, bool PAIRWISE>
+__device__ __forceinline__ bool lazy_fill(const TaskRegs<VEC, PAIRWISE>& r, const StepsArgs& a, int lane) {
+  const int sub = lane % LPR, grp = lane / LPR;
+  const int64_t row_f = (int64_t)a.nv * 4;
+  unsigned int cbit;
+  const bool won = lazy_claim_of(r, a, sub, cbit) != nullptr && (r.old & cbit) == 0u;
+  const unsigned int won_mask = __ballot_sync(0xffffffffu, won);
+  if (won_mask != 0u) {
+    const unsigned int gw = won_mask >> (grp * LPR);   // bits 0..2: the group's user / item+ / item- row was won
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* du = (gw & 1u) ? shard_row(a.user_dst, 0, r.iu, row_f) : nullptr;
+    float* da = (gw & 2u) ? shard_row(a.item_dst, 0, r.ia, row_f) : nullptr;
+    float* db = (PAIRWISE && (gw & 4u)) ? shard_row(a.item_dst, 0, r.ib, row_f) : nullptr;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int c = sub + v * LPR;
+      if (c >= a.nv) continue;
+      if (du) st4(du, c, z4);
+      if (da) st4(da, c, z4);
+      if (db) st4(db, c, z4);
+    }
+  }
+  return won_mask != 0u;
+}
+template <int VEC, bool PAIRWISE>
+__device__ __forceinline__ void lazy_publish(const TaskRegs<VEC, PAIRWISE>& r, const StepsArgs& a, int sub) {
+  unsigned int cbit;
+  unsigned int* wp = lazy_claim_of(r, a, sub, cbit);
+  if (wp != nullptr && (r.old & cbit) == 0u) atomicOr(wp, cbit << 1);
+}
+template <int VEC, bool PAIRWISE>
+__device__ __forceinline__ void lazy_wait_filled(const TaskRegs<VEC, PAIRWISE>& r, const StepsArgs& a, int sub) {
+  unsigned int cbit;
+  unsigned int* wp = lazy_claim_of(r, a, sub, cbit);
+  const bool pending = wp != nullptr && (r.old & cbit) != 0u && (r.old & (cbit << 1)) == 0u;
+  if (__any_sync(0xffffffffu, pending)) {
+    for (;;) {
+      const bool ok = !pending || (ld_acquire_u32(wp) & (cbit << 1)) != 0u;
+      if (__all_sync(0xffffffffu, ok)) break;
+    }
+  }
+}
+template <int LPR, int VEC, bool PAIRWISE>
+__device__ __forceinline__ void lazy_resolve(TaskRegs<VEC, PAIRWISE>& r0, TaskRegs<VEC, PAIRWISE>& r1, bool two,
+                                             const StepsArgs& a, int lane) {
+  bool any = lazy_fill<LPR, VEC, PAIRWISE>(r0, a, lane);
+  if (two) any = lazy_fill<LPR, VEC, PAIRWISE>(r1, a, lane) || any;
+  if (any) {
+    fence_acq_rel_gpu();   // every lane's zeros are in L2 ...
+    __syncwarp();          // ... and every lane is past its fence
+    lazy_publish(r0, a, lane % LPR);
+    if (two) lazy_publish(r1, a, lane % LPR);
+  }
+  lazy_wait_filled(r0, a, lane % LPR);
+  if (two) lazy_wait_filled(r1, a, lane % LPR);
 }
 
 // score, loss term and squared norms of the task (consumes the row loads); returns the task partial in every lane
@@ -579,7 +681,6 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
   unsigned char* ids_ring = smem_raw + L.ids_off();
   unsigned char* stage_ring = smem_raw + L.stage_off();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr bool lazy = LAZY;  // lazily zeroed destination tables (a.touch_u / a.touch_i): first touch stores, see the scatterers
   // hot rows: table + zeroed accumulators in shared memory (built by everybody before the roles split)
   constexpr bool hot_on = HOT && !LAZY;   // (a template parameter: the plain instantiation carries none of this)
   const HotRows hot(smem_raw + a.hot_off);
@@ -632,7 +733,7 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
     const int sub = lane % LPR, grp = lane / LPR;
     const int total = a.n_steps * tasks;
     using Regs = TaskRegs<VEC, PAIRWISE>;
-    auto issue = [&](Regs& r, int lt) { task_issue<LPR, VEC, PAIRWISE>(r, lt, a, L, B, ids_ring, tasks, cnt, lane); };
+    auto issue = [&](Regs& r, int lt) { task_issue<LPR, VEC, PAIRWISE, LAZY>(r, lt, a, L, B, ids_ring, tasks, cnt, lane); };
     auto score_and_stash = [&](Regs& r) {
       const float4 p = task_score<LPR, VEC, PAIRWISE>(r, a);
       const int st = r.s % n_stages;
@@ -662,6 +763,22 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
       }
     };
     Regs r0, r1;
+    if constexpr (LAZY) {
+      // lazily zeroed tables: windows of two tasks -- wait for both id tiles, gather + claim both, resolve the claims (zero
+      // fill of first-touch rows, fence, "filled" bits), then score and stash both (see lazy_resolve)
+      for (int lt = w; lt < total; lt += 2 * n_loaders) {
+        const int l1 = lt + n_loaders;
+        const bool two = l1 < total;
+        { const int s0 = lt / tasks; mbar_wait(&B.idsf[s0 % kRing], (uint32_t)((s0 / kRing) & 1)); }
+        if (two) { const int s1 = l1 / tasks; mbar_wait(&B.idsf[s1 % kRing], (uint32_t)((s1 / kRing) & 1)); }
+        issue(r0, lt);
+        if (two) issue(r1, l1);
+        lazy_resolve<LPR, VEC, PAIRWISE>(r0, r1, two, a, lane);
+        score_and_stash(r0);
+        if (two) score_and_stash(r1);
+      }
+      return;
+    }
     int lt = w;
     if (lt < total) issue(r0, lt);
     while (lt < total) {
@@ -677,20 +794,12 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
     }
   } else {
     // ------------------------------------------------ scatterers ------------------------------------------------------
-    // Lazily zeroed destination tables (a.touch_u != NULL), "store first": every row of a task is CLAIMED (atomicOr of bit 0
-    // of the row's pair in the touch map; requested before the norm wait, so the round trip hides behind the exchange).
-    //   won the claim          -> nobody has touched the row since the map was cleared: the gradient is STORED (whole lines, no
-    //                             DRAM read, whatever the row held is overwritten), and after the warp's per-step fence the
-    //                             row's "filled" bit (bit 1) is set;
-    //   lost, row filled       -> RED as usual (the line is in L2 or is fetched: an honest accumulate);
-    //   lost, not yet filled   -> deferred to the end of the step: wait for the bit, then RED.  The winner is a scatter warp
-    //                             that sets the bit after its own stores + fence without waiting for anybody (a warp sets
-    //                             its own bits BEFORE it turns to its deferred rows), so the wait is bounded.
+    // (Lazily zeroed destination tables need nothing here: the loaders have claimed the step's rows, zero-filled the first-touch
+    // ones and waited for those somebody else was filling before they stashed the task, so every row is ready for plain REDs.)
     const int x = warp - kServiceWarps - kLoaderWarps;
     const int sub = lane % LPR, grp = lane / LPR;
     const float inv_b = 1.0f / (float)a.batch;
     const float g = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f) * a.scale;
-    constexpr int kT = 4;  // tasks of a step whose claims a warp keeps in flight (statically indexed registers)
     for (int s = 0; s < a.n_steps; ++s) {
       const int slot = s % kRing, st = s % n_stages;
       const uint32_t par = (uint32_t)((s / kRing) & 1);
@@ -699,25 +808,9 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
       const float* lab = reinterpret_cast<const float*>(ids + (size_t)R * L.slice);
       const float* rows = reinterpret_cast<const float*>(stage_ring + (size_t)st * L.stage_slot_bytes());
       const float* sc = rows + (size_t)R * L.slice * row_f;
-      // lanes 0..R-1 of an interaction's group look after the touch-map word of its user / item+ / item- row
-      auto touch_word = [&](int q, unsigned int& cbit) -> unsigned int* {
-        cbit = 0u;
-        const int j = q * IPW + grp;
-        if (q >= tasks || j >= cnt || sub >= R) return nullptr;
-        const int64_t id = ids[(size_t)sub * L.slice + j];
-        if ((uint64_t)id >= (uint64_t)(sub == 0 ? a.n_users : a.n_items)) return nullptr;
-        cbit = 1u << (((unsigned int)id & 15u) * 2u);
-        return (sub == 0 ? a.touch_u : a.touch_i) + (id >> 4);
-      };
-      // one task: the rows of 32 / LPR interactions -> gradient rows -> destination, each row in its own mode (the modes of
-      // the group's three rows sit in lanes 0..2 of the group); only == kRowAdd/-1: restrict to rows whose mode was `only`
-      auto scatter_task = [&](int q, float2 nf, int my_mode) {
+      // one task: the rows of 32 / LPR interactions -> gradient rows -> destination
+      auto scatter_task = [&](int q, float2 nf) {
         int mu = kRowAdd, ma = kRowAdd, mb = kRowAdd;
-        if (lazy) {
-          mu = __shfl_sync(0xffffffffu, my_mode, grp * LPR);
-          ma = __shfl_sync(0xffffffffu, my_mode, grp * LPR + 1);
-          mb = PAIRWISE ? __shfl_sync(0xffffffffu, my_mode, grp * LPR + 2) : kRowSkip;
-        }
         const int j = q * IPW + grp;
         if (j >= cnt) return;
         const int64_t iu64 = ids[j], ia64 = ids[L.slice + j], ib64 = PAIRWISE ? ids[2 * L.slice + j] : 0;
@@ -743,72 +836,11 @@ __global__ void __launch_bounds__(kStagedBound, 1) train_steps_staged_kernel(Ste
           scatter_cols<PAIRWISE>(a, cidx, c, nf.x, nf.y, iu, ia, ib, ru, ra, rb, mu, ma, mb, hu, ha, hb);
         }
       };
-      unsigned int* wp[kT];
-      unsigned int cb[kT], old[kT];
-      if (lazy) {   // the claims of this warp's first kT tasks go out before the norm wait
-#pragma unroll
-        for (int t = 0; t < kT; ++t) {
-          wp[t] = touch_word(x + t * kScatterWarps, cb[t]);
-          old[t] = wp[t] ? atomicOr(wp[t], cb[t]) : 0u;
-        }
-      }
       if (!EARLY) mbar_wait(&B.normf[slot], par);  // => every CTA (this one included) has scored and stashed the step
       mbar_wait(&B.adone[slot], par);  // (long complete) acquire: the loaders' stage writes are visible to this warp
       if (a.trace && lane == 0 && x == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 5] = gtime();
       const float2 nf = EARLY ? make_float2(0.f, 0.f) : norms[slot];
-      if (!lazy) {
-        for (int q = x; q < tasks; q += kScatterWarps) scatter_task(q, nf, kRowAdd);
-      } else {
-        for (int q0 = x; q0 < tasks; q0 += kT * kScatterWarps) {   // (one round unless a warp owns more than kT tasks)
-          if (q0 != x) {
-#pragma unroll
-            for (int t = 0; t < kT; ++t) {
-              wp[t] = touch_word(q0 + t * kScatterWarps, cb[t]);
-              old[t] = wp[t] ? atomicOr(wp[t], cb[t]) : 0u;
-            }
-          }
-          // pass 1: store what we won, add to what is filled, remember the rest
-          bool won_any = false, deferred_any = false;
-          int mode[kT];
-#pragma unroll
-          for (int t = 0; t < kT; ++t) {
-            mode[t] = kRowSkip;
-            bool defer = false;
-            if (wp[t] != nullptr) {
-              if ((old[t] & cb[t]) == 0u) mode[t] = kRowStore;
-              else if ((old[t] & (cb[t] << 1)) != 0u) mode[t] = kRowAdd;
-              else defer = true;
-            }
-            won_any = won_any || mode[t] == kRowStore;
-            deferred_any = deferred_any || defer;
-            if (q0 + t * kScatterWarps < tasks) scatter_task(q0 + t * kScatterWarps, nf, mode[t]);
-            if (!defer) { if (mode[t] != kRowStore) wp[t] = nullptr; }   // keep the word of won rows (to publish) ...
-            else mode[t] = -1;                                            // ... and of deferred rows (to wait for)
-          }
-          // publish the rows stored above: every lane's stores are in L2 (fence), all lanes are past their fence (syncwarp)
-          if (__any_sync(0xffffffffu, won_any)) {
-            __threadfence();
-            __syncwarp();
-#pragma unroll
-            for (int t = 0; t < kT; ++t)
-              if (mode[t] == kRowStore) atomicOr(wp[t], cb[t] << 1);
-          }
-          // pass 2: rows somebody else is still storing -- wait for their "filled" bit, then add
-          if (__any_sync(0xffffffffu, deferred_any)) {
-#pragma unroll
-            for (int t = 0; t < kT; ++t) {
-              const bool mine = mode[t] == -1;
-              if (__any_sync(0xffffffffu, mine)) {
-                for (;;) {
-                  const bool ok = !mine || (ld_acquire_u32(wp[t]) & (cb[t] << 1)) != 0u;
-                  if (__all_sync(0xffffffffu, ok)) break;
-                }
-                scatter_task(q0 + t * kScatterWarps, nf, mine ? (int)kRowAdd : (int)kRowSkip);
-              }
-            }
-          }
-        }
-      }
+      for (int q = x; q < tasks; q += kScatterWarps) scatter_task(q, nf);
       __syncwarp();
       if (a.trace && lane == 0 && x == 0) a.trace[((size_t)s * gridDim.x + blockIdx.x) * 8 + 6] = gtime();
       if (EARLY) {

@@ -102,6 +102,8 @@ struct Fiber {
   char* stack = nullptr;
   bool done = false;
   unsigned tid = 0, cta = 0;
+  const char* site = "";        // debug: what the fiber last waited for (printed by the deadlock report)
+  const void* site_arg = nullptr;
   std::vector<std::pair<uint32_t*, uint32_t>> tmem_pending;   // tcgen05.ld results not yet released by tcgen05.wait::ld
 };
 
@@ -189,8 +191,12 @@ inline void mbar_expect_tx(const void* bar, uint32_t bytes) { MBar& m = cta().mb
 inline void mbar_complete_tx(const void* bar, uint32_t bytes) { MBar& m = cta().mbars[bar]; m.tx -= bytes; m.check(); }
 inline bool mbar_test(const void* bar, uint32_t parity) { return cta().mbars[bar].phase != (parity & 1u); }
 inline void mbar_wait(const void* bar, uint32_t parity) {
+  self().site = parity ? "mbar_wait(parity 1)" : "mbar_wait(parity 0)";
+  self().site_arg = bar;
   while (!mbar_test(bar, parity)) yield();
+  self().site = "";
 }
+inline void note_site(const char* what, const void* arg = nullptr) { self().site = what; self().site_arg = arg; }
 // cp.async.bulk (global -> shared, mbarrier completion): the copy engine is asynchronous too -- the bytes land, and the
 // barrier's transaction count drops, some scheduler slices after the issue (same queue discipline as the tensor core)
 inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, const void* bar) {
@@ -413,8 +419,14 @@ inline void run_ctas(const std::vector<std::pair<int, unsigned>>& which) {
   uint64_t rng = s.rng ? (s.rng * 0x9E3779B97F4A7C15ull + which[0].second + 1) : 0;
   uint64_t rounds = 0;
   while (remaining) {
-    if (++rounds > 200000000ull / (n ? n : 1) + 100000ull) {
+    static const uint64_t kRoundScale = std::getenv("XDR_EMU_PATIENCE") ? std::strtoull(std::getenv("XDR_EMU_PATIENCE"), nullptr, 10) : 1;
+    if (++rounds > kRoundScale * (200000000ull / (n ? n : 1) + 100000ull)) {
       std::fprintf(stderr, "cuda_emu: no fiber finished for too long -- deadlock in the emulated kernel?\n");
+      if (std::getenv("XDR_EMU_REPORT"))   // lane 0 of every unfinished warp: what it last waited for
+        for (const Fiber& f : s.fibers)
+          if (!f.done)
+            std::fprintf(stderr, "  cta %u warp %u: %s %+ld\n", f.cta, f.tid >> 5, f.site,
+                         f.site_arg ? (long)((const char*)f.site_arg - (const char*)s.ctas[f.cta].dyn_smem.data()) : 0l);
       std::abort();
     }
     if (rng) {  // seeded Fisher-Yates reshuffle of the resume order each round

@@ -70,7 +70,7 @@ def parse_args():
                          'every launch produces the gradient of its K batches, first touch of a row stores (touch map)')
     ap.add_argument('--coop', type=int, default=1, help='1: cudaLaunchCooperativeKernel, 0: plain launch')
     ap.add_argument('--dense-engine', type=int, default=0, help='model-step workloads: 1 tcgen05 dense layers, 0 fp32 FMA')
-    ap.add_argument('--map-engine', default='', help="emcdr_map: 'tc5' (tcgen05), 'tc' (mma.sync), 'fma', '' (composed kernels)")
+    ap.add_argument('--map-engine', default='', help="emcdr_map: '' (the model's default: tcgen05), 'tc5', 'tc' (mma.sync), 'fma', 'composed'")
     ap.add_argument('--shard-chunk', type=int, default=50, help='N>1: steps per persistent launch')
     ap.add_argument('--chunk', type=int, default=0, help='steps per launch on the end-to-end (host-fed) path (0: K/2, 50 from K = 100)')
     return ap.parse_args()
@@ -802,7 +802,8 @@ def run_model_step(args, dev, name):
     _ops.set_table_grad_mode('inplace')   # table gradients are scatter-added into persistent .grad buffers (no dense [N, D] temporaries)
     ds, cfg, make, units, phase = _model_workload(name, b, dev)
     if name == 'emcdr_map':
-        cfg['xdr_fused_mlp'] = args.map_engine or False
+        if args.map_engine:   # default: the model's own choice ('auto': the tcgen05 map-step kernel where it applies)
+            cfg['xdr_fused_mlp'] = False if args.map_engine == 'composed' else args.map_engine
     torch.manual_seed(2022)
     with torch.device(dev):
         model = cls(cfg, ds)
@@ -860,13 +861,14 @@ def run_model_step(args, dev, name):
     amed = statistics.median(api)
     achieved = bytes_per * units * K / (med * 1e-3) / 1e9
     engine = ('tcgen05 dense engine (tc5_dense.cu)' if args.dense_engine else 'fp32 FMA dense kernels')
-    if name == 'emcdr_map' and args.map_engine:
+    if name == 'emcdr_map':
         engine = {'tc5': 'tc5_mlp_kernel (one fused tcgen05 kernel per pass)', 'tc': 'tc_mlp_kernel (mma.sync)',
-                  'fma': 'fused_mlp_kernel (fp32)'}.get(args.map_engine, args.map_engine)
+                  'fma': 'fused_mlp_kernel (fp32)', 'composed': 'composed fp32 FMA kernels'}.get(args.map_engine or 'tc5', args.map_engine)
     line = {
         'metric': 'interactions/sec (gather+map+score+scatter)', 'value': units * K / (med * 1e-3), 'unit': 'interactions/s',
         'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': med / K, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32 (dense products: bf16x3 on tcgen05, fp32 accumulate)' if args.dense_engine else 'f32',
+        'vs_baseline': None,
+        'dtype': 'f32 (dense products: bf16x3 on tcgen05, fp32 accumulate)' if (args.dense_engine or (name == 'emcdr_map' and args.map_engine in ('', 'tc5'))) else 'f32',
         'data': 'synthetic',
         'config': {'workload': what % b, 'engine': engine, 'users_total': ds.num_total_user, 'items_total': ds.num_total_item,
                    'batch_per_gpu': b, 'l2': 'inputs larger than L2 (tables of 0.8 .. 7 GB, uniform random rows)',

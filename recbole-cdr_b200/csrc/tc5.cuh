@@ -286,10 +286,20 @@ __device__ __forceinline__ uint32_t bf16_rn(float x) {   // round-to-nearest-eve
   u += 0x7fffu + ((u >> 16) & 1u);
   return u >> 16;
 }
+#ifndef XDR_EMU
+// two fp32 -> one packed bf16x2 word (x0 in the low half), round-to-nearest-even: ONE conversion instruction (F2FP.BF16) where
+// the integer form above costs ~6 per element -- the split was a third of the tcgen05 kernels' epilogue instructions
+__device__ __forceinline__ uint32_t bf16x2_rn(float x0, float x1) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  return r;
+}
+#else
+__device__ __forceinline__ uint32_t bf16x2_rn(float x0, float x1) { return bf16_rn(x0) | (bf16_rn(x1) << 16); }
+#endif
 __device__ __forceinline__ void split_bf16_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {   // element 0 in the low half
-  const uint32_t h0 = bf16_rn(x0), h1 = bf16_rn(x1);
-  hi = h0 | (h1 << 16);
-  lo = bf16_rn(x0 - __uint_as_float(h0 << 16)) | (bf16_rn(x1 - __uint_as_float(h1 << 16)) << 16);
+  hi = bf16x2_rn(x0, x1);
+  lo = bf16x2_rn(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
 }
 // eight values that are consecutive along the operand's contiguous direction -> one 16-byte chunk in the hi plane and one in
 // the lo plane.  K-major: (row r, K elements 8*k8 ..);  MN-major: (rows 8*r8 .., reduction index k) -- pass the matching offset.
@@ -323,12 +333,10 @@ __device__ __forceinline__ void mma_bf16x3(uint32_t tmem_d, uint32_t a_hi, uint3
 // layers whose outputs go through a ReLU: with bf16x3 (~2^-16 per product) a pre-activation within 1e-5 of zero gets another
 // sub-gradient than the fp32 reference, which showed up as whole rows of differing gradients (round 2, GPU call 12).
 __device__ __forceinline__ void split_bf16_pair3(float x0, float x1, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
-  const uint32_t h0 = bf16_rn(x0), h1 = bf16_rn(x1);
-  const float r0 = x0 - __uint_as_float(h0 << 16), r1 = x1 - __uint_as_float(h1 << 16);
-  const uint32_t m0 = bf16_rn(r0), m1 = bf16_rn(r1);
-  hi = h0 | (h1 << 16);
-  mid = m0 | (m1 << 16);
-  lo = bf16_rn(r0 - __uint_as_float(m0 << 16)) | (bf16_rn(r1 - __uint_as_float(m1 << 16)) << 16);
+  hi = bf16x2_rn(x0, x1);
+  const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+  mid = bf16x2_rn(r0, r1);
+  lo = bf16x2_rn(r0 - __uint_as_float(mid << 16), r1 - __uint_as_float(mid & 0xffff0000u));
 }
 __device__ __forceinline__ void store_split8_3(unsigned char* hi_plane, unsigned char* mid_plane, unsigned char* lo_plane,
                                                int chunk_off, float4 v0, float4 v1) {

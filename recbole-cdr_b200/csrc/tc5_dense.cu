@@ -19,6 +19,7 @@
 // tc5_mlp.cu).  Shapes this engine takes: M >= 128, N % 16 == 0, 16 <= N <= 128, K % 16 == 0, 16 <= K <= 256, 16-byte
 // aligned contiguous operands; everything else stays on the fp32 FMA kernels of dense.cu.
 #include "tc5.cuh"
+#include <stdlib.h>
 #include "tc5_dense.cuh"
 
 namespace xdr {
@@ -364,7 +365,11 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_bwd_weight_kernel(const 
 // (scripts/bench_dense_engines.py, profiles/r2_dense_engines.jsonl): per call the two engines tie at the model shapes of
 // BASELINE.json (6 .. 50 us, both bound by the dependent chain stage -> product -> epilogue of ONE 128-row tile per SM, not by
 // the tensor pipe), so the validated tcgen05 engine is opt-in until it is pipelined across tiles.
-static int g_dense_engine = 0;
+static int env_dense_engine() {   // XDR_DENSE_ENGINE=1 in the environment switches the engine on without a call (test sweeps)
+  const char* e = getenv("XDR_DENSE_ENGINE");
+  return (e && e[0] == '1') ? 1 : 0;
+}
+static int g_dense_engine = env_dense_engine();
 
 static bool d5_shape_ok(int64_t M, int N, int K) {
   return M >= kD5Rows && N % 16 == 0 && N >= 16 && N <= 128 && K % 16 == 0 && K >= 16 && K <= 256 && (kD5Threads % (N / 8)) == 0;

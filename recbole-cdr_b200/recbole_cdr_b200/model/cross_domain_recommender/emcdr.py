@@ -42,8 +42,14 @@ class EMCDR(CrossDomainRecommender):
         else:
             self.input_type = InputType.PAIRWISE
         self.bpr_gamma = 1e-10  # recbole BPRLoss default
-        # False: composed kernels; True / 'fma': fp32 row-tile kernel; 'tc': tensor-core row-tile kernel
-        self.fused_mlp_engine = ops.fused_mlp_engine(config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else False)
+        # Engine of the map step (config key ``xdr_fused_mlp``).  Absent / 'auto' (default): the tcgen05 kernel (tc5_mlp.cu:
+        # gather -> both layers -> MSE -> whole backward -> scatter in one launch, bf16x3 products on the tensor cores) for
+        # the stacks it takes -- [D, 128, D], D a multiple of 16 up to 64, i.e. the yaml default -- and the composed fp32
+        # kernels for everything else (measured on a B200 at b = 8192: 57 us against 98 us per step, profiles/r2_rows.md).
+        # False: always composed; True / 'fma': fp32 row-tile kernel; 'tc': mma.sync row-tile kernel; 'tc5': tcgen05 or error.
+        flag = config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else 'auto'
+        self.fused_mlp_auto = flag == 'auto'
+        self.fused_mlp_engine = 'tc5' if self.fused_mlp_auto else ops.fused_mlp_engine(flag)
         self.use_fused_mlp = self.fused_mlp_engine is not None
         self.source_latent_dim = config['source_embedding_size']
         self.target_latent_dim = config['target_embedding_size']

@@ -150,6 +150,47 @@ class CrossDomainTrainer(object):
         self.train_loss_dict = dict()
         self.best_valid_score, self.best_valid_result = -np.inf, None
         self.epochs = 0
+        # per-phase validation / early stopping / checkpoint of recbole's Trainer.fit [recbole-1.0.1], which the reference runs
+        # once per phase (trainer.py:59-73).  The evaluator itself (metrics over full_sort_predict) is outside this package's
+        # scope: ``valid_fn(model, valid_data) -> (score, result)`` is supplied by the caller
+        # (``set_valid_fn``); without one, passing ``valid_data`` warns instead of being silently dropped.
+        self.eval_step = int(config['eval_step']) if 'eval_step' in config else 1
+        self.stopping_step = int(config['stopping_step']) if 'stopping_step' in config else 10
+        self.checkpoint_dir = config['checkpoint_dir'] if 'checkpoint_dir' in config else None
+        self.saved_model_file = None
+        self.valid_fn = None
+        self.cur_step = 0
+        self.start_epoch = 0
+
+    def set_valid_fn(self, valid_fn):
+        """``valid_fn(model, valid_data) -> (score: float, result)``: the evaluation used by ``fit`` every ``eval_step`` epochs."""
+        self.valid_fn = valid_fn
+
+    # ---- checkpoints in the reference's format (recbole Trainer._save_checkpoint / resume_checkpoint) ----------------
+    def _save_checkpoint(self, epoch):
+        if not self.checkpoint_dir:
+            return None
+        import os
+        os.makedirs(self.checkpoint_dir, exist_ok=True)
+        if self.saved_model_file is None:
+            self.saved_model_file = os.path.join(self.checkpoint_dir, f'{type(self.model).__name__}-xdr.pth')
+        other = self.model.other_parameter() if hasattr(self.model, 'other_parameter') else None
+        state = {'config': dict(self.config) if hasattr(self.config, 'keys') else None, 'epoch': epoch, 'cur_step': self.cur_step,
+                 'best_valid_score': self.best_valid_score, 'state_dict': self.model.state_dict(), 'other_parameter': other,
+                 'optimizer': self.optimizer.state_dict() if self.optimizer is not None else None}
+        torch.save(state, self.saved_model_file)
+        return self.saved_model_file
+
+    def resume_checkpoint(self, resume_file):
+        ckpt = torch.load(resume_file, map_location=self.device, weights_only=False)
+        self.start_epoch = ckpt['epoch'] + 1
+        self.cur_step = ckpt['cur_step']
+        self.best_valid_score = ckpt['best_valid_score']
+        self.model.load_state_dict(ckpt['state_dict'])
+        if ckpt.get('other_parameter') is not None and hasattr(self.model, 'load_other_parameter'):
+            self.model.load_other_parameter(ckpt['other_parameter'])
+        if self.optimizer is not None and ckpt.get('optimizer') is not None:
+            self.optimizer.load_state_dict(ckpt['optimizer'])
 
     def _build_optimizer(self):
         """recbole Trainer._build_optimizer [recbole-1.0.1]: dense torch optimizers keyed by ``learner``."""
@@ -378,7 +419,13 @@ class CrossDomainTrainer(object):
 
     # ---- phase loop ------------------------------------------------------------------------------------------
     def _fit_phase(self, train_data, valid_data, verbose, saved, show_progress, callback_fn):
+        """One phase of recbole's Trainer.fit: train; every ``eval_step`` epochs validate, keep the best score, save the
+        checkpoint on improvement, stop after ``stopping_step`` validations without one."""
         spec = self._fused_spec()
+        if valid_data is not None and self.valid_fn is None:
+            import warnings
+            warnings.warn('CrossDomainTrainer.fit: valid_data was given but no evaluation function is set (set_valid_fn); this '
+                          'phase trains all its epochs without validation, early stopping or best-model selection', stacklevel=3)
         for epoch_idx in range(self.start_epoch, self.epochs):
             if spec is not None:
                 loss = self._train_epoch_fused(train_data, epoch_idx, spec)
@@ -387,6 +434,23 @@ class CrossDomainTrainer(object):
             self.train_loss_dict[epoch_idx] = loss
             if callback_fn:
                 callback_fn(epoch_idx, loss)
+            if valid_data is None or self.valid_fn is None or self.eval_step <= 0:
+                if saved and (epoch_idx + 1 == self.epochs):
+                    self._save_checkpoint(epoch_idx)
+                continue
+            if (epoch_idx + 1) % self.eval_step == 0:
+                self.model.eval()
+                with torch.no_grad():
+                    score, result = self.valid_fn(self.model, valid_data)
+                better = score > self.best_valid_score if self.valid_metric_bigger else score < self.best_valid_score
+                if better:
+                    self.best_valid_score, self.best_valid_result, self.cur_step = score, result, 0
+                    if saved:
+                        self._save_checkpoint(epoch_idx)
+                else:
+                    self.cur_step += 1
+                    if self.cur_step > self.stopping_step:
+                        break
         return self.best_valid_score, self.best_valid_result
 
     def fit(self, train_data, valid_data=None, verbose=True, saved=True, show_progress=False, callback_fn=None):

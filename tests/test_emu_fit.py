@@ -78,3 +78,37 @@ def test_fit_runs_every_phase(name, pairwise, overlap, cfg, modes, epochs, falli
         assert l[-1] < l[0], (name, modes[k], l)
     if name in ('EMCDR', 'SSCDR', 'DCDCSR'):
         assert model.phase == 'OVERLAP'       # trainer.py:75 / :129
+
+
+def test_fit_validates_stops_early_and_checkpoints(tmp_path):
+    """recbole's per-phase Trainer.fit contract around the reference's phase loop (trainer.py:59-73): every eval_step epochs the
+    evaluation function is called, the best score is kept and checkpointed (reference checkpoint keys), and the phase stops after
+    stopping_step validations without improvement; valid_data without an evaluation function warns instead of vanishing."""
+    from recbole_cdr_b200.utils import ModelType, get_model, get_trainer
+    np.random.seed(0)
+    with emu_util.patched_ops(sms=2):
+        ds, loader = make_world(False, 'both')
+        full = base_config(device='cpu', learner='adam', learning_rate=0.01, weight_decay=0.0, train_modes=['BOTH'],
+                           epoch_num=['8'], source_split=False, embedding_size=64, alpha=0.5, gamma=0.0, eval_step=1,
+                           stopping_step=2, checkpoint_dir=str(tmp_path), **{'lambda': 0.0})
+        torch.manual_seed(2022)
+        model = get_model('CMF')(full, ds)
+        trainer = get_trainer(ModelType.CROSSDOMAIN, 'CMF')(full, model)
+        with pytest.warns(UserWarning, match='no evaluation function'):
+            trainer.fit(loader, valid_data='held-out', saved=False)
+        scores = iter([0.1, 0.3, 0.2, 0.25, 0.28, 0.9, 0.9, 0.9])     # best at the 2nd validation, then three without improvement
+        calls = []
+
+        def valid_fn(m, vd):
+            assert vd == 'held-out' and not m.training
+            calls.append(next(scores))
+            return calls[-1], {'recall@10': calls[-1]}
+        trainer.set_valid_fn(valid_fn)
+        epochs = []
+        best, result = trainer.fit(loader, valid_data='held-out', saved=True, callback_fn=lambda e, l: epochs.append(e))
+    assert calls == [0.1, 0.3, 0.2, 0.25, 0.28] and epochs == [0, 1, 2, 3, 4]          # stopped after 3 > stopping_step misses
+    assert best == 0.3 and result == {'recall@10': 0.3}
+    ckpt = torch.load(trainer.saved_model_file, weights_only=False)
+    assert set(ckpt) >= {'config', 'epoch', 'cur_step', 'best_valid_score', 'state_dict', 'other_parameter', 'optimizer'}
+    assert ckpt['epoch'] == 1 and ckpt['best_valid_score'] == 0.3
+    assert set(ckpt['state_dict']) == set(model.state_dict())

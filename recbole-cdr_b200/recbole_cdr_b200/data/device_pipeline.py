@@ -28,7 +28,8 @@ class DeviceDomainData(object):
         pairwise: rows = (user, item, neg_item), B = batch_size positives per step.
         pointwise: rows = (user, item), B = batch_size with batch_size // 2 positives followed by their negatives.
         The ragged tail that does not fill a whole step is dropped when ``drop_last`` (the persistent kernel wants equal
-        steps); otherwise it is returned as a final block of one shorter step."""
+        steps); otherwise it is returned as a final block of one shorter step, rounded down to a multiple of 4 interactions
+        (the kernel's id tiles are 16-byte granular: at most 3 interactions of an epoch are left out)."""
         n = self.users.numel()
         perm = torch.randperm(n, device=self.device, generator=generator) if shuffle else torch.arange(n, device=self.device)
         pos = batch_size if pairwise else max(batch_size // 2, 1)
@@ -37,9 +38,10 @@ class DeviceDomainData(object):
             k = min(steps_per_block, n_steps - s0)
             sel = perm[s0 * pos:(s0 + k) * pos]
             yield self._block(sel, k, pos, pairwise)
-        if not drop_last and n_steps * pos < n:
-            sel = perm[n_steps * pos:]
-            yield self._block(sel, 1, sel.numel(), pairwise)
+        tail = (n - n_steps * pos) // 4 * 4
+        if not drop_last and tail > 0:
+            sel = perm[n_steps * pos:n_steps * pos + tail]
+            yield self._block(sel, 1, tail, pairwise)
 
     def _block(self, sel, k, pos, pairwise):
         u = self.users[sel]

@@ -76,7 +76,15 @@ def _maybe_check(device):
 
 
 def _oob(device):
-    return ptr(_lib.oob_flag(device)) if CHECK_IDS else None
+    """The device-side out-of-range flag is ALWAYS armed (a kernel that meets a bad id sets it; that costs nothing otherwise);
+    ``CHECK_IDS`` only decides whether every op also reads it back (a sync per op).  ``check_ids_now`` reads it on demand --
+    the trainer does so once per epoch, where it reads the loss anyway."""
+    return ptr(_lib.oob_flag(device))
+
+
+def check_ids_now(device):
+    """Raise IndexError (as nn.Embedding would have, at the op) if any kernel since the last check met an out-of-range id."""
+    _lib.check_ids(torch.device(device))
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -70,13 +70,20 @@ class _DeviceUniformSampler(object):
              self.n_users, self.n_overlap, self.n_gap, self.n_valid, self.seed, self._calls & 0xFFFFFFFF, 1000, ptr(out),
              ptr(self._status), cur_stream())
         if check:
-            st = int(self._status.item())
-            if st:
-                self._status.zero_()
-                if st & 2:
-                    raise ValueError('user_id not exist.')
-                raise ValueError('negative sampling exhausted its attempts for some user')
+            self.check_status()
         return out
+
+    def check_status(self):
+        """Read (one device->host sync) and clear the status word the draws since the last check have OR-ed into: raises as
+        the reference does for an unknown user id, and when a draw exhausted its attempts (its slot then holds an item the
+        user HAS interacted with).  ``sample_by_key_ids(check=False)`` callers -- the device-resident epoch loops -- call it
+        once per epoch."""
+        st = int(self._status.item())
+        if st:
+            self._status.zero_()
+            if st & 2:
+                raise ValueError('user_id not exist.')
+            raise ValueError('negative sampling exhausted its attempts for some user')
 
 
 class CrossDomainSourceSampler(_DeviceUniformSampler):
@@ -104,7 +111,10 @@ class CrossDomainSourceSampler(_DeviceUniformSampler):
 class TargetDomainSampler(_DeviceUniformSampler):
     """recbole.sampler.Sampler for the target domain [recbole-1.0.1]: uniform over [1, item_num)."""
 
-    def __init__(self, n_users, item_num, user_ids, item_ids, device='cuda', seed=2022, distribution='uniform'):
+    def __init__(self, n_users, item_num, user_ids, item_ids, device='cuda', seed=None, distribution='uniform'):
+        # default key differs from the source sampler's: with one key and equal call counters the two domains of a BOTH-mode
+        # step would draw from the same Philox stream position by position (ADVICE r1)
+        seed = (2022 ^ 0x5bd1e995) if seed is None else seed
         super().__init__(n_users, item_num, 0, item_num - 1, user_ids, item_ids, device, seed, distribution)
 
     def sample_by_user_ids(self, user_ids, item_ids, num):

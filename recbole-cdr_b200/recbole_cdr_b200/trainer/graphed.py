@@ -29,11 +29,23 @@ class GraphedTrainStep(object):
         self._prev_mode = ops.get_table_grad_mode()
         ops.set_table_grad_mode('inplace')
         self._table_grads = {}
+        # The warm-up steps below are REAL steps on the example batch (they allocate what the capture needs: cuBLAS-free here,
+        # but the graph pool, the small parameters' .grad tensors and the optimizer's state).  Everything they change is put
+        # back afterwards -- in place, so that the captured graph keeps pointing at the same memory: table gradients (zeroed
+        # if created here, restored if the caller had some), and, when an optimizer steps inside the graph, the parameters
+        # and the optimizer state (a fresh optimizer ends up with allocated, zeroed state: what its first real step expects).
+        saved_grads, saved_params, saved_state = {}, {}, None
         for p in model.parameters():
             if p.numel() >= _TABLE_NUMEL:
                 if p.grad is None:
                     p.grad = torch.zeros_like(p)
+                else:
+                    saved_grads[p] = p.grad.clone()
                 self._table_grads[p] = p.grad   # the captured kernels scatter-add into exactly this memory
+        if optimizer is not None:
+            saved_params = {p: p.detach().clone() for p in model.parameters()}
+            saved_state = {p: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                           for p, st in optimizer.state.items()}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -42,6 +54,23 @@ class GraphedTrainStep(object):
                 self._step()
             torch.cuda.synchronize()
             self._zero_small()
+            with torch.no_grad():
+                for p, gbuf in self._table_grads.items():
+                    if p in saved_grads:
+                        gbuf.copy_(saved_grads[p])
+                    else:
+                        gbuf.zero_()
+                for p, v in saved_params.items():
+                    p.copy_(v)
+                if optimizer is not None:
+                    for p, st in optimizer.state.items():
+                        before = saved_state.get(p, {})
+                        for k, v in st.items():
+                            if torch.is_tensor(v):
+                                v.copy_(before[k]) if k in before else v.zero_()
+                            elif k in before:
+                                st[k] = before[k]
+            del saved_grads, saved_params, saved_state
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, stream=side):
                 self.loss = self._step()

@@ -217,8 +217,12 @@ class CrossDomainTrainer(object):
 
     @staticmethod
     def _check_nan(loss):
+        """End-of-epoch checks at the one place the epoch reads from the device anyway: the loss is a number, and no kernel of
+        the epoch met an out-of-range id (the reference's nn.Embedding would have raised at the op)."""
         if torch.isnan(loss).any():
             raise ValueError('Training loss is nan')
+        if loss.is_cuda:
+            ops.check_ids_now(loss.device)
 
     # ---- inner loops -----------------------------------------------------------------------------------------
     def _train_epoch(self, train_data, epoch_idx, loss_func=None, show_progress=False):
@@ -337,8 +341,9 @@ class CrossDomainTrainer(object):
         total = torch.zeros((), dtype=torch.float32, device=spec['user_tab'].device)
         if self.row_optimizer is not None:
             return self._train_epoch_device_row_sparse(domain_data, batch_size, spec, K, generator, total)
+        self._require_plain_sgd('train_epoch_device')
         scale = -float(self.learning_rate) * float(spec.get('loss_weight', 1.0))
-        for ids, label in domain_data.epoch_blocks(batch_size, K, pairwise=spec['pairwise'], generator=generator):
+        for ids, label in domain_data.epoch_blocks(batch_size, K, pairwise=spec['pairwise'], generator=generator, drop_last=False):
             out8, _, _ = ops.train_steps(spec['user_tab'].data, spec['item_tab'].data, ids[:, 0], ids[:, 1],
                                          ids[:, 2] if spec['pairwise'] else None, label,
                                          loss_kind=spec.get('loss_kind', _lib.LOSS_MSE), reg_weight=spec['reg_weight'],
@@ -346,7 +351,15 @@ class CrossDomainTrainer(object):
                                          item_dst=spec['item_tab'].data, scale=scale)
             total = total + out8[:, 0].sum()
         self._check_nan(total)
+        domain_data.sampler.check_status()
         return float(total.item())
+
+    def _require_plain_sgd(self, what):
+        """The fused launches apply ``-lr * grad`` inside the scatter: that IS plain SGD and nothing else (the
+        trainer's default learner is adam)."""
+        if self.learner != 'sgd' or self.weight_decay:
+            raise ValueError(f"{what} applies a fused plain-SGD update; it needs learner='sgd' and weight_decay=0 "
+                             f"(got learner={self.learner!r}, weight_decay={self.weight_decay!r}), or an xdr_row_optimizer")
 
     def train_epoch_device_both(self, source_data, target_data, batch_size, specs=None, steps_per_launch=None,
                                 generator=None):
@@ -360,6 +373,7 @@ class CrossDomainTrainer(object):
         K = steps_per_launch or max(self.fused_steps, 1)
         dev = specs[0]['user_tab'].device
         total = torch.zeros((), dtype=torch.float32, device=dev)
+        self._require_plain_sgd('train_epoch_device_both')
 
         def source_blocks():
             while True:  # the source loader silently restarts (dataloader.py:156-159)
@@ -393,6 +407,8 @@ class CrossDomainTrainer(object):
                 need -= take
             total = total + run(specs[1], t_ids, t_lab)
         self._check_nan(total)
+        source_data.sampler.check_status()
+        target_data.sampler.check_status()
         return float(total.item())
 
     def _train_epoch_device_row_sparse(self, domain_data, batch_size, spec, K, generator, total):
@@ -415,6 +431,7 @@ class CrossDomainTrainer(object):
                 self.row_optimizer.step([(ut, ids[k, 0]), (it, ids[k, 1:])])
                 total = total + out8[0, 0]
         self._check_nan(total)
+        domain_data.sampler.check_status()
         return float(total.item())
 
     # ---- phase loop ------------------------------------------------------------------------------------------

@@ -129,6 +129,44 @@ def test_graphed_step_equals_eager_step():
             torch.testing.assert_close(p.grad, ge[n].grad, rtol=1e-4, atol=1e-7, msg=lambda s: f'{n}: {s}')
 
 
+def test_graphed_step_construction_leaves_model_and_optimizer_untouched():
+    """The warm-up steps of GraphedTrainStep are real steps on the example batch; whatever they changed -- parameters, table
+    gradients, optimizer state -- is put back, so the first replay is the first step of training."""
+    from recbole_cdr_b200.data import Interaction
+    from recbole_cdr_b200.trainer import GraphedTrainStep
+    from recbole_cdr_b200.utils import get_model
+    from fake_data import make_batch
+    ds = FakeDataset(201, 300, 280, 101, 500, 450)
+    cfg = base_config(embedding_size=64, mlp_hidden_size=[32, 16], dropout_prob=0.0, base_model='NeuMF', alpha=0.4)
+    torch.manual_seed(1)
+    model = get_model('DTCDR')(cfg, ds).to('cuda')
+    import copy
+    twin = copy.deepcopy(model)
+    r = np.random.RandomState(3)
+    b = make_batch(ds, 'source', 512, r)
+    b.update(make_batch(ds, 'target', 512, r))
+    b = Interaction(b).to('cuda')
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2, momentum=0.9)   # (graph-safe: its state is one tensor per parameter)
+    step = GraphedTrainStep(model, b, optimizer=opt, warmup=3)
+    for (n, p), (_, q) in zip(model.named_parameters(), twin.named_parameters()):
+        assert torch.equal(p, q), n                                # the warm-up's optimizer steps were undone
+    for st in opt.state.values():
+        for k, v in st.items():
+            if torch.is_tensor(v):
+                assert float(v.abs().max()) == 0.0, k              # allocated (the graph points at it) and zeroed
+    for p, g in step._table_grads.items():
+        assert float(g.abs().max()) == 0.0
+    # and the first replay equals the first eager step of the untouched twin
+    opt2 = torch.optim.SGD(twin.parameters(), lr=1e-2, momentum=0.9)
+    loss_g = step(b).clone()
+    loss_e = twin.calculate_loss(b)
+    loss_e.sum().backward()
+    opt2.step()
+    torch.testing.assert_close(loss_g, loss_e.detach().sum(), rtol=1e-6, atol=0)
+    for (n, p), (_, q) in zip(model.named_parameters(), twin.named_parameters()):
+        torch.testing.assert_close(p, q, rtol=1e-4, atol=1e-6, msg=lambda s: f'{n}: {s}')
+
+
 def test_cmf_fused_both_epoch_tracks_per_batch_sgd():
     """CMF (the reference's default model): two weighted domain terms on shared tables through the persistent path."""
     from recbole_cdr_b200.utils import get_model, get_trainer, ModelType

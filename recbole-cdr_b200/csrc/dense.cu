@@ -10,6 +10,7 @@
 // micro-tile per thread, K staged through shared memory in slabs of 16.  fp32 FMA keeps the loss within the
 // 1e-4 contract without any split-precision trick; the tcgen05 engine (tc5_dense.cu) takes over for the shapes it
 // takes (M >= 128, N and K multiples of 16): xdr_set_dense_engine(0) keeps everything here.
+#include <stdlib.h>
 #include "xdr_common.cuh"
 #include "tc5_dense.cuh"
 
@@ -17,6 +18,8 @@ namespace xdr {
 
 constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
 constexpr int kDenseThreads = 256;
+static int env_flag_fwd2() { const char* e = getenv("XDR_DENSE_FWD2"); return e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1; }
+static int g_dense_fwd2 = env_flag_fwd2();   // XDR_DENSE_FWD2=0 in the environment keeps the 64 x 64 single-buffered forward tiles
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -129,6 +132,122 @@ __global__ void __launch_bounds__(kDenseThreads)
       float v = acc[i][j] + (bias ? bias[n] : 0.f);
       if (X2 != nullptr) v += mk * acc2[i][j];
       Y[m * N + n] = apply_act(v, act);
+    }
+  }
+}
+
+// ---- forward, register-blocked and double-buffered (round 2): the same product as dense_fwd_kernel for 16-byte aligned
+// operands with K % 4 == 0.  128 x BN output tile per CTA, 256 threads; thread (ty, tx) owns RM = 128 / (1024 / BN) rows x 4
+// columns (8 x 4 at BN = 64: 32 FMAs per 3 shared-memory loads), the next K slab is prefetched into registers while the
+// current one is multiplied, shared memory is double-buffered (one barrier per slab), the slabs are written transposed
+// without bank conflicts (a warp covers 32 consecutive rows of one 4-column group).  The cross-stitch term continues the
+// same accumulators: masked-out rows of X2 are staged as zeros.  Used for narrow layers (N <= 32), where it is 1.3-1.4x the
+// 64 x 64 tiles; for N >= 64 the grid of 128-row tiles is too small to fill the SMs (see xdr_dense_fwd).
+constexpr int BM2 = 128;
+template <int BN2>
+__global__ void __launch_bounds__(kDenseThreads)
+    dense_fwd2_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
+                      const float* __restrict__ X2, const float* __restrict__ W2, const int64_t* __restrict__ mask_ids,
+                      int64_t mask_lt, int act, float* __restrict__ Y, int64_t M, int N, int K) {
+  constexpr int TX = BN2 / 4, TY = kDenseThreads / TX, RM = BM2 / TY;   // 16 x 16 threads, 8 rows each at BN2 = 64
+  constexpr int LDA = BM2 + 4, LDB = BN2 + 4;
+  constexpr int A_LOADS = BM2 * BK / 4 / kDenseThreads;                  // float4 loads per thread and slab: 2
+  constexpr int B_ROWS_PER_PASS = kDenseThreads / (BK / 4);              // 64 rows of W per pass of all threads
+  constexpr int B_LOADS = (BN2 + B_ROWS_PER_PASS - 1) / B_ROWS_PER_PASS; // 1
+  __shared__ __align__(16) float As[2][BK][LDA];
+  __shared__ __align__(16) float Bs[2][BK][LDB];
+  const int tid = threadIdx.x, ty = tid / TX, tx = tid % TX;
+  const int64_t m0 = (int64_t)blockIdx.x * BM2;
+  const int n0 = blockIdx.y * BN2;
+  // staging roles: the 64 threads tid % 64 of a pass cover 64 consecutive rows; tid / 64 picks the 4-column group of the slab
+  const int lr = tid & 63, kq = (tid >> 6) * 4;
+  const int slabs1 = (K + BK - 1) / BK, slabs = X2 != nullptr ? 2 * slabs1 : slabs1;
+  float acc[RM][4] = {};
+  float4 pa[A_LOADS], pb[B_LOADS];
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fetch = [&](int sl) {   // slab sl of [X | X2] and [W | W2] -> registers
+    const bool second = sl >= slabs1;
+    const float* __restrict__ P = second ? X2 : X;
+    const float* __restrict__ Q = second ? W2 : W;
+    const int k = (second ? sl - slabs1 : sl) * BK + kq;
+#pragma unroll
+    for (int i = 0; i < A_LOADS; ++i) {
+      const int64_t m = m0 + lr + 64 * i;
+      bool on = m < M && k < K;
+      if (on && second && mask_ids != nullptr) on = mask_ids[m] < mask_lt;
+      pa[i] = on ? __ldg(reinterpret_cast<const float4*>(P + m * K + k)) : z4;
+    }
+#pragma unroll
+    for (int i = 0; i < B_LOADS; ++i) {
+      const int n = n0 + lr + 64 * i;
+      pb[i] = (lr + 64 * i < BN2 && n < N && k < K) ? __ldg(reinterpret_cast<const float4*>(Q + (int64_t)n * K + k)) : z4;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_LOADS; ++i) {
+      As[buf][kq + 0][lr + 64 * i] = pa[i].x;
+      As[buf][kq + 1][lr + 64 * i] = pa[i].y;
+      As[buf][kq + 2][lr + 64 * i] = pa[i].z;
+      As[buf][kq + 3][lr + 64 * i] = pa[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < B_LOADS; ++i) {
+      if (lr + 64 * i < BN2) {
+        Bs[buf][kq + 0][lr + 64 * i] = pb[i].x;
+        Bs[buf][kq + 1][lr + 64 * i] = pb[i].y;
+        Bs[buf][kq + 2][lr + 64 * i] = pb[i].z;
+        Bs[buf][kq + 3][lr + 64 * i] = pb[i].w;
+      }
+    }
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int sl = 0; sl < slabs; ++sl) {
+    const int buf = sl & 1;
+    if (sl + 1 < slabs) fetch(sl + 1);   // global loads in flight while this slab is multiplied
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[RM];
+      if constexpr (RM % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < RM; i += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(&As[buf][kk][ty * RM + i]);
+          av[i] = a.x; av[i + 1] = a.y; av[i + 2] = a.z; av[i + 3] = a.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < RM; ++i) av[i] = As[buf][kk][ty * RM + i];
+      }
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (sl + 1 < slabs) stash(buf ^ 1);   // (the other buffer: its last readers passed the barrier of the previous slab)
+    __syncthreads();
+  }
+  const int n = n0 + tx * 4;
+  if (n >= N) return;
+  float bb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bb[j] = (bias != nullptr && n + j < N) ? bias[n + j] : 0.f;
+#pragma unroll
+  for (int i = 0; i < RM; ++i) {
+    const int64_t m = m0 + ty * RM + i;
+    if (m >= M) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = apply_act(acc[i][j] + bb[j], act);
+    if (n + 3 < N && (N & 3) == 0) {
+      *reinterpret_cast<float4*>(Y + m * N + n) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < N) Y[m * N + n + j] = v[j];
     }
   }
 }
@@ -361,6 +480,21 @@ int xdr_dense_fwd(const float* X, const float* W, const float* bias, const float
   XDR_REQUIRE(act >= XDR_ACT_NONE && act <= XDR_ACT_SIGMOID, "xdr_dense_fwd: bad act %d", act);
   if (tc5_dense_fwd_ok(X, W, X2, W2, Y, M, N, K))   // tensor cores (tcgen05, bf16x3) for the shapes that are GEMMs
     return tc5_dense_fwd(X, W, bias, X2, W2, mask_ids, mask_lt, act, Y, M, N, K, (cudaStream_t)stream);
+  // (measured, call 29: the 128-row tiles win for narrow layers -- N <= 32: 12.6 vs 16.7 us, 7.4 vs 10.5 us at the CoNet shapes --
+  // and lose for N >= 64, where 128 CTAs of 8 warps leave the FMA pipe under-occupied: 55.6 vs 51.5 us; XDR_DENSE_FWD2=2 forces them)
+  if (g_dense_fwd2 && (N <= 32 || g_dense_fwd2 == 2) && M >= BM2 && (K & 3) == 0 && aligned16(X) && aligned16(W) && aligned16(Y) && aligned16(X2) && aligned16(W2)) {
+    // register-blocked, double-buffered tiles (128 x 64 / 128 x 32 / 128 x 16 by the layer's width)
+    const int bn = N > 32 ? 64 : (N > 16 ? 32 : 16);
+    dim3 grid((unsigned)((M + BM2 - 1) / BM2), (unsigned)((N + bn - 1) / bn));
+    if (bn == 64)
+      XDR_LAUNCH((dense_fwd2_kernel<64>), grid, kDenseThreads, 0, (cudaStream_t)stream, X, W, bias, X2, W2, mask_ids, mask_lt, act, Y, M, N, K);
+    else if (bn == 32)
+      XDR_LAUNCH((dense_fwd2_kernel<32>), grid, kDenseThreads, 0, (cudaStream_t)stream, X, W, bias, X2, W2, mask_ids, mask_lt, act, Y, M, N, K);
+    else
+      XDR_LAUNCH((dense_fwd2_kernel<16>), grid, kDenseThreads, 0, (cudaStream_t)stream, X, W, bias, X2, W2, mask_ids, mask_lt, act, Y, M, N, K);
+    XDR_LAUNCH_OK();
+    return XDR_OK;
+  }
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
   XDR_LAUNCH((dense_fwd_kernel), grid, kDenseThreads, 0, (cudaStream_t)stream, X, W, bias, X2, W2, mask_ids, mask_lt, act, Y, M, N, K);
   XDR_LAUNCH_OK();

@@ -91,7 +91,7 @@ class _Aliasless(torch.Tensor):
         return self.as_subclass(torch.Tensor).clone()
 
 
-@pytest.mark.parametrize('M,N,K', [(1, 1, 8), (100, 64, 128), (777, 33, 20)])
+@pytest.mark.parametrize('M,N,K', [(1, 1, 8), (100, 64, 128), (777, 33, 20), (300, 24, 32), (257, 16, 64), (130, 128, 36)])
 @pytest.mark.parametrize('act', ['none', 'relu', 'tanh', 'sigmoid'])
 def test_dense_fwd_bwd(M, N, K, act):
     G.test_dense_fwd_bwd(M, N, K, act)

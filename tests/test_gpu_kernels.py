@@ -218,7 +218,8 @@ def test_fused_sgd_scatter_updates_weights_in_place():
 
 
 # ---------------------------------------------------------------------------------------------------- dense family
-@pytest.mark.parametrize('M,N,K', [(1, 1, 8), (100, 64, 128), (8192, 128, 64), (1000, 8, 16), (777, 33, 20), (4096, 64, 256)])
+@pytest.mark.parametrize('M,N,K', [(1, 1, 8), (100, 64, 128), (8192, 128, 64), (1000, 8, 16), (777, 33, 20), (4096, 64, 256),
+                                   (300, 24, 32), (257, 16, 64), (130, 128, 36)])   # (the last three: the 128 x 32 / 128 x 16 forward tiles, row tails)
 @pytest.mark.parametrize('act', ['none', 'relu', 'tanh', 'sigmoid'])
 def test_dense_fwd_bwd(M, N, K, act):
     L = lib()

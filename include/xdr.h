@@ -320,9 +320,9 @@ XDR_API int xdr_train_steps(const float* user_tab, const float* item_tab, int64_
 /* The same launch with LAZILY ZEROED gradient tables (single GPU).  A scatter-add (RED) into a gradient line that is not in
  * L2 costs a DRAM read and, later, a write-back: twice the bytes the reference's `zeros + index_add` needs to produce.
  * touch_map (xdr_touch_map_bytes(n_users, n_items) bytes, 16-byte aligned; user part first) holds 2 bits per destination
- * row.  A row whose bits are clear COUNTS AS ZERO whatever the table holds there: the first touch of such a row in a launch
- * stores a full row of zeros (full-line stores allocate in L2 without reading DRAM), and the scatter-adds of that row wait
- * for them, then hit L2.  So `optimizer.zero_grad()` (a dense N x D fill in the reference, emcdr.py tables via recbole
+ * row.  A row whose bits are clear COUNTS AS ZERO whatever the table holds there: the loader warp that gathers a row also
+ * claims its destination row (bit 0), and the first claimer stores a full row of zeros (full-line stores allocate in L2 without
+ * reading DRAM), fences and sets bit 1 ("filled"); later claimers wait for bit 1; the scatter-adds then hit L2.  So `optimizer.zero_grad()` (a dense N x D fill in the reference, emcdr.py tables via recbole
  * Trainer._train_epoch) becomes clearing the map -- clear_map != 0 does that first, making user_dst / item_dst the gradient of
  * exactly this launch's K batches on the rows the map marks afterwards (bit 0 of a row's pair), e.g. for a row-sparse
  * optimizer; clear_map == 0 keeps accumulating into the marked rows.  Rows with clear bits are never written and may hold

@@ -578,9 +578,13 @@ def run_xdr(args):
             src_ids = wl.ids
         Re2 = max(3, R // 2)
         host = src_ids[W: W + min(R, Re2) * K].cpu().pin_memory()   # pinned [*, 3, B] int64 id blocks on the host
-        for c in range(min(3, n_chunks)):
-            runner.run(host[c * chunk:(c + 1) * chunk])
-        timer.barrier()
+        # untimed passes of exactly the timed code path: buffers of every shape created, and the pinned-memory pool filled with
+        # the loss tensors of three passes (a first-time cudaHostAlloc inside the timed region cost 0.4 ms of a 0.2 ms pass)
+        warm = []
+        for _ in range(3):
+            warm.append([runner.run(host[c * chunk:(c + 1) * chunk]) for c in range(n_chunks)])
+            timer.barrier()
+        del warm
         api_ms, api_loss = [], []
         for r in range(min(R, Re2)):
             blocks = [host[r * K + c * chunk: r * K + (c + 1) * chunk] for c in range(n_chunks)]

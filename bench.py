@@ -576,7 +576,8 @@ def run_xdr(args):
             if args.grad_mode == 'fresh':   # the K-step block's gradient: the map is cleared per block, chunks accumulate
                 runner.steps_kw = dict(touch=wl.touch_map(), fresh=False)
             src_ids = wl.ids
-        Re2 = max(3, R // 2)
+        Re2 = max(3, R)   # (as many samples as the device-timed value: the median must survive host hiccups -- the clock sampler's
+                          # nvidia-smi fork, a first cudaHostAlloc -- that land inside a 0.2 ms pass)
         host = src_ids[W: W + min(R, Re2) * K].cpu().pin_memory()   # pinned [*, 3, B] int64 id blocks on the host
         # untimed passes of exactly the timed code path: buffers of every shape created, and the pinned-memory pool filled with
         # the loss tensors of three passes (a first-time cudaHostAlloc inside the timed region cost 0.4 ms of a 0.2 ms pass)

@@ -200,7 +200,11 @@ XDR_API int xdr_tc_mlp_step(int n_layers, const int* dims_host, const float* con
  * The EMCDR map step (in_mode 0, head 0, two layers [D, 128, D], D % 16 == 0, D <= 64) with all six products of a 128-row
  * tile on tcgen05.mma kind::f16 (bf16x3: bf16 hi / lo operand planes, fp32 accumulation in tensor memory, ~2^-16 relative per
  * product) and the weight-gradient accumulators resident in tensor memory over all tiles of a CTA.  Same arguments and
- * results as xdr_fused_mlp_step; anything else is XDR_ERR_INVALID.  NOT yet run on hardware (see tc5.cuh).             */
+ * results as xdr_fused_mlp_step; anything else is XDR_ERR_INVALID.  Validated on a B200 (round 2); EMCDR's default engine.
+ * backward == 2 (this entry point only) is the CORRECTION pass of an eager step: a caller that already ran backward == 1
+ * with an upstream gradient of 1 at forward time (so that loss and gradients cost ONE launch) calls it from its autograd
+ * backward with the real upstream gradient g (grad_loss, required): it adds (g - 1) x the gradients to the same destinations
+ * and returns at once, before allocating anything, when g == 1 -- which is what loss.backward() passes.                       */
 XDR_API int xdr_tc5_mlp_supported(int n_layers, const int* dims_host);
 XDR_API int xdr_tc5_mlp_step(int n_layers, const int* dims_host, const float* const* W_host, const float* const* b_host,
                              float* const* dW_host, float* const* db_host, int hidden_act, int in_mode, int head,

@@ -109,6 +109,14 @@ __device__ __forceinline__ float m5_bf16_pair_lo(uint32_t u) { return __uint_as_
 __device__ __forceinline__ float m5_bf16_pair_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
 __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Workspace ws) {
+  // backward == 2, the "correction" pass of an eager step (see xdr.h): the gradients were already accumulated with an upstream
+  // gradient of 1 by a backward == 1 launch at forward time; this launch adds (g - 1) times the same -- and is over before it
+  // allocates anything when g == 1, which is what loss.backward() passes
+  float g_up = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f);
+  if (a.backward == 2) {
+    g_up -= 1.0f;
+    if (g_up == 0.f) return;
+  }
   XDR_DYN_SMEM_ALIGNED(unsigned char, smem_m5, 128);
   __shared__ float red_smem[kM5Threads / 32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -162,7 +170,6 @@ __global__ void __launch_bounds__(kM5Threads, 1) tc5_mlp_kernel(MlpArgs a, Works
     tc5::fence_after_sync();
   };
 
-  const float g_up = (a.grad_loss ? __ldg(a.grad_loss) : 1.0f);
   const float gs = g_up * 2.0f / ((float)a.batch * (float)D);
   float loss_acc[1] = {0.f};
   const int64_t n_tiles = (a.batch + kM5Rows - 1) / kM5Rows;
@@ -408,6 +415,8 @@ int xdr_tc5_mlp_step(int n_layers, const int* dims_host, const float* const* W_h
   XDR_REQUIRE(in_mode == 0 && head == 0, "xdr_tc5_mlp_step: only the single-table input with the MSE head (the EMCDR map step)");
   XDR_REQUIRE(dim == dims_host[0] && batch > 0, "xdr_tc5_mlp_step: bad dim/batch");
   XDR_REQUIRE(W_host && idx_u && out8 && ws && Au && T, "xdr_tc5_mlp_step: null pointer");
+  XDR_REQUIRE(backward >= 0 && backward <= 2, "xdr_tc5_mlp_step: backward must be 0, 1 or 2 (correction pass)");
+  XDR_REQUIRE(backward != 2 || grad_loss, "xdr_tc5_mlp_step: the correction pass needs grad_loss");
   XDR_REQUIRE(!backward || (dAu && dT), "xdr_tc5_mlp_step: null destination");
   XDR_REQUIRE(aligned16(Au) && aligned16(T) && (!backward || (aligned16(dAu) && aligned16(dT))),
               "xdr_tc5_mlp_step: tables must be 16-byte aligned");

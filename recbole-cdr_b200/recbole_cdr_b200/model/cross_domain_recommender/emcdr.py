@@ -45,7 +45,7 @@ class EMCDR(CrossDomainRecommender):
         # Engine of the map step (config key ``xdr_fused_mlp``).  Absent / 'auto' (default): the tcgen05 kernel (tc5_mlp.cu:
         # gather -> both layers -> MSE -> whole backward -> scatter in one launch, bf16x3 products on the tensor cores) for
         # the stacks it takes -- [D, 128, D], D a multiple of 16 up to 64, i.e. the yaml default -- and the composed fp32
-        # kernels for everything else (measured on a B200 at b = 8192: 57 us against 98 us per step, profiles/r2_rows.md).
+        # kernels for everything else (measured on a B200 at b = 8192: 37 us against 98 us per step, profiles/r2_rows.md).
         # False: always composed; True / 'fma': fp32 row-tile kernel; 'tc': mma.sync row-tile kernel; 'tc5': tcgen05 or error.
         flag = config['xdr_fused_mlp'] if 'xdr_fused_mlp' in config else 'auto'
         self.fused_mlp_auto = flag == 'auto'

@@ -23,6 +23,8 @@ from . import _lib
 from ._lib import call, cur_stream, ptr
 
 _TABLE_GRAD_MODE = 'autograd'
+# tcgen05 map step + 'inplace' table gradients: loss and gradients in ONE launch at forward time (XDR_EAGER_TC5=0 switches it off)
+EAGER_TC5 = _os.environ.get('XDR_EAGER_TC5', '1') != '0'
 # set True (or env XDR_CHECK_IDS=1) to raise IndexError on out-of-range ids (adds a sync per op)
 CHECK_IDS = _os.environ.get('XDR_CHECK_IDS', '0') == '1'
 
@@ -643,7 +645,7 @@ def _fused_mlp_call(in_mode, head, hidden_act, tabs, idx_u, idx_i, label, Ws, bs
     call(_FUSED_MLP_ENTRY[engine] + '_step', len(Ws), _ct.cast(arr, _ct.c_void_p), _ptr_array(Ws), _ptr_array(bs),
          _ptr_array(dWs) if dWs else None, _ptr_array(dbs) if dbs else None, int(hidden_act), int(in_mode), int(head),
          ptr(Au), ptr(Bu), ptr(Ai), ptr(Bi), ptr(T), Au.shape[0], Ai.shape[0] if Ai is not None else 0, Au.shape[1],
-         ptr(idx_u), ptr(idx_i), ptr(label), B, 1 if backward else 0, ptr(grad_loss), 1.0, ptr(dAu), ptr(dBu), ptr(dAi),
+         ptr(idx_u), ptr(idx_i), ptr(label), B, int(backward), ptr(grad_loss), 1.0, ptr(dAu), ptr(dBu), ptr(dAi),
          ptr(dBi), ptr(dT), ptr(prob), ptr(out8), ptr(_lib.workspace(dev)), _oob(dev), cur_stream())
     _maybe_check(dev)
     return out8, prob
@@ -656,16 +658,31 @@ class FusedMlpLoss(torch.autograd.Function):
     the layer biases (None where a layer has none)."""
 
     @staticmethod
-    def forward(ctx, in_mode, head, hidden_act, idx_u, idx_i, label, n_layers, engine, Au, Bu, Ai, Bi, T, *wb):
+    def forward(ctx, in_mode, head, hidden_act, idx_u, idx_i, label, n_layers, engine, eager, Au, Bu, Ai, Bi, T, *wb):
         Ws, bs = list(wb[:n_layers]), list(wb[n_layers:])
         for t in (Au, Bu, Ai, Bi, T) + tuple(Ws):
             if t is not None:
                 _require_cuda_f32(t, 'fused_mlp operand')
         idx_u = _ids(idx_u, 'idx_u').reshape(-1)
         idx_i = _ids(idx_i, 'idx_i').reshape(-1) if idx_i is not None else None
-        out8, _ = _fused_mlp_call(in_mode, head, hidden_act, (Au, Bu, Ai, Bi, T), idx_u, idx_i, label, Ws, bs, False, None,
-                                  (None,) * 5, None, None, False, engine)
         ctx.cfg = (in_mode, head, hidden_act, n_layers, engine)
+        ctx.eager = None
+        if eager:
+            # ONE launch for the loss and every gradient (upstream gradient 1, what loss.backward() passes): table gradients go
+            # straight into the tables' .grad ('inplace' mode), the MLP's into one zeroed scratch block that backward() returns;
+            # backward() adds the (g - 1)-fold with a correction launch that is over at once when g == 1 (xdr.h)
+            dsts = [None if t is None else _grad_dst(t)[0] for t in (Au, Bu, Ai, Bi, T)]
+            sizes = [w.numel() for w in Ws] + [0 if b is None else b.numel() for b in bs]
+            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=Au.device)
+            parts = list(torch.split(flat, sizes))
+            dWs = [parts[k].view_as(w) for k, w in enumerate(Ws)]
+            dbs = [None if b is None else parts[n_layers + k].view_as(b) for k, b in enumerate(bs)]
+            out8, _ = _fused_mlp_call(in_mode, head, hidden_act, (Au, Bu, Ai, Bi, T), idx_u, idx_i, label, Ws, bs, 1, None, dsts,
+                                      dWs, dbs, False, engine)
+            ctx.eager = (dsts, dWs, dbs)
+        else:
+            out8, _ = _fused_mlp_call(in_mode, head, hidden_act, (Au, Bu, Ai, Bi, T), idx_u, idx_i, label, Ws, bs, 0, None,
+                                      (None,) * 5, None, None, False, engine)
         ctx.save_for_backward(idx_u, idx_i, label, Au, Bu, Ai, Bi, T, *Ws, *bs)
         return out8[0]
 
@@ -676,6 +693,12 @@ class FusedMlpLoss(torch.autograd.Function):
         idx_u, idx_i, label, Au, Bu, Ai, Bi, T = sv[:8]
         Ws, bs = list(sv[8:8 + n_layers]), list(sv[8 + n_layers:])
         g = grad_loss.reshape(-1)[:1].contiguous().float()
+        if ctx.eager is not None:
+            dsts, dWs, dbs = ctx.eager
+            ctx.eager = None   # (the returned gradients are then unshared: autograd adopts them as .grad instead of copying)
+            _fused_mlp_call(in_mode, head, hidden_act, (Au, Bu, Ai, Bi, T), idx_u, idx_i, label, Ws, bs, 2, g, dsts, dWs, dbs,
+                            False, engine)
+            return (None,) * 9 + (None,) * 5 + tuple(dWs) + tuple(dbs)
         dsts, rets = [], []
         for t in (Au, Bu, Ai, Bi, T):
             if t is None:
@@ -687,14 +710,21 @@ class FusedMlpLoss(torch.autograd.Function):
                 rets.append(r)
         dWs = [torch.zeros_like(w) for w in Ws]
         dbs = [None if b is None else torch.zeros_like(b) for b in bs]
-        _fused_mlp_call(in_mode, head, hidden_act, (Au, Bu, Ai, Bi, T), idx_u, idx_i, label, Ws, bs, True, g, dsts, dWs, dbs,
+        _fused_mlp_call(in_mode, head, hidden_act, (Au, Bu, Ai, Bi, T), idx_u, idx_i, label, Ws, bs, 1, g, dsts, dWs, dbs,
                         False, engine)
-        return (None,) * 8 + tuple(rets) + tuple(dWs) + tuple(dbs)
+        return (None,) * 9 + tuple(rets) + tuple(dWs) + tuple(dbs)
 
 
 def fused_mlp_loss(in_mode, head, hidden_act, idx_u, idx_i, label, tabs, Ws, bs, engine='fma'):
+    """``loss(MLP(gathered rows))`` with its whole backward in the fused kernels.  With the tcgen05 engine and 'inplace' table
+    gradients the step is EAGER: forward computes the loss and accumulates every gradient in one launch, backward only
+    corrects for an upstream gradient other than 1 (see FusedMlpLoss.forward).  Consequence of eagerness, as for every
+    in-place gradient: a forward under grad mode whose backward is never called has still added to the tables' ``.grad``."""
     Au, Bu, Ai, Bi, T = tabs
-    return FusedMlpLoss.apply(in_mode, head, hidden_act, idx_u, idx_i, label, len(Ws), engine, Au, Bu, Ai, Bi, T, *Ws, *bs)
+    tables = [t for t in tabs if t is not None]
+    eager = (engine == 'tc5' and EAGER_TC5 and _TABLE_GRAD_MODE == 'inplace' and torch.is_grad_enabled() and
+             all(t.is_leaf and t.requires_grad for t in tables) and all(w.requires_grad for w in Ws))
+    return FusedMlpLoss.apply(in_mode, head, hidden_act, idx_u, idx_i, label, len(Ws), engine, eager, Au, Bu, Ai, Bi, T, *Ws, *bs)
 
 
 def fused_mlp_prob(hidden_act, idx_u, idx_i, tabs, Ws, bs, engine='fma'):

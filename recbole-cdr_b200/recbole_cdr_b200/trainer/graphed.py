@@ -89,7 +89,8 @@ class GraphedTrainStep(object):
     def _step(self):
         losses = self.loss_fn(self.static)
         loss = sum(losses) if isinstance(losses, tuple) else losses
-        loss = loss.sum()
+        if loss.dim() > 0:   # (a 0-d loss needs no reduction kernel and no expand in its backward)
+            loss = loss.sum()
         loss.backward()
         if self.optimizer is not None:
             self.optimizer.step()

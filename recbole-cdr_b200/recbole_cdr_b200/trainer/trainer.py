@@ -237,7 +237,8 @@ class CrossDomainTrainer(object):
             self.optimizer.zero_grad()
             losses = loss_func(interaction)
             loss = sum(losses) if isinstance(losses, tuple) else losses
-            loss = loss.sum()
+            if loss.dim() > 0:
+                loss = loss.sum()
             total = loss.detach() if total is None else total + loss.detach()
             loss.backward()
             if self.clip_grad_norm:

@@ -108,3 +108,75 @@ def test_emcdr_map_phase_vs_reference_golden(case):
         M.check(m, g, M.cpu_batch(g), grad_rtol=2e-4, grad_atol=2e-6)
         after = emu_util.counters(reset=False)
         assert after['umma_bf16'] > 0, 'the tcgen05 kernel did not run'
+
+
+def test_correction_pass_completes_an_eager_step():
+    """backward = 2 adds (g - 1) x the gradients on top of a backward = 1 launch that used an upstream gradient of 1 -- together
+    they are the step with upstream gradient g -- and is a no-op for g = 1."""
+    D, B, n_rows, sms = 64, 200, 300, 2
+    rng = np.random.RandomState(11)
+    src, tgt = (rng.randn(n_rows, D) * 0.5).astype(np.float32), (rng.randn(n_rows, D) * 0.5).astype(np.float32)
+    W1, b1 = (rng.randn(128, D) / 8).astype(np.float32), (rng.randn(128) * 0.1).astype(np.float32)
+    W2, b2 = (rng.randn(D, 128) / 11).astype(np.float32), (rng.randn(D) * 0.1).astype(np.float32)
+    idx = rng.randint(0, n_rows, B).astype(np.int64)
+    L, p = emu_util.lib(), emu_util.p
+    emu_util.config(sms=sms, seed=1)
+    dims = (ctypes.c_int * 3)(D, 128, D)
+
+    def launch(mode, g, dst):
+        dW, db, dsrc, dtgt = dst
+        out8, gg, ws = np.full(8, np.nan, np.float32), np.array([g], np.float32), emu_util.workspace()
+        rc = L.xdr_tc5_mlp_step(ctypes.c_int(2), dims, emu_util.ptr_array([W1, W2]), emu_util.ptr_array([b1, b2]),
+                                emu_util.ptr_array(dW), emu_util.ptr_array(db), ctypes.c_int(2), ctypes.c_int(0), ctypes.c_int(0),
+                                p(src), None, None, None, p(tgt), ctypes.c_int64(n_rows), ctypes.c_int64(0), ctypes.c_int(D),
+                                p(idx), None, None, ctypes.c_int64(B), ctypes.c_int(mode), p(gg) if g is not None else None,
+                                ctypes.c_float(1.0), p(dsrc), None, None, None, p(dtgt), None, p(out8), p(ws), None, None)
+        assert rc == 0, L.emu_last_error()
+        return out8
+
+    fresh = lambda: ([np.zeros_like(W1), np.zeros_like(W2)], [np.zeros_like(b1), np.zeros_like(b2)], np.zeros_like(src), np.zeros_like(tgt))
+    for g in (1.0, 0.25, 3.0):
+        want = fresh()
+        launch(1, g, want)                       # the ordinary backward with upstream gradient g
+        got = fresh()
+        launch(1, None, got)                     # eager: upstream gradient 1 at forward time ...
+        snap = [a.copy() for a in got[0]]
+        out8 = launch(2, g, got)                 # ... then the correction
+        if g == 1.0:
+            assert np.isnan(out8).all(), 'the correction pass must return before it does anything when g == 1'
+            for a, b in zip(snap, got[0]):
+                np.testing.assert_array_equal(a, b)
+        for a, b in zip(want[0] + want[1] + [want[2], want[3]], got[0] + got[1] + [got[2], got[3]]):
+            np.testing.assert_allclose(b, a, rtol=1e-4, atol=1e-6 * max(1.0, float(np.abs(a).max())))
+    assert L.xdr_tc5_mlp_step is not None
+
+
+def test_eager_step_through_the_drop_in_class():
+    """'inplace' table gradients + the tcgen05 engine: calculate_loss accumulates every gradient in ONE launch, backward() only
+    corrects; same loss and gradients as the reference golden, also when the loss is scaled before backward()."""
+    import test_emu_models as M
+    from recbole_cdr_b200.model.cross_domain_recommender.emcdr import EMCDR
+    g = Golden('emcdr_map_non_linear')
+    for factor in (1.0, 0.5):
+        with emu_util.patched_ops() as ops:
+            prev = ops.get_table_grad_mode()
+            ops.set_table_grad_mode('inplace')
+            try:
+                m = M.build_cpu(EMCDR, g, dict(M.EMCDR_CFG, latent_factor_model='BPR', mapping_function='non_linear'))
+                m.set_phase('OVERLAP')
+                assert m.fused_mlp_auto and m.fused_mlp_engine == 'tc5'
+                calls = []
+                real = ops.call
+                ops.call = lambda nm, *a, **k: (calls.append((nm, a[21])) if nm == 'xdr_tc5_mlp_step' else None, real(nm, *a, **k))[1]
+                try:
+                    loss = m.calculate_loss(M.cpu_batch(g))
+                    (loss * factor).sum().backward()
+                finally:
+                    ops.call = real
+                assert [c[1] for c in calls] == [1, 2], calls      # one eager launch, one correction launch
+                torch.testing.assert_close(loss.detach().reshape(-1), g.losses()[0].reshape(-1), rtol=1e-4, atol=0)
+                for name, prm in m.named_parameters():
+                    got = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+                    torch.testing.assert_close(got, g.grad(name) * factor, rtol=2e-4, atol=2e-6, msg=lambda s: f'{name} (x{factor}): {s}')
+            finally:
+                ops.set_table_grad_mode(prev)

@@ -100,6 +100,37 @@ def test_emcdr_map_phase_tc5_engine(case):
     check_loss_and_grads(m, g, cuda_batch(g), grad_rtol=2e-4, grad_atol=2e-6)
 
 
+@pytest.mark.parametrize('batch,factor', [(8192, 1.0), (1000, 1.3), (129, 0.25)])
+def test_tc5_mlp_eager_step_in_place_gradients(batch, factor):
+    """'inplace' table gradients + the tcgen05 engine: forward accumulates every gradient in ONE launch (upstream gradient 1),
+    backward() runs the correction pass ((g - 1)-fold; over at once for g = 1).  Same loss and gradients as the oracle."""
+    g = torch.Generator().manual_seed(311)
+    src, tgt = rand_table(3000, 64, 312, 0.3), rand_table(3000, 64, 313, 0.3)
+    ws = [torch.randn(128, 64, generator=g) * 0.2, torch.randn(64, 128, generator=g) * 0.2]
+    bs = [torch.randn(128, generator=g) * 0.1, torch.randn(64, generator=g) * 0.1]
+    idx = rand_ids(batch, 3000, 314, 1.3)
+    leaves = [t.clone().requires_grad_(True) for t in [src, tgt] + ws + bs]
+    ref = O.emcdr_map_loss(leaves[0], leaves[1], idx.view(-1, 1), leaves[2:4], leaves[4:6])
+    (ref * factor).backward()
+    c = [t.to(dev()).requires_grad_(True) for t in [src, tgt] + ws + bs]
+    prev = ops().get_table_grad_mode()
+    ops().set_table_grad_mode('inplace')
+    seen, real = [], ops().call
+    ops().call = lambda nm, *a, **k: (seen.append(a[21]) if nm == 'xdr_tc5_mlp_step' else None, real(nm, *a, **k))[1]
+    try:
+        loss = ops().fused_mlp_loss(0, 0, lib().ACT_TANH, idx.to(dev()), None, None, (c[0], None, None, None, c[1]), c[2:4], c[4:6],
+                                    'tc5')
+        (loss * factor).backward()
+    finally:
+        ops().call = real
+        ops().set_table_grad_mode(prev)
+    assert seen == [1, 2]
+    torch.testing.assert_close(loss.detach().cpu(), ref.detach(), rtol=LOSS_RTOL, atol=0)
+    for got, want, nm in zip(c, leaves, ('src', 'tgt', 'W1', 'W2', 'b1', 'b2')):
+        atol = max(1e-7, 1e-4 * want.grad.abs().max().item())
+        torch.testing.assert_close(got.grad.cpu(), want.grad, rtol=2e-4, atol=atol, msg=lambda s: f'{nm}: {s}')
+
+
 def test_tc_mlp_supported_stacks():
     assert ops().fused_mlp_supported([64, 128, 64], 'tc') and ops().fused_mlp_supported([128, 32, 16, 1], 'tc')
     assert not ops().fused_mlp_supported([512, 64, 1], 'tc')

@@ -341,19 +341,28 @@ class Dense(torch.autograd.Function):
         call('xdr_act_bwd', ptr(Y), ptr(dY), ctx.act, ptr(dZ), dY.numel(), s)
         needs = ctx.needs_input_grad
         dX = dW = db = dX2 = dW2 = None
+        # the weight-gradient kernels accumulate: their destinations (dW, db, dW2) are views of ONE zero-filled block -- one
+        # fill kernel per layer instead of three
+        want_w = needs[1] or (bias is not None and needs[2])
+        want_w2 = X2 is not None and needs[4]
+        pad4 = lambda n: (n + 3) // 4 * 4   # every view starts 16-byte aligned
+        sizes = [pad4(W.numel()) if want_w else 0, pad4(bias.numel()) if (want_w and bias is not None) else 0,
+                 pad4(W2.numel()) if want_w2 else 0]
+        if sum(sizes):
+            parts = torch.split(torch.zeros(sum(sizes), dtype=torch.float32, device=X.device), sizes)
         if needs[0]:
             dX = torch.empty_like(X)
             call('xdr_dense_bwd_input', ptr(dZ), ptr(W), None, 0, ptr(dX), M, N, K, 0, s)
-        if needs[1] or (bias is not None and needs[2]):
-            dW = torch.zeros_like(W)
-            db = torch.zeros_like(bias) if bias is not None else None
+        if want_w:
+            dW = parts[0][:W.numel()].view_as(W)
+            db = parts[1][:bias.numel()].view_as(bias) if bias is not None else None
             call('xdr_dense_bwd_weight', ptr(dZ), ptr(X), None, 0, ptr(dW), ptr(db), M, N, K, s)
         if X2 is not None:
             if needs[3]:
                 dX2 = torch.empty_like(X2)
                 call('xdr_dense_bwd_input', ptr(dZ), ptr(W2), ptr(mask_ids), ctx.mask_lt, ptr(dX2), M, N, K, 0, s)
-            if needs[4]:
-                dW2 = torch.zeros_like(W2)
+            if want_w2:
+                dW2 = parts[2][:W2.numel()].view_as(W2)
                 call('xdr_dense_bwd_weight', ptr(dZ), ptr(X2), ptr(mask_ids), ctx.mask_lt, ptr(dW2), None, M, N, K, s)
         return dX, dW, db, dX2, dW2, None, None, None
 

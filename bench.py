@@ -605,7 +605,7 @@ def run_xdr(args):
         api_ms = t.tolist()
         med = statistics.median(api_ms)
         e2e = {'value': world * B * Ke / (med * 1e-3), 'unit': 'interactions/s',
-               'h2d_bytes_per_step': 3 * 8 * B, 'd2h_bytes_per_step': 4, 'steps': Ke, 'steps_per_launch': chunk,
+               'h2d_bytes_per_step': 3 * 8 * B, 'd2h_bytes_per_step': 32, 'steps': Ke, 'steps_per_launch': chunk,
                'repeats': len(api_ms), 'min_ms': min(api_ms), 'max_ms': max(api_ms), 'loss_mean': statistics.mean(api_loss),
                'api': 'trainer.FusedStepRunner.run(pinned [chunk,3,B] int64 ids): H2D copy -> xdr_train_steps -> D2H losses, '
                       'chunks triple-buffered so copies overlap launches; host enqueue time included'}

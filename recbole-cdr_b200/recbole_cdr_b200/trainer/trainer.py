@@ -111,11 +111,12 @@ class FusedStepRunner:
         self.launches += 1
         # one pinned tensor PER RUN (torch's caching host allocator makes this cheap): the caller owns it, so a later chunk
         # that reuses this device buffer cannot overwrite losses the caller has not read yet
-        loss = torch.empty(K, dtype=torch.float32, pin_memory=True)
-        loss.copy_(buf['out8'][:, 0], non_blocking=True)
+        # (the whole [K, 8] record in one contiguous device->host copy: a strided column would cost a gather kernel first)
+        rec = torch.empty((K, 8), dtype=torch.float32, pin_memory=True)
+        rec.copy_(buf['out8'], non_blocking=True)
         buf['done'].record(main)
         buf['used'] = True
-        return loss
+        return rec[:, 0]
 
     def synchronize(self):
         torch.cuda.current_stream(self.dev).synchronize()

@@ -134,6 +134,8 @@ class GatherRows(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         table, idx = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:   # a frozen table: no dense [N, D] gradient is allocated for it, nothing is scattered
+            return None, None
         go = grad_out.reshape(-1, table.shape[1]).contiguous()
         dst, ret = _grad_dst(table)
         scatter_add_rows_raw(dst, idx, go)
@@ -162,10 +164,13 @@ class GatherConcat(torch.autograd.Function):
         user_tab, item_tab, user, item = ctx.saved_tensors
         go = grad_out.contiguous()
         d = user_tab.shape[1]
-        du, ru = _grad_dst(user_tab)
-        scatter_add_rows_raw(du, user, go, 1.0, 0)
-        di, ri = _grad_dst(item_tab)
-        scatter_add_rows_raw(di, item, go, 1.0, d)
+        ru = ri = None
+        if ctx.needs_input_grad[0]:   # (frozen tables get neither a dense gradient nor a scatter)
+            du, ru = _grad_dst(user_tab)
+            scatter_add_rows_raw(du, user, go, 1.0, 0)
+        if ctx.needs_input_grad[1]:
+            di, ri = _grad_dst(item_tab)
+            scatter_add_rows_raw(di, item, go, 1.0, d)
         return ru, ri, None, None
 
 

@@ -103,3 +103,27 @@ def test_mse_rows_and_bce_logit():
 
 def test_gather_max2_concat_fwd_bwd():
     G.test_gather_max2_concat_fwd_bwd()
+
+
+def test_frozen_tables_get_no_gradient_and_no_dense_allocation():
+    """the row gathers consult needs_input_grad -- a table with requires_grad = False is neither scattered into nor
+    given a dense [N, D] zero gradient."""
+    with emu_util.patched_ops() as ops:
+        g = torch.Generator().manual_seed(5)
+        ut, it = torch.randn(50, 16, generator=g), torch.randn(60, 16, generator=g)
+        u, i = torch.randint(0, 50, (33,), generator=g), torch.randint(0, 60, (33,), generator=g)
+        ut.requires_grad_(False)
+        it.requires_grad_(True)
+        seen, real = [], ops.call
+        ops.call = lambda nm, *a, **k: (seen.append(nm), real(nm, *a, **k))[1]
+        try:
+            out = ops.gather_concat(ut, it, u, i) if hasattr(ops, 'gather_concat') else ops.GatherConcat.apply(ut, it, u, i)
+            out.sum().backward()
+            rows = ops.gather_rows(ut, u)          # nothing requires grad here: no backward at all
+            assert not rows.requires_grad
+        finally:
+            ops.call = real
+        assert ut.grad is None and it.grad is not None
+        assert seen.count('xdr_scatter_add_rows') == 1          # the item table only
+        ref = torch.zeros_like(it).index_add_(0, i, torch.ones(33, 16))
+        torch.testing.assert_close(it.grad, ref)

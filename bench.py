@@ -587,6 +587,9 @@ def run_xdr(args):
             timer.barrier()
         del warm
         api_ms, api_loss = [], []
+        import gc
+        gc.collect()
+        gc.disable()   # (no cyclic-GC pause inside a 0.2 ms host-driven pass; re-enabled below)
         for r in range(min(R, Re2)):
             blocks = [host[r * K + c * chunk: r * K + (c + 1) * chunk] for c in range(n_chunks)]
             timer.barrier()
@@ -599,6 +602,7 @@ def run_xdr(args):
             timer.barrier()
             api_ms.append(a0.elapsed_time(a1))
             api_loss.append(float(torch.stack([l.mean() for l in losses]).mean()))
+        gc.enable()
         t = torch.tensor(api_ms, device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -606,7 +610,8 @@ def run_xdr(args):
         med = statistics.median(api_ms)
         e2e = {'value': world * B * Ke / (med * 1e-3), 'unit': 'interactions/s',
                'h2d_bytes_per_step': 3 * 8 * B, 'd2h_bytes_per_step': 32, 'steps': Ke, 'steps_per_launch': chunk,
-               'repeats': len(api_ms), 'min_ms': min(api_ms), 'max_ms': max(api_ms), 'loss_mean': statistics.mean(api_loss),
+               'repeats': len(api_ms), 'min_ms': min(api_ms), 'max_ms': max(api_ms), 'samples_ms': [round(x, 4) for x in api_ms],
+               'loss_mean': statistics.mean(api_loss),
                'api': 'trainer.FusedStepRunner.run(pinned [chunk,3,B] int64 ids): H2D copy -> xdr_train_steps -> D2H losses, '
                       'chunks triple-buffered so copies overlap launches; host enqueue time included'}
     clk = clocks.stop() if rank == 0 else None

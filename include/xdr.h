@@ -321,6 +321,20 @@ XDR_API int xdr_train_steps(const float* user_tab, const float* item_tab, int64_
                             float reg_weight, const float* grad_loss, float scale, float* user_dst, float* item_dst,
                             float* out8, void* steps_ws, size_t steps_ws_bytes, int32_t* oob, xdr_stream_t stream);
 
+/* One chunk of K pairwise steps fed from a PINNED HOST id block, enqueued with ONE call (the engine of trainer.FusedStepRunner):
+ * on copy_stream -- wait for buf_free_event (the event recorded after the launch that last read dev_ids; NULL: nothing to wait
+ * for), copy host_ids [n_steps][3][batch] (user, item+, item-) into dev_ids, record ids_ready_event; on stream -- wait for it,
+ * run xdr_train_steps over dev_ids (step stride 3 * batch), copy the [n_steps][8] records into host_out8 (pinned; NULL: no
+ * copy) and record launch_done_event (NULL: none).  Replaces, per chunk, the host side of K iterations of recbole
+ * Trainer._train_epoch: `interaction.to(device)` and the loss read-back around calculate_loss / backward (reference
+ * trainer.py:59-73 via recbole-1.0.1).  The events and streams are the caller's (cudaEvent_t / cudaStream_t handles).       */
+XDR_API int xdr_train_steps_host(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
+                                 const int64_t* host_ids, int64_t* dev_ids, int64_t batch, int n_steps, float gamma,
+                                 float reg_weight, const float* grad_loss, float scale, float* user_dst, float* item_dst,
+                                 float* out8, float* host_out8, void* steps_ws, size_t steps_ws_bytes, int32_t* oob,
+                                 xdr_stream_t copy_stream, void* buf_free_event, void* ids_ready_event,
+                                 void* launch_done_event, xdr_stream_t stream);
+
 /* The same launch with LAZILY ZEROED gradient tables (single GPU).  A scatter-add (RED) into a gradient line that is not in
  * L2 costs a DRAM read and, later, a write-back: twice the bytes the reference's `zeros + index_add` needs to produce.
  * touch_map (xdr_touch_map_bytes(n_users, n_items) bytes, 16-byte aligned; user part first) holds 2 bits per destination

@@ -1276,7 +1276,36 @@ int xdr_train_steps_sharded(const float* const* user_shards, const float* const*
                           steps_ws_bytes, staged_item_a, staged_item_b, oob, stream);
 }
 
-#ifndef XDR_EMU  // CUDA IPC has no emulator counterpart
+#ifndef XDR_EMU  // streams, events and host copies have no emulator counterpart
+// ---- one chunk of K steps fed from PINNED HOST id blocks, enqueued with ONE call -------------------------------------------
+int xdr_train_steps_host(const float* user_tab, const float* item_tab, int64_t n_users, int64_t n_items, int dim,
+                         const int64_t* host_ids, int64_t* dev_ids, int64_t batch, int n_steps, float gamma, float reg_weight,
+                         const float* grad_loss, float scale, float* user_dst, float* item_dst, float* out8, float* host_out8,
+                         void* steps_ws, size_t steps_ws_bytes, int32_t* oob, xdr_stream_t copy_stream, void* buf_free_event,
+                         void* ids_ready_event, void* launch_done_event, xdr_stream_t stream) {
+  const char* fn = "xdr_train_steps_host";
+  XDR_REQUIRE(user_tab && item_tab && host_ids && dev_ids && user_dst && item_dst && out8 && steps_ws && ids_ready_event,
+              "%s: null pointer", fn);
+  XDR_REQUIRE(dim_ok(dim), "%s: dim=%d must be a multiple of 4 in (0, 256]", fn, dim);
+  XDR_REQUIRE(batch > 0 && batch % 4 == 0 && n_steps > 0, "%s: batch=%lld (a positive multiple of 4) n_steps=%d (> 0)", fn,
+              (long long)batch, n_steps);
+  XDR_REQUIRE(aligned16(dev_ids), "%s: the device id block must be 16-byte aligned", fn);
+  cudaStream_t cs = (cudaStream_t)copy_stream, ms = (cudaStream_t)stream;
+  if (buf_free_event) XDR_CUDA_OK(cudaStreamWaitEvent(cs, (cudaEvent_t)buf_free_event, 0));   // the buffer's previous launch is over
+  XDR_CUDA_OK(cudaMemcpyAsync(dev_ids, host_ids, (size_t)n_steps * 3 * (size_t)batch * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+  XDR_CUDA_OK(cudaEventRecord((cudaEvent_t)ids_ready_event, cs));
+  XDR_CUDA_OK(cudaStreamWaitEvent(ms, (cudaEvent_t)ids_ready_event, 0));
+  const int rc = xdr_train_steps(user_tab, item_tab, n_users, n_items, dim, dev_ids, dev_ids + batch, dev_ids + 2 * batch, nullptr,
+                                 3 * batch, batch, n_steps, 1, XDR_LOSS_NONE, gamma, reg_weight, grad_loss, scale, user_dst, item_dst,
+                                 out8, steps_ws, steps_ws_bytes, oob, stream);
+  if (rc != XDR_OK) return rc;
+  if (host_out8)
+    XDR_CUDA_OK(cudaMemcpyAsync(host_out8, out8, (size_t)n_steps * 8 * sizeof(float), cudaMemcpyDeviceToHost, ms));
+  if (launch_done_event) XDR_CUDA_OK(cudaEventRecord((cudaEvent_t)launch_done_event, ms));
+  return XDR_OK;
+}
+
+// (CUDA IPC has no emulator counterpart either)
 // ---- peer-memory plumbing for row-sharded tables (CUDA IPC; one process per GPU) --------------------------------------
 int xdr_ipc_export(const void* dev_ptr, unsigned char* handle64_host, int64_t* offset_host) {
   XDR_REQUIRE(dev_ptr && handle64_host && offset_host, "xdr_ipc_export: null pointer");

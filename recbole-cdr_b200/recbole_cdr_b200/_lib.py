@@ -46,6 +46,8 @@ PROTOTYPES = {
     'xdr_steps_workspace_bytes': (c_sz, [c_int]),
     'xdr_train_steps': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int,
                                 c_f32, c_f32, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_vp]),
+    'xdr_train_steps_host': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_i64, c_int, c_f32, c_f32, c_vp, c_f32, c_vp,
+                                     c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'xdr_steps_set_hot_rows': (c_int, [c_vp, c_int, c_vp, c_int]),
     'xdr_touch_map_bytes': (c_sz, [c_i64, c_i64]),
     'xdr_train_steps_lazy': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int,

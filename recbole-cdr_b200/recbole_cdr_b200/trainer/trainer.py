@@ -50,6 +50,7 @@ class FusedStepRunner:
         else:
             self.dev = torch.device(device)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.one_call = self.dev.type == 'cuda'   # pairwise chunks from pinned blocks go through xdr_train_steps_host
         self.steps_kw = {}      # extra keyword arguments of ops.train_steps (e.g. the touch maps of lazily zeroed gradient tables)
         self.n_buffers = n_buffers
         self._bufs = []  # per in-flight chunk: (dev ids, dev label, out8, host loss, ready event, done event)
@@ -75,12 +76,15 @@ class FusedStepRunner:
                 for t in (ids, lab):
                     if t is not None:
                         t.record_stream(self.copy_stream)   # written on the copy stream, read on the main stream
+                ready, done = torch.cuda.Event(), torch.cuda.Event()
+                ready.record(self.copy_stream)   # (recorded once so that the CUDA events exist: the one-call path below hands
+                done.record(main)                #  their raw handles to the library)
                 self._bufs.append({
                     'key': key, 'ids': ids,
                     # the kernel walks ids and labels with ONE step stride: give the label rows the stride of the id rows
                     'label': (lab[:, 0] if with_label else None),
                     'out8': torch.empty((K, 8), dtype=torch.float32, device=self.dev),
-                    'ready': torch.cuda.Event(), 'done': torch.cuda.Event(), 'used': False})
+                    'ready': ready, 'done': done, 'used': False, 'rec': None})
         b = self._bufs[self._turn % self.n_buffers]
         self._turn += 1
         return b
@@ -92,6 +96,22 @@ class FusedStepRunner:
             raise ValueError(f'id block must be [K, {3 if sp["pairwise"] else 2}, B]')
         buf = self._buffers(host_block.shape, host_label is not None)
         main = torch.cuda.current_stream(self.dev)
+        if (self.one_call and self.launch is None and sp['pairwise'] and host_label is None and not self.steps_kw and
+                host_block.dtype == torch.int64 and host_block.is_contiguous() and host_block.is_pinned()):
+            # the whole chunk -- H2D ids on the copy stream, events, the persistent launch, D2H loss records -- in ONE library
+            # call (xdr_train_steps_host): a dozen torch calls per chunk made a K = 20 pass host-bound
+            rec = torch.empty((K, 8), dtype=torch.float32, pin_memory=True)
+            ws = ops._steps_workspace(self.dev, K)
+            ops.call('xdr_train_steps_host', ops.ptr(self.ut.data), ops.ptr(self.it.data), self.ut.shape[0], self.it.shape[0],
+                     self.ut.shape[1], host_block.data_ptr(), ops.ptr(buf['ids']), B, K, float(sp.get('gamma', 1e-10)),
+                     float(sp['reg_weight']), None, float(self.scale), ops.ptr(self.dst_u), ops.ptr(self.dst_i),
+                     ops.ptr(buf['out8']), rec.data_ptr(), ops.ptr(ws), ws.numel(), ops._oob(self.dev),
+                     self.copy_stream.cuda_stream, buf['done'].cuda_event if buf['used'] else None, buf['ready'].cuda_event,
+                     buf['done'].cuda_event, main.cuda_stream)
+            self.launches += 1
+            buf['used'] = True
+            buf['rec'] = rec   # the pinned block stays referenced until this device buffer's next turn (its copy is raw CUDA)
+            return rec[:, 0]
         with torch.cuda.stream(self.copy_stream):
             if buf['used']:
                 self.copy_stream.wait_event(buf['done'])  # the launch that last read this buffer has finished

@@ -69,7 +69,9 @@ def parse_args():
                     help='accumulate (default): scatter-add into the dense gradient tables; fresh: lazily zeroed gradient tables -- '
                          'every launch produces the gradient of its K batches, first touch of a row stores (touch map)')
     ap.add_argument('--coop', type=int, default=1, help='1: cudaLaunchCooperativeKernel, 0: plain launch')
-    ap.add_argument('--dense-engine', type=int, default=0, help='model-step workloads: 1 tcgen05 dense layers, 0 fp32 FMA')
+    ap.add_argument('--dense-engine', type=int, default=-1,
+                    help='model-step workloads: 0 fp32 FMA dense layers, 1 tcgen05, 2 tcgen05 where it measured faster (wide layers, '
+                         'forward / input gradient), -1 the library default')
     ap.add_argument('--map-engine', default='', help="emcdr_map: '' (the model's default: tcgen05), 'tc5', 'tc' (mma.sync), 'fma', 'composed'")
     ap.add_argument('--shard-chunk', type=int, default=50, help='N>1: steps per persistent launch')
     ap.add_argument('--chunk', type=int, default=0, help='steps per launch on the end-to-end (host-fed) path (0: K/2, 50 from K = 100)')
@@ -866,7 +868,10 @@ def run_model_step(args, dev, name):
     b = args.batch if name == 'emcdr_map' else (16384 if args.batch == 8192 else args.batch)
     K, W, R = args.steps, max(3, args.warmup), max(1, args.repeats)
     peak, peak_src = measured_peaks()
-    _lib._lib.xdr_set_dense_engine(int(args.dense_engine))
+    if args.dense_engine >= 0:
+        _lib._lib.xdr_set_dense_engine(int(args.dense_engine))
+    dense_engine = _lib._lib.xdr_set_dense_engine(0)          # (read back: the call returns the previous setting)
+    _lib._lib.xdr_set_dense_engine(dense_engine)
     from recbole_cdr_b200 import ops as _ops
     _ops.set_table_grad_mode('inplace')   # table gradients are scatter-added into persistent .grad buffers (no dense [N, D] temporaries)
     ds, cfg, make, units, phase = _model_workload(name, b, dev)
@@ -929,7 +934,8 @@ def run_model_step(args, dev, name):
     clk = clocks.stop()
     amed = statistics.median(api)
     achieved = bytes_per * units * K / (med * 1e-3) / 1e9
-    engine = ('tcgen05 dense engine (tc5_dense.cu)' if args.dense_engine else 'fp32 FMA dense kernels')
+    engine = {0: 'fp32 FMA dense kernels', 1: 'tcgen05 dense engine (tc5_dense.cu)',
+              2: 'tcgen05 (tc5_dense.cu) for forward / input gradient of the wide layers, fp32 FMA for the rest'}[dense_engine]
     if name == 'emcdr_map':
         engine = {'tc5': 'tc5_mlp_kernel (one fused tcgen05 kernel per pass)', 'tc': 'tc_mlp_kernel (mma.sync)',
                   'fma': 'fused_mlp_kernel (fp32)', 'composed': 'composed fp32 FMA kernels'}.get(args.map_engine or 'tc5', args.map_engine)
@@ -937,7 +943,7 @@ def run_model_step(args, dev, name):
         'metric': 'interactions/sec (gather+map+score+scatter)', 'value': units * K / (med * 1e-3), 'unit': 'interactions/s',
         'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': med / K, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None,
-        'dtype': 'f32 (dense products: bf16x3 on tcgen05, fp32 accumulate)' if (args.dense_engine or (name == 'emcdr_map' and args.map_engine in ('', 'tc5'))) else 'f32',
+        'dtype': 'f32 (dense products: bf16x3 on tcgen05, fp32 accumulate)' if (dense_engine or (name == 'emcdr_map' and args.map_engine in ('', 'tc5'))) else 'f32',
         'data': 'synthetic',
         'config': {'workload': what % b, 'engine': engine, 'users_total': ds.num_total_user, 'items_total': ds.num_total_item,
                    'batch_per_gpu': b, 'l2': 'inputs larger than L2 (tables of 0.8 .. 7 GB, uniform random rows)',

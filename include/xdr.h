@@ -125,8 +125,10 @@ XDR_API int xdr_point_bwd(const float* user_tab, const float* item_tab, int64_t 
  * recbole MLPLayers (dtcdr.py:61-67).                                                                     */
 /* Engine of the three GEMM entry points below: 1 = tcgen05.mma on three bf16 operand planes (bf16x6: fp32-faithful products,
  * fp32 accumulation in tensor memory) for M >= 128, N % 16 == 0 (16..128), K % 16 == 0 (16..256) and 16-byte aligned
- * operands, fp32 FMA otherwise; 0 (default) = fp32 FMA for every shape -- on a B200 the two tie per call at the BASELINE
- * model shapes (profiles/r2_dense_engines.jsonl), so tcgen05 is opt-in.  Returns the previous setting.                 */
+ * operands, fp32 FMA otherwise; 2 = tcgen05 only for the calls it measured faster on a B200 (forward and input gradient of
+ * wide layers: K >= 192 and N >= 64, i.e. CoNet's layer 0), fp32 FMA for the rest; 0 (default) = fp32 FMA for every shape --
+ * on a B200 the two tie per call at the BASELINE model shapes (profiles/r2_dense_engines.jsonl), so tcgen05 is opt-in.
+ * Returns the previous setting.                                                                                         */
 XDR_API int xdr_set_dense_engine(int engine);
 XDR_API int xdr_dense_fwd(const float* X, const float* W, const float* bias, const float* X2, const float* W2,
                   const int64_t* mask_ids, int64_t mask_lt, int act, float* Y, int64_t M, int N, int K,
@@ -158,6 +160,16 @@ XDR_API int xdr_bce_logit_fwd(const float* logit, const float* label, int64_t co
 /* dlogit[m] = g * (p - y) / max(p*(1-p), 1e-12) * p*(1-p) / count  (BCELoss backward x sigmoid backward).   */
 XDR_API int xdr_bce_logit_bwd(const float* prob, const float* label, int64_t count, const float* grad_loss,
                       float* dlogit, xdr_stream_t stream);
+
+/* ---- A8: CoNet's regulariser sum_l ||H_l||_F over the cross-stitch matrices (conet.py:198-201: reg_loss += torch.norm(
+ * para.weight) per layer -- reg_weight is read but never applied) ---------------------------------------------------------
+ * mats_host / counts_host / dsts_host: HOST arrays of n_mats (1..8) device pointers / element counts.
+ * norms[l] = ||H_l||_F, out[0] = sum_l norms[l]; one launch, one CTA, fixed summation order.                          */
+XDR_API int xdr_frob_sum_fwd(const float* const* mats_host, const int64_t* counts_host, int n_mats, float* norms, float* out,
+                     xdr_stream_t stream);
+/* dsts[l][i] = g * H_l[i] / norms[l]  (0 where the norm is 0, as torch.norm's backward); g = *grad_loss (NULL: 1).     */
+XDR_API int xdr_frob_sum_bwd(const float* const* mats_host, const int64_t* counts_host, int n_mats, const float* norms,
+                     const float* grad_loss, float* const* dsts_host, xdr_stream_t stream);
 
 /* ---- A4 / A14-A15 fused: gather -> small MLP -> loss head -> backward -> scatter-add in one persistent kernel ------------
  * Replaces the whole of EMCDR.calculate_map_loss (emcdr.py:156-168, mapping of emcdr.py:58-64,86-93) and of one

@@ -424,6 +424,49 @@ __global__ void bce_logit_bwd_kernel(const float* __restrict__ prob, const float
   }
 }
 
+// ---- sum of the Frobenius norms of a few small matrices: CoNet's regulariser sum_l ||H_l||_F (conet.py:198-201) ---------
+// torch runs it as a reduction + an add per matrix forward and four element-wise kernels per matrix backward (28 launches of
+// 2-7 us in a CoNet step); here: one launch each way.  Forward is ONE CTA going through the matrices in order (20 k elements
+// at the yaml stack), so the sums have a fixed order.
+constexpr int kMaxFrob = 8;
+struct FrobArgs {
+  const float* mat[kMaxFrob];
+  float* dst[kMaxFrob];
+  int64_t count[kMaxFrob];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) frob_sum_fwd_kernel(FrobArgs a, float* __restrict__ norms, float* __restrict__ out) {
+  __shared__ float smem[8];
+  float total = 0.f;
+  for (int l = 0; l < a.n; ++l) {
+    float acc[1] = {0.f};
+    for (int64_t i = threadIdx.x; i < a.count[l]; i += blockDim.x) {
+      const float v = a.mat[l][i];
+      acc[0] += v * v;
+    }
+    block_sum<1>(acc, smem);
+    if (threadIdx.x == 0) {
+      const float nrm = sqrtf(acc[0]);
+      norms[l] = nrm;
+      total += nrm;
+    }
+  }
+  if (threadIdx.x == 0) out[0] = total;
+}
+
+// d(sum_l ||H_l||_F)/dH_l = H_l / ||H_l||_F (torch: 0 where the norm is 0), times the upstream gradient
+__global__ void __launch_bounds__(256) frob_sum_bwd_kernel(FrobArgs a, const float* __restrict__ norms,
+                                                           const float* __restrict__ grad_loss) {
+  const float g = grad_loss ? __ldg(grad_loss) : 1.f;
+  for (int l = 0; l < a.n; ++l) {
+    const float nrm = norms[l];
+    const float sc = nrm > 0.f ? g / nrm : 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.count[l]; i += (int64_t)gridDim.x * blockDim.x)
+      a.dst[l][i] = sc * a.mat[l][i];
+  }
+}
+
 // ---- select + dot: score[b] = ((sel_ids[b] < n_overlap) ? mapped[b,:] : tgt_tab[sel_ids[b],:]) . other_tab[other_ids[b],:]
 template <int VEC>
 __global__ void __launch_bounds__(256) select_dot_kernel(const float* __restrict__ mapped, const float* __restrict__ tgt_tab,
@@ -578,6 +621,46 @@ int xdr_bce_logit_bwd(const float* prob, const float* label, int64_t count, cons
   XDR_REQUIRE(count > 0, "xdr_bce_logit_bwd: count must be positive");
   XDR_REQUIRE(prob && label && dlogit, "xdr_bce_logit_bwd: null pointer");
   XDR_LAUNCH((bce_logit_bwd_kernel), ew_grid(count, 256), 256, 0, (cudaStream_t)stream, prob, label, count, grad_loss, dlogit);
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+static int frob_args(const char* fn, const float* const* mats, float* const* dsts, const int64_t* counts, int n_mats,
+                     FrobArgs* a) {
+  XDR_REQUIRE(n_mats > 0 && n_mats <= kMaxFrob, "%s: n_mats=%d must be in [1, %d]", fn, n_mats, kMaxFrob);
+  XDR_REQUIRE(mats && counts && (dsts != nullptr || a->n == 0), "%s: null pointer", fn);
+  a->n = n_mats;
+  for (int l = 0; l < n_mats; ++l) {
+    XDR_REQUIRE(mats[l] && counts[l] > 0 && (dsts == nullptr || dsts[l]), "%s: matrix %d is null or empty", fn, l);
+    a->mat[l] = mats[l];
+    a->dst[l] = dsts ? dsts[l] : nullptr;
+    a->count[l] = counts[l];
+  }
+  return XDR_OK;
+}
+
+int xdr_frob_sum_fwd(const float* const* mats_host, const int64_t* counts_host, int n_mats, float* norms, float* out,
+                     xdr_stream_t stream) {
+  FrobArgs a;
+  a.n = 0;   // (no destinations on the way forward)
+  const int rc = frob_args("xdr_frob_sum_fwd", mats_host, nullptr, counts_host, n_mats, &a);
+  if (rc != XDR_OK) return rc;
+  XDR_REQUIRE(norms && out, "xdr_frob_sum_fwd: null pointer");
+  XDR_LAUNCH((frob_sum_fwd_kernel), 1, 256, 0, (cudaStream_t)stream, a, norms, out);
+  XDR_LAUNCH_OK();
+  return XDR_OK;
+}
+
+int xdr_frob_sum_bwd(const float* const* mats_host, const int64_t* counts_host, int n_mats, const float* norms,
+                     const float* grad_loss, float* const* dsts_host, xdr_stream_t stream) {
+  FrobArgs a;
+  a.n = 1;   // (destinations required)
+  XDR_REQUIRE(dsts_host && norms, "xdr_frob_sum_bwd: null pointer");
+  const int rc = frob_args("xdr_frob_sum_bwd", mats_host, dsts_host, counts_host, n_mats, &a);
+  if (rc != XDR_OK) return rc;
+  int64_t most = 0;
+  for (int l = 0; l < n_mats; ++l) most = counts_host[l] > most ? counts_host[l] : most;
+  XDR_LAUNCH((frob_sum_bwd_kernel), ew_grid(most, 256), 256, 0, (cudaStream_t)stream, a, norms, grad_loss);
   XDR_LAUNCH_OK();
   return XDR_OK;
 }

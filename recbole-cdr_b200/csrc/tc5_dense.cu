@@ -361,28 +361,35 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_bwd_weight_kernel(const 
 
 #endif  // __CUDACC__ || XDR_EMU
 
-// 0 (default): fp32 FMA kernels (dense.cu) for every shape; 1: tcgen05 for the shapes this file takes.  Measured on a B200
-// (scripts/bench_dense_engines.py, profiles/r2_dense_engines.jsonl): per call the two engines tie at the model shapes of
-// BASELINE.json (6 .. 50 us, both bound by the dependent chain stage -> product -> epilogue of ONE 128-row tile per SM, not by
-// the tensor pipe), so the validated tcgen05 engine is opt-in until it is pipelined across tiles.
-static int env_dense_engine() {   // XDR_DENSE_ENGINE=1 in the environment switches the engine on without a call (test sweeps)
+// 0 (default): fp32 FMA kernels (dense.cu) for every shape; 1: tcgen05 for every shape this file takes; 2: tcgen05 for the
+// calls it measured FASTER on a B200 (profiles/r2_dense_engines_fwd2_tiles.jsonl: forward and input gradient of wide layers --
+// CoNet's layer 0, 256(+256) -> 64: 47.4 vs 51.5 us and 18.7 vs 25.0 us; it loses or ties on narrow layers and on every weight
+// gradient), fp32 tiles for the rest.  Per call both engines are bound by the dependent chain stage -> product -> epilogue of
+// ONE 128-row tile per SM, not by the tensor pipe, so the validated tcgen05 engine stays opt-in until it is pipelined across
+// tiles.
+static int env_dense_engine() {   // XDR_DENSE_ENGINE=1|2 in the environment switches the engine on without a call (test sweeps)
   const char* e = getenv("XDR_DENSE_ENGINE");
-  return (e && e[0] == '1') ? 1 : 0;
+  return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
 }
 static int g_dense_engine = env_dense_engine();
 
 static bool d5_shape_ok(int64_t M, int N, int K) {
   return M >= kD5Rows && N % 16 == 0 && N >= 16 && N <= 128 && K % 16 == 0 && K >= 16 && K <= 256 && (kD5Threads % (N / 8)) == 0;
 }
+// does the engine setting send this call to tcgen05?  (what: 0 forward, 1 input gradient, 2 weight gradient)
+static bool d5_wanted(int what, int N, int K) {
+  if (g_dense_engine == 1) return true;
+  return g_dense_engine == 2 && what != 2 && K >= 192 && N >= 64;
+}
 
 bool tc5_dense_fwd_ok(const float* X, const float* W, const float* X2, const float* W2, const float* Y, int64_t M, int N, int K) {
-  return g_dense_engine == 1 && d5_shape_ok(M, N, K) && aligned16(X) && aligned16(W) && aligned16(Y) && aligned16(X2) && aligned16(W2);
+  return d5_wanted(0, N, K) && d5_shape_ok(M, N, K) && aligned16(X) && aligned16(W) && aligned16(Y) && aligned16(X2) && aligned16(W2);
 }
 bool tc5_dense_bwd_input_ok(const float* dZ, const float* W, const float* dX, int64_t M, int N, int K) {
-  return g_dense_engine == 1 && d5_shape_ok(M, N, K) && aligned16(dZ) && aligned16(W) && aligned16(dX);
+  return d5_wanted(1, N, K) && d5_shape_ok(M, N, K) && aligned16(dZ) && aligned16(W) && aligned16(dX);
 }
 bool tc5_dense_bwd_weight_ok(const float* dZ, const float* X, const float* dW, int64_t M, int N, int K) {
-  return g_dense_engine == 1 && d5_shape_ok(M, N, K) && aligned16(dZ) && aligned16(X) && aligned16(dW);
+  return d5_wanted(2, N, K) && d5_shape_ok(M, N, K) && aligned16(dZ) && aligned16(X) && aligned16(dW);
 }
 
 // raises a kernel's dynamic shared-memory limit when a launch needs more than any launch before it (once per size, not per call)
@@ -439,11 +446,11 @@ int tc5_dense_bwd_weight(const float* dZ, const float* X, const int64_t* mask_id
 
 extern "C" {
 
-// 1: dense layers whose shapes qualify run on tcgen05 (bf16x6); 0 (default): always the fp32 FMA kernels.  Returns the previous
-// setting.
+// 1: dense layers whose shapes qualify run on tcgen05 (bf16x6); 2: only the calls tcgen05 measured faster (forward / input
+// gradient of wide layers); 0 (default): always the fp32 FMA kernels.  Returns the previous setting.
 int xdr_set_dense_engine(int engine) {
   const int prev = xdr::g_dense_engine;
-  xdr::g_dense_engine = engine ? 1 : 0;
+  xdr::g_dense_engine = (engine == 1 || engine == 2) ? engine : 0;
   return prev;
 }
 

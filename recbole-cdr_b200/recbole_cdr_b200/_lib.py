@@ -42,6 +42,8 @@ PROTOTYPES = {
     'xdr_mse_rows_bwd': (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_f32, c_vp, c_vp, c_vp]),
     'xdr_bce_logit_fwd': (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'xdr_bce_logit_bwd': (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    'xdr_frob_sum_fwd': (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
+    'xdr_frob_sum_bwd': (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp]),
     'xdr_set_coop_launch': (c_int, [c_int]),
     'xdr_steps_workspace_bytes': (c_sz, [c_int]),
     'xdr_train_steps': (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int,

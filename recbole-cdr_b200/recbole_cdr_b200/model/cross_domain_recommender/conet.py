@@ -4,6 +4,8 @@ Per tower pass: 2 concat-gathers (4 table reads) -> L cross-stitch layers, each 
 ``relu(W x + b + m * (x_other H_l))`` (the reference does 2 GEMMs, a boolean-indexed in-place add and a ReLU per
 tower per layer, conet.py:118-138) -> output unit fused with BCE.  Same parameters and ``state_dict`` keys
 (``source_crossunit_linear.{l}``, ``target_crossunit_linear.{l}``, ``crossparas.{l}``, ``*_outputunit.0``)."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -51,6 +53,10 @@ class CoNet(CrossDomainRecommender):
         self.apply(xavier_normal_initialization)
         # opt-in: one tensor-core kernel per tower pass (tc_conet.cu) instead of the composed dense-layer kernels
         self.use_fused_conet = bool(config['xdr_fused_conet']) if 'xdr_fused_conet' in config else False
+        # calculate_loss runs the source-batch and the target-batch tower passes as one pass over the stacked rows
+        # (``xdr_stack_passes: False`` / XDR_CONET_STACK=0 keeps two passes)
+        self.stack_passes = bool(config['xdr_stack_passes']) if 'xdr_stack_passes' in config else \
+            os.environ.get('XDR_CONET_STACK', '1') != '0'
 
     def _fused_ok(self):
         return self.use_fused_conet and ops.conet_fused_supported([2 * self.latent_dim] + self.cross_layers, self.latent_dim)
@@ -79,30 +85,47 @@ class CoNet(CrossDomainRecommender):
     def cross_parameters(dims):
         return nn.ModuleList([nn.Linear(a, b, bias=False) for a, b in zip(dims[:-1], dims[1:])])
 
-    def _towers(self, user, item, want):
-        """Both towers through the cross-stitch stack (conet.py:105-138); returns the logit [B] of tower ``want``."""
+    def _mask(self, user, item):
+        """The overlapped rows of a batch, as (ids, bound): ``ids < bound`` (conet.py:113-116)."""
+        if self.mode == 'overlap_users':
+            return user.contiguous(), self.overlapped_num_users
+        return item.contiguous(), self.overlapped_num_items
+
+    def _stack(self, user, item):
+        """Gathers + every cross-stitch layer but the last (conet.py:105-138), both towers; returns (x_s, x_t, mask ids, bound)."""
         x_s = ops.GatherConcat.apply(self.source_user_embedding.weight, self.source_item_embedding.weight, user, item)
         x_t = ops.GatherConcat.apply(self.target_user_embedding.weight, self.target_item_embedding.weight, user, item)
-        if self.mode == 'overlap_users':
-            mask_ids, mask_lt = user, self.overlapped_num_users
-        else:
-            mask_ids, mask_lt = item, self.overlapped_num_items
-        mask_ids = mask_ids.contiguous()
-        n_layers = len(self.source_crossunit_linear)
-        for l in range(n_layers):
+        mask_ids, mask_lt = self._mask(user, item)
+        for l in range(len(self.source_crossunit_linear) - 1):
             fs, ft, h = self.source_crossunit_linear[l], self.target_crossunit_linear[l], self.crossparas[l].weight
-            last = l == n_layers - 1
-            h_s = h_t = None
-            if not last or want == 'source':
-                h_s = ops.dense(x_s, fs.weight, fs.bias, _lib.ACT_RELU, x_t, h, mask_ids, mask_lt)
-            if not last or want == 'target':
-                h_t = ops.dense(x_t, ft.weight, ft.bias, _lib.ACT_RELU, x_s, h, mask_ids, mask_lt)
-            x_s, x_t = h_s, h_t
+            x_s, x_t = ops.cross_pair(x_s, x_t, fs.weight, fs.bias, ft.weight, ft.bias, h, mask_ids, mask_lt, _lib.ACT_RELU)
+        return x_s, x_t, mask_ids, mask_lt
+
+    def _head(self, x_s, x_t, mask_ids, mask_lt, want):
+        """Last cross-stitch layer of tower ``want`` only (the other tower's last layer feeds nothing) + its output unit."""
+        h = self.crossparas[-1].weight
         if want == 'source':
-            out = self.source_outputunit[0]
-            return ops.dense(x_s, out.weight, out.bias, _lib.ACT_NONE).reshape(-1)
-        out = self.target_outputunit[0]
-        return ops.dense(x_t, out.weight, out.bias, _lib.ACT_NONE).reshape(-1)
+            fc, out, x, x_other = self.source_crossunit_linear[-1], self.source_outputunit[0], x_s, x_t
+        else:
+            fc, out, x, x_other = self.target_crossunit_linear[-1], self.target_outputunit[0], x_t, x_s
+        x = ops.dense(x, fc.weight, fc.bias, _lib.ACT_RELU, x_other, h, mask_ids, mask_lt)
+        return ops.dense(x, out.weight, out.bias, _lib.ACT_NONE).reshape(-1)
+
+    def _towers(self, user, item, want):
+        """Both towers through the cross-stitch stack (conet.py:105-138); returns the logit [B] of tower ``want``."""
+        return self._head(*self._stack(user, item), want)
+
+    def _both_passes(self, s_user, s_item, t_user, t_item):
+        """``source_forward(source batch)`` and ``target_forward(target batch)`` of ``calculate_loss`` (conet.py:194-195) in ONE
+        pass: the two tower passes apply the same gathers and the same layers (same weights) to different rows up to the last
+        layer, so the rows of the two batches are stacked -- half the launches, twice the rows per launch -- and split again
+        where the passes differ (last layer + output unit of the wanted tower).  Same sums, row for row."""
+        s_user, s_item, t_user, t_item = (t.reshape(-1) for t in (s_user, s_item, t_user, t_item))
+        n_s, n_t = s_user.numel(), t_user.numel()
+        x_s, x_t, mask_ids, mask_lt = self._stack(torch.cat([s_user, t_user]), torch.cat([s_item, t_item]))
+        (xs_s, xs_t), (xt_s, xt_t) = x_s.split([n_s, n_t]), x_t.split([n_s, n_t])
+        m_s, m_t = mask_ids.split([n_s, n_t])
+        return self._head(xs_s, xt_s, m_s, mask_lt, 'source'), self._head(xs_t, xt_t, m_t, mask_lt, 'target')
 
     def source_forward(self, user, item):
         return torch.sigmoid(self._towers(user, item, 'source'))
@@ -130,13 +153,21 @@ class CoNet(CrossDomainRecommender):
             loss_t = self._fused_tower_loss(interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID],
                                             interaction[self.TARGET_LABEL], 'target')
         else:
-            logit_s = self._towers(interaction[self.SOURCE_USER_ID], interaction[self.SOURCE_ITEM_ID], 'source')
-            logit_t = self._towers(interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID], 'target')
+            if self.stack_passes:
+                logit_s, logit_t = self._both_passes(interaction[self.SOURCE_USER_ID], interaction[self.SOURCE_ITEM_ID],
+                                                     interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID])
+            else:
+                logit_s = self._towers(interaction[self.SOURCE_USER_ID], interaction[self.SOURCE_ITEM_ID], 'source')
+                logit_t = self._towers(interaction[self.TARGET_USER_ID], interaction[self.TARGET_ITEM_ID], 'target')
             loss_s, _ = ops.bce_logit(logit_s, interaction[self.SOURCE_LABEL])
             loss_t, _ = ops.bce_logit(logit_t, interaction[self.TARGET_LABEL])
-        reg_loss = 0
-        for para in self.crossparas:
-            reg_loss = reg_loss + torch.norm(para.weight)
+        hs = [para.weight for para in self.crossparas]
+        if len(hs) <= ops.FrobSum.MAX_MATS:
+            reg_loss = ops.frob_sum(hs)     # one launch each way (torch: 7 kernels per matrix)
+        else:
+            reg_loss = 0
+            for h in hs:
+                reg_loss = reg_loss + torch.norm(h)
         return loss_s + loss_t + reg_loss
 
     def predict(self, interaction):

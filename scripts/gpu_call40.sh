@@ -1,0 +1,32 @@
+#!/bin/bash
+# call 40: CoNet BOTH step as one stacked pass (ops.cross_pair, ops.frob_sum), dense engine 2 -- whole GPU suite on the new code,
+# smoke, the default bench line, then the conet_5m step in its forms and one ncu launch list of the new step
+set -u
+OUT=gpurun_out/c40
+mkdir -p $OUT
+say() { echo "$1" | tee -a $OUT/summary.txt; }
+T0=$(date +%s)
+el() { echo $(( $(date +%s) - T0 ))s; }
+timeout 600 python -m pytest tests/ -q -m gpu --timeout 300 -p no:cacheprovider > $OUT/gpu_suite.log 2>&1; say "gpu suite rc=$? $(el)"
+tail -3 $OUT/gpu_suite.log; grep -E "^(FAILED|ERROR)" $OUT/gpu_suite.log | head -20
+timeout 200 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > $OUT/smoke.log 2>&1; say "smoke rc=$? $(el)"
+tail -1 $OUT/smoke.log
+timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 > $OUT/bench_k20.json 2> $OUT/bench_k20.err; say "bench default rc=$? $(el)"
+timeout 300 python bench.py --workload conet_5m --steps 10 --warmup 3 --repeats 5 > $OUT/conet_stacked.json 2> $OUT/conet_stacked.err; say "conet stacked (default) rc=$? $(el)"
+XDR_CONET_STACK=0 timeout 200 python bench.py --workload conet_5m --steps 10 --warmup 3 --repeats 5 --no-cpu-baseline > $OUT/conet_two_pass.json 2> $OUT/conet_two_pass.err; say "conet two passes rc=$? $(el)"
+timeout 200 python bench.py --workload conet_5m --steps 10 --warmup 3 --repeats 5 --no-cpu-baseline --dense-engine 2 > $OUT/conet_stacked_e2.json 2> $OUT/conet_stacked_e2.err; say "conet stacked engine 2 rc=$? $(el)"
+timeout 200 python bench.py --workload conet_5m --steps 10 --warmup 3 --repeats 5 --no-cpu-baseline --dense-engine 1 > $OUT/conet_stacked_e1.json 2> $OUT/conet_stacked_e1.err; say "conet stacked engine 1 rc=$? $(el)"
+python - <<PY
+import json
+for f in ('bench_k20', 'conet_stacked', 'conet_two_pass', 'conet_stacked_e2', 'conet_stacked_e1'):
+    try:
+        d = json.loads(open('$OUT/' + f + '.json').read().strip().splitlines()[-1])
+        print(f, 'value %.4e us/step %.2f [%s .. %s] frac %.4f e2e %s launches %s loss %s' % (
+            d['value'], d['ms_per_step'] * 1e3, d['timing'].get('min_ms'), d['timing'].get('max_ms'), d['roofline']['frac'],
+            d.get('e2e') and '%.3e' % d['e2e']['value'], d.get('gpu_launches'), d.get('loss_mean')))
+    except Exception as e:
+        print(f, 'ERR', e, open('$OUT/' + f + '.err').read()[-600:])
+PY
+timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/conet_launches_ncu.csv \
+  python bench.py --workload conet_5m --steps 2 --warmup 3 --repeats 1 --no-cpu-baseline > $OUT/conet_ncu.log 2>&1; say "ncu launch list rc=$? $(el)"
+cat $OUT/summary.txt

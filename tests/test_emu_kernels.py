@@ -101,6 +101,17 @@ def test_mse_rows_and_bce_logit():
     G.test_mse_rows_and_bce_logit()
 
 
+@pytest.mark.parametrize('shapes', [[(64, 256), (32, 64), (16, 32), (8, 16)], [(1, 1)], [(5, 3), (7, 1), (30, 33)], [(2, 2)] * 8])
+def test_frob_sum(shapes):
+    G.test_frob_sum(shapes)
+
+
+def test_frob_sum_refuses_more_matrices_than_the_launch_carries():
+    from recbole_cdr_b200 import _lib, ops
+    with pytest.raises(_lib.XdrError, match='n_mats'):
+        ops.frob_sum([torch.ones(2, 2) for _ in range(9)])
+
+
 def test_gather_max2_concat_fwd_bwd():
     G.test_gather_max2_concat_fwd_bwd()
 

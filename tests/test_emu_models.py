@@ -136,6 +136,48 @@ def test_conet_composed(tag):
         torch.testing.assert_close(m.predict(batch), g.t('predict'), rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize('tag', ['users', 'items'])
+def test_conet_two_pass_form_still_matches_the_golden(tag):
+    """``xdr_stack_passes: False`` keeps one tower pass per domain batch (the form the stacked pass replaced)."""
+    from recbole_cdr_b200.model.cross_domain_recommender.conet import CoNet
+    g = Golden(f'conet_{tag}')
+    with emu_util.patched_ops():
+        m = build_cpu(CoNet, g, dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8], xdr_stack_passes=False))
+        assert not m.stack_passes
+        check(m, g, cpu_batch(g))
+
+
+@pytest.mark.parametrize('n_s,n_t', [(37, 64), (64, 5), (1, 1)])
+def test_conet_stacked_pass_equals_two_passes_on_ragged_halves(n_s, n_t):
+    """The two halves of a BOTH batch may differ in length on the last batch (dataloader.py:148-162): the stacked pass splits
+    at the right row (odd row counts: the second half's views start at unaligned row offsets)."""
+    from recbole_cdr_b200.data import Interaction
+    from recbole_cdr_b200.model.cross_domain_recommender.conet import CoNet
+    g = Golden('conet_users')
+    b = cpu_batch(g)
+    gen = torch.Generator().manual_seed(n_s * 100 + n_t)
+    pick = lambda t, n: t[torch.randint(0, t.numel(), (n,), generator=gen)]
+    batch = {}
+    for dom, n in (('source', n_s), ('target', n_t)):
+        for k in b.columns:
+            if k.startswith(dom):
+                batch[k] = pick(b[k], n)
+    batch = Interaction(batch)
+    res = []
+    with emu_util.patched_ops():
+        for stacked in (True, False):
+            m = build_cpu(CoNet, g, dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8],
+                                         xdr_stack_passes=stacked))
+            m.zero_grad()
+            loss = m.calculate_loss(batch)
+            loss.backward()
+            res.append((loss.detach().clone(), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=1e-6, atol=0)
+    assert res[0][1].keys() == res[1][1].keys()
+    for n in res[0][1]:
+        torch.testing.assert_close(res[0][1][n], res[1][1][n], rtol=1e-5, atol=1e-7, msg=lambda s: f'grad {n}: {s}')
+
+
 def test_dtcdr_composed():
     from recbole_cdr_b200.model.cross_domain_recommender.dtcdr import DTCDR
     g = Golden('dtcdr_neumf')

@@ -78,3 +78,65 @@ def test_dense_engine_switch_and_fallback_shapes():
                 torch.testing.assert_close(ops.dense(x, w, None, 0), x @ w.t(), rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(y1, y0, rtol=1e-4, atol=1e-4)
         assert not torch.equal(y1, y0)      # different arithmetic (bf16x6 on tensor cores vs fp32 FMA): the switch switches
+
+
+def test_engine_2_takes_only_the_wide_forward_and_input_gradient():
+    """xdr_set_dense_engine(2): tcgen05 where it measured faster on a B200 (K >= 192 and N >= 64: forward and input gradient),
+    the fp32 tiles for narrow layers and for every weight gradient -- told apart by whose arithmetic the result carries."""
+    g = torch.Generator().manual_seed(5)
+    dY = {}
+    with emu_util.patched_ops(sms=2) as ops:
+        def run(e, K, N):
+            X, W = torch.randn(256, K, generator=torch.Generator().manual_seed(K + N)), \
+                torch.randn(N, K, generator=torch.Generator().manual_seed(K * N)) * 0.2
+            X.requires_grad_(True)
+            W.requires_grad_(True)
+            d = dY.setdefault((K, N), torch.randn(256, N, generator=g))
+            with _engine(e):
+                Y = ops.dense(X, W, None, 0)
+                Y.backward(d)
+            return Y.detach(), X.grad, W.grad
+        wide = {e: run(e, 256, 64) for e in (0, 1, 2)}
+        assert torch.equal(wide[2][0], wide[1][0]) and not torch.equal(wide[2][0], wide[0][0])   # forward: tcgen05
+        assert torch.equal(wide[2][1], wide[1][1]) and not torch.equal(wide[2][1], wide[0][1])   # input gradient: tcgen05
+        torch.testing.assert_close(wide[2][2], wide[0][2], rtol=1e-5, atol=1e-5)                  # weight gradient: fp32 tiles
+        assert not torch.equal(wide[1][2], wide[0][2])
+        narrow = {e: run(e, 64, 32) for e in (0, 1, 2)}
+        assert torch.equal(narrow[2][0], narrow[0][0]) and torch.equal(narrow[2][1], narrow[0][1])   # narrow layer: fp32 tiles
+        assert not torch.equal(narrow[1][0], narrow[0][0])
+
+
+@pytest.mark.parametrize('engine', [0, 1])
+@pytest.mark.parametrize('M,N,K', [(200, 32, 64), (129, 16, 32)])
+def test_cross_pair_node_equals_two_dense_nodes(engine, M, N, K):
+    """ops.cross_pair (both directions of a cross-stitch layer as one autograd node: the second input-gradient product
+    ACCUMULATES into the first one's result, both dH products add into one destination) against two ops.dense nodes whose
+    gradient halves autograd adds -- on both engines (the accumulating input-gradient form of each)."""
+    g = torch.Generator().manual_seed(M + N + K + engine)
+    mk = lambda *s, sc=1.0: torch.randn(*s, generator=g) * sc
+    base = [mk(M, K, sc=0.5), mk(M, K, sc=0.5), mk(N, K, sc=0.2), mk(N, sc=0.1), mk(N, K, sc=0.2), mk(N, sc=0.1), mk(N, K, sc=0.2)]
+    ids = torch.randint(0, 100, (M,), generator=g)
+    d_s, d_t = mk(M, N), mk(M, N)
+    res = []
+    with emu_util.patched_ops(sms=2) as ops, _engine(engine):
+        for pair in (True, False):
+            x_s, x_t, Ws, bs, Wt, bt, H = [t.clone().requires_grad_(True) for t in base]
+            if pair:
+                h_s, h_t = ops.cross_pair(x_s, x_t, Ws, bs, Wt, bt, H, ids, 40, 1)
+            else:
+                h_s = ops.dense(x_s, Ws, bs, 1, x_t, H, ids, 40)
+                h_t = ops.dense(x_t, Wt, bt, 1, x_s, H, ids, 40)
+            torch.autograd.backward([h_s, h_t], [d_s, d_t])
+            res.append([h_s.detach(), h_t.detach()] + [t.grad for t in (x_s, x_t, Ws, bs, Wt, bt, H)])
+        # one output unused: its half of every gradient is absent, not garbage
+        x_s, x_t, Ws, bs, Wt, bt, H = [t.clone().requires_grad_(True) for t in base]
+        h_s, _ = ops.cross_pair(x_s, x_t, Ws, bs, Wt, bt, H, ids, 40, 1)
+        h_s.backward(d_s)
+        y_s, y_t, Vs, cs, Vt, ct, G = [t.clone().requires_grad_(True) for t in base]
+        ops.dense(y_s, Vs, cs, 1, y_t, G, ids, 40).backward(d_s)
+        for a, b in ((x_s, y_s), (x_t, y_t), (Ws, Vs), (bs, cs), (H, G)):
+            torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-6)
+        assert Wt.grad is None or not bool(Wt.grad.any())
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    for a, b in zip(res[0][2:], res[1][2:]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)

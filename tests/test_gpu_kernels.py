@@ -292,6 +292,28 @@ def test_mse_rows_and_bce_logit():
     torch.testing.assert_close(zc.grad.cpu(), zr.grad, rtol=1e-4, atol=1e-9)
 
 
+@pytest.mark.parametrize('shapes', [[(64, 256), (32, 64), (16, 32), (8, 16)], [(1, 1)], [(5, 3), (7, 1), (300, 333)],
+                                    [(2, 2)] * 8])
+def test_frob_sum(shapes):
+    """CoNet's regulariser sum_l ||H_l||_F (conet.py:198-201) as one launch each way, against torch.norm per matrix: value,
+    gradients under an upstream factor, and the all-zero matrix (torch.norm's gradient there is 0, not NaN)."""
+    g = torch.Generator().manual_seed(len(shapes) * 17 + shapes[0][0])
+    mats = [torch.randn(*sh, generator=g) * 0.3 for sh in shapes]
+    if len(mats) > 1:
+        mats[1].zero_()
+    ref_in = [m.clone().requires_grad_(True) for m in mats]
+    ref = sum(torch.norm(m) for m in ref_in)
+    (ref * 0.37).backward()
+    got_in = [m.to(dev()).requires_grad_(True) for m in mats]
+    got = ops().frob_sum(got_in)
+    assert got.shape == ()
+    (got * 0.37).backward()
+    torch.testing.assert_close(got.detach().cpu(), ref.detach(), rtol=2e-6, atol=0)
+    for a, b in zip(got_in, ref_in):
+        assert bool(torch.isfinite(a.grad).all())
+        torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-5, atol=1e-9)
+
+
 def test_gather_max2_concat_fwd_bwd():
     su, tu, si, ti = (rand_table(200, 64, s) for s in (101, 102, 103, 104))
     tu[5] = su[5]  # exact ties: torch.maximum splits the gradient 0.5 / 0.5

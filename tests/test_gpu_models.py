@@ -104,6 +104,56 @@ def test_conet(tag):
     torch.testing.assert_close(pred.cpu(), g.t('predict'), rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize('tag', ['users', 'items'])
+def test_conet_two_pass_form(tag):
+    """``xdr_stack_passes: False``: one tower pass per domain batch (the stacked pass of ``calculate_loss`` is the default)."""
+    from recbole_cdr_b200.model.cross_domain_recommender.conet import CoNet
+    g = Golden(f'conet_{tag}')
+    m = build(CoNet, g, dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8], xdr_stack_passes=False))
+    assert not m.stack_passes
+    check_loss_and_grads(m, g, cuda_batch(g), grad_rtol=2e-4, grad_atol=2e-6)
+
+
+@pytest.mark.parametrize('engine', [0, 1])
+@pytest.mark.parametrize('n_s,n_t', [(37, 64), (1000, 333), (1, 1), (4096, 4096)])
+def test_conet_stacked_pass_equals_two_passes_on_ragged_halves(n_s, n_t, engine):
+    """The halves of a BOTH batch may differ in length (dataloader.py:148-162); odd row counts make the second half's views
+    start at rows that are not multiples of anything.  Both dense engines (fp32 tiles; tcgen05, whose input-gradient kernel
+    takes the accumulating form here for the first time in a model)."""
+    from recbole_cdr_b200 import _lib
+    from recbole_cdr_b200.data import Interaction
+    from recbole_cdr_b200.model.cross_domain_recommender.conet import CoNet
+    g = Golden('conet_users')
+    b = cuda_batch(g)
+    gen = torch.Generator().manual_seed(n_s * 100 + n_t)
+    batch = {}
+    for dom, n in (('source', n_s), ('target', n_t)):
+        sel = None
+        for k in b.columns:
+            if k.startswith(dom):
+                if sel is None:
+                    sel = torch.randint(0, b[k].numel(), (n,), generator=gen).cuda()
+                batch[k] = b[k][sel]
+    batch = Interaction(batch)
+    prev = _lib._lib.xdr_set_dense_engine(engine)
+    try:
+        res = []
+        for stacked in (True, False):
+            m = build(CoNet, g, dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8], xdr_stack_passes=stacked))
+            m.zero_grad()
+            loss = m.calculate_loss(batch)
+            loss.backward()
+            torch.cuda.synchronize()
+            res.append((loss.detach().cpu(), {n: p.grad.cpu() for n, p in m.named_parameters() if p.grad is not None}))
+    finally:
+        _lib._lib.xdr_set_dense_engine(prev)
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=2e-6, atol=0)
+    assert res[0][1].keys() == res[1][1].keys()
+    for n in res[0][1]:
+        scale = max(1e-6, float(res[1][1][n].abs().max()))
+        torch.testing.assert_close(res[0][1][n], res[1][1][n], rtol=1e-4, atol=2e-5 * scale, msg=lambda s: f'grad {n}: {s}')
+
+
 @pytest.mark.parametrize('fused', [True, False])
 def test_dtcdr(fused):
     from recbole_cdr_b200.model.cross_domain_recommender.dtcdr import DTCDR

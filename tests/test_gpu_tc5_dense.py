@@ -70,3 +70,36 @@ def test_engine_switch_changes_the_arithmetic_not_the_result():
     assert prev == 1   # (the fixture switched it on)
     torch.testing.assert_close(y1, y0, rtol=1e-4, atol=1e-4)
     assert not torch.equal(y1, y0)
+
+
+@pytest.mark.parametrize('engine', [0, 1, 2])
+@pytest.mark.parametrize('M,N,K', [(32768, 64, 256), (4097, 32, 64), (333, 16, 32)])
+def test_cross_pair_node_equals_two_dense_nodes(engine, M, N, K):
+    """ops.cross_pair (both directions of a CoNet cross-stitch layer as one autograd node; the second input-gradient product
+    accumulates into the first one's result -- ``xdr_dense_bwd_input(accumulate=1)`` -- and both dH products add into one
+    destination) against two ops.dense nodes, on every engine setting.  CPU twin: tests/test_emu_tc5_dense.py."""
+    from recbole_cdr_b200 import _lib, ops
+    g = torch.Generator().manual_seed(M + N + K + engine)
+    mk = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(dev())
+    base = [mk(M, K, sc=0.5), mk(M, K, sc=0.5), mk(N, K, sc=0.2), mk(N, sc=0.1), mk(N, K, sc=0.2), mk(N, sc=0.1), mk(N, K, sc=0.2)]
+    ids = torch.randint(0, 100, (M,), generator=g).to(dev())
+    d_s, d_t = mk(M, N), mk(M, N)
+    res = []
+    prev = _lib._lib.xdr_set_dense_engine(engine)
+    try:
+        for pair in (True, False):
+            x_s, x_t, Ws, bs, Wt, bt, H = [t.clone().requires_grad_(True) for t in base]
+            if pair:
+                h_s, h_t = ops.cross_pair(x_s, x_t, Ws, bs, Wt, bt, H, ids, 40, 1)
+            else:
+                h_s = ops.dense(x_s, Ws, bs, 1, x_t, H, ids, 40)
+                h_t = ops.dense(x_t, Wt, bt, 1, x_s, H, ids, 40)
+            torch.autograd.backward([h_s, h_t], [d_s, d_t])
+            torch.cuda.synchronize()
+            res.append([h_s.detach(), h_t.detach()] + [t.grad for t in (x_s, x_t, Ws, bs, Wt, bt, H)])
+    finally:
+        _lib._lib.xdr_set_dense_engine(prev)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    for nm, a, b in zip(('x_s', 'x_t', 'Ws', 'bs', 'Wt', 'bt', 'H'), res[0][2:], res[1][2:]):
+        scale = max(1e-6, float(b.abs().max()))   # (weight gradients are sums of atomics: order differs from run to run)
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5 * scale, msg=lambda s: f'd{nm}: {s}')

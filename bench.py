@@ -870,19 +870,20 @@ def run_model_step(args, dev, name):
     peak, peak_src = measured_peaks()
     if args.dense_engine >= 0:
         _lib._lib.xdr_set_dense_engine(int(args.dense_engine))
-    dense_engine = _lib._lib.xdr_set_dense_engine(0)          # (read back: the call returns the previous setting)
-    _lib._lib.xdr_set_dense_engine(dense_engine)
     from recbole_cdr_b200 import ops as _ops
     _ops.set_table_grad_mode('inplace')   # table gradients are scatter-added into persistent .grad buffers (no dense [N, D] temporaries)
     ds, cfg, make, units, phase = _model_workload(name, b, dev)
     if name == 'emcdr_map':
         if args.map_engine:   # default: the model's own choice ('auto': the tcgen05 map-step kernel where it applies)
             cfg['xdr_fused_mlp'] = False if args.map_engine == 'composed' else args.map_engine
+    if args.dense_engine >= 0:
+        cfg['xdr_dense_engine'] = int(args.dense_engine)   # (models that choose their layers' engine themselves: CoNet)
     torch.manual_seed(2022)
     with torch.device(dev):
         model = cls(cfg, ds)
     if phase:
         model.set_phase(phase)
+    dense_engine = getattr(model, 'dense_engine', max(0, args.dense_engine))
     n = W + R * K
     batches = [Interaction(make(s_)) for s_ in range(n)]
     # how many libxdr entry points one step goes through (each launches at least one kernel of this repository)

@@ -426,8 +426,9 @@ __global__ void bce_logit_bwd_kernel(const float* __restrict__ prob, const float
 
 // ---- sum of the Frobenius norms of a few small matrices: CoNet's regulariser sum_l ||H_l||_F (conet.py:198-201) ---------
 // torch runs it as a reduction + an add per matrix forward and four element-wise kernels per matrix backward (28 launches of
-// 2-7 us in a CoNet step); here: one launch each way.  Forward is ONE CTA going through the matrices in order (20 k elements
-// at the yaml stack), so the sums have a fixed order.
+// 2-7 us in a CoNet step); here: one launch each way.  Forward is ONE CTA of 1024 threads going through the matrices in order
+// (20 k elements at the yaml stack; first version: 256 threads, one scalar load per round = 64 dependent rounds, 37 us cold
+// under ncu), so the sums have a fixed order.
 constexpr int kMaxFrob = 8;
 struct FrobArgs {
   const float* mat[kMaxFrob];
@@ -436,14 +437,29 @@ struct FrobArgs {
   int n;
 };
 
-__global__ void __launch_bounds__(256) frob_sum_fwd_kernel(FrobArgs a, float* __restrict__ norms, float* __restrict__ out) {
-  __shared__ float smem[8];
+constexpr int kFrobThreads = 1024;
+__global__ void __launch_bounds__(kFrobThreads) frob_sum_fwd_kernel(FrobArgs a, float* __restrict__ norms, float* __restrict__ out) {
+  __shared__ float smem[kFrobThreads / 32];
   float total = 0.f;
   for (int l = 0; l < a.n; ++l) {
+    const float* __restrict__ m = a.mat[l];
+    const int64_t n = a.count[l];
     float acc[1] = {0.f};
-    for (int64_t i = threadIdx.x; i < a.count[l]; i += blockDim.x) {
-      const float v = a.mat[l][i];
-      acc[0] += v * v;
+    if (aligned16_dev(m)) {   // four independent 128-bit loads per thread and round: a 256 x 64 matrix is ONE round of loads
+      const int64_t n4 = n / 4;
+      for (int64_t i = threadIdx.x; i < n4; i += 4 * kFrobThreads) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t j = i + (int64_t)u * kFrobThreads;
+          v[u] = j < n4 ? ldg_row4(m, (int)j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[0] += dot4(v[u], v[u]);
+      }
+      for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += kFrobThreads) acc[0] += m[i] * m[i];
+    } else {
+      for (int64_t i = threadIdx.x; i < n; i += kFrobThreads) acc[0] += m[i] * m[i];
     }
     block_sum<1>(acc, smem);
     if (threadIdx.x == 0) {
@@ -646,7 +662,7 @@ int xdr_frob_sum_fwd(const float* const* mats_host, const int64_t* counts_host, 
   const int rc = frob_args("xdr_frob_sum_fwd", mats_host, nullptr, counts_host, n_mats, &a);
   if (rc != XDR_OK) return rc;
   XDR_REQUIRE(norms && out, "xdr_frob_sum_fwd: null pointer");
-  XDR_LAUNCH((frob_sum_fwd_kernel), 1, 256, 0, (cudaStream_t)stream, a, norms, out);
+  XDR_LAUNCH((frob_sum_fwd_kernel), 1, kFrobThreads, 0, (cudaStream_t)stream, a, norms, out);
   XDR_LAUNCH_OK();
   return XDR_OK;
 }

@@ -57,6 +57,13 @@ class CoNet(CrossDomainRecommender):
         # (``xdr_stack_passes: False`` / XDR_CONET_STACK=0 keeps two passes)
         self.stack_passes = bool(config['xdr_stack_passes']) if 'xdr_stack_passes' in config else \
             os.environ.get('XDR_CONET_STACK', '1') != '0'
+        # engine of the cross-stitch layers in calculate_loss (ops.dense_engine): 1 = tcgen05 (bf16x3 products, fp32-faithful) for
+        # every layer shape it takes, the fp32 tiles for the rest.  Measured on a B200 at BASELINE configs[2] (stacked pass,
+        # 2 x 16384 rows): 1005 us per step on engine 1, 1060 on engine 2, 1132 on engine 0 (profiles/r2_conet_stacked.md)
+        if 'xdr_dense_engine' in config:
+            self.dense_engine = int(config['xdr_dense_engine'])
+        else:
+            self.dense_engine = int(os.environ.get('XDR_DENSE_ENGINE') or 1)
 
     def _fused_ok(self):
         return self.use_fused_conet and ops.conet_fused_supported([2 * self.latent_dim] + self.cross_layers, self.latent_dim)
@@ -98,7 +105,8 @@ class CoNet(CrossDomainRecommender):
         mask_ids, mask_lt = self._mask(user, item)
         for l in range(len(self.source_crossunit_linear) - 1):
             fs, ft, h = self.source_crossunit_linear[l], self.target_crossunit_linear[l], self.crossparas[l].weight
-            x_s, x_t = ops.cross_pair(x_s, x_t, fs.weight, fs.bias, ft.weight, ft.bias, h, mask_ids, mask_lt, _lib.ACT_RELU)
+            x_s, x_t = ops.cross_pair(x_s, x_t, fs.weight, fs.bias, ft.weight, ft.bias, h, mask_ids, mask_lt, _lib.ACT_RELU,
+                                      self.dense_engine)
         return x_s, x_t, mask_ids, mask_lt
 
     def _head(self, x_s, x_t, mask_ids, mask_lt, want):
@@ -108,7 +116,7 @@ class CoNet(CrossDomainRecommender):
             fc, out, x, x_other = self.source_crossunit_linear[-1], self.source_outputunit[0], x_s, x_t
         else:
             fc, out, x, x_other = self.target_crossunit_linear[-1], self.target_outputunit[0], x_t, x_s
-        x = ops.dense(x, fc.weight, fc.bias, _lib.ACT_RELU, x_other, h, mask_ids, mask_lt)
+        x = ops.dense(x, fc.weight, fc.bias, _lib.ACT_RELU, x_other, h, mask_ids, mask_lt, self.dense_engine)
         return ops.dense(x, out.weight, out.bias, _lib.ACT_NONE).reshape(-1)
 
     def _towers(self, user, item, want):

@@ -311,12 +311,30 @@ def dot_score(user_tab, item_tab, user, item):
 # A4/A7/A14: dense layers
 # ------------------------------------------------------------------------------------------------------------------
 
+class dense_engine(object):
+    """``with ops.dense_engine(e):`` -- the dense entry points called inside run on engine ``e`` (``xdr_set_dense_engine``:
+    0 fp32 FMA tiles, 1 tcgen05 for every shape it takes, 2 tcgen05 where it measured faster per call); ``None`` leaves the
+    library's setting alone.  ``dense`` / ``cross_pair`` take the engine as an argument and re-apply it in their backward."""
+
+    def __init__(self, engine):
+        self.engine = engine
+
+    def __enter__(self):
+        self.prev = None if self.engine is None else _lib._lib.xdr_set_dense_engine(int(self.engine))
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            _lib._lib.xdr_set_dense_engine(self.prev)
+        return False
+
+
 class Dense(torch.autograd.Function):
     """``act(X W^T + b + mask * (X2 W2^T))``: nn.Linear + activation (emcdr.py:86-93, recbole MLPLayers dtcdr.py:61-67)
     and, with X2/W2/mask, one CoNet cross-stitch unit (conet.py:118-138, mask = ids < n_overlap, conet.py:113-116)."""
 
     @staticmethod
-    def forward(ctx, X, W, bias, X2, W2, mask_ids, mask_lt, act):
+    def forward(ctx, X, W, bias, X2, W2, mask_ids, mask_lt, act, engine=None):
         X = X.contiguous()
         _require_cuda_f32(X, 'X')
         _require_cuda_f32(W, 'W')
@@ -329,14 +347,20 @@ class Dense(torch.autograd.Function):
             if X2.shape != X.shape or W2.shape != W.shape:
                 raise ValueError('dense: cross operands must have the shapes of X and W')
         Y = torch.empty((M, N), dtype=torch.float32, device=X.device)
-        call('xdr_dense_fwd', ptr(X), ptr(W), ptr(bias), ptr(X2), ptr(W2), ptr(mask_ids), int(mask_lt), int(act), ptr(Y), M,
-             N, K, cur_stream())
+        with dense_engine(engine):
+            call('xdr_dense_fwd', ptr(X), ptr(W), ptr(bias), ptr(X2), ptr(W2), ptr(mask_ids), int(mask_lt), int(act), ptr(Y), M,
+                 N, K, cur_stream())
         ctx.save_for_backward(X, W, bias, X2, W2, mask_ids, Y)
-        ctx.mask_lt, ctx.act = int(mask_lt), int(act)
+        ctx.mask_lt, ctx.act, ctx.engine = int(mask_lt), int(act), engine
         return Y
 
     @staticmethod
     def backward(ctx, dY):
+        with dense_engine(ctx.engine):
+            return Dense._backward(ctx, dY)
+
+    @staticmethod
+    def _backward(ctx, dY):
         X, W, bias, X2, W2, mask_ids, Y = ctx.saved_tensors
         M, K = X.shape
         N = W.shape[0]
@@ -369,11 +393,11 @@ class Dense(torch.autograd.Function):
             if want_w2:
                 dW2 = parts[2][:W2.numel()].view_as(W2)
                 call('xdr_dense_bwd_weight', ptr(dZ), ptr(X2), ptr(mask_ids), ctx.mask_lt, ptr(dW2), None, M, N, K, s)
-        return dX, dW, db, dX2, dW2, None, None, None
+        return dX, dW, db, dX2, dW2, None, None, None, None
 
 
-def dense(X, W, bias=None, act=_lib.ACT_NONE, X2=None, W2=None, mask_ids=None, mask_lt=0):
-    return Dense.apply(X, W, bias, X2, W2, mask_ids, mask_lt, act)
+def dense(X, W, bias=None, act=_lib.ACT_NONE, X2=None, W2=None, mask_ids=None, mask_lt=0, engine=None):
+    return Dense.apply(X, W, bias, X2, W2, mask_ids, mask_lt, act, engine)
 
 
 class CrossPair(torch.autograd.Function):
@@ -385,7 +409,7 @@ class CrossPair(torch.autograd.Function):
     layer lives in one zero-filled block: 11 launches per layer backward instead of 15."""
 
     @staticmethod
-    def forward(ctx, x_s, x_t, Ws, bs, Wt, bt, H, mask_ids, mask_lt, act):
+    def forward(ctx, x_s, x_t, Ws, bs, Wt, bt, H, mask_ids, mask_lt, act, engine=None):
         x_s, x_t = x_s.contiguous(), x_t.contiguous()
         for t, nm in ((x_s, 'x_s'), (x_t, 'x_t'), (Ws, 'Ws'), (Wt, 'Wt'), (H, 'H')):
             _require_cuda_f32(t, nm)
@@ -397,17 +421,23 @@ class CrossPair(torch.autograd.Function):
         s = cur_stream()
         h_s = torch.empty((M, N), dtype=torch.float32, device=x_s.device)
         h_t = torch.empty((M, N), dtype=torch.float32, device=x_s.device)
-        call('xdr_dense_fwd', ptr(x_s), ptr(Ws), ptr(bs), ptr(x_t), ptr(H), ptr(mask_ids), int(mask_lt), int(act), ptr(h_s), M, N,
-             K, s)
-        call('xdr_dense_fwd', ptr(x_t), ptr(Wt), ptr(bt), ptr(x_s), ptr(H), ptr(mask_ids), int(mask_lt), int(act), ptr(h_t), M, N,
-             K, s)
+        with dense_engine(engine):
+            call('xdr_dense_fwd', ptr(x_s), ptr(Ws), ptr(bs), ptr(x_t), ptr(H), ptr(mask_ids), int(mask_lt), int(act), ptr(h_s), M,
+                 N, K, s)
+            call('xdr_dense_fwd', ptr(x_t), ptr(Wt), ptr(bt), ptr(x_s), ptr(H), ptr(mask_ids), int(mask_lt), int(act), ptr(h_t), M,
+                 N, K, s)
         ctx.save_for_backward(x_s, x_t, Ws, bs, Wt, bt, H, mask_ids, h_s, h_t)
-        ctx.mask_lt, ctx.act = int(mask_lt), int(act)
+        ctx.mask_lt, ctx.act, ctx.engine = int(mask_lt), int(act), engine
         ctx.set_materialize_grads(False)
         return h_s, h_t
 
     @staticmethod
     def backward(ctx, d_hs, d_ht):
+        with dense_engine(ctx.engine):
+            return CrossPair._backward(ctx, d_hs, d_ht)
+
+    @staticmethod
+    def _backward(ctx, d_hs, d_ht):
         x_s, x_t, Ws, bs, Wt, bt, H, mask_ids, h_s, h_t = ctx.saved_tensors
         M, K = x_s.shape
         N = Ws.shape[0]
@@ -461,11 +491,11 @@ class CrossPair(torch.autograd.Function):
                 call('xdr_dense_bwd_weight', ptr(dz_s), ptr(x_t), ptr(mask_ids), ctx.mask_lt, ptr(dH), None, M, N, K, s)
             if dz_t is not None:
                 call('xdr_dense_bwd_weight', ptr(dz_t), ptr(x_s), ptr(mask_ids), ctx.mask_lt, ptr(dH), None, M, N, K, s)
-        return d_xs, d_xt, dWs, dbs, dWt, dbt, dH, None, None, None
+        return d_xs, d_xt, dWs, dbs, dWt, dbt, dH, None, None, None, None
 
 
-def cross_pair(x_s, x_t, Ws, bs, Wt, bt, H, mask_ids, mask_lt, act=_lib.ACT_RELU):
-    return CrossPair.apply(x_s, x_t, Ws, bs, Wt, bt, H, mask_ids, mask_lt, act)
+def cross_pair(x_s, x_t, Ws, bs, Wt, bt, H, mask_ids, mask_lt, act=_lib.ACT_RELU, engine=None):
+    return CrossPair.apply(x_s, x_t, Ws, bs, Wt, bt, H, mask_ids, mask_lt, act, engine)
 
 
 class MseRows(torch.autograd.Function):

@@ -140,3 +140,32 @@ def test_cross_pair_node_equals_two_dense_nodes(engine, M, N, K):
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     for a, b in zip(res[0][2:], res[1][2:]):
         torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_per_call_engine_reaches_the_backward_and_does_not_leak():
+    """``ops.dense(..., engine=e)`` / ``ops.cross_pair(..., engine=e)`` (how CoNet picks tcgen05 for its own layers): the forward
+    AND the backward launches -- which autograd runs later, outside the caller's code -- take engine ``e``; the library's own
+    setting is what it was before and after."""
+    import ctypes
+    g = torch.Generator().manual_seed(11)
+    X0, W0 = torch.randn(256, 64, generator=g) * 0.5, torch.randn(32, 64, generator=g) * 0.2
+    d = torch.randn(256, 32, generator=g)
+    L = emu_util.lib()
+    L.xdr_set_dense_engine.argtypes = [ctypes.c_int]
+
+    def run(ops, global_engine, call_engine):
+        X, W = X0.clone().requires_grad_(True), W0.clone().requires_grad_(True)
+        with _engine(global_engine):
+            Y = ops.dense(X, W, None, 1, engine=call_engine)
+            assert L.xdr_set_dense_engine(global_engine) == global_engine     # restored right after the forward launch
+            Y.backward(d)
+            assert L.xdr_set_dense_engine(global_engine) == global_engine
+        return Y.detach(), X.grad, W.grad
+
+    with emu_util.patched_ops(sms=2) as ops:
+        fma, tc5 = run(ops, 0, None), run(ops, 1, None)
+        assert not torch.equal(fma[0], tc5[0]) and not torch.equal(fma[2], tc5[2])
+        for a, b in zip(run(ops, 0, 1), tc5):      # per-call tcgen05 under a library default of fp32 tiles
+            assert torch.equal(a, b)
+        for a, b in zip(run(ops, 1, 0), fma):      # and the other way round
+            assert torch.equal(a, b)

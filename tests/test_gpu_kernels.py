@@ -305,6 +305,11 @@ def test_frob_sum(shapes):
     ref = sum(torch.norm(m) for m in ref_in)
     (ref * 0.37).backward()
     got_in = [m.to(dev()).requires_grad_(True) for m in mats]
+    # the last matrix as a view that starts 4 bytes into its buffer: the scalar (not 16-byte aligned) read path
+    pad = torch.zeros(mats[-1].numel() + 1, device=dev())
+    pad[1:] = mats[-1].reshape(-1).to(dev())
+    got_in[-1] = pad[1:].view(mats[-1].shape).detach().requires_grad_(True)
+    assert got_in[-1].data_ptr() % 16 != 0 and got_in[-1].is_contiguous()
     got = ops().frob_sum(got_in)
     assert got.shape == ()
     (got * 0.37).backward()

@@ -114,12 +114,12 @@ def test_conet_two_pass_form(tag):
     check_loss_and_grads(m, g, cuda_batch(g), grad_rtol=2e-4, grad_atol=2e-6)
 
 
-@pytest.mark.parametrize('engine', [0, 1])
+@pytest.mark.parametrize('engine', [0, 1, 2])
 @pytest.mark.parametrize('n_s,n_t', [(37, 64), (1000, 333), (1, 1), (4096, 4096)])
 def test_conet_stacked_pass_equals_two_passes_on_ragged_halves(n_s, n_t, engine):
     """The halves of a BOTH batch may differ in length (dataloader.py:148-162); odd row counts make the second half's views
-    start at rows that are not multiples of anything.  Both dense engines (fp32 tiles; tcgen05, whose input-gradient kernel
-    takes the accumulating form here for the first time in a model)."""
+    start at rows that are not multiples of anything.  Every dense engine of the cross-stitch layers (``xdr_dense_engine``:
+    fp32 tiles; tcgen05, whose input-gradient kernel takes the accumulating form in ``ops.cross_pair``; the per-call mix)."""
     from recbole_cdr_b200 import _lib
     from recbole_cdr_b200.data import Interaction
     from recbole_cdr_b200.model.cross_domain_recommender.conet import CoNet
@@ -135,23 +135,57 @@ def test_conet_stacked_pass_equals_two_passes_on_ragged_halves(n_s, n_t, engine)
                     sel = torch.randint(0, b[k].numel(), (n,), generator=gen).cuda()
                 batch[k] = b[k][sel]
     batch = Interaction(batch)
-    prev = _lib._lib.xdr_set_dense_engine(engine)
-    try:
-        res = []
-        for stacked in (True, False):
-            m = build(CoNet, g, dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8], xdr_stack_passes=stacked))
-            m.zero_grad()
-            loss = m.calculate_loss(batch)
-            loss.backward()
-            torch.cuda.synchronize()
-            res.append((loss.detach().cpu(), {n: p.grad.cpu() for n, p in m.named_parameters() if p.grad is not None}))
-    finally:
-        _lib._lib.xdr_set_dense_engine(prev)
-    torch.testing.assert_close(res[0][0], res[1][0], rtol=2e-6, atol=0)
+    res = []
+    for stacked in (True, False):
+        m = build(CoNet, g, dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8], xdr_stack_passes=stacked,
+                                 xdr_dense_engine=engine))
+        assert m.dense_engine == engine
+        m.zero_grad()
+        loss = m.calculate_loss(batch)
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((loss.detach().cpu(), {n: p.grad.cpu() for n, p in m.named_parameters() if p.grad is not None}))
+    assert _lib._lib.xdr_set_dense_engine(0) == 0     # the per-call engine never leaks into the library's setting
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=1e-5, atol=0)
     assert res[0][1].keys() == res[1][1].keys()
     for n in res[0][1]:
         scale = max(1e-6, float(res[1][1][n].abs().max()))
         torch.testing.assert_close(res[0][1][n], res[1][1][n], rtol=1e-4, atol=2e-5 * scale, msg=lambda s: f'grad {n}: {s}')
+
+
+def test_conet_default_engine_is_tcgen05_and_the_fp32_tiles_agree():
+    """CoNet's cross-stitch layers run on the tcgen05 dense engine by default (bf16x3 products, fp32-faithful): against the
+    golden (``test_conet``) and, here, against the same step on the fp32 FMA tiles -- different arithmetic, same result."""
+    from recbole_cdr_b200.data import Interaction
+    from recbole_cdr_b200.model.cross_domain_recommender.conet import CoNet
+    g = Golden('conet_users')
+    b = cuda_batch(g)
+    gen = torch.Generator().manual_seed(7)
+    batch = {}
+    for dom in ('source', 'target'):
+        sel = None
+        for k in b.columns:
+            if k.startswith(dom):
+                if sel is None:
+                    sel = torch.randint(0, b[k].numel(), (2048,), generator=gen).cuda()
+                batch[k] = b[k][sel]
+    batch = Interaction(batch)
+    res = []
+    for cfg in ({}, {'xdr_dense_engine': 0}):
+        m = build(CoNet, g, dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8], **cfg))
+        m.zero_grad()
+        loss = m.calculate_loss(batch)
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((m.dense_engine, loss.detach().cpu(), {n: p.grad.cpu() for n, p in m.named_parameters() if p.grad is not None}))
+    assert [r[0] for r in res] == [1, 0]
+    torch.testing.assert_close(res[0][1], res[1][1], rtol=1e-5, atol=0)
+    differs = False
+    for n in res[0][2]:
+        scale = max(1e-6, float(res[1][2][n].abs().max()))
+        torch.testing.assert_close(res[0][2][n], res[1][2][n], rtol=2e-4, atol=5e-5 * scale, msg=lambda s: f'grad {n}: {s}')
+        differs = differs or not torch.equal(res[0][2][n], res[1][2][n])
+    assert differs      # (the engines really differ: bf16x6 on tensor cores vs fp32 FMA)
 
 
 @pytest.mark.parametrize('fused', [True, False])

@@ -400,6 +400,50 @@ def dense(X, W, bias=None, act=_lib.ACT_NONE, X2=None, W2=None, mask_ids=None, m
     return Dense.apply(X, W, bias, X2, W2, mask_ids, mask_lt, act, engine)
 
 
+# Independent launches of one autograd node on parallel streams (fork from the current stream, join back into it; inside a
+# CUDA-graph capture the lanes become parallel branches of the graph).  0 = off: every launch on the current stream.
+# Only LAUNCHES go to the side streams -- every tensor is allocated on the current stream before the fork and used after the
+# join, so the caching allocator's per-stream pools never see a cross-stream free.
+CROSS_STREAMS = int(_os.environ.get('XDR_CROSS_STREAMS', '0'))
+_SIDE_STREAMS = {}
+
+
+def set_cross_streams(n: int) -> int:
+    """Number of streams ``cross_pair`` spreads its independent launches over (1 or 0: none); returns the previous setting."""
+    global CROSS_STREAMS
+    prev, CROSS_STREAMS = CROSS_STREAMS, max(0, int(n))
+    return prev
+
+
+def _run_lanes(device, lanes):
+    """Runs the callables of ``lanes``: lane 0 on the current stream, the others on side streams when CROSS_STREAMS > 1."""
+    n = min(CROSS_STREAMS, len(lanes))
+    if n <= 1 or device.type != 'cuda':
+        for lane in lanes:
+            lane()
+        return
+    main = torch.cuda.current_stream(device)
+    sides = _SIDE_STREAMS.setdefault(_lib._device_key(device), [])
+    while len(sides) < n - 1:
+        sides.append(torch.cuda.Stream(device=device))
+    used = []
+    for i, lane in enumerate(lanes):
+        k = i % n
+        if k == 0:
+            continue
+        st = sides[k - 1]
+        if st not in used:
+            st.wait_stream(main)
+            used.append(st)
+        with torch.cuda.stream(st):
+            lane()
+    for i, lane in enumerate(lanes):
+        if i % n == 0:
+            lane()
+    for st in used:
+        main.wait_stream(st)
+
+
 class CrossPair(torch.autograd.Function):
     """Both directions of one CoNet cross-stitch layer (conet.py:118-138) as ONE autograd node:
     ``h_s = act(x_s Ws^T + bs + m * (x_t H^T))``, ``h_t = act(x_t Wt^T + bt + m * (x_s H^T))`` with the SAME ``H`` in both.
@@ -422,10 +466,11 @@ class CrossPair(torch.autograd.Function):
         h_s = torch.empty((M, N), dtype=torch.float32, device=x_s.device)
         h_t = torch.empty((M, N), dtype=torch.float32, device=x_s.device)
         with dense_engine(engine):
-            call('xdr_dense_fwd', ptr(x_s), ptr(Ws), ptr(bs), ptr(x_t), ptr(H), ptr(mask_ids), int(mask_lt), int(act), ptr(h_s), M,
-                 N, K, s)
-            call('xdr_dense_fwd', ptr(x_t), ptr(Wt), ptr(bt), ptr(x_s), ptr(H), ptr(mask_ids), int(mask_lt), int(act), ptr(h_t), M,
-                 N, K, s)
+            _run_lanes(x_s.device, [
+                lambda: call('xdr_dense_fwd', ptr(x_s), ptr(Ws), ptr(bs), ptr(x_t), ptr(H), ptr(mask_ids), int(mask_lt), int(act),
+                             ptr(h_s), M, N, K, cur_stream()),
+                lambda: call('xdr_dense_fwd', ptr(x_t), ptr(Wt), ptr(bt), ptr(x_s), ptr(H), ptr(mask_ids), int(mask_lt), int(act),
+                             ptr(h_t), M, N, K, cur_stream())])
         ctx.save_for_backward(x_s, x_t, Ws, bs, Wt, bt, H, mask_ids, h_s, h_t)
         ctx.mask_lt, ctx.act, ctx.engine = int(mask_lt), int(act), engine
         ctx.set_materialize_grads(False)
@@ -461,36 +506,45 @@ class CrossPair(torch.autograd.Function):
         if sum(sizes):
             parts = torch.split(torch.zeros(sum(sizes), dtype=torch.float32, device=x_s.device), sizes)
 
-        def d_input(dz_own, W_own, dz_other):   # dX = dz_own W_own + m * (dz_other H)
+        # every destination is allocated here, on the current stream; the launches below may run on parallel streams (_run_lanes)
+        def d_input(dz_own, W_own, dz_other):   # dX = dz_own W_own + m * (dz_other H); returns (dX, its launches)
             if dz_own is None and dz_other is None:
-                return None
+                return None, None
             dX = torch.empty((M, K), dtype=torch.float32, device=x_s.device)
-            if dz_own is not None:
-                call('xdr_dense_bwd_input', ptr(dz_own), ptr(W_own), None, 0, ptr(dX), M, N, K, 0, s)
-            if dz_other is not None:
-                call('xdr_dense_bwd_input', ptr(dz_other), ptr(H), ptr(mask_ids), ctx.mask_lt, ptr(dX), M, N, K,
-                     0 if dz_own is None else 1, s)
-            return dX
 
-        d_xs = d_input(dz_s, Ws, dz_t) if needs[0] else None
-        d_xt = d_input(dz_t, Wt, dz_s) if needs[1] else None
+            def lane():
+                if dz_own is not None:
+                    call('xdr_dense_bwd_input', ptr(dz_own), ptr(W_own), None, 0, ptr(dX), M, N, K, 0, cur_stream())
+                if dz_other is not None:
+                    call('xdr_dense_bwd_input', ptr(dz_other), ptr(H), ptr(mask_ids), ctx.mask_lt, ptr(dX), M, N, K,
+                         0 if dz_own is None else 1, cur_stream())
+            return dX, lane
+
+        d_xs, lane_xs = d_input(dz_s, Ws, dz_t) if needs[0] else (None, None)
+        d_xt, lane_xt = d_input(dz_t, Wt, dz_s) if needs[1] else (None, None)
         dWs = dbs = dWt = dbt = dH = None
         if want[0]:
             dWs = parts[0][:Ws.numel()].view_as(Ws)
             dbs = parts[1][:bs.numel()].view_as(bs) if bs is not None else None
-            if dz_s is not None:
-                call('xdr_dense_bwd_weight', ptr(dz_s), ptr(x_s), None, 0, ptr(dWs), ptr(dbs), M, N, K, s)
         if want[1]:
             dWt = parts[2][:Wt.numel()].view_as(Wt)
             dbt = parts[3][:bt.numel()].view_as(bt) if bt is not None else None
-            if dz_t is not None:
-                call('xdr_dense_bwd_weight', ptr(dz_t), ptr(x_t), None, 0, ptr(dWt), ptr(dbt), M, N, K, s)
         if want[2]:
             dH = parts[4][:H.numel()].view_as(H)
-            if dz_s is not None:
-                call('xdr_dense_bwd_weight', ptr(dz_s), ptr(x_t), ptr(mask_ids), ctx.mask_lt, ptr(dH), None, M, N, K, s)
-            if dz_t is not None:
-                call('xdr_dense_bwd_weight', ptr(dz_t), ptr(x_s), ptr(mask_ids), ctx.mask_lt, ptr(dH), None, M, N, K, s)
+
+        def lane_w():    # the towers' own weights (and biases)
+            if want[0] and dz_s is not None:
+                call('xdr_dense_bwd_weight', ptr(dz_s), ptr(x_s), None, 0, ptr(dWs), ptr(dbs), M, N, K, cur_stream())
+            if want[1] and dz_t is not None:
+                call('xdr_dense_bwd_weight', ptr(dz_t), ptr(x_t), None, 0, ptr(dWt), ptr(dbt), M, N, K, cur_stream())
+
+        def lane_h():    # the shared cross-stitch matrix: both products add into one destination
+            if want[2] and dz_s is not None:
+                call('xdr_dense_bwd_weight', ptr(dz_s), ptr(x_t), ptr(mask_ids), ctx.mask_lt, ptr(dH), None, M, N, K, cur_stream())
+            if want[2] and dz_t is not None:
+                call('xdr_dense_bwd_weight', ptr(dz_t), ptr(x_s), ptr(mask_ids), ctx.mask_lt, ptr(dH), None, M, N, K, cur_stream())
+
+        _run_lanes(x_s.device, [ln for ln in (lane_xs, lane_xt, lane_w, lane_h) if ln is not None])
         return d_xs, d_xt, dWs, dbs, dWt, dbt, dH, None, None, None, None
 
 

@@ -72,9 +72,10 @@ def test_engine_switch_changes_the_arithmetic_not_the_result():
     assert not torch.equal(y1, y0)
 
 
+@pytest.mark.parametrize('streams', [0, 4])
 @pytest.mark.parametrize('engine', [0, 1, 2])
 @pytest.mark.parametrize('M,N,K', [(32768, 64, 256), (4097, 32, 64), (333, 16, 32)])
-def test_cross_pair_node_equals_two_dense_nodes(engine, M, N, K):
+def test_cross_pair_node_equals_two_dense_nodes(engine, M, N, K, streams):
     """ops.cross_pair (both directions of a CoNet cross-stitch layer as one autograd node; the second input-gradient product
     accumulates into the first one's result -- ``xdr_dense_bwd_input(accumulate=1)`` -- and both dH products add into one
     destination) against two ops.dense nodes, on every engine setting.  CPU twin: tests/test_emu_tc5_dense.py."""
@@ -86,6 +87,7 @@ def test_cross_pair_node_equals_two_dense_nodes(engine, M, N, K):
     d_s, d_t = mk(M, N), mk(M, N)
     res = []
     prev = _lib._lib.xdr_set_dense_engine(engine)
+    prev_streams = ops.set_cross_streams(streams)    # (4: the node's independent launches on parallel streams)
     try:
         for pair in (True, False):
             x_s, x_t, Ws, bs, Wt, bt, H = [t.clone().requires_grad_(True) for t in base]
@@ -99,6 +101,7 @@ def test_cross_pair_node_equals_two_dense_nodes(engine, M, N, K):
             res.append([h_s.detach(), h_t.detach()] + [t.grad for t in (x_s, x_t, Ws, bs, Wt, bt, H)])
     finally:
         _lib._lib.xdr_set_dense_engine(prev)
+        ops.set_cross_streams(prev_streams)
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     for nm, a, b in zip(('x_s', 'x_t', 'Ws', 'bs', 'Wt', 'bt', 'H'), res[0][2:], res[1][2:]):
         scale = max(1e-6, float(b.abs().max()))   # (weight gradients are sums of atomics: order differs from run to run)

@@ -129,6 +129,52 @@ def test_graphed_step_equals_eager_step():
             torch.testing.assert_close(p.grad, ge[n].grad, rtol=1e-4, atol=1e-7, msg=lambda s: f'{n}: {s}')
 
 
+@pytest.mark.parametrize('streams', [0, 4])
+def test_graphed_conet_step_equals_eager_step(streams):
+    """CoNet's stacked BOTH step (ops.cross_pair on the tcgen05 engine, ops.frob_sum) captured as a CUDA graph against the eager
+    step -- also with the independent launches of every cross-stitch layer on parallel streams (``ops.set_cross_streams``:
+    forked and joined inside the autograd nodes, parallel branches of the captured graph)."""
+    from recbole_cdr_b200 import ops
+    from recbole_cdr_b200.data import Interaction
+    from recbole_cdr_b200.trainer import GraphedTrainStep
+    from recbole_cdr_b200.utils import get_model
+    from fake_data import make_batch
+    ds = FakeDataset(201, 300, 280, 1, 500, 450)
+    cfg = base_config(embedding_size=64, reg_weight=0.01, mlp_hidden_size=[64, 32, 16, 8])
+    torch.manual_seed(1)
+    model = get_model('CoNet')(cfg, ds).to('cuda')
+    assert model.stack_passes and model.dense_engine == 1
+
+    def batch(seed):
+        r = np.random.RandomState(seed)
+        b = make_batch(ds, 'source', 1024, r)
+        b.update(make_batch(ds, 'target', 1024, r))
+        return Interaction(b).to('cuda')
+
+    import copy
+    eager = copy.deepcopy(model)
+    prev = ops.set_cross_streams(streams)
+    try:
+        step = GraphedTrainStep(model, batch(0))
+        for seed in (1, 2, 3):
+            b = batch(seed)
+            step.zero_table_grads()
+            loss_g = step(b).clone()
+            ops.set_cross_streams(0)
+            eager.zero_grad(set_to_none=True)
+            loss_e = eager.calculate_loss(b)
+            loss_e.sum().backward()
+            ops.set_cross_streams(streams)
+            torch.cuda.synchronize()
+            torch.testing.assert_close(loss_g, loss_e.detach().sum(), rtol=1e-6, atol=0)
+            ge = dict(eager.named_parameters())
+            for n, p in model.named_parameters():
+                scale = max(1e-6, float(ge[n].grad.abs().max()))
+                torch.testing.assert_close(p.grad, ge[n].grad, rtol=1e-4, atol=2e-5 * scale, msg=lambda s: f'{n}: {s}')
+    finally:
+        ops.set_cross_streams(prev)
+
+
 def test_graphed_step_construction_leaves_model_and_optimizer_untouched():
     """The warm-up steps of GraphedTrainStep are real steps on the example batch; whatever they changed -- parameters, table
     gradients, optimizer state -- is put back, so the first replay is the first step of training."""

@@ -948,7 +948,8 @@ def run_model_step(args, dev, name):
         'data': 'synthetic',
         'config': {'workload': what % b, 'engine': engine, 'users_total': ds.num_total_user, 'items_total': ds.num_total_item,
                    'batch_per_gpu': b, 'l2': 'inputs larger than L2 (tables of 0.8 .. 7 GB, uniform random rows)',
-                   'parallelism': 'single GPU'},
+                   'parallelism': 'single GPU',
+                   'graph_lanes': {-1: 2, 0: 1, 1: 1}.get(_ops.CROSS_STREAMS, _ops.CROSS_STREAMS) if name == 'conet_5m' else 1},
         'timing': Timer.summary(ms_list),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                      'peak_source': peak_src, 'kernel': engine, 'units_per_launch': units, 'bytes_per_interaction': bytes_per,

@@ -401,31 +401,44 @@ def dense(X, W, bias=None, act=_lib.ACT_NONE, X2=None, W2=None, mask_ids=None, m
 
 
 # Independent launches of one autograd node on parallel streams (fork from the current stream, join back into it; inside a
-# CUDA-graph capture the lanes become parallel branches of the graph).  0 = off: every launch on the current stream.
-# Only LAUNCHES go to the side streams -- every tensor is allocated on the current stream before the fork and used after the
-# join, so the caching allocator's per-stream pools never see a cross-stream free.
-CROSS_STREAMS = int(_os.environ.get('XDR_CROSS_STREAMS', '0'))
+# CUDA-graph capture the lanes become parallel branches of the graph).  Only LAUNCHES go to the side streams -- every tensor is
+# allocated on the current stream before the fork and used after the join, so the caching allocator's per-stream pools never see
+# a cross-stream free.  -1 (default) = two lanes inside a CUDA-graph capture (trainer.GraphedTrainStep: CoNet's BOTH step at
+# BASELINE configs[2] 995 -> 900 us on a B200, profiles/r2_conet_stacked.md), none in eager steps (the fork / join events are
+# host work an eager step cannot hide); 0 = never; n > 1 = always n lanes.
+CROSS_STREAMS = int(_os.environ.get('XDR_CROSS_STREAMS', '-1'))
 _SIDE_STREAMS = {}
 
 
 def set_cross_streams(n: int) -> int:
-    """Number of streams ``cross_pair`` spreads its independent launches over (1 or 0: none); returns the previous setting."""
+    """Streams ``cross_pair`` spreads its independent launches over: -1 two inside a graph capture, else none; 0 / 1 none;
+    n > 1 always n.  Returns the previous setting."""
     global CROSS_STREAMS
-    prev, CROSS_STREAMS = CROSS_STREAMS, max(0, int(n))
+    prev, CROSS_STREAMS = CROSS_STREAMS, max(-1, int(n))
     return prev
 
 
+def side_streams(device, n: int):
+    """The cached side streams of ``device`` (created on first use; trainer.GraphedTrainStep asks for them before it starts a
+    capture so that no stream is created inside one)."""
+    sides = _SIDE_STREAMS.setdefault(_lib._device_key(device), [])
+    while len(sides) < n:
+        sides.append(torch.cuda.Stream(device=device))
+    return sides[:n]
+
+
 def _run_lanes(device, lanes):
-    """Runs the callables of ``lanes``: lane 0 on the current stream, the others on side streams when CROSS_STREAMS > 1."""
-    n = min(CROSS_STREAMS, len(lanes))
+    """Runs the callables of ``lanes``: lane 0 (mod n) on the current stream, the others on side streams."""
+    n = CROSS_STREAMS
+    if n < 0:
+        n = 2 if (device.type == 'cuda' and torch.cuda.is_current_stream_capturing()) else 0
+    n = min(n, len(lanes))
     if n <= 1 or device.type != 'cuda':
         for lane in lanes:
             lane()
         return
     main = torch.cuda.current_stream(device)
-    sides = _SIDE_STREAMS.setdefault(_lib._device_key(device), [])
-    while len(sides) < n - 1:
-        sides.append(torch.cuda.Stream(device=device))
+    sides = side_streams(device, n - 1)
     used = []
     for i, lane in enumerate(lanes):
         k = i % n

@@ -48,6 +48,9 @@ class GraphedTrainStep(object):
                            for p, st in optimizer.state.items()}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        dev = next(model.parameters()).device
+        if dev.type == 'cuda':   # streams that ops.cross_pair forks its independent launches onto inside the capture
+            ops.side_streams(dev, max(1, ops.CROSS_STREAMS - 1))
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self._zero_small()

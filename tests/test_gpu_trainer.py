@@ -129,11 +129,12 @@ def test_graphed_step_equals_eager_step():
             torch.testing.assert_close(p.grad, ge[n].grad, rtol=1e-4, atol=1e-7, msg=lambda s: f'{n}: {s}')
 
 
-@pytest.mark.parametrize('streams', [0, 4])
+@pytest.mark.parametrize('streams', [-1, 0, 4])
 def test_graphed_conet_step_equals_eager_step(streams):
     """CoNet's stacked BOTH step (ops.cross_pair on the tcgen05 engine, ops.frob_sum) captured as a CUDA graph against the eager
-    step -- also with the independent launches of every cross-stitch layer on parallel streams (``ops.set_cross_streams``:
-    forked and joined inside the autograd nodes, parallel branches of the captured graph)."""
+    step -- with the independent launches of every cross-stitch layer on parallel streams (``ops.set_cross_streams``: forked
+    and joined inside the autograd nodes, parallel branches of the captured graph; -1, the default: two lanes inside a capture,
+    none in eager steps), on one stream (0), and on four lanes everywhere (4)."""
     from recbole_cdr_b200 import ops
     from recbole_cdr_b200.data import Interaction
     from recbole_cdr_b200.trainer import GraphedTrainStep

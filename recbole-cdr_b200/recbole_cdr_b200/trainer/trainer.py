@@ -84,7 +84,7 @@ class FusedStepRunner:
                     # the kernel walks ids and labels with ONE step stride: give the label rows the stride of the id rows
                     'label': (lab[:, 0] if with_label else None),
                     'out8': torch.empty((K, 8), dtype=torch.float32, device=self.dev),
-                    'ready': ready, 'done': done, 'used': False, 'rec': None})
+                    'ready': ready, 'done': done, 'used': False, 'rec': None, 'src': None})
         b = self._bufs[self._turn % self.n_buffers]
         self._turn += 1
         return b
@@ -110,7 +110,9 @@ class FusedStepRunner:
                      buf['done'].cuda_event, main.cuda_stream)
             self.launches += 1
             buf['used'] = True
-            buf['rec'] = rec   # the pinned block stays referenced until this device buffer's next turn (its copy is raw CUDA)
+            # both pinned blocks stay referenced until this device buffer's next turn: their copies are raw CUDA calls that torch's
+            # caching host allocator does not know about (a block the caller drops right after run() must not be recycled mid-DMA)
+            buf['rec'], buf['src'] = rec, host_block
             return rec[:, 0]
         with torch.cuda.stream(self.copy_stream):
             if buf['used']:

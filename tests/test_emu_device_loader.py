@@ -57,7 +57,8 @@ def test_conet_trains_an_epoch_from_the_device_loader():
     with emu_util.patched_ops():
         torch.manual_seed(0)
         cfg = base_config(device='cpu', embedding_size=16, reg_weight=0.0, mlp_hidden_size=[16, 8], learner='adam',
-                          learning_rate=0.01, weight_decay=0.0, train_modes=['BOTH'], epoch_num=['4'], source_split=False)
+                          learning_rate=0.01, weight_decay=0.0, train_modes=['BOTH'], epoch_num=['4'], source_split=False,
+                          xdr_dense_engine=0)   # (loader / trainer logic: the fp32 tiles emulate 5x faster than tcgen05)
         model = CoNet(cfg, ds)
         trainer = CrossDomainTrainer(cfg, model)
         data = loaders(ds, True, False)

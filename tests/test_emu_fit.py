@@ -39,7 +39,7 @@ CASES = [
     ('EMCDR', True, 'users', dict(latent_factor_model='BPR', source_embedding_size=64, target_embedding_size=64, reg_weight=0.01,
                                   mapping_function='non_linear', mlp_hidden_size=[128]), ['SOURCE', 'TARGET', 'OVERLAP'], 2, None),
     ('CMF', False, 'both', dict(embedding_size=64, alpha=0.5, gamma=0.0, **{'lambda': 0.0}), ['BOTH'], 2, None),
-    ('CoNet', False, 'users', dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8]), ['BOTH'], 2, None),
+    ('CoNet', False, 'users', dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8], xdr_dense_engine=0), ['BOTH'], 2, None),
     ('CoNet', False, 'users', dict(embedding_size=32, reg_weight=0.01, mlp_hidden_size=[32, 16, 8], xdr_fused_conet=True),
      ['BOTH'], 2, None),
     ('DTCDR', False, 'both', dict(embedding_size=64, mlp_hidden_size=[32, 16], dropout_prob=0.0, base_model='NeuMF', alpha=0.5,

@@ -475,7 +475,6 @@ class CrossPair(torch.autograd.Function):
         if x_t.shape != x_s.shape or Ws.shape != (N, K) or Wt.shape != (N, K) or H.shape != (N, K):
             raise ValueError(f'cross_pair: x {tuple(x_s.shape)} / {tuple(x_t.shape)}, weights {tuple(Ws.shape)} / '
                              f'{tuple(Wt.shape)} / {tuple(H.shape)}')
-        s = cur_stream()
         h_s = torch.empty((M, N), dtype=torch.float32, device=x_s.device)
         h_t = torch.empty((M, N), dtype=torch.float32, device=x_s.device)
         with dense_engine(engine):

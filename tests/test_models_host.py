@@ -61,3 +61,36 @@ def test_dtcdr_dmf_is_out_of_scope():
     g = Golden('dtcdr_neumf')
     with pytest.raises(NotImplementedError):
         DTCDR(base_config(device='cpu', **dict(CASES['dtcdr_neumf'][1], base_model='DMF')), FakeDataset.from_golden(g))
+
+
+def test_conet_hot_path_switches(monkeypatch):
+    """CoNet's host-side choices: one stacked pass per BOTH step and the tcgen05 dense engine by default; config keys win over
+    the environment (``XDR_CONET_STACK``, ``XDR_DENSE_ENGINE``), the environment over the defaults."""
+    from recbole_cdr_b200.model.cross_domain_recommender.conet import CoNet
+    ds = FakeDataset(41, 30, 35, 1, 50, 60)
+    mk = lambda **kw: CoNet(base_config(device='cpu', embedding_size=16, reg_weight=0.0, mlp_hidden_size=[16, 8], **kw), ds)
+    monkeypatch.delenv('XDR_CONET_STACK', raising=False)
+    monkeypatch.delenv('XDR_DENSE_ENGINE', raising=False)
+    m = mk()
+    assert m.stack_passes and m.dense_engine == 1 and not m.use_fused_conet
+    m = mk(xdr_stack_passes=False, xdr_dense_engine=0)
+    assert not m.stack_passes and m.dense_engine == 0
+    monkeypatch.setenv('XDR_CONET_STACK', '0')
+    monkeypatch.setenv('XDR_DENSE_ENGINE', '2')
+    m = mk()
+    assert not m.stack_passes and m.dense_engine == 2
+    m = mk(xdr_stack_passes=True, xdr_dense_engine=1)
+    assert m.stack_passes and m.dense_engine == 1
+
+
+def test_cross_streams_setting_round_trip():
+    from recbole_cdr_b200 import ops
+    prev = ops.set_cross_streams(4)
+    try:
+        assert ops.set_cross_streams(-5) == 4      # clamped to -1 = "two lanes inside a graph capture, none in eager steps"
+        assert ops.set_cross_streams(0) == -1
+        ran = []
+        ops._run_lanes(torch.device('cpu'), [lambda: ran.append(0), lambda: ran.append(1), lambda: ran.append(2)])
+        assert ran == [0, 1, 2]                    # no CUDA device: every lane in order on the caller's stream
+    finally:
+        ops.set_cross_streams(prev)

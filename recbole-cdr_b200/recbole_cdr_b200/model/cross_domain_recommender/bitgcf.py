@@ -82,12 +82,22 @@ class BiTGCF(CrossDomainRecommender):
         if self.connect_way == 'concat':
             fs, ft = torch.cat(ls, 1), torch.cat(lt, 1)
         elif self.connect_way == 'mean':
-            fs, ft = torch.stack(ls, dim=1).mean(dim=1), torch.stack(lt, dim=1).mean(dim=1)
+            # mean over the layer outputs (bitgcf.py:195-198: stack + mean) as a running sum: stack + mean writes an
+            # [N, L + 1, D] copy forward and, backward, an expanded gradient plus one strided-to-contiguous copy per layer --
+            # 26 table-sized passes per domain at 3 layers where the running sum needs 13 (same value up to fp32 rounding)
+            fs, ft = self._layer_mean(ls), self._layer_mean(lt)
         else:
             raise ValueError(f'connect_way [{self.connect_way}] is not supported')
         su, si = torch.split(fs, [self.total_num_users, self.total_num_items])
         tu, ti = torch.split(ft, [self.total_num_users, self.total_num_items])
         return su, si, tu, ti
+
+    @staticmethod
+    def _layer_mean(layers):
+        acc = layers[0]
+        for e in layers[1:]:
+            acc = acc + e
+        return acc * (1.0 / len(layers))
 
     def calculate_loss(self, interaction):
         """bitgcf.py:207-250: per domain BCE(sigmoid(dot of propagated rows)) + reg_weight * EmbLoss(ego rows);

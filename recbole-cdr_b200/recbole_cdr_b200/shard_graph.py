@@ -217,7 +217,12 @@ class ShardedBiTGCF(object):
             lt.append(nt)
         if self.connect_way == 'concat':
             return torch.cat(ls, 1), torch.cat(lt, 1)
-        return torch.stack(ls, dim=1).mean(dim=1), torch.stack(lt, dim=1).mean(dim=1)
+        def layer_mean(layers):   # running sum instead of stack + mean: half the table-sized passes (see BiTGCF._layer_mean)
+            acc = layers[0]
+            for e in layers[1:]:
+                acc = acc + e
+            return acc * (1.0 / len(layers))
+        return layer_mean(ls), layer_mean(lt)
 
     def train_step(self, source_batch, target_batch):
         """``calculate_loss`` + ``backward`` (bitgcf.py:207-250) for this rank's batch: (user, item, label) per domain

@@ -661,7 +661,7 @@ __device__ __forceinline__ void init_bars(const Bars& B, int tasks, int ifree_co
 // =====================================================================================================================
 // STAGED kernel: loaders (gather -> score -> stash) and scatterers (norms -> gradients -> RED) are different warps
 // =====================================================================================================================
-// EARLY (opt-in, reg_weight == 0 only; not yet run on hardware): without the EmbLoss term the row gradients do not depend on
+// EARLY (opt-in, reg_weight == 0 only; parity-green on a B200, tests/test_gpu_engines.py): without the EmbLoss term the row gradients do not depend on
 // the batch-wide norms, so the scatterers do not wait for the step's norm exchange before they issue the REDs and free the
 // stage slot; they still wait for it before they free the id slot, which keeps the id / partial / norm rings in step (the
 // per-step loss is still the exchanged batch mean).
@@ -1074,7 +1074,7 @@ extern "C" {
 // the scatter side, [6] scatter issued.
 XDR_API void xdr_debug_set_steps_trace(void* buf) { g_trace = reinterpret_cast<unsigned long long*>(buf); }
 XDR_API void xdr_debug_force_register_kernel(int on) { g_force_regs = on; }
-// Opt-in until it has run on hardware: launches with reg_weight == 0 (CMF's yaml default lambda = gamma = 0, reg-free BPR)
+// Opt-in (validated on hardware; the default kernel stays the one every measurement was taken on): launches with reg_weight == 0 (CMF's yaml default lambda = gamma = 0, reg-free BPR)
 // scatter without waiting for the step's norm exchange (train_steps_staged_kernel<..., EARLY = true>).
 XDR_API void xdr_steps_set_early_scatter(int on) { g_early_scatter = on; }
 

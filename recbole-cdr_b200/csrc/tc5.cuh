@@ -9,9 +9,11 @@
 // Descriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version 1 [46,48) | layout [61,64) = 0.
 // Instruction descriptor: F32 accumulate (1 << 4) | TF32 A (2 << 7) | TF32 B (2 << 10) | a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29).
 //
-// STATUS: this is the repository's READING of the interface, written without GPU access.  scripts/ubench_tcgen05.cu is the
-// one-CTA hardware experiment that confirms (or corrects) the layout / descriptor reading; the CPU emulator (tests/emu)
-// models the same reading, so what the emulator tests prove is the logic AROUND the MMAs (pipelines, barriers, epilogues).
+// STATUS: written in round 1 without GPU access as the repository's READING of the interface; confirmed on a B200 in round 2 by
+// scripts/ubench_tcgen05.cu (profiles/r2_ubench_tcgen05.txt: kind::tf32 with both operands K-major and every kind::f16 major
+// combination PASS with LBO / SBO as read here; kind::tf32 does NOT take MN-major operands -- the kernels that need an MN-major
+// view use bf16 planes) and by the GPU parity tests of every kernel built on it.  The CPU emulator (tests/emu) models the same
+// reading; what its tests prove is the logic AROUND the MMAs (pipelines, barriers, epilogues).
 #pragma once
 #include "xdr_common.cuh"
 

@@ -700,7 +700,7 @@ def _steps_workspace(device, n_steps):
 def set_steps_early_scatter(on: bool):
     """Opt in to the early-scatter form of the persistent kernel for launches with ``reg_weight == 0`` (CMF's yaml default
     lambda = gamma = 0, reg-free BPR): the row gradients do not depend on the batch-wide EmbLoss norms then, so the scatter
-    warps do not wait for the step's norm exchange.  Results are the same; not yet run on hardware, hence opt-in."""
+    warps do not wait for the step's norm exchange.  Results are the same (tests/test_gpu_engines.py on a B200); opt-in."""
     _lib._lib.xdr_steps_set_early_scatter(1 if on else 0)
 
 
@@ -1089,7 +1089,8 @@ def full_sort_topk(user_vecs, item_tab, k, n_items=None, first_item=1, hist_ptr=
     The fused form of ``full_sort_predict`` (emcdr.py:208-233, cmf.py:107-112) + recbole's full-sort masking + ``topk``.
     ``hist_ptr`` ``[B + 1]`` / ``hist_ids``: int64 CSR of ascending item ids per user.  Returns ``(scores [B, k] fp32,
     ids [B, k] int64)``, score descending, ties by ascending id, padded with ``(-inf, -1)``.  ``engine``: ``'mma'``
-    (mma.sync row tiles) or ``'tc5'`` (tcgen05.mma with tensor-memory accumulators; dim <= 64; not yet run on hardware)."""
+    (mma.sync row tiles) or ``'tc5'`` (tcgen05.mma with tensor-memory accumulators; dim <= 64; on a B200 25 ms against 70 ms for ``'mma'`` at 4096 users x 1M
+    items, profiles/r2_call1_new_kernels.jsonl)."""
     with torch.no_grad():
         user_vecs = user_vecs.contiguous()
         _require_cuda_f32(user_vecs, 'user_vecs')

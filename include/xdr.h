@@ -127,8 +127,9 @@ XDR_API int xdr_point_bwd(const float* user_tab, const float* item_tab, int64_t 
  * fp32 accumulation in tensor memory) for M >= 128, N % 16 == 0 (16..128), K % 16 == 0 (16..256) and 16-byte aligned
  * operands, fp32 FMA otherwise; 2 = tcgen05 only for the calls it measured faster on a B200 (forward and input gradient of
  * wide layers: K >= 192 and N >= 64, i.e. CoNet's layer 0), fp32 FMA for the rest; 0 (default) = fp32 FMA for every shape --
- * on a B200 the two tie per call at the BASELINE model shapes (profiles/r2_dense_engines.jsonl), so tcgen05 is opt-in.
- * Returns the previous setting.                                                                                         */
+ * on a B200 the two tie per call at the BASELINE model shapes (profiles/r2_dense_engines.jsonl), so tcgen05 is opt-in at
+ * the library level; the drop-in CoNet class switches its own calls to engine 1, which wins at its 32768-row launches
+ * (profiles/r2_conet_stacked.md).  Returns the previous setting.                                                        */
 XDR_API int xdr_set_dense_engine(int engine);
 XDR_API int xdr_dense_fwd(const float* X, const float* W, const float* bias, const float* X2, const float* W2,
                   const int64_t* mask_ids, int64_t mask_lt, int act, float* Y, int64_t M, int N, int K,

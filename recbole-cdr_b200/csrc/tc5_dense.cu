@@ -365,8 +365,9 @@ __global__ void __launch_bounds__(kD5Threads) tc5_dense_bwd_weight_kernel(const 
 // calls it measured FASTER on a B200 (profiles/r2_dense_engines_fwd2_tiles.jsonl: forward and input gradient of wide layers --
 // CoNet's layer 0, 256(+256) -> 64: 47.4 vs 51.5 us and 18.7 vs 25.0 us; it loses or ties on narrow layers and on every weight
 // gradient), fp32 tiles for the rest.  Per call both engines are bound by the dependent chain stage -> product -> epilogue of
-// ONE 128-row tile per SM, not by the tensor pipe, so the validated tcgen05 engine stays opt-in until it is pipelined across
-// tiles.
+// ONE 128-row tile per SM, not by the tensor pipe, so the LIBRARY default stays 0 until the engine is pipelined across tiles.
+// Callers choose per call (ops.dense_engine): CoNet's stacked BOTH pass (32768-row launches) runs on engine 1 by default -- as
+// a whole step it measured 1005 us against 1060 (engine 2) and 1132 (engine 0), profiles/r2_conet_stacked.md.
 static int env_dense_engine() {   // XDR_DENSE_ENGINE=1|2 in the environment switches the engine on without a call (test sweeps)
   const char* e = getenv("XDR_DENSE_ENGINE");
   return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;

@@ -94,3 +94,60 @@ def test_cross_streams_setting_round_trip():
         assert ran == [0, 1, 2]                    # no CUDA device: every lane in order on the caller's stream
     finally:
         ops.set_cross_streams(prev)
+
+
+def test_run_lanes_forks_after_main_and_joins_every_side_stream(monkeypatch):
+    """ops._run_lanes with stand-in streams: every side stream first waits for the caller's stream (everything queued so far),
+    lanes i with i % n == k run on side stream k - 1 (k = 0: the caller's stream), and the caller's stream waits for every side
+    stream that was used before anything after the node can run -- the fork / join shape a CUDA-graph capture records."""
+    import contextlib
+    from recbole_cdr_b200 import ops
+    log = []
+
+    class FakeStream:
+        def __init__(self, name):
+            self.name = name
+
+        def wait_stream(self, other):
+            log.append(('wait', self.name, other.name))
+
+    main = FakeStream('main')
+    sides = [FakeStream(f'side{i}') for i in range(3)]
+    current = [main]
+
+    @contextlib.contextmanager
+    def fake_stream_ctx(st):
+        current.append(st)
+        try:
+            yield
+        finally:
+            current.pop()
+
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda device=None: current[-1])
+    monkeypatch.setattr(torch.cuda, 'stream', fake_stream_ctx)
+    monkeypatch.setattr(torch.cuda, 'is_current_stream_capturing', lambda: False)
+    monkeypatch.setattr(ops, 'side_streams', lambda device, n: sides[:n])
+    dev = torch.device('cuda', 0)
+    lanes = [(lambda i=i: log.append(('lane', i, current[-1].name))) for i in range(4)]
+
+    prev = ops.set_cross_streams(2)
+    try:
+        ops._run_lanes(dev, lanes)
+        assert log == [('wait', 'side0', 'main'), ('lane', 1, 'side0'), ('lane', 3, 'side0'), ('lane', 0, 'main'),
+                       ('lane', 2, 'main'), ('wait', 'main', 'side0')]
+        log.clear()
+        ops.set_cross_streams(4)
+        ops._run_lanes(dev, lanes[:3])           # fewer lanes than streams: one stream per lane
+        assert log == [('wait', 'side0', 'main'), ('lane', 1, 'side0'), ('wait', 'side1', 'main'), ('lane', 2, 'side1'),
+                       ('lane', 0, 'main'), ('wait', 'main', 'side0'), ('wait', 'main', 'side1')]
+        log.clear()
+        ops.set_cross_streams(-1)                # default: lanes only inside a capture
+        ops._run_lanes(dev, lanes)
+        assert [e for e in log if e[0] == 'wait'] == [] and [e[2] for e in log] == ['main'] * 4
+        log.clear()
+        monkeypatch.setattr(torch.cuda, 'is_current_stream_capturing', lambda: True)
+        ops._run_lanes(dev, lanes)
+        assert log[0] == ('wait', 'side0', 'main') and log[-1] == ('wait', 'main', 'side0')
+        assert sorted(e[1] for e in log if e[0] == 'lane' and e[2] == 'side0') == [1, 3]
+    finally:
+        ops.set_cross_streams(prev)

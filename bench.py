@@ -8,6 +8,8 @@ Workloads (config.workload):
              item-) triples per step, BPR + 0.01 EmbLoss, SOURCE phase.  Default at N = 1.
   emcdr_10m  configs[4] -- the same step on 10M x 10M tables, batch 8192 per GPU.  Default at N > 1 (tables row-sharded over
              the GPUs); at N = 1 it is measured as the `emcdr_10m` sub-object of the line (the denominator of the 8-GPU claim).
+  (the default N = 1 line also carries `model_steps`: the emcdr_map and conet_5m lines below, each measured by this script in a
+   child process after the main numbers are final)
   emcdr_map  the OVERLAP-phase mapping step (gather -> MLP 64-128-64 -> MSE -> backward -> scatter), b = 8192.
 A "step" is one pass of the hot path over one batch: gather + score + loss forward, row gradients, scatter-add into the
 embedding-gradient tables (optimizer excluded, as in the metric's definition).
@@ -709,6 +711,13 @@ def run_xdr(args):
             torch.cuda.empty_cache()
         except Exception as e:  # never lose the main line to the sub-run
             line['emcdr_10m'] = {'error': repr(e)[:200]}
+        # ---- the dense rows of the path, so that the default line carries them too: the OVERLAP-phase map step ("map" of the
+        # metric's name) and CoNet's BOTH step at BASELINE configs[2], each measured by THIS script in a child process (its own
+        # CUDA context: nothing of it can disturb the numbers above, which are final by now)
+        try:
+            line['model_steps'] = model_step_sublines()
+        except Exception as e:
+            line['model_steps'] = {'error': repr(e)[:200]}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             r = cpu_reference_rates(scale, B, 1, args.cpu_steps)
@@ -716,6 +725,30 @@ def run_xdr(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def model_step_sublines():
+    """`bench.py --workload emcdr_map` and `--workload conet_5m` as child processes; a summary of each line (or its error)."""
+    import subprocess
+    out = {}
+    for name, flags in (('emcdr_map', ['--steps', '20', '--warmup', '5']),
+                        ('conet_5m', ['--steps', '10', '--warmup', '3', '--repeats', '5'])):
+        cmd = [sys.executable, os.path.abspath(__file__), '--workload', name, '--no-cpu-baseline'] + flags
+        try:
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=150)
+            rows = [l for l in p.stdout.splitlines() if l.startswith('{')]
+            if p.returncode != 0 or not rows:
+                out[name] = {'error': ('rc=%d ' % p.returncode) + p.stderr[-300:]}
+                continue
+            d = json.loads(rows[-1])
+            out[name] = {'workload': d['config']['workload'], 'engine': d['config'].get('engine'), 'value': d['value'],
+                         'unit': d['unit'], 'ms_per_step': d['ms_per_step'], 'steps': d['steps'], 'timing': d.get('timing'),
+                         'roofline_frac': d['roofline']['frac'], 'bytes_per_interaction': d['roofline']['bytes_per_interaction'],
+                         'e2e': d.get('e2e'), 'gpu_launches': d.get('gpu_launches'), 'loss_mean': d.get('loss_mean'),
+                         'dtype': d.get('dtype'), 'command': 'python bench.py ' + ' '.join(cmd[2:])}
+        except Exception as e:   # a time-out or an unreadable line: the main line goes out without this row
+            out[name] = {'error': repr(e)[:300]}
+    return out
 
 
 def ncu_traffic(B, K, sharded, grad_mode):
